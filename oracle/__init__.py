@@ -1,0 +1,26 @@
+"""CPU oracle for the streaming voice-conversion hot path -- TEST INFRASTRUCTURE ONLY.
+
+This package is a plain torch-fp32 (CPU) restatement of the reference's algorithm for
+the three stages of `InferenceWrapper.process_one_chunk`
+(/root/reference/evaluations/infer_arvc.py:492-596):
+
+  E  content encoder   oracle/content_encoder.py
+  A  dual-AR decode    oracle/dual_ar.py
+  V  vocoder           oracle/vocoder.py
+  loop                 oracle/streaming.py
+
+Every function cites the reference file:line it follows.  Nothing in the product
+package (`streamvoiceanon_b200/`) imports this package: only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs do,
+and only as the checker / the timed CPU baseline.
+
+Pinning: the reference ships no tests and no golden vectors, so the
+oracle is pinned against outputs of the reference's own modules executed in the build
+container: `oracle/make_golden.py` imports /root/reference (through the import shims in
+`oracle/refshim/`), loads the same synthetic weights, runs the same inputs and writes
+`tests/golden/*.npz`; `tests/test_oracle_golden.py` checks the oracle against those
+fixtures on every CPU run.  The third-party FSQ arithmetic
+(`vector-quantize-pytorch==1.14.24`, reference requirements.txt:26) is not vendored as a
+package; it is pinned through the reference's own vendored twin
+(modules/bicodec_speaker_encoder/fsq/residual_fsq.py:269-336).
+"""

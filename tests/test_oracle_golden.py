@@ -1,0 +1,160 @@
+"""Pins the CPU oracle (oracle/) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py).  CPU only.  Integer outputs must match exactly; floating-point
+outputs to the tolerance written beside each check (both sides are fp32 on CPU, the
+only differences are operator fusion / summation order)."""
+import hashlib
+
+import numpy as np
+import torch
+
+from oracle import content_encoder as E
+from oracle import vocoder as V
+from oracle.dual_ar import DualAR
+from oracle.streaming import StreamOracle
+from streamvoiceanon_b200 import synth
+
+
+def _digest(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].contiguous().numpy().tobytes()[:4096])
+    return h.hexdigest()
+
+
+def test_synthetic_weights_are_reproducible(weights, gold):
+    d = gold("weights_digest")
+    assert _digest(weights["ar"]) == str(d["ar"])
+    assert _digest(weights["tok"]) == str(d["tok"])
+    assert _digest(weights["voc"]) == str(d["voc"])
+
+
+def test_mel_filterbank_matches_torchaudio():
+    import torchaudio.functional as AF
+    fb = AF.melscale_fbanks(n_freqs=1025, f_min=0.0, f_max=22050.0, n_mels=160, sample_rate=44100,
+                            norm="slaney", mel_scale="slaney")
+    assert torch.allclose(E.slaney_fbanks(), fb, atol=1e-9, rtol=1e-6)
+
+
+def test_encoder_40_frames(weights, gold):
+    g = gold("encoder_40f")
+    wav = synth.synth_audio_44k(int(g["audio_seed"]), 2.0)[: int(g["n_samples"])][None]
+    with torch.no_grad():
+        ids, flen = E.encode(wav, weights["tok"])
+        mel = E.log_mel(wav)
+    assert int(flen[0]) == 40
+    assert np.abs(mel[0, :, -8:].numpy() - g["mel_tail"]).max() < 1e-4
+    assert np.array_equal(ids.numpy(), g["ids"])          # bit-exact ids
+
+
+def test_encoder_causal_prefix(weights, gold):
+    """Prefix causality of encode() (SURVEY.md section 8a-E note i): tokens of x[:N] equal the
+    first N tokens of x."""
+    g = gold("encoder_40f")
+    wav = synth.synth_audio_44k(int(g["audio_seed"]), 2.0)[: 24 * 2048][None]
+    with torch.no_grad():
+        ids, _ = E.encode(wav, weights["tok"])
+    assert np.array_equal(ids.numpy()[0, 0], g["ids"][0, 0, :24])
+
+
+def test_encoder_streaming_window(weights, gold):
+    g = gold("encoder_window128")
+    live = int(g["live_frames"])
+    win = torch.zeros(1, 128 * 2048)
+    win[:, -live * 2048:] = synth.synth_audio_44k(int(g["audio_seed"]), 2.0)[: live * 2048]
+    with torch.no_grad():
+        ids, _ = E.encode(win, weights["tok"])
+    assert np.array_equal(ids.numpy(), g["ids"])
+
+
+def test_vocoder_20_frames(weights, gold):
+    g = gold("vocoder_20f")
+    codes = torch.from_numpy(g["codes"])
+    with torch.no_grad():
+        z = V.quantizer_decode(codes, weights["voc_folded"])
+        wave = V.head(z, weights["voc_folded"])
+    assert np.abs(z[0, :, -8:].numpy() - g["z_tail"]).max() < 1e-4
+    mse = float(((wave[0, 0].numpy() - g["wave"]) ** 2).mean())
+    assert mse < 1e-10, mse                                  # fp32 waveform MSE tolerance
+
+
+def test_ar_streaming_codes(weights, gold, tape):
+    g = gold("ar_stream")
+    ar = DualAR(weights["ar"], tape(int(g["tape_seed"])))
+    style, timbre = synth.synth_speaker(int(g["spk_seed"]))
+    src = torch.from_numpy(g["src_content"])
+    with torch.no_grad():
+        ar.set_delay(int(g["delay"]))
+        ar.prefill_prompt(torch.from_numpy(g["ref_content"]), torch.from_numpy(g["ref_audio"]), style, timbre)
+        ar.prefill_src_condition4delay(src[:, :2])
+        for i, t in enumerate(range(2, 16)):
+            codes, pos = ar.decode_one(src[:, t:t + 1])
+            assert np.array_equal(codes.numpy(), g["codes"][i]), (i, codes.T, g["codes"][i].T)
+            assert int(pos) == int(g["pos"][i])
+
+
+def test_ar_logits(weights, gold, tape):
+    g = gold("ar_logits")
+    s = gold("ar_stream")
+    ar = DualAR(weights["ar"], tape(int(s["tape_seed"])))
+    style, timbre = synth.synth_speaker(int(s["spk_seed"]))
+    src = torch.from_numpy(s["src_content"])
+    with torch.no_grad():
+        ar.set_delay(2)
+        ar.prefill_prompt(torch.from_numpy(s["ref_content"]), torch.from_numpy(s["ref_audio"]), style, timbre)
+        assert np.abs(ar.last_hidden.numpy() - g["prefill_hidden"]).max() < 2e-4
+        assert np.abs(ar.last_logits[0].numpy() - g["prefill_logits"]).max() < 2e-4
+        ar.prefill_src_condition4delay(src[:, :2])
+        codes, _ = ar.decode_one(src[:, 2:3])
+    assert np.abs(ar.last_hidden.numpy() - g["hidden"]).max() < 2e-4
+    assert np.abs(ar.last_logits[0].numpy() - g["slow_logits"]).max() < 2e-4
+    assert np.abs(torch.stack(ar.last_logits[1:]).numpy() - g["fast_logits"]).max() < 2e-4
+    assert np.array_equal(codes.numpy(), g["codes"])
+
+
+def test_ar_offline_generate(weights, gold, tape):
+    g = gold("ar_generate")
+    s = gold("ar_stream")
+    ar = DualAR(weights["ar"], tape(int(s["tape_seed"])))
+    style, timbre = synth.synth_speaker(int(s["spk_seed"]))
+    with torch.no_grad():
+        ar.set_delay(2)
+        out = ar.generate(torch.from_numpy(s["ref_content"]), torch.from_numpy(s["ref_audio"]),
+                          torch.from_numpy(s["src_content"])[:, :10], style, timbre)
+    assert np.array_equal(out.numpy(), g["codes"])
+
+
+def _run_stream(weights, g, tape):
+    so = StreamOracle(weights["ar"], weights["tok"], weights["voc_folded"], tape(int(g["tape_seed"])))
+    n_ref, n_chunks = int(g["n_ref"]), int(g["n_chunks"])
+    style, timbre = synth.synth_speaker(int(g["ref_seed"]))
+    ref_wave = synth.synth_audio_44k(int(g["ref_seed"]), 3.5)[: n_ref * 2048][None]
+    gen = torch.Generator().manual_seed(int(g["codes_seed"]))
+    ref_audio = torch.randint(0, 1000, (1, 8, n_ref), generator=gen).int()
+    with torch.no_grad():
+        ref_content = E.encode(ref_wave, weights["tok"])[0].squeeze(0)
+        assert np.array_equal(ref_content.numpy(), g["ref_content"])
+        so.prefill_prompt(ref_audio, ref_content, style, timbre, max_prompt_frames=256, delay=int(g["delay"]))
+        so.setup_stream_caches(int(g["encode_window_frames"]), int(g["decode_window_frames"]),
+                               int(g["max_seq_frames"]), int(g["buffer_frames"]), 1)
+        src = synth.synth_audio_44k(int(g["src_seed"]), 1.5)[: n_chunks * 2048].view(n_chunks, 2048)
+        waves = [so.process_one_chunk(src[i][None]) for i in range(n_chunks)]
+    return so, torch.cat(waves, dim=-1)
+
+
+def test_stream_reprompt_loop(weights, gold, tape):
+    """Whole loop, small windows, re-prompt (infer_arvc.py:547-564) firing every few frames."""
+    g = gold("stream_reprompt")
+    so, wave = _run_stream(weights, g, tape)
+    assert np.array_equal(so.src_content_codes.numpy(), g["src_content"])
+    assert np.array_equal(so.pred_codes.numpy(), g["pred_codes"])
+    assert float(((wave[0].numpy() - g["wave"]) ** 2).mean()) < 1e-10
+
+
+def test_stream_default_loop(weights, gold, tape):
+    """Whole loop at the CLI defaults (encode window 128, decode window 64)."""
+    g = gold("stream_default")
+    so, wave = _run_stream(weights, g, tape)
+    assert np.array_equal(so.src_content_codes.numpy(), g["src_content"])
+    assert np.array_equal(so.pred_codes.numpy(), g["pred_codes"])
+    assert float(((wave[0].numpy() - g["wave"]) ** 2).mean()) < 1e-10
