@@ -1,0 +1,134 @@
+/*
+ * svanon_b200 -- C ABI of the B200-native streaming voice-conversion hot path.
+ *
+ * Drop-in boundary for the per-chunk loop of Plachtaa/StreamVoiceAnon
+ * (`InferenceWrapper.process_one_chunk`, evaluations/infer_arvc.py:492-596).  The reference has no FFI: its
+ * "plugin API" is hydra `_target_` instantiation plus Python method calls on three model objects.  Each entry
+ * point below states the reference method it replaces (file:line, relative to the reference root); the Python
+ * shims in streamvoiceanon_b200/ bind them with ctypes and re-expose the reference's method names
+ * (INTEGRATION.md shows the binding a maintainer adds).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; `svanon_last_error()` (thread-local) explains.
+ *  - data pointers may be HOST or DEVICE memory (detected with cudaPointerGetAttributes).  Device pointers are
+ *    consumed / produced stream-ordered on `cuda_stream` (a cudaStream_t, NULL = legacy default stream) with no
+ *    host synchronisation; host pointers are copied in/out inside the call, and calls that write to host
+ *    memory return after the copy has completed.
+ *  - activations are fp32.  Shapes use the reference's names; [a][b] is row-major with b contiguous.
+ *  - one engine per process / GPU; the library may be called from any thread, one call at a time per engine.
+ */
+#ifndef SVANON_H
+#define SVANON_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svanon_engine svanon_engine;
+typedef struct svanon_stream svanon_stream;
+
+#define SVANON_MODEL_AR 0        /* modules.arvc_wrapper.ARVCWrapper            (dual_ar_delay_0_8.pth)           */
+#define SVANON_MODEL_TOKENIZER 1 /* firefly_encoder.FireflyArchitecture         (asr_s2s_bsq_8192_causal_...pth)  */
+#define SVANON_MODEL_VOCODER 2   /* firefly.FireflyArchitecture (decode path)   (firefly-gan-vq-fsq-...pth)       */
+
+const char* svanon_last_error(void);
+int64_t svanon_kernel_launches(void); /* kernels launched by this library so far (process-wide) */
+
+/* ---- engine + weights --------------------------------------------------------------------------------------
+ * Replaces model construction + `load_state_dict(strict=False)` (evaluations/infer_arvc.py:51-65,67-96,160-165).
+ * Tensors are passed one by one under their reference state-dict key, fp32.  The vocoder may be given in
+ * weight-norm form (`...parametrizations.weight.original0/1`); it is folded at finalize, which is what
+ * `remove_parametrizations()` (infer_arvc.py:94) does.  Three derived buffers must be supplied too, because the
+ * reference builds them with torch ops whose last-bit results the engine must share:
+ *   AR:        "decoder.model.freqs_cis" [2048][32][2], "decoder.model.fast_freqs_cis" [8][32][2]
+ *              (precompute_freqs_cis, dual_ar_stream.py:993-1001: bf16-rounded, widened to fp32)
+ *   tokenizer: "quantizer.pre_module.freqs_cis" [2048][32][2] (persistent buffer of the checkpoint),
+ *              "spec_transform.fb" [1025][160] (slaney mel filterbank, spectrogram.py:93-106)
+ */
+int svanon_engine_create(int device, svanon_engine** out);
+void svanon_engine_destroy(svanon_engine* e);
+int svanon_load_tensor(svanon_engine* e, int model, const char* name, const float* data, int rank,
+                       const int64_t* shape);
+int svanon_finalize_weights(svanon_engine* e, int model);
+
+/* ---- stage E: content tokenizer ---------------------------------------------------------------------------
+ * Replaces `FireflyArchitecture.encode(audios, audio_lengths)` (modules/vqgan/modules/firefly_encoder.py:553-566)
+ * for one full-length utterance or streaming window: log-mel -> ConvNeXt -> 2x down-sample -> windowed
+ * transformer -> 13-bit BSQ ids.  wave [n_samples] at 44.1 kHz; ids_out [svanon_enc_num_ids(n_samples)] int64. */
+int svanon_enc_num_ids(int64_t n_samples);
+int svanon_enc_encode(svanon_engine* e, const float* wave, int64_t n_samples, int64_t* ids_out, void* cuda_stream);
+
+/* ---- stage V: vocoder -------------------------------------------------------------------------------------
+ * `svanon_voc_quantizer_decode` replaces `DownsampleFiniteScalarQuantize.decode` (modules/vqgan/modules/fsq.py:
+ * 112-116): codes [8][T] int64 -> z [4T][512] (channels-LAST; the reference returns the transpose [512][4T]).
+ * `svanon_voc_head` replaces `HiFiGANGenerator.forward` (modules/vqgan/modules/firefly.py:280-293):
+ * z [L][512] -> wave [512 L].  `svanon_voc_decode` is `code2wav_fn` (evaluations/infer_arvc.py:173-176). */
+int svanon_voc_quantizer_decode(svanon_engine* e, const int64_t* codes, int T, float* z_out, void* cuda_stream);
+int svanon_voc_head(svanon_engine* e, const float* z, int L, float* wave_out, void* cuda_stream);
+int svanon_voc_decode(svanon_engine* e, const int64_t* codes, int T, float* wave_out, void* cuda_stream);
+
+/* ---- stage A: dual-AR decode ------------------------------------------------------------------------------
+ * A stream owns what the reference keeps inside one ARVCWrapper/DualARWrapper instance: the slow/fast KV
+ * caches (`setup_caches`, infer_arvc.py:55-59, dual_ar_stream.py:225-243,459-475), cached positions,
+ * `cached_new_audio_emb` and `cached_ref_emb` (dual_ar_stream.py:775-796,808-815,834-836). */
+int svanon_stream_create(svanon_engine* e, int max_seq_len, svanon_stream** out);
+void svanon_stream_destroy(svanon_stream* s);
+/* DualARWrapper.set_delay, dual_ar_stream.py:630-637 (0..8) */
+int svanon_ar_set_delay(svanon_stream* s, int delay);
+/* sampling: temperature/top_p defaults 0.7/0.7 (dual_ar_stream.py:1103-1104); seed drives the built-in
+ * counter-based Exp(1) generator used when no noise tape is passed */
+int svanon_ar_set_sampling(svanon_stream* s, float temperature, float top_p, uint64_t seed);
+/* ARVCWrapper.prefill_prompt, arvc_wrapper.py:100-112 -> dual_ar_stream.py:764-796.
+ * ref_content [T] int64, ref_audio [8][T] int32, style [192], timbre [32][128] */
+int svanon_ar_prefill_prompt(svanon_stream* s, const int64_t* ref_content, const int32_t* ref_audio, int T,
+                             const float* style, const float* timbre, void* cuda_stream);
+/* ARVCWrapper.prefill_src_condition4delay, arvc_wrapper.py:114-119 -> dual_ar_stream.py:798-815; n == delay */
+int svanon_ar_prefill_delay(svanon_stream* s, const int64_t* src_content, int n, void* cuda_stream);
+/* ARVCWrapper.decode_one, arvc_wrapper.py:121-126 -> dual_ar_stream.py:817-837 -> decode_one_token_ar :1168-1219.
+ * content_id: one int64.  noise: NULL or the Exp(1) tape of this step for the 8 codebook samplers, [8][1000]
+ * (slot 0, the discarded 8192-way token head, is never drawn).  codes_out [8] int32; *last_pos (host int) is the
+ * value the reference returns as `kv_pos[-1]`. */
+int svanon_ar_decode_one(svanon_stream* s, const int64_t* content_id, const float* noise, int32_t* codes_out,
+                         int32_t* last_pos, void* cuda_stream);
+/* the same step for n in {1,2,4} independent streams in ONE kernel launch (weights are read once).
+ * content_ids [n], noise NULL or [n][8][1000], codes_out [n][8] */
+int svanon_ar_decode_batch(svanon_stream* const* streams, int n, const int64_t* content_ids, const float* noise,
+                           int32_t* codes_out, void* cuda_stream);
+/* ARVCWrapper.generate (offline), arvc_wrapper.py:82-98 -> dual_ar_stream.py:698-762.
+ * ref_content [Tr], ref_audio [8][Tr] int32, src_content [Ts]; noise NULL or [Ts][8][1000]; codes_out [8][Ts] */
+int svanon_ar_generate(svanon_stream* s, const int64_t* ref_content, const int32_t* ref_audio, int Tr,
+                       const int64_t* src_content, int Ts, const float* style, const float* timbre,
+                       const float* noise, int32_t* codes_out, void* cuda_stream);
+int svanon_ar_position(const svanon_stream* s); /* next free sequence position */
+/* test hook: capture the logits of the next decode steps (slow 8192-way head, pre-norm hidden state, 8 fast
+ * heads) of stream 0 of each launch; read them back with svanon_ar_read_debug (host pointers, may be NULL) */
+int svanon_ar_debug_logits(svanon_engine* e, int enable);
+int svanon_ar_read_debug(svanon_engine* e, float* slow_logits /*[8192]*/, float* hidden /*[768]*/,
+                         float* fast_logits /*[8][1000]*/);
+
+/* ---- the per-chunk loop -----------------------------------------------------------------------------------
+ * `svanon_stream_set_prompt` = the tail of InferenceWrapper.prefill_prompt (evaluations/infer_arvc.py:468-489)
+ * after the setup-path encoders: keeps the prompt truncated to max_prompt_frames for window padding and
+ * re-prompting, sets the delay and prefills the KV cache with the full prompt.
+ * `svanon_stream_setup` = InferenceWrapper.setup_stream_caches (:443-460).
+ * `svanon_stream_process_chunk` = InferenceWrapper.process_one_chunk (:492-596): wave ring update, window
+ * re-encode (E), warm-up phases, `chunk` decode steps (A), re-prompt when pos//2 >= max_seq_frames, vocoder on
+ * the last decode_window_frames frames (V), tail select.  wave_chunk / wave_out [chunk*2048]; noise NULL or
+ * [chunk][8][1000]. */
+int svanon_stream_set_prompt(svanon_stream* s, const int64_t* ref_content, const int32_t* ref_audio, int T,
+                             const float* style, const float* timbre, int max_prompt_frames, int delay,
+                             void* cuda_stream);
+int svanon_stream_setup(svanon_stream* s, int encode_window_frames, int decode_window_frames, int max_seq_frames,
+                        int buffer_frames, int decode_chunk_frames);
+int svanon_stream_process_chunk(svanon_stream* s, const float* wave_chunk, int n_samples, const float* noise,
+                                float* wave_out, void* cuda_stream);
+/* copies of the loop's histories (host pointers): src_content_codes [<= cap] and pred_codes [8][n] (int64) */
+int svanon_stream_history(svanon_stream* s, int64_t* src_content, int* n_src, int64_t* pred_codes, int* n_pred,
+                          int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVANON_H */

@@ -1,0 +1,26 @@
+"""B200-native engine for the streaming voice-conversion hot path of Plachtaa/StreamVoiceAnon.
+
+Three reference-facing surfaces (same names / arguments as the reference's classes) over one C-ABI CUDA
+library (include/svanon.h, streamvoiceanon_b200/libsvanon_b200.so):
+
+    ARVCWrapper        <-> modules.arvc_wrapper.ARVCWrapper
+    ContentTokenizer   <-> modules.vqgan.modules.firefly_encoder.FireflyArchitecture   (encode)
+    Vocoder            <-> modules.vqgan.modules.firefly.FireflyArchitecture           (quantizer.decode, head)
+    StreamSession      <-> InferenceWrapper.process_one_chunk as one library call per chunk
+"""
+from . import synth  # noqa: F401
+
+__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "synth"]
+
+
+def __getattr__(name):
+    if name == "ARVCWrapper":
+        from .arvc_wrapper import ARVCWrapper
+        return ARVCWrapper
+    if name in ("ContentTokenizer", "Vocoder"):
+        from . import firefly
+        return getattr(firefly, name)
+    if name == "StreamSession":
+        from .streaming import StreamSession
+        return StreamSession
+    raise AttributeError(name)

@@ -1,0 +1,546 @@
+// C ABI (include/svanon.h): argument marshalling (host or device pointers), stream lifecycle and the
+// per-chunk loop.  All model work is in engine.cu / ar_decode.cu.
+#include "../../include/svanon.h"
+
+#include <algorithm>
+#include <mutex>
+
+#include "engine.hpp"
+
+using namespace svanon;
+
+struct svanon_engine {
+  Engine eng;
+  Workspace staging;      // host<->device staging of API arguments
+  std::mutex mu;
+};
+struct svanon_stream {
+  Stream st;
+  svanon_engine* owner = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  } catch (...) {
+    g_err = "unknown error";
+    return 1;
+  }
+}
+
+bool on_device(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Per-call argument staging.  Inputs in host memory are copied to the staging arena; outputs in host memory are
+// produced in the arena and copied back (followed by one stream synchronisation) when the scope ends.
+struct Args {
+  svanon_engine* h;
+  cudaStream_t st;
+  struct Out { void* host; void* dev; size_t bytes; };
+  std::vector<Out> outs;
+  Args(svanon_engine* h_, void* stream, size_t budget) : h(h_), st((cudaStream_t)stream) {
+    SV_CUDA(cudaSetDevice(h->eng.device));
+    h->staging.ensure(budget + (1u << 20));
+    h->staging.reset();
+  }
+  template <typename T>
+  const T* in(const T* p, size_t n) {
+    if (!p) return nullptr;
+    if (on_device(p)) return p;
+    T* d = (T*)h->staging.alloc_bytes(n * sizeof(T));
+    SV_CUDA(cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return d;
+  }
+  template <typename T>
+  T* out(T* p, size_t n) {
+    if (on_device(p)) return p;
+    T* d = (T*)h->staging.alloc_bytes(n * sizeof(T));
+    outs.push_back({(void*)p, (void*)d, n * sizeof(T)});
+    return d;
+  }
+  void finish() {
+    if (outs.empty()) return;
+    for (auto& o : outs) SV_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+    SV_CUDA(cudaStreamSynchronize(st));
+    outs.clear();
+  }
+};
+
+template <typename T>
+T* dmalloc(size_t n) {
+  T* p = nullptr;
+  SV_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return p;
+}
+
+void set_prompt_copy(Stream& s, const long long* ref_content, const int* ref_audio, int T, int keep, const float* style,
+                     const float* timbre, cudaStream_t st) {
+  // InferenceWrapper.prefill_prompt keeps `[:max_prompt_frames]` copies for window padding and re-prompting
+  // (infer_arvc.py:469-473)
+  if (s.ref_content_dev) cudaFree(s.ref_content_dev);
+  if (s.ref_audio_dev) cudaFree(s.ref_audio_dev);
+  s.ref_content_dev = dmalloc<long long>(keep);
+  s.ref_audio_dev = dmalloc<int>((size_t)8 * keep);
+  s.ref_frames = keep;
+  SV_CUDA(cudaMemcpyAsync(s.ref_content_dev, ref_content, (size_t)keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+  SV_CUDA(cudaMemcpy2DAsync(s.ref_audio_dev, (size_t)keep * sizeof(int), ref_audio, (size_t)T * sizeof(int),
+                            (size_t)keep * sizeof(int), 8, cudaMemcpyDeviceToDevice, st));
+  if (!s.style_dev) s.style_dev = dmalloc<float>(192);
+  if (!s.timbre_dev) s.timbre_dev = dmalloc<float>(32 * 128);
+  SV_CUDA(cudaMemcpyAsync(s.style_dev, style, 192 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SV_CUDA(cudaMemcpyAsync(s.timbre_dev, timbre, 32 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+void decode_frames(Stream& s, const long long* content_ids_dev, int n, const float* noise_dev, cudaStream_t st) {
+  Engine& e = *s.eng;
+  for (int i = 0; i < n; ++i) {
+    if (s.n_pred >= HIST_CAP) {     // keep the newest half (the reference keeps at most 2048 entries, :593-594)
+      const int keep = HIST_CAP / 2;
+      int* tmp = (int*)e.ws.base;   // workspace is free between stages
+      SV_CUDA(cudaMemcpy2DAsync(tmp, keep * sizeof(int), s.pred_hist + (s.n_pred - keep), HIST_CAP * sizeof(int),
+                                keep * sizeof(int), 8, cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpy2DAsync(s.pred_hist, HIST_CAP * sizeof(int), tmp, keep * sizeof(int), keep * sizeof(int), 8,
+                                cudaMemcpyDeviceToDevice, st));
+      s.n_pred = keep;
+    }
+    s.step_content_id = content_ids_dev + i;
+    s.step_cond_row = nullptr;
+    s.step_noise = noise_dev ? noise_dev + (size_t)i * 8 * AR_CB_SIZE : nullptr;
+    Stream* one = &s;
+    e.ar_decode_step(&one, 1, st);
+    launch_append_codes(s.codes_dev, s.pred_hist, HIST_CAP, s.n_pred, st);
+    s.n_pred += 1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* svanon_last_error(void) { return g_err.c_str(); }
+int64_t svanon_kernel_launches(void) { return g_kernel_launches; }
+
+int svanon_engine_create(int device, svanon_engine** out) {
+  return guarded([&] {
+    SV_CHECK(out, "null out pointer");
+    int count = 0;
+    SV_CUDA(cudaGetDeviceCount(&count));
+    SV_CHECK(device >= 0 && device < count, "no such CUDA device");
+    SV_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SV_CUDA(cudaGetDeviceProperties(&prop, device));
+    SV_CHECK(prop.major == 10, "svanon_b200 is built for sm_100a (B200) only");
+    auto* h = new svanon_engine();
+    h->eng.device = device;
+    h->eng.num_sms = prop.multiProcessorCount;
+    *out = h;
+  });
+}
+
+void svanon_engine_destroy(svanon_engine* e) { delete e; }
+
+int svanon_load_tensor(svanon_engine* e, int model, const char* name, const float* data, int rank, const int64_t* shape) {
+  return guarded([&] {
+    SV_CHECK(e && name && data && shape && rank >= 1 && rank <= 4, "bad arguments");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    long long shp[4];
+    for (int i = 0; i < rank; ++i) shp[i] = shape[i];
+    e->eng.load_tensor(model, name, data, rank, shp);
+  });
+}
+
+int svanon_finalize_weights(svanon_engine* e, int model) {
+  return guarded([&] {
+    SV_CHECK(e, "null engine");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    e->eng.finalize(model);
+    SV_CUDA(cudaDeviceSynchronize());
+  });
+}
+
+int svanon_enc_num_ids(int64_t n_samples) { return (int)(((n_samples / HOP) / 2) / 2); }
+
+int svanon_enc_encode(svanon_engine* e, const float* wave, int64_t n, int64_t* ids_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && wave && ids_out, "null argument");
+    Args a(e, stream, (size_t)n * 4 + 65536);
+    const float* w = a.in(wave, (size_t)n);
+    long long* ids = (long long*)a.out(ids_out, (size_t)svanon_enc_num_ids(n));
+    e->eng.enc_encode(w, n, ids, a.st);
+    a.finish();
+  });
+}
+
+int svanon_voc_quantizer_decode(svanon_engine* e, const int64_t* codes, int T, float* z_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && codes && z_out, "null argument");
+    Args a(e, stream, (size_t)T * (64 + 4 * 512 * 4));
+    const long long* c = (const long long*)a.in(codes, (size_t)8 * T);
+    float* z = a.out(z_out, (size_t)4 * T * 512);
+    e->eng.voc_quantizer_decode(c, T, T, z, a.st);
+    a.finish();
+  });
+}
+
+int svanon_voc_head(svanon_engine* e, const float* z, int L, float* wave_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && z && wave_out, "null argument");
+    Args a(e, stream, (size_t)L * 512 * 4 * 2);
+    const float* zd = a.in(z, (size_t)L * 512);
+    float* w = a.out(wave_out, (size_t)L * 512);
+    e->eng.voc_head(zd, L, w, a.st);
+    a.finish();
+  });
+}
+
+int svanon_voc_decode(svanon_engine* e, const int64_t* codes, int T, float* wave_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && codes && wave_out, "null argument");
+    Args a(e, stream, (size_t)T * (64 + 2048 * 4));
+    const long long* c = (const long long*)a.in(codes, (size_t)8 * T);
+    float* w = a.out(wave_out, (size_t)T * SAMPLES_PER_FRAME);
+    e->eng.voc_decode(c, T, T, w, a.st);
+    a.finish();
+  });
+}
+
+int svanon_stream_create(svanon_engine* e, int max_seq_len, svanon_stream** out) {
+  return guarded([&] {
+    SV_CHECK(e && out, "null argument");
+    SV_CHECK(max_seq_len >= 64 && max_seq_len <= AR_MAX_SEQ, "max_seq_len must be in [64, 2048]");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    auto* h = new svanon_stream();
+    h->owner = e;
+    Stream& s = h->st;
+    s.eng = &e->eng;
+    s.max_seq = (max_seq_len + 7) / 8 * 8;   // find_multiple(max_seq_len, 8), dual_ar_stream.py:232
+    const size_t kv = (size_t)AR_LAYERS * AR_HEADS * s.max_seq * HEAD_DIM;
+    const size_t fkv = (size_t)AR_FAST_LAYERS * AR_HEADS * AR_CODEBOOKS * HEAD_DIM;
+    s.kc = dmalloc<float>(kv); s.vc = dmalloc<float>(kv);
+    s.fkc = dmalloc<float>(fkv); s.fvc = dmalloc<float>(fkv);
+    SV_CUDA(cudaMemset(s.kc, 0, kv * 4)); SV_CUDA(cudaMemset(s.vc, 0, kv * 4));
+    SV_CUDA(cudaMemset(s.fkc, 0, fkv * 4)); SV_CUDA(cudaMemset(s.fvc, 0, fkv * 4));
+    s.x_audio = dmalloc<float>(AR_DIM);
+    s.ref_emb_tail = dmalloc<float>(AR_MAX_DELAY * AR_DIM);
+    s.spk_rows = dmalloc<float>(AR_SPK_TOKENS * AR_DIM);
+    s.codes_dev = dmalloc<int>(8);
+    s.content_id_dev = dmalloc<long long>(8);
+    s.noise_dev = dmalloc<float>((size_t)8 * 8 * AR_CB_SIZE);
+    s.src_hist = dmalloc<long long>(HIST_CAP);
+    s.pred_hist = dmalloc<int>((size_t)8 * HIST_CAP);
+    *out = h;
+  });
+}
+
+void svanon_stream_destroy(svanon_stream* s) { delete s; }
+
+int svanon_ar_set_delay(svanon_stream* s, int delay) {
+  return guarded([&] {
+    SV_CHECK(s, "null stream");
+    SV_CHECK(delay >= 0 && delay <= AR_MAX_DELAY, "delay must be in [0, 8]");
+    s->st.delay = delay;
+  });
+}
+
+int svanon_ar_set_sampling(svanon_stream* s, float temperature, float top_p, uint64_t seed) {
+  return guarded([&] {
+    SV_CHECK(s, "null stream");
+    s->st.temperature = temperature; s->st.top_p = top_p; s->st.seed = seed;
+  });
+}
+
+int svanon_ar_prefill_prompt(svanon_stream* s, const int64_t* ref_content, const int32_t* ref_audio, int T,
+                             const float* style, const float* timbre, void* stream) {
+  return guarded([&] {
+    SV_CHECK(s && ref_content && ref_audio && style && timbre, "null argument");
+    Args a(s->owner, stream, (size_t)T * 48 + 32768);
+    const long long* rc = (const long long*)a.in(ref_content, (size_t)T);
+    const int* ra = a.in(ref_audio, (size_t)8 * T);
+    const float* sv = a.in(style, 192);
+    const float* tl = a.in(timbre, 32 * 128);
+    s->st.eng->ar_prefill_prompt(s->st, rc, ra, T, sv, tl, a.st);
+    a.finish();
+  });
+}
+
+int svanon_ar_prefill_delay(svanon_stream* s, const int64_t* src_content, int n, void* stream) {
+  return guarded([&] {
+    SV_CHECK(s && src_content, "null argument");
+    Args a(s->owner, stream, 4096);
+    const long long* sc = (const long long*)a.in(src_content, (size_t)n);
+    s->st.eng->ar_prefill_delay(s->st, sc, n, a.st);
+    a.finish();
+  });
+}
+
+int svanon_ar_decode_batch(svanon_stream* const* streams, int n, const int64_t* content_ids, const float* noise,
+                           int32_t* codes_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(streams && n >= 1 && n <= AR_MAX_BATCH && content_ids && codes_out, "bad arguments");
+    svanon_engine* h = streams[0]->owner;
+    Args a(h, stream, (size_t)n * (8 * AR_CB_SIZE * 4 + 256));
+    const long long* ids = (const long long*)a.in(content_ids, (size_t)n);
+    const float* nz = a.in(noise, (size_t)n * 8 * AR_CB_SIZE);
+    int* out = a.out(codes_out, (size_t)n * 8);
+    Stream* ss[AR_MAX_BATCH];
+    for (int i = 0; i < n; ++i) {
+      SV_CHECK(streams[i] && streams[i]->owner == h, "streams must belong to one engine");
+      ss[i] = &streams[i]->st;
+      ss[i]->step_content_id = ids + i;
+      ss[i]->step_cond_row = nullptr;
+      ss[i]->step_noise = nz ? nz + (size_t)i * 8 * AR_CB_SIZE : nullptr;
+    }
+    h->eng.ar_decode_step(ss, n, a.st);
+    for (int i = 0; i < n; ++i)
+      SV_CUDA(cudaMemcpyAsync(out + i * 8, ss[i]->codes_dev, 8 * sizeof(int), cudaMemcpyDeviceToDevice, a.st));
+    a.finish();
+  });
+}
+
+int svanon_ar_decode_one(svanon_stream* s, const int64_t* content_id, const float* noise, int32_t* codes_out,
+                         int32_t* last_pos, void* stream) {
+  if (!s) { g_err = "null stream"; return 1; }
+  svanon_stream* one = s;
+  const int rc = svanon_ar_decode_batch(&one, 1, content_id, noise, codes_out, stream);
+  if (rc == 0 && last_pos) *last_pos = s->st.pos_next - 1;
+  return rc;
+}
+
+int svanon_ar_generate(svanon_stream* sh, const int64_t* ref_content, const int32_t* ref_audio, int Tr,
+                       const int64_t* src_content, int Ts, const float* style, const float* timbre, const float* noise,
+                       int32_t* codes_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(sh && ref_content && ref_audio && src_content && style && timbre && codes_out, "null argument");
+    Stream& s = sh->st;
+    Engine& e = *s.eng;
+    const int d = s.delay;
+    SV_CHECK(Tr >= 1 && Ts >= 1 && Ts >= d, "generate needs Tr >= 1 and Ts >= delay");
+    Args a(sh->owner, stream, (size_t)(Tr + Ts) * 64 + (size_t)Ts * 8 * AR_CB_SIZE * 4 + 65536);
+    const long long* rc = (const long long*)a.in(ref_content, (size_t)Tr);
+    const int* ra = a.in(ref_audio, (size_t)8 * Tr);
+    const long long* sc = (const long long*)a.in(src_content, (size_t)Ts);
+    const float* sv = a.in(style, 192);
+    const float* tl = a.in(timbre, 32 * 128);
+    const float* nz = a.in(noise, (size_t)Ts * 8 * AR_CB_SIZE);
+    int* out = a.out(codes_out, (size_t)8 * Ts);
+    cudaStream_t st = a.st;
+    // prefill sequence (dual_ar_stream.py:709-722): 33 spk rows, then (cond_t, audio'_t) for t < Tr+d with
+    // cond = [ref_cond, src_cond[:d]] and audio' = [wait4start[:d], embed(ref_audio)], then remaining[0].
+    const int n_pairs = Tr + d;
+    const int n_tok = AR_SPK_TOKENS + 2 * n_pairs + 1;
+    SV_CHECK(n_tok + 2 * (Ts - 1) <= s.max_seq, "utterance does not fit the KV cache (max_seq_len)");
+    e.ws.ensure(((size_t)(n_tok + 8) * 12000 + (1u << 20)) * sizeof(float));
+    e.ws.reset();
+    float* x = e.ws.alloc_f((long long)(n_tok + 2) * AR_DIM);
+    {
+      GemmParams p;
+      p.A = tl; p.W = e.ctx_w; p.C = x; p.bias = e.ctx_b; p.M = 32; p.N = AR_DIM; p.K = 128; p.lda = 128; p.ldc = AR_DIM;
+      launch_gemm(p, st);
+      GemmParams q;
+      q.A = sv; q.W = e.style_w; q.C = x + 32 * AR_DIM; q.bias = e.style_b; q.M = 1; q.N = AR_DIM; q.K = 192; q.lda = 192;
+      q.ldc = AR_DIM;
+      launch_gemm(q, st);
+    }
+    float* seq = x + AR_SPK_TOKENS * AR_DIM;
+    launch_gather_rows(e.ar.cond_emb, rc, seq, Tr, AR_DIM, 2 * AR_DIM, st);
+    if (d > 0) {
+      launch_gather_rows(e.ar.cond_emb, sc, seq + (long long)2 * Tr * AR_DIM, d, AR_DIM, 2 * AR_DIM, st);
+      launch_copy_rows(e.w4s, AR_DIM, seq + AR_DIM, 2 * AR_DIM, d, AR_DIM, st);
+    }
+    launch_embed_codes(e.ar.codebook_emb, ra, Tr, seq + (long long)(2 * d + 1) * AR_DIM, Tr, 2 * AR_DIM, st);
+    // all but the last two tokens through the multi-token path; the last two are a normal decode step
+    const int n_pre = n_tok - 2;
+    launch_copy_rows(seq + (long long)(2 * n_pairs - 1) * AR_DIM, AR_DIM, s.x_audio, AR_DIM, 1, AR_DIM, st);
+    e.ar_forward_tokens(s, x, n_pre, 0, st);
+    s.pos_next = n_pre;
+    for (int i = 0; i < Ts; ++i) {
+      // remaining = [src_cond[d:], wait4end[:d]]  (dual_ar_stream.py:716)
+      const int j = d + i;
+      if (j < Ts) { s.step_content_id = sc + j; s.step_cond_row = nullptr; }
+      else { s.step_content_id = nullptr; s.step_cond_row = e.w4e + (long long)(j - Ts) * AR_DIM; }
+      s.step_noise = nz ? nz + (size_t)i * 8 * AR_CB_SIZE : nullptr;
+      Stream* one = &s;
+      e.ar_decode_step(&one, 1, st);
+      SV_CUDA(cudaMemcpy2DAsync(out + i, (size_t)Ts * sizeof(int), s.codes_dev, sizeof(int), sizeof(int), 8,
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    a.finish();
+  });
+}
+
+int svanon_ar_position(const svanon_stream* s) { return s ? s->st.pos_next : -1; }
+
+int svanon_ar_debug_logits(svanon_engine* e, int enable) {
+  return guarded([&] {
+    SV_CHECK(e, "null engine");
+    e->eng.debug_logits = enable != 0;
+  });
+}
+
+int svanon_ar_read_debug(svanon_engine* e, float* slow_logits, float* hidden, float* fast_logits) {
+  return guarded([&] {
+    SV_CHECK(e && e->eng.finalized[MODEL_AR], "AR weights not finalized");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    SV_CUDA(cudaDeviceSynchronize());
+    if (slow_logits) SV_CUDA(cudaMemcpy(slow_logits, e->eng.dbg_slow_logits, AR_VOCAB * 4, cudaMemcpyDeviceToHost));
+    if (hidden) SV_CUDA(cudaMemcpy(hidden, e->eng.dbg_hidden, AR_DIM * 4, cudaMemcpyDeviceToHost));
+    if (fast_logits) SV_CUDA(cudaMemcpy(fast_logits, e->eng.dbg_fast_logits, 8 * AR_CB_SIZE * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+// ----------------------------------------------------------------------------------------------- per-chunk loop
+int svanon_stream_set_prompt(svanon_stream* sh, const int64_t* ref_content, const int32_t* ref_audio, int T,
+                             const float* style, const float* timbre, int max_prompt_frames, int delay, void* stream) {
+  return guarded([&] {
+    SV_CHECK(sh && ref_content && ref_audio && style && timbre, "null argument");
+    SV_CHECK(delay >= 0 && delay <= AR_MAX_DELAY, "delay must be in [0, 8]");
+    Stream& s = sh->st;
+    Args a(sh->owner, stream, (size_t)T * 48 + 32768);
+    const long long* rc = (const long long*)a.in(ref_content, (size_t)T);
+    const int* ra = a.in(ref_audio, (size_t)8 * T);
+    const float* sv = a.in(style, 192);
+    const float* tl = a.in(timbre, 32 * 128);
+    s.delay = delay;
+    set_prompt_copy(s, rc, ra, T, std::min(T, max_prompt_frames), sv, tl, a.st);
+    s.eng->ar_prefill_prompt(s, rc, ra, T, sv, tl, a.st);   // NOTE: the reference prefills the UNtruncated prompt
+    a.finish();
+  });
+}
+
+int svanon_stream_setup(svanon_stream* sh, int enc_win, int dec_win, int max_seq_frames, int buffer_frames, int chunk) {
+  return guarded([&] {
+    SV_CHECK(sh, "null stream");
+    SV_CHECK(enc_win >= 1 && enc_win <= 2048 && dec_win >= 1 && dec_win <= 1024, "window sizes out of range");
+    SV_CHECK(chunk >= 1 && chunk <= 8 && chunk <= enc_win && chunk <= dec_win, "decode_chunk_frames must be in [1, 8]");
+    SV_CHECK(buffer_frames >= 0 && buffer_frames < HIST_CAP / 2, "buffer_frames out of range");
+    Stream& s = sh->st;
+    SV_CUDA(cudaSetDevice(s.eng->device));
+    SV_CUDA(cudaDeviceSynchronize());
+    for (void* p : {(void*)s.wave_ring, (void*)s.wave_ring_tmp, (void*)s.ids_win_dev, (void*)s.codes_win_dev, (void*)s.wave_win_dev})
+      if (p) cudaFree(p);
+    s.enc_win = enc_win; s.dec_win = dec_win; s.max_seq_frames = max_seq_frames; s.buffer_frames = buffer_frames;
+    s.chunk = chunk;
+    const size_t nw = (size_t)enc_win * SAMPLES_PER_FRAME;
+    s.wave_ring = dmalloc<float>(nw);
+    s.wave_ring_tmp = dmalloc<float>(nw);
+    SV_CUDA(cudaMemset(s.wave_ring, 0, nw * 4));
+    s.ids_win_dev = dmalloc<long long>(enc_win);
+    s.codes_win_dev = dmalloc<long long>((size_t)8 * dec_win);
+    s.wave_win_dev = dmalloc<float>((size_t)dec_win * SAMPLES_PER_FRAME);
+    s.n_src = 0; s.n_pred = 0; s.delay_prefilled = false;
+  });
+}
+
+int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int n, const float* noise, float* wave_out,
+                                void* stream) {
+  return guarded([&] {
+    SV_CHECK(sh && wave_chunk && wave_out, "null argument");
+    Stream& s = sh->st;
+    Engine& e = *s.eng;
+    SV_CHECK(s.enc_win > 0, "svanon_stream_setup has not been called");
+    SV_CHECK(s.ref_frames > 0, "svanon_stream_set_prompt has not been called");
+    SV_CHECK(n == s.chunk * SAMPLES_PER_FRAME, "chunk must hold decode_chunk_frames * 2048 samples");
+    Args a(sh->owner, stream, (size_t)n * 8 + (size_t)s.chunk * 8 * AR_CB_SIZE * 4 +
+                                  (size_t)(s.ref_frames + s.buffer_frames) * 64 + 65536);
+    cudaStream_t st = a.st;
+    const float* wc = a.in(wave_chunk, (size_t)n);
+    const float* nz = a.in(noise, (size_t)s.chunk * 8 * AR_CB_SIZE);
+    float* out = a.out(wave_out, (size_t)n);
+    const size_t nw = (size_t)s.enc_win * SAMPLES_PER_FRAME;
+    // 1. wave ring: shift left by n, append the chunk (infer_arvc.py:495-496)
+    SV_CUDA(cudaMemcpyAsync(s.wave_ring_tmp, s.wave_ring + n, (nw - n) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SV_CUDA(cudaMemcpyAsync(s.wave_ring_tmp + (nw - n), wc, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    std::swap(s.wave_ring, s.wave_ring_tmp);
+    // 2. E: re-encode the whole window, keep the last `chunk` ids (:505-518)
+    e.enc_encode(s.wave_ring, (long long)nw, s.ids_win_dev, st);
+    if (s.n_src + s.chunk > HIST_CAP) {
+      const int keep = HIST_CAP / 2;
+      long long* tmp = (long long*)e.ws.base;
+      SV_CUDA(cudaMemcpyAsync(tmp, s.src_hist + (s.n_src - keep), keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpyAsync(s.src_hist, tmp, keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+      s.n_src = keep;
+    }
+    SV_CUDA(cudaMemcpyAsync(s.src_hist + s.n_src, s.ids_win_dev + (s.enc_win - s.chunk), s.chunk * sizeof(long long),
+                            cudaMemcpyDeviceToDevice, st));
+    s.n_src += s.chunk;
+    // 3./4. warm-up phases (:519-525)
+    bool silent = false;
+    if (s.n_src < s.delay) {
+      silent = true;
+    } else if (!s.delay_prefilled && s.delay != 0) {
+      e.ar_prefill_delay(s, s.src_hist + (s.n_src - s.delay), s.delay, st);
+      silent = true;
+    }
+    if (silent) {
+      SV_CUDA(cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), st));
+      a.finish();
+      return;
+    }
+    // 5. A: `chunk` decode steps (:534-538)
+    decode_frames(s, s.src_hist + (s.n_src - s.chunk), s.chunk, nz, st);
+    const int current_pos = s.pos_next - 1;
+    // 6. re-prompt (:547-564)
+    if (current_pos / 2 >= s.max_seq_frames) {
+      const int buf = std::min(s.buffer_frames, s.n_pred);
+      const int Tn = s.ref_frames + buf;
+      SV_CHECK(s.n_src - s.delay >= buf, "not enough source history for re-prompting");
+      int* ext_audio = (int*)a.h->staging.alloc_bytes((size_t)8 * Tn * sizeof(int));
+      long long* ext_content = (long long*)a.h->staging.alloc_bytes((size_t)Tn * sizeof(long long));
+      launch_concat_cols(s.ref_audio_dev, s.ref_frames, s.ref_frames, s.pred_hist + (s.n_pred - buf), HIST_CAP, buf,
+                         ext_audio, Tn, 8, false, st);
+      SV_CUDA(cudaMemcpyAsync(ext_content, s.ref_content_dev, (size_t)s.ref_frames * sizeof(long long),
+                              cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpyAsync(ext_content + s.ref_frames, s.src_hist + (s.n_src - buf - s.delay),
+                              (size_t)buf * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+      e.ar_prefill_prompt(s, ext_content, ext_audio, Tn, s.style_dev, s.timbre_dev, st);
+      if (s.delay > 0) e.ar_prefill_delay(s, s.src_hist + (s.n_src - s.delay), s.delay, st);
+    }
+    // 7. V on the last decode_window_frames frames, left-padded with the prompt's tail (:567-583)
+    const int have = std::min(s.n_pred, s.dec_win);
+    const int pad = s.dec_win - have;
+    SV_CHECK(pad <= s.ref_frames, "prompt shorter than the vocoder window padding needs (the reference fails here too)");
+    launch_concat_cols(s.ref_audio_dev + (s.ref_frames - pad), s.ref_frames, pad, s.pred_hist + (s.n_pred - have),
+                       HIST_CAP, have, s.codes_win_dev, s.dec_win, 8, true, st);
+    e.voc_decode(s.codes_win_dev, s.dec_win, s.dec_win, s.wave_win_dev, st);
+    // 8. tail select (:596)
+    SV_CUDA(cudaMemcpyAsync(out, s.wave_win_dev + ((size_t)s.dec_win * SAMPLES_PER_FRAME - n), (size_t)n * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+    a.finish();
+  });
+}
+
+int svanon_stream_history(svanon_stream* sh, int64_t* src_content, int* n_src, int64_t* pred_codes, int* n_pred, int cap) {
+  return guarded([&] {
+    SV_CHECK(sh && n_src && n_pred, "null argument");
+    Stream& s = sh->st;
+    SV_CUDA(cudaSetDevice(s.eng->device));
+    SV_CUDA(cudaDeviceSynchronize());
+    const int ns = std::min(s.n_src, cap), np = std::min(s.n_pred, cap);
+    *n_src = ns; *n_pred = np;
+    if (src_content && ns > 0)
+      SV_CUDA(cudaMemcpy(src_content, s.src_hist + (s.n_src - ns), (size_t)ns * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (pred_codes && np > 0) {
+      std::vector<int> tmp((size_t)8 * np);
+      SV_CUDA(cudaMemcpy2D(tmp.data(), (size_t)np * sizeof(int), s.pred_hist + (s.n_pred - np), HIST_CAP * sizeof(int),
+                           (size_t)np * sizeof(int), 8, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < tmp.size(); ++i) pred_codes[i] = tmp[i];
+    }
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Multi-token causal (optionally window-limited) attention in fp32, one warp per query row.
+// Used by the content encoder's WindowLimitedTransformer (windowed_transformer.py:163-194, mask :291-303)
+// and by the AR prompt prefill (dual_ar_stream.py:895-936 with the causal_mask rows of :333).
+// Keys/values are staged through shared memory in tiles of 32 keys shared by the 8 queries of a CTA;
+// softmax is the usual running max / running sum formulation in fp32.
+#include "common.cuh"
+
+namespace svanon {
+
+namespace {
+
+constexpr int QW = 8;        // queries (warps) per CTA
+constexpr int KT = 32;       // keys per tile
+
+__global__ void __launch_bounds__(QW * 32)
+attention_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
+                 long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
+                 int qpos0, int window) {
+  __shared__ float Ks[KT][HEAD_DIM + 1];
+  __shared__ float Vs[KT][HEAD_DIM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int qi0 = blockIdx.x * QW;
+  const int qi = qi0 + warp;
+  const bool active = qi < nq;
+  const int pos = qpos0 + qi;
+  const int lo = max(0, pos - window + 1);
+
+  float qr[HEAD_DIM];
+  if (active) {
+    const float* qp = q + (long long)qi * q_ld + h * HEAD_DIM;
+#pragma unroll
+    for (int d = 0; d < HEAD_DIM; ++d) qr[d] = __ldg(qp + d) * 0.125f;   // 1/sqrt(64)
+  } else {
+#pragma unroll
+    for (int d = 0; d < HEAD_DIM; ++d) qr[d] = 0.f;
+  }
+
+  // key range needed by this CTA
+  const int last_q = min(qi0 + QW, nq) - 1;
+  const int k_hi = qpos0 + last_q;                         // inclusive
+  const int k_lo = max(0, qpos0 + qi0 - window + 1);
+  const float* kb = k + (long long)h * kv_head_stride;
+  const float* vb = v + (long long)h * kv_head_stride;
+
+  float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;
+  for (int kt = (k_lo / KT) * KT; kt <= k_hi; kt += KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KT * HEAD_DIM; i += QW * 32) {
+      const int key = i / HEAD_DIM, d = i % HEAD_DIM;
+      const int kp = kt + key;
+      float kv = 0.f, vv = 0.f;
+      if (kp <= k_hi) {
+        kv = __ldg(kb + (long long)kp * kv_row_stride + d);
+        vv = __ldg(vb + (long long)kp * kv_row_stride + d);
+      }
+      Ks[key][d] = kv;
+      Vs[key][d] = vv;
+    }
+    __syncthreads();
+    if (!active) continue;
+    const int kp = kt + lane;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < HEAD_DIM; ++d) s = fmaf(qr[d], Ks[lane][d], s);
+    const bool valid = (kp >= lo) && (kp <= pos);
+    s = valid ? s : -INFINITY;
+    float tmax = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (tmax == -INFINITY) continue;                      // whole tile masked for this query (warp-uniform)
+    const float m_new = fmaxf(m, tmax);
+    const float corr = expf(m - m_new);                   // m = -inf on the first tile -> 0
+    const float p = valid ? expf(s - m_new) : 0.f;
+    float psum = p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+    l = l * corr + psum;
+    acc0 *= corr;
+    acc1 *= corr;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      acc0 = fmaf(pj, Vs[j][lane], acc0);
+      acc1 = fmaf(pj, Vs[j][lane + 32], acc1);
+    }
+    m = m_new;
+  }
+  if (active) {
+    float* op = out + (long long)qi * out_ld + h * HEAD_DIM;
+    const float inv = 1.f / l;
+    op[lane] = acc0 * inv;
+    op[lane + 32] = acc1 * inv;
+  }
+}
+
+__global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float* __restrict__ kc, float* __restrict__ vc,
+                                 int max_seq, int pos0) {
+  const int row = blockIdx.x;
+  const int D = heads * HEAD_DIM;
+  const float* kr = qkv + (long long)row * 3 * D + D;
+  const float* vr = kr + D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const int h = c / HEAD_DIM, d = c % HEAD_DIM;
+    const long long dst = ((long long)h * max_seq + pos0 + row) * HEAD_DIM + d;
+    kc[dst] = kr[c];
+    vc[dst] = vr[c];
+  }
+}
+
+}  // namespace
+
+void launch_attention(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
+                      long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
+                      cudaStream_t st) {
+  if (nq <= 0) return;
+  dim3 grid((nq + QW - 1) / QW, heads);
+  attention_kernel<<<grid, QW * 32, 0, st>>>(q, q_ld, k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0,
+                                             window);
+  SV_LAUNCHED();
+}
+
+void launch_kv_append(const float* qkv, int rows, int heads, float* kc, float* vc, int max_seq, int pos0,
+                      cudaStream_t st) {
+  if (rows <= 0) return;
+  kv_append_kernel<<<rows, 256, 0, st>>>(qkv, heads, kc, vc, max_seq, pos0);
+  SV_LAUNCHED();
+}
+
+}  // namespace svanon

@@ -1,0 +1,141 @@
+// Shared declarations for the svanon_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace svanon {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define SV_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      throw ::svanon::Error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + \
+                            __FILE__ + ":" + std::to_string(__LINE__));                    \
+  } while (0)
+
+#define SV_CHECK(cond, msg)                                                            \
+  do {                                                                                 \
+    if (!(cond))                                                                       \
+      throw ::svanon::Error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" + \
+                            std::to_string(__LINE__));                                 \
+  } while (0)
+
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+extern long long g_kernel_launches;
+#define SV_LAUNCHED()                 \
+  do {                                \
+    ++::svanon::g_kernel_launches;    \
+    SV_CUDA(cudaGetLastError());      \
+  } while (0)
+
+// ---------------------------------------------------------------- model constants
+// configs/hydra_arcs/vc/firefly_arvc_bsq_8192_delay0_8.yaml
+constexpr int AR_DIM = 768;
+constexpr int AR_HEADS = 12;
+constexpr int HEAD_DIM = 64;
+constexpr int AR_INTER = 2304;
+constexpr int AR_LAYERS = 12;
+constexpr int AR_FAST_LAYERS = 4;
+constexpr int AR_CODEBOOKS = 8;
+constexpr int AR_CB_SIZE = 1000;
+constexpr int AR_VOCAB = 8192;
+constexpr int AR_MAX_SEQ = 2048;
+constexpr int AR_SPK_TOKENS = 33;   // 32 timbre tokens + 1 style token (arvc_wrapper.py:108-109)
+constexpr int AR_MAX_DELAY = 8;
+constexpr float AR_NORM_EPS = 1e-5f;
+// configs/hydra_arcs/speech_tokenizers/causal-encoder-lfq-8192.yaml
+constexpr int N_FFT = 2048;
+constexpr int HOP = 512;
+constexpr int N_FREQ = 1025;
+constexpr int N_FREQ_PAD = 1040;    // K of the mel GEMM, padded to a multiple of 16
+constexpr int N_MELS = 160;
+constexpr int ENC_DIM = 512;
+constexpr int ENC_HEADS = 8;
+constexpr int ENC_INTER = 1536;
+constexpr int ENC_LAYERS = 8;
+constexpr int ENC_WINDOW = 512;
+constexpr int BSQ_BITS = 13;
+constexpr int SAMPLES_PER_FRAME = 2048;
+
+// ---------------------------------------------------------------- generic GEMM
+// C[m, n] (op)= epilogue( sum_t sum_k pro(A[(m * a_row_step + tap_off[t]) * lda + k]) * W[t][n][k] )
+// A rows may overlap (lda < K) and may start before the buffer's row 0 (history / zero margin rows).
+enum Prologue : int { PRO_NONE = 0, PRO_SILU = 1 };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LOGCLAMP = 2 };
+
+constexpr int MAX_TAPS = 11;
+
+struct GemmParams {
+  const float* A = nullptr;
+  const float* W = nullptr;        // [taps][N][K]
+  float* C = nullptr;
+  const float* bias = nullptr;     // [N] or null
+  const float* gamma = nullptr;    // [N] or null: y *= gamma[n] (after activation)
+  const float* residual = nullptr; // [M][ldr] or null: y += residual
+  int M = 0, N = 0, K = 0;
+  long long lda = 0, ldc = 0, ldr = 0;
+  int a_row_step = 1;
+  int taps = 1;
+  int tap_off[MAX_TAPS] = {0};     // row offset (in A rows) of each tap
+  int prologue = PRO_NONE;
+  int act = ACT_NONE;
+  float out_scale = 1.f;           // y *= out_scale (applied last, before accumulate)
+  int accumulate = 0;              // C += y instead of C = y
+};
+
+// up to 3 independent problems of identical shape run as blockIdx.z
+void launch_gemm(const GemmParams* p, int count, cudaStream_t st);
+inline void launch_gemm(const GemmParams& p, cudaStream_t st) { launch_gemm(&p, 1, st); }
+
+// ---------------------------------------------------------------- misc kernels (kernels_misc.cu)
+void launch_layernorm(const float* x, float* y, const float* w, const float* b, int rows, int C, float eps,
+                      cudaStream_t st);
+// depthwise causal conv k=7 (rows before 0 are read from the buffer margin) + LayerNorm over C, channels-last
+void launch_dwconv7_ln(const float* x, float* y, const float* dw_w /*[7][C]*/, const float* dw_b, const float* ln_w,
+                       const float* ln_b, int rows, int C, float eps, cudaStream_t st);
+void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st);
+// interleaved-pair RoPE on q and k inside a fused [rows, 3*H*64] qkv buffer; table [pos][32][2] (bf16-rounded fp32)
+void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos0, cudaStream_t st);
+void launch_silu_mul(const float* h13 /*[rows][2*I]*/, float* out /*[rows][I]*/, int rows, int I, cudaStream_t st);
+void launch_magnitude(const float* spec /*[T][ld_in] re|im*/, float* mag /*[T][N_FREQ_PAD]*/, int T, int ld_in,
+                      cudaStream_t st);
+void launch_bsq(const float* z /*[T][512]*/, const float* w /*[13][512]*/, const float* b, long long* ids, int T,
+                cudaStream_t st);
+void launch_fsq_lookup(const long long* codes /*[8][T] (stride ld)*/, long long ld, const float* w /*[8][64][4]*/,
+                       const float* b /*[8][64]*/, float* z /*[T][512]*/, int T, cudaStream_t st);
+void launch_conv_post(const float* x /*[L][16] with 12 margin rows*/, const float* w /*[13][16]*/, const float* b,
+                      float* out, int L, cudaStream_t st);
+void launch_gather_rows(const float* table, const long long* idx, float* out, int rows, int C, long long out_ld,
+                        cudaStream_t st);
+// out[t] = sum_i table[codes[i][t] + i*1000]  (BaseTransformer.embed)
+void launch_embed_codes(const float* table, const int* codes /*[8][T] stride ld*/, long long ld, float* out, int T,
+                        long long out_ld, cudaStream_t st);
+void launch_copy_rows(const float* src, long long src_ld, float* dst, long long dst_ld, int rows, int C,
+                      cudaStream_t st);
+void launch_scale_add3(const float* a, const float* b, const float* c, float* out, long long n, float s, cudaStream_t st);
+void launch_fill(float* p, long long n, float v, cudaStream_t st);
+void launch_concat_cols(const int* a, long long a_ld, int a_n, const int* b, long long b_ld, int b_n, void* out,
+                        long long out_ld, int rows, bool out_i64, cudaStream_t st);
+void launch_append_codes(const int* codes8, int* hist, long long ld, int col, cudaStream_t st);
+void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t st);
+
+// ---------------------------------------------------------------- attention (attn.cu)
+// Multi-query causal attention, one warp per query.  q rows [nq][q_ld] (head h at +h*64); keys/values addressed as
+// base + h*head_stride + key*row_stride.  Query i sits at absolute position qpos0+i and attends keys
+// max(0, pos-window+1) .. pos.
+void launch_attention(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
+                      long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
+                      cudaStream_t st);
+// scatter k,v of a fused qkv buffer into a [H][max_seq][64] cache at positions pos0..pos0+rows-1
+void launch_kv_append(const float* qkv, int rows, int heads, float* kc, float* vc, int max_seq, int pos0,
+                      cudaStream_t st);
+
+}  // namespace svanon

@@ -1,0 +1,797 @@
+// Engine: weight store + packing, workspace, and the E / V / A(prefill) stage drivers.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace svanon {
+
+long long g_kernel_launches = 0;
+
+// ------------------------------------------------------------------------------------------ workspace
+void Workspace::ensure(size_t bytes) {
+  if (bytes <= cap) return;
+  SV_CUDA(cudaDeviceSynchronize());
+  if (base) SV_CUDA(cudaFree(base));
+  base = nullptr;
+  cap = 0;
+  const size_t want = (bytes + (64u << 20)) & ~((size_t)(1u << 20) - 1);
+  SV_CUDA(cudaMalloc(&base, want));
+  cap = want;
+}
+void* Workspace::alloc_bytes(size_t bytes) {
+  const size_t a = (off + 255) & ~(size_t)255;
+  SV_CHECK(a + bytes <= cap, "workspace overflow");
+  off = a + bytes;
+  return base + a;
+}
+Workspace::~Workspace() {
+  if (base) cudaFree(base);
+}
+
+Stream::~Stream() {
+  for (void* p : {(void*)kc, (void*)vc, (void*)fkc, (void*)fvc, (void*)x_audio, (void*)ref_emb_tail, (void*)spk_rows,
+                  (void*)codes_dev, (void*)content_id_dev, (void*)noise_dev, (void*)wave_ring, (void*)wave_ring_tmp,
+                  (void*)src_hist, (void*)pred_hist, (void*)ref_content_dev, (void*)ref_audio_dev, (void*)style_dev,
+                  (void*)timbre_dev, (void*)ids_win_dev, (void*)codes_win_dev, (void*)wave_win_dev})
+    if (p) cudaFree(p);
+}
+
+Engine::~Engine() {
+  for (int m = 0; m < MODEL_COUNT; ++m)
+    for (auto& kv : w[m]) cudaFree(kv.second.data);
+  for (float* p : owned) cudaFree(p);
+  for (void* p : {(void*)ar_x, (void*)ar_h, (void*)ar_q, (void*)ar_g, (void*)ar_part, (void*)ar_logits,
+                  (void*)ar_barrier, (void*)dbg_slow_logits, (void*)dbg_hidden, (void*)dbg_fast_logits})
+    if (p) cudaFree(p);
+  if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+const Tensor& Engine::get(int model, const std::string& name) const {
+  auto it = w[model].find(name);
+  if (it == w[model].end()) throw Error("missing tensor '" + name + "' in model " + std::to_string(model));
+  return it->second;
+}
+
+float* Engine::dev_alloc(long long n) {
+  float* p = nullptr;
+  SV_CUDA(cudaMalloc(&p, (size_t)std::max<long long>(n, 1) * sizeof(float)));
+  owned.push_back(p);
+  return p;
+}
+
+float* Engine::upload(const std::vector<float>& host) {
+  float* p = dev_alloc((long long)host.size());
+  SV_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return p;
+}
+
+void Engine::load_tensor(int model, const std::string& name, const float* data, int rank, const long long* shape) {
+  SV_CHECK(model >= 0 && model < MODEL_COUNT, "bad model id");
+  SV_CHECK(!finalized[model], "model already finalized");
+  Tensor t;
+  t.shape.assign(shape, shape + rank);
+  const long long n = t.numel();
+  SV_CHECK(n > 0, "empty tensor");
+  SV_CUDA(cudaMalloc(&t.data, (size_t)n * sizeof(float)));
+  SV_CUDA(cudaMemcpy(t.data, data, (size_t)n * sizeof(float), cudaMemcpyDefault));
+  auto it = w[model].find(name);
+  if (it != w[model].end()) {
+    cudaFree(it->second.data);
+    w[model].erase(it);
+  }
+  w[model].emplace(name, std::move(t));
+}
+
+namespace {
+
+std::vector<float> to_host(const Tensor& t) {
+  std::vector<float> h((size_t)t.numel());
+  SV_CUDA(cudaMemcpy(h.data(), t.data, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  return h;
+}
+
+void expect_shape(const Tensor& t, std::initializer_list<long long> shp, const std::string& name) {
+  if (t.shape != std::vector<long long>(shp)) throw Error("tensor '" + name + "' has an unexpected shape");
+}
+
+}  // namespace
+
+void Engine::finalize(int model) {
+  SV_CHECK(model >= 0 && model < MODEL_COUNT, "bad model id");
+  if (finalized[model]) return;
+  if (model == MODEL_AR) finalize_ar();
+  else if (model == MODEL_TOKENIZER) finalize_tokenizer();
+  else finalize_vocoder();
+  finalized[model] = true;
+}
+
+// ------------------------------------------------------------------------------------------ AR weights
+void Engine::finalize_ar() {
+  auto g = [&](const std::string& n) { return get(MODEL_AR, n).data; };
+  auto layer = [&](const std::string& p) {
+    ArLayerWeights lw;
+    expect_shape(get(MODEL_AR, p + ".attention.wqkv.weight"), {3 * AR_DIM, AR_DIM}, p);
+    expect_shape(get(MODEL_AR, p + ".feed_forward.w2.weight"), {AR_DIM, AR_INTER}, p);
+    lw.attn_norm = g(p + ".attention_norm.weight");
+    lw.wqkv = g(p + ".attention.wqkv.weight");
+    lw.wo = g(p + ".attention.wo.weight");
+    lw.ffn_norm = g(p + ".ffn_norm.weight");
+    lw.w1 = g(p + ".feed_forward.w1.weight");
+    lw.w3 = g(p + ".feed_forward.w3.weight");
+    lw.w2 = g(p + ".feed_forward.w2.weight");
+    return lw;
+  };
+  for (int i = 0; i < AR_LAYERS; ++i) ar.slow[i] = layer("decoder.model.layers." + std::to_string(i));
+  for (int i = 0; i < AR_FAST_LAYERS; ++i) ar.fast[i] = layer("decoder.model.fast_layers." + std::to_string(i));
+  ar.norm_w = g("decoder.model.norm.weight");
+  ar.output_w = g("decoder.model.output.weight");
+  ar.fast_norm_w = g("decoder.model.fast_norm.weight");
+  ar.fast_output_w = g("decoder.model.fast_output.weight");
+  ar.fast_emb = g("decoder.model.fast_embeddings.weight");
+  ar.codebook_emb = g("decoder.model.codebook_embeddings.weight");
+  ar.cond_emb = g("embedding.weight");
+  expect_shape(get(MODEL_AR, "decoder.model.freqs_cis"), {AR_MAX_SEQ, HEAD_DIM / 2, 2}, "decoder.model.freqs_cis");
+  expect_shape(get(MODEL_AR, "decoder.model.fast_freqs_cis"), {AR_CODEBOOKS, HEAD_DIM / 2, 2}, "fast_freqs_cis");
+  ar.rope = g("decoder.model.freqs_cis");
+  ar.fast_rope = g("decoder.model.fast_freqs_cis");
+  ctx_w = g("context_in.weight"); ctx_b = g("context_in.bias");
+  style_w = g("style_in.weight"); style_b = g("style_in.bias");
+  w4s = g("decoder.wait4start_embedding.weight");
+  w4e = g("decoder.wait4end_embedding.weight");
+
+  const int B = AR_MAX_BATCH;
+  ar_x = nullptr;
+  SV_CUDA(cudaMalloc(&ar_x, (size_t)2 * B * AR_DIM * 4));
+  SV_CUDA(cudaMalloc(&ar_h, (size_t)2 * B * AR_DIM * 4));
+  SV_CUDA(cudaMalloc(&ar_q, (size_t)2 * B * AR_DIM * 4));
+  SV_CUDA(cudaMalloc(&ar_g, (size_t)2 * B * AR_INTER * 4));
+  SV_CUDA(cudaMalloc(&ar_part, (size_t)B * AR_HEADS * 16 * 2 * (2 + HEAD_DIM) * 4));
+  SV_CUDA(cudaMalloc(&ar_logits, (size_t)B * 1024 * 4));
+  SV_CUDA(cudaMalloc(&ar_barrier, 2 * sizeof(unsigned)));
+  SV_CUDA(cudaMemset(ar_barrier, 0, 2 * sizeof(unsigned)));
+  SV_CUDA(cudaMalloc(&dbg_slow_logits, AR_VOCAB * 4));
+  SV_CUDA(cudaMalloc(&dbg_hidden, AR_DIM * 4));
+  SV_CUDA(cudaMalloc(&dbg_fast_logits, AR_CODEBOOKS * AR_CB_SIZE * 4));
+  ar.x = ar_x; ar.h = ar_h; ar.q = ar_q; ar.g = ar_g; ar.part = ar_part; ar.logits = ar_logits;
+  ar.barrier = ar_barrier;
+  ar.temperature = 0.7f;   // logits_to_probs defaults, dual_ar_stream.py:1103-1104
+  ar.top_p = 0.7f;
+}
+
+// ------------------------------------------------------------------------------------------ shared packers
+namespace {
+
+// Conv1d weight [Co][Ci][k] -> [Co][k][Ci]  (one GEMM row = k consecutive channels-last input rows)
+std::vector<float> pack_conv_rows(const std::vector<float>& w, int Co, int Ci, int k) {
+  std::vector<float> o((size_t)Co * k * Ci);
+  for (int co = 0; co < Co; ++co)
+    for (int ci = 0; ci < Ci; ++ci)
+      for (int j = 0; j < k; ++j) o[((size_t)co * k + j) * Ci + ci] = w[((size_t)co * Ci + ci) * k + j];
+  return o;
+}
+// Conv1d weight [Co][Ci][k] -> [k][Co][Ci]  (one GEMM tap per kernel element)
+std::vector<float> pack_conv_taps(const std::vector<float>& w, int Co, int Ci, int k) {
+  std::vector<float> o((size_t)Co * k * Ci);
+  for (int co = 0; co < Co; ++co)
+    for (int ci = 0; ci < Ci; ++ci)
+      for (int j = 0; j < k; ++j) o[((size_t)j * Co + co) * Ci + ci] = w[((size_t)co * Ci + ci) * k + j];
+  return o;
+}
+// depthwise [C][1][7] -> [7][C]
+std::vector<float> pack_dw(const std::vector<float>& w, int C) {
+  std::vector<float> o((size_t)7 * C);
+  for (int c = 0; c < C; ++c)
+    for (int j = 0; j < 7; ++j) o[(size_t)j * C + c] = w[(size_t)c * 7 + j];
+  return o;
+}
+// ConvTranspose1d weight [Ci][Co][k], stride s.
+//  k == 2s: out[t*s+r][co] = sum_ci x[t-1][ci] w[ci][co][r+s] + x[t][ci] w[ci][co][r]   (firefly.py:114-138)
+//           -> W'[n = r*Co+co][tap*Ci+ci], tap 0 = row t-1, tap 1 = row t
+//  k == s : out[t*s+r][co] = sum_ci x[t][ci] w[ci][co][r] -> W'[n][ci]
+std::vector<float> pack_tconv(const std::vector<float>& w, int Ci, int Co, int k, int s) {
+  const int taps = k / s;
+  std::vector<float> o((size_t)s * Co * taps * Ci);
+  for (int r = 0; r < s; ++r)
+    for (int co = 0; co < Co; ++co)
+      for (int ci = 0; ci < Ci; ++ci) {
+        const size_t n = (size_t)r * Co + co;
+        if (taps == 2) {
+          o[n * 2 * Ci + ci] = w[((size_t)ci * Co + co) * k + r + s];
+          o[n * 2 * Ci + Ci + ci] = w[((size_t)ci * Co + co) * k + r];
+        } else {
+          o[n * Ci + ci] = w[((size_t)ci * Co + co) * k + r];
+        }
+      }
+  return o;
+}
+std::vector<float> tile_bias(const std::vector<float>& b, int s) {
+  std::vector<float> o;
+  for (int r = 0; r < s; ++r) o.insert(o.end(), b.begin(), b.end());
+  return o;
+}
+
+}  // namespace
+
+static ConvNextW pack_convnext(Engine& e, int model, const std::string& p, int C) {
+  ConvNextW cw;
+  cw.C = C;
+  cw.gamma = e.get(model, p + ".gamma").data;
+  cw.dw_w = e.upload(pack_dw(to_host(e.get(model, p + ".dwconv.conv.weight")), C));
+  cw.dw_b = e.get(model, p + ".dwconv.conv.bias").data;
+  cw.ln_w = e.get(model, p + ".norm.weight").data;
+  cw.ln_b = e.get(model, p + ".norm.bias").data;
+  expect_shape(e.get(model, p + ".pwconv1.weight"), {4 * C, C}, p);
+  cw.pw1_w = e.get(model, p + ".pwconv1.weight").data;
+  cw.pw1_b = e.get(model, p + ".pwconv1.bias").data;
+  cw.pw2_w = e.get(model, p + ".pwconv2.weight").data;
+  cw.pw2_b = e.get(model, p + ".pwconv2.bias").data;
+  return cw;
+}
+
+// ------------------------------------------------------------------------------------------ tokenizer weights
+void Engine::finalize_tokenizer() {
+  const int M = MODEL_TOKENIZER;
+  auto g = [&](const std::string& n) { return get(M, n).data; };
+  // windowed DFT basis: rows 0..1024 real, 1025..2049 imaginary; torch.hann_window(2048) is periodic
+  {
+    std::vector<float> dft((size_t)2 * N_FREQ * N_FFT);
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<double> win(N_FFT);
+    for (int n = 0; n < N_FFT; ++n) win[n] = 0.5 - 0.5 * std::cos(two_pi * n / N_FFT);
+    for (int f = 0; f < N_FREQ; ++f)
+      for (int n = 0; n < N_FFT; ++n) {
+        const long long ph = ((long long)f * n) % N_FFT;
+        const double a = two_pi * (double)ph / N_FFT;
+        dft[(size_t)f * N_FFT + n] = (float)(win[n] * std::cos(a));
+        dft[(size_t)(N_FREQ + f) * N_FFT + n] = (float)(-win[n] * std::sin(a));
+      }
+    dft_w = upload(dft);
+  }
+  {
+    const Tensor& fb = get(M, "spec_transform.fb");
+    expect_shape(fb, {N_FREQ, N_MELS}, "spec_transform.fb");
+    auto h = to_host(fb);
+    std::vector<float> t((size_t)N_MELS * N_FREQ_PAD, 0.f);
+    for (int f = 0; f < N_FREQ; ++f)
+      for (int m = 0; m < N_MELS; ++m) t[(size_t)m * N_FREQ_PAD + f] = h[(size_t)f * N_MELS + m];
+    fb_t = upload(t);
+  }
+  const int dims[4] = {128, 256, 384, 512};
+  const int depths[4] = {3, 3, 9, 3};
+  expect_shape(get(M, "backbone.downsample_layers.0.0.conv.weight"), {128, N_MELS, 7}, "stem");
+  stem_w = upload(pack_conv_rows(to_host(get(M, "backbone.downsample_layers.0.0.conv.weight")), 128, N_MELS, 7));
+  stem_b = g("backbone.downsample_layers.0.0.conv.bias");
+  stem_ln_w = g("backbone.downsample_layers.0.1.weight");
+  stem_ln_b = g("backbone.downsample_layers.0.1.bias");
+  for (int i = 1; i < 4; ++i) {
+    const std::string p = "backbone.downsample_layers." + std::to_string(i);
+    mid_ln_w[i - 1] = g(p + ".0.weight");
+    mid_ln_b[i - 1] = g(p + ".0.bias");
+    expect_shape(get(M, p + ".1.weight"), {dims[i], dims[i - 1], 1}, p);
+    mid_w[i - 1] = g(p + ".1.weight");
+    mid_b[i - 1] = g(p + ".1.bias");
+  }
+  for (int s = 0; s < 4; ++s) {
+    enc_blocks[s].clear();
+    for (int j = 0; j < depths[s]; ++j)
+      enc_blocks[s].push_back(pack_convnext(*this, M, "backbone.stages." + std::to_string(s) + "." + std::to_string(j), dims[s]));
+  }
+  bb_norm_w = g("backbone.norm.weight");
+  bb_norm_b = g("backbone.norm.bias");
+  for (int i = 0; i < 2; ++i) {
+    const std::string p = "quantizer.downsample." + std::to_string(i);
+    expect_shape(get(M, p + ".0.conv.weight"), {ENC_DIM, ENC_DIM, 2}, p);
+    down_w[i] = upload(pack_conv_rows(to_host(get(M, p + ".0.conv.weight")), ENC_DIM, ENC_DIM, 2));
+    down_b[i] = g(p + ".0.conv.bias");
+    down_block[i] = pack_convnext(*this, M, p + ".1", ENC_DIM);
+  }
+  for (int i = 0; i < ENC_LAYERS; ++i) {
+    const std::string p = "quantizer.pre_module.layers." + std::to_string(i);
+    EncLayerW& l = enc_layers[i];
+    expect_shape(get(M, p + ".attention.wqkv.weight"), {3 * ENC_DIM, ENC_DIM}, p);
+    l.attn_norm = g(p + ".attention_norm.weight");
+    l.wqkv = g(p + ".attention.wqkv.weight");
+    l.wo = g(p + ".attention.wo.weight");
+    l.ffn_norm = g(p + ".ffn_norm.weight");
+    l.w1 = g(p + ".feed_forward.w1.weight");
+    l.w3 = g(p + ".feed_forward.w3.weight");
+    l.w2 = g(p + ".feed_forward.w2.weight");
+    l.ls_attn = g(p + ".attention_layer_scale.gamma");
+    l.ls_ffn = g(p + ".ffn_layer_scale.gamma");
+  }
+  enc_norm_w = g("quantizer.pre_module.norm.weight");
+  expect_shape(get(M, "quantizer.pre_module.freqs_cis"), {2048, HEAD_DIM / 2, 2}, "quantizer.pre_module.freqs_cis");
+  enc_rope = g("quantizer.pre_module.freqs_cis");
+  expect_shape(get(M, "quantizer.residual_bsq.rvqs.0.project_in.weight"), {BSQ_BITS, ENC_DIM}, "bsq project_in");
+  bsq_w = g("quantizer.residual_bsq.rvqs.0.project_in.weight");
+  bsq_b = g("quantizer.residual_bsq.rvqs.0.project_in.bias");
+}
+
+// ------------------------------------------------------------------------------------------ vocoder weights
+void Engine::finalize_vocoder() {
+  const int M = MODEL_VOCODER;
+  // fold weight norm: w = g * v / ||v||_(1,2)  (remove_parametrizations, infer_arvc.py:94)
+  {
+    std::vector<std::string> bases;
+    const std::string suf = ".parametrizations.weight.original1";
+    for (auto& kv : w[M])
+      if (kv.first.size() > suf.size() && kv.first.compare(kv.first.size() - suf.size(), suf.size(), suf) == 0)
+        bases.push_back(kv.first.substr(0, kv.first.size() - suf.size()));
+    for (auto& base : bases) {
+      const Tensor& tv = get(M, base + ".parametrizations.weight.original1");
+      const Tensor& tg = get(M, base + ".parametrizations.weight.original0");
+      auto v = to_host(tv);
+      auto gg = to_host(tg);
+      const long long n0 = tv.shape[0], inner = tv.numel() / n0;
+      SV_CHECK(tg.numel() == n0, "weight-norm g shape");
+      for (long long i = 0; i < n0; ++i) {
+        double nrm = 0;
+        for (long long j = 0; j < inner; ++j) nrm += (double)v[i * inner + j] * v[i * inner + j];
+        const float sc = (float)(gg[i] / std::sqrt(nrm));
+        for (long long j = 0; j < inner; ++j) v[i * inner + j] *= sc;
+      }
+      finalized[M] = false;
+      load_tensor(M, base + ".weight", v.data(), (int)tv.shape.size(), tv.shape.data());
+    }
+  }
+  auto g = [&](const std::string& n) { return get(M, n).data; };
+  {
+    std::vector<float> fw, fbv;
+    for (int gi = 0; gi < 8; ++gi) {
+      const std::string p = "quantizer.residual_fsq.rvqs." + std::to_string(gi) + ".project_out";
+      expect_shape(get(M, p + ".weight"), {64, 4}, p);
+      auto a = to_host(get(M, p + ".weight"));
+      auto b = to_host(get(M, p + ".bias"));
+      fw.insert(fw.end(), a.begin(), a.end());
+      fbv.insert(fbv.end(), b.begin(), b.end());
+    }
+    fsq_w = upload(fw);
+    fsq_b = upload(fbv);
+  }
+  for (int i = 0; i < 2; ++i) {
+    const std::string p = "quantizer.upsample." + std::to_string(i);
+    expect_shape(get(M, p + ".0.conv.weight"), {512, 512, 2}, p);
+    up_w[i] = upload(pack_tconv(to_host(get(M, p + ".0.conv.weight")), 512, 512, 2, 2));
+    up_b[i] = upload(tile_bias(to_host(get(M, p + ".0.conv.bias")), 2));
+    up_block[i] = pack_convnext(*this, M, p + ".1", 512);
+  }
+  expect_shape(get(M, "head.conv_pre.conv.weight"), {512, 512, 13}, "conv_pre");
+  pre_w = upload(pack_conv_rows(to_host(get(M, "head.conv_pre.conv.weight")), 512, 512, 13));
+  pre_b = g("head.conv_pre.conv.bias");
+  const int ch[6] = {512, 256, 128, 64, 32, 16};
+  const int upk[5] = {16, 16, 4, 4, 4}, ups[5] = {8, 8, 2, 2, 2};
+  const int rk[3] = {3, 7, 11}, rd[3] = {1, 3, 5};
+  for (int i = 0; i < 5; ++i) {
+    const std::string p = "head.ups." + std::to_string(i) + ".conv";
+    expect_shape(get(M, p + ".weight"), {ch[i], ch[i + 1], upk[i]}, p);
+    ups_w[i] = upload(pack_tconv(to_host(get(M, p + ".weight")), ch[i], ch[i + 1], upk[i], ups[i]));
+    ups_b[i] = upload(tile_bias(to_host(get(M, p + ".bias")), ups[i]));
+    const int C = ch[i + 1];
+    for (int j = 0; j < 3; ++j)
+      for (int d = 0; d < 3; ++d)
+        for (int which = 0; which < 2; ++which) {
+          const std::string q = "head.resblocks." + std::to_string(i) + ".blocks." + std::to_string(j) +
+                                (which ? ".convs2." : ".convs1.") + std::to_string(d) + ".conv";
+          expect_shape(get(M, q + ".weight"), {C, C, rk[j]}, q);
+          ResConvW rw;
+          rw.k = rk[j];
+          rw.d = rd[d];
+          auto hw = to_host(get(M, q + ".weight"));
+          rw.w = upload(rd[d] == 1 ? pack_conv_rows(hw, C, C, rk[j]) : pack_conv_taps(hw, C, C, rk[j]));
+          rw.b = g(q + ".bias");
+          (which ? res2 : res1)[i][j][d] = rw;
+        }
+  }
+  expect_shape(get(M, "head.conv_post.conv.weight"), {1, 16, 13}, "conv_post");
+  post_w = upload(pack_conv_rows(to_host(get(M, "head.conv_post.conv.weight")), 1, 16, 13));
+  post_b = g("head.conv_post.conv.bias");
+}
+
+// ------------------------------------------------------------------------------------------ ConvNeXt block
+// ConvNeXtBlock.forward (firefly.py:421-440), channels-last, in place on x (x has >= 6 zero/history rows
+// before row 0).  tmp [rows][C], hid [rows][4C].
+void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float* hid, cudaStream_t st) {
+  const int C = cw.C;
+  launch_dwconv7_ln(x, tmp, cw.dw_w, cw.dw_b, cw.ln_w, cw.ln_b, rows, C, 1e-6f, st);
+  GemmParams p1;
+  p1.A = tmp; p1.W = cw.pw1_w; p1.C = hid; p1.bias = cw.pw1_b; p1.M = rows; p1.N = 4 * C; p1.K = C;
+  p1.lda = C; p1.ldc = 4 * C; p1.act = ACT_GELU;
+  launch_gemm(p1, st);
+  GemmParams p2;
+  p2.A = hid; p2.W = cw.pw2_w; p2.C = x; p2.bias = cw.pw2_b; p2.gamma = cw.gamma; p2.residual = x;
+  p2.M = rows; p2.N = C; p2.K = 4 * C; p2.lda = 4 * C; p2.ldc = C; p2.ldr = C;
+  launch_gemm(p2, st);
+
+}
+
+// ------------------------------------------------------------------------------------------ stage E
+// FireflyArchitecture.encode (firefly_encoder.py:553-566) for one full-length utterance / window.
+void Engine::enc_encode(const float* wave, long long n, long long* ids_dev, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
+  const int T = (int)(n / HOP);
+  const int T2 = T / 2, S = T2 / 2;
+  SV_CHECK(S >= 1, "utterance shorter than one content frame (2048 samples)");
+  SV_CHECK(S <= 2048, "utterance longer than the tokenizer's RoPE table (2048 content frames)");
+  ws.ensure(((size_t)T * 14000 + (size_t)n + (4u << 20)) * sizeof(float));
+  ws.reset();
+  const int MARG = 6;
+  // 1. left-pad win-hop zeros (spectrogram.py:37-45) and take frames as overlapping GEMM rows (lda = hop)
+  float* wpad = ws.alloc_f(N_FFT - HOP + n);
+  launch_fill(wpad, N_FFT - HOP, 0.f, st);
+  SV_CUDA(cudaMemcpyAsync(wpad + (N_FFT - HOP), wave, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int SPEC_LD = 2052;
+  float* spec = ws.alloc_f((long long)T * SPEC_LD);
+  {
+    GemmParams p;
+    p.A = wpad; p.W = dft_w; p.C = spec; p.M = T; p.N = 2 * N_FREQ; p.K = N_FFT; p.lda = HOP; p.ldc = SPEC_LD;
+    launch_gemm(p, st);
+  }
+  float* mag = ws.alloc_f((long long)T * N_FREQ_PAD);
+  launch_magnitude(spec, mag, T, SPEC_LD, st);
+  // 2. mel filterbank + log(clamp(., 1e-5))  (spectrogram.py:108-130); 6 zero rows in front for the causal stem
+  float* mel_buf = ws.alloc_f((long long)(MARG + T) * N_MELS);
+  launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st);
+  float* mel = mel_buf + MARG * N_MELS;
+  {
+    GemmParams p;
+    p.A = mag; p.W = fb_t; p.C = mel; p.M = T; p.N = N_MELS; p.K = N_FREQ_PAD; p.lda = N_FREQ_PAD; p.ldc = N_MELS;
+    p.act = ACT_LOGCLAMP;
+    launch_gemm(p, st);
+  }
+
+  // 3. ConvNeXtEncoder (firefly.py:506-517)
+  const int dims[4] = {128, 256, 384, 512};
+  float* tmp = ws.alloc_f((long long)T * 512);
+  float* hid = ws.alloc_f((long long)T * 2048);
+  float* x = nullptr;
+  for (int s = 0; s < 4; ++s) {
+    const int C = dims[s];
+    float* xb = ws.alloc_f((long long)(MARG + T) * C);
+    launch_fill(xb, (long long)MARG * C, 0.f, st);
+    float* xn = xb + MARG * C;
+    if (s == 0) {
+      GemmParams p;   // stem: causal conv k=7 as one GEMM over 7 overlapping rows
+      p.A = mel; p.W = stem_w; p.C = tmp; p.bias = stem_b; p.M = T; p.N = C; p.K = 7 * N_MELS; p.lda = N_MELS;
+      p.ldc = C; p.tap_off[0] = -6;
+      launch_gemm(p, st);
+      launch_layernorm(tmp, xn, stem_ln_w, stem_ln_b, T, C, 1e-6f, st);
+    } else {
+      const int Cp = dims[s - 1];
+      launch_layernorm(x, tmp, mid_ln_w[s - 1], mid_ln_b[s - 1], T, Cp, 1e-6f, st);
+      GemmParams p;
+      p.A = tmp; p.W = mid_w[s - 1]; p.C = xn; p.bias = mid_b[s - 1]; p.M = T; p.N = C; p.K = Cp; p.lda = Cp; p.ldc = C;
+      launch_gemm(p, st);
+    }
+
+    x = xn;
+    for (auto& blk : enc_blocks[s]) convnext(blk, x, T, tmp, hid, st);
+  }
+  float* feat = ws.alloc_f((long long)T * 512);
+  launch_layernorm(x, feat, bb_norm_w, bb_norm_b, T, 512, 1e-6f, st);
+  // 4. DownsampleBinarySphericalQuantize.downsample (bsq_no_upsample.py:46-60): 2 x [conv k2 s2 + ConvNeXt]
+  float* cur = feat;
+  int rows = T;
+  for (int i = 0; i < 2; ++i) {
+    const int r2 = rows / 2;
+    float* db = ws.alloc_f((long long)(MARG + r2) * 512);
+    launch_fill(db, (long long)MARG * 512, 0.f, st);
+    float* dn = db + MARG * 512;
+    GemmParams p;
+    p.A = cur; p.W = down_w[i]; p.C = dn; p.bias = down_b[i]; p.M = r2; p.N = 512; p.K = 1024; p.lda = 512;
+    p.a_row_step = 2; p.ldc = 512;
+    launch_gemm(p, st);
+
+    convnext(down_block[i], dn, r2, tmp, hid, st);
+    cur = dn;
+    rows = r2;
+  }
+  // 5. WindowLimitedTransformer (windowed_transformer.py:337-354), positions 0..S-1
+  float* xt = cur;
+  float* nrm = ws.alloc_f((long long)S * ENC_DIM);
+  float* qkv = ws.alloc_f((long long)S * 3 * ENC_DIM);
+  float* y = ws.alloc_f((long long)S * ENC_DIM);
+  float* h13 = ws.alloc_f((long long)S * 2 * ENC_INTER);
+  float* gbuf = ws.alloc_f((long long)S * ENC_INTER);
+  for (int l = 0; l < ENC_LAYERS; ++l) {
+    const EncLayerW& L = enc_layers[l];
+    launch_rmsnorm(xt, nrm, L.attn_norm, S, ENC_DIM, 1e-5f, st);
+    GemmParams p;
+    p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = S; p.N = 3 * ENC_DIM; p.K = ENC_DIM; p.lda = ENC_DIM; p.ldc = 3 * ENC_DIM;
+    launch_gemm(p, st);
+    launch_rope_qk(qkv, enc_rope, S, ENC_HEADS, 0, st);
+    launch_attention(qkv, 3 * ENC_DIM, qkv + ENC_DIM, qkv + 2 * ENC_DIM, HEAD_DIM, 3 * ENC_DIM, y, ENC_DIM, S, 0,
+                     ENC_HEADS, ENC_WINDOW, st);
+    GemmParams po;
+    po.A = y; po.W = L.wo; po.C = xt; po.gamma = L.ls_attn; po.residual = xt; po.M = S; po.N = ENC_DIM; po.K = ENC_DIM;
+    po.lda = ENC_DIM; po.ldc = ENC_DIM; po.ldr = ENC_DIM;
+    launch_gemm(po, st);
+    launch_rmsnorm(xt, nrm, L.ffn_norm, S, ENC_DIM, 1e-5f, st);
+    GemmParams p1;
+    p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = S; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM; p1.ldc = 2 * ENC_INTER;
+    launch_gemm(p1, st);
+    p1.W = L.w3; p1.C = h13 + ENC_INTER;
+    launch_gemm(p1, st);
+    launch_silu_mul(h13, gbuf, S, ENC_INTER, st);
+    GemmParams p2;
+    p2.A = gbuf; p2.W = L.w2; p2.C = xt; p2.gamma = L.ls_ffn; p2.residual = xt; p2.M = S; p2.N = ENC_DIM; p2.K = ENC_INTER;
+    p2.lda = ENC_INTER; p2.ldc = ENC_DIM; p2.ldr = ENC_DIM;
+    launch_gemm(p2, st);
+
+  }
+  launch_rmsnorm(xt, nrm, enc_norm_w, S, ENC_DIM, 1e-5f, st);
+  // 6. BSQ ids (bsq.py:330-369)
+  launch_bsq(nrm, bsq_w, bsq_b, ids_dev, S, st);
+
+}
+
+// ------------------------------------------------------------------------------------------ stage V
+static size_t voc_ws_bytes(int T) { return ((size_t)T * 1300000 + (8u << 20)) * sizeof(float); }
+
+// DownsampleFiniteScalarQuantize.decode (fsq.py:112-116): FSQ lookup + 2 x [tconv k2 s2 + ConvNeXt]
+static void voc_qdecode_impl(Engine& e, const long long* codes, long long ld, int T, float* z_out, cudaStream_t st) {
+  Workspace& ws = e.ws;
+  float* z0 = ws.alloc_f((long long)T * 512);
+  launch_fsq_lookup(codes, ld, e.fsq_w, e.fsq_b, z0, T, st);
+  const int MARG = 6;
+  float* tmp = ws.alloc_f((long long)4 * T * 512);
+  float* hid = ws.alloc_f((long long)4 * T * 2048);
+  float* cur = z0;
+  int rows = T;
+  for (int i = 0; i < 2; ++i) {
+    const int r2 = rows * 2;
+    float* xb;
+    if (i == 1) {
+      xb = z_out;                       // caller provides >= 6 rows of margin in front of z_out
+    } else {
+      float* buf = ws.alloc_f((long long)(MARG + r2) * 512);
+      xb = buf + MARG * 512;
+    }
+    launch_fill(xb - MARG * 512, (long long)MARG * 512, 0.f, st);
+    GemmParams p;
+    p.A = cur; p.W = e.up_w[i]; p.C = xb; p.bias = e.up_b[i]; p.M = rows; p.N = 1024; p.K = 512; p.lda = 512; p.ldc = 1024;
+    launch_gemm(p, st);
+    e.convnext(e.up_block[i], xb, r2, tmp, hid, st);
+
+    cur = xb;
+    rows = r2;
+  }
+
+}
+
+// HiFiGANGenerator.forward (firefly.py:280-293).  z has >= 12 zero rows in front (conv_pre k = 13).
+static void voc_head_impl(Engine& e, const float* z, int L, float* wave, cudaStream_t st) {
+  Workspace& ws = e.ws;
+  const int ch[6] = {512, 256, 128, 64, 32, 16};
+  const int ups[5] = {8, 8, 2, 2, 2};
+  // conv_pre -> c0 with 1 margin row (x[t-1] of the first transposed conv)
+  float* c0b = ws.alloc_f((long long)(1 + L) * 512);
+  launch_fill(c0b, 512, 0.f, st);
+  float* cur = c0b + 512;
+  {
+    GemmParams p;
+    p.A = z; p.W = e.pre_w; p.C = cur; p.bias = e.pre_b; p.M = L; p.N = 512; p.K = 13 * 512; p.lda = 512; p.ldc = 512;
+    p.tap_off[0] = -12;
+    launch_gemm(p, st);
+  }
+
+  int rows = L;
+  const int RM = 50;                       // largest causal reach of a ResBlock1 conv: (11-1)*5
+  for (int i = 0; i < 5; ++i) {
+    const int Ci = ch[i], Co = ch[i + 1], s = ups[i];
+    const int Lo = rows * s;
+    auto with_margin = [&](int margin) {
+      float* b = ws.alloc_f((long long)(margin + Lo) * Co);
+      launch_fill(b, (long long)margin * Co, 0.f, st);
+      return b + (long long)margin * Co;
+    };
+    float* x = with_margin(RM);
+    {
+      GemmParams p;                        // SiLU -> FishTransConvNet (k = 2s): rows t-1, t
+      p.A = cur; p.W = e.ups_w[i]; p.C = x; p.bias = e.ups_b[i]; p.M = rows; p.N = s * Co; p.K = 2 * Ci; p.lda = Ci;
+      p.ldc = (long long)s * Co; p.tap_off[0] = -1; p.prologue = PRO_SILU;
+      launch_gemm(p, st);
+    }
+    float* tmpb[3];
+    float* xb[3];
+    for (int j = 0; j < 3; ++j) { tmpb[j] = with_margin(RM); xb[j] = with_margin(RM); }
+
+    for (int d = 0; d < 3; ++d) {
+      GemmParams p1[3], p2[3];
+      for (int j = 0; j < 3; ++j) {
+        const ResConvW& w1 = e.res1[i][j][d];
+        const ResConvW& w2 = e.res2[i][j][d];
+        const float* in = (d == 0) ? x : xb[j];
+        auto setup = [&](GemmParams& p, const ResConvW& w, const float* A, float* C, const float* res) {
+          p.A = A; p.W = w.w; p.C = C; p.bias = w.b; p.residual = res; p.M = Lo; p.N = Co; p.lda = Co; p.ldc = Co;
+          p.ldr = Co; p.prologue = PRO_SILU;
+          if (w.d == 1) {
+            p.K = w.k * Co; p.taps = 1; p.tap_off[0] = -(w.k - 1);
+          } else {
+            p.K = Co; p.taps = w.k;
+            for (int t = 0; t < w.k; ++t) p.tap_off[t] = -(w.k - 1 - t) * w.d;
+          }
+        };
+        setup(p1[j], w1, in, tmpb[j], nullptr);
+        setup(p2[j], w2, tmpb[j], xb[j], in);
+      }
+      launch_gemm(p1, 3, st);
+      launch_gemm(p2, 3, st);
+
+    }
+    // ParallelBlock mean (firefly.py:214-215) into the next level's input buffer
+    const int next_margin = (i == 4) ? 12 : 1;
+    float* nx = with_margin(next_margin);
+    launch_scale_add3(xb[0], xb[1], xb[2], nx, (long long)Lo * Co, 1.f / 3.f, st);
+
+    cur = nx;
+    rows = Lo;
+  }
+  launch_conv_post(cur, e.post_w, e.post_b, wave, rows, st);
+
+}
+
+void Engine::voc_quantizer_decode(const long long* codes, long long ld, int T, float* z, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
+  SV_CHECK(T >= 1, "empty code sequence");
+  ws.ensure(voc_ws_bytes(T));
+  ws.reset();
+  float* zb = ws.alloc_f((long long)(6 + 4 * T) * 512);
+  voc_qdecode_impl(*this, codes, ld, T, zb + 6 * 512, st);
+  SV_CUDA(cudaMemcpyAsync(z, zb + 6 * 512, (size_t)4 * T * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+void Engine::voc_head(const float* z, int L, float* wave, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
+  SV_CHECK(L >= 1, "empty feature sequence");
+  ws.ensure(voc_ws_bytes((L + 3) / 4));
+  ws.reset();
+  float* zb = ws.alloc_f((long long)(12 + L) * 512);
+  launch_fill(zb, 12 * 512, 0.f, st);
+  SV_CUDA(cudaMemcpyAsync(zb + 12 * 512, z, (size_t)L * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  voc_head_impl(*this, zb + 12 * 512, L, wave, st);
+}
+
+void Engine::voc_decode(const long long* codes, long long ld, int T, float* wave, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
+  SV_CHECK(T >= 1, "empty code sequence");
+  ws.ensure(voc_ws_bytes(T));
+  ws.reset();
+  float* zb = ws.alloc_f((long long)(12 + 4 * T) * 512);
+  launch_fill(zb, 12 * 512, 0.f, st);
+  voc_qdecode_impl(*this, codes, ld, T, zb + 12 * 512, st);
+  voc_head_impl(*this, zb + 12 * 512, 4 * T, wave, st);
+}
+
+// ------------------------------------------------------------------------------------------ stage A (multi-token)
+// BaseTransformer.forward_generate over M new tokens at positions pos0.. (dual_ar_stream.py:312-356) without the
+// heads: fills the KV cache; x is updated in place to the last layer's residual stream.
+void Engine::ar_forward_tokens(Stream& s, float* x, int M, int pos0, cudaStream_t st) {
+  SV_CHECK(pos0 + M <= s.max_seq, "sequence position exceeds the KV cache (max_seq_len)");
+  float* nrm = ws.alloc_f((long long)M * AR_DIM);
+  float* qkv = ws.alloc_f((long long)M * 3 * AR_DIM);
+  float* y = ws.alloc_f((long long)M * AR_DIM);
+  float* h13 = ws.alloc_f((long long)M * 2 * AR_INTER);
+  float* gbuf = ws.alloc_f((long long)M * AR_INTER);
+  const long long layer_stride = (long long)AR_HEADS * s.max_seq * HEAD_DIM;
+  for (int l = 0; l < AR_LAYERS; ++l) {
+    const ArLayerWeights& L = ar.slow[l];
+    launch_rmsnorm(x, nrm, L.attn_norm, M, AR_DIM, AR_NORM_EPS, st);
+    GemmParams p;
+    p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = M; p.N = 3 * AR_DIM; p.K = AR_DIM; p.lda = AR_DIM; p.ldc = 3 * AR_DIM;
+    launch_gemm(p, st);
+    launch_rope_qk(qkv, ar.rope, M, AR_HEADS, pos0, st);
+    launch_kv_append(qkv, M, AR_HEADS, s.kc + l * layer_stride, s.vc + l * layer_stride, s.max_seq, pos0, st);
+    launch_attention(qkv, 3 * AR_DIM, s.kc + l * layer_stride, s.vc + l * layer_stride, (long long)s.max_seq * HEAD_DIM,
+                     HEAD_DIM, y, AR_DIM, M, pos0, AR_HEADS, 1 << 30, st);
+    GemmParams po;
+    po.A = y; po.W = L.wo; po.C = x; po.residual = x; po.M = M; po.N = AR_DIM; po.K = AR_DIM; po.lda = AR_DIM;
+    po.ldc = AR_DIM; po.ldr = AR_DIM;
+    launch_gemm(po, st);
+    launch_rmsnorm(x, nrm, L.ffn_norm, M, AR_DIM, AR_NORM_EPS, st);
+    GemmParams p1;
+    p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = M; p1.N = AR_INTER; p1.K = AR_DIM; p1.lda = AR_DIM; p1.ldc = 2 * AR_INTER;
+    launch_gemm(p1, st);
+    p1.W = L.w3; p1.C = h13 + AR_INTER;
+    launch_gemm(p1, st);
+    launch_silu_mul(h13, gbuf, M, AR_INTER, st);
+    GemmParams p2;
+    p2.A = gbuf; p2.W = L.w2; p2.C = x; p2.residual = x; p2.M = M; p2.N = AR_DIM; p2.K = AR_INTER; p2.lda = AR_INTER;
+    p2.ldc = AR_DIM; p2.ldr = AR_DIM;
+    launch_gemm(p2, st);
+
+  }
+}
+
+// ARVCWrapper.prefill_prompt (arvc_wrapper.py:100-112) -> DualARWrapper.prefill_prompt (dual_ar_stream.py:764-796).
+// ref_content [T] int64 (device), ref_audio [8][T] int32 (device), style [192], timbre [32][128] (device).
+void Engine::ar_prefill_prompt(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
+                               const float* timbre, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_AR], "AR weights not finalized");
+  const int d = s.delay;
+  SV_CHECK(T >= 1 && T > d, "prompt must be longer than the delay");
+  const int n_tok = AR_SPK_TOKENS + 2 * T - (d == 0 ? 1 : 0);
+  SV_CHECK(n_tok <= s.max_seq, "prompt does not fit the KV cache");
+  ws.ensure(((size_t)(n_tok + 8) * 12000 + (1u << 20)) * sizeof(float));
+  ws.reset();
+  float* x = ws.alloc_f((long long)(n_tok + 2) * AR_DIM);
+  // speaker rows: context_in(timbre) 32 tokens, style_in(style) 1 token
+  {
+    GemmParams p;
+    p.A = timbre; p.W = ctx_w; p.C = x; p.bias = ctx_b; p.M = 32; p.N = AR_DIM; p.K = 128; p.lda = 128; p.ldc = AR_DIM;
+    launch_gemm(p, st);
+    GemmParams q;
+    q.A = style; q.W = style_w; q.C = x + 32 * AR_DIM; q.bias = style_b; q.M = 1; q.N = AR_DIM; q.K = 192; q.lda = 192;
+    q.ldc = AR_DIM;
+    launch_gemm(q, st);
+  }
+  launch_copy_rows(x, AR_DIM, s.spk_rows, AR_DIM, AR_SPK_TOKENS, AR_DIM, st);
+  float* seq = x + AR_SPK_TOKENS * AR_DIM;
+  // condition rows (even), audio rows (odd): wait4start[:d] then embed(ref_audio[:, :T-d])
+  launch_gather_rows(ar.cond_emb, ref_content, seq, T, AR_DIM, 2 * AR_DIM, st);
+  if (d > 0) launch_copy_rows(w4s, AR_DIM, seq + AR_DIM, 2 * AR_DIM, d, AR_DIM, st);
+  // (for d == 0 the last audio row is dropped: n_tok already excludes it, the buffer has room for it)
+  launch_embed_codes(ar.codebook_emb, ref_audio, T, seq + (long long)(2 * d + 1) * AR_DIM, T - d, 2 * AR_DIM, st);
+  // cached_ref_emb = embed(ref_audio[:, T-d:]) ; for d == 0 cached_new_audio_emb = embed(last frame)
+  if (d > 0) launch_embed_codes(ar.codebook_emb, ref_audio + (T - d), T, s.ref_emb_tail, d, AR_DIM, st);
+  else launch_embed_codes(ar.codebook_emb, ref_audio + (T - 1), T, s.x_audio, 1, AR_DIM, st);
+
+  ar_forward_tokens(s, x, n_tok, 0, st);
+  s.pos_next = n_tok;
+  s.step += 1;
+  s.delay_prefilled = false;
+}
+
+// ARVCWrapper.prefill_src_condition4delay (arvc_wrapper.py:114-119) -> dual_ar_stream.py:798-815
+void Engine::ar_prefill_delay(Stream& s, const long long* src_content, int n, cudaStream_t st) {
+  const int d = s.delay;
+  SV_CHECK(n == d, "prefill_src_condition4delay expects exactly `delay` content codes");
+  SV_CHECK(d > 0, "prefill_src_condition4delay is only defined for delay > 0");
+  ws.ensure(((size_t)(2 * d + 8) * 12000 + (1u << 20)) * sizeof(float));
+  ws.reset();
+  float* x = ws.alloc_f((long long)2 * d * AR_DIM);
+  launch_gather_rows(ar.cond_emb, src_content, x, d, AR_DIM, 2 * AR_DIM, st);
+  launch_copy_rows(s.ref_emb_tail, AR_DIM, x + AR_DIM, 2 * AR_DIM, d, AR_DIM, st);
+  launch_copy_rows(x + (long long)(2 * d - 1) * AR_DIM, AR_DIM, s.x_audio, AR_DIM, 1, AR_DIM, st);
+
+  ar_forward_tokens(s, x, 2 * d - 1, s.pos_next, st);
+  s.pos_next += 2 * d - 1;
+  s.step += 1;
+  s.delay_prefilled = true;
+}
+
+// DualARWrapper.decode_one (dual_ar_stream.py:817-837) for `batch` independent streams in one launch.
+void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_AR], "AR weights not finalized");
+  SV_CHECK(batch == 1 || batch == 2 || batch == 4, "decode batch must be 1, 2 or 4");
+  ArDecodeArgs a = ar;
+  int max_keys = 0;
+  for (int b = 0; b < batch; ++b) {
+    Stream& s = *streams[b];
+    SV_CHECK(s.pos_next + 2 <= s.max_seq, "KV cache full: re-prompt before decoding further");
+    SV_CHECK(s.max_seq == streams[0]->max_seq, "batched streams must share max_seq_len");
+    ArStreamDev& sd = a.s[b];
+    sd.kc = s.kc; sd.vc = s.vc; sd.fkc = s.fkc; sd.fvc = s.fvc; sd.x_audio = s.x_audio;
+    sd.content_id = s.step_content_id; sd.cond_row = s.step_cond_row; sd.noise = s.step_noise; sd.out_codes = s.codes_dev;
+    SV_CHECK(sd.content_id || sd.cond_row, "decode step without a content id");
+    sd.pos = s.pos_next; sd.step = s.step; sd.seed = s.seed;
+    max_keys = std::max(max_keys, s.pos_next + 2);
+  }
+  a.max_seq = streams[0]->max_seq;
+  a.temperature = streams[0]->temperature;
+  a.top_p = streams[0]->top_p;
+  int nsplit = std::max(1, num_sms / (batch * AR_HEADS));
+  nsplit = std::min(nsplit, 16);
+  nsplit = std::min(nsplit, std::max(1, max_keys / 16));
+  a.nsplit = nsplit;
+  if (debug_logits) { a.dbg_slow_logits = dbg_slow_logits; a.dbg_hidden = dbg_hidden; a.dbg_fast_logits = dbg_fast_logits; }
+  else { a.dbg_slow_logits = nullptr; a.dbg_hidden = nullptr; a.dbg_fast_logits = nullptr; }
+  launch_ar_decode(a, batch, num_sms, st);
+
+  for (int b = 0; b < batch; ++b) {
+    streams[b]->pos_next += 2;
+    streams[b]->step += 1;
+  }
+}
+
+}  // namespace svanon

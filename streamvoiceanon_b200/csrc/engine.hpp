@@ -1,0 +1,161 @@
+// Host-side engine: weight store, workspace, per-stream state and the three stage drivers.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ar_decode.cuh"
+#include "common.cuh"
+
+namespace svanon {
+
+enum Model : int { MODEL_AR = 0, MODEL_TOKENIZER = 1, MODEL_VOCODER = 2, MODEL_COUNT = 3 };
+
+struct Tensor {
+  float* data = nullptr;
+  std::vector<long long> shape;
+  long long numel() const {
+    long long n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// Bump allocator over one device arena; reset at the start of every stage call.  Growing reallocates
+// (device sync) and only happens the first time a larger problem size is seen.
+struct Workspace {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void ensure(size_t bytes);
+  void reset() { off = 0; }
+  float* alloc_f(long long n) { return reinterpret_cast<float*>(alloc_bytes((size_t)n * sizeof(float))); }
+  void* alloc_bytes(size_t bytes);
+  ~Workspace();
+};
+
+struct ConvNextW {
+  const float *gamma, *dw_w /*[7][C]*/, *dw_b, *ln_w, *ln_b, *pw1_w, *pw1_b, *pw2_w, *pw2_b;
+  int C;
+};
+
+struct EncLayerW {
+  const float *attn_norm, *wqkv, *wo, *ffn_norm, *w1, *w3, *w2, *ls_attn, *ls_ffn;
+};
+
+struct ResConvW {
+  const float* w;   // d == 1: [C][k][C]  (single GEMM over k overlapping rows); d > 1: [k][C][C] (k taps)
+  const float* b;
+  int k, d;
+};
+
+struct Engine;
+
+constexpr int HIST_CAP = 4096;     // columns kept of src_content_codes / pred_codes (the reference trims to 2048)
+
+struct Stream {
+  Engine* eng = nullptr;
+  int max_seq = AR_MAX_SEQ;
+  int delay = 0;
+  float temperature = 0.7f, top_p = 0.7f;
+  // ---- AR state (device)
+  float *kc = nullptr, *vc = nullptr, *fkc = nullptr, *fvc = nullptr;
+  float* x_audio = nullptr;        // [768]     cached_new_audio_emb
+  float* ref_emb_tail = nullptr;   // [8][768]  cached_ref_emb (last `delay` prompt frames)
+  float* spk_rows = nullptr;       // [33][768] speaker condition rows of the current prompt
+  int* codes_dev = nullptr;        // [8]       codes of the last decode step
+  long long* content_id_dev = nullptr;
+  float* noise_dev = nullptr;      // [8][8][1000] staging for host-side noise tapes (up to 8 frames per chunk)
+  const long long* step_content_id = nullptr;   // per-step inputs of the next decode launch
+  const float* step_noise = nullptr;
+  const float* step_cond_row = nullptr;
+  int pos_next = 0;                // next free sequence position (== cached_kv_pos[-1] + 1)
+  unsigned step = 0;               // decode_one_token_ar calls so far (prefills included)
+  unsigned long long seed = 0;
+  // ---- per-chunk loop state (InferenceWrapper.setup_stream_caches, infer_arvc.py:443-460), all on the device
+  int enc_win = 0, dec_win = 0, max_seq_frames = 0, buffer_frames = 0, chunk = 1;
+  float *wave_ring = nullptr, *wave_ring_tmp = nullptr;     // [enc_win*2048]
+  long long* src_hist = nullptr;   // [HIST_CAP]     src_content_codes
+  int n_src = 0;
+  int* pred_hist = nullptr;        // [8][HIST_CAP]  pred_codes
+  int n_pred = 0;
+  long long* ref_content_dev = nullptr;   // [ref_frames]   prompt truncated to max_prompt_frames
+  int* ref_audio_dev = nullptr;           // [8][ref_frames]
+  int ref_frames = 0;
+  float *style_dev = nullptr, *timbre_dev = nullptr;
+  bool delay_prefilled = false;
+  long long* ids_win_dev = nullptr;       // [enc_win]
+  long long* codes_win_dev = nullptr;     // [8][dec_win]
+  float* wave_win_dev = nullptr;          // [dec_win*2048]
+  ~Stream();
+};
+
+struct Engine {
+  int device = 0;
+  int num_sms = 148;
+  std::unordered_map<std::string, Tensor> w[MODEL_COUNT];
+  bool finalized[MODEL_COUNT] = {false, false, false};
+  std::vector<float*> owned;                   // packed weights built at finalize
+  Workspace ws;
+  cudaStream_t own_stream = nullptr;
+
+  // ---- AR
+  ArDecodeArgs ar{};
+  const float *ctx_w = nullptr, *ctx_b = nullptr, *style_w = nullptr, *style_b = nullptr;
+  const float *w4s = nullptr, *w4e = nullptr;
+  float *ar_x = nullptr, *ar_h = nullptr, *ar_q = nullptr, *ar_g = nullptr, *ar_part = nullptr, *ar_logits = nullptr;
+  unsigned* ar_barrier = nullptr;
+  float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
+  bool debug_logits = false;
+
+  // ---- tokenizer
+  const float *dft_w = nullptr, *fb_t = nullptr, *stem_w = nullptr, *stem_b = nullptr, *stem_ln_w = nullptr,
+              *stem_ln_b = nullptr;
+  const float *mid_ln_w[3] = {}, *mid_ln_b[3] = {}, *mid_w[3] = {}, *mid_b[3] = {};
+  std::vector<ConvNextW> enc_blocks[4];
+  const float *bb_norm_w = nullptr, *bb_norm_b = nullptr;
+  const float *down_w[2] = {}, *down_b[2] = {};
+  ConvNextW down_block[2];
+  EncLayerW enc_layers[ENC_LAYERS];
+  const float *enc_norm_w = nullptr, *enc_rope = nullptr, *bsq_w = nullptr, *bsq_b = nullptr;
+
+  // ---- vocoder
+  const float *fsq_w = nullptr, *fsq_b = nullptr;
+  const float *up_w[2] = {}, *up_b[2] = {};
+  ConvNextW up_block[2];
+  const float *pre_w = nullptr, *pre_b = nullptr;
+  const float *ups_w[5] = {}, *ups_b[5] = {};
+  ResConvW res1[5][3][3], res2[5][3][3];
+  const float *post_w = nullptr, *post_b = nullptr;
+
+  ~Engine();
+
+  const Tensor& get(int model, const std::string& name) const;
+  bool has(int model, const std::string& name) const { return w[model].count(name) != 0; }
+  float* upload(const std::vector<float>& host);
+  float* dev_alloc(long long n_floats);
+
+  void load_tensor(int model, const std::string& name, const float* data, int rank, const long long* shape);
+  void finalize(int model);
+  void finalize_ar();
+  void finalize_tokenizer();
+  void finalize_vocoder();
+
+  // stage drivers (all device pointers, stream-ordered, no host sync)
+  int enc_num_ids(long long n_samples) const { return (int)(((n_samples / HOP) / 2) / 2); }
+  void enc_encode(const float* wave_dev, long long n_samples, long long* ids_dev, cudaStream_t st);
+  void voc_quantizer_decode(const long long* codes_dev, long long ld, int T, float* z_dev /*[4T][512]*/, cudaStream_t st);
+  void voc_head(const float* z_dev /*[L][512]*/, int L, float* wave_dev /*[512 L]*/, cudaStream_t st);
+  void voc_decode(const long long* codes_dev, long long ld, int T, float* wave_dev, cudaStream_t st);
+  void convnext(const ConvNextW& w, float* x, int rows, float* tmp, float* hid, cudaStream_t st);
+
+  // AR
+  void ar_forward_tokens(Stream& s, float* x /*[M][768]*/, int M, int pos0, cudaStream_t st);
+  void ar_prefill_prompt(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
+                         const float* timbre, cudaStream_t st);
+  void ar_prefill_delay(Stream& s, const long long* src_content, int n, cudaStream_t st);
+  void ar_decode_step(Stream* const* streams, int batch, cudaStream_t st);
+};
+
+}  // namespace svanon

@@ -1,0 +1,231 @@
+// fp32 multi-tap GEMM on CUDA cores (parity mode: bit-level agreement of token ids with the fp32
+// oracle needs fp32 products and fp32 accumulation; see DESIGN.md "precision").
+//
+//   C[m,n] (op)= epi( sum_t sum_k pro(A[(m*a_row_step + tap_off[t])*lda + k]) * W[t][n][k] )
+//
+// One kernel covers: Linear layers, 1x1 convs, the DFT/mel matmuls (overlapping frame rows, lda = hop),
+// causal dense convs in channels-last layout (dilation 1 -> a single GEMM over k overlapping rows,
+// dilation > 1 -> one tap per kernel element), strided down-sampling convs (a_row_step = stride) and
+// transposed convs (N = stride*C_out).  Up to three same-shape problems run side by side (blockIdx.z):
+// the three ResBlock1 branches of a HiFi-GAN ParallelBlock.
+//
+// Tiling: BMxBN output tile per CTA, BK = 16, register micro-tiles of (4*MG)x(4*NG), global->register
+// prefetch of the next K-slab overlapped with the FMAs of the current one (double-buffered smem).
+#include "common.cuh"
+
+namespace svanon {
+
+namespace {
+
+constexpr int BK = 16;
+
+struct GemmBatch {
+  GemmParams p[3];
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+template <int BM, int BN, int MG, int NG>
+__global__ void __launch_bounds__((BM / (4 * MG)) * (BN / (4 * NG)))
+gemm_kernel(const GemmBatch batch) {
+  constexpr int TM = 4 * MG, TN = 4 * NG;
+  constexpr int NTX = BN / TN, NTY = BM / TM, NT = NTX * NTY;
+  constexpr int A_F4 = BM * BK / 4, B_F4 = BN * BK / 4;
+  constexpr int A_LD = (A_F4 + NT - 1) / NT, B_LD = (B_F4 + NT - 1) / NT;
+  constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+
+  const GemmParams& p = batch.p[blockIdx.z];
+  __shared__ __align__(16) float As[2][BK][LDA_S];
+  __shared__ __align__(16) float Bs[2][BK][LDB_S];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % NTX, ty = tid / NTX;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kIters = p.K / BK;
+  const int total = kIters * p.taps;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[A_LD], rb[B_LD];
+
+  auto load_tiles = [&](int it) {
+    const int t = it / kIters;
+    const int k0 = (it - t * kIters) * BK;
+    const long long off = p.tap_off[t];
+#pragma unroll
+    for (int l = 0; l < A_LD; ++l) {
+      const int i = tid + l * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A_F4 % NT == 0 || i < A_F4) {
+        const int row = i >> 2, kq = i & 3;
+        const int m = m0 + row;
+        if (m < p.M) {
+          const float* src = p.A + ((long long)m * p.a_row_step + off) * p.lda + k0 + kq * 4;
+          v = __ldg(reinterpret_cast<const float4*>(src));
+          if (p.prologue == PRO_SILU) {
+            v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+          }
+        }
+      }
+      ra[l] = v;
+    }
+#pragma unroll
+    for (int l = 0; l < B_LD; ++l) {
+      const int i = tid + l * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (B_F4 % NT == 0 || i < B_F4) {
+        const int row = i >> 2, kq = i & 3;
+        const int n = n0 + row;
+        if (n < p.N) {
+          const float* src = p.W + ((long long)t * p.N + n) * p.K + k0 + kq * 4;
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        }
+      }
+      rb[l] = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int l = 0; l < A_LD; ++l) {
+      const int i = tid + l * NT;
+      if (A_F4 % NT == 0 || i < A_F4) {
+        const int row = i >> 2, kq = i & 3;
+        As[buf][kq * 4 + 0][row] = ra[l].x;
+        As[buf][kq * 4 + 1][row] = ra[l].y;
+        As[buf][kq * 4 + 2][row] = ra[l].z;
+        As[buf][kq * 4 + 3][row] = ra[l].w;
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < B_LD; ++l) {
+      const int i = tid + l * NT;
+      if (B_F4 % NT == 0 || i < B_F4) {
+        const int row = i >> 2, kq = i & 3;
+        Bs[buf][kq * 4 + 0][row] = rb[l].x;
+        Bs[buf][kq * 4 + 1][row] = rb[l].y;
+        Bs[buf][kq * 4 + 2][row] = rb[l].z;
+        Bs[buf][kq * 4 + 3][row] = rb[l].w;
+      }
+    }
+  };
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+
+  for (int it = 0; it < total; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < total) load_tiles(it + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < MG; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][g * (BM / MG) + ty * 4]);
+        a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][g * (BN / NG) + tx * 4]);
+        b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (it + 1 < total) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---------------------------------------------------------------- epilogue
+#pragma unroll
+  for (int gi = 0; gi < MG; ++gi) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + gi * (BM / MG) + ty * 4 + i;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int gj = 0; gj < NG; ++gj) {
+        const int nb = n0 + gj * (BN / NG) + tx * 4;
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = nb + j;
+          float v = acc[gi * 4 + i][gj * 4 + j];
+          if (n < p.N) {
+            if (p.bias) v += __ldg(p.bias + n);
+            if (p.act == ACT_GELU) v = gelu_erf(v);
+            else if (p.act == ACT_LOGCLAMP) v = logf(fmaxf(v, 1e-5f));
+            if (p.gamma) v *= __ldg(p.gamma + n);
+            if (p.residual) v += __ldg(p.residual + (long long)m * p.ldr + n);
+            v *= p.out_scale;
+          }
+          y[j] = v;
+        }
+        float* dst = p.C + (long long)m * p.ldc + nb;
+        if (nb + 3 < p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          float4 o = make_float4(y[0], y[1], y[2], y[3]);
+          if (p.accumulate) {
+            const float4 c = *reinterpret_cast<const float4*>(dst);
+            o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+          }
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (nb + j < p.N) dst[j] = p.accumulate ? dst[j] + y[j] : y[j];
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int MG, int NG>
+void launch_cfg(const GemmBatch& b, int count, cudaStream_t st) {
+  constexpr int NT = (BM / (4 * MG)) * (BN / (4 * NG));
+  const GemmParams& p = b.p[0];
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, count);
+  gemm_kernel<BM, BN, MG, NG><<<grid, NT, 0, st>>>(b);
+}
+
+}  // namespace
+
+void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
+  SV_CHECK(count >= 1 && count <= 3, "gemm batch count");
+  GemmBatch b;
+  for (int i = 0; i < count; ++i) {
+    b.p[i] = ps[i];
+    SV_CHECK(ps[i].K % BK == 0 && ps[i].K > 0, "gemm K must be a positive multiple of 16");
+    SV_CHECK(ps[i].lda % 4 == 0, "gemm lda must be a multiple of 4");
+    SV_CHECK(ps[i].taps >= 1 && ps[i].taps <= MAX_TAPS, "gemm taps");
+    SV_CHECK(ps[i].M == ps[0].M && ps[i].N == ps[0].N, "batched gemm problems must share M and N");
+  }
+  for (int i = count; i < 3; ++i) b.p[i] = ps[0];
+  const GemmParams& p = ps[0];
+  if (p.M <= 0 || p.N <= 0) return;
+  auto ctas = [&](int bm, int bn) { return (long long)((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * count; };
+  if (p.N <= 16) {
+    launch_cfg<128, 16, 1, 1>(b, count, st);
+  } else if (p.N <= 32) {
+    launch_cfg<128, 32, 2, 1>(b, count, st);
+  } else if (p.N <= 64 && p.M >= 2048) {
+    launch_cfg<128, 64, 2, 1>(b, count, st);
+  } else if (ctas(128, 128) >= 2 * 148) {
+    launch_cfg<128, 128, 2, 2>(b, count, st);
+  } else if (ctas(64, 64) >= 148 || p.M > 32) {
+    launch_cfg<64, 64, 1, 1>(b, count, st);
+  } else {
+    launch_cfg<32, 64, 1, 1>(b, count, st);
+  }
+  SV_LAUNCHED();
+}
+
+}  // namespace svanon

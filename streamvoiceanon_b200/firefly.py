@@ -1,0 +1,162 @@
+"""Host-side mirrors of the two `FireflyArchitecture` objects the hot path touches.
+
+  ContentTokenizer  <-> modules.vqgan.modules.firefly_encoder.FireflyArchitecture  (only `encode`, :553-566)
+  Vocoder           <-> modules.vqgan.modules.firefly.FireflyArchitecture          (`quantizer.decode` + `head`)
+
+Constructor signatures follow the reference (`backbone, head, quantizer, spec_transform`, all ignored: the
+engine is compiled for the shipped YAMLs) so hydra instantiation keeps working.  Arithmetic is in
+libsvanon_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from .engine import Engine, ptr, rope_table, slaney_fbanks, _cuda_stream_ptr
+
+_IncompatibleKeys = namedtuple("_IncompatibleKeys", ["missing_keys", "unexpected_keys"])
+
+
+class _Shim:
+    training = False
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def half(self):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+
+class ContentTokenizer(_Shim):
+    _WANTED = ("backbone.", "quantizer.downsample.", "quantizer.pre_module.layers.", "quantizer.pre_module.norm.",
+               "quantizer.residual_bsq.rvqs.0.project_in.")
+
+    def __init__(self, backbone=None, head=None, quantizer=None, spec_transform=None, device=None):
+        self._engine = Engine.get(device)
+        self.downsample_factor = 4
+
+    def load_state_dict(self, sd, strict: bool = False):
+        eng = self._engine
+        unexpected = eng.load_state_dict(_lib.MODEL_TOKENIZER, sd, lambda k: k.startswith(self._WANTED))
+        # persistent buffer of the checkpoint when present, else rebuilt like the reference
+        fc = sd.get("quantizer.pre_module.freqs_cis")
+        eng.load_tensor(_lib.MODEL_TOKENIZER, "quantizer.pre_module.freqs_cis",
+                        fc.float() if fc is not None else rope_table(2048))
+        eng.load_tensor(_lib.MODEL_TOKENIZER, "spec_transform.fb", slaney_fbanks())
+        eng.finalize(_lib.MODEL_TOKENIZER)
+        unexpected = [k for k in unexpected if not k.startswith(("head.", "quantizer.post_module.", "quantizer.pre_module.",
+                                                                 "quantizer.residual_bsq."))]
+        return _IncompatibleKeys([], unexpected)
+
+    @torch.no_grad()
+    def encode(self, audios, audio_lengths):
+        """FireflyArchitecture.encode, firefly_encoder.py:553-566: wav [B,L] f32, lens [B] ->
+        (ids int64 [1,B,T], feature_lengths [B]).  Rows are encoded one by one; for a row shorter than L the
+        causal-prefix property makes ids[:len//2048] identical to the reference, later ids are 0."""
+        audios = audios.float()
+        B, L = audios.shape
+        dev = audios.device if audios.is_cuda else torch.device("cuda", self._engine.device)
+        T = _lib.load().svanon_enc_num_ids(L)
+        ids = torch.zeros(1, B, T, dtype=torch.int64, device=dev)
+        lens = [int(x) for x in audio_lengths.reshape(-1).tolist()]
+        for b in range(B):
+            n = min(lens[b], L)
+            row = audios[b, :n].contiguous()
+            tb = _lib.load().svanon_enc_num_ids(n)
+            if tb == 0:
+                continue
+            out = ids[0, b, :tb] if tb == T else torch.empty(tb, dtype=torch.int64, device=dev)
+            _lib.check(self._engine.lib.svanon_enc_encode(self._engine.handle, ptr(row), n, ptr(out),
+                                                          C.c_void_p(_cuda_stream_ptr())))
+            if tb != T:
+                ids[0, b, :tb] = out
+        feature_lengths = (audio_lengths // 512) // self.downsample_factor
+        return ids, feature_lengths
+
+
+class _Quantizer:
+    def __init__(self, owner):
+        self._o = owner
+        self.downsample_factor = (2, 2)
+
+    @torch.no_grad()
+    def decode(self, indices):
+        """DownsampleFiniteScalarQuantize.decode, fsq.py:112-116: [B,8,T] -> [B,512,4T] (a transposed view of the
+        engine's channels-last buffer, which `head` consumes without a copy)."""
+        eng = self._o._engine
+        B, G, T = indices.shape
+        assert G == 8
+        dev = indices.device if indices.is_cuda else torch.device("cuda", eng.device)
+        z = torch.empty(B, 4 * T, 512, dtype=torch.float32, device=dev)
+        for b in range(B):
+            codes = indices[b].to(torch.int64).contiguous()
+            _lib.check(eng.lib.svanon_voc_quantizer_decode(eng.handle, ptr(codes), T, ptr(z[b]),
+                                                           C.c_void_p(_cuda_stream_ptr())))
+        return z.transpose(1, 2)
+
+
+class _Head:
+    def __init__(self, owner):
+        self._o = owner
+
+    @torch.no_grad()
+    def __call__(self, z, template=None):
+        """HiFiGANGenerator.forward, firefly.py:280-293: [B,512,L] -> [B,1,512 L]."""
+        eng = self._o._engine
+        B, Cc, L = z.shape
+        assert Cc == 512
+        zl = z.transpose(1, 2)
+        if not zl.is_contiguous() or zl.dtype != torch.float32:
+            zl = zl.float().contiguous()
+        dev = zl.device if zl.is_cuda else torch.device("cuda", eng.device)
+        wave = torch.empty(B, 1, 512 * L, dtype=torch.float32, device=dev)
+        for b in range(B):
+            _lib.check(eng.lib.svanon_voc_head(eng.handle, ptr(zl[b]), L, ptr(wave[b]), C.c_void_p(_cuda_stream_ptr())))
+        return wave
+
+    forward = __call__
+
+
+class Vocoder(_Shim):
+    _WANTED = ("head.", "quantizer.upsample.", "quantizer.residual_fsq.rvqs.")
+
+    def __init__(self, backbone=None, head=None, quantizer=None, spec_transform=None, device=None):
+        self._engine = Engine.get(device)
+        self.quantizer = _Quantizer(self)
+        self.head = _Head(self)          # callers may rebind it (torch.compile, infer_arvc.py:128-134)
+        self.downsample_factor = 4
+
+    def load_state_dict(self, sd, strict: bool = False):
+        eng = self._engine
+
+        def wanted(k):
+            return k.startswith(self._WANTED) and "project_in" not in k
+        unexpected = eng.load_state_dict(_lib.MODEL_VOCODER, sd, wanted)
+        eng.finalize(_lib.MODEL_VOCODER)         # folds weight norm (remove_parametrizations, infer_arvc.py:94)
+        unexpected = [k for k in unexpected if not (k.startswith(("backbone.", "quantizer.downsample.")) or "project_in" in k)]
+        return _IncompatibleKeys([], unexpected)
+
+    def remove_parametrizations(self):
+        """firefly.py:597-602 -- weight norm is folded when the weights are finalized."""
+        return None
+
+    @torch.no_grad()
+    def decode_codes(self, codes):
+        """code2wav_fn (evaluations/infer_arvc.py:173-176) in one library call: [B,8,T] -> [B,1,2048 T]."""
+        eng = self._engine
+        B, G, T = codes.shape
+        dev = codes.device if codes.is_cuda else torch.device("cuda", eng.device)
+        wave = torch.empty(B, 1, 2048 * T, dtype=torch.float32, device=dev)
+        for b in range(B):
+            c = codes[b].to(torch.int64).contiguous()
+            _lib.check(eng.lib.svanon_voc_decode(eng.handle, ptr(c), T, ptr(wave[b]), C.c_void_p(_cuda_stream_ptr())))
+        return wave

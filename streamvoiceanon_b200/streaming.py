@@ -1,0 +1,106 @@
+"""The per-chunk loop (`InferenceWrapper.process_one_chunk`, evaluations/infer_arvc.py:492-596) as ONE
+library call per chunk: wave ring, E window, warm-up, A, re-prompt, V window, tail select all run
+stream-ordered inside `svanon_stream_process_chunk` with no host synchronisation until the result is
+copied out."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+from .engine import Engine, ptr, _cuda_stream_ptr
+
+
+class StreamSession:
+    def __init__(self, device=None, max_seq_len: int = 2048):
+        self._engine = Engine.get(device)
+        for m in (0, 1, 2):
+            if not self._engine.loaded[m]:
+                raise RuntimeError("load the AR, tokenizer and vocoder weights first (ARVCWrapper / ContentTokenizer / "
+                                   "Vocoder .load_state_dict)")
+        h = C.c_void_p()
+        _lib.check(self._engine.lib.svanon_stream_create(self._engine.handle, max_seq_len, C.byref(h)))
+        self._h = h
+        self.chunk = 1
+        self._noise_fn: Optional[Callable] = None
+        self._step = 0
+
+    def set_noise_fn(self, fn, step0: int = 0):
+        self._noise_fn, self._step = fn, step0
+
+    def set_sampling(self, temperature=0.7, top_p=0.7, seed=0):
+        _lib.check(self._engine.lib.svanon_ar_set_sampling(self._h, temperature, top_p, seed))
+
+    def set_prompt(self, ref_content_codes, ref_audio_codes, style_vectors, timbre_latents, max_prompt_frames=256, delay=2):
+        """Tail of InferenceWrapper.prefill_prompt (infer_arvc.py:468-489)."""
+        rc = ref_content_codes.reshape(-1).to(torch.int64).contiguous()
+        ra = ref_audio_codes.reshape(8, -1).to(torch.int32).contiguous()
+        sv = style_vectors.reshape(-1).float().contiguous()
+        tl = timbre_latents.reshape(32, 128).float().contiguous()
+        _lib.check(self._engine.lib.svanon_stream_set_prompt(self._h, ptr(rc), ptr(ra), rc.numel(), ptr(sv), ptr(tl),
+                                                             max_prompt_frames, delay, C.c_void_p(_cuda_stream_ptr())))
+        self.delay = delay
+        self._step += 1
+        self._n_src = 0
+        self._prefilled = False
+
+    def setup(self, encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32,
+              decode_chunk_frames=1):
+        """InferenceWrapper.setup_stream_caches (infer_arvc.py:443-460)."""
+        _lib.check(self._engine.lib.svanon_stream_setup(self._h, encode_window_frames, decode_window_frames,
+                                                        max_seq_frames, buffer_frames, decode_chunk_frames))
+        self.chunk = decode_chunk_frames
+        self.max_seq_frames = max_seq_frames
+        self._n_src = 0
+        self._prefilled = False
+
+    def _noise(self):
+        """Mirrors the oracle's step counter: one step per prefill / decode_one_token_ar call."""
+        self._n_src += self.chunk
+        if self._n_src < self.delay:
+            return None
+        if not self._prefilled and self.delay != 0:
+            self._prefilled = True
+            self._step += 1
+            return None
+        rows = []
+        for _ in range(self.chunk):
+            if self._noise_fn is not None:
+                rows.append(torch.stack([self._noise_fn(self._step, s, 1000)[:1000] for s in range(1, 9)]))
+            self._step += 1
+        pos = int(self._engine.lib.svanon_ar_position(self._h)) + 2 * self.chunk - 1
+        if pos // 2 >= self.max_seq_frames:
+            self._step += 2 if self.delay > 0 else 1          # re-prompt: prefill_prompt + prefill_delay
+        return torch.stack(rows).float().contiguous() if rows else None
+
+    def process_chunk(self, wave_chunk: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """InferenceWrapper.process_one_chunk (infer_arvc.py:492-596).  `wave_chunk` [chunk*2048] on the host or the
+        device; the result lands where `out` lives (default: same place as the input)."""
+        w = wave_chunk.reshape(-1).float().contiguous()
+        if out is None:
+            out = torch.empty_like(w)
+        noise = self._noise()
+        _lib.check(self._engine.lib.svanon_stream_process_chunk(self._h, ptr(w), w.numel(),
+                                                                ptr(noise) if noise is not None else None, ptr(out),
+                                                                C.c_void_p(_cuda_stream_ptr())))
+        return out
+
+    def history(self, cap: int = 4096):
+        src = torch.empty(cap, dtype=torch.int64)
+        pred = torch.empty(8 * cap, dtype=torch.int64)
+        ns, npred = C.c_int(0), C.c_int(0)
+        _lib.check(self._engine.lib.svanon_stream_history(self._h, ptr(src), C.byref(ns), ptr(pred), C.byref(npred), cap))
+        return src[: ns.value].clone(), pred[: 8 * npred.value].view(8, npred.value).clone()
+
+    def close(self):
+        if self._h is not None:
+            self._engine.lib.svanon_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-facing shims) against
+ (1) the golden fixtures produced by the UNMODIFIED reference (tests/golden, oracle/make_golden.py), and
+ (2) the CPU oracle on the same seeded inputs.
+Bar: bit-exact for every integer output (BSQ content ids, codec ids, positions); floating point within the
+tolerance written beside each check (fp32 on both sides; only summation order / libm differ)."""
+import numpy as np
+import pytest
+import torch
+
+from streamvoiceanon_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+WAVE_MSE_TOL = 1e-8          # fp32 waveform MSE tolerance
+LOGIT_TOL = 2e-3             # max-abs error of teacher-forced logits (values are O(3))
+
+
+@pytest.fixture(scope="module")
+def models(weights):
+    from streamvoiceanon_b200 import ARVCWrapper, ContentTokenizer, Vocoder
+    ar = ARVCWrapper()
+    ar.setup_caches(max_batch_size=1, max_seq_len=2048, dtype=torch.float16)
+    ar.load_state_dict(weights["ar"], strict=False)
+    tok = ContentTokenizer()
+    tok.load_state_dict(weights["tok"], strict=False)
+    voc = Vocoder()
+    voc.load_state_dict(weights["voc"], strict=False)       # weight-norm form, folded by the library
+    voc.remove_parametrizations()
+    return ar, tok, voc
+
+
+def test_native_library_is_loaded(models):
+    import os
+    maps = open(f"/proc/{os.getpid()}/maps").read()
+    assert "libsvanon_b200.so" in maps
+    from streamvoiceanon_b200 import _lib
+    assert _lib.kernel_launches() >= 0
+
+
+# ------------------------------------------------------------------------------------------------ E
+def test_encoder_40_frames_vs_reference(models, gold):
+    _, tok, _ = models
+    g = gold("encoder_40f")
+    wav = synth.synth_audio_44k(int(g["audio_seed"]), 2.0)[: int(g["n_samples"])][None]
+    ids, flen = tok.encode(wav.cuda(), torch.LongTensor([wav.shape[1]]).cuda())
+    assert int(flen[0]) == 40
+    assert np.array_equal(ids.cpu().numpy(), g["ids"])
+
+
+def test_encoder_host_buffers(models, gold):
+    """Same call with HOST tensors: the C ABI stages them itself."""
+    _, tok, _ = models
+    g = gold("encoder_40f")
+    wav = synth.synth_audio_44k(int(g["audio_seed"]), 2.0)[: int(g["n_samples"])][None]
+    ids, _ = tok.encode(wav, torch.LongTensor([wav.shape[1]]))
+    assert np.array_equal(ids.cpu().numpy(), g["ids"])
+
+
+def test_encoder_streaming_window_vs_reference(models, gold):
+    _, tok, _ = models
+    g = gold("encoder_window128")
+    live = int(g["live_frames"])
+    win = torch.zeros(1, 128 * 2048)
+    win[:, -live * 2048:] = synth.synth_audio_44k(int(g["audio_seed"]), 2.0)[: live * 2048]
+    ids, _ = tok.encode(win.cuda(), torch.LongTensor([win.shape[1]]).cuda())
+    assert np.array_equal(ids.cpu().numpy(), g["ids"])
+
+
+def test_encoder_vs_oracle_other_inputs(models, weights):
+    """Seeds and lengths the fixtures do not cover, incl. ragged lengths and the one-frame minimum."""
+    from oracle import content_encoder as E
+    _, tok, _ = models
+    for seed, n in ((2001, 2048), (2002, 13 * 2048 + 700), (2003, 61 * 2048)):
+        wav = synth.synth_audio_44k(seed, 3.0)[:n][None]
+        with torch.no_grad():
+            ref, _ = E.encode(wav, weights["tok"])
+        ids, _ = tok.encode(wav.cuda(), torch.LongTensor([n]).cuda())
+        assert np.array_equal(ids.cpu().numpy(), ref.numpy()), (seed, n)
+
+
+def test_encoder_prefix_causality(models):
+    """Property (size-independent): ids of x[:N] are the first N ids of x."""
+    _, tok, _ = models
+    wav = synth.synth_audio_44k(2004, 3.0)[: 60 * 2048][None].cuda()
+    full, _ = tok.encode(wav, torch.LongTensor([wav.shape[1]]).cuda())
+    part, _ = tok.encode(wav[:, : 33 * 2048].contiguous(), torch.LongTensor([33 * 2048]).cuda())
+    assert torch.equal(full[0, 0, :33], part[0, 0])
+
+
+def test_encoder_rejects_too_short(models):
+    _, tok, _ = models
+    ids, _ = tok.encode(torch.zeros(1, 1000).cuda(), torch.LongTensor([1000]).cuda())
+    assert ids.shape[-1] == 0
+
+
+# ------------------------------------------------------------------------------------------------ V
+def test_vocoder_vs_reference(models, gold):
+    _, _, voc = models
+    g = gold("vocoder_20f")
+    codes = torch.from_numpy(g["codes"]).cuda()
+    z = voc.quantizer.decode(codes)
+    assert z.shape == (1, 512, 80)
+    assert np.abs(z[0, :, -8:].cpu().numpy() - g["z_tail"]).max() < 1e-4
+    wave = voc.head(z)
+    assert wave.shape == (1, 1, 20 * 2048)
+    mse = float(((wave[0, 0].cpu().numpy() - g["wave"]) ** 2).mean())
+    assert mse < WAVE_MSE_TOL, mse
+    fused = voc.decode_codes(codes)
+    assert torch.equal(fused, wave)
+
+
+def test_vocoder_vs_oracle_and_causality(models, weights):
+    from oracle import vocoder as V
+    _, _, voc = models
+    g = torch.Generator().manual_seed(77)
+    codes = torch.randint(0, 1000, (1, 8, 9), generator=g)
+    with torch.no_grad():
+        ref = V.code2wav(codes, weights["voc_folded"])
+    wave = voc.decode_codes(codes.cuda())
+    assert float(((wave.cpu() - ref) ** 2).mean()) < WAVE_MSE_TOL
+    # strict causality: changing the last frame leaves every earlier sample bit-identical
+    codes2 = codes.clone()
+    codes2[:, :, -1] = (codes2[:, :, -1] + 17) % 1000
+    wave2 = voc.decode_codes(codes2.cuda())
+    assert torch.equal(wave[..., : 8 * 2048], wave2[..., : 8 * 2048])
+    assert not torch.equal(wave[..., 8 * 2048:], wave2[..., 8 * 2048:])
+
+
+def test_vocoder_window_receptive_field(models):
+    """the last frame depends on the last 16 code frames only, so a 16-frame window
+    reproduces the tail of a 64-frame window (the property the stateful design relies on)."""
+    _, _, voc = models
+    g = torch.Generator().manual_seed(78)
+    codes = torch.randint(0, 1000, (1, 8, 64), generator=g).cuda()
+    w64 = voc.decode_codes(codes)[..., -2048:]
+    w16 = voc.decode_codes(codes[:, :, -16:].contiguous())[..., -2048:]
+    assert float(((w64 - w16) ** 2).mean()) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ A
+def _prefill(ar, s, tape):
+    style, timbre = synth.synth_speaker(int(s["spk_seed"]))
+    ar.set_delay(delay=int(s["delay"]))
+    ar.set_noise_fn(tape(int(s["tape_seed"])), 0)
+    ar.prefill_prompt(torch.from_numpy(s["ref_content"]).cuda(), torch.from_numpy(s["ref_audio"]).cuda(),
+                      style.cuda(), timbre.cuda())
+    return torch.from_numpy(s["src_content"])
+
+
+def test_ar_streaming_codes_vs_reference(models, gold, tape):
+    ar, _, _ = models
+    s = gold("ar_stream")
+    src = _prefill(ar, s, tape)
+    ar.prefill_src_condition4delay(src[:, :2].cuda())
+    for i, t in enumerate(range(2, 16)):
+        codes, pos = ar.decode_one(src[:, t:t + 1].cuda())
+        assert codes.dtype == torch.int32 and tuple(codes.shape) == (8, 1)
+        assert np.array_equal(codes.cpu().numpy(), s["codes"][i]), (i, codes.T.tolist(), s["codes"][i].T.tolist())
+        assert int(pos) == int(s["pos"][i])
+
+
+def test_ar_teacher_forced_logits_vs_reference(models, gold, tape):
+    ar, _, _ = models
+    s, g = gold("ar_stream"), gold("ar_logits")
+    src = _prefill(ar, s, tape)
+    ar.prefill_src_condition4delay(src[:, :2].cuda())
+    ar.debug_logits(True)
+    try:
+        codes, _ = ar.decode_one(src[:, 2:3].cuda())
+        slow, hidden, fast = ar.read_debug()
+    finally:
+        ar.debug_logits(False)
+    assert np.abs(hidden.numpy() - g["hidden"]).max() < LOGIT_TOL
+    assert np.abs(slow.numpy() - g["slow_logits"]).max() < LOGIT_TOL
+    assert np.abs(fast.numpy() - g["fast_logits"]).max() < LOGIT_TOL
+    assert np.array_equal(codes.cpu().numpy(), g["codes"])
+
+
+def test_ar_offline_generate_vs_reference(models, gold, tape):
+    ar, _, _ = models
+    s, g = gold("ar_stream"), gold("ar_generate")
+    style, timbre = synth.synth_speaker(int(s["spk_seed"]))
+    ar.set_delay(delay=2)
+    ar.set_noise_fn(tape(int(s["tape_seed"])), 0)
+    out = ar.generate(torch.from_numpy(s["ref_content"]).cuda(), torch.from_numpy(s["ref_audio"]).cuda(),
+                      torch.from_numpy(s["src_content"])[:, :10].cuda(), style.cuda(), timbre.cuda())
+    assert np.array_equal(out.cpu().numpy(), g["codes"])
+
+
+def test_ar_vs_oracle_long_prompt_other_delay(models, weights, tape):
+    """A longer prompt (S_valid ~ 400), delay 4, different tape: 10 frames bit-exact vs the oracle."""
+    from oracle.dual_ar import DualAR
+    ar, _, _ = models
+    g = torch.Generator().manual_seed(555)
+    T = 180
+    ref_content = torch.randint(0, 8192, (1, T), generator=g)
+    ref_audio = torch.randint(0, 1000, (1, 8, T), generator=g).int()
+    src = torch.randint(0, 8192, (1, 14), generator=g)
+    style, timbre = synth.synth_speaker(5003)
+    orc = DualAR(weights["ar"], tape(7100))
+    with torch.no_grad():
+        orc.set_delay(4)
+        orc.prefill_prompt(ref_content, ref_audio, style, timbre)
+        orc.prefill_src_condition4delay(src[:, :4])
+        want = [orc.decode_one(src[:, t:t + 1]) for t in range(4, 14)]
+    ar.set_delay(delay=4)
+    ar.set_noise_fn(tape(7100), 0)
+    ar.prefill_prompt(ref_content.cuda(), ref_audio.cuda(), style.cuda(), timbre.cuda())
+    ar.prefill_src_condition4delay(src[:, :4].cuda())
+    for i, t in enumerate(range(4, 14)):
+        codes, pos = ar.decode_one(src[:, t:t + 1].cuda())
+        assert np.array_equal(codes.cpu().numpy(), want[i][0].numpy()), i
+        assert int(pos) == int(want[i][1])
+
+
+def test_ar_batched_streams_match_single_stream(models, weights, tape):
+    """Engine-only property (the reference is batch-1): stream i of a 2-stream launch == stream i alone."""
+    import ctypes as C
+    from streamvoiceanon_b200 import ARVCWrapper, _lib
+    from streamvoiceanon_b200.engine import ptr
+    ar0, _, _ = models
+    g = torch.Generator().manual_seed(900)
+    prompts = []
+    for b, T in enumerate((20, 37)):
+        prompts.append((torch.randint(0, 8192, (1, T), generator=g), torch.randint(0, 1000, (1, 8, T), generator=g).int(),
+                        torch.randint(0, 8192, (1, 8), generator=g), synth.synth_speaker(6000 + b)))
+    singles = []
+    for b, (rc, ra, src, (style, timbre)) in enumerate(prompts):
+        ar0.set_delay(delay=2)
+        ar0.set_noise_fn(tape(7200 + b), 0)
+        ar0.prefill_prompt(rc.cuda(), ra.cuda(), style.cuda(), timbre.cuda())
+        ar0.prefill_src_condition4delay(src[:, :2].cuda())
+        singles.append([ar0.decode_one(src[:, t:t + 1].cuda())[0].cpu() for t in range(2, 8)])
+    wrappers = []
+    for b, (rc, ra, src, (style, timbre)) in enumerate(prompts):
+        w = ARVCWrapper()
+        w.setup_caches(max_batch_size=1, max_seq_len=2048)
+        w.set_delay(delay=2)
+        w.prefill_prompt(rc.cuda(), ra.cuda(), style.cuda(), timbre.cuda())
+        w.prefill_src_condition4delay(src[:, :2].cuda())
+        wrappers.append(w)
+    lib = _lib.load()
+    handles = (C.c_void_p * 2)(wrappers[0]._stream, wrappers[1]._stream)
+    for i, t in enumerate(range(2, 8)):
+        ids = torch.tensor([int(prompts[0][2][0, t]), int(prompts[1][2][0, t])], dtype=torch.int64).cuda()
+        noise = torch.stack([torch.stack([tape(7200 + b)(2 + i, s, 1000)[:1000] for s in range(1, 9)]) for b in range(2)])
+        noise = noise.float().contiguous().cuda()
+        out = torch.empty(2, 8, dtype=torch.int32, device="cuda")
+        _lib.check(lib.svanon_ar_decode_batch(handles, 2, ptr(ids), ptr(noise), ptr(out), None))
+        for b in range(2):
+            assert torch.equal(out[b].cpu(), singles[b][i][:, 0]), (b, i)
+
+
+def test_ar_errors(models):
+    ar, _, _ = models
+    with pytest.raises(AssertionError):
+        ar.set_delay(delay=2)
+        ar.prefill_src_condition4delay(torch.zeros(1, 5, dtype=torch.long).cuda())     # != delay (dual_ar_stream.py:805)
+    with pytest.raises(ValueError):
+        ar.setup_caches(max_batch_size=2, max_seq_len=2048)
+
+
+# ------------------------------------------------------------------------------------------------ loop
+def _run_loop(models, weights, g, tape, host_io):
+    from streamvoiceanon_b200 import StreamSession
+    _, tok, _ = models
+    n_ref, n_chunks = int(g["n_ref"]), int(g["n_chunks"])
+    style, timbre = synth.synth_speaker(int(g["ref_seed"]))
+    ref_wave = synth.synth_audio_44k(int(g["ref_seed"]), 3.5)[: n_ref * 2048][None]
+    gen = torch.Generator().manual_seed(int(g["codes_seed"]))
+    ref_audio = torch.randint(0, 1000, (1, 8, n_ref), generator=gen).int()
+    ref_content, _ = tok.encode(ref_wave.cuda(), torch.LongTensor([ref_wave.shape[1]]).cuda())
+    assert np.array_equal(ref_content[0].cpu().numpy(), g["ref_content"])
+    sess = StreamSession()
+    sess.set_noise_fn(tape(int(g["tape_seed"])), 0)
+    sess.set_prompt(ref_content[0].cuda(), ref_audio.cuda(), style.cuda(), timbre.cuda(), max_prompt_frames=256,
+                    delay=int(g["delay"]))
+    sess.setup(int(g["encode_window_frames"]), int(g["decode_window_frames"]), int(g["max_seq_frames"]),
+               int(g["buffer_frames"]), 1)
+    src = synth.synth_audio_44k(int(g["src_seed"]), 1.5)[: n_chunks * 2048].view(n_chunks, 2048)
+    waves = []
+    for i in range(n_chunks):
+        chunk = src[i] if host_io else src[i].cuda()
+        waves.append(sess.process_chunk(chunk).cpu())
+    src_hist, pred_hist = sess.history()
+    sess.close()
+    return src_hist, pred_hist, torch.cat(waves)
+
+
+@pytest.mark.parametrize("name,host_io", [("stream_reprompt", False), ("stream_default", True)])
+def test_stream_loop_vs_reference(models, weights, gold, tape, name, host_io):
+    """The whole per-chunk loop against the UNMODIFIED reference's process_one_chunk: content ids and codec ids
+    bit-exact, waveform within the fp32 MSE tolerance.  `stream_default` = CLI defaults (windows 128/64) with
+    HOST buffers through the C ABI; `stream_reprompt` = small windows with the re-prompt path firing."""
+    g = gold(name)
+    src_hist, pred_hist, wave = _run_loop(models, weights, g, tape, host_io)
+    assert np.array_equal(src_hist.numpy()[None], g["src_content"])
+    assert np.array_equal(pred_hist.numpy()[None], g["pred_codes"])
+    mse = float(((wave.numpy() - g["wave"]) ** 2).mean())
+    assert mse < WAVE_MSE_TOL, mse
