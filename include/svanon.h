@@ -124,6 +124,15 @@ int svanon_stream_setup(svanon_stream* s, int encode_window_frames, int decode_w
                         int buffer_frames, int decode_chunk_frames);
 int svanon_stream_process_chunk(svanon_stream* s, const float* wave_chunk, int n_samples, const float* noise,
                                 float* wave_out, void* cuda_stream);
+/* vocoder evaluation inside the loop: 1 (default) = incremental -- only the new frames are computed, every causal
+ * conv reads its left context from per-stream history (equal to the window recompute whenever the window leaves
+ * >= 15 frames of history); 0 = recompute decode_window_frames frames per chunk exactly like
+ * the reference does.  Call before the first chunk. */
+int svanon_stream_set_vocoder_mode(svanon_stream* s, int incremental);
+/* per-stage device time (CUDA events on the launching stream) of the last non-warm-up chunk:
+ * ms[0] = E (window encode), ms[1] = A (decode steps), ms[2] = V (vocoder) */
+int svanon_stream_set_timing(svanon_stream* s, int enable);
+int svanon_stream_last_timing(svanon_stream* s, float* ms);
 /* copies of the loop's histories (host pointers): src_content_codes [<= cap] and pred_codes [8][n] (int64) */
 int svanon_stream_history(svanon_stream* s, int64_t* src_content, int* n_src, int64_t* pred_codes, int* n_pred,
                           int cap);

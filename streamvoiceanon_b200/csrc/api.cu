@@ -443,6 +443,10 @@ int svanon_stream_setup(svanon_stream* sh, int enc_win, int dec_win, int max_seq
     s.codes_win_dev = dmalloc<long long>((size_t)8 * dec_win);
     s.wave_win_dev = dmalloc<float>((size_t)dec_win * SAMPLES_PER_FRAME);
     s.n_src = 0; s.n_pred = 0; s.delay_prefilled = false;
+    // incremental vocoder when the window leaves >= 15 frames of history in front of the new chunk
+    s.voc_incremental = s.voc_mode != 0 && (dec_win - chunk >= 15) && (std::min(dec_win - chunk, 24) / chunk * chunk >= 15);
+    s.voc_fed = 0;
+    if (s.voc_incremental) s.eng->voc_state_init(s.voc, chunk);
   });
 }
 
@@ -467,7 +471,10 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
     SV_CUDA(cudaMemcpyAsync(s.wave_ring_tmp + (nw - n), wc, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     std::swap(s.wave_ring, s.wave_ring_tmp);
     // 2. E: re-encode the whole window, keep the last `chunk` ids (:505-518)
+    s.ev_valid = false;
+    if (s.timing) SV_CUDA(cudaEventRecord(s.ev[0], st));
     e.enc_encode(s.wave_ring, (long long)nw, s.ids_win_dev, st);
+    if (s.timing) SV_CUDA(cudaEventRecord(s.ev[1], st));
     if (s.n_src + s.chunk > HIST_CAP) {
       const int keep = HIST_CAP / 2;
       long long* tmp = (long long*)e.ws.base;
@@ -493,6 +500,7 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
     }
     // 5. A: `chunk` decode steps (:534-538)
     decode_frames(s, s.src_hist + (s.n_src - s.chunk), s.chunk, nz, st);
+    if (s.timing) SV_CUDA(cudaEventRecord(s.ev[2], st));
     const int current_pos = s.pos_next - 1;
     // 6. re-prompt (:547-564)
     if (current_pos / 2 >= s.max_seq_frames) {
@@ -510,17 +518,79 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
       e.ar_prefill_prompt(s, ext_content, ext_audio, Tn, s.style_dev, s.timbre_dev, st);
       if (s.delay > 0) e.ar_prefill_delay(s, s.src_hist + (s.n_src - s.delay), s.delay, st);
     }
-    // 7. V on the last decode_window_frames frames, left-padded with the prompt's tail (:567-583)
+    // 7. V.  Reference: vocoder over the last decode_window_frames frames, left-padded with the prompt's tail,
+    //    keep the last chunk (:567-583,596).  With >= 15 frames of true history the incremental vocoder produces
+    //    the same samples from the `chunk` new frames only (voc_stream.cu); smaller windows are recomputed.
     const int have = std::min(s.n_pred, s.dec_win);
     const int pad = s.dec_win - have;
     SV_CHECK(pad <= s.ref_frames, "prompt shorter than the vocoder window padding needs (the reference fails here too)");
-    launch_concat_cols(s.ref_audio_dev + (s.ref_frames - pad), s.ref_frames, pad, s.pred_hist + (s.n_pred - have),
-                       HIST_CAP, have, s.codes_win_dev, s.dec_win, 8, true, st);
-    e.voc_decode(s.codes_win_dev, s.dec_win, s.dec_win, s.wave_win_dev, st);
-    // 8. tail select (:596)
-    SV_CUDA(cudaMemcpyAsync(out, s.wave_win_dev + ((size_t)s.dec_win * SAMPLES_PER_FRAME - n), (size_t)n * sizeof(float),
-                            cudaMemcpyDeviceToDevice, st));
+    if (s.voc_incremental) {
+      const int c = s.chunk;
+      if (s.voc_fed == 0) {
+        // prime with the newest prompt frames the reference would have put in front of the first window
+        const int k = std::min(pad, 24) / c * c;
+        SV_CHECK(k >= 15, "internal: not enough padding frames to prime the incremental vocoder");
+        for (int f = 0; f < k; f += c) {
+          launch_concat_cols(s.ref_audio_dev + (s.ref_frames - k + f), s.ref_frames, c, s.pred_hist, HIST_CAP, 0,
+                             s.codes_win_dev, c, 8, true, st);
+          e.voc_step(s.voc, s.codes_win_dev, c, s.wave_win_dev, st);
+        }
+      }
+      launch_concat_cols(s.pred_hist + (s.n_pred - c), HIST_CAP, c, s.pred_hist, HIST_CAP, 0, s.codes_win_dev, c, 8, true, st);
+      if (s.timing) SV_CUDA(cudaEventRecord(s.ev[3], st));
+      e.voc_step(s.voc, s.codes_win_dev, c, out, st);
+      if (s.timing) { SV_CUDA(cudaEventRecord(s.ev[4], st)); s.ev_valid = true; }
+      s.voc_fed += c;
+    } else {
+      launch_concat_cols(s.ref_audio_dev + (s.ref_frames - pad), s.ref_frames, pad, s.pred_hist + (s.n_pred - have),
+                         HIST_CAP, have, s.codes_win_dev, s.dec_win, 8, true, st);
+      if (s.timing) SV_CUDA(cudaEventRecord(s.ev[3], st));
+      e.voc_decode(s.codes_win_dev, s.dec_win, s.dec_win, s.wave_win_dev, st);
+      if (s.timing) { SV_CUDA(cudaEventRecord(s.ev[4], st)); s.ev_valid = true; }
+      // 8. tail select (:596)
+      SV_CUDA(cudaMemcpyAsync(out, s.wave_win_dev + ((size_t)s.dec_win * SAMPLES_PER_FRAME - n), (size_t)n * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+    }
     a.finish();
+  });
+}
+
+int svanon_stream_set_vocoder_mode(svanon_stream* sh, int incremental) {
+  return guarded([&] {
+    SV_CHECK(sh, "null stream");
+    SV_CHECK(sh->st.enc_win == 0 || sh->st.n_pred == 0, "set the vocoder mode before streaming starts");
+    sh->st.voc_mode = incremental ? 1 : 0;
+    if (sh->st.enc_win > 0) {
+      Stream& s = sh->st;
+      s.voc_incremental = s.voc_mode != 0 && (s.dec_win - s.chunk >= 15) &&
+                          (std::min(s.dec_win - s.chunk, 24) / s.chunk * s.chunk >= 15);
+      if (s.voc_incremental && !s.voc.arena) s.eng->voc_state_init(s.voc, s.chunk);
+    }
+  });
+}
+
+int svanon_stream_set_timing(svanon_stream* sh, int enable) {
+  return guarded([&] {
+    SV_CHECK(sh, "null stream");
+    Stream& s = sh->st;
+    SV_CUDA(cudaSetDevice(s.eng->device));
+    if (enable)
+      for (auto& e : s.ev)
+        if (!e) SV_CUDA(cudaEventCreate(&e));
+    s.timing = enable != 0;
+    s.ev_valid = false;
+  });
+}
+
+int svanon_stream_last_timing(svanon_stream* sh, float* ms) {
+  return guarded([&] {
+    SV_CHECK(sh && ms, "null argument");
+    Stream& s = sh->st;
+    SV_CHECK(s.timing && s.ev_valid, "no timed chunk available (enable timing, then process a non-warm-up chunk)");
+    SV_CUDA(cudaEventSynchronize(s.ev[4]));
+    SV_CUDA(cudaEventElapsedTime(&ms[0], s.ev[0], s.ev[1]));
+    SV_CUDA(cudaEventElapsedTime(&ms[1], s.ev[1], s.ev[2]));
+    SV_CUDA(cudaEventElapsedTime(&ms[2], s.ev[3], s.ev[4]));
   });
 }
 

@@ -35,6 +35,8 @@ Stream::~Stream() {
                   (void*)src_hist, (void*)pred_hist, (void*)ref_content_dev, (void*)ref_audio_dev, (void*)style_dev,
                   (void*)timbre_dev, (void*)ids_win_dev, (void*)codes_win_dev, (void*)wave_win_dev})
     if (p) cudaFree(p);
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
 }
 
 Engine::~Engine() {
@@ -391,7 +393,7 @@ void Engine::finalize_vocoder() {
 // ------------------------------------------------------------------------------------------ ConvNeXt block
 // ConvNeXtBlock.forward (firefly.py:421-440), channels-last, in place on x (x has >= 6 zero/history rows
 // before row 0).  tmp [rows][C], hid [rows][4C].
-void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float* hid, cudaStream_t st) {
+void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out) {
   const int C = cw.C;
   launch_dwconv7_ln(x, tmp, cw.dw_w, cw.dw_b, cw.ln_w, cw.ln_b, rows, C, 1e-6f, st);
   GemmParams p1;
@@ -399,7 +401,7 @@ void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float
   p1.lda = C; p1.ldc = 4 * C; p1.act = ACT_GELU;
   launch_gemm(p1, st);
   GemmParams p2;
-  p2.A = hid; p2.W = cw.pw2_w; p2.C = x; p2.bias = cw.pw2_b; p2.gamma = cw.gamma; p2.residual = x;
+  p2.A = hid; p2.W = cw.pw2_w; p2.C = out ? out : x; p2.bias = cw.pw2_b; p2.gamma = cw.gamma; p2.residual = x;
   p2.M = rows; p2.N = C; p2.K = 4 * C; p2.lda = 4 * C; p2.ldc = C; p2.ldr = C;
   launch_gemm(p2, st);
 

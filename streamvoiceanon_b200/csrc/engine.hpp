@@ -52,6 +52,39 @@ struct ResConvW {
 
 struct Engine;
 
+// A channels-last activation buffer that keeps `margin` rows of history in front of the `rows` new rows of a
+// step: [margin + rows][C].  After every step the newest `margin` rows are moved to the front.
+struct SBuf {
+  float* base = nullptr;
+  int margin = 0, rows = 0, C = 0;
+  float* data() const { return base + (long long)margin * C; }
+};
+
+struct ShiftDesc {
+  float* base;
+  int margin_floats;
+  int shift_floats;
+};
+
+// Persistent state of the incremental vocoder for one stream (with >= 15 frames of true
+// history the per-frame result equals the reference's 64-frame window recompute).
+struct VocState {
+  int c = 0;                    // code frames per step
+  float* arena = nullptr;
+  size_t arena_floats = 0;
+  SBuf u1, u2, p0, c0;
+  struct Level {
+    SBuf x;                     // transposed-conv output, read by conv1 of iteration 0 of all branches
+    SBuf t[3][3];               // conv1 outputs  [branch][iteration]
+    SBuf r[3][2];               // residual stream after iterations 0 and 1 [branch][iteration]
+    SBuf next;                  // ParallelBlock mean = next level's (or conv_post's) input
+  } lv[5];
+  ShiftDesc* desc_dev = nullptr;
+  int n_desc = 0;
+  int primed_frames = 0;
+  ~VocState();
+};
+
 constexpr int HIST_CAP = 4096;     // columns kept of src_content_codes / pred_codes (the reference trims to 2048)
 
 struct Stream {
@@ -88,6 +121,14 @@ struct Stream {
   long long* ids_win_dev = nullptr;       // [enc_win]
   long long* codes_win_dev = nullptr;     // [8][dec_win]
   float* wave_win_dev = nullptr;          // [dec_win*2048]
+  VocState voc;                           // incremental vocoder state (used when dec_win >= 16)
+  int voc_mode = 1;                       // 1: incremental when possible, 0: always recompute the window
+  bool voc_incremental = false;
+  int voc_fed = 0;                        // pred frames already pushed through the incremental vocoder
+  // optional per-stage device timing of the last processed chunk (bench.py): events E0,E1=A0,A1,V0,V1
+  bool timing = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
   ~Stream();
 };
 
@@ -148,7 +189,12 @@ struct Engine {
   void voc_quantizer_decode(const long long* codes_dev, long long ld, int T, float* z_dev /*[4T][512]*/, cudaStream_t st);
   void voc_head(const float* z_dev /*[L][512]*/, int L, float* wave_dev /*[512 L]*/, cudaStream_t st);
   void voc_decode(const long long* codes_dev, long long ld, int T, float* wave_dev, cudaStream_t st);
-  void convnext(const ConvNextW& w, float* x, int rows, float* tmp, float* hid, cudaStream_t st);
+  // out == nullptr: in place on x
+  void convnext(const ConvNextW& w, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out = nullptr);
+  // stateful (incremental) vocoder, voc_stream.cu
+  void voc_state_init(VocState& vs, int frames_per_step);
+  void voc_state_reset(VocState& vs, cudaStream_t st);
+  void voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st);
 
   // AR
   void ar_forward_tokens(Stream& s, float* x /*[M][768]*/, int M, int pos0, cudaStream_t st);

@@ -6,12 +6,24 @@
 // One kernel covers: Linear layers, 1x1 convs, the DFT/mel matmuls (overlapping frame rows, lda = hop),
 // causal dense convs in channels-last layout (dilation 1 -> a single GEMM over k overlapping rows,
 // dilation > 1 -> one tap per kernel element), strided down-sampling convs (a_row_step = stride) and
-// transposed convs (N = stride*C_out).  Up to three same-shape problems run side by side (blockIdx.z):
-// the three ResBlock1 branches of a HiFi-GAN ParallelBlock.
+// transposed convs (N = stride*C_out).  Up to three same-shape problems run side by side (the three
+// ResBlock1 branches of a HiFi-GAN ParallelBlock).
 //
 // Tiling: BMxBN output tile per CTA, BK = 16, register micro-tiles of (4*MG)x(4*NG), global->register
 // prefetch of the next K-slab overlapped with the FMAs of the current one (double-buffered smem).
+//
+// Small problems (the per-frame stateful vocoder, the 512-row encoder window) would leave most of the 148 SMs
+// idle, so the K loop can be split over a thread-block CLUSTER of S CTAs (S <= 8): every CTA accumulates its
+// K-slice in registers, parks the partial tile in its own shared memory, and the cluster's rank-0 CTA sums the
+// partials in fixed rank order through distributed shared memory before running the epilogue -- one launch, no
+// global scratch, deterministic summation order.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace svanon {
 
@@ -21,12 +33,13 @@ constexpr int BK = 16;
 
 struct GemmBatch {
   GemmParams p[3];
+  int split;   // cluster size along z (1 = no split-K)
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
-template <int BM, int BN, int MG, int NG>
+template <int BM, int BN, int MG, int NG, bool SPLIT>
 __global__ void __launch_bounds__((BM / (4 * MG)) * (BN / (4 * NG)))
 gemm_kernel(const GemmBatch batch) {
   constexpr int TM = 4 * MG, TN = 4 * NG;
@@ -34,16 +47,24 @@ gemm_kernel(const GemmBatch batch) {
   constexpr int A_F4 = BM * BK / 4, B_F4 = BN * BK / 4;
   constexpr int A_LD = (A_F4 + NT - 1) / NT, B_LD = (B_F4 + NT - 1) / NT;
   constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+  constexpr int SMEM_FLOATS = 2 * BK * (LDA_S + LDB_S);
+  static_assert(!SPLIT || BM * BN <= SMEM_FLOATS, "partial tile must fit the staging shared memory");
 
-  const GemmParams& p = batch.p[blockIdx.z];
-  __shared__ __align__(16) float As[2][BK][LDA_S];
-  __shared__ __align__(16) float Bs[2][BK][LDB_S];
+  const int split = SPLIT ? batch.split : 1;
+  const int zb = SPLIT ? blockIdx.z / split : blockIdx.z;       // problem index
+  const int rank = SPLIT ? blockIdx.z % split : 0;              // == cluster rank (cluster dims (1,1,split))
+  const GemmParams& p = batch.p[zb];
+  __shared__ __align__(16) float smem[SMEM_FLOATS];
+  float (*As)[BK][LDA_S] = reinterpret_cast<float (*)[BK][LDA_S]>(smem);
+  float (*Bs)[BK][LDB_S] = reinterpret_cast<float (*)[BK][LDB_S]>(smem + 2 * BK * LDA_S);
 
   const int tid = threadIdx.x;
   const int tx = tid % NTX, ty = tid / NTX;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kIters = p.K / BK;
   const int total = kIters * p.taps;
+  const int it_begin = (int)((long long)total * rank / split);
+  const int it_end = (int)((long long)total * (rank + 1) / split);
 
   float acc[TM][TN];
 #pragma unroll
@@ -114,35 +135,60 @@ gemm_kernel(const GemmBatch batch) {
     }
   };
 
-  load_tiles(0);
-  store_tiles(0);
-  __syncthreads();
+  if (it_begin < it_end) {
+    load_tiles(it_begin);
+    store_tiles(0);
+    __syncthreads();
+    for (int it = it_begin; it < it_end; ++it) {
+      const int buf = (it - it_begin) & 1;
+      if (it + 1 < it_end) load_tiles(it + 1);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[TM], b[TN];
+#pragma unroll
+        for (int g = 0; g < MG; ++g) {
+          const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][g * (BM / MG) + ty * 4]);
+          a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][g * (BN / NG) + tx * 4]);
+          b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (it + 1 < it_end) {
+        store_tiles(buf ^ 1);
+        __syncthreads();
+      }
+    }
+  }
 
-  for (int it = 0; it < total; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < total) load_tiles(it + 1);
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[TM], b[TN];
-#pragma unroll
-      for (int g = 0; g < MG; ++g) {
-        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][g * (BM / MG) + ty * 4]);
-        a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
-      }
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][g * (BN / NG) + tx * 4]);
-        b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
-      }
+  if (SPLIT) {
+    // ---- split-K reduction over the cluster through distributed shared memory
+    cg::cluster_group cluster = cg::this_cluster();
+    __syncthreads();                                   // everyone is done reading As/Bs
+    if (rank != 0) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) smem[(i * TN + j) * NT + tid] = acc[i][j];
     }
-    if (it + 1 < total) {
-      store_tiles(buf ^ 1);
-      __syncthreads();
+    cluster.sync();
+    if (rank == 0) {
+      for (int r = 1; r < split; ++r) {
+        const float* remote = cluster.map_shared_rank(smem, r);
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] += remote[(i * TN + j) * NT + tid];
+      }
     }
+    cluster.sync();                                    // keep the partials alive until rank 0 has read them
+    if (rank != 0) return;
   }
 
   // ---------------------------------------------------------------- epilogue
@@ -189,11 +235,33 @@ gemm_kernel(const GemmBatch batch) {
 }
 
 template <int BM, int BN, int MG, int NG>
-void launch_cfg(const GemmBatch& b, int count, cudaStream_t st) {
+void launch_cfg(GemmBatch& b, int count, int split, cudaStream_t st) {
   constexpr int NT = (BM / (4 * MG)) * (BN / (4 * NG));
+  constexpr bool CAN_SPLIT = BM * BN <= 2 * BK * (BM + 4 + BN + 4);
   const GemmParams& p = b.p[0];
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, count);
-  gemm_kernel<BM, BN, MG, NG><<<grid, NT, 0, st>>>(b);
+  if constexpr (CAN_SPLIT) {
+    if (split > 1) {
+      b.split = split;
+      grid.z = count * split;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(NT);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = split;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BM, BN, MG, NG, true>, b));
+      return;
+    }
+  }
+  b.split = 1;
+  gemm_kernel<BM, BN, MG, NG, false><<<grid, NT, 0, st>>>(b);
 }
 
 }  // namespace
@@ -201,29 +269,37 @@ void launch_cfg(const GemmBatch& b, int count, cudaStream_t st) {
 void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   SV_CHECK(count >= 1 && count <= 3, "gemm batch count");
   GemmBatch b;
+  int min_iters = 1 << 30;
   for (int i = 0; i < count; ++i) {
     b.p[i] = ps[i];
     SV_CHECK(ps[i].K % BK == 0 && ps[i].K > 0, "gemm K must be a positive multiple of 16");
     SV_CHECK(ps[i].lda % 4 == 0, "gemm lda must be a multiple of 4");
     SV_CHECK(ps[i].taps >= 1 && ps[i].taps <= MAX_TAPS, "gemm taps");
     SV_CHECK(ps[i].M == ps[0].M && ps[i].N == ps[0].N, "batched gemm problems must share M and N");
+    min_iters = std::min(min_iters, ps[i].K / BK * ps[i].taps);
   }
   for (int i = count; i < 3; ++i) b.p[i] = ps[0];
   const GemmParams& p = ps[0];
   if (p.M <= 0 || p.N <= 0) return;
   auto ctas = [&](int bm, int bn) { return (long long)((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * count; };
+  // split-K over a cluster when the plain grid cannot fill the 148 SMs twice and each slice keeps >= 4 K-slabs
+  auto pick_split = [&](long long n_ctas) {
+    int s = 1;
+    while (s < 8 && n_ctas * s < 2 * 148 && min_iters / (s * 2) >= 4) s *= 2;
+    return s;
+  };
   if (p.N <= 16) {
-    launch_cfg<128, 16, 1, 1>(b, count, st);
+    launch_cfg<128, 16, 1, 1>(b, count, pick_split(ctas(128, 16)), st);
   } else if (p.N <= 32) {
-    launch_cfg<128, 32, 2, 1>(b, count, st);
+    launch_cfg<128, 32, 2, 1>(b, count, pick_split(ctas(128, 32)), st);
   } else if (p.N <= 64 && p.M >= 2048) {
-    launch_cfg<128, 64, 2, 1>(b, count, st);
+    launch_cfg<128, 64, 2, 1>(b, count, 1, st);
   } else if (ctas(128, 128) >= 2 * 148) {
-    launch_cfg<128, 128, 2, 2>(b, count, st);
-  } else if (ctas(64, 64) >= 148 || p.M > 32) {
-    launch_cfg<64, 64, 1, 1>(b, count, st);
+    launch_cfg<128, 128, 2, 2>(b, count, 1, st);
+  } else if (p.M > 32) {
+    launch_cfg<64, 64, 1, 1>(b, count, pick_split(ctas(64, 64)), st);
   } else {
-    launch_cfg<32, 64, 1, 1>(b, count, st);
+    launch_cfg<32, 64, 1, 1>(b, count, pick_split(ctas(32, 64)), st);
   }
   SV_LAUNCHED();
 }

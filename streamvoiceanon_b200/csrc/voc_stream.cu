@@ -1,0 +1,176 @@
+// Incremental (stateful) vocoder: `code2wav_fn` (evaluations/infer_arvc.py:173-176) evaluated on the NEW code
+// frames only, with every causal conv reading its left context from per-stream history rows instead of
+// re-computing the reference's 64-frame window.
+//
+// Why this equals the reference: all convs of quantizer.upsample + HiFiGANGenerator are left-pad-only causal
+// (firefly.py:92-103,114-138) and the structural receptive field of one output frame is 30 182 samples = 14.74
+// code frames, so with >= 15 frames of true history the last frame of the window
+// recompute and the incremental result are the same function of the same inputs.  The reference guarantees that
+// history by left-padding the window with the prompt's codec ids (infer_arvc.py:567-571); the stream primes the
+// state with the same frames before the first real frame.
+//
+// Every activation that some later conv reads "into the past" lives in an SBuf: [margin + rows][C] with the
+// newest `margin` rows of the previous step in front.  One batched kernel moves the histories after a step.
+#include "engine.hpp"
+
+namespace svanon {
+
+namespace {
+
+constexpr int CH[6] = {512, 256, 128, 64, 32, 16};
+constexpr int UPS[5] = {8, 8, 2, 2, 2};
+constexpr int RK[3] = {3, 7, 11};
+constexpr int RD[3] = {1, 3, 5};
+
+// dst[i] = src[i + shift] for i < margin, possibly overlapping: walk upwards in chunks, read-all then write-all.
+__global__ void __launch_bounds__(256) shift_history_kernel(const ShiftDesc* __restrict__ descs) {
+  const ShiftDesc d = descs[blockIdx.x];
+  constexpr int PER = 8;
+  for (int base = 0; base < d.margin_floats; base += 256 * PER) {
+    float v[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = base + j * 256 + threadIdx.x;
+      v[j] = (i < d.margin_floats) ? d.base[i + d.shift_floats] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = base + j * 256 + threadIdx.x;
+      if (i < d.margin_floats) d.base[i] = v[j];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+VocState::~VocState() {
+  if (arena) cudaFree(arena);
+  if (desc_dev) cudaFree(desc_dev);
+}
+
+void Engine::voc_state_init(VocState& vs, int c) {
+  SV_CHECK(c >= 1 && c <= 8, "frames per vocoder step");
+  if (vs.arena) { cudaFree(vs.arena); vs.arena = nullptr; }
+  if (vs.desc_dev) { cudaFree(vs.desc_dev); vs.desc_dev = nullptr; }
+  vs.c = c;
+  std::vector<SBuf*> all;
+  size_t total = 0;
+  auto plan = [&](SBuf& b, int margin, int rows, int C) {
+    b.margin = margin; b.rows = rows; b.C = C;
+    b.base = reinterpret_cast<float*>(total);          // offset for now
+    total += ((size_t)(margin + rows) * C + 63) & ~(size_t)63;
+    all.push_back(&b);
+  };
+  plan(vs.u1, 6, 2 * c, 512);
+  plan(vs.u2, 6, 4 * c, 512);
+  plan(vs.p0, 12, 4 * c, 512);
+  plan(vs.c0, 1, 4 * c, 512);
+  int rows = 4 * c;
+  for (int i = 0; i < 5; ++i) {
+    rows *= UPS[i];
+    const int C = CH[i + 1];
+    VocState::Level& L = vs.lv[i];
+    plan(L.x, (RK[2] - 1) * RD[0], rows, C);
+    for (int j = 0; j < 3; ++j) {
+      for (int d = 0; d < 3; ++d) plan(L.t[j][d], (RK[j] - 1) * RD[d], rows, C);
+      for (int d = 0; d < 2; ++d) plan(L.r[j][d], (RK[j] - 1) * RD[d + 1], rows, C);
+    }
+    plan(L.next, i == 4 ? 12 : 1, rows, C);
+  }
+  vs.arena_floats = total;
+  SV_CUDA(cudaMalloc(&vs.arena, total * sizeof(float)));
+  SV_CUDA(cudaMemset(vs.arena, 0, total * sizeof(float)));
+  std::vector<ShiftDesc> descs;
+  for (SBuf* b : all) {
+    b->base = vs.arena + reinterpret_cast<size_t>(b->base);
+    descs.push_back({b->base, b->margin * b->C, b->rows * b->C});
+  }
+  vs.n_desc = (int)descs.size();
+  SV_CUDA(cudaMalloc(&vs.desc_dev, descs.size() * sizeof(ShiftDesc)));
+  SV_CUDA(cudaMemcpy(vs.desc_dev, descs.data(), descs.size() * sizeof(ShiftDesc), cudaMemcpyHostToDevice));
+  vs.primed_frames = 0;
+}
+
+void Engine::voc_state_reset(VocState& vs, cudaStream_t st) {
+  if (vs.arena) SV_CUDA(cudaMemsetAsync(vs.arena, 0, vs.arena_floats * sizeof(float), st));
+  vs.primed_frames = 0;
+}
+
+// One step: vs.c new code frames (codes [8][..] with row stride ld) -> vs.c * 2048 new samples.
+void Engine::voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
+  SV_CHECK(vs.arena, "vocoder state not initialised");
+  const int c = vs.c;
+  ws.ensure(((size_t)c * 500000 + (4u << 20)) * sizeof(float));
+  ws.reset();
+  // DownsampleFiniteScalarQuantize.decode (fsq.py:112-116)
+  float* z0 = ws.alloc_f((long long)c * 512);
+  launch_fsq_lookup(codes, ld, fsq_w, fsq_b, z0, c, st);
+  float* tmp = ws.alloc_f((long long)4 * c * 512);
+  float* hid = ws.alloc_f((long long)4 * c * 2048);
+  float* o1 = ws.alloc_f((long long)2 * c * 512);
+  {
+    GemmParams p;
+    p.A = z0; p.W = up_w[0]; p.C = vs.u1.data(); p.bias = up_b[0]; p.M = c; p.N = 1024; p.K = 512; p.lda = 512; p.ldc = 1024;
+    launch_gemm(p, st);
+    convnext(up_block[0], vs.u1.data(), 2 * c, tmp, hid, st, o1);
+    GemmParams q;
+    q.A = o1; q.W = up_w[1]; q.C = vs.u2.data(); q.bias = up_b[1]; q.M = 2 * c; q.N = 1024; q.K = 512; q.lda = 512; q.ldc = 1024;
+    launch_gemm(q, st);
+    convnext(up_block[1], vs.u2.data(), 4 * c, tmp, hid, st, vs.p0.data());
+  }
+  // HiFiGANGenerator.forward (firefly.py:280-293)
+  {
+    GemmParams p;
+    p.A = vs.p0.data(); p.W = pre_w; p.C = vs.c0.data(); p.bias = pre_b; p.M = 4 * c; p.N = 512; p.K = 13 * 512; p.lda = 512;
+    p.ldc = 512; p.tap_off[0] = -12;
+    launch_gemm(p, st);
+  }
+  const float* cur = vs.c0.data();
+  int rows = 4 * c;
+  for (int i = 0; i < 5; ++i) {
+    const int Ci = CH[i], Co = CH[i + 1], s = UPS[i];
+    const int Lo = rows * s;
+    VocState::Level& L = vs.lv[i];
+    {
+      GemmParams p;
+      p.A = cur; p.W = ups_w[i]; p.C = L.x.data(); p.bias = ups_b[i]; p.M = rows; p.N = s * Co; p.K = 2 * Ci; p.lda = Ci;
+      p.ldc = (long long)s * Co; p.tap_off[0] = -1; p.prologue = PRO_SILU;
+      launch_gemm(p, st);
+    }
+    float* r2[3];
+    for (int j = 0; j < 3; ++j) r2[j] = ws.alloc_f((long long)Lo * Co);
+    for (int d = 0; d < 3; ++d) {
+      GemmParams p1[3], p2[3];
+      for (int j = 0; j < 3; ++j) {
+        const float* in = (d == 0) ? L.x.data() : L.r[j][d - 1].data();
+        float* out = (d == 2) ? r2[j] : L.r[j][d].data();
+        auto setup = [&](GemmParams& p, const ResConvW& w, const float* A, float* C, const float* res) {
+          p.A = A; p.W = w.w; p.C = C; p.bias = w.b; p.residual = res; p.M = Lo; p.N = Co; p.lda = Co; p.ldc = Co;
+          p.ldr = Co; p.prologue = PRO_SILU;
+          if (w.d == 1) {
+            p.K = w.k * Co; p.taps = 1; p.tap_off[0] = -(w.k - 1);
+          } else {
+            p.K = Co; p.taps = w.k;
+            for (int t = 0; t < w.k; ++t) p.tap_off[t] = -(w.k - 1 - t) * w.d;
+          }
+        };
+        setup(p1[j], res1[i][j][d], in, L.t[j][d].data(), nullptr);
+        setup(p2[j], res2[i][j][d], L.t[j][d].data(), out, in);
+      }
+      launch_gemm(p1, 3, st);
+      launch_gemm(p2, 3, st);
+    }
+    launch_scale_add3(r2[0], r2[1], r2[2], L.next.data(), (long long)Lo * Co, 1.f / 3.f, st);
+    cur = L.next.data();
+    rows = Lo;
+  }
+  launch_conv_post(cur, post_w, post_b, wave_out, rows, st);
+  shift_history_kernel<<<vs.n_desc, 256, 0, st>>>(vs.desc_dev);
+  SV_LAUNCHED();
+  vs.primed_frames += c;
+}
+
+}  // namespace svanon

@@ -87,6 +87,19 @@ class StreamSession:
                                                                 C.c_void_p(_cuda_stream_ptr())))
         return out
 
+    def set_vocoder_mode(self, incremental: bool = True):
+        """True (default): incremental vocoder; False: recompute the decode window every chunk like the reference."""
+        _lib.check(self._engine.lib.svanon_stream_set_vocoder_mode(self._h, int(incremental)))
+
+    def set_timing(self, enable: bool = True):
+        _lib.check(self._engine.lib.svanon_stream_set_timing(self._h, int(enable)))
+
+    def last_timing(self):
+        """(E, A, V) device milliseconds of the last non-warm-up chunk."""
+        ms = (C.c_float * 3)()
+        _lib.check(self._engine.lib.svanon_stream_last_timing(self._h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
     def history(self, cap: int = 4096):
         src = torch.empty(cap, dtype=torch.int64)
         pred = torch.empty(8 * cap, dtype=torch.int64)

@@ -261,7 +261,7 @@ def test_ar_errors(models):
 
 
 # ------------------------------------------------------------------------------------------------ loop
-def _run_loop(models, weights, g, tape, host_io):
+def _run_loop(models, weights, g, tape, host_io, incremental=True):
     from streamvoiceanon_b200 import StreamSession
     _, tok, _ = models
     n_ref, n_chunks = int(g["n_ref"]), int(g["n_chunks"])
@@ -277,6 +277,7 @@ def _run_loop(models, weights, g, tape, host_io):
                     delay=int(g["delay"]))
     sess.setup(int(g["encode_window_frames"]), int(g["decode_window_frames"]), int(g["max_seq_frames"]),
                int(g["buffer_frames"]), 1)
+    sess.set_vocoder_mode(incremental)
     src = synth.synth_audio_44k(int(g["src_seed"]), 1.5)[: n_chunks * 2048].view(n_chunks, 2048)
     waves = []
     for i in range(n_chunks):
@@ -287,13 +288,25 @@ def _run_loop(models, weights, g, tape, host_io):
     return src_hist, pred_hist, torch.cat(waves)
 
 
-@pytest.mark.parametrize("name,host_io", [("stream_reprompt", False), ("stream_default", True)])
-def test_stream_loop_vs_reference(models, weights, gold, tape, name, host_io):
+def test_incremental_vocoder_equals_window_recompute(models, weights, gold, tape):
+    """The incremental vocoder (new frames only, per-stream conv history) against the reference-style recompute
+    of the 64-frame window inside the same loop: identical codec ids, waveform equal to fp32 rounding."""
+    g = gold("stream_default")
+    _, pred_a, wave_a = _run_loop(models, weights, g, tape, False, incremental=True)
+    _, pred_b, wave_b = _run_loop(models, weights, g, tape, False, incremental=False)
+    assert torch.equal(pred_a, pred_b)
+    assert float(((wave_a - wave_b) ** 2).mean()) < 1e-11
+    assert float((wave_a - wave_b).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("name,host_io,incremental", [("stream_reprompt", False, True), ("stream_default", True, True),
+                                                      ("stream_default", False, False)])
+def test_stream_loop_vs_reference(models, weights, gold, tape, name, host_io, incremental):
     """The whole per-chunk loop against the UNMODIFIED reference's process_one_chunk: content ids and codec ids
     bit-exact, waveform within the fp32 MSE tolerance.  `stream_default` = CLI defaults (windows 128/64) with
     HOST buffers through the C ABI; `stream_reprompt` = small windows with the re-prompt path firing."""
     g = gold(name)
-    src_hist, pred_hist, wave = _run_loop(models, weights, g, tape, host_io)
+    src_hist, pred_hist, wave = _run_loop(models, weights, g, tape, host_io, incremental)
     assert np.array_equal(src_hist.numpy()[None], g["src_content"])
     assert np.array_equal(pred_hist.numpy()[None], g["pred_codes"])
     mse = float(((wave.numpy() - g["wave"]) ** 2).mean())
