@@ -105,6 +105,9 @@ int svanon_ar_position(const svanon_stream* s); /* next free sequence position *
 /* test hook: capture the logits of the next decode steps (slow 8192-way head, pre-norm hidden state, 8 fast
  * heads) of stream 0 of each launch; read them back with svanon_ar_read_debug (host pointers, may be NULL) */
 int svanon_ar_debug_logits(svanon_engine* e, int enable);
+/* batch-1 decode kernel variant: 1 (default) = weights staged through shared memory with TMA bulk copies that
+ * overlap the grid barriers; 0 = weights loaded straight from global memory (the variant batched launches use) */
+int svanon_ar_use_staged_weights(svanon_engine* e, int enable);
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits /*[8192]*/, float* hidden /*[768]*/,
                          float* fast_logits /*[8][1000]*/);
 

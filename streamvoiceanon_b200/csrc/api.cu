@@ -392,6 +392,13 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable) {
   });
 }
 
+int svanon_ar_use_staged_weights(svanon_engine* e, int enable) {
+  return guarded([&] {
+    SV_CHECK(e, "null engine");
+    e->eng.ar_staged = enable != 0;
+  });
+}
+
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits, float* hidden, float* fast_logits) {
   return guarded([&] {
     SV_CHECK(e && e->eng.finalized[MODEL_AR], "AR weights not finalized");

@@ -62,5 +62,8 @@ struct ArDecodeArgs {
 
 int ar_decode_max_batch();
 void launch_ar_decode(const ArDecodeArgs& args, int batch, int grid, cudaStream_t st);
+// batch-1 variant with TMA-staged weights (ar_decode_staged.cu)
+bool ar_decode_staged_supported(int grid);
+void launch_ar_decode_staged(const ArDecodeArgs& args, int grid, cudaStream_t st);
 
 }  // namespace svanon

@@ -788,7 +788,8 @@ void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) 
   a.nsplit = nsplit;
   if (debug_logits) { a.dbg_slow_logits = dbg_slow_logits; a.dbg_hidden = dbg_hidden; a.dbg_fast_logits = dbg_fast_logits; }
   else { a.dbg_slow_logits = nullptr; a.dbg_hidden = nullptr; a.dbg_fast_logits = nullptr; }
-  launch_ar_decode(a, batch, num_sms, st);
+  if (batch == 1 && ar_staged && ar_decode_staged_supported(num_sms)) launch_ar_decode_staged(a, num_sms, st);
+  else launch_ar_decode(a, batch, num_sms, st);
 
   for (int b = 0; b < batch; ++b) {
     streams[b]->pos_next += 2;

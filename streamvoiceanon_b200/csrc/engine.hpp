@@ -149,6 +149,7 @@ struct Engine {
   unsigned* ar_barrier = nullptr;
   float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
   bool debug_logits = false;
+  bool ar_staged = true;                       // batch-1 decode: TMA-staged weights (false: direct global loads)
 
   // ---- tokenizer
   const float *dft_w = nullptr, *fb_t = nullptr, *stem_w = nullptr, *stem_b = nullptr, *stem_ln_w = nullptr,

@@ -159,6 +159,22 @@ def test_ar_streaming_codes_vs_reference(models, gold, tape):
         assert int(pos) == int(s["pos"][i])
 
 
+def test_ar_direct_load_kernel_variant(models, gold, tape):
+    """The non-staged batch-1 kernel (weights straight from global memory) produces the same codes."""
+    from streamvoiceanon_b200 import _lib
+    ar, _, _ = models
+    s = gold("ar_stream")
+    _lib.check(_lib.load().svanon_ar_use_staged_weights(ar._engine.handle, 0))
+    try:
+        src = _prefill(ar, s, tape)
+        ar.prefill_src_condition4delay(src[:, :2].cuda())
+        for i, t in enumerate(range(2, 8)):
+            codes, pos = ar.decode_one(src[:, t:t + 1].cuda())
+            assert np.array_equal(codes.cpu().numpy(), s["codes"][i]), i
+    finally:
+        _lib.check(_lib.load().svanon_ar_use_staged_weights(ar._engine.handle, 1))
+
+
 def test_ar_teacher_forced_logits_vs_reference(models, gold, tape):
     ar, _, _ = models
     s, g = gold("ar_stream"), gold("ar_logits")
