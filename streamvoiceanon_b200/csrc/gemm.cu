@@ -266,6 +266,9 @@ void launch_cfg(GemmBatch& b, int count, int split, cudaStream_t st) {
 
 }  // namespace
 
+bool g_gemm_use_pipe = true;
+bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pipe.cu
+
 void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   SV_CHECK(count >= 1 && count <= 3, "gemm batch count");
   GemmBatch b;
@@ -281,6 +284,10 @@ void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   for (int i = count; i < 3; ++i) b.p[i] = ps[0];
   const GemmParams& p = ps[0];
   if (p.M <= 0 || p.N <= 0) return;
+  if (g_gemm_use_pipe && launch_gemm_pipe(ps, count, st)) {     // small / latency-bound problems
+    SV_LAUNCHED();
+    return;
+  }
   auto ctas = [&](int bm, int bn) { return (long long)((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * count; };
   // split-K over a cluster when the plain grid cannot fill the 148 SMs twice and each slice keeps >= 4 K-slabs
   auto pick_split = [&](long long n_ctas) {
