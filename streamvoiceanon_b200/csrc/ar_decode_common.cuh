@@ -30,27 +30,39 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Sense-reversing grid barrier; co-residency is guaranteed by the cooperative launch.
+// Grid barrier on a monotonically increasing arrival counter (bar[0]); co-residency is guaranteed by the
+// cooperative launch.  Arriving is a fire-and-forget `red.release` (no round trip), waiting is an acquire-poll
+// until the counter reaches this barrier's target = base + k * nblocks: ~1.5 L2 round trips per barrier instead
+// of the 4 of a generation-flag barrier.  bar[1] carries the counter value at the end of the previous launch.
+__device__ __forceinline__ unsigned& grid_target() {
+  __shared__ unsigned t;
+  return t;
+}
+__device__ __forceinline__ void grid_sync_init(unsigned* bar) {
+  if (threadIdx.x == 0) {
+    unsigned base;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(base) : "l"(bar + 1) : "memory");
+    grid_target() = base;
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned gen;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    const unsigned t = grid_target() + nblocks;
+    grid_target() = t;
     __threadfence();
-    const unsigned arrived = atomicAdd(bar, 1u);
-    if (arrived == nblocks - 1) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
-    } else {
-      unsigned g;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory");
-      } while (g == gen);
-    }
-    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while ((int)(v - t) < 0);
   }
   __syncthreads();
+}
+// every CTA has passed the last barrier's arrive before any CTA can get here, so the counter is final
+__device__ __forceinline__ void grid_sync_finish(unsigned* bar) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) bar[1] = grid_target();
 }
 
 // dot products of NR weight rows (length K, row-major, streamed) with M activation vectors held in shared

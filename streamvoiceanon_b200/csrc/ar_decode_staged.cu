@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   }
   __syncthreads();
   if (threadIdx.x == 0) issue(a, sg, 0);
+  grid_sync_init(a.barrier);
 
   // ---- phase 0: the 2 input rows [cached_new_audio_emb, embedding[content_id]]
   for (int i = gtid; i < 2 * D; i += NT * gridDim.x) {
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
     }
     st.x_audio[c] = s;
   }
+  grid_sync_finish(a.barrier);
 }
 
 }  // namespace

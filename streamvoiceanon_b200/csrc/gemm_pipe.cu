@@ -241,6 +241,9 @@ bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st) {
     else launch_pipe_cfg<64, 32, 4, 2>(b, count, pick_split(ctas(64, 32)), st);
   } else if (p.M <= 32) {
     launch_pipe_cfg<32, 64, 2, 4>(b, count, pick_split(ctas(32, 64)), st);
+  } else if (p.M > 128 && p.N >= 128) {
+    // encoder-window sized problems (M = 256..512): 8x4 register tiles keep the FMA pipe, not LDS, the limiter
+    launch_pipe_cfg<128, 64, 8, 4>(b, count, pick_split(ctas(128, 64)), st);
   } else {
     launch_pipe_cfg<64, 64, 4, 4>(b, count, pick_split(ctas(64, 64)), st);
   }
