@@ -7,6 +7,10 @@
 
 #include "engine.hpp"
 
+namespace svanon {
+extern bool g_gemm_use_pipe;
+extern bool g_gemm_use_tc;
+}
 using namespace svanon;
 
 struct svanon_engine {
@@ -389,6 +393,28 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable) {
   return guarded([&] {
     SV_CHECK(e, "null engine");
     e->eng.debug_logits = enable != 0;
+  });
+}
+
+int svanon_set_gemm_mode(int mode) {
+  return guarded([&] {
+    SV_CHECK(mode >= 0 && mode <= 2, "gemm mode: 0 = fp32 CUDA-core (register double-buffer only), 1 = fp32 CUDA-core, 2 = tcgen05 3xTF32");
+    g_gemm_use_pipe = mode >= 1;
+    g_gemm_use_tc = mode == 2;
+  });
+}
+
+int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                      int act, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && A && W && C && M > 0 && N > 0 && K > 0 && K % 16 == 0, "bad arguments");
+    Args a(e, stream, ((size_t)M * K + (size_t)N * K + (size_t)M * N + N) * 4 + 65536);
+    GemmParams p;
+    p.A = a.in(A, (size_t)M * K); p.W = a.in(W, (size_t)N * K); p.bias = a.in(bias, (size_t)N);
+    p.C = a.out(C, (size_t)M * N);
+    p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N; p.act = act;
+    launch_gemm(p, a.st);
+    a.finish();
   });
 }
 

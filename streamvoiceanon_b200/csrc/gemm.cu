@@ -267,7 +267,9 @@ void launch_cfg(GemmBatch& b, int count, int split, cudaStream_t st) {
 }  // namespace
 
 bool g_gemm_use_pipe = true;
+bool g_gemm_use_tc = false;
 bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pipe.cu
+bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st);     // gemm_tc.cu
 
 void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   SV_CHECK(count >= 1 && count <= 3, "gemm batch count");
@@ -284,6 +286,10 @@ void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   for (int i = count; i < 3; ++i) b.p[i] = ps[0];
   const GemmParams& p = ps[0];
   if (p.M <= 0 || p.N <= 0) return;
+  if (g_gemm_use_tc && launch_gemm_tc(ps, count, st)) {         // tcgen05 3xTF32 (M >= 96, N >= 64)
+    SV_LAUNCHED();
+    return;
+  }
   if (g_gemm_use_pipe && launch_gemm_pipe(ps, count, st)) {     // small / latency-bound problems
     SV_LAUNCHED();
     return;

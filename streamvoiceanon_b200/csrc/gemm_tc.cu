@@ -1,0 +1,325 @@
+// Tensor-core GEMM for the dense projections of the encoder window and the AR prompt prefill: tcgen05.mma
+// (5th-gen tensor cores, accumulator in TMEM) with fp32-grade products through a 3xTF32 split.
+//
+// Why a split: token ids are decided by sign(proj) (BSQ) and argmax(p/q) (sampler), so parity with the fp32
+// reference needs ~fp32 products; a single TF32 pass (10-bit mantissa) flips ids.  Every fp32 operand x is split
+// into hi = tf32(x) and lo = x - hi (exact in fp32; the tensor core truncates lo to TF32 again), and
+//     x*y ~= hi_x*hi_y + hi_x*lo_y + lo_x*hi_y          (dropped terms <= 2^-20 |x*y|)
+// is accumulated in fp32 in TMEM: three kind::tf32 MMAs per K-step.
+//
+// Data path: the same 128-byte-swizzled K-major tiles gemm_pipe.cu uses ([row][32 floats], 16-byte chunks XORed
+// with row&7 == UMMA/TMA SWIZZLE_128B) are filled with cp.async; after a slab lands all 128 threads split it in
+// place (hi) and into a sibling tile (lo), fence the generic->async proxy, and one thread issues the 12 MMAs of the
+// slab (4 K-steps x 3 products) and commits them to an mbarrier that frees the stage.  CTA tile 128 x BN, one CTA
+// per SM, accumulator = BN TMEM columns, epilogue reads TMEM with tcgen05.ld (one row per thread).  Split-K over a
+// thread-block cluster with a DSMEM reduction as in gemm.cu.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace svanon {
+
+namespace {
+
+constexpr int TK = 32;                 // K-slab = one 128-byte swizzle row
+constexpr int TBM = 128;
+
+struct TcBatch {
+  GemmParams p[3];
+  int split;
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int swz(int row, int c) { return row * TK + ((c ^ (row & 7)) << 2); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni TC_WAIT_DONE;\n"
+      "bra.uni TC_WAIT_LOOP;\n"
+      "TC_WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp: start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) = 2)
+__device__ __forceinline__ unsigned long long umma_desc(const void* tile) {
+  const unsigned long long addr = smem_u32(tile);
+  return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | ((1024ull >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ unsigned umma_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+  unsigned r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN, int STAGES, bool SPLIT>
+__global__ void __launch_bounds__(128, 1) gemm_tc_kernel(const TcBatch batch) {
+  constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;
+  constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;           // A_hi | A_lo | B_hi | B_lo
+  constexpr int A_CH = TBM * 8, B_CH = BN * 8;
+  static_assert(TBM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
+  extern __shared__ unsigned char dsmem_raw[];
+  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ unsigned long long mma_done[STAGES];
+  __shared__ unsigned tmem_holder;
+
+  const int split = SPLIT ? batch.split : 1;
+  const int zb = SPLIT ? blockIdx.z / split : blockIdx.z;
+  const int rank = SPLIT ? blockIdx.z % split : 0;
+  const GemmParams& p = batch.p[zb];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
+  const int kSlabs = (p.K + TK - 1) / TK;
+  const int total = kSlabs * p.taps;
+  const int it_begin = (int)((long long)total * rank / split);
+  const int it_end = (int)((long long)total * (rank + 1) / split);
+  const int n_it = it_end - it_begin;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&mma_done[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_d = tmem_holder;
+  const unsigned idesc = umma_idesc(BN);
+
+  auto issue = [&](int it, int stage) {
+    float* As = smem + stage * STAGE_FLOATS;
+    float* Bs = As + 2 * A_FLOATS;
+    const int t = it / kSlabs;
+    const int k0 = (it - t * kSlabs) * TK;
+    const long long off = p.tap_off[t];
+    for (int i = tid; i < A_CH; i += 128) {
+      const int row = i >> 3, c = i & 7;
+      const int m = m0 + row, k = k0 + c * 4;
+      const bool ok = (m < p.M) && (k < p.K);
+      const float* src = ok ? p.A + ((long long)m * p.a_row_step + off) * p.lda + k : p.A;
+      cp_async16(As + swz(row, c), src, ok ? 16 : 0);
+    }
+    for (int i = tid; i < B_CH; i += 128) {
+      const int row = i >> 3, c = i & 7;
+      const int n = n0 + row, k = k0 + c * 4;
+      const bool ok = (n < p.N) && (k < p.K);
+      const float* src = ok ? p.W + ((long long)t * p.N + n) * p.K + k : p.W;
+      cp_async16(Bs + swz(row, c), src, ok ? 16 : 0);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < n_it) issue(it_begin + s, s);
+    cp_async_commit();
+  }
+
+  for (int li = 0; li < n_it; ++li) {
+    const int stage = li % STAGES;
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();                                              // slab li has landed
+    // split pass: raw -> hi (in place), lo (sibling tile)
+    float* As = smem + stage * STAGE_FLOATS;
+    float* Bs = As + 2 * A_FLOATS;
+    const bool silu = p.prologue == PRO_SILU;
+    for (int i = tid; i < A_CH + B_CH; i += 128) {
+      float4* q = (i < A_CH) ? reinterpret_cast<float4*>(As) + i : reinterpret_cast<float4*>(Bs) + (i - A_CH);
+      float4* ql = q + ((i < A_CH) ? A_FLOATS / 4 : B_FLOATS / 4);
+      float4 v = *q;
+      if (silu && i < A_CH) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+      *q = h;
+      *ql = l;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
+      const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
+#pragma unroll
+      for (int kk = 0; kk < TK / 8; ++kk) {
+        const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
+        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
+        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+      }
+      umma_commit(&mma_done[stage]);
+    }
+    // refill the stage that held slab li-1 once its MMAs have finished reading it (they were issued one
+    // iteration ago, so this wait is normally already satisfied)
+    if (li + STAGES - 1 < n_it) {
+      if (li >= 1) mbar_wait(&mma_done[(li - 1) % STAGES], ((li - 1) / STAGES) & 1);
+      issue(it_begin + li + STAGES - 1, (li + STAGES - 1) % STAGES);
+    }
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  if (n_it > 0) mbar_wait(&mma_done[(n_it - 1) % STAGES], ((n_it - 1) / STAGES) & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
+
+  // ---------------------------------------------------------------- TMEM -> registers -> (split-K reduce) -> global
+  const int row = warp * 32 + lane;                 // accumulator row == TMEM lane
+  const int m = m0 + row;
+  cg::cluster_group cluster = cg::this_cluster();
+  if (SPLIT && rank != 0) {
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) smem[(c0 + j) * TBM + row] = v[j];
+    }
+  }
+  if (SPLIT) cluster.sync();
+  if (!SPLIT || rank == 0) {
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (SPLIT) {
+        for (int r = 1; r < split; ++r) {
+          const float* remote = cluster.map_shared_rank(smem, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += remote[(c0 + j) * TBM + row];
+        }
+      }
+      if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < p.N) {
+            float y = v[j];
+            if (p.bias) y += __ldg(p.bias + n);
+            if (p.act == ACT_GELU) y = gelu_erf(y);
+            else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
+            if (p.gamma) y *= __ldg(p.gamma + n);
+            if (p.residual) y += __ldg(p.residual + (long long)m * p.ldr + n);
+            y *= p.out_scale;
+            float* dst = p.C + (long long)m * p.ldc + n;
+            *dst = p.accumulate ? *dst + y : y;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (SPLIT) cluster.sync();
+  else __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+}
+
+template <int BN, int STAGES>
+void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
+  constexpr size_t SMEM = (size_t)STAGES * (2 * TBM * TK + 2 * BN * TK) * sizeof(float) + 1024;
+  const GemmParams& p = b.p[0];
+  dim3 grid((p.N + BN - 1) / BN, (p.M + TBM - 1) / TBM, count * split);
+  b.split = split;
+  static bool configured = false;
+  if (!configured) {
+    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  if (split > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = split;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, b));
+  } else {
+    gemm_tc_kernel<BN, STAGES, false><<<grid, 128, SMEM, st>>>(b);
+  }
+}
+
+}  // namespace
+
+// Returns false when the problem is not a good fit (small M: latency kernels; tiny N).
+bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
+  const GemmParams& p = ps[0];
+  if (p.M < 96 || p.N < 64) return false;
+  TcBatch b;
+  int min_slabs = 1 << 30;
+  for (int i = 0; i < count; ++i) {
+    b.p[i] = ps[i];
+    min_slabs = std::min(min_slabs, (ps[i].K + TK - 1) / TK * ps[i].taps);
+  }
+  for (int i = count; i < 3; ++i) b.p[i] = ps[0];
+  auto ctas = [&](int bn) { return (long long)((p.M + TBM - 1) / TBM) * ((p.N + bn - 1) / bn) * count; };
+  auto pick_split = [&](long long n_ctas) {
+    int s = 1;
+    while (s < 8 && n_ctas * s * 2 <= 160 && min_slabs / (s * 2) >= 2) s *= 2;
+    return s;
+  };
+  if (ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 3>(b, count, 1, st);
+  else launch_tc_cfg<64, 4>(b, count, pick_split(ctas(64)), st);
+  return true;
+}
+
+}  // namespace svanon

@@ -1,0 +1,53 @@
+"""GEMM back ends against torch fp64 on the GPU: fp32 CUDA-core kernels and the tcgen05 3xTF32 kernel."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mode, M, N, K, act=0, seed=0):
+    from streamvoiceanon_b200 import _lib
+    from streamvoiceanon_b200.engine import Engine, ptr
+    eng = Engine.get(0)
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda")
+    _lib.check(lib.svanon_set_gemm_mode(mode))
+    try:
+        _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, act, None))
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.svanon_set_gemm_mode(1))
+    ref = A.double() @ W.double().T + b.double()
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    return out, ref
+
+
+SHAPES = [(512, 1536, 384), (512, 384, 1536), (128, 1536, 512), (545, 2304, 768), (512, 2050, 2048), (100, 72, 48),
+          (32, 256, 2816), (2048, 16, 48)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_simt_gemm(M, N, K):
+    out, ref = _run(1, M, N, K)
+    assert float((out.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:6])
+def test_tcgen05_3xtf32_gemm(M, N, K):
+    """fp32-grade accuracy: the 3xTF32 split must be as close to fp64 as the fp32 FMA kernel is (single-pass TF32
+    would be ~1e-3)."""
+    out, ref = _run(2, M, N, K)
+    err = float((out.double() - ref).abs().max())
+    assert err < 2e-5 * max(1.0, float(ref.abs().max())), err
+
+
+def test_tcgen05_gelu_epilogue():
+    out, ref = _run(2, 512, 1536, 384, act=1)
+    assert float((out.double() - ref).abs().max()) < 3e-5
