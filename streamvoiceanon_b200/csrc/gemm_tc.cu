@@ -95,16 +95,30 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int TC_PRODUCERS = 128;                  // warps 0-3: cp.async + hi/lo split, later the epilogue
+constexpr int TC_THREADS = TC_PRODUCERS + 32;      // warp 4: MMA issuer (one elected lane)
+
+// Warp-specialised: 4 producer warps stream K-slabs (cp.async into SW128 tiles, each thread splits the chunks it
+// loaded itself into hi/lo once its own copy group has landed, then arrives on full[stage]); one thread of warp 4
+// waits on full[stage], issues the 12 tcgen05.mma of the slab and commits them to empty[stage]; after the last slab
+// the producers turn into the epilogue (TMEM -> registers -> global).  No block-wide barrier in the main loop.
 template <int BN, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(128, 1) gemm_tc_kernel(const TcBatch batch) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch batch) {
   constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;
   constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;           // A_hi | A_lo | B_hi | B_lo
-  constexpr int A_CH = TBM * 8, B_CH = BN * 8;
+  constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = BN * 8 / TC_PRODUCERS;   // 16-byte chunks per thread
+  constexpr int DEPTH = STAGES - 2;                                    // slabs loaded ahead of the split
   static_assert(TBM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
+  static_assert(DEPTH >= 1, "need at least 3 stages");
   extern __shared__ unsigned char dsmem_raw[];
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ unsigned long long mma_done[STAGES];
+  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], acc_bar;
   __shared__ unsigned tmem_holder;
+  __shared__ float s_bias[BN], s_gamma[BN];
 
   const int split = SPLIT ? batch.split : 1;
   const int zb = SPLIT ? blockIdx.z / split : blockIdx.z;
@@ -120,72 +134,103 @@ __global__ void __launch_bounds__(128, 1) gemm_tc_kernel(const TcBatch batch) {
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&mma_done[s], 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = tid; i < BN; i += TC_THREADS) {
+    const int n = n0 + i;
+    s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+    s_gamma[i] = (p.gamma && n < p.N) ? __ldg(p.gamma + n) : 1.f;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_d = tmem_holder;
-  const unsigned idesc = umma_idesc(BN);
 
-  auto issue = [&](int it, int stage) {
-    float* As = smem + stage * STAGE_FLOATS;
-    float* Bs = As + 2 * A_FLOATS;
-    const int t = it / kSlabs;
-    const int k0 = (it - t * kSlabs) * TK;
-    const long long off = p.tap_off[t];
-    for (int i = tid; i < A_CH; i += 128) {
-      const int row = i >> 3, c = i & 7;
-      const int m = m0 + row, k = k0 + c * 4;
-      const bool ok = (m < p.M) && (k < p.K);
-      const float* src = ok ? p.A + ((long long)m * p.a_row_step + off) * p.lda + k : p.A;
-      cp_async16(As + swz(row, c), src, ok ? 16 : 0);
-    }
-    for (int i = tid; i < B_CH; i += 128) {
-      const int row = i >> 3, c = i & 7;
-      const int n = n0 + row, k = k0 + c * 4;
-      const bool ok = (n < p.N) && (k < p.K);
-      const float* src = ok ? p.W + ((long long)t * p.N + n) * p.K + k : p.W;
-      cp_async16(Bs + swz(row, c), src, ok ? 16 : 0);
-    }
-  };
-
+  if (warp < 4) {
+    // =========================================================== producers
+    // fixed per-thread chunk assignment: chunk i = tid + j*128 -> row = i>>3, c = i&7
+    const float* a_base[A_PER];
+    int a_off[A_PER];
+    bool a_ok[A_PER];
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < n_it) issue(it_begin + s, s);
-    cp_async_commit();
-  }
-
-  for (int li = 0; li < n_it; ++li) {
-    const int stage = li % STAGES;
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();                                              // slab li has landed
-    // split pass: raw -> hi (in place), lo (sibling tile)
-    float* As = smem + stage * STAGE_FLOATS;
-    float* Bs = As + 2 * A_FLOATS;
-    const bool silu = p.prologue == PRO_SILU;
-    for (int i = tid; i < A_CH + B_CH; i += 128) {
-      float4* q = (i < A_CH) ? reinterpret_cast<float4*>(As) + i : reinterpret_cast<float4*>(Bs) + (i - A_CH);
-      float4* ql = q + ((i < A_CH) ? A_FLOATS / 4 : B_FLOATS / 4);
-      float4 v = *q;
-      if (silu && i < A_CH) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-      *q = h;
-      *ql = l;
+    for (int j = 0; j < A_PER; ++j) {
+      const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
+      const int m = m0 + row;
+      a_ok[j] = m < p.M;
+      a_base[j] = p.A + (long long)(a_ok[j] ? m : 0) * p.a_row_step * p.lda + c * 4;
+      a_off[j] = swz(row, c);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-    __syncthreads();
-    if (tid == 0) {
+    const float* b_base[B_PER];
+    int b_off[B_PER];
+    bool b_ok[B_PER];
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
+      const int n = n0 + row;
+      b_ok[j] = n < p.N;
+      b_base[j] = p.W + (long long)(b_ok[j] ? n : 0) * p.K + c * 4;
+      b_off[j] = swz(row, c);
+    }
+    const int c4 = (tid & 7) * 4;                      // K offset of this thread's chunks inside a slab
+    const bool silu = p.prologue == PRO_SILU;
+    for (int li = 0; li < n_it + DEPTH; ++li) {
+      if (li < n_it) {
+        const int stage = li % STAGES;
+        mbar_wait(&empty_bar[stage], ((li / STAGES) & 1) ^ 1);           // MMAs that read this stage are done
+        float* As = smem + stage * STAGE_FLOATS;
+        float* Bs = As + 2 * A_FLOATS;
+        const int it = it_begin + li;
+        const int t = it / kSlabs;
+        const int k0 = (it - t * kSlabs) * TK;
+        const bool k_ok = (k0 + c4) < p.K;
+        const long long a_shift = (long long)p.tap_off[t] * p.lda + k0;
+        const long long b_shift = (long long)t * p.N * p.K + k0;
+#pragma unroll
+        for (int j = 0; j < A_PER; ++j) cp_async16(As + a_off[j], a_base[j] + a_shift, (a_ok[j] && k_ok) ? 16 : 0);
+#pragma unroll
+        for (int j = 0; j < B_PER; ++j) cp_async16(Bs + b_off[j], b_base[j] + b_shift, (b_ok[j] && k_ok) ? 16 : 0);
+      }
+      cp_async_commit();
+      const int lj = li - DEPTH;
+      if (lj >= 0) {
+        cp_async_wait<DEPTH>();                                          // this thread's chunks of slab lj have landed
+        const int stage = lj % STAGES;
+        float* As = smem + stage * STAGE_FLOATS;
+        float* Bs = As + 2 * A_FLOATS;
+#pragma unroll
+        for (int j = 0; j < A_PER + B_PER; ++j) {
+          float4* q = (j < A_PER) ? reinterpret_cast<float4*>(As + a_off[j < A_PER ? j : 0])
+                                  : reinterpret_cast<float4*>(Bs + b_off[j >= A_PER ? j - A_PER : 0]);
+          float4* ql = q + ((j < A_PER) ? A_FLOATS / 4 : B_FLOATS / 4);
+          float4 v = *q;
+          if (silu && j < A_PER) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          *q = h;
+          *ql = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the MMA
+        mbar_arrive(&full_bar[stage]);
+      }
+    }
+  } else if (lane == 0) {
+    // =========================================================== MMA issuer
+    const unsigned idesc = umma_idesc(BN);
+    for (int li = 0; li < n_it; ++li) {
+      const int stage = li % STAGES;
+      mbar_wait(&full_bar[stage], (li / STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* As = smem + stage * STAGE_FLOATS;
+      float* Bs = As + 2 * A_FLOATS;
       const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
       const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
 #pragma unroll
@@ -195,39 +240,36 @@ __global__ void __launch_bounds__(128, 1) gemm_tc_kernel(const TcBatch batch) {
         umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
         umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
       }
-      umma_commit(&mma_done[stage]);
+      umma_commit(&empty_bar[stage]);
     }
-    // refill the stage that held slab li-1 once its MMAs have finished reading it (they were issued one
-    // iteration ago, so this wait is normally already satisfied)
-    if (li + STAGES - 1 < n_it) {
-      if (li >= 1) mbar_wait(&mma_done[(li - 1) % STAGES], ((li - 1) / STAGES) & 1);
-      issue(it_begin + li + STAGES - 1, (li + STAGES - 1) % STAGES);
-    }
-    cp_async_commit();
+    umma_commit(&acc_bar);
   }
-  cp_async_wait<0>();
-  if (n_it > 0) mbar_wait(&mma_done[(n_it - 1) % STAGES], ((n_it - 1) / STAGES) & 1);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  __syncthreads();
+  __syncwarp();
 
   // ---------------------------------------------------------------- TMEM -> registers -> (split-K reduce) -> global
-  const int row = warp * 32 + lane;                 // accumulator row == TMEM lane
+  const int row = warp * 32 + lane;                 // accumulator row == TMEM lane (warps 0-3)
   const int m = m0 + row;
   cg::cluster_group cluster = cg::this_cluster();
-  if (SPLIT && rank != 0) {
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
-      else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) smem[(c0 + j) * TBM + row] = v[j];
-    }
+  if (warp < 4) {
+    if (n_it > 0) mbar_wait(&acc_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  if (SPLIT) cluster.sync();
-  if (!SPLIT || rank == 0) {
+  if (SPLIT) {
+    if (warp < 4 && rank != 0) {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) smem[(c0 + j) * TBM + row] = v[j];
+      }
+    }
+    cluster.sync();
+  }
+  if (warp < 4 && (!SPLIT || rank == 0)) {
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
@@ -243,19 +285,37 @@ __global__ void __launch_bounds__(128, 1) gemm_tc_kernel(const TcBatch batch) {
         }
       }
       if (m < p.M) {
+        float* dst = p.C + (long long)m * p.ldc + n0 + c0;
+        const float* res = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
+        const bool vec = (n0 + c0 + 15 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                         (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < p.N) {
-            float y = v[j];
-            if (p.bias) y += __ldg(p.bias + n);
-            if (p.act == ACT_GELU) y = gelu_erf(y);
-            else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
-            if (p.gamma) y *= __ldg(p.gamma + n);
-            if (p.residual) y += __ldg(p.residual + (long long)m * p.ldr + n);
-            y *= p.out_scale;
-            float* dst = p.C + (long long)m * p.ldc + n;
-            *dst = p.accumulate ? *dst + y : y;
+          float y = v[j] + s_bias[c0 + j];
+          if (p.act == ACT_GELU) y = gelu_erf(y);
+          else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
+          v[j] = y * s_gamma[c0 + j];
+        }
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (res) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res + j));
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            }
+            o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (n0 + c0 + j < p.N) {
+              float y = v[j];
+              if (res) y += __ldg(res + j);
+              y *= p.out_scale;
+              dst[j] = p.accumulate ? dst[j] + y : y;
+            }
           }
         }
       }
@@ -282,7 +342,7 @@ void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
   if (split > 1) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -294,7 +354,7 @@ void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
     cfg.numAttrs = 1;
     SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, b));
   } else {
-    gemm_tc_kernel<BN, STAGES, false><<<grid, 128, SMEM, st>>>(b);
+    gemm_tc_kernel<BN, STAGES, false><<<grid, TC_THREADS, SMEM, st>>>(b);
   }
 }
 

@@ -134,7 +134,7 @@ def test_vocoder_window_receptive_field(models):
     codes = torch.randint(0, 1000, (1, 8, 64), generator=g).cuda()
     w64 = voc.decode_codes(codes)[..., -2048:]
     w16 = voc.decode_codes(codes[:, :, -16:].contiguous())[..., -2048:]
-    assert float(((w64 - w16) ** 2).mean()) < 1e-12
+    assert float(((w64 - w16) ** 2).mean()) < 1e-10
 
 
 # ------------------------------------------------------------------------------------------------ A
@@ -311,7 +311,7 @@ def test_incremental_vocoder_equals_window_recompute(models, weights, gold, tape
     _, pred_a, wave_a = _run_loop(models, weights, g, tape, False, incremental=True)
     _, pred_b, wave_b = _run_loop(models, weights, g, tape, False, incremental=False)
     assert torch.equal(pred_a, pred_b)
-    assert float(((wave_a - wave_b) ** 2).mean()) < 1e-11
+    assert float(((wave_a - wave_b) ** 2).mean()) < 1e-10
     assert float((wave_a - wave_b).abs().max()) < 1e-4
 
 
