@@ -105,16 +105,17 @@ int svanon_ar_position(const svanon_stream* s); /* next free sequence position *
 /* test hook: capture the logits of the next decode steps (slow 8192-way head, pre-norm hidden state, 8 fast
  * heads) of stream 0 of each launch; read them back with svanon_ar_read_debug (host pointers, may be NULL) */
 int svanon_ar_debug_logits(svanon_engine* e, int enable);
-/* GEMM back end of the encoder / prefill / vocoder projections (process-wide): 1 (default) = fp32 on CUDA cores,
- * 2 = tcgen05 tensor cores with a 3xTF32 split (fp32-grade products, accumulator in TMEM) for M >= 96, N >= 64,
+/* GEMM back end of the encoder / prefill / vocoder projections (process-wide): 1 = fp32 on CUDA cores,
+ * 2 (default) = tcgen05 tensor cores with a 3xTF32 split (fp32-grade products, accumulator in TMEM) for M >= 96, N >= 64,
  * 0 = the register double-buffered CUDA-core kernel only.  `svanon_debug_gemm` runs one C = act(A W^T + bias)
  * (A [M][K], W [N][K], row-major fp32, K % 16 == 0; act 0 none / 1 GELU) through the selected back end (tests). */
 int svanon_set_gemm_mode(int mode);
 int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N,
                       int K, int act, void* cuda_stream);
-/* batch-1 decode kernel variant: 1 (default) = weights staged through shared memory with TMA bulk copies that
- * overlap the grid barriers; 0 = weights loaded straight from global memory (the variant batched launches use) */
-int svanon_ar_use_staged_weights(svanon_engine* e, int enable);
+/* batch-1 decode kernel variant: 2 (default) = weights staged through shared memory with TMA bulk copies and
+ * activations exchanged between CTAs as self-validating {value, tag} words (no grid barriers); 1 = staged weights +
+ * grid barriers; 0 = weights loaded straight from global memory + grid barriers (what batched launches use) */
+int svanon_ar_set_kernel_variant(svanon_engine* e, int variant);
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits /*[8192]*/, float* hidden /*[768]*/,
                          float* fast_logits /*[8][1000]*/);
 

@@ -418,10 +418,11 @@ int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const fl
   });
 }
 
-int svanon_ar_use_staged_weights(svanon_engine* e, int enable) {
+int svanon_ar_set_kernel_variant(svanon_engine* e, int variant) {
   return guarded([&] {
     SV_CHECK(e, "null engine");
-    e->eng.ar_staged = enable != 0;
+    SV_CHECK(variant >= 0 && variant <= 2, "variant: 0 direct loads, 1 TMA-staged weights, 2 staged + flag-in-data exchange");
+    e->eng.ar_variant = variant;
   });
 }
 
@@ -430,6 +431,7 @@ int svanon_ar_read_debug(svanon_engine* e, float* slow_logits, float* hidden, fl
     SV_CHECK(e && e->eng.finalized[MODEL_AR], "AR weights not finalized");
     SV_CUDA(cudaSetDevice(e->eng.device));
     SV_CUDA(cudaDeviceSynchronize());
+    SV_CHECK(!ar_decode_ll_aborted(), "AR decode kernel (flag-in-data variant) hit its poll watchdog");
     if (slow_logits) SV_CUDA(cudaMemcpy(slow_logits, e->eng.dbg_slow_logits, AR_VOCAB * 4, cudaMemcpyDeviceToHost));
     if (hidden) SV_CUDA(cudaMemcpy(hidden, e->eng.dbg_hidden, AR_DIM * 4, cudaMemcpyDeviceToHost));
     if (fast_logits) SV_CUDA(cudaMemcpy(fast_logits, e->eng.dbg_fast_logits, 8 * AR_CB_SIZE * 4, cudaMemcpyDeviceToHost));
@@ -633,6 +635,7 @@ int svanon_stream_history(svanon_stream* sh, int64_t* src_content, int* n_src, i
     Stream& s = sh->st;
     SV_CUDA(cudaSetDevice(s.eng->device));
     SV_CUDA(cudaDeviceSynchronize());
+    SV_CHECK(!ar_decode_ll_aborted(), "AR decode kernel (flag-in-data variant) hit its poll watchdog");
     const int ns = std::min(s.n_src, cap), np = std::min(s.n_pred, cap);
     *n_src = ns; *n_pred = np;
     if (src_content && ns > 0)

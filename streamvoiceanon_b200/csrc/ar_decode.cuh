@@ -51,6 +51,8 @@ struct ArDecodeArgs {
   float* part;                  // [B][12][nsplit][2][66]
   float* logits;                // [B][1024]
   unsigned* barrier;            // [2], zero-initialised once
+  void* ll;                     // tagged-word scratch of the barrier-free variant (ar_decode_ll.cu), zero-initialised
+  unsigned epoch;               // launch counter (>= 1) that makes this launch's tags unique
   float* dbg_slow_logits;       // [8192] or null
   float* dbg_hidden;            // [768] or null
   float* dbg_fast_logits;       // [8][1000] or null
@@ -65,5 +67,9 @@ void launch_ar_decode(const ArDecodeArgs& args, int batch, int grid, cudaStream_
 // batch-1 variant with TMA-staged weights (ar_decode_staged.cu)
 bool ar_decode_staged_supported(int grid);
 void launch_ar_decode_staged(const ArDecodeArgs& args, int grid, cudaStream_t st);
+// batch-1 variant without grid barriers: flag-in-data exchange of activations (ar_decode_ll.cu)
+size_t ar_decode_ll_scratch_words();
+int ar_decode_ll_aborted();      // 1 if a launch hit the poll watchdog (synchronises)
+void launch_ar_decode_ll(const ArDecodeArgs& args, int grid, cudaStream_t st);
 
 }  // namespace svanon

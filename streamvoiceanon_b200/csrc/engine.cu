@@ -44,7 +44,7 @@ Engine::~Engine() {
     for (auto& kv : w[m]) cudaFree(kv.second.data);
   for (float* p : owned) cudaFree(p);
   for (void* p : {(void*)ar_x, (void*)ar_h, (void*)ar_q, (void*)ar_g, (void*)ar_part, (void*)ar_logits,
-                  (void*)ar_barrier, (void*)dbg_slow_logits, (void*)dbg_hidden, (void*)dbg_fast_logits})
+                  (void*)ar_barrier, (void*)ar_ll, (void*)dbg_slow_logits, (void*)dbg_hidden, (void*)dbg_fast_logits})
     if (p) cudaFree(p);
   if (own_stream) cudaStreamDestroy(own_stream);
 }
@@ -152,6 +152,8 @@ void Engine::finalize_ar() {
   SV_CUDA(cudaMalloc(&ar_logits, (size_t)B * 1024 * 4));
   SV_CUDA(cudaMalloc(&ar_barrier, 2 * sizeof(unsigned)));
   SV_CUDA(cudaMemset(ar_barrier, 0, 2 * sizeof(unsigned)));
+  SV_CUDA(cudaMalloc(&ar_ll, ar_decode_ll_scratch_words() * 8));
+  SV_CUDA(cudaMemset(ar_ll, 0, ar_decode_ll_scratch_words() * 8));
   SV_CUDA(cudaMalloc(&dbg_slow_logits, AR_VOCAB * 4));
   SV_CUDA(cudaMalloc(&dbg_hidden, AR_DIM * 4));
   SV_CUDA(cudaMalloc(&dbg_fast_logits, AR_CODEBOOKS * AR_CB_SIZE * 4));
@@ -788,8 +790,16 @@ void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) 
   a.nsplit = nsplit;
   if (debug_logits) { a.dbg_slow_logits = dbg_slow_logits; a.dbg_hidden = dbg_hidden; a.dbg_fast_logits = dbg_fast_logits; }
   else { a.dbg_slow_logits = nullptr; a.dbg_hidden = nullptr; a.dbg_fast_logits = nullptr; }
-  if (batch == 1 && ar_staged && ar_decode_staged_supported(num_sms)) launch_ar_decode_staged(a, num_sms, st);
-  else launch_ar_decode(a, batch, num_sms, st);
+  if (batch == 1 && ar_variant == 2 && ar_decode_staged_supported(num_sms)) {
+    a.ll = ar_ll;
+    a.epoch = ++ar_epoch;
+    if ((a.epoch & 0xFFFFFu) == 0) a.epoch = ++ar_epoch;      // tag base must never be 0
+    launch_ar_decode_ll(a, num_sms, st);
+  } else if (batch == 1 && ar_variant == 1 && ar_decode_staged_supported(num_sms)) {
+    launch_ar_decode_staged(a, num_sms, st);
+  } else {
+    launch_ar_decode(a, batch, num_sms, st);
+  }
 
   for (int b = 0; b < batch; ++b) {
     streams[b]->pos_next += 2;

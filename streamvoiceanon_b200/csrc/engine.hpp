@@ -149,7 +149,9 @@ struct Engine {
   unsigned* ar_barrier = nullptr;
   float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
   bool debug_logits = false;
-  bool ar_staged = true;                       // batch-1 decode: TMA-staged weights (false: direct global loads)
+  int ar_variant = 2;                          // batch-1 decode kernel: 0 direct loads, 1 TMA-staged, 2 staged + flag-in-data (no grid barriers)
+  void* ar_ll = nullptr;
+  unsigned ar_epoch = 0;
 
   // ---- tokenizer
   const float *dft_w = nullptr, *fb_t = nullptr, *stem_w = nullptr, *stem_b = nullptr, *stem_ln_w = nullptr,

@@ -267,7 +267,7 @@ void launch_cfg(GemmBatch& b, int count, int split, cudaStream_t st) {
 }  // namespace
 
 bool g_gemm_use_pipe = true;
-bool g_gemm_use_tc = false;
+bool g_gemm_use_tc = true;
 bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pipe.cu
 bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st);     // gemm_tc.cu
 

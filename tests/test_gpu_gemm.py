@@ -22,7 +22,7 @@ def _run(mode, M, N, K, act=0, seed=0):
         _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, act, None))
         torch.cuda.synchronize()
     finally:
-        _lib.check(lib.svanon_set_gemm_mode(1))
+        _lib.check(lib.svanon_set_gemm_mode(2))
     ref = A.double() @ W.double().T + b.double()
     if act == 1:
         ref = torch.nn.functional.gelu(ref)

@@ -159,12 +159,14 @@ def test_ar_streaming_codes_vs_reference(models, gold, tape):
         assert int(pos) == int(s["pos"][i])
 
 
-def test_ar_direct_load_kernel_variant(models, gold, tape):
-    """The non-staged batch-1 kernel (weights straight from global memory) produces the same codes."""
+@pytest.mark.parametrize("variant", [0, 1])
+def test_ar_other_kernel_variants(models, gold, tape, variant):
+    """The barrier-based batch-1 kernels (0: weights straight from global memory, 1: TMA-staged weights) produce
+    the same codes as the default barrier-free variant."""
     from streamvoiceanon_b200 import _lib
     ar, _, _ = models
     s = gold("ar_stream")
-    _lib.check(_lib.load().svanon_ar_use_staged_weights(ar._engine.handle, 0))
+    _lib.check(_lib.load().svanon_ar_set_kernel_variant(ar._engine.handle, variant))
     try:
         src = _prefill(ar, s, tape)
         ar.prefill_src_condition4delay(src[:, :2].cuda())
@@ -172,7 +174,7 @@ def test_ar_direct_load_kernel_variant(models, gold, tape):
             codes, pos = ar.decode_one(src[:, t:t + 1].cuda())
             assert np.array_equal(codes.cpu().numpy(), s["codes"][i]), i
     finally:
-        _lib.check(_lib.load().svanon_ar_use_staged_weights(ar._engine.handle, 1))
+        _lib.check(_lib.load().svanon_ar_set_kernel_variant(ar._engine.handle, 2))
 
 
 def test_ar_teacher_forced_logits_vs_reference(models, gold, tape):

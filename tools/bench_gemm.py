@@ -1,0 +1,40 @@
+"""Micro-benchmark of the GEMM back ends on encoder-window shapes: warm (same weights every call, L2-resident) vs
+cold (cycling through 64 different weight matrices > L2) timings, CUDA events."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from streamvoiceanon_b200 import _lib  # noqa: E402
+from streamvoiceanon_b200.engine import Engine, ptr  # noqa: E402
+
+eng = Engine.get(0)
+lib = _lib.load()
+SHAPES = [(512, 1536, 384), (512, 384, 1536), (512, 2048, 512), (512, 512, 2048), (128, 1536, 512), (128, 512, 1536),
+          (512, 2050, 2048), (256, 128, 1408), (32, 256, 2816)]
+for mode in (1, 2):
+    _lib.check(lib.svanon_set_gemm_mode(mode))
+    for (M, N, K) in SHAPES:
+        A = torch.randn(M, K, device="cuda")
+        nW = max(2, min(64, int(400e6 / (N * K * 4))))
+        Ws = [torch.randn(N, K, device="cuda") for _ in range(nW)]
+        b = torch.randn(N, device="cuda")
+        out = torch.empty(M, N, device="cuda")
+        res = {}
+        for name, pick in (("warm", lambda i: Ws[0]), ("cold", lambda i: Ws[i % nW])):
+            for i in range(5):
+                lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(pick(i)), ptr(b), ptr(out), M, N, K, 0, None)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 100
+            e0.record()
+            for i in range(n):
+                lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(pick(i)), ptr(b), ptr(out), M, N, K, 0, None)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / n * 1e3
+        gf = 2 * M * N * K / 1e9
+        print(f"mode {mode} M={M:4d} N={N:4d} K={K:4d}: warm {res['warm']:6.1f} us ({gf / res['warm'] * 1e3:6.1f} TFLOP/s)  "
+              f"cold {res['cold']:6.1f} us ({gf / res['cold'] * 1e3:6.1f} TFLOP/s)")
+_lib.check(lib.svanon_set_gemm_mode(2))
