@@ -112,9 +112,10 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable);
 int svanon_set_gemm_mode(int mode);
 int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N,
                       int K, int act, void* cuda_stream);
-/* batch-1 decode kernel variant: 2 (default) = weights staged through shared memory with TMA bulk copies and
- * activations exchanged between CTAs as self-validating {value, tag} words (no grid barriers); 1 = staged weights +
- * grid barriers; 0 = weights loaded straight from global memory + grid barriers (what batched launches use) */
+/* batch-1 decode kernel variant: 1 (default) = weights staged through shared memory with TMA bulk copies, grid
+ * barriers between phases; 2 = staged weights + activations exchanged between CTAs as self-validating {value, tag}
+ * words instead of barriers (experimental: correct, but measured slower -- polling congestion, profiles/README.md);
+ * 0 = weights loaded straight from global memory + grid barriers (what batched launches use) */
 int svanon_ar_set_kernel_variant(svanon_engine* e, int variant);
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits /*[8192]*/, float* hidden /*[768]*/,
                          float* fast_logits /*[8][1000]*/);

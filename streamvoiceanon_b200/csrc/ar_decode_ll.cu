@@ -114,6 +114,31 @@ __device__ __forceinline__ float ll_load(const uint2* p, unsigned tag) {
   return __uint_as_float(v);
 }
 
+// N tagged words at base[i*stride]: all loads are issued back to back (they overlap in flight) and only then
+// checked; a miss re-polls the whole batch.  One L2 round trip when the data is already there.
+template <int N>
+__device__ __forceinline__ void ll_load_n(const uint2* base, int stride, unsigned tag, float (&out)[N]) {
+  unsigned v[N], t[N];
+  unsigned spins = 0;
+  while (true) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[i]), "=r"(t[i]) : "l"(base + (size_t)i * stride));
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok = ok && (t[i] == tag);
+    if (ok) break;
+    if ((++spins & 0x3FFu) == 0) {
+      if (*reinterpret_cast<volatile int*>(&g_ll_abort) != 0 || spins > (1u << 20)) {
+        g_ll_abort = 1;
+        break;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = __uint_as_float(v[i]);
+}
+
 struct Stage {
   unsigned char* wbuf;
   unsigned long long* mbar;
@@ -191,11 +216,9 @@ __device__ __forceinline__ void load_rmsnorm_ll(const uint2* x, unsigned tag, co
   for (int m = warp; m < M; m += NW) {
     float v[D / 32];
     float s = 0.f;
+    ll_load_n<D / 32>(x + m * D + lane, 32, tag, v);
 #pragma unroll
-    for (int i = 0; i < D / 32; ++i) {
-      v[i] = ll_load(x + m * D + lane + 32 * i, tag);
-      s = fmaf(v[i], v[i], s);
-    }
+    for (int i = 0; i < D / 32; ++i) s = fmaf(v[i], v[i], s);
     s = warp_sum(s);
     const float inv = rsqrtf(s / D + AR_NORM_EPS);
 #pragma unroll
@@ -298,10 +321,13 @@ __device__ __forceinline__ void layer_ll(const ArDecodeArgs& a, const ArLayerWei
       const float* kc = st.kc + ((long long)layer_idx * H + h) * a.max_seq * HEAD_DIM;
       const float* vc = st.vc + ((long long)layer_idx * H + h) * a.max_seq * HEAD_DIM;
       float2 q0, q1;
-      q0.x = ll_load(ll.q + h * HEAD_DIM + 2 * lane, tg.q);
-      q0.y = ll_load(ll.q + h * HEAD_DIM + 2 * lane + 1, tg.q);
-      q1.x = ll_load(ll.q + D + h * HEAD_DIM + 2 * lane, tg.q);
-      q1.y = ll_load(ll.q + D + h * HEAD_DIM + 2 * lane + 1, tg.q);
+      {
+        float t0[2], t1[2];
+        ll_load_n<2>(ll.q + h * HEAD_DIM + 2 * lane, 1, tg.q, t0);
+        ll_load_n<2>(ll.q + D + h * HEAD_DIM + 2 * lane, 1, tg.q, t1);
+        q0 = make_float2(t0[0], t0[1]);
+        q1 = make_float2(t1[0], t1[1]);
+      }
       float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
       float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
       for (int key = k_begin + warp; key < k_end; key += NW) {
@@ -311,10 +337,11 @@ __device__ __forceinline__ void layer_ll(const ArDecodeArgs& a, const ArLayerWei
           vv = __ldcg(reinterpret_cast<const float2*>(vc + (long long)key * HEAD_DIM) + lane);
         } else {
           const int mrow = key - pos;
-          kv.x = ll_load(ll.knew + mrow * D + h * HEAD_DIM + 2 * lane, tg.q);
-          kv.y = ll_load(ll.knew + mrow * D + h * HEAD_DIM + 2 * lane + 1, tg.q);
-          vv.x = ll_load(ll.vnew + mrow * D + h * HEAD_DIM + 2 * lane, tg.q);
-          vv.y = ll_load(ll.vnew + mrow * D + h * HEAD_DIM + 2 * lane + 1, tg.q);
+          float tk[2], tv[2];
+          ll_load_n<2>(ll.knew + mrow * D + h * HEAD_DIM + 2 * lane, 1, tg.q, tk);
+          ll_load_n<2>(ll.vnew + mrow * D + h * HEAD_DIM + 2 * lane, 1, tg.q, tv);
+          kv = make_float2(tk[0], tk[1]);
+          vv = make_float2(tv[0], tv[1]);
         }
         const float s0 = warp_sum(q0.x * kv.x + q0.y * kv.y) * 0.125f;
         const float s1 = warp_sum(q1.x * kv.x + q1.y * kv.y) * 0.125f;
@@ -359,16 +386,51 @@ __device__ __forceinline__ void layer_ll(const ArDecodeArgs& a, const ArLayerWei
     for (int it = warp; it < H * 2; it += NW) {
       const int h = it / 2, tkn = it % 2;
       const uint2* base = ll.part + ((size_t)h * a.nsplit * 2 + tkn) * PART;
+      // four strided batches over the splits: m, l, acc.x, acc.y  (unused splits of the 16-wide batch are clamped)
+      float pm[16], pl[16], pax[16], pay[16];
+      {
+        const int ns = a.nsplit;
+        const int stride = 2 * PART;
+        // clamp: entries >= ns re-read split ns-1 (valid tag) and are ignored below
+        const uint2* b0 = base;
+        unsigned spins = 0;
+        while (true) {
+          unsigned vm[16], tm[16], vl[16], tl[16], vx[16], tx[16], vy[16], ty[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint2* pp = b0 + (size_t)min(i, ns - 1) * stride;
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vm[i]), "=r"(tm[i]) : "l"(pp));
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vl[i]), "=r"(tl[i]) : "l"(pp + 1));
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx[i]), "=r"(tx[i]) : "l"(pp + 2 + 2 * lane));
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vy[i]), "=r"(ty[i]) : "l"(pp + 3 + 2 * lane));
+          }
+          bool ok = true;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            ok = ok && tm[i] == tag_part && tl[i] == tag_part && tx[i] == tag_part && ty[i] == tag_part;
+          if (ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              pm[i] = __uint_as_float(vm[i]); pl[i] = __uint_as_float(vl[i]);
+              pax[i] = __uint_as_float(vx[i]); pay[i] = __uint_as_float(vy[i]);
+            }
+            break;
+          }
+          if ((++spins & 0x3FFu) == 0) {
+            if (*reinterpret_cast<volatile int*>(&g_ll_abort) != 0 || spins > (1u << 20)) { g_ll_abort = 1; break; }
+          }
+        }
+      }
       float mm = -INFINITY;
-      for (int sp = 0; sp < a.nsplit; ++sp) mm = fmaxf(mm, ll_load(base + (size_t)sp * 2 * PART, tag_part));
+#pragma unroll
+      for (int sp = 0; sp < 16; ++sp) if (sp < a.nsplit) mm = fmaxf(mm, pm[sp]);
       float lsum = 0.f, ax = 0.f, ay = 0.f;
-      for (int sp = 0; sp < a.nsplit; ++sp) {
-        const uint2* pp = base + (size_t)sp * 2 * PART;
-        const float pm = ll_load(pp, tag_part);
-        const float c = (pm == -INFINITY) ? 0.f : expf(pm - mm);
-        lsum += ll_load(pp + 1, tag_part) * c;
-        ax += ll_load(pp + 2 + 2 * lane, tag_part) * c;
-        ay += ll_load(pp + 3 + 2 * lane, tag_part) * c;
+#pragma unroll
+      for (int sp = 0; sp < 16; ++sp) {
+        if (sp < a.nsplit) {
+          const float c = (pm[sp] == -INFINITY) ? 0.f : expf(pm[sp] - mm);
+          lsum += pl[sp] * c; ax += pax[sp] * c; ay += pay[sp] * c;
+        }
       }
       const float inv = 1.f / lsum;
       ys[tkn * D + h * HEAD_DIM + 2 * lane] = ax * inv;
@@ -380,23 +442,34 @@ __device__ __forceinline__ void layer_ll(const ArDecodeArgs& a, const ArLayerWei
     __syncthreads();
     for (int h = warp; h < H; h += NW) {
       float2 qv;
-      qv.x = ll_load(ll.q + h * HEAD_DIM + 2 * lane, tg.q);
-      qv.y = ll_load(ll.q + h * HEAD_DIM + 2 * lane + 1, tg.q);
+      {
+        float t0[2];
+        ll_load_n<2>(ll.q + h * HEAD_DIM + 2 * lane, 1, tg.q, t0);
+        qv = make_float2(t0[0], t0[1]);
+      }
       float sc[AR_CODEBOOKS];
       float2 vvs[AR_CODEBOOKS];
-      float mx = -INFINITY;
+      float2 kks[AR_CODEBOOKS];
+      // keys 0..cb-1 were published in earlier codebook steps (valid long ago): issue all their loads at once
 #pragma unroll
       for (int key = 0; key < AR_CODEBOOKS; ++key) {
-        float sv = -INFINITY;
+        kks[key] = make_float2(0.f, 0.f);
         vvs[key] = make_float2(0.f, 0.f);
         if (key <= cb) {
           const uint2* kp = ll.fkv + (((size_t)layer_idx * AR_CODEBOOKS + key) * 2 + 0) * D + h * HEAD_DIM + 2 * lane;
           const unsigned ftag = tg.base | (unsigned)(2048 + layer_idx * AR_CODEBOOKS + key);
-          const float kx = ll_load(kp, ftag), ky = ll_load(kp + 1, ftag);
-          vvs[key].x = ll_load(kp + D, ftag);
-          vvs[key].y = ll_load(kp + D + 1, ftag);
-          sv = warp_sum(qv.x * kx + qv.y * ky) * 0.125f;
+          float tk[2], tv[2];
+          ll_load_n<2>(kp, 1, ftag, tk);
+          ll_load_n<2>(kp + D, 1, ftag, tv);
+          kks[key] = make_float2(tk[0], tk[1]);
+          vvs[key] = make_float2(tv[0], tv[1]);
         }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int key = 0; key < AR_CODEBOOKS; ++key) {
+        float sv = -INFINITY;
+        if (key <= cb) sv = warp_sum(qv.x * kks[key].x + qv.y * kks[key].y) * 0.125f;
         sc[key] = sv;
         mx = fmaxf(mx, sv);
       }
@@ -420,12 +493,22 @@ __device__ __forceinline__ void layer_ll(const ArDecodeArgs& a, const ArLayerWei
     const unsigned tag = tg.next();
     tg.h = tag;
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
+      // the residual was published a phase ago: start its load now, use it after the dot product
+      unsigned rv[M], rt[M];
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(rv[m]), "=r"(rt[m]) : "l"(x_src + m * D + u));
+      }
       const float* rows[1] = {wb + (size_t)(u - s.u0) * D};
       float o[1][M];
       warp_rows_dot_s<1, M>(rows, ys, D, o);
       if (lane == 0) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) ll_store(ll.h + m * D + u, ll_load(x_src + m * D + u, tag_x_in) + o[0][m], tag);
+        for (int m = 0; m < M; ++m) {
+          const float r = (rt[m] == tag_x_in) ? __uint_as_float(rv[m]) : ll_load(x_src + m * D + u, tag_x_in);
+          ll_store(ll.h + m * D + u, r + o[0][m], tag);
+        }
       }
     }
   }
@@ -453,18 +536,38 @@ __device__ __forceinline__ void layer_ll(const ArDecodeArgs& a, const ArLayerWei
 
   // ---- phase 5: w2 + residual -> x (row 0.. of the x buffer)
   __syncthreads();
-  for (int i = threadIdx.x; i < M * I; i += NT) xs[i] = ll_load(ll.g + i, tg.g);
+  {
+    constexpr int PER = (M * I + NT - 1) / NT;
+    constexpr int FULL = (M * I) / NT;               // batches that are complete for every thread
+    float gv[FULL > 0 ? FULL : 1];
+    ll_load_n<FULL>(ll.g + threadIdx.x, NT, tg.g, gv);
+#pragma unroll
+    for (int k = 0; k < FULL; ++k) xs[threadIdx.x + k * NT] = gv[k];
+    if (PER > FULL) {
+      const int i = threadIdx.x + FULL * NT;
+      if (i < M * I) xs[i] = ll_load(ll.g + i, tg.g);
+    }
+  }
   __syncthreads();
   {
     const float* wb = begin_phase(a, sg, s);
     const unsigned tag = tg.next();
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
+      unsigned rv[M], rt[M];
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(rv[m]), "=r"(rt[m]) : "l"(ll.h + m * D + u));
+      }
       const float* rows[1] = {wb + (size_t)(u - s.u0) * I};
       float o[1][M];
       warp_rows_dot_s<1, M>(rows, xs, I, o);
       if (lane == 0) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) ll_store(ll.x + m * D + u, ll_load(ll.h + m * D + u, tg.h) + o[0][m], tag);
+        for (int m = 0; m < M; ++m) {
+          const float r = (rt[m] == tg.h) ? __uint_as_float(rv[m]) : ll_load(ll.h + m * D + u, tg.h);
+          ll_store(ll.x + m * D + u, r + o[0][m], tag);
+        }
       }
     }
     tg.x = tag;
@@ -550,10 +653,18 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_ll_kernel(const ArDecodeArgs 
     const unsigned tag_x = tg.next();
     if (blockIdx.x == 0) {
       __syncthreads();
-      for (int i = threadIdx.x; i < AR_CB_SIZE; i += NT) {
-        const float v = ll_load(ll.logits + i, tg.logits);
-        a.logits[i] = v;
-        if (a.dbg_fast_logits) a.dbg_fast_logits[cb * AR_CB_SIZE + i] = v;
+      {
+        float lv[2] = {0.f, 0.f};
+        if (threadIdx.x + NT < AR_CB_SIZE) ll_load_n<2>(ll.logits + threadIdx.x, NT, tg.logits, lv);
+        else lv[0] = ll_load(ll.logits + threadIdx.x, tg.logits);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int i = threadIdx.x + k * NT;
+          if (i < AR_CB_SIZE) {
+            a.logits[i] = lv[k];
+            if (a.dbg_fast_logits) a.dbg_fast_logits[cb * AR_CB_SIZE + i] = lv[k];
+          }
+        }
       }
       __syncthreads();
       const float* noise = st.noise ? st.noise + cb * AR_CB_SIZE : nullptr;

@@ -149,7 +149,7 @@ struct Engine {
   unsigned* ar_barrier = nullptr;
   float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
   bool debug_logits = false;
-  int ar_variant = 2;                          // batch-1 decode kernel: 0 direct loads, 1 TMA-staged, 2 staged + flag-in-data (no grid barriers)
+  int ar_variant = 1;                          // batch-1 decode kernel: 0 direct loads, 1 TMA-staged, 2 staged + flag-in-data (no grid barriers)
   void* ar_ll = nullptr;
   unsigned ar_epoch = 0;
 
