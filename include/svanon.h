@@ -110,6 +110,9 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable);
  * 0 = the register double-buffered CUDA-core kernel only.  `svanon_debug_gemm` runs one C = act(A W^T + bias)
  * (A [M][K], W [N][K], row-major fp32, K % 16 == 0; act 0 none / 1 GELU) through the selected back end (tests). */
 int svanon_set_gemm_mode(int mode);
+/* programmatic dependent launch of the GEMM kernels (default on): a GEMM's launch and weight-only prologue overlap
+ * the tail of the kernel before it; it blocks in griddepcontrol.wait before touching activations */
+int svanon_set_pdl(int enable);
 int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N,
                       int K, int act, void* cuda_stream);
 /* batch-1 decode kernel variant: 1 (default) = weights staged through shared memory with TMA bulk copies, grid

@@ -41,6 +41,7 @@ _SIGS = {
     "svanon_ar_position": (C.c_int, [_p]),
     "svanon_ar_debug_logits": (C.c_int, [_p, C.c_int]),
     "svanon_set_gemm_mode": (C.c_int, [C.c_int]),
+    "svanon_set_pdl": (C.c_int, [C.c_int]),
     "svanon_debug_gemm": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "svanon_ar_set_kernel_variant": (C.c_int, [_p, C.c_int]),
     "svanon_ar_read_debug": (C.c_int, [_p, _p, _p, _p]),

@@ -10,6 +10,7 @@
 namespace svanon {
 extern bool g_gemm_use_pipe;
 extern bool g_gemm_use_tc;
+extern bool g_use_pdl;
 }
 using namespace svanon;
 
@@ -394,6 +395,11 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable) {
     SV_CHECK(e, "null engine");
     e->eng.debug_logits = enable != 0;
   });
+}
+
+int svanon_set_pdl(int enable) {
+  g_use_pdl = enable != 0;
+  return 0;
 }
 
 int svanon_set_gemm_mode(int mode) {

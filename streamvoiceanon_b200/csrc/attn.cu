@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(QW * 32)
 attention_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
                  long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
                  int qpos0, int window) {
+  pdl_trigger();
   __shared__ float Ks[KT][HEAD_DIM + 1];
   __shared__ float Vs[KT][HEAD_DIM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,6 +97,7 @@ attention_kernel(const float* __restrict__ q, long long q_ld, const float* __res
 
 __global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float* __restrict__ kc, float* __restrict__ vc,
                                  int max_seq, int pos0) {
+  pdl_trigger();
   const int row = blockIdx.x;
   const int D = heads * HEAD_DIM;
   const float* kr = qkv + (long long)row * 3 * D + D;

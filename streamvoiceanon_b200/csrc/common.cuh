@@ -36,6 +36,14 @@ extern long long g_kernel_launches;
     SV_CUDA(cudaGetLastError());      \
   } while (0)
 
+// Programmatic dependent launch: every kernel lets its successor start launching right away; kernels launched with
+// the programmatic-serialization attribute (the GEMMs) block in pdl_wait() until their predecessors have completed
+// and flushed, after doing the part of their prologue that only touches weights.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------- model constants
 // configs/hydra_arcs/vc/firefly_arvc_bsq_8192_delay0_8.yaml
 constexpr int AR_DIM = 768;

@@ -42,6 +42,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 template <int BM, int BN, int MG, int NG, bool SPLIT>
 __global__ void __launch_bounds__((BM / (4 * MG)) * (BN / (4 * NG)))
 gemm_kernel(const GemmBatch batch) {
+  pdl_trigger();
   constexpr int TM = 4 * MG, TN = 4 * NG;
   constexpr int NTX = BN / TN, NTY = BM / TM, NT = NTX * NTY;
   constexpr int A_F4 = BM * BK / 4, B_F4 = BN * BK / 4;
@@ -266,6 +267,7 @@ void launch_cfg(GemmBatch& b, int count, int split, cudaStream_t st) {
 
 }  // namespace
 
+bool g_use_pdl = true;      // programmatic dependent launch for the GEMM kernels (gemm_pipe.cu, gemm_tc.cu)
 bool g_gemm_use_pipe = true;
 bool g_gemm_use_tc = true;
 bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pipe.cu

@@ -17,6 +17,8 @@ namespace cg = cooperative_groups;
 
 namespace svanon {
 
+extern bool g_use_pdl;
+
 namespace {
 
 constexpr int PK = 32;         // K-slab depth (floats) = one 128-byte row
@@ -49,6 +51,8 @@ gemm_pipe_kernel(const PipeBatch batch) {
   constexpr int A_CH = BM * 8, B_CH = BN * 8;                 // 16-byte chunks per stage
   static_assert(BM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
   extern __shared__ __align__(128) float smem[];
+  pdl_trigger();
+  pdl_wait();
 
   const int split = SPLIT ? batch.split : 1;
   const int zb = SPLIT ? blockIdx.z / split : blockIdx.z;
@@ -194,23 +198,22 @@ void launch_pipe_cfg(PipeBatch& b, int count, int split, cudaStream_t st) {
     SV_CUDA(cudaFuncSetAttribute(gemm_pipe_kernel<BM, BN, TM, TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
-  if (split > 1) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(NT);
-    cfg.dynamicSmemBytes = SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = split;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_pipe_kernel<BM, BN, TM, TN, true>, b));
-  } else {
-    gemm_pipe_kernel<BM, BN, TM, TN, false><<<grid, NT, SMEM, st>>>(b);
-  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 1;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = split;
+  cfg.attrs = attr;
+  cfg.numAttrs = split > 1 ? 2 : 1;
+  if (split > 1) SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_pipe_kernel<BM, BN, TM, TN, true>, b));
+  else SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_pipe_kernel<BM, BN, TM, TN, false>, b));
 }
 
 }  // namespace

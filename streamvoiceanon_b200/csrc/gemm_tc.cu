@@ -23,6 +23,8 @@ namespace cg = cooperative_groups;
 
 namespace svanon {
 
+extern bool g_use_pdl;
+
 namespace {
 
 constexpr int TK = 32;                 // K-slab = one 128-byte swizzle row
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   const int it_end = (int)((long long)total * (rank + 1) / split);
   const int n_it = it_end - it_begin;
 
+  pdl_trigger();
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_d = tmem_holder;
+  pdl_wait();            // everything above touched only weights / on-chip state; activations come next
 
   if (warp < 4) {
     // =========================================================== producers
@@ -339,23 +343,22 @@ void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
     SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
-  if (split > 1) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = split;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, b));
-  } else {
-    gemm_tc_kernel<BN, STAGES, false><<<grid, TC_THREADS, SMEM, st>>>(b);
-  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 1;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = split;
+  cfg.attrs = attr;
+  cfg.numAttrs = split > 1 ? 2 : 1;
+  if (split > 1) SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, b));
+  else SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false>, b));
 }
 
 }  // namespace

@@ -30,6 +30,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 template <int MAXPT>
 __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
                                  const float* __restrict__ b, int C, float eps) {
+  pdl_trigger();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * C;
@@ -63,6 +64,7 @@ template <int MAXPT>
 __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ dw_w,
                                   const float* __restrict__ dw_b, const float* __restrict__ ln_w,
                                   const float* __restrict__ ln_b, int C, float eps) {
+  pdl_trigger();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   float v[MAXPT];
@@ -99,6 +101,7 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict
 template <int MAXPT>
 __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w, int C,
                                float eps) {
+  pdl_trigger();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   float v[MAXPT];
@@ -120,6 +123,7 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ 
 // apply_rotary_emb (dual_ar_stream.py:1004-1016 / windowed_transformer.py:368-380): pairs (2i,2i+1),
 // table entry [pos][i] = (cos, sin) already rounded to bf16 and widened back to fp32.
 __global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict__ table, int rows, int heads, int pos0) {
+  pdl_trigger();
   const int D = heads * HEAD_DIM;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over rows * 2 * D/2
   const long long total = (long long)rows * D;                              // q pairs + k pairs = 2 * D/2 * rows
@@ -138,6 +142,7 @@ __global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict_
 }
 
 __global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__ out, long long rows, int I) {
+  pdl_trigger();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * I) return;
   const long long r = idx / I;
@@ -148,6 +153,7 @@ __global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__
 
 // LinearSpectrogram magnitude, spectrogram.py:62: sqrt(re^2 + im^2 + 1e-6); pad columns are zero.
 __global__ void magnitude_kernel(const float* __restrict__ spec, float* __restrict__ mag, int T, int ld_in) {
+  pdl_trigger();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)T * N_FREQ_PAD) return;
   const int t = idx / N_FREQ_PAD, f = idx % N_FREQ_PAD;
@@ -163,6 +169,7 @@ __global__ void magnitude_kernel(const float* __restrict__ spec, float* __restri
 // not change signs, skipped), bit_i = proj_i > 0, id = sum bit_i << (12 - i).  One warp per token.
 __global__ void bsq_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
                            long long* __restrict__ ids, int T) {
+  pdl_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= T) return;
   const float* zr = z + (long long)warp * ENC_DIM;
@@ -184,6 +191,7 @@ __global__ void bsq_kernel(const float* __restrict__ z, const float* __restrict_
 // (vendored twin: finite_scalar_quantization.py:143-162, residual_fsq.py:112-156).
 __global__ void fsq_lookup_kernel(const long long* __restrict__ codes, long long ld, const float* __restrict__ w,
                                   const float* __restrict__ b, float* __restrict__ z, int T) {
+  pdl_trigger();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)T * 512) return;
   const int t = idx / 512, c = idx % 512, g = c / 64, o = c % 64;
@@ -204,6 +212,7 @@ __global__ void fsq_lookup_kernel(const long long* __restrict__ codes, long long
 // activation_post (SiLU) + conv_post (16 -> 1, k = 13, causal) + tanh, firefly.py:289-291.
 __global__ void conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                  float* __restrict__ out, int L) {
+  pdl_trigger();
   __shared__ float ws[13 * 16];
   for (int i = threadIdx.x; i < 13 * 16; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -224,6 +233,7 @@ __global__ void conv_post_kernel(const float* __restrict__ x, const float* __res
 
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
                                    float* __restrict__ out, int C, long long out_ld) {
+  pdl_trigger();
   const long long row = blockIdx.x;
   const float* src = table + idx[row] * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) out[row * out_ld + c] = src[c];
@@ -231,6 +241,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const long l
 
 __global__ void embed_codes_kernel(const float* __restrict__ table, const int* __restrict__ codes, long long ld,
                                    float* __restrict__ out, long long out_ld) {
+  pdl_trigger();
   const long long t = blockIdx.x;
   for (int c = threadIdx.x; c < AR_DIM; c += blockDim.x) {
     float s = 0.f;
@@ -243,17 +254,20 @@ __global__ void embed_codes_kernel(const float* __restrict__ table, const int* _
 
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst,
                                  long long dst_ld, int C) {
+  pdl_trigger();
   const long long row = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) dst[row * dst_ld + c] = src[row * src_ld + c];
 }
 
 __global__ void scale_add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                   float* __restrict__ out, long long n, float s) {
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (a[i] + b[i] + c[i]) * s;
 }
 
 __global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -262,6 +276,7 @@ __global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
 template <typename OutT>
 __global__ void concat_cols_kernel(const int* __restrict__ a, long long a_ld, int a_n, const int* __restrict__ b,
                                    long long b_ld, int b_n, OutT* __restrict__ out, long long out_ld, int rows) {
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = a_n + b_n;
   if (idx >= rows * n) return;
@@ -270,10 +285,12 @@ __global__ void concat_cols_kernel(const int* __restrict__ a, long long a_ld, in
 }
 
 __global__ void append_codes_kernel(const int* __restrict__ codes, int* __restrict__ hist, long long ld, int col) {
+  pdl_trigger();
   if (threadIdx.x < AR_CODEBOOKS) hist[threadIdx.x * ld + col] = codes[threadIdx.x];
 }
 
 __global__ void i64_to_i32_kernel(const long long* __restrict__ in, int* __restrict__ out, long long n) {
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int)in[i];
 }

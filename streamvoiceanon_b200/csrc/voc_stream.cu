@@ -24,6 +24,7 @@ constexpr int RD[3] = {1, 3, 5};
 
 // dst[i] = src[i + shift] for i < margin, possibly overlapping: walk upwards in chunks, read-all then write-all.
 __global__ void __launch_bounds__(256) shift_history_kernel(const ShiftDesc* __restrict__ descs) {
+  pdl_trigger();
   const ShiftDesc d = descs[blockIdx.x];
   constexpr int PER = 8;
   for (int base = 0; base < d.margin_floats; base += 256 * PER) {
