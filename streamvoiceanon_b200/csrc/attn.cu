@@ -17,6 +17,7 @@ attention_kernel(const float* __restrict__ q, long long q_ld, const float* __res
                  long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
                  int qpos0, int window) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float Ks[KT][HEAD_DIM + 1];
   __shared__ float Vs[KT][HEAD_DIM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,6 +99,7 @@ attention_kernel(const float* __restrict__ q, long long q_ld, const float* __res
 __global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float* __restrict__ kc, float* __restrict__ vc,
                                  int max_seq, int pos0) {
   pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   const int D = heads * HEAD_DIM;
   const float* kr = qkv + (long long)row * 3 * D + D;
@@ -117,7 +119,7 @@ void launch_attention(const float* q, long long q_ld, const float* k, const floa
                       cudaStream_t st) {
   if (nq <= 0) return;
   dim3 grid((nq + QW - 1) / QW, heads);
-  attention_kernel<<<grid, QW * 32, 0, st>>>(q, q_ld, k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0,
+  launch_pdl(attention_kernel, dim3(grid), dim3(QW * 32), 0, st, q, q_ld, k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0,
                                              window);
   SV_LAUNCHED();
 }
@@ -125,7 +127,7 @@ void launch_attention(const float* q, long long q_ld, const float* k, const floa
 void launch_kv_append(const float* qkv, int rows, int heads, float* kc, float* vc, int max_seq, int pos0,
                       cudaStream_t st) {
   if (rows <= 0) return;
-  kv_append_kernel<<<rows, 256, 0, st>>>(qkv, heads, kc, vc, max_seq, pos0);
+  launch_pdl(kv_append_kernel, dim3(rows), dim3(256), 0, st, qkv, heads, kc, vc, max_seq, pos0);
   SV_LAUNCHED();
 }
 

@@ -39,7 +39,24 @@ extern long long g_kernel_launches;
 // Programmatic dependent launch: every kernel lets its successor start launching right away; kernels launched with
 // the programmatic-serialization attribute (the GEMMs) block in pdl_wait() until their predecessors have completed
 // and flushed, after doing the part of their prologue that only touches weights.
+extern bool g_use_pdl;
 #ifdef __CUDACC__
+// launch with the programmatic-stream-serialization attribute (the kernel must call pdl_wait() before it touches
+// anything a predecessor wrote)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SV_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif

@@ -17,8 +17,6 @@ namespace cg = cooperative_groups;
 
 namespace svanon {
 
-extern bool g_use_pdl;
-
 namespace {
 
 constexpr int PK = 32;         // K-slab depth (floats) = one 128-byte row

@@ -23,8 +23,6 @@ namespace cg = cooperative_groups;
 
 namespace svanon {
 
-extern bool g_use_pdl;
-
 namespace {
 
 constexpr int TK = 32;                 // K-slab = one 128-byte swizzle row

@@ -31,6 +31,7 @@ template <int MAXPT>
 __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
                                  const float* __restrict__ b, int C, float eps) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * C;
@@ -65,6 +66,7 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict
                                   const float* __restrict__ dw_b, const float* __restrict__ ln_w,
                                   const float* __restrict__ ln_b, int C, float eps) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   float v[MAXPT];
@@ -102,6 +104,7 @@ template <int MAXPT>
 __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w, int C,
                                float eps) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   float v[MAXPT];
@@ -124,6 +127,7 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ 
 // table entry [pos][i] = (cos, sin) already rounded to bf16 and widened back to fp32.
 __global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict__ table, int rows, int heads, int pos0) {
   pdl_trigger();
+  pdl_wait();
   const int D = heads * HEAD_DIM;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over rows * 2 * D/2
   const long long total = (long long)rows * D;                              // q pairs + k pairs = 2 * D/2 * rows
@@ -143,6 +147,7 @@ __global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict_
 
 __global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__ out, long long rows, int I) {
   pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * I) return;
   const long long r = idx / I;
@@ -154,6 +159,7 @@ __global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__
 // LinearSpectrogram magnitude, spectrogram.py:62: sqrt(re^2 + im^2 + 1e-6); pad columns are zero.
 __global__ void magnitude_kernel(const float* __restrict__ spec, float* __restrict__ mag, int T, int ld_in) {
   pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)T * N_FREQ_PAD) return;
   const int t = idx / N_FREQ_PAD, f = idx % N_FREQ_PAD;
@@ -170,6 +176,7 @@ __global__ void magnitude_kernel(const float* __restrict__ spec, float* __restri
 __global__ void bsq_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
                            long long* __restrict__ ids, int T) {
   pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= T) return;
   const float* zr = z + (long long)warp * ENC_DIM;
@@ -192,6 +199,7 @@ __global__ void bsq_kernel(const float* __restrict__ z, const float* __restrict_
 __global__ void fsq_lookup_kernel(const long long* __restrict__ codes, long long ld, const float* __restrict__ w,
                                   const float* __restrict__ b, float* __restrict__ z, int T) {
   pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)T * 512) return;
   const int t = idx / 512, c = idx % 512, g = c / 64, o = c % 64;
@@ -213,6 +221,7 @@ __global__ void fsq_lookup_kernel(const long long* __restrict__ codes, long long
 __global__ void conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                  float* __restrict__ out, int L) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float ws[13 * 16];
   for (int i = threadIdx.x; i < 13 * 16; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -234,6 +243,7 @@ __global__ void conv_post_kernel(const float* __restrict__ x, const float* __res
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
                                    float* __restrict__ out, int C, long long out_ld) {
   pdl_trigger();
+  pdl_wait();
   const long long row = blockIdx.x;
   const float* src = table + idx[row] * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) out[row * out_ld + c] = src[c];
@@ -242,6 +252,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const long l
 __global__ void embed_codes_kernel(const float* __restrict__ table, const int* __restrict__ codes, long long ld,
                                    float* __restrict__ out, long long out_ld) {
   pdl_trigger();
+  pdl_wait();
   const long long t = blockIdx.x;
   for (int c = threadIdx.x; c < AR_DIM; c += blockDim.x) {
     float s = 0.f;
@@ -255,6 +266,7 @@ __global__ void embed_codes_kernel(const float* __restrict__ table, const int* _
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst,
                                  long long dst_ld, int C) {
   pdl_trigger();
+  pdl_wait();
   const long long row = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) dst[row * dst_ld + c] = src[row * src_ld + c];
 }
@@ -262,12 +274,14 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld
 __global__ void scale_add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                   float* __restrict__ out, long long n, float s) {
   pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (a[i] + b[i] + c[i]) * s;
 }
 
 __global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
   pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -277,6 +291,7 @@ template <typename OutT>
 __global__ void concat_cols_kernel(const int* __restrict__ a, long long a_ld, int a_n, const int* __restrict__ b,
                                    long long b_ld, int b_n, OutT* __restrict__ out, long long out_ld, int rows) {
   pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = a_n + b_n;
   if (idx >= rows * n) return;
@@ -286,11 +301,13 @@ __global__ void concat_cols_kernel(const int* __restrict__ a, long long a_ld, in
 
 __global__ void append_codes_kernel(const int* __restrict__ codes, int* __restrict__ hist, long long ld, int col) {
   pdl_trigger();
+  pdl_wait();
   if (threadIdx.x < AR_CODEBOOKS) hist[threadIdx.x * ld + col] = codes[threadIdx.x];
 }
 
 __global__ void i64_to_i32_kernel(const long long* __restrict__ in, int* __restrict__ out, long long n) {
   pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int)in[i];
 }
@@ -303,8 +320,8 @@ void launch_layernorm(const float* x, float* y, const float* w, const float* b, 
                       cudaStream_t st) {
   if (rows <= 0) return;
   SV_CHECK(C <= 2048, "layernorm C");
-  if (C <= 512) layernorm_kernel<4><<<rows, 128, 0, st>>>(x, y, w, b, C, eps);
-  else layernorm_kernel<8><<<rows, 256, 0, st>>>(x, y, w, b, C, eps);
+  if (C <= 512) launch_pdl(layernorm_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, w, b, C, eps);
+  else launch_pdl(layernorm_kernel<8>, dim3(rows), dim3(256), 0, st, x, y, w, b, C, eps);
   SV_LAUNCHED();
 }
 
@@ -312,80 +329,80 @@ void launch_dwconv7_ln(const float* x, float* y, const float* dw_w, const float*
                        const float* ln_b, int rows, int C, float eps, cudaStream_t st) {
   if (rows <= 0) return;
   SV_CHECK(C <= 512, "dwconv C");
-  dwconv7_ln_kernel<4><<<rows, 128, 0, st>>>(x, y, dw_w, dw_b, ln_w, ln_b, C, eps);
+  launch_pdl(dwconv7_ln_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, dw_w, dw_b, ln_w, ln_b, C, eps);
   SV_LAUNCHED();
 }
 
 void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st) {
   if (rows <= 0) return;
   SV_CHECK(C <= 1024, "rmsnorm C");
-  rmsnorm_kernel<4><<<rows, 256, 0, st>>>(x, y, w, C, eps);
+  launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, x, y, w, C, eps);
   SV_LAUNCHED();
 }
 
 void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos0, cudaStream_t st) {
   if (rows <= 0) return;
   const long long total = (long long)rows * heads * HEAD_DIM;
-  rope_qk_kernel<<<blocks_for(total, 256), 256, 0, st>>>(qkv, table, rows, heads, pos0);
+  launch_pdl(rope_qk_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, qkv, table, rows, heads, pos0);
   SV_LAUNCHED();
 }
 
 void launch_silu_mul(const float* h13, float* out, int rows, int I, cudaStream_t st) {
   if (rows <= 0) return;
-  silu_mul_kernel<<<blocks_for((long long)rows * I, 256), 256, 0, st>>>(h13, out, rows, I);
+  launch_pdl(silu_mul_kernel, dim3(blocks_for((long long)rows * I, 256)), dim3(256), 0, st, h13, out, rows, I);
   SV_LAUNCHED();
 }
 
 void launch_magnitude(const float* spec, float* mag, int T, int ld_in, cudaStream_t st) {
   if (T <= 0) return;
-  magnitude_kernel<<<blocks_for((long long)T * N_FREQ_PAD, 256), 256, 0, st>>>(spec, mag, T, ld_in);
+  launch_pdl(magnitude_kernel, dim3(blocks_for((long long)T * N_FREQ_PAD, 256)), dim3(256), 0, st, spec, mag, T, ld_in);
   SV_LAUNCHED();
 }
 
 void launch_bsq(const float* z, const float* w, const float* b, long long* ids, int T, cudaStream_t st) {
   if (T <= 0) return;
-  bsq_kernel<<<blocks_for((long long)T * 32, 128), 128, 0, st>>>(z, w, b, ids, T);
+  launch_pdl(bsq_kernel, dim3(blocks_for((long long)T * 32, 128)), dim3(128), 0, st, z, w, b, ids, T);
   SV_LAUNCHED();
 }
 
 void launch_fsq_lookup(const long long* codes, long long ld, const float* w, const float* b, float* z, int T,
                        cudaStream_t st) {
   if (T <= 0) return;
-  fsq_lookup_kernel<<<blocks_for((long long)T * 512, 256), 256, 0, st>>>(codes, ld, w, b, z, T);
+  launch_pdl(fsq_lookup_kernel, dim3(blocks_for((long long)T * 512, 256)), dim3(256), 0, st, codes, ld, w, b, z, T);
   SV_LAUNCHED();
 }
 
 void launch_conv_post(const float* x, const float* w, const float* b, float* out, int L, cudaStream_t st) {
   if (L <= 0) return;
-  conv_post_kernel<<<blocks_for(L, 256), 256, 0, st>>>(x, w, b, out, L);
+  launch_pdl(conv_post_kernel, dim3(blocks_for(L, 256)), dim3(256), 0, st, x, w, b, out, L);
   SV_LAUNCHED();
 }
 
 void launch_gather_rows(const float* table, const long long* idx, float* out, int rows, int C, long long out_ld,
                         cudaStream_t st) {
   if (rows <= 0) return;
-  gather_rows_kernel<<<rows, 256, 0, st>>>(table, idx, out, C, out_ld);
+  launch_pdl(gather_rows_kernel, dim3(rows), dim3(256), 0, st, table, idx, out, C, out_ld);
   SV_LAUNCHED();
 }
 
 void launch_embed_codes(const float* table, const int* codes, long long ld, float* out, int T, long long out_ld,
                         cudaStream_t st) {
   if (T <= 0) return;
-  embed_codes_kernel<<<T, 256, 0, st>>>(table, codes, ld, out, out_ld);
+  launch_pdl(embed_codes_kernel, dim3(T), dim3(256), 0, st, table, codes, ld, out, out_ld);
   SV_LAUNCHED();
 }
 
 void launch_copy_rows(const float* src, long long src_ld, float* dst, long long dst_ld, int rows, int C,
                       cudaStream_t st) {
   if (rows <= 0) return;
-  copy_rows_kernel<<<rows, 256, 0, st>>>(src, src_ld, dst, dst_ld, C);
+  launch_pdl(copy_rows_kernel, dim3(rows), dim3(256), 0, st, src, src_ld, dst, dst_ld, C);
   SV_LAUNCHED();
 }
 
 void launch_scale_add3(const float* a, const float* b, const float* c, float* out, long long n, float s,
                        cudaStream_t st) {
   if (n <= 0) return;
-  scale_add3_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a, b, c, out, n, s);
+  launch_pdl(scale_add3_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, a, b, c, out, n, s);
   SV_LAUNCHED();
 }
 
@@ -393,25 +410,25 @@ void launch_concat_cols(const int* a, long long a_ld, int a_n, const int* b, lon
                         long long out_ld, int rows, bool out_i64, cudaStream_t st) {
   const int n = rows * (a_n + b_n);
   if (n <= 0) return;
-  if (out_i64) concat_cols_kernel<long long><<<blocks_for(n, 256), 256, 0, st>>>(a, a_ld, a_n, b, b_ld, b_n, (long long*)out, out_ld, rows);
-  else concat_cols_kernel<int><<<blocks_for(n, 256), 256, 0, st>>>(a, a_ld, a_n, b, b_ld, b_n, (int*)out, out_ld, rows);
+  if (out_i64) launch_pdl(concat_cols_kernel<long long>, dim3(blocks_for(n, 256)), dim3(256), 0, st, a, a_ld, a_n, b, b_ld, b_n, (long long*)out, out_ld, rows);
+  else launch_pdl(concat_cols_kernel<int>, dim3(blocks_for(n, 256)), dim3(256), 0, st, a, a_ld, a_n, b, b_ld, b_n, (int*)out, out_ld, rows);
   SV_LAUNCHED();
 }
 
 void launch_append_codes(const int* codes, int* hist, long long ld, int col, cudaStream_t st) {
-  append_codes_kernel<<<1, 32, 0, st>>>(codes, hist, ld, col);
+  launch_pdl(append_codes_kernel, dim3(1), dim3(32), 0, st, codes, hist, ld, col);
   SV_LAUNCHED();
 }
 
 void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t st) {
   if (n <= 0) return;
-  i64_to_i32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n);
+  launch_pdl(i64_to_i32_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, in, out, n);
   SV_LAUNCHED();
 }
 
 void launch_fill(float* p, long long n, float v, cudaStream_t st) {
   if (n <= 0) return;
-  fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, n, v);
+  launch_pdl(fill_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, p, n, v);
   SV_LAUNCHED();
 }
 

@@ -25,6 +25,7 @@ constexpr int RD[3] = {1, 3, 5};
 // dst[i] = src[i + shift] for i < margin, possibly overlapping: walk upwards in chunks, read-all then write-all.
 __global__ void __launch_bounds__(256) shift_history_kernel(const ShiftDesc* __restrict__ descs) {
   pdl_trigger();
+  pdl_wait();
   const ShiftDesc d = descs[blockIdx.x];
   constexpr int PER = 8;
   for (int base = 0; base < d.margin_floats; base += 256 * PER) {
@@ -169,7 +170,7 @@ void Engine::voc_step(VocState& vs, const long long* codes, long long ld, float*
     rows = Lo;
   }
   launch_conv_post(cur, post_w, post_b, wave_out, rows, st);
-  shift_history_kernel<<<vs.n_desc, 256, 0, st>>>(vs.desc_dev);
+  launch_pdl(shift_history_kernel, dim3(vs.n_desc), dim3(256), 0, st, vs.desc_dev);
   SV_LAUNCHED();
   vs.primed_frames += c;
 }
