@@ -152,6 +152,41 @@ int svanon_stream_last_timing(svanon_stream* s, float* ms);
 int svanon_stream_history(svanon_stream* s, int64_t* src_content, int* n_src, int64_t* pred_codes, int* n_pred,
                           int cap);
 
+/* ---- many concurrent streams in lock-step --------------------------------------------------------------------
+ * The reference is strictly batch-1 (max_batch_size=1, evaluations/infer_arvc.py:56; `x.view(1, 1, -1)`,
+ * modules/dual_ar_stream.py:544): N concurrent utterances are N sequential calls.  These entry points run the same
+ * per-stream arithmetic for N independent streams with ONE pass over the weights per step (BASELINE configs 3-4);
+ * every stream produces what it would produce alone.
+ *
+ * `svanon_enc_encode_batch`: FireflyArchitecture.encode (firefly_encoder.py:553-566) for n_utt utterances of the
+ * same length; waves [n_utt][n_samples], ids_out [n_utt][svanon_enc_num_ids(n_samples)].
+ * `svanon_ar_decode_many`: ARVCWrapper.decode_one (arvc_wrapper.py:121-126) for any number of streams: the frame
+ * as tensor-core GEMMs over all streams + per-stream KV-cache attention and samplers (svanon_ar_decode_batch keeps
+ * the single persistent kernel, 1/2/4 streams).  content_ids [n], noise NULL or [n][8][1000], codes_out [n][8].
+ * A svanon_batch is InferenceWrapper.process_one_chunk (infer_arvc.py:492-596) for N streams that started
+ * together: create the streams, give each its prompt (svanon_stream_set_prompt, same delay), then
+ * `svanon_batch_setup` (= setup_stream_caches, :443-460, for all of them; the vocoder runs incrementally, so
+ * decode_window_frames - decode_chunk_frames must be >= 15) and one `svanon_batch_process_chunk` per chunk:
+ * wave_chunks / wave_out [n][chunk*2048], noise NULL or [n][chunk][8][1000].  Streams re-prompt individually.
+ * The batch does not own the streams; destroy it before them. */
+typedef struct svanon_batch svanon_batch;
+int svanon_enc_encode_batch(svanon_engine* e, const float* waves, int n_utt, int64_t n_samples, int64_t* ids_out,
+                            void* cuda_stream);
+int svanon_ar_decode_many(svanon_stream* const* streams, int n, const int64_t* content_ids, const float* noise,
+                          int32_t* codes_out, void* cuda_stream);
+int svanon_batch_create(svanon_engine* e, svanon_stream* const* streams, int n, svanon_batch** out);
+void svanon_batch_destroy(svanon_batch* b);
+int svanon_batch_setup(svanon_batch* b, int encode_window_frames, int decode_window_frames, int max_seq_frames,
+                       int buffer_frames, int decode_chunk_frames);
+int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_samples_per_stream, const float* noise,
+                               float* wave_out, void* cuda_stream);
+/* decode path of the batch: 0 (default) = persistent kernel for 1/2/4 streams, many-stream kernels otherwise;
+ * 1 = always the many-stream kernels */
+int svanon_batch_set_ar_path(svanon_batch* b, int path);
+/* per-stage device time of the last non-warm-up chunk, as svanon_stream_last_timing */
+int svanon_batch_set_timing(svanon_batch* b, int enable);
+int svanon_batch_last_timing(svanon_batch* b, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,10 +7,11 @@ library (include/svanon.h, streamvoiceanon_b200/libsvanon_b200.so):
     ContentTokenizer   <-> modules.vqgan.modules.firefly_encoder.FireflyArchitecture   (encode)
     Vocoder            <-> modules.vqgan.modules.firefly.FireflyArchitecture           (quantizer.decode, head)
     StreamSession      <-> InferenceWrapper.process_one_chunk as one library call per chunk
+    BatchSession       <-> the same loop for N concurrent streams in lock-step (the reference is batch-1)
 """
 from . import synth  # noqa: F401
 
-__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "synth"]
+__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "BatchSession", "synth"]
 
 
 def __getattr__(name):
@@ -20,7 +21,7 @@ def __getattr__(name):
     if name in ("ContentTokenizer", "Vocoder"):
         from . import firefly
         return getattr(firefly, name)
-    if name == "StreamSession":
-        from .streaming import StreamSession
-        return StreamSession
+    if name in ("StreamSession", "BatchSession"):
+        from . import streaming
+        return getattr(streaming, name)
     raise AttributeError(name)

@@ -1,97 +1,17 @@
 // C ABI (include/svanon.h): argument marshalling (host or device pointers), stream lifecycle and the
 // per-chunk loop.  All model work is in engine.cu / ar_decode.cu.
-#include "../../include/svanon.h"
-
-#include <algorithm>
-#include <mutex>
-
-#include "engine.hpp"
+#include "api_common.hpp"
 
 namespace svanon {
 extern bool g_gemm_use_pipe;
 extern bool g_gemm_use_tc;
 extern bool g_use_pdl;
 }
-using namespace svanon;
-
-struct svanon_engine {
-  Engine eng;
-  Workspace staging;      // host<->device staging of API arguments
-  std::mutex mu;
-};
-struct svanon_stream {
-  Stream st;
-  svanon_engine* owner = nullptr;
-};
+namespace svanon {
+thread_local std::string g_api_err;
+}
 
 namespace {
-
-thread_local std::string g_err;
-
-template <typename F>
-int guarded(F&& f) {
-  try {
-    f();
-    return 0;
-  } catch (const std::exception& e) {
-    g_err = e.what();
-    return 1;
-  } catch (...) {
-    g_err = "unknown error";
-    return 1;
-  }
-}
-
-bool on_device(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-
-// Per-call argument staging.  Inputs in host memory are copied to the staging arena; outputs in host memory are
-// produced in the arena and copied back (followed by one stream synchronisation) when the scope ends.
-struct Args {
-  svanon_engine* h;
-  cudaStream_t st;
-  struct Out { void* host; void* dev; size_t bytes; };
-  std::vector<Out> outs;
-  Args(svanon_engine* h_, void* stream, size_t budget) : h(h_), st((cudaStream_t)stream) {
-    SV_CUDA(cudaSetDevice(h->eng.device));
-    h->staging.ensure(budget + (1u << 20));
-    h->staging.reset();
-  }
-  template <typename T>
-  const T* in(const T* p, size_t n) {
-    if (!p) return nullptr;
-    if (on_device(p)) return p;
-    T* d = (T*)h->staging.alloc_bytes(n * sizeof(T));
-    SV_CUDA(cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
-    return d;
-  }
-  template <typename T>
-  T* out(T* p, size_t n) {
-    if (on_device(p)) return p;
-    T* d = (T*)h->staging.alloc_bytes(n * sizeof(T));
-    outs.push_back({(void*)p, (void*)d, n * sizeof(T)});
-    return d;
-  }
-  void finish() {
-    if (outs.empty()) return;
-    for (auto& o : outs) SV_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
-    SV_CUDA(cudaStreamSynchronize(st));
-    outs.clear();
-  }
-};
-
-template <typename T>
-T* dmalloc(size_t n) {
-  T* p = nullptr;
-  SV_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-  return p;
-}
 
 void set_prompt_copy(Stream& s, const long long* ref_content, const int* ref_audio, int T, int keep, const float* style,
                      const float* timbre, cudaStream_t st) {
@@ -137,7 +57,7 @@ void decode_frames(Stream& s, const long long* content_ids_dev, int n, const flo
 
 extern "C" {
 
-const char* svanon_last_error(void) { return g_err.c_str(); }
+const char* svanon_last_error(void) { return g_api_err.c_str(); }
 int64_t svanon_kernel_launches(void) { return g_kernel_launches; }
 
 int svanon_engine_create(int device, svanon_engine** out) {
@@ -186,7 +106,7 @@ int svanon_enc_encode(svanon_engine* e, const float* wave, int64_t n, int64_t* i
     Args a(e, stream, (size_t)n * 4 + 65536);
     const float* w = a.in(wave, (size_t)n);
     long long* ids = (long long*)a.out(ids_out, (size_t)svanon_enc_num_ids(n));
-    e->eng.enc_encode(w, n, ids, a.st);
+    e->eng.enc_encode(w, 1, n, ids, a.st);
     a.finish();
   });
 }
@@ -319,7 +239,7 @@ int svanon_ar_decode_batch(svanon_stream* const* streams, int n, const int64_t* 
 
 int svanon_ar_decode_one(svanon_stream* s, const int64_t* content_id, const float* noise, int32_t* codes_out,
                          int32_t* last_pos, void* stream) {
-  if (!s) { g_err = "null stream"; return 1; }
+  if (!s) { g_api_err = "null stream"; return 1; }
   svanon_stream* one = s;
   const int rc = svanon_ar_decode_batch(&one, 1, content_id, noise, codes_out, stream);
   if (rc == 0 && last_pos) *last_pos = s->st.pos_next - 1;
@@ -514,7 +434,7 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
     // 2. E: re-encode the whole window, keep the last `chunk` ids (:505-518)
     s.ev_valid = false;
     if (s.timing) SV_CUDA(cudaEventRecord(s.ev[0], st));
-    e.enc_encode(s.wave_ring, (long long)nw, s.ids_win_dev, st);
+    e.enc_encode(s.wave_ring, 1, (long long)nw, s.ids_win_dev, st);
     if (s.timing) SV_CUDA(cudaEventRecord(s.ev[1], st));
     if (s.n_src + s.chunk > HIST_CAP) {
       const int keep = HIST_CAP / 2;
@@ -544,21 +464,7 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
     if (s.timing) SV_CUDA(cudaEventRecord(s.ev[2], st));
     const int current_pos = s.pos_next - 1;
     // 6. re-prompt (:547-564)
-    if (current_pos / 2 >= s.max_seq_frames) {
-      const int buf = std::min(s.buffer_frames, s.n_pred);
-      const int Tn = s.ref_frames + buf;
-      SV_CHECK(s.n_src - s.delay >= buf, "not enough source history for re-prompting");
-      int* ext_audio = (int*)a.h->staging.alloc_bytes((size_t)8 * Tn * sizeof(int));
-      long long* ext_content = (long long*)a.h->staging.alloc_bytes((size_t)Tn * sizeof(long long));
-      launch_concat_cols(s.ref_audio_dev, s.ref_frames, s.ref_frames, s.pred_hist + (s.n_pred - buf), HIST_CAP, buf,
-                         ext_audio, Tn, 8, false, st);
-      SV_CUDA(cudaMemcpyAsync(ext_content, s.ref_content_dev, (size_t)s.ref_frames * sizeof(long long),
-                              cudaMemcpyDeviceToDevice, st));
-      SV_CUDA(cudaMemcpyAsync(ext_content + s.ref_frames, s.src_hist + (s.n_src - buf - s.delay),
-                              (size_t)buf * sizeof(long long), cudaMemcpyDeviceToDevice, st));
-      e.ar_prefill_prompt(s, ext_content, ext_audio, Tn, s.style_dev, s.timbre_dev, st);
-      if (s.delay > 0) e.ar_prefill_delay(s, s.src_hist + (s.n_src - s.delay), s.delay, st);
-    }
+    if (current_pos / 2 >= s.max_seq_frames) e.reprompt(s, a.h->staging, st);
     // 7. V.  Reference: vocoder over the last decode_window_frames frames, left-padded with the prompt's tail,
     //    keep the last chunk (:567-583,596).  With >= 15 frames of true history the incremental vocoder produces
     //    the same samples from the `chunk` new frames only (voc_stream.cu); smaller windows are recomputed.

@@ -22,7 +22,14 @@ attention_kernel(const float* __restrict__ q, long long q_ld, const float* __res
   __shared__ float Vs[KT][HEAD_DIM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y;
-  const int qi0 = blockIdx.x * QW;
+  // independent streams side by side: segment `seg` owns query rows [seg*nq, (seg+1)*nq) and the same key rows
+  const int bps = (nq + QW - 1) / QW;
+  const int seg = blockIdx.x / bps;
+  const int qi0 = (blockIdx.x - seg * bps) * QW;
+  q += (long long)seg * nq * q_ld;
+  k += (long long)seg * nq * kv_row_stride;
+  v += (long long)seg * nq * kv_row_stride;
+  out += (long long)seg * nq * out_ld;
   const int qi = qi0 + warp;
   const bool active = qi < nq;
   const int pos = qpos0 + qi;
@@ -116,9 +123,9 @@ __global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float
 
 void launch_attention(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
                       long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
-                      cudaStream_t st) {
-  if (nq <= 0) return;
-  dim3 grid((nq + QW - 1) / QW, heads);
+                      cudaStream_t st, int nseg) {
+  if (nq <= 0 || nseg <= 0) return;
+  dim3 grid((nq + QW - 1) / QW * nseg, heads);
   launch_pdl(attention_kernel, dim3(grid), dim3(QW * 32), 0, st, q, q_ld, k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0,
                                              window);
   SV_LAUNCHED();

@@ -1,0 +1,322 @@
+// Many concurrent streams in lock-step (BASELINE configs 3-4: "concurrent streams / GPU at RTF < 1").
+//
+// The reference is strictly batch-1 (max_batch_size=1, infer_arvc.py:56): N concurrent utterances are N sequential
+// `process_one_chunk` calls.  A svanon_batch advances N streams by one chunk with ONE pass over the weights:
+//   E  every stream's 128-frame window side by side through the same GEMMs (M = N * 512 rows),
+//   A  the many-stream decode path of ar_batch.cu (1, 2 or 4 streams: the persistent kernel),
+//   V  the incremental vocoder with N conv histories side by side,
+// while each stream keeps its own prompt, KV cache, histories, sampler state and re-prompt schedule, so every
+// stream produces exactly what it would produce alone (tests/test_gpu_batch.py).
+#include "api_common.hpp"
+
+struct svanon_batch {
+  svanon_engine* owner = nullptr;
+  std::vector<svanon_stream*> streams;
+  int enc_win = 0, dec_win = 0, max_seq_frames = 0, buffer_frames = 0, chunk = 1, delay = 0;
+  float *wave_ring = nullptr, *wave_ring_tmp = nullptr;   // [n][enc_win*2048]
+  long long* ids_win = nullptr;                           // [n][enc_win]
+  long long* codes_win = nullptr;                         // [n][8][chunk]
+  long long* step_ids = nullptr;                          // [chunk][n] content ids of this chunk, step-major
+  VocState voc;
+  struct SlotPtrs {                                       // static per-stream pointers (device table)
+    long long* src_hist;
+    int* pred_hist;
+    const int* ref_audio;
+    int ref_frames;
+  };
+  SlotPtrs* ptrs_dev = nullptr;
+  int n_src = 0, n_pred = 0, voc_fed = 0;
+  bool delay_prefilled = false;
+  int ar_path = 0;                                        // 0 auto, 1 always the many-stream GEMM path
+  bool timing = false, ev_valid = false;
+  cudaEvent_t ev[5] = {};
+  ~svanon_batch() {
+    for (void* p : {(void*)wave_ring, (void*)wave_ring_tmp, (void*)ids_win, (void*)codes_win, (void*)step_ids, (void*)ptrs_dev})
+      if (p) cudaFree(p);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+
+namespace {
+
+using SlotPtrs = svanon_batch::SlotPtrs;
+
+// src_content_codes[b][col0 + j] = ids_win[b][enc_win - chunk + j];  step_ids[j][b] = the same id
+__global__ void batch_take_ids_kernel(const SlotPtrs* __restrict__ ptrs, const long long* __restrict__ ids_win, int enc_win,
+                                      int chunk, int col0, long long* __restrict__ step_ids, int n) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * chunk) return;
+  const int b = i / chunk, j = i % chunk;
+  const long long id = ids_win[(long long)b * enc_win + enc_win - chunk + j];
+  ptrs[b].src_hist[col0 + j] = id;
+  step_ids[(long long)j * n + b] = id;
+}
+
+// codes_win[b][k][j] = from_ref ? ref_audio[b][k][ref_frames - back + j] : pred_hist[b][k][col0 + j]
+__global__ void batch_gather_codes_kernel(const SlotPtrs* __restrict__ ptrs, long long* __restrict__ codes_win, int chunk,
+                                          int from_ref, int back, int col0, int n) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 8 * chunk) return;
+  const int b = i / (8 * chunk), k = (i / chunk) % 8, j = i % chunk;
+  const SlotPtrs& p = ptrs[b];
+  const int v = from_ref ? p.ref_audio[(long long)k * p.ref_frames + (p.ref_frames - back + j)]
+                         : p.pred_hist[(long long)k * HIST_CAP + col0 + j];
+  codes_win[i] = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int svanon_enc_encode_batch(svanon_engine* e, const float* waves, int n_utt, int64_t n_samples, int64_t* ids_out,
+                            void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && waves && ids_out && n_utt >= 1, "bad arguments");
+    const size_t S = (size_t)svanon_enc_num_ids(n_samples);
+    Args a(e, stream, ((size_t)n_samples * 4 + S * 8) * n_utt + 65536);
+    const float* w = a.in(waves, (size_t)n_samples * n_utt);
+    long long* ids = (long long*)a.out(ids_out, S * n_utt);
+    e->eng.enc_encode(w, n_utt, n_samples, ids, a.st);
+    a.finish();
+  });
+}
+
+int svanon_ar_decode_many(svanon_stream* const* streams, int n, const int64_t* content_ids, const float* noise,
+                          int32_t* codes_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(streams && n >= 1 && content_ids && codes_out, "bad arguments");
+    svanon_engine* h = streams[0]->owner;
+    Args a(h, stream, (size_t)n * (8 * AR_CB_SIZE * 4 + 256) + 65536);
+    const long long* ids = (const long long*)a.in(content_ids, (size_t)n);
+    const float* nz = a.in(noise, (size_t)n * 8 * AR_CB_SIZE);
+    int* out = a.out(codes_out, (size_t)n * 8);
+    std::vector<Stream*> ss(n);
+    for (int i = 0; i < n; ++i) {
+      SV_CHECK(streams[i] && streams[i]->owner == h, "streams must belong to one engine");
+      ss[i] = &streams[i]->st;
+      ss[i]->step_content_id = ids + i;
+      ss[i]->step_cond_row = nullptr;
+      ss[i]->step_noise = nz ? nz + (size_t)i * 8 * AR_CB_SIZE : nullptr;
+      ss[i]->step_pred_hist = nullptr;
+    }
+    h->eng.ar_decode_step_gemm(ss.data(), n, a.st);
+    for (int i = 0; i < n; ++i)
+      SV_CUDA(cudaMemcpyAsync(out + i * 8, ss[i]->codes_dev, 8 * sizeof(int), cudaMemcpyDeviceToDevice, a.st));
+    a.finish();
+  });
+}
+
+int svanon_batch_create(svanon_engine* e, svanon_stream* const* streams, int n, svanon_batch** out) {
+  return guarded([&] {
+    SV_CHECK(e && streams && out && n >= 1, "bad arguments");
+    auto* b = new svanon_batch();
+    b->owner = e;
+    for (int i = 0; i < n; ++i) {
+      SV_CHECK(streams[i] && streams[i]->owner == e, "streams must belong to the batch's engine");
+      for (int j = 0; j < i; ++j) SV_CHECK(streams[j] != streams[i], "a stream may appear only once in a batch");
+      b->streams.push_back(streams[i]);
+    }
+    *out = b;
+  });
+}
+
+void svanon_batch_destroy(svanon_batch* b) { delete b; }
+
+int svanon_batch_set_ar_path(svanon_batch* b, int path) {
+  return guarded([&] {
+    SV_CHECK(b && (path == 0 || path == 1), "path: 0 auto (persistent kernel for 1/2/4 streams), 1 many-stream kernels");
+    b->ar_path = path;
+  });
+}
+
+int svanon_batch_setup(svanon_batch* b, int enc_win, int dec_win, int max_seq_frames, int buffer_frames, int chunk) {
+  return guarded([&] {
+    SV_CHECK(b, "null batch");
+    SV_CHECK(enc_win >= 1 && enc_win <= 2048 && dec_win >= 1 && dec_win <= 1024, "window sizes out of range");
+    SV_CHECK(chunk >= 1 && chunk <= 8 && chunk <= enc_win && chunk <= dec_win, "decode_chunk_frames must be in [1, 8]");
+    SV_CHECK(buffer_frames >= 0 && buffer_frames < HIST_CAP / 2, "buffer_frames out of range");
+    SV_CHECK((dec_win - chunk >= 15) && (std::min(dec_win - chunk, 24) / chunk * chunk >= 15),
+             "batched streaming uses the incremental vocoder: decode_window_frames must leave >= 15 frames of history");
+    Engine& e = b->owner->eng;
+    SV_CUDA(cudaSetDevice(e.device));
+    SV_CUDA(cudaDeviceSynchronize());
+    const int n = (int)b->streams.size();
+    for (void* p : {(void*)b->wave_ring, (void*)b->wave_ring_tmp, (void*)b->ids_win, (void*)b->codes_win, (void*)b->step_ids,
+                    (void*)b->ptrs_dev})
+      if (p) cudaFree(p);
+    b->enc_win = enc_win; b->dec_win = dec_win; b->max_seq_frames = max_seq_frames; b->buffer_frames = buffer_frames;
+    b->chunk = chunk;
+    b->delay = b->streams[0]->st.delay;
+    const size_t nw = (size_t)enc_win * SAMPLES_PER_FRAME;
+    b->wave_ring = dmalloc<float>(nw * n);
+    b->wave_ring_tmp = dmalloc<float>(nw * n);
+    SV_CUDA(cudaMemset(b->wave_ring, 0, nw * n * 4));
+    b->ids_win = dmalloc<long long>((size_t)enc_win * n);
+    b->codes_win = dmalloc<long long>((size_t)8 * chunk * n);
+    b->step_ids = dmalloc<long long>((size_t)chunk * n);
+    std::vector<SlotPtrs> ptrs(n);
+    for (int i = 0; i < n; ++i) {
+      Stream& s = b->streams[i]->st;
+      SV_CHECK(s.ref_frames > 0, "svanon_stream_set_prompt must be called on every stream before svanon_batch_setup");
+      SV_CHECK(s.delay == b->delay, "all streams of a batch must use the same delay");
+      const int pad = dec_win;       // first window is all padding
+      SV_CHECK(std::min(pad, 24) <= s.ref_frames, "prompt shorter than the vocoder window padding needs");
+      s.enc_win = enc_win; s.dec_win = dec_win; s.max_seq_frames = max_seq_frames; s.buffer_frames = buffer_frames;
+      s.chunk = chunk; s.n_src = 0; s.n_pred = 0; s.delay_prefilled = false;
+      ptrs[i] = {s.src_hist, s.pred_hist, s.ref_audio_dev, s.ref_frames};
+    }
+    b->ptrs_dev = dmalloc<SlotPtrs>(n);
+    SV_CUDA(cudaMemcpy(b->ptrs_dev, ptrs.data(), (size_t)n * sizeof(SlotPtrs), cudaMemcpyHostToDevice));
+    b->n_src = 0; b->n_pred = 0; b->voc_fed = 0; b->delay_prefilled = false;
+    e.voc_state_init(b->voc, chunk, n);
+  });
+}
+
+int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_samples, const float* noise, float* wave_out,
+                               void* stream) {
+  return guarded([&] {
+    SV_CHECK(b && wave_chunks && wave_out, "null argument");
+    SV_CHECK(b->enc_win > 0, "svanon_batch_setup has not been called");
+    SV_CHECK(n_samples == b->chunk * SAMPLES_PER_FRAME, "every stream's chunk must hold decode_chunk_frames * 2048 samples");
+    Engine& e = b->owner->eng;
+    const int n = (int)b->streams.size();
+    const int c = b->chunk;
+    const size_t per_noise = (size_t)c * 8 * AR_CB_SIZE;
+    size_t prompt_budget = 0;
+    for (auto* sh : b->streams) prompt_budget += (size_t)(sh->st.ref_frames + b->buffer_frames) * 64 + 1024;
+    Args a(b->owner, stream, ((size_t)n_samples * 8 + per_noise * 4) * n + prompt_budget + 65536);
+    cudaStream_t st = a.st;
+    const float* wc = a.in(wave_chunks, (size_t)n_samples * n);
+    const float* nz = a.in(noise, per_noise * n);
+    float* out = a.out(wave_out, (size_t)n_samples * n);
+    const size_t nw = (size_t)b->enc_win * SAMPLES_PER_FRAME;
+    // 1. wave rings: shift left by the chunk, append (infer_arvc.py:495-496), all streams at once
+    SV_CUDA(cudaMemcpy2DAsync(b->wave_ring_tmp, nw * 4, b->wave_ring + n_samples, nw * 4, (nw - n_samples) * 4, n,
+                              cudaMemcpyDeviceToDevice, st));
+    SV_CUDA(cudaMemcpy2DAsync(b->wave_ring_tmp + (nw - n_samples), nw * 4, wc, (size_t)n_samples * 4, (size_t)n_samples * 4, n,
+                              cudaMemcpyDeviceToDevice, st));
+    std::swap(b->wave_ring, b->wave_ring_tmp);
+    // 2. E: all windows side by side, keep the last `chunk` ids of each (:505-518)
+    b->ev_valid = false;
+    if (b->timing) SV_CUDA(cudaEventRecord(b->ev[0], st));
+    e.enc_encode(b->wave_ring, n, (long long)nw, b->ids_win, st);
+    if (b->timing) SV_CUDA(cudaEventRecord(b->ev[1], st));
+    if (b->n_src + c > HIST_CAP) {
+      const int keep = HIST_CAP / 2;
+      long long* tmp = (long long*)e.ws.base;
+      for (auto* sh : b->streams) {
+        Stream& s = sh->st;
+        SV_CUDA(cudaMemcpyAsync(tmp, s.src_hist + (b->n_src - keep), keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+        SV_CUDA(cudaMemcpyAsync(s.src_hist, tmp, keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+      }
+      b->n_src = keep;
+    }
+    launch_pdl(batch_take_ids_kernel, dim3((n * c + 127) / 128), dim3(128), 0, st, (const SlotPtrs*)b->ptrs_dev,
+               (const long long*)b->ids_win, b->enc_win, c, b->n_src, b->step_ids, n);
+    SV_LAUNCHED();
+    b->n_src += c;
+    for (auto* sh : b->streams) sh->st.n_src = b->n_src;
+    // 3./4. warm-up phases (:519-525) -- the streams started together and share the delay
+    bool silent = false;
+    if (b->n_src < b->delay) {
+      silent = true;
+    } else if (!b->delay_prefilled && b->delay != 0) {
+      for (auto* sh : b->streams) e.ar_prefill_delay(sh->st, sh->st.src_hist + (b->n_src - b->delay), b->delay, st);
+      b->delay_prefilled = true;
+      silent = true;
+    }
+    if (silent) {
+      SV_CUDA(cudaMemsetAsync(out, 0, (size_t)n_samples * n * sizeof(float), st));
+      a.finish();
+      return;
+    }
+    // 5. A: `chunk` decode steps for all streams (:534-538)
+    std::vector<Stream*> ss(n);
+    for (int i = 0; i < n; ++i) ss[i] = &b->streams[i]->st;
+    const bool persistent = b->ar_path == 0 && (n == 1 || n == 2 || n == 4);
+    for (int j = 0; j < c; ++j) {
+      if (b->n_pred >= HIST_CAP) {     // keep the newest half (the reference keeps at most 2048 entries, :593-594)
+        const int keep = HIST_CAP / 2;
+        int* tmp = (int*)e.ws.base;
+        for (Stream* s : ss) {
+          SV_CUDA(cudaMemcpy2DAsync(tmp, keep * sizeof(int), s->pred_hist + (b->n_pred - keep), HIST_CAP * sizeof(int),
+                                    keep * sizeof(int), 8, cudaMemcpyDeviceToDevice, st));
+          SV_CUDA(cudaMemcpy2DAsync(s->pred_hist, HIST_CAP * sizeof(int), tmp, keep * sizeof(int), keep * sizeof(int), 8,
+                                    cudaMemcpyDeviceToDevice, st));
+        }
+        b->n_pred = keep;
+      }
+      for (int i = 0; i < n; ++i) {
+        Stream& s = *ss[i];
+        s.step_content_id = b->step_ids + (size_t)j * n + i;
+        s.step_cond_row = nullptr;
+        s.step_noise = nz ? nz + (size_t)i * per_noise + (size_t)j * 8 * AR_CB_SIZE : nullptr;
+        s.step_pred_hist = s.pred_hist;
+        s.step_pred_col = b->n_pred;
+      }
+      if (persistent) {
+        e.ar_decode_step(ss.data(), n, st);
+        for (Stream* s : ss) launch_append_codes(s->codes_dev, s->pred_hist, HIST_CAP, b->n_pred, st);
+      } else {
+        e.ar_decode_step_gemm(ss.data(), n, st);
+      }
+      b->n_pred += 1;
+      for (Stream* s : ss) s->n_pred = b->n_pred;
+    }
+    if (b->timing) SV_CUDA(cudaEventRecord(b->ev[2], st));
+    // 6. re-prompt (:547-564): per stream, on its own schedule (prompt lengths differ)
+    for (Stream* s : ss) {
+      const int current_pos = s->pos_next - 1;
+      if (current_pos / 2 >= b->max_seq_frames) e.reprompt(*s, a.h->staging, st);
+    }
+    // 7. V: incremental vocoder on the new frames of every stream; primed with the prompt's newest frames, which
+    //    is what the reference puts in front of the first windows (:567-571)
+    if (b->voc_fed == 0) {
+      const int k = std::min(b->dec_win - c, 24) / c * c;
+      for (int f = 0; f < k; f += c) {
+        launch_pdl(batch_gather_codes_kernel, dim3((n * 8 * c + 127) / 128), dim3(128), 0, st, (const SlotPtrs*)b->ptrs_dev,
+                   b->codes_win, c, 1, k - f, 0, n);
+        SV_LAUNCHED();
+        e.voc_step(b->voc, b->codes_win, c, out, st, (long long)8 * c);
+      }
+    }
+    launch_pdl(batch_gather_codes_kernel, dim3((n * 8 * c + 127) / 128), dim3(128), 0, st, (const SlotPtrs*)b->ptrs_dev,
+               b->codes_win, c, 0, 0, b->n_pred - c, n);
+    SV_LAUNCHED();
+    if (b->timing) SV_CUDA(cudaEventRecord(b->ev[3], st));
+    e.voc_step(b->voc, b->codes_win, c, out, st, (long long)8 * c);
+    if (b->timing) { SV_CUDA(cudaEventRecord(b->ev[4], st)); b->ev_valid = true; }
+    b->voc_fed += c;
+    a.finish();
+  });
+}
+
+int svanon_batch_set_timing(svanon_batch* b, int enable) {
+  return guarded([&] {
+    SV_CHECK(b, "null batch");
+    SV_CUDA(cudaSetDevice(b->owner->eng.device));
+    if (enable)
+      for (auto& e : b->ev)
+        if (!e) SV_CUDA(cudaEventCreate(&e));
+    b->timing = enable != 0;
+    b->ev_valid = false;
+  });
+}
+
+int svanon_batch_last_timing(svanon_batch* b, float* ms) {
+  return guarded([&] {
+    SV_CHECK(b && ms, "null argument");
+    SV_CHECK(b->timing && b->ev_valid, "no timed chunk available (enable timing, then process a non-warm-up chunk)");
+    SV_CUDA(cudaEventSynchronize(b->ev[4]));
+    SV_CUDA(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]));
+    SV_CUDA(cudaEventElapsedTime(&ms[1], b->ev[1], b->ev[2]));
+    SV_CUDA(cudaEventElapsedTime(&ms[2], b->ev[3], b->ev[4]));
+  });
+}
+
+}  // extern "C"

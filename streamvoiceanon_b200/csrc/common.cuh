@@ -114,30 +114,72 @@ struct GemmParams {
   int act = ACT_NONE;
   float out_scale = 1.f;           // y *= out_scale (applied last, before accumulate)
   int accumulate = 0;              // C += y instead of C = y
+  // Independent streams side by side: with seg_rows > 0 output row m belongs to segment b = m / seg_rows (row
+  // t = m % seg_rows of that stream) and the A / C / residual rows of segment b start b * {a,c,r}_seg floats after
+  // the base pointer (each stream's buffer keeps its own causal margin rows in front).  seg_rows == 0: one stream.
+  int seg_rows = 0;
+  long long a_seg = 0, c_seg = 0, r_seg = 0;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ long long gemm_a_row(const GemmParams& p, int m) {
+  if (p.seg_rows > 0) {
+    const int b = m / p.seg_rows;
+    return (long long)b * p.a_seg + (long long)(m - b * p.seg_rows) * p.a_row_step * p.lda;
+  }
+  return (long long)m * p.a_row_step * p.lda;
+}
+__device__ __forceinline__ long long gemm_c_row(const GemmParams& p, int m) {
+  if (p.seg_rows > 0) {
+    const int b = m / p.seg_rows;
+    return (long long)b * p.c_seg + (long long)(m - b * p.seg_rows) * p.ldc;
+  }
+  return (long long)m * p.ldc;
+}
+__device__ __forceinline__ long long gemm_r_row(const GemmParams& p, int m) {
+  if (p.seg_rows > 0) {
+    const int b = m / p.seg_rows;
+    return (long long)b * p.r_seg + (long long)(m - b * p.seg_rows) * p.ldr;
+  }
+  return (long long)m * p.ldr;
+}
+// row `row` of a buffer made of segments of seg_rows rows that start seg_stride floats apart (0 rows: plain)
+__device__ __forceinline__ long long seg_row_off(long long row, int seg_rows, long long seg_stride, long long ld) {
+  if (seg_rows > 0) {
+    const long long b = row / seg_rows;
+    return b * seg_stride + (row - b * seg_rows) * ld;
+  }
+  return row * ld;
+}
+#endif
 
 // up to 3 independent problems of identical shape run as blockIdx.z
 void launch_gemm(const GemmParams* p, int count, cudaStream_t st);
 inline void launch_gemm(const GemmParams& p, cudaStream_t st) { launch_gemm(&p, 1, st); }
 
 // ---------------------------------------------------------------- misc kernels (kernels_misc.cu)
+// Row-wise kernels take an optional segment description for side-by-side streams: rows are numbered over all
+// streams, stream b = row / seg_rows, and its rows start b * {x,y}_seg floats after the base (seg_rows 0: plain).
 void launch_layernorm(const float* x, float* y, const float* w, const float* b, int rows, int C, float eps,
-                      cudaStream_t st);
+                      cudaStream_t st, int seg_rows = 0, long long x_seg = 0, long long y_seg = 0);
 // depthwise causal conv k=7 (rows before 0 are read from the buffer margin) + LayerNorm over C, channels-last
 void launch_dwconv7_ln(const float* x, float* y, const float* dw_w /*[7][C]*/, const float* dw_b, const float* ln_w,
-                       const float* ln_b, int rows, int C, float eps, cudaStream_t st);
-void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st);
+                       const float* ln_b, int rows, int C, float eps, cudaStream_t st, int seg_rows = 0,
+                       long long x_seg = 0);
+void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st,
+                    long long x_ld = 0);
 // interleaved-pair RoPE on q and k inside a fused [rows, 3*H*64] qkv buffer; table [pos][32][2] (bf16-rounded fp32)
-void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos0, cudaStream_t st);
+void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos0, cudaStream_t st, int seg_rows = 0);
 void launch_silu_mul(const float* h13 /*[rows][2*I]*/, float* out /*[rows][I]*/, int rows, int I, cudaStream_t st);
 void launch_magnitude(const float* spec /*[T][ld_in] re|im*/, float* mag /*[T][N_FREQ_PAD]*/, int T, int ld_in,
                       cudaStream_t st);
 void launch_bsq(const float* z /*[T][512]*/, const float* w /*[13][512]*/, const float* b, long long* ids, int T,
                 cudaStream_t st);
 void launch_fsq_lookup(const long long* codes /*[8][T] (stride ld)*/, long long ld, const float* w /*[8][64][4]*/,
-                       const float* b /*[8][64]*/, float* z /*[T][512]*/, int T, cudaStream_t st);
+                       const float* b /*[8][64]*/, float* z /*[T][512]*/, int T, cudaStream_t st, int seg_rows = 0,
+                       long long codes_seg = 0);
 void launch_conv_post(const float* x /*[L][16] with 12 margin rows*/, const float* w /*[13][16]*/, const float* b,
-                      float* out, int L, cudaStream_t st);
+                      float* out, int L, cudaStream_t st, int seg_rows = 0, long long x_seg = 0);
 void launch_gather_rows(const float* table, const long long* idx, float* out, int rows, int C, long long out_ld,
                         cudaStream_t st);
 // out[t] = sum_i table[codes[i][t] + i*1000]  (BaseTransformer.embed)
@@ -145,8 +187,9 @@ void launch_embed_codes(const float* table, const int* codes /*[8][T] stride ld*
                         long long out_ld, cudaStream_t st);
 void launch_copy_rows(const float* src, long long src_ld, float* dst, long long dst_ld, int rows, int C,
                       cudaStream_t st);
-void launch_scale_add3(const float* a, const float* b, const float* c, float* out, long long n, float s, cudaStream_t st);
-void launch_fill(float* p, long long n, float v, cudaStream_t st);
+void launch_scale_add3(const float* a, const float* b, const float* c, float* out, long long n, float s, cudaStream_t st,
+                       long long seg_n = 0, long long out_seg = 0);
+void launch_fill(float* p, long long n, float v, cudaStream_t st, int nseg = 1, long long seg_stride = 0);
 void launch_concat_cols(const int* a, long long a_ld, int a_n, const int* b, long long b_ld, int b_n, void* out,
                         long long out_ld, int rows, bool out_i64, cudaStream_t st);
 void launch_append_codes(const int* codes8, int* hist, long long ld, int col, cudaStream_t st);
@@ -158,7 +201,7 @@ void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t 
 // max(0, pos-window+1) .. pos.
 void launch_attention(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
                       long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
-                      cudaStream_t st);
+                      cudaStream_t st, int nseg = 1);
 // scatter k,v of a fused qkv buffer into a [H][max_seq][64] cache at positions pos0..pos0+rows-1
 void launch_kv_append(const float* qkv, int rows, int heads, float* kc, float* vc, int max_seq, int pos0,
                       cudaStream_t st);

@@ -393,11 +393,13 @@ void Engine::finalize_vocoder() {
 }
 
 // ------------------------------------------------------------------------------------------ ConvNeXt block
-// ConvNeXtBlock.forward (firefly.py:421-440), channels-last, in place on x (x has >= 6 zero/history rows
-// before row 0).  tmp [rows][C], hid [rows][4C].
-void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out) {
+// ConvNeXtBlock.forward (firefly.py:421-440), channels-last, in place on x (every stream's x has >= 6 zero/history
+// rows before its row 0).  tmp [rows][C], hid [rows][4C] are plain.  `rows` counts the rows of all streams; with
+// seg_rows > 0 stream b's x (and out) rows start b * x_seg (out_seg) floats after the base.
+void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out,
+                      int seg_rows, long long x_seg, long long out_seg) {
   const int C = cw.C;
-  launch_dwconv7_ln(x, tmp, cw.dw_w, cw.dw_b, cw.ln_w, cw.ln_b, rows, C, 1e-6f, st);
+  launch_dwconv7_ln(x, tmp, cw.dw_w, cw.dw_b, cw.ln_w, cw.ln_b, rows, C, 1e-6f, st, seg_rows, x_seg);
   GemmParams p1;
   p1.A = tmp; p1.W = cw.pw1_w; p1.C = hid; p1.bias = cw.pw1_b; p1.M = rows; p1.N = 4 * C; p1.K = C;
   p1.lda = C; p1.ldc = 4 * C; p1.act = ACT_GELU;
@@ -405,128 +407,148 @@ void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float
   GemmParams p2;
   p2.A = hid; p2.W = cw.pw2_w; p2.C = out ? out : x; p2.bias = cw.pw2_b; p2.gamma = cw.gamma; p2.residual = x;
   p2.M = rows; p2.N = C; p2.K = 4 * C; p2.lda = 4 * C; p2.ldc = C; p2.ldr = C;
+  if (seg_rows > 0) {
+    p2.seg_rows = seg_rows; p2.a_seg = (long long)seg_rows * 4 * C; p2.c_seg = out ? out_seg : x_seg; p2.r_seg = x_seg;
+  }
   launch_gemm(p2, st);
-
 }
 
 // ------------------------------------------------------------------------------------------ stage E
-// FireflyArchitecture.encode (firefly_encoder.py:553-566) for one full-length utterance / window.
-void Engine::enc_encode(const float* wave, long long n, long long* ids_dev, cudaStream_t st) {
+// FireflyArchitecture.encode (firefly_encoder.py:553-566) for B full-length utterances / windows of the same length,
+// side by side: wave [B][n] -> ids [B][n/2048].  Streams never mix: every causal conv reads its own stream's zero
+// margin, attention is per stream; the GEMMs simply see B times more rows.
+void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_dev, cudaStream_t st) {
   SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
+  SV_CHECK(B >= 1, "no utterances");
   const int T = (int)(n / HOP);
   const int T2 = T / 2, S = T2 / 2;
   SV_CHECK(S >= 1, "utterance shorter than one content frame (2048 samples)");
   SV_CHECK(S <= 2048, "utterance longer than the tokenizer's RoPE table (2048 content frames)");
-  ws.ensure(((size_t)T * 14000 + (size_t)n + (4u << 20)) * sizeof(float));
+  SV_CHECK((long long)B * T < (1 << 30), "batch too large");
+  ws.ensure((((size_t)T * 14000 + (size_t)n) * B + (4u << 20)) * sizeof(float));
   ws.reset();
   const int MARG = 6;
+  const int BT = B * T;
+  const int segT = B > 1 ? T : 0;          // seg_rows of the T-row buffers (0 = plain single stream)
   // 1. left-pad win-hop zeros (spectrogram.py:37-45) and take frames as overlapping GEMM rows (lda = hop)
-  float* wpad = ws.alloc_f(N_FFT - HOP + n);
-  launch_fill(wpad, N_FFT - HOP, 0.f, st);
-  SV_CUDA(cudaMemcpyAsync(wpad + (N_FFT - HOP), wave, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const long long wseg = N_FFT - HOP + n;
+  float* wpad = ws.alloc_f(wseg * B);
+  launch_fill(wpad, N_FFT - HOP, 0.f, st, B, wseg);
+  SV_CUDA(cudaMemcpy2DAsync(wpad + (N_FFT - HOP), (size_t)wseg * sizeof(float), wave, (size_t)n * sizeof(float),
+                            (size_t)n * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
   const int SPEC_LD = 2052;
-  float* spec = ws.alloc_f((long long)T * SPEC_LD);
+  float* spec = ws.alloc_f((long long)BT * SPEC_LD);
   {
     GemmParams p;
-    p.A = wpad; p.W = dft_w; p.C = spec; p.M = T; p.N = 2 * N_FREQ; p.K = N_FFT; p.lda = HOP; p.ldc = SPEC_LD;
+    p.A = wpad; p.W = dft_w; p.C = spec; p.M = BT; p.N = 2 * N_FREQ; p.K = N_FFT; p.lda = HOP; p.ldc = SPEC_LD;
+    p.seg_rows = segT; p.a_seg = wseg; p.c_seg = (long long)T * SPEC_LD;
     launch_gemm(p, st);
   }
-  float* mag = ws.alloc_f((long long)T * N_FREQ_PAD);
-  launch_magnitude(spec, mag, T, SPEC_LD, st);
+  float* mag = ws.alloc_f((long long)BT * N_FREQ_PAD);
+  launch_magnitude(spec, mag, BT, SPEC_LD, st);
   // 2. mel filterbank + log(clamp(., 1e-5))  (spectrogram.py:108-130); 6 zero rows in front for the causal stem
-  float* mel_buf = ws.alloc_f((long long)(MARG + T) * N_MELS);
-  launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st);
+  const long long mel_seg = (long long)(MARG + T) * N_MELS;
+  float* mel_buf = ws.alloc_f(mel_seg * B);
+  launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st, B, mel_seg);
   float* mel = mel_buf + MARG * N_MELS;
   {
     GemmParams p;
-    p.A = mag; p.W = fb_t; p.C = mel; p.M = T; p.N = N_MELS; p.K = N_FREQ_PAD; p.lda = N_FREQ_PAD; p.ldc = N_MELS;
+    p.A = mag; p.W = fb_t; p.C = mel; p.M = BT; p.N = N_MELS; p.K = N_FREQ_PAD; p.lda = N_FREQ_PAD; p.ldc = N_MELS;
     p.act = ACT_LOGCLAMP;
+    p.seg_rows = segT; p.a_seg = (long long)T * N_FREQ_PAD; p.c_seg = mel_seg;
     launch_gemm(p, st);
   }
 
   // 3. ConvNeXtEncoder (firefly.py:506-517)
   const int dims[4] = {128, 256, 384, 512};
-  float* tmp = ws.alloc_f((long long)T * 512);
-  float* hid = ws.alloc_f((long long)T * 2048);
+  float* tmp = ws.alloc_f((long long)BT * 512);
+  float* hid = ws.alloc_f((long long)BT * 2048);
   float* x = nullptr;
+  long long x_seg = 0;
   for (int s = 0; s < 4; ++s) {
     const int C = dims[s];
-    float* xb = ws.alloc_f((long long)(MARG + T) * C);
-    launch_fill(xb, (long long)MARG * C, 0.f, st);
+    const long long xs = (long long)(MARG + T) * C;
+    float* xb = ws.alloc_f(xs * B);
+    launch_fill(xb, (long long)MARG * C, 0.f, st, B, xs);
     float* xn = xb + MARG * C;
     if (s == 0) {
       GemmParams p;   // stem: causal conv k=7 as one GEMM over 7 overlapping rows
-      p.A = mel; p.W = stem_w; p.C = tmp; p.bias = stem_b; p.M = T; p.N = C; p.K = 7 * N_MELS; p.lda = N_MELS;
+      p.A = mel; p.W = stem_w; p.C = tmp; p.bias = stem_b; p.M = BT; p.N = C; p.K = 7 * N_MELS; p.lda = N_MELS;
       p.ldc = C; p.tap_off[0] = -6;
+      p.seg_rows = segT; p.a_seg = mel_seg; p.c_seg = (long long)T * C;
       launch_gemm(p, st);
-      launch_layernorm(tmp, xn, stem_ln_w, stem_ln_b, T, C, 1e-6f, st);
+      launch_layernorm(tmp, xn, stem_ln_w, stem_ln_b, BT, C, 1e-6f, st, segT, (long long)T * C, xs);
     } else {
       const int Cp = dims[s - 1];
-      launch_layernorm(x, tmp, mid_ln_w[s - 1], mid_ln_b[s - 1], T, Cp, 1e-6f, st);
+      launch_layernorm(x, tmp, mid_ln_w[s - 1], mid_ln_b[s - 1], BT, Cp, 1e-6f, st, segT, x_seg, (long long)T * Cp);
       GemmParams p;
-      p.A = tmp; p.W = mid_w[s - 1]; p.C = xn; p.bias = mid_b[s - 1]; p.M = T; p.N = C; p.K = Cp; p.lda = Cp; p.ldc = C;
+      p.A = tmp; p.W = mid_w[s - 1]; p.C = xn; p.bias = mid_b[s - 1]; p.M = BT; p.N = C; p.K = Cp; p.lda = Cp; p.ldc = C;
+      p.seg_rows = segT; p.a_seg = (long long)T * Cp; p.c_seg = xs;
       launch_gemm(p, st);
     }
-
     x = xn;
-    for (auto& blk : enc_blocks[s]) convnext(blk, x, T, tmp, hid, st);
+    x_seg = xs;
+    for (auto& blk : enc_blocks[s]) convnext(blk, x, BT, tmp, hid, st, nullptr, segT, x_seg, 0);
   }
-  float* feat = ws.alloc_f((long long)T * 512);
-  launch_layernorm(x, feat, bb_norm_w, bb_norm_b, T, 512, 1e-6f, st);
+  float* feat = ws.alloc_f((long long)BT * 512);
+  launch_layernorm(x, feat, bb_norm_w, bb_norm_b, BT, 512, 1e-6f, st, segT, x_seg, (long long)T * 512);
   // 4. DownsampleBinarySphericalQuantize.downsample (bsq_no_upsample.py:46-60): 2 x [conv k2 s2 + ConvNeXt]
   float* cur = feat;
+  long long cur_seg = (long long)T * 512;
   int rows = T;
+  float* xt = ws.alloc_f((long long)B * S * ENC_DIM);       // transformer residual stream, plain [B*S][512]
   for (int i = 0; i < 2; ++i) {
     const int r2 = rows / 2;
-    float* db = ws.alloc_f((long long)(MARG + r2) * 512);
-    launch_fill(db, (long long)MARG * 512, 0.f, st);
+    const long long ds = (long long)(MARG + r2) * 512;
+    float* db = ws.alloc_f(ds * B);
+    launch_fill(db, (long long)MARG * 512, 0.f, st, B, ds);
     float* dn = db + MARG * 512;
     GemmParams p;
-    p.A = cur; p.W = down_w[i]; p.C = dn; p.bias = down_b[i]; p.M = r2; p.N = 512; p.K = 1024; p.lda = 512;
+    p.A = cur; p.W = down_w[i]; p.C = dn; p.bias = down_b[i]; p.M = B * r2; p.N = 512; p.K = 1024; p.lda = 512;
     p.a_row_step = 2; p.ldc = 512;
+    p.seg_rows = B > 1 ? r2 : 0; p.a_seg = cur_seg; p.c_seg = ds;
     launch_gemm(p, st);
-
-    convnext(down_block[i], dn, r2, tmp, hid, st);
+    // the second block writes its result straight into the plain transformer buffer
+    convnext(down_block[i], dn, B * r2, tmp, hid, st, i == 1 ? xt : nullptr, B > 1 ? r2 : 0, ds, (long long)r2 * 512);
     cur = dn;
+    cur_seg = ds;
     rows = r2;
   }
-  // 5. WindowLimitedTransformer (windowed_transformer.py:337-354), positions 0..S-1
-  float* xt = cur;
-  float* nrm = ws.alloc_f((long long)S * ENC_DIM);
-  float* qkv = ws.alloc_f((long long)S * 3 * ENC_DIM);
-  float* y = ws.alloc_f((long long)S * ENC_DIM);
-  float* h13 = ws.alloc_f((long long)S * 2 * ENC_INTER);
-  float* gbuf = ws.alloc_f((long long)S * ENC_INTER);
+  // 5. WindowLimitedTransformer (windowed_transformer.py:337-354), positions 0..S-1 in every stream
+  const int BS = B * S;
+  float* nrm = ws.alloc_f((long long)BS * ENC_DIM);
+  float* qkv = ws.alloc_f((long long)BS * 3 * ENC_DIM);
+  float* y = ws.alloc_f((long long)BS * ENC_DIM);
+  float* h13 = ws.alloc_f((long long)BS * 2 * ENC_INTER);
+  float* gbuf = ws.alloc_f((long long)BS * ENC_INTER);
   for (int l = 0; l < ENC_LAYERS; ++l) {
     const EncLayerW& L = enc_layers[l];
-    launch_rmsnorm(xt, nrm, L.attn_norm, S, ENC_DIM, 1e-5f, st);
+    launch_rmsnorm(xt, nrm, L.attn_norm, BS, ENC_DIM, 1e-5f, st);
     GemmParams p;
-    p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = S; p.N = 3 * ENC_DIM; p.K = ENC_DIM; p.lda = ENC_DIM; p.ldc = 3 * ENC_DIM;
+    p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = BS; p.N = 3 * ENC_DIM; p.K = ENC_DIM; p.lda = ENC_DIM; p.ldc = 3 * ENC_DIM;
     launch_gemm(p, st);
-    launch_rope_qk(qkv, enc_rope, S, ENC_HEADS, 0, st);
+    launch_rope_qk(qkv, enc_rope, BS, ENC_HEADS, 0, st, B > 1 ? S : 0);
     launch_attention(qkv, 3 * ENC_DIM, qkv + ENC_DIM, qkv + 2 * ENC_DIM, HEAD_DIM, 3 * ENC_DIM, y, ENC_DIM, S, 0,
-                     ENC_HEADS, ENC_WINDOW, st);
+                     ENC_HEADS, ENC_WINDOW, st, B);
     GemmParams po;
-    po.A = y; po.W = L.wo; po.C = xt; po.gamma = L.ls_attn; po.residual = xt; po.M = S; po.N = ENC_DIM; po.K = ENC_DIM;
+    po.A = y; po.W = L.wo; po.C = xt; po.gamma = L.ls_attn; po.residual = xt; po.M = BS; po.N = ENC_DIM; po.K = ENC_DIM;
     po.lda = ENC_DIM; po.ldc = ENC_DIM; po.ldr = ENC_DIM;
     launch_gemm(po, st);
-    launch_rmsnorm(xt, nrm, L.ffn_norm, S, ENC_DIM, 1e-5f, st);
+    launch_rmsnorm(xt, nrm, L.ffn_norm, BS, ENC_DIM, 1e-5f, st);
     GemmParams p1;
-    p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = S; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM; p1.ldc = 2 * ENC_INTER;
+    p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = BS; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM; p1.ldc = 2 * ENC_INTER;
     launch_gemm(p1, st);
     p1.W = L.w3; p1.C = h13 + ENC_INTER;
     launch_gemm(p1, st);
-    launch_silu_mul(h13, gbuf, S, ENC_INTER, st);
+    launch_silu_mul(h13, gbuf, BS, ENC_INTER, st);
     GemmParams p2;
-    p2.A = gbuf; p2.W = L.w2; p2.C = xt; p2.gamma = L.ls_ffn; p2.residual = xt; p2.M = S; p2.N = ENC_DIM; p2.K = ENC_INTER;
+    p2.A = gbuf; p2.W = L.w2; p2.C = xt; p2.gamma = L.ls_ffn; p2.residual = xt; p2.M = BS; p2.N = ENC_DIM; p2.K = ENC_INTER;
     p2.lda = ENC_INTER; p2.ldc = ENC_DIM; p2.ldr = ENC_DIM;
     launch_gemm(p2, st);
-
   }
-  launch_rmsnorm(xt, nrm, enc_norm_w, S, ENC_DIM, 1e-5f, st);
+  launch_rmsnorm(xt, nrm, enc_norm_w, BS, ENC_DIM, 1e-5f, st);
   // 6. BSQ ids (bsq.py:330-369)
-  launch_bsq(nrm, bsq_w, bsq_b, ids_dev, S, st);
-
+  launch_bsq(nrm, bsq_w, bsq_b, ids_dev, BS, st);
 }
 
 // ------------------------------------------------------------------------------------------ stage V
@@ -762,6 +784,24 @@ void Engine::ar_prefill_delay(Stream& s, const long long* src_content, int n, cu
   s.pos_next += 2 * d - 1;
   s.step += 1;
   s.delay_prefilled = true;
+}
+
+// Re-prompt of the per-chunk loop (infer_arvc.py:547-564): the prompt kept at set_prompt time, extended by the last
+// `buffer_frames` predicted frames and their source content ids, is prefilled again from position 0.
+void Engine::reprompt(Stream& s, Workspace& staging, cudaStream_t st) {
+  const int buf = std::min(s.buffer_frames, s.n_pred);
+  const int Tn = s.ref_frames + buf;
+  SV_CHECK(s.n_src - s.delay >= buf, "not enough source history for re-prompting");
+  int* ext_audio = (int*)staging.alloc_bytes((size_t)8 * Tn * sizeof(int));
+  long long* ext_content = (long long*)staging.alloc_bytes((size_t)Tn * sizeof(long long));
+  launch_concat_cols(s.ref_audio_dev, s.ref_frames, s.ref_frames, s.pred_hist + (s.n_pred - buf), HIST_CAP, buf,
+                     ext_audio, Tn, 8, false, st);
+  SV_CUDA(cudaMemcpyAsync(ext_content, s.ref_content_dev, (size_t)s.ref_frames * sizeof(long long),
+                          cudaMemcpyDeviceToDevice, st));
+  SV_CUDA(cudaMemcpyAsync(ext_content + s.ref_frames, s.src_hist + (s.n_src - buf - s.delay),
+                          (size_t)buf * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+  ar_prefill_prompt(s, ext_content, ext_audio, Tn, s.style_dev, s.timbre_dev, st);
+  if (s.delay > 0) ar_prefill_delay(s, s.src_hist + (s.n_src - s.delay), s.delay, st);
 }
 
 // DualARWrapper.decode_one (dual_ar_stream.py:817-837) for `batch` independent streams in one launch.

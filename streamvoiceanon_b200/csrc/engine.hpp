@@ -57,6 +57,7 @@ struct Engine;
 struct SBuf {
   float* base = nullptr;
   int margin = 0, rows = 0, C = 0;
+  long long seg = 0;               // floats between the buffers of consecutive streams
   float* data() const { return base + (long long)margin * C; }
 };
 
@@ -64,12 +65,14 @@ struct ShiftDesc {
   float* base;
   int margin_floats;
   int shift_floats;
+  long long seg;
 };
 
 // Persistent state of the incremental vocoder for one stream (with >= 15 frames of true
 // history the per-frame result equals the reference's 64-frame window recompute).
 struct VocState {
   int c = 0;                    // code frames per step
+  int B = 1;                    // streams side by side (every SBuf holds B segments)
   float* arena = nullptr;
   size_t arena_floats = 0;
   SBuf u1, u2, p0, c0;
@@ -83,6 +86,35 @@ struct VocState {
   int n_desc = 0;
   int primed_frames = 0;
   ~VocState();
+};
+
+// Per-stream descriptor of the many-stream decode path (ar_batch.cu), rebuilt by the host every step
+struct ArBatchSlot {
+  float *kc, *vc, *fkc, *fvc, *x_audio;
+  const long long* content_id;
+  const float* cond_row;
+  const float* noise;
+  int* out_codes;
+  int* pred_hist;               // [8][pred_ld] history to append this frame's codes to (column pred_col), or null
+  long long pred_ld;
+  int pred_col;
+  int pos;
+  unsigned step;
+  unsigned long long seed;
+};
+
+struct ArBatchWork {
+  static constexpr int RING = 4;
+  int cap = 0;
+  float *x = nullptr, *nrm = nullptr, *qkv = nullptr, *y = nullptr, *h13 = nullptr, *g = nullptr, *xf = nullptr,
+        *logits = nullptr;
+  ArBatchSlot* slots_dev = nullptr;
+  ArBatchSlot* slots_host[RING] = {};     // pinned staging ring
+  cudaEvent_t ev[RING] = {};
+  bool ev_pending[RING] = {};
+  int cur = 0;
+  void ensure(int B);
+  ~ArBatchWork();
 };
 
 constexpr int HIST_CAP = 4096;     // columns kept of src_content_codes / pred_codes (the reference trims to 2048)
@@ -103,6 +135,8 @@ struct Stream {
   const long long* step_content_id = nullptr;   // per-step inputs of the next decode launch
   const float* step_noise = nullptr;
   const float* step_cond_row = nullptr;
+  int* step_pred_hist = nullptr;                // many-stream path: append the step's codes here (column step_pred_col)
+  int step_pred_col = 0;
   int pos_next = 0;                // next free sequence position (== cached_kv_pos[-1] + 1)
   unsigned step = 0;               // decode_one_token_ar calls so far (prefills included)
   unsigned long long seed = 0;
@@ -188,23 +222,30 @@ struct Engine {
 
   // stage drivers (all device pointers, stream-ordered, no host sync)
   int enc_num_ids(long long n_samples) const { return (int)(((n_samples / HOP) / 2) / 2); }
-  void enc_encode(const float* wave_dev, long long n_samples, long long* ids_dev, cudaStream_t st);
+  void enc_encode(const float* wave_dev /*[B][n]*/, int B, long long n_samples, long long* ids_dev /*[B][S]*/, cudaStream_t st);
   void voc_quantizer_decode(const long long* codes_dev, long long ld, int T, float* z_dev /*[4T][512]*/, cudaStream_t st);
   void voc_head(const float* z_dev /*[L][512]*/, int L, float* wave_dev /*[512 L]*/, cudaStream_t st);
   void voc_decode(const long long* codes_dev, long long ld, int T, float* wave_dev, cudaStream_t st);
   // out == nullptr: in place on x
-  void convnext(const ConvNextW& w, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out = nullptr);
+  void convnext(const ConvNextW& w, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out = nullptr,
+                int seg_rows = 0, long long x_seg = 0, long long out_seg = 0);
   // stateful (incremental) vocoder, voc_stream.cu
-  void voc_state_init(VocState& vs, int frames_per_step);
+  void voc_state_init(VocState& vs, int frames_per_step, int n_streams = 1);
   void voc_state_reset(VocState& vs, cudaStream_t st);
-  void voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st);
+  // codes: stream b's [8][c] block starts b * codes_seg after `codes` (row stride ld); wave_out [B][c*2048]
+  void voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st,
+                long long codes_seg = 0);
 
   // AR
   void ar_forward_tokens(Stream& s, float* x /*[M][768]*/, int M, int pos0, cudaStream_t st);
   void ar_prefill_prompt(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
                          const float* timbre, cudaStream_t st);
   void ar_prefill_delay(Stream& s, const long long* src_content, int n, cudaStream_t st);
+  void reprompt(Stream& s, Workspace& staging, cudaStream_t st);
   void ar_decode_step(Stream* const* streams, int batch, cudaStream_t st);
+  // any number of streams: the frame as a sequence of GEMM / attention / sampler kernels over all streams (ar_batch.cu)
+  void ar_decode_step_gemm(Stream* const* streams, int batch, cudaStream_t st);
+  ArBatchWork arb;
 };
 
 }  // namespace svanon

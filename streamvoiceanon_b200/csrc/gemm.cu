@@ -74,6 +74,12 @@ gemm_kernel(const GemmBatch batch) {
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   float4 ra[A_LD], rb[B_LD];
+  long long a_row[A_LD];                 // start of this thread's A rows (-1: past M); fixed over the K loop
+#pragma unroll
+  for (int l = 0; l < A_LD; ++l) {
+    const int m = m0 + ((tid + l * NT) >> 2);
+    a_row[l] = (m < p.M) ? gemm_a_row(p, m) : -1;
+  }
 
   auto load_tiles = [&](int it) {
     const int t = it / kIters;
@@ -84,10 +90,9 @@ gemm_kernel(const GemmBatch batch) {
       const int i = tid + l * NT;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (A_F4 % NT == 0 || i < A_F4) {
-        const int row = i >> 2, kq = i & 3;
-        const int m = m0 + row;
-        if (m < p.M) {
-          const float* src = p.A + ((long long)m * p.a_row_step + off) * p.lda + k0 + kq * 4;
+        const int kq = i & 3;
+        if (a_row[l] >= 0) {
+          const float* src = p.A + a_row[l] + off * p.lda + k0 + kq * 4;
           v = __ldg(reinterpret_cast<const float4*>(src));
           if (p.prologue == PRO_SILU) {
             v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
@@ -199,6 +204,8 @@ gemm_kernel(const GemmBatch batch) {
     for (int i = 0; i < 4; ++i) {
       const int m = m0 + gi * (BM / MG) + ty * 4 + i;
       if (m >= p.M) continue;
+      const long long c_row = gemm_c_row(p, m);
+      const long long r_row = p.residual ? gemm_r_row(p, m) : 0;
 #pragma unroll
       for (int gj = 0; gj < NG; ++gj) {
         const int nb = n0 + gj * (BN / NG) + tx * 4;
@@ -212,12 +219,12 @@ gemm_kernel(const GemmBatch batch) {
             if (p.act == ACT_GELU) v = gelu_erf(v);
             else if (p.act == ACT_LOGCLAMP) v = logf(fmaxf(v, 1e-5f));
             if (p.gamma) v *= __ldg(p.gamma + n);
-            if (p.residual) v += __ldg(p.residual + (long long)m * p.ldr + n);
+            if (p.residual) v += __ldg(p.residual + r_row + n);
             v *= p.out_scale;
           }
           y[j] = v;
         }
-        float* dst = p.C + (long long)m * p.ldc + nb;
+        float* dst = p.C + c_row + nb;
         if (nb + 3 < p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
           float4 o = make_float4(y[0], y[1], y[2], y[3]);
           if (p.accumulate) {

@@ -72,18 +72,28 @@ gemm_pipe_kernel(const PipeBatch batch) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+  constexpr int A_PER = A_CH / NT;
+  static_assert(A_CH % NT == 0, "A chunks must divide evenly over the threads");
+  long long a_row[A_PER];                // start of this thread's A rows (-1: past M); fixed over the K loop
+#pragma unroll
+  for (int j = 0; j < A_PER; ++j) {
+    const int m = m0 + ((tid + j * NT) >> 3);
+    a_row[j] = (m < p.M) ? gemm_a_row(p, m) : -1;
+  }
+
   auto issue = [&](int it, int stage) {
     float* As = smem + stage * STAGE_FLOATS;
     float* Bs = As + BM * PK;
     const int t = it / kSlabs;
     const int k0 = (it - t * kSlabs) * PK;
     const long long off = p.tap_off[t];
-    for (int i = tid; i < A_CH; i += NT) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      const int i = tid + j * NT;
       const int row = i >> 3, c = i & 7;
-      const int m = m0 + row;
       const int k = k0 + c * 4;
-      const bool ok = (m < p.M) && (k < p.K);
-      const float* src = ok ? p.A + ((long long)m * p.a_row_step + off) * p.lda + k : p.A;
+      const bool ok = (a_row[j] >= 0) && (k < p.K);
+      const float* src = ok ? p.A + a_row[j] + off * p.lda + k : p.A;
       cp_async16(As + swz(row, c), src, ok ? 16 : 0);
     }
     for (int i = tid; i < B_CH; i += NT) {
@@ -166,6 +176,8 @@ gemm_pipe_kernel(const PipeBatch batch) {
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty + i * NTY;
     if (m >= p.M) continue;
+    const long long c_row = gemm_c_row(p, m);
+    const long long r_row = p.residual ? gemm_r_row(p, m) : 0;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx + j * NTX;
@@ -175,9 +187,9 @@ gemm_pipe_kernel(const PipeBatch batch) {
       if (p.act == ACT_GELU) v = gelu_erf(v);
       else if (p.act == ACT_LOGCLAMP) v = logf(fmaxf(v, 1e-5f));
       if (p.gamma) v *= __ldg(p.gamma + n);
-      if (p.residual) v += __ldg(p.residual + (long long)m * p.ldr + n);
+      if (p.residual) v += __ldg(p.residual + r_row + n);
       v *= p.out_scale;
-      float* dst = p.C + (long long)m * p.ldc + n;
+      float* dst = p.C + c_row + n;
       *dst = p.accumulate ? *dst + v : v;
     }
   }

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
       const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
       const int m = m0 + row;
       a_ok[j] = m < p.M;
-      a_base[j] = p.A + (long long)(a_ok[j] ? m : 0) * p.a_row_step * p.lda + c * 4;
+      a_base[j] = p.A + gemm_a_row(p, a_ok[j] ? m : 0) + c * 4;
       a_off[j] = swz(row, c);
     }
     const float* b_base[B_PER];
@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     cluster.sync();
   }
   if (warp < 4 && (!SPLIT || rank == 0)) {
+    const long long c_row = (m < p.M) ? gemm_c_row(p, m) : 0;
+    const long long r_row = (m < p.M && p.residual) ? gemm_r_row(p, m) : 0;
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
@@ -287,8 +289,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
         }
       }
       if (m < p.M) {
-        float* dst = p.C + (long long)m * p.ldc + n0 + c0;
-        const float* res = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
+        float* dst = p.C + c_row + n0 + c0;
+        const float* res = p.residual ? p.residual + r_row + n0 + c0 : nullptr;
         const bool vec = (n0 + c0 + 15 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
                          (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
 #pragma unroll

@@ -29,12 +29,14 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 // MAXPT values per thread are kept in registers: C <= 128*MAXPT... launched with blockDim = 128.
 template <int MAXPT>
 __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
-                                 const float* __restrict__ b, int C, float eps) {
+                                 const float* __restrict__ b, int C, float eps, int seg_rows, long long x_seg,
+                                 long long y_seg) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
-  const float* xr = x + row * C;
+  const float* xr = x + seg_row_off(row, seg_rows, x_seg, C);
+  float* yr = y + seg_row_off(row, seg_rows, y_seg, C);
   float v[MAXPT];
   float s = 0.f;
 #pragma unroll
@@ -56,7 +58,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict_
 #pragma unroll
   for (int i = 0; i < MAXPT; ++i) {
     const int c = threadIdx.x + i * blockDim.x;
-    if (c < C) y[row * C + c] = (v[i] - mean) * inv * w[c] + b[c];
+    if (c < C) yr[c] = (v[i] - mean) * inv * w[c] + b[c];
   }
 }
 
@@ -64,11 +66,12 @@ __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict_
 template <int MAXPT>
 __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ dw_w,
                                   const float* __restrict__ dw_b, const float* __restrict__ ln_w,
-                                  const float* __restrict__ ln_b, int C, float eps) {
+                                  const float* __restrict__ ln_b, int C, float eps, int seg_rows, long long x_seg) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
+  const float* xr = x + seg_row_off(row, seg_rows, x_seg, C);      // rows -6..-1 are this stream's margin/history
   float v[MAXPT];
   float s = 0.f;
 #pragma unroll
@@ -78,7 +81,7 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict
     if (c < C) {
       a = dw_b[c];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) a = fmaf(dw_w[j * C + c], x[(row - 6 + j) * C + c], a);
+      for (int j = 0; j < 7; ++j) a = fmaf(dw_w[j * C + c], xr[(j - 6) * C + c], a);
     }
     v[i] = a;
     s += a;
@@ -102,11 +105,12 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict
 
 template <int MAXPT>
 __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w, int C,
-                               float eps) {
+                               float eps, long long x_ld) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
+  x += row * (x_ld - C);                                            // input rows may be strided (x_ld >= C)
   float v[MAXPT];
   float s = 0.f;
 #pragma unroll
@@ -125,7 +129,8 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ 
 
 // apply_rotary_emb (dual_ar_stream.py:1004-1016 / windowed_transformer.py:368-380): pairs (2i,2i+1),
 // table entry [pos][i] = (cos, sin) already rounded to bf16 and widened back to fp32.
-__global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict__ table, int rows, int heads, int pos0) {
+__global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict__ table, int rows, int heads, int pos0,
+                               int seg_rows) {
   pdl_trigger();
   pdl_wait();
   const int D = heads * HEAD_DIM;
@@ -138,8 +143,9 @@ __global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict_
   const int pair = r % (D / 2);
   const int i = pair % (HEAD_DIM / 2);
   float* p = qkv + (long long)row * 3 * D + which * D + pair * 2;
-  const float c = table[((long long)(pos0 + row) * (HEAD_DIM / 2) + i) * 2 + 0];
-  const float s = table[((long long)(pos0 + row) * (HEAD_DIM / 2) + i) * 2 + 1];
+  const int pos = pos0 + (seg_rows > 0 ? row % seg_rows : row);     // every stream's window starts at pos0
+  const float c = table[((long long)pos * (HEAD_DIM / 2) + i) * 2 + 0];
+  const float s = table[((long long)pos * (HEAD_DIM / 2) + i) * 2 + 1];
   const float x0 = p[0], x1 = p[1];
   p[0] = x0 * c - x1 * s;
   p[1] = x1 * c + x0 * s;
@@ -197,13 +203,14 @@ __global__ void bsq_kernel(const float* __restrict__ z, const float* __restrict_
 // GroupedResidualFSQ.get_output_from_indices for 8 groups x 1 quantizer, levels (8,5,5,5)
 // (vendored twin: finite_scalar_quantization.py:143-162, residual_fsq.py:112-156).
 __global__ void fsq_lookup_kernel(const long long* __restrict__ codes, long long ld, const float* __restrict__ w,
-                                  const float* __restrict__ b, float* __restrict__ z, int T) {
+                                  const float* __restrict__ b, float* __restrict__ z, int T, int seg_rows,
+                                  long long codes_seg) {
   pdl_trigger();
   pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)T * 512) return;
   const int t = idx / 512, c = idx % 512, g = c / 64, o = c % 64;
-  const long long id = codes[g * ld + t];
+  const long long id = seg_rows > 0 ? codes[(t / seg_rows) * codes_seg + g * ld + (t % seg_rows)] : codes[g * ld + t];
   const int levels[4] = {8, 5, 5, 5};
   const int basis[4] = {1, 8, 40, 200};
   float acc = b[g * 64 + o];
@@ -219,7 +226,7 @@ __global__ void fsq_lookup_kernel(const long long* __restrict__ codes, long long
 
 // activation_post (SiLU) + conv_post (16 -> 1, k = 13, causal) + tanh, firefly.py:289-291.
 __global__ void conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                 float* __restrict__ out, int L) {
+                                 float* __restrict__ out, int L, int seg_rows, long long x_seg) {
   pdl_trigger();
   pdl_wait();
   __shared__ float ws[13 * 16];
@@ -228,7 +235,7 @@ __global__ void conv_post_kernel(const float* __restrict__ x, const float* __res
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L) return;
   float acc = b[0];
-  const float4* xr = reinterpret_cast<const float4*>(x + (t - 12) * 16);
+  const float4* xr = reinterpret_cast<const float4*>(x + seg_row_off(t, seg_rows, x_seg, 16) - 12 * 16);
 #pragma unroll
   for (int j = 0; j < 13 * 4; ++j) {
     float4 v = __ldg(xr + j);
@@ -272,18 +279,18 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld
 }
 
 __global__ void scale_add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
-                                  float* __restrict__ out, long long n, float s) {
+                                  float* __restrict__ out, long long n, float s, long long seg_n, long long out_seg) {
   pdl_trigger();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (a[i] + b[i] + c[i]) * s;
+  if (i < n) out[seg_n > 0 ? (i / seg_n) * out_seg + i % seg_n : i] = (a[i] + b[i] + c[i]) * s;
 }
 
-__global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
+__global__ void fill_kernel(float* __restrict__ p, long long n, float v, long long seg_stride) {
   pdl_trigger();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  if (i < n) p[blockIdx.y * seg_stride + i] = v;
 }
 
 // out[r][c] = c < a_n ? a[r][c] : b[r][c - a_n]   (int32 sources, int32 or int64 destination)
@@ -317,33 +324,34 @@ inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1)
 }  // namespace
 
 void launch_layernorm(const float* x, float* y, const float* w, const float* b, int rows, int C, float eps,
-                      cudaStream_t st) {
+                      cudaStream_t st, int seg_rows, long long x_seg, long long y_seg) {
   if (rows <= 0) return;
   SV_CHECK(C <= 2048, "layernorm C");
-  if (C <= 512) launch_pdl(layernorm_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, w, b, C, eps);
-  else launch_pdl(layernorm_kernel<8>, dim3(rows), dim3(256), 0, st, x, y, w, b, C, eps);
+  if (C <= 512) launch_pdl(layernorm_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, w, b, C, eps, seg_rows, x_seg, y_seg);
+  else launch_pdl(layernorm_kernel<8>, dim3(rows), dim3(256), 0, st, x, y, w, b, C, eps, seg_rows, x_seg, y_seg);
   SV_LAUNCHED();
 }
 
 void launch_dwconv7_ln(const float* x, float* y, const float* dw_w, const float* dw_b, const float* ln_w,
-                       const float* ln_b, int rows, int C, float eps, cudaStream_t st) {
+                       const float* ln_b, int rows, int C, float eps, cudaStream_t st, int seg_rows, long long x_seg) {
   if (rows <= 0) return;
   SV_CHECK(C <= 512, "dwconv C");
-  launch_pdl(dwconv7_ln_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, dw_w, dw_b, ln_w, ln_b, C, eps);
+  launch_pdl(dwconv7_ln_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, dw_w, dw_b, ln_w, ln_b, C, eps, seg_rows, x_seg);
   SV_LAUNCHED();
 }
 
-void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st) {
+void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st,
+                    long long x_ld) {
   if (rows <= 0) return;
   SV_CHECK(C <= 1024, "rmsnorm C");
-  launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, x, y, w, C, eps);
+  launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, x, y, w, C, eps, x_ld > 0 ? x_ld : (long long)C);
   SV_LAUNCHED();
 }
 
-void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos0, cudaStream_t st) {
+void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos0, cudaStream_t st, int seg_rows) {
   if (rows <= 0) return;
   const long long total = (long long)rows * heads * HEAD_DIM;
-  launch_pdl(rope_qk_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, qkv, table, rows, heads, pos0);
+  launch_pdl(rope_qk_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, qkv, table, rows, heads, pos0, seg_rows);
   SV_LAUNCHED();
 }
 
@@ -366,15 +374,17 @@ void launch_bsq(const float* z, const float* w, const float* b, long long* ids, 
 }
 
 void launch_fsq_lookup(const long long* codes, long long ld, const float* w, const float* b, float* z, int T,
-                       cudaStream_t st) {
+                       cudaStream_t st, int seg_rows, long long codes_seg) {
   if (T <= 0) return;
-  launch_pdl(fsq_lookup_kernel, dim3(blocks_for((long long)T * 512, 256)), dim3(256), 0, st, codes, ld, w, b, z, T);
+  launch_pdl(fsq_lookup_kernel, dim3(blocks_for((long long)T * 512, 256)), dim3(256), 0, st, codes, ld, w, b, z, T, seg_rows,
+             codes_seg);
   SV_LAUNCHED();
 }
 
-void launch_conv_post(const float* x, const float* w, const float* b, float* out, int L, cudaStream_t st) {
+void launch_conv_post(const float* x, const float* w, const float* b, float* out, int L, cudaStream_t st, int seg_rows,
+                      long long x_seg) {
   if (L <= 0) return;
-  launch_pdl(conv_post_kernel, dim3(blocks_for(L, 256)), dim3(256), 0, st, x, w, b, out, L);
+  launch_pdl(conv_post_kernel, dim3(blocks_for(L, 256)), dim3(256), 0, st, x, w, b, out, L, seg_rows, x_seg);
   SV_LAUNCHED();
 }
 
@@ -400,9 +410,9 @@ void launch_copy_rows(const float* src, long long src_ld, float* dst, long long 
 }
 
 void launch_scale_add3(const float* a, const float* b, const float* c, float* out, long long n, float s,
-                       cudaStream_t st) {
+                       cudaStream_t st, long long seg_n, long long out_seg) {
   if (n <= 0) return;
-  launch_pdl(scale_add3_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, a, b, c, out, n, s);
+  launch_pdl(scale_add3_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, a, b, c, out, n, s, seg_n, out_seg);
   SV_LAUNCHED();
 }
 
@@ -426,9 +436,9 @@ void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t 
   SV_LAUNCHED();
 }
 
-void launch_fill(float* p, long long n, float v, cudaStream_t st) {
-  if (n <= 0) return;
-  launch_pdl(fill_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, p, n, v);
+void launch_fill(float* p, long long n, float v, cudaStream_t st, int nseg, long long seg_stride) {
+  if (n <= 0 || nseg <= 0) return;
+  launch_pdl(fill_kernel, dim3(blocks_for(n, 256), nseg), dim3(256), 0, st, p, n, v, seg_stride);
   SV_LAUNCHED();
 }
 

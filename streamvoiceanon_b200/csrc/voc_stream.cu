@@ -23,23 +23,25 @@ constexpr int RK[3] = {3, 7, 11};
 constexpr int RD[3] = {1, 3, 5};
 
 // dst[i] = src[i + shift] for i < margin, possibly overlapping: walk upwards in chunks, read-all then write-all.
+// grid (buffers, streams)
 __global__ void __launch_bounds__(256) shift_history_kernel(const ShiftDesc* __restrict__ descs) {
   pdl_trigger();
   pdl_wait();
   const ShiftDesc d = descs[blockIdx.x];
+  float* base = d.base + blockIdx.y * d.seg;
   constexpr int PER = 8;
-  for (int base = 0; base < d.margin_floats; base += 256 * PER) {
+  for (int b0 = 0; b0 < d.margin_floats; b0 += 256 * PER) {
     float v[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      const int i = base + j * 256 + threadIdx.x;
-      v[j] = (i < d.margin_floats) ? d.base[i + d.shift_floats] : 0.f;
+      const int i = b0 + j * 256 + threadIdx.x;
+      v[j] = (i < d.margin_floats) ? base[i + d.shift_floats] : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      const int i = base + j * 256 + threadIdx.x;
-      if (i < d.margin_floats) d.base[i] = v[j];
+      const int i = b0 + j * 256 + threadIdx.x;
+      if (i < d.margin_floats) base[i] = v[j];
     }
     __syncthreads();
   }
@@ -52,17 +54,20 @@ VocState::~VocState() {
   if (desc_dev) cudaFree(desc_dev);
 }
 
-void Engine::voc_state_init(VocState& vs, int c) {
+void Engine::voc_state_init(VocState& vs, int c, int B) {
   SV_CHECK(c >= 1 && c <= 8, "frames per vocoder step");
+  SV_CHECK(B >= 1, "streams per vocoder state");
   if (vs.arena) { cudaFree(vs.arena); vs.arena = nullptr; }
   if (vs.desc_dev) { cudaFree(vs.desc_dev); vs.desc_dev = nullptr; }
   vs.c = c;
+  vs.B = B;
   std::vector<SBuf*> all;
   size_t total = 0;
   auto plan = [&](SBuf& b, int margin, int rows, int C) {
     b.margin = margin; b.rows = rows; b.C = C;
+    b.seg = (long long)((((size_t)(margin + rows) * C + 63) & ~(size_t)63));
     b.base = reinterpret_cast<float*>(total);          // offset for now
-    total += ((size_t)(margin + rows) * C + 63) & ~(size_t)63;
+    total += (size_t)b.seg * B;
     all.push_back(&b);
   };
   plan(vs.u1, 6, 2 * c, 512);
@@ -87,7 +92,7 @@ void Engine::voc_state_init(VocState& vs, int c) {
   std::vector<ShiftDesc> descs;
   for (SBuf* b : all) {
     b->base = vs.arena + reinterpret_cast<size_t>(b->base);
-    descs.push_back({b->base, b->margin * b->C, b->rows * b->C});
+    descs.push_back({b->base, b->margin * b->C, b->rows * b->C, b->seg});
   }
   vs.n_desc = (int)descs.size();
   SV_CUDA(cudaMalloc(&vs.desc_dev, descs.size() * sizeof(ShiftDesc)));
@@ -100,37 +105,48 @@ void Engine::voc_state_reset(VocState& vs, cudaStream_t st) {
   vs.primed_frames = 0;
 }
 
-// One step: vs.c new code frames (codes [8][..] with row stride ld) -> vs.c * 2048 new samples.
-void Engine::voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st) {
+// One step: vs.c new code frames per stream (codes [8][..] with row stride ld) -> vs.c * 2048 new samples per stream.
+void Engine::voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st,
+                      long long codes_seg) {
   SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
   SV_CHECK(vs.arena, "vocoder state not initialised");
-  const int c = vs.c;
-  ws.ensure(((size_t)c * 500000 + (4u << 20)) * sizeof(float));
+  const int c = vs.c, B = vs.B;
+  const bool seg = B > 1;
+  ws.ensure(((size_t)c * B * 500000 + (4u << 20)) * sizeof(float));
   ws.reset();
+  // output rows of stream b start b * buf.seg after buf.data(); plain scratch rows are [B * rows][C]
+  auto seg_out = [&](GemmParams& p, int rows_per_stream, long long a_seg, long long c_seg, long long r_seg = 0) {
+    if (!seg) return;
+    p.seg_rows = rows_per_stream; p.a_seg = a_seg; p.c_seg = c_seg; p.r_seg = r_seg;
+  };
   // DownsampleFiniteScalarQuantize.decode (fsq.py:112-116)
-  float* z0 = ws.alloc_f((long long)c * 512);
-  launch_fsq_lookup(codes, ld, fsq_w, fsq_b, z0, c, st);
-  float* tmp = ws.alloc_f((long long)4 * c * 512);
-  float* hid = ws.alloc_f((long long)4 * c * 2048);
-  float* o1 = ws.alloc_f((long long)2 * c * 512);
+  float* z0 = ws.alloc_f((long long)B * c * 512);
+  launch_fsq_lookup(codes, ld, fsq_w, fsq_b, z0, B * c, st, seg ? c : 0, codes_seg);
+  float* tmp = ws.alloc_f((long long)B * 4 * c * 512);
+  float* hid = ws.alloc_f((long long)B * 4 * c * 2048);
+  float* o1 = ws.alloc_f((long long)B * 2 * c * 512);
   {
     GemmParams p;
-    p.A = z0; p.W = up_w[0]; p.C = vs.u1.data(); p.bias = up_b[0]; p.M = c; p.N = 1024; p.K = 512; p.lda = 512; p.ldc = 1024;
+    p.A = z0; p.W = up_w[0]; p.C = vs.u1.data(); p.bias = up_b[0]; p.M = B * c; p.N = 1024; p.K = 512; p.lda = 512; p.ldc = 1024;
+    seg_out(p, c, (long long)c * 512, vs.u1.seg);
     launch_gemm(p, st);
-    convnext(up_block[0], vs.u1.data(), 2 * c, tmp, hid, st, o1);
+    convnext(up_block[0], vs.u1.data(), B * 2 * c, tmp, hid, st, o1, seg ? 2 * c : 0, vs.u1.seg, (long long)2 * c * 512);
     GemmParams q;
-    q.A = o1; q.W = up_w[1]; q.C = vs.u2.data(); q.bias = up_b[1]; q.M = 2 * c; q.N = 1024; q.K = 512; q.lda = 512; q.ldc = 1024;
+    q.A = o1; q.W = up_w[1]; q.C = vs.u2.data(); q.bias = up_b[1]; q.M = B * 2 * c; q.N = 1024; q.K = 512; q.lda = 512; q.ldc = 1024;
+    seg_out(q, 2 * c, (long long)2 * c * 512, vs.u2.seg);
     launch_gemm(q, st);
-    convnext(up_block[1], vs.u2.data(), 4 * c, tmp, hid, st, vs.p0.data());
+    convnext(up_block[1], vs.u2.data(), B * 4 * c, tmp, hid, st, vs.p0.data(), seg ? 4 * c : 0, vs.u2.seg, vs.p0.seg);
   }
   // HiFiGANGenerator.forward (firefly.py:280-293)
   {
     GemmParams p;
-    p.A = vs.p0.data(); p.W = pre_w; p.C = vs.c0.data(); p.bias = pre_b; p.M = 4 * c; p.N = 512; p.K = 13 * 512; p.lda = 512;
+    p.A = vs.p0.data(); p.W = pre_w; p.C = vs.c0.data(); p.bias = pre_b; p.M = B * 4 * c; p.N = 512; p.K = 13 * 512; p.lda = 512;
     p.ldc = 512; p.tap_off[0] = -12;
+    seg_out(p, 4 * c, vs.p0.seg, vs.c0.seg);
     launch_gemm(p, st);
   }
   const float* cur = vs.c0.data();
+  long long cur_seg = vs.c0.seg;
   int rows = 4 * c;
   for (int i = 0; i < 5; ++i) {
     const int Ci = CH[i], Co = CH[i + 1], s = UPS[i];
@@ -138,20 +154,26 @@ void Engine::voc_step(VocState& vs, const long long* codes, long long ld, float*
     VocState::Level& L = vs.lv[i];
     {
       GemmParams p;
-      p.A = cur; p.W = ups_w[i]; p.C = L.x.data(); p.bias = ups_b[i]; p.M = rows; p.N = s * Co; p.K = 2 * Ci; p.lda = Ci;
+      p.A = cur; p.W = ups_w[i]; p.C = L.x.data(); p.bias = ups_b[i]; p.M = B * rows; p.N = s * Co; p.K = 2 * Ci; p.lda = Ci;
       p.ldc = (long long)s * Co; p.tap_off[0] = -1; p.prologue = PRO_SILU;
+      seg_out(p, rows, cur_seg, L.x.seg);
       launch_gemm(p, st);
     }
     float* r2[3];
-    for (int j = 0; j < 3; ++j) r2[j] = ws.alloc_f((long long)Lo * Co);
+    const long long plain_seg = (long long)Lo * Co;
+    for (int j = 0; j < 3; ++j) r2[j] = ws.alloc_f((long long)B * Lo * Co);
     for (int d = 0; d < 3; ++d) {
       GemmParams p1[3], p2[3];
       for (int j = 0; j < 3; ++j) {
-        const float* in = (d == 0) ? L.x.data() : L.r[j][d - 1].data();
+        const SBuf& inb = (d == 0) ? L.x : L.r[j][d - 1];
+        const float* in = inb.data();
         float* out = (d == 2) ? r2[j] : L.r[j][d].data();
-        auto setup = [&](GemmParams& p, const ResConvW& w, const float* A, float* C, const float* res) {
-          p.A = A; p.W = w.w; p.C = C; p.bias = w.b; p.residual = res; p.M = Lo; p.N = Co; p.lda = Co; p.ldc = Co;
+        const long long out_seg = (d == 2) ? plain_seg : L.r[j][d].seg;
+        auto setup = [&](GemmParams& p, const ResConvW& w, const float* A, long long a_seg, float* C, long long c_seg,
+                         const float* res, long long r_seg) {
+          p.A = A; p.W = w.w; p.C = C; p.bias = w.b; p.residual = res; p.M = B * Lo; p.N = Co; p.lda = Co; p.ldc = Co;
           p.ldr = Co; p.prologue = PRO_SILU;
+          seg_out(p, Lo, a_seg, c_seg, r_seg);
           if (w.d == 1) {
             p.K = w.k * Co; p.taps = 1; p.tap_off[0] = -(w.k - 1);
           } else {
@@ -159,18 +181,20 @@ void Engine::voc_step(VocState& vs, const long long* codes, long long ld, float*
             for (int t = 0; t < w.k; ++t) p.tap_off[t] = -(w.k - 1 - t) * w.d;
           }
         };
-        setup(p1[j], res1[i][j][d], in, L.t[j][d].data(), nullptr);
-        setup(p2[j], res2[i][j][d], L.t[j][d].data(), out, in);
+        setup(p1[j], res1[i][j][d], in, inb.seg, L.t[j][d].data(), L.t[j][d].seg, nullptr, 0);
+        setup(p2[j], res2[i][j][d], L.t[j][d].data(), L.t[j][d].seg, out, out_seg, in, inb.seg);
       }
       launch_gemm(p1, 3, st);
       launch_gemm(p2, 3, st);
     }
-    launch_scale_add3(r2[0], r2[1], r2[2], L.next.data(), (long long)Lo * Co, 1.f / 3.f, st);
+    launch_scale_add3(r2[0], r2[1], r2[2], L.next.data(), (long long)B * Lo * Co, 1.f / 3.f, st, seg ? plain_seg : 0,
+                      L.next.seg);
     cur = L.next.data();
+    cur_seg = L.next.seg;
     rows = Lo;
   }
-  launch_conv_post(cur, post_w, post_b, wave_out, rows, st);
-  launch_pdl(shift_history_kernel, dim3(vs.n_desc), dim3(256), 0, st, vs.desc_dev);
+  launch_conv_post(cur, post_w, post_b, wave_out, B * rows, st, seg ? rows : 0, cur_seg);
+  launch_pdl(shift_history_kernel, dim3(vs.n_desc, B), dim3(256), 0, st, vs.desc_dev);
   SV_LAUNCHED();
   vs.primed_frames += c;
 }

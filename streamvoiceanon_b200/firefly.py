@@ -60,14 +60,20 @@ class ContentTokenizer(_Shim):
     @torch.no_grad()
     def encode(self, audios, audio_lengths):
         """FireflyArchitecture.encode, firefly_encoder.py:553-566: wav [B,L] f32, lens [B] ->
-        (ids int64 [1,B,T], feature_lengths [B]).  Rows are encoded one by one; for a row shorter than L the
-        causal-prefix property makes ids[:len//2048] identical to the reference, later ids are 0."""
+        (ids int64 [1,B,T], feature_lengths [B]).  Full-length rows go through the engine side by side in one call;
+        ragged rows are encoded one by one: for a row shorter than L the causal-prefix property makes
+        ids[:len//2048] identical to the reference, later ids are 0."""
         audios = audios.float()
         B, L = audios.shape
         dev = audios.device if audios.is_cuda else torch.device("cuda", self._engine.device)
         T = _lib.load().svanon_enc_num_ids(L)
         ids = torch.zeros(1, B, T, dtype=torch.int64, device=dev)
         lens = [int(x) for x in audio_lengths.reshape(-1).tolist()]
+        if B > 1 and T > 0 and all(n >= L for n in lens):
+            rows = audios.contiguous()
+            _lib.check(self._engine.lib.svanon_enc_encode_batch(self._engine.handle, ptr(rows), B, L, ptr(ids),
+                                                                C.c_void_p(_cuda_stream_ptr())))
+            return ids, (audio_lengths // 512) // self.downsample_factor
         for b in range(B):
             n = min(lens[b], L)
             row = audios[b, :n].contiguous()

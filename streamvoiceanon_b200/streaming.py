@@ -117,3 +117,75 @@ class StreamSession:
             self.close()
         except Exception:
             pass
+
+
+class BatchSession:
+    """N streams advanced in lock-step, one library call per chunk for all of them (BASELINE configs 3-4).
+
+    The reference has no equivalent (it is batch-1: `max_batch_size=1`, evaluations/infer_arvc.py:56); the contract
+    is that stream i of the batch produces exactly what `StreamSession` i produces alone.  Usage: create the
+    StreamSessions, `set_prompt` each (same delay), then `BatchSession(sessions).setup(...)` and
+    `process_chunk(waves [n, chunk*2048])` per chunk."""
+
+    def __init__(self, sessions):
+        if not sessions:
+            raise ValueError("empty batch")
+        self.sessions = list(sessions)
+        self._engine = self.sessions[0]._engine
+        arr = (C.c_void_p * len(self.sessions))(*[s._h for s in self.sessions])
+        h = C.c_void_p()
+        _lib.check(self._engine.lib.svanon_batch_create(self._engine.handle, arr, len(self.sessions), C.byref(h)))
+        self._h = h
+        self.chunk = 1
+
+    def setup(self, encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32,
+              decode_chunk_frames=1):
+        _lib.check(self._engine.lib.svanon_batch_setup(self._h, encode_window_frames, decode_window_frames, max_seq_frames,
+                                                       buffer_frames, decode_chunk_frames))
+        self.chunk = decode_chunk_frames
+        for s in self.sessions:
+            s.chunk = decode_chunk_frames
+            s.max_seq_frames = max_seq_frames
+            s._n_src = 0
+            s._prefilled = False
+
+    def set_ar_path(self, path: int):
+        """0: persistent kernel for 1/2/4 streams, many-stream kernels otherwise; 1: always the many-stream kernels."""
+        _lib.check(self._engine.lib.svanon_batch_set_ar_path(self._h, path))
+
+    def process_chunk(self, wave_chunks: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n = len(self.sessions)
+        w = wave_chunks.reshape(n, -1).float().contiguous()
+        if out is None:
+            out = torch.empty_like(w)
+        noises = [s._noise() for s in self.sessions]
+        noise = None
+        if any(z is not None for z in noises):
+            if any(z is None for z in noises):
+                raise RuntimeError("either every stream of a batch has a noise tape or none has")
+            noise = torch.stack(noises).float().contiguous()
+            if w.is_cuda:
+                noise = noise.to(w.device)
+        _lib.check(self._engine.lib.svanon_batch_process_chunk(self._h, ptr(w), w.shape[1],
+                                                               ptr(noise) if noise is not None else None, ptr(out),
+                                                               C.c_void_p(_cuda_stream_ptr())))
+        return out
+
+    def set_timing(self, enable: bool = True):
+        _lib.check(self._engine.lib.svanon_batch_set_timing(self._h, int(enable)))
+
+    def last_timing(self):
+        ms = (C.c_float * 3)()
+        _lib.check(self._engine.lib.svanon_batch_last_timing(self._h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def close(self):
+        if self._h is not None:
+            self._engine.lib.svanon_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

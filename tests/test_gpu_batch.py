@@ -1,0 +1,198 @@
+"""GPU tests of the many-stream (lock-step) path.  The reference is batch-1, so the contract is per-stream parity:
+stream i of a batch == the same stream alone (which tests/test_gpu_parity.py pins to the reference fixtures and the
+oracle), plus one direct check of a batched stream against the reference fixture.  Integer outputs bit-exact;
+waveforms within the fp32 MSE tolerance written beside each check (GEMM tile/split choices differ with M)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from streamvoiceanon_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+WAVE_MSE_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def models(weights):
+    from streamvoiceanon_b200 import ARVCWrapper, ContentTokenizer, Vocoder
+    ar = ARVCWrapper()
+    ar.setup_caches(max_batch_size=1, max_seq_len=2048, dtype=torch.float16)
+    ar.load_state_dict(weights["ar"], strict=False)
+    tok = ContentTokenizer()
+    tok.load_state_dict(weights["tok"], strict=False)
+    voc = Vocoder()
+    voc.load_state_dict(weights["voc"], strict=False)
+    return ar, tok, voc
+
+
+def test_encode_batch_equals_single(models):
+    _, tok, _ = models
+    n = 21 * 2048
+    wavs = torch.stack([synth.synth_audio_44k(3000 + i, 1.2)[:n] for i in range(3)]).cuda()
+    lens = torch.LongTensor([n] * 3).cuda()
+    both, flen = tok.encode(wavs, lens)
+    assert tuple(both.shape) == (1, 3, 21) and flen.tolist() == [21, 21, 21]
+    for i in range(3):
+        one, _ = tok.encode(wavs[i:i + 1].contiguous(), lens[:1])
+        assert torch.equal(one[0, 0], both[0, i]), i
+
+
+def test_encode_batch_streaming_window_vs_reference(models, gold):
+    """Row 1 of a 2-row batched call is the reference's 128-frame streaming-window fixture."""
+    _, tok, _ = models
+    g = gold("encoder_window128")
+    live = int(g["live_frames"])
+    win = torch.zeros(2, 128 * 2048)
+    win[0] = synth.synth_audio_44k(3100, 6.5)[: 128 * 2048]
+    win[1, -live * 2048:] = synth.synth_audio_44k(int(g["audio_seed"]), 2.0)[: live * 2048]
+    ids, _ = tok.encode(win.cuda(), torch.LongTensor([win.shape[1]] * 2).cuda())
+    assert np.array_equal(ids[:, 1:2].cpu().numpy(), g["ids"])
+
+
+def _prompts(n, seed=900):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for b in range(n):
+        T = 20 + 9 * b
+        out.append((torch.randint(0, 8192, (1, T), generator=g), torch.randint(0, 1000, (1, 8, T), generator=g).int(),
+                    torch.randint(0, 8192, (1, 8), generator=g), synth.synth_speaker(6000 + b)))
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 3, 5])
+def test_decode_many_equals_single_stream(models, tape, n):
+    """svanon_ar_decode_many (GEMM path, any stream count) == the persistent single-stream kernel, codes bit-exact."""
+    from streamvoiceanon_b200 import ARVCWrapper, _lib
+    from streamvoiceanon_b200.engine import ptr
+    ar0, _, _ = models
+    prompts = _prompts(n)
+    singles = []
+    for b, (rc, ra, src, (style, timbre)) in enumerate(prompts):
+        ar0.set_delay(delay=2)
+        ar0.set_noise_fn(tape(7200 + b), 0)
+        ar0.prefill_prompt(rc.cuda(), ra.cuda(), style.cuda(), timbre.cuda())
+        ar0.prefill_src_condition4delay(src[:, :2].cuda())
+        singles.append([ar0.decode_one(src[:, t:t + 1].cuda())[0].cpu() for t in range(2, 8)])
+    wrappers = []
+    for b, (rc, ra, src, (style, timbre)) in enumerate(prompts):
+        w = ARVCWrapper()
+        w.setup_caches(max_batch_size=1, max_seq_len=2048)
+        w.set_delay(delay=2)
+        w.prefill_prompt(rc.cuda(), ra.cuda(), style.cuda(), timbre.cuda())
+        w.prefill_src_condition4delay(src[:, :2].cuda())
+        wrappers.append(w)
+    lib = _lib.load()
+    handles = (C.c_void_p * n)(*[w._stream for w in wrappers])
+    for i, t in enumerate(range(2, 8)):
+        ids = torch.tensor([int(p[2][0, t]) for p in prompts], dtype=torch.int64).cuda()
+        noise = torch.stack([torch.stack([tape(7200 + b)(2 + i, s, 1000)[:1000] for s in range(1, 9)]) for b in range(n)])
+        noise = noise.float().contiguous().cuda()
+        out = torch.empty(n, 8, dtype=torch.int32, device="cuda")
+        _lib.check(lib.svanon_ar_decode_many(handles, n, ptr(ids), ptr(noise), ptr(out), None))
+        for b in range(n):
+            assert torch.equal(out[b].cpu(), singles[b][i][:, 0]), (b, i)
+            assert int(lib.svanon_ar_position(wrappers[b]._stream)) == 33 + 2 * prompts[b][0].shape[1] + 3 + 2 * (i + 1)
+
+
+def _stream_inputs(tok, b, n_ref, n_chunks, chunk):
+    style, timbre = synth.synth_speaker(5100 + b)
+    ref_wave = synth.synth_audio_44k(5100 + b, 3.5)[: n_ref * 2048][None]
+    gen = torch.Generator().manual_seed(300 + b)
+    ref_audio = torch.randint(0, 1000, (1, 8, n_ref), generator=gen).int()
+    ref_content, _ = tok.encode(ref_wave.cuda(), torch.LongTensor([ref_wave.shape[1]]).cuda())
+    src = synth.synth_audio_44k(1100 + b, 3.0)[: n_chunks * chunk * 2048].view(n_chunks, chunk * 2048)
+    return ref_content[0], ref_audio, style, timbre, src
+
+
+def _session(inp, tape_fn, delay):
+    from streamvoiceanon_b200 import StreamSession
+    ref_content, ref_audio, style, timbre, _ = inp
+    sess = StreamSession()
+    sess.set_noise_fn(tape_fn, 0)
+    sess.set_prompt(ref_content.cuda(), ref_audio.cuda(), style.cuda(), timbre.cuda(), max_prompt_frames=256, delay=delay)
+    return sess
+
+
+@pytest.mark.parametrize("n,chunk,ar_path", [(3, 1, 0), (2, 2, 1), (2, 1, 0)])
+def test_batch_loop_equals_single_sessions(models, tape, n, chunk, ar_path):
+    """N streams with different prompts (lengths 26, 31, ...), sources and noise tapes, small windows so that the
+    streams re-prompt at DIFFERENT chunks (stream 0 after 9 frames, stream 1 after 4, stream 2 at once): ids bit-exact and waveform equal to fp32 rounding vs each stream alone."""
+    from streamvoiceanon_b200 import BatchSession
+    _, tok, _ = models
+    n_chunks, delay = 16, 2
+    cfg = dict(encode_window_frames=24, decode_window_frames=24, max_seq_frames=52, buffer_frames=6,
+               decode_chunk_frames=chunk)
+    inputs = [_stream_inputs(tok, b, 26 + 5 * b, n_chunks, chunk) for b in range(n)]
+    singles = []
+    for b, inp in enumerate(inputs):
+        sess = _session(inp, tape(7300 + b), delay)
+        sess.setup(**cfg)
+        waves = torch.cat([sess.process_chunk(inp[4][i].cuda()).cpu() for i in range(n_chunks)])
+        singles.append((*sess.history(), waves))
+        sess.close()
+    sessions = [_session(inp, tape(7300 + b), delay) for b, inp in enumerate(inputs)]
+    batch = BatchSession(sessions)
+    batch.setup(**cfg)
+    batch.set_ar_path(ar_path)
+    outs = []
+    for i in range(n_chunks):
+        w = torch.stack([inp[4][i] for inp in inputs])
+        outs.append(batch.process_chunk(w.cuda() if i % 2 == 0 else w).cpu())       # device and host buffers
+    waves = torch.cat(outs, dim=1)
+    for b, sess in enumerate(sessions):
+        src_hist, pred_hist = sess.history()
+        assert torch.equal(src_hist, singles[b][0]), b
+        assert torch.equal(pred_hist, singles[b][1]), b
+        mse = float(((waves[b] - singles[b][2]) ** 2).mean())
+        assert mse < 1e-10, (b, mse)
+    batch.close()
+    for s in sessions:
+        s.close()
+
+
+def test_batch_loop_vs_reference_fixture(models, gold, tape):
+    """Stream 0 of a 2-stream batch (many-stream decode kernels forced) reproduces the UNMODIFIED reference's
+    process_one_chunk run with CLI-default windows (tests/golden/stream_default.npz)."""
+    from streamvoiceanon_b200 import BatchSession, StreamSession
+    _, tok, _ = models
+    g = gold("stream_default")
+    n_ref, n_chunks = int(g["n_ref"]), int(g["n_chunks"])
+    style, timbre = synth.synth_speaker(int(g["ref_seed"]))
+    ref_wave = synth.synth_audio_44k(int(g["ref_seed"]), 3.5)[: n_ref * 2048][None]
+    gen = torch.Generator().manual_seed(int(g["codes_seed"]))
+    ref_audio = torch.randint(0, 1000, (1, 8, n_ref), generator=gen).int()
+    ref_content, _ = tok.encode(ref_wave.cuda(), torch.LongTensor([ref_wave.shape[1]]).cuda())
+    s0 = StreamSession()
+    s0.set_noise_fn(tape(int(g["tape_seed"])), 0)
+    s0.set_prompt(ref_content[0].cuda(), ref_audio.cuda(), style.cuda(), timbre.cuda(), 256, int(g["delay"]))
+    other = _stream_inputs(tok, 7, 40, n_chunks, 1)
+    s1 = _session(other, tape(7400), int(g["delay"]))
+    batch = BatchSession([s0, s1])
+    batch.setup(int(g["encode_window_frames"]), int(g["decode_window_frames"]), int(g["max_seq_frames"]),
+                int(g["buffer_frames"]), 1)
+    batch.set_ar_path(1)
+    src = synth.synth_audio_44k(int(g["src_seed"]), 1.5)[: n_chunks * 2048].view(n_chunks, 2048)
+    waves = torch.cat([batch.process_chunk(torch.stack([src[i], other[4][i]]).cuda())[0].cpu() for i in range(n_chunks)])
+    src_hist, pred_hist = s0.history()
+    assert np.array_equal(src_hist.numpy()[None], g["src_content"])
+    assert np.array_equal(pred_hist.numpy()[None], g["pred_codes"])
+    mse = float(((waves.numpy() - g["wave"]) ** 2).mean())
+    assert mse < WAVE_MSE_TOL, mse
+    batch.close(); s0.close(); s1.close()
+
+
+def test_batch_errors(models, tape):
+    from streamvoiceanon_b200 import BatchSession
+    _, tok, _ = models
+    inp = _stream_inputs(tok, 0, 26, 2, 1)
+    a, b = _session(inp, None, 2), _session(inp, None, 4)
+    with pytest.raises(RuntimeError, match="same delay"):
+        BatchSession([a, b]).setup(24, 24, 36, 6, 1)
+    with pytest.raises(RuntimeError, match="incremental vocoder"):
+        BatchSession([a]).setup(24, 8, 36, 6, 1)
+    with pytest.raises(RuntimeError, match="only once"):
+        BatchSession([a, a])
+    a.close(); b.close()
