@@ -166,7 +166,8 @@ int svanon_batch_setup(svanon_batch* b, int enc_win, int dec_win, int max_seq_fr
       SV_CHECK(s.delay == b->delay, "all streams of a batch must use the same delay");
       const int pad = dec_win;       // first window is all padding
       SV_CHECK(std::min(pad, 24) <= s.ref_frames, "prompt shorter than the vocoder window padding needs");
-      s.enc_win = enc_win; s.dec_win = dec_win; s.max_seq_frames = max_seq_frames; s.buffer_frames = buffer_frames;
+      s.enc_win = 0;                 // the stream is driven by the batch now, not by svanon_stream_process_chunk
+      s.dec_win = dec_win; s.max_seq_frames = max_seq_frames; s.buffer_frames = buffer_frames;
       s.chunk = chunk; s.n_src = 0; s.n_pred = 0; s.delay_prefilled = false;
       ptrs[i] = {s.src_hist, s.pred_hist, s.ref_audio_dev, s.ref_frames};
     }

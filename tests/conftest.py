@@ -45,6 +45,21 @@ def weights():
 
 
 @pytest.fixture(scope="session")
+def models(weights):
+    """The three reference-facing model objects, loaded ONCE per process (one engine per GPU)."""
+    from streamvoiceanon_b200 import ARVCWrapper, ContentTokenizer, Vocoder
+    ar = ARVCWrapper()
+    ar.setup_caches(max_batch_size=1, max_seq_len=2048, dtype=torch.float16)
+    ar.load_state_dict(weights["ar"], strict=False)
+    tok = ContentTokenizer()
+    tok.load_state_dict(weights["tok"], strict=False)
+    voc = Vocoder()
+    voc.load_state_dict(weights["voc"], strict=False)       # weight-norm form, folded by the library
+    voc.remove_parametrizations()
+    return ar, tok, voc
+
+
+@pytest.fixture(scope="session")
 def tape():
     from streamvoiceanon_b200 import synth
 

@@ -15,19 +15,6 @@ pytestmark = pytest.mark.gpu
 WAVE_MSE_TOL = 1e-8
 
 
-@pytest.fixture(scope="module")
-def models(weights):
-    from streamvoiceanon_b200 import ARVCWrapper, ContentTokenizer, Vocoder
-    ar = ARVCWrapper()
-    ar.setup_caches(max_batch_size=1, max_seq_len=2048, dtype=torch.float16)
-    ar.load_state_dict(weights["ar"], strict=False)
-    tok = ContentTokenizer()
-    tok.load_state_dict(weights["tok"], strict=False)
-    voc = Vocoder()
-    voc.load_state_dict(weights["voc"], strict=False)
-    return ar, tok, voc
-
-
 def test_encode_batch_equals_single(models):
     _, tok, _ = models
     n = 21 * 2048

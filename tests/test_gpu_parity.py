@@ -15,20 +15,6 @@ WAVE_MSE_TOL = 1e-8          # fp32 waveform MSE tolerance (SURVEY.md section 8c
 LOGIT_TOL = 2e-3             # max-abs error of teacher-forced logits (values are O(3))
 
 
-@pytest.fixture(scope="module")
-def models(weights):
-    from streamvoiceanon_b200 import ARVCWrapper, ContentTokenizer, Vocoder
-    ar = ARVCWrapper()
-    ar.setup_caches(max_batch_size=1, max_seq_len=2048, dtype=torch.float16)
-    ar.load_state_dict(weights["ar"], strict=False)
-    tok = ContentTokenizer()
-    tok.load_state_dict(weights["tok"], strict=False)
-    voc = Vocoder()
-    voc.load_state_dict(weights["voc"], strict=False)       # weight-norm form, folded by the library
-    voc.remove_parametrizations()
-    return ar, tok, voc
-
-
 def test_native_library_is_loaded(models):
     import os
     maps = open(f"/proc/{os.getpid()}/maps").read()

@@ -13,8 +13,10 @@ from streamvoiceanon_b200.engine import Engine, ptr  # noqa: E402
 eng = Engine.get(0)
 lib = _lib.load()
 SHAPES = [(512, 1536, 384), (512, 384, 1536), (512, 2048, 512), (512, 512, 2048), (128, 1536, 512), (128, 512, 1536),
-          (512, 2050, 2048), (256, 128, 1408), (32, 256, 2816)]
-for mode in (1, 2):
+          (512, 2050, 2048), (256, 128, 1408), (32, 256, 2816), (16, 2304, 768), (16, 768, 2304), (64, 2304, 768),
+          (256, 2304, 768), (4096, 1536, 384), (16384, 2048, 512), (16384, 512, 2048), (8192, 128, 1408)]
+MODES = [int(x) for x in sys.argv[1:]] or [1, 2]
+for mode in MODES:
     _lib.check(lib.svanon_set_gemm_mode(mode))
     for (M, N, K) in SHAPES:
         A = torch.randn(M, K, device="cuda")
