@@ -7,15 +7,17 @@
 //     x*y ~= hi_x*hi_y + hi_x*lo_y + lo_x*hi_y          (dropped terms <= 2^-20 |x*y|)
 // is accumulated in fp32 in TMEM: three kind::tf32 MMAs per K-step.
 //
-// Data path: the same 128-byte-swizzled K-major tiles gemm_pipe.cu uses ([row][32 floats], 16-byte chunks XORed
-// with row&7 == UMMA/TMA SWIZZLE_128B) are filled with cp.async; after a slab lands all 128 threads split it in
-// place (hi) and into a sibling tile (lo), fence the generic->async proxy, and one thread issues the 12 MMAs of the
-// slab (4 K-steps x 3 products) and commits them to an mbarrier that frees the stage.  CTA tile 128 x BN, one CTA
-// per SM, accumulator = BN TMEM columns, epilogue reads TMEM with tcgen05.ld (one row per thread).  Split-K over a
-// thread-block cluster with a DSMEM reduction as in gemm.cu.
+// Data path: 128-byte-swizzled K-major tiles ([row][32 floats], 16-byte chunks XORed with row&7 == UMMA/TMA
+// SWIZZLE_128B).  The operands have to pass through registers anyway (the hi/lo split is arithmetic), so the 16
+// producer warps load their chunks global -> registers several K-slabs ahead, split, and store hi and lo tiles
+// straight into a free pipeline stage, fence the generic->async proxy, and one thread issues the 12 MMAs of the slab
+// (4 K-steps x 3 products) and commits them to an mbarrier that frees the stage.  CTA tile 128 x BN, one CTA per SM,
+// accumulator = BN TMEM columns, epilogue reads TMEM with tcgen05.ld.  Split-K over a thread-block cluster with a
+// DSMEM reduction distributed over the ranks.
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -99,21 +101,46 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int TC_PRODUCERS = 128;                  // warps 0-3: cp.async + hi/lo split, later the epilogue
-constexpr int TC_THREADS = TC_PRODUCERS + 32;      // warp 4: MMA issuer (one elected lane)
+constexpr int TC_PRODUCER_WARPS = 16;              // warps 0-15: global -> registers -> hi/lo split -> swizzled tiles; epilogue
+constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
+constexpr int TC_THREADS = TC_PRODUCERS + 32;      // warp 16: MMA issuer (one elected lane)
+constexpr int TC_DEPTH = 4;                        // K-slabs a producer thread keeps in flight in registers
 
-// Warp-specialised: 4 producer warps stream K-slabs (cp.async into SW128 tiles, each thread splits the chunks it
-// loaded itself into hi/lo once its own copy group has landed, then arrives on full[stage]); one thread of warp 4
-// waits on full[stage], issues the 12 tcgen05.mma of the slab and commits them to empty[stage]; after the last slab
-// the producers turn into the epilogue (TMEM -> registers -> global).  No block-wide barrier in the main loop.
+__device__ __forceinline__ float4 ldg_nc(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ void split_store(float* hi_dst, float* lo_dst, float4 v) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_dst) = h;
+  *reinterpret_cast<float4*>(lo_dst) = l;
+}
+
+// Warp-specialised.  16 producer warps stream the K-slabs: every thread keeps TC_DEPTH slabs of its own 16-byte chunks
+// in flight in REGISTERS (plain 128-bit no-allocate loads; the weight chunks of the first slabs are requested before
+// griddepcontrol.wait), splits a slab into hi/lo TF32 terms straight into the 128-byte-swizzled tiles of a free
+// pipeline stage and arrives on full[stage].  One thread of warp 16 waits on full[stage], issues the slab's 12
+// tcgen05.mma and commits them to empty[stage].  The first kernel version used 4 producer warps and was bound by
+// their instruction latency (ncu: 1.3 warps per scheduler, 9.4 cycles per issued instruction, ~2.7 us per slab);
+// with 16 warps a slab costs each thread 3-4 chunks.  After the last slab all 16 warps run the epilogue
+// (TMEM -> registers -> global).  Split-K over a thread-block cluster: every rank parks its partial tile in its own
+// shared memory and then reduces (in fixed rank order) and writes ONE column slice of the tile, so the DSMEM reads are
+// spread over all ranks instead of being serialised in rank 0.
 template <int BN, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch batch) {
   constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;
   constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;           // A_hi | A_lo | B_hi | B_lo
   constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = BN * 8 / TC_PRODUCERS;   // 16-byte chunks per thread
-  constexpr int DEPTH = STAGES - 2;                                    // slabs loaded ahead of the split
+  constexpr int D = TC_DEPTH;
   static_assert(TBM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
-  static_assert(DEPTH >= 1, "need at least 3 stages");
+  static_assert(A_PER >= 1 && B_PER >= 1, "tile too small for the producer count");
   extern __shared__ unsigned char dsmem_raw[];
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], acc_bar;
@@ -152,11 +179,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_d = tmem_holder;
-  pdl_wait();            // everything above touched only weights / on-chip state; activations come next
 
-  if (warp < 4) {
+  if (warp < TC_PRODUCER_WARPS) {
     // =========================================================== producers
-    // fixed per-thread chunk assignment: chunk i = tid + j*128 -> row = i>>3, c = i&7
+    // fixed per-thread chunk assignment: chunk i = tid + j*512 -> row = i>>3, c = i&7
     const float* a_base[A_PER];
     int a_off[A_PER];
     bool a_ok[A_PER];
@@ -181,86 +207,153 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     }
     const int c4 = (tid & 7) * 4;                      // K offset of this thread's chunks inside a slab
     const bool silu = p.prologue == PRO_SILU;
-    for (int li = 0; li < n_it + DEPTH; ++li) {
-      if (li < n_it) {
-        const int stage = li % STAGES;
-        mbar_wait(&empty_bar[stage], ((li / STAGES) & 1) ^ 1);           // MMAs that read this stage are done
-        float* As = smem + stage * STAGE_FLOATS;
-        float* Bs = As + 2 * A_FLOATS;
-        const int it = it_begin + li;
-        const int t = it / kSlabs;
-        const int k0 = (it - t * kSlabs) * TK;
-        const bool k_ok = (k0 + c4) < p.K;
-        const long long a_shift = (long long)p.tap_off[t] * p.lda + k0;
-        const long long b_shift = (long long)t * p.N * p.K + k0;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ra[D][A_PER], rb[D][B_PER];
+    auto load_b = [&](int li, float4 (&dst)[B_PER]) {
+      const int it = it_begin + li;
+      const int t = it / kSlabs;
+      const int k0 = (it - t * kSlabs) * TK;
+      const bool k_ok = (k0 + c4) < p.K;
+      const long long b_shift = (long long)t * p.N * p.K + k0;
 #pragma unroll
-        for (int j = 0; j < A_PER; ++j) cp_async16(As + a_off[j], a_base[j] + a_shift, (a_ok[j] && k_ok) ? 16 : 0);
+      for (int j = 0; j < B_PER; ++j) dst[j] = (b_ok[j] && k_ok) ? ldg_nc(b_base[j] + b_shift) : zero4;
+    };
+    auto load_a = [&](int li, float4 (&dst)[A_PER]) {
+      const int it = it_begin + li;
+      const int t = it / kSlabs;
+      const int k0 = (it - t * kSlabs) * TK;
+      const bool k_ok = (k0 + c4) < p.K;
+      const long long a_shift = (long long)p.tap_off[t] * p.lda + k0;
 #pragma unroll
-        for (int j = 0; j < B_PER; ++j) cp_async16(Bs + b_off[j], b_base[j] + b_shift, (b_ok[j] && k_ok) ? 16 : 0);
-      }
-      cp_async_commit();
-      const int lj = li - DEPTH;
-      if (lj >= 0) {
-        cp_async_wait<DEPTH>();                                          // this thread's chunks of slab lj have landed
-        const int stage = lj % STAGES;
-        float* As = smem + stage * STAGE_FLOATS;
-        float* Bs = As + 2 * A_FLOATS;
+      for (int j = 0; j < A_PER; ++j) dst[j] = (a_ok[j] && k_ok) ? ldg_nc(a_base[j] + a_shift) : zero4;
+    };
+    // weights do not depend on the previous kernel: request them before waiting for it
 #pragma unroll
-        for (int j = 0; j < A_PER + B_PER; ++j) {
-          float4* q = (j < A_PER) ? reinterpret_cast<float4*>(As + a_off[j < A_PER ? j : 0])
-                                  : reinterpret_cast<float4*>(Bs + b_off[j >= A_PER ? j - A_PER : 0]);
-          float4* ql = q + ((j < A_PER) ? A_FLOATS / 4 : B_FLOATS / 4);
-          float4 v = *q;
-          if (silu && j < A_PER) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          *q = h;
-          *ql = l;
+    for (int d = 0; d < D; ++d)
+      if (d < n_it) load_b(d, rb[d]);
+    pdl_wait();
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      if (d < n_it) load_a(d, ra[d]);
+    for (int li0 = 0; li0 < n_it; li0 += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int li = li0 + d;
+        if (li < n_it) {
+          const int stage = li % STAGES;
+          mbar_wait(&empty_bar[stage], ((li / STAGES) & 1) ^ 1);           // MMAs that read this stage are done
+          float* As = smem + stage * STAGE_FLOATS;
+          float* Bs = As + 2 * A_FLOATS;
+#pragma unroll
+          for (int j = 0; j < A_PER; ++j) {
+            float4 v = ra[d][j];
+            if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
+            split_store(As + a_off[j], As + A_FLOATS + a_off[j], v);
+          }
+#pragma unroll
+          for (int j = 0; j < B_PER; ++j) split_store(Bs + b_off[j], Bs + B_FLOATS + b_off[j], rb[d][j]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the MMA
+          mbar_arrive(&full_bar[stage]);
+          if (li + D < n_it) { load_b(li + D, rb[d]); load_a(li + D, ra[d]); }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the MMA
-        mbar_arrive(&full_bar[stage]);
       }
     }
-  } else if (lane == 0) {
-    // =========================================================== MMA issuer
-    const unsigned idesc = umma_idesc(BN);
-    for (int li = 0; li < n_it; ++li) {
-      const int stage = li % STAGES;
-      mbar_wait(&full_bar[stage], (li / STAGES) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float* As = smem + stage * STAGE_FLOATS;
-      float* Bs = As + 2 * A_FLOATS;
-      const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
-      const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
+  } else {
+    pdl_wait();
+    if (lane == 0) {
+      // =========================================================== MMA issuer
+      const unsigned idesc = umma_idesc(BN);
+      for (int li = 0; li < n_it; ++li) {
+        const int stage = li % STAGES;
+        mbar_wait(&full_bar[stage], (li / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* As = smem + stage * STAGE_FLOATS;
+        float* Bs = As + 2 * A_FLOATS;
+        const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
+        const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
 #pragma unroll
-      for (int kk = 0; kk < TK / 8; ++kk) {
-        const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
-        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
-        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+        for (int kk = 0; kk < TK / 8; ++kk) {
+          const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
+          umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
+          umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+          umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
       }
-      umma_commit(&empty_bar[stage]);
+      umma_commit(&acc_bar);
     }
-    umma_commit(&acc_bar);
   }
   __syncwarp();
 
   // ---------------------------------------------------------------- TMEM -> registers -> (split-K reduce) -> global
-  const int row = warp * 32 + lane;                 // accumulator row == TMEM lane (warps 0-3)
-  const int m = m0 + row;
+  // warp w reads TMEM lanes (w & 3) * 32 .. +31 (the hardware's lane quadrant of a warp) and the column group w >> 2
+  constexpr int CG = BN / 4;                        // columns per column group
+  const int quad = warp & 3, grp = warp >> 2;
   cg::cluster_group cluster = cg::this_cluster();
-  if (warp < 4) {
+  if (warp < TC_PRODUCER_WARPS) {
     if (n_it > 0) mbar_wait(&acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  if (SPLIT) {
-    if (warp < 4 && rank != 0) {
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+  auto finish = [&](float (&v)[16], int m, int col0) {      // bias/act/gamma/residual/scale + store of 16 columns
+    const int n_base = n0 + col0;
+    const long long c_row = gemm_c_row(p, m);
+    float* dst = p.C + c_row + n_base;
+    const float* res = p.residual ? p.residual + gemm_r_row(p, m) + n_base : nullptr;
+    const bool vec = (n_base + 15 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float y = v[j] + s_bias[col0 + j];
+      if (p.act == ACT_GELU) y = gelu_erf(y);
+      else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
+      v[j] = y * s_gamma[col0 + j];
+    }
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (res) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(res + j));
+          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (n_base + j < p.N) {
+          float y = v[j];
+          if (res) y += __ldg(res + j);
+          y *= p.out_scale;
+          dst[j] = p.accumulate ? dst[j] + y : y;
+        }
+      }
+    }
+  };
+  if (!SPLIT) {
+    if (warp < TC_PRODUCER_WARPS) {
+      const int row = quad * 32 + lane;
+      const int m = m0 + row;
+#pragma unroll
+      for (int c0 = grp * CG; c0 < (grp + 1) * CG; c0 += 16) {
         float v[16];
-        if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
+        if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(quad * 32) << 16) + c0, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (m < p.M) finish(v, m, c0);
+      }
+    }
+  } else {
+    // every rank parks its partial tile column-major ([BN][128] floats) in its own shared memory
+    if (warp < TC_PRODUCER_WARPS) {
+      const int row = quad * 32 + lane;
+#pragma unroll
+      for (int c0 = grp * CG; c0 < (grp + 1) * CG; c0 += 16) {
+        float v[16];
+        if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(quad * 32) << 16) + c0, v);
         else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -270,52 +363,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
       }
     }
     cluster.sync();
-  }
-  if (warp < 4 && (!SPLIT || rank == 0)) {
-    const long long c_row = (m < p.M) ? gemm_c_row(p, m) : 0;
-    const long long r_row = (m < p.M && p.residual) ? gemm_r_row(p, m) : 0;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(warp * 32) << 16) + c0, v);
-      else {
+    // rank r owns the 16-column groups r, r + split, ...: 128 rows x 16 columns = 512 (row, 4-column) items per group
+    if (warp < TC_PRODUCER_WARPS) {
+      const int row = tid & (TBM - 1), sub = tid >> 7;          // sub 0..3 -> columns sub*4 .. +3 of the group
+      const int m = m0 + row;
+      for (int g16 = rank; g16 < BN / 16; g16 += split) {
+        const int col0 = g16 * 16 + sub * 4;
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < split; ++r) {
+          const float* part = cluster.map_shared_rank(smem, r);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-      }
-      if (SPLIT) {
-        for (int r = 1; r < split; ++r) {
-          const float* remote = cluster.map_shared_rank(smem, r);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += remote[(c0 + j) * TBM + row];
+          for (int j = 0; j < 4; ++j) acc4[j] += part[(col0 + j) * TBM + row];
         }
-      }
-      if (m < p.M) {
-        float* dst = p.C + c_row + n0 + c0;
-        const float* res = p.residual ? p.residual + r_row + n0 + c0 : nullptr;
-        const bool vec = (n0 + c0 + 15 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                         (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
+        if (m < p.M) {
+          const int n_base = n0 + col0;
+          float* dst = p.C + gemm_c_row(p, m) + n_base;
+          const float* res = p.residual ? p.residual + gemm_r_row(p, m) + n_base : nullptr;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float y = v[j] + s_bias[c0 + j];
-          if (p.act == ACT_GELU) y = gelu_erf(y);
-          else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
-          v[j] = y * s_gamma[c0 + j];
-        }
-        if (vec) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (res) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res + j));
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-            }
-            o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
-            *reinterpret_cast<float4*>(dst + j) = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (n0 + c0 + j < p.N) {
-              float y = v[j];
+          for (int j = 0; j < 4; ++j) {
+            if (n_base + j < p.N) {
+              float y = acc4[j] + s_bias[col0 + j];
+              if (p.act == ACT_GELU) y = gelu_erf(y);
+              else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
+              y *= s_gamma[col0 + j];
               if (res) y += __ldg(res + j);
               y *= p.out_scale;
               dst[j] = p.accumulate ? dst[j] + y : y;
@@ -366,7 +436,11 @@ void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
 // Returns false when the problem is not a good fit (small M: latency kernels; tiny N).
 bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
   const GemmParams& p = ps[0];
-  if (p.M < 96 || p.N < 64) return false;
+  static const int min_m = [] {
+    const char* e = getenv("SVANON_TC_MIN_M");          // tuning knob: smallest M that goes to the tensor cores
+    return e ? atoi(e) : 96;
+  }();
+  if (p.M < min_m || p.N < 64) return false;
   TcBatch b;
   int min_slabs = 1 << 30;
   for (int i = 0; i < count; ++i) {
