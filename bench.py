@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=10, help="chunks of the CPU baseline sample (main arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--concurrent", default="16,32,48", help="stream counts of the lock-step batch sweep (N=1 only; '' = skip)")
     return ap.parse_args()
 
 
@@ -142,6 +143,51 @@ def cpu_oracle_loop(rank: int, n_chunks: int, warm: int, threads: int):
     times.sort()
     stage = {k: (sorted(v)[len(v) // 2] * 1e3 if v else None) for k, v in so.timings.items()}
     return sum(times) / len(times) * 1e3, times[len(times) // 2] * 1e3, stage
+
+
+def concurrent_sweep(tok, counts, steps=10, warm=3):
+    """BASELINE metric, second half: "concurrent streams/GPU at RTF<1".  B streams advanced in lock-step by ONE library
+    call per chunk (svanon_batch_process_chunk): same windows / delay / prompt length as the single-stream workload,
+    device-resident chunks, CUDA-event timed.  The reference is batch-1, so its figure is 1 stream x its RTF."""
+    from streamvoiceanon_b200 import BatchSession, StreamSession, synth
+    out = []
+    ref_wave, _, style, timbre, _ = make_inputs(0)
+    n_ref = ref_wave.shape[1] // 2048
+    ref_content, _ = tok.encode(ref_wave.cuda(), torch.LongTensor([ref_wave.shape[1]]).cuda())
+    for B in counts:
+        sessions = []
+        for b in range(B):
+            g = torch.Generator().manual_seed(99 + b)
+            s = StreamSession()
+            s.set_sampling(0.7, 0.7, seed=7000 + b)
+            s.set_prompt(ref_content[0], torch.randint(0, 1000, (1, 8, n_ref), generator=g).int().cuda(), style.cuda(),
+                         timbre.cuda(), WORKLOAD["max_prompt_frames"], WORKLOAD["delay"])
+            sessions.append(s)
+        batch = BatchSession(sessions)
+        batch.setup(WORKLOAD["encode_window_frames"], WORKLOAD["decode_window_frames"], WORKLOAD["max_seq_frames"],
+                    WORKLOAD["buffer_frames"], 1)
+        src = torch.stack([synth.synth_audio_44k(1000 + (b % 8), 2.0)[: 40 * 2048] for b in range(B)]).cuda()
+        o = torch.empty(B, 2048, device="cuda")
+        it = 0
+        for _ in range(warm + WORKLOAD["delay"]):
+            batch.process_chunk(src[:, (it % 40) * 2048:(it % 40 + 1) * 2048], o); it += 1
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            batch.process_chunk(src[:, (it % 40) * 2048:(it % 40 + 1) * 2048], o); it += 1
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        batch.set_timing(True)
+        batch.process_chunk(src[:, :2048], o)
+        st = batch.last_timing()
+        batch.close()
+        for s in sessions:
+            s.close()
+        out.append({"streams": B, "ms_per_step": ms, "rtf": ms / 1e3 / FRAME_S, "frames_per_s": B / (ms / 1e3),
+                    "stage_ms": {"E": st[0], "A": st[1], "V": st[2]}})
+    return out
 
 
 def run_reference(args):
@@ -284,6 +330,15 @@ def run_engine(args):
                      "algorithmic_bytes_per_launch": ar_bytes, "launch_ms": ar_ms, "s_valid": s_valid},
         "clocks": clocks,
     }
+    counts = [int(x) for x in args.concurrent.split(",") if x.strip()] if world == 1 else []
+    if counts:
+        sess.close()
+        sweep = concurrent_sweep(tok, counts)
+        ok = [r["streams"] for r in sweep if r["rtf"] < 1.0]
+        line["concurrent_streams"] = {
+            "what": "B streams per GPU in lock-step through svanon_batch_process_chunk (one pass over the weights per chunk "
+                    "for all streams), same workload per stream as `value`; the reference is batch-1",
+            "max_measured_streams_rtf_lt_1": max(ok) if ok else 1, "sweep": sweep}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         mean_ms, med_ms, cstage = cpu_oracle_loop(0, args.cpu_sample, 2, cores)

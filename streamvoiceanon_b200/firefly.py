@@ -63,6 +63,11 @@ class ContentTokenizer(_Shim):
         (ids int64 [1,B,T], feature_lengths [B]).  Full-length rows go through the engine side by side in one call;
         ragged rows are encoded one by one: for a row shorter than L the causal-prefix property makes
         ids[:len//2048] identical to the reference, later ids are 0."""
+        if torch.compiler.is_compiling():
+            # under the caller's torch.compile(fullgraph=True) (infer_arvc.py:136-142) the call is one opaque custom op;
+            # lengths cannot be read on the host there, rows are taken as full-length (the streaming loop's case)
+            from . import ops
+            return ops.enc_encode(audios), (audio_lengths // 512) // self.downsample_factor
         audios = audios.float()
         B, L = audios.shape
         dev = audios.device if audios.is_cuda else torch.device("cuda", self._engine.device)
@@ -98,6 +103,9 @@ class _Quantizer:
     def decode(self, indices):
         """DownsampleFiniteScalarQuantize.decode, fsq.py:112-116: [B,8,T] -> [B,512,4T] (a transposed view of the
         engine's channels-last buffer, which `head` consumes without a copy)."""
+        if torch.compiler.is_compiling():
+            from . import ops
+            return ops.voc_quantizer_decode(indices).transpose(1, 2)
         eng = self._o._engine
         B, G, T = indices.shape
         assert G == 8
@@ -117,6 +125,9 @@ class _Head:
     @torch.no_grad()
     def __call__(self, z, template=None):
         """HiFiGANGenerator.forward, firefly.py:280-293: [B,512,L] -> [B,1,512 L]."""
+        if torch.compiler.is_compiling():           # torch.compile(self.firefly.head, fullgraph=True), infer_arvc.py:128-134
+            from . import ops
+            return ops.voc_head(z)
         eng = self._o._engine
         B, Cc, L = z.shape
         assert Cc == 512

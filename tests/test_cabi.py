@@ -54,3 +54,16 @@ def test_product_does_not_import_oracle():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.hpp")):
         text = p.read_text()
         assert "import oracle" not in text and "from oracle" not in text, p
+
+
+def test_custom_ops_registered_with_fake_impls():
+    """torch.compile(fullgraph=True) in the reference's caller code needs the engine entries as custom ops whose output
+    shapes can be derived without running them (streamvoiceanon_b200/ops.py)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from streamvoiceanon_b200 import ops  # noqa: F401
+    with FakeTensorMode():
+        assert tuple(torch.ops.svanon_b200.enc_encode(torch.empty(2, 40960)).shape) == (1, 2, 20)
+        assert tuple(torch.ops.svanon_b200.voc_head(torch.empty(1, 512, 8)).shape) == (1, 1, 4096)
+        assert tuple(torch.ops.svanon_b200.voc_quantizer_decode(torch.empty(1, 8, 3, dtype=torch.int64)).shape) == (1, 12, 512)
+        assert tuple(torch.ops.svanon_b200.voc_decode(torch.empty(1, 8, 3, dtype=torch.int64)).shape) == (1, 1, 6144)
