@@ -144,6 +144,13 @@ int svanon_stream_process_chunk(svanon_stream* s, const float* wave_chunk, int n
  * >= 15 frames of history); 0 = recompute decode_window_frames frames per chunk exactly like
  * the reference does.  Call before the first chunk. */
 int svanon_stream_set_vocoder_mode(svanon_stream* s, int incremental);
+/* window re-encode inside the loop: 1 (default) = ring-buffer state -- the tokenizer's conv-stack outputs (the
+ * transformer inputs) of the previous window are kept per stream; when the window slides only its first and last
+ * 40 + chunk frames go through the conv stack again (the first ones see the window-start zero padding exactly as in
+ * the reference's recompute, the last ones contain the new frames), the attention transformer then runs over the
+ * whole window as in the reference.  Same function of the same samples as 0 = re-encode the whole window every chunk
+ * (evaluations/infer_arvc.py:495-508); used when encode_window_frames >= 2 * (40 + chunk) + 8. */
+int svanon_stream_set_encoder_mode(svanon_stream* s, int incremental);
 /* per-stage device time (CUDA events on the launching stream) of the last non-warm-up chunk:
  * ms[0] = E (window encode), ms[1] = A (decode steps), ms[2] = V (vocoder) */
 int svanon_stream_set_timing(svanon_stream* s, int enable);
@@ -183,6 +190,7 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
 /* decode path of the batch: 0 (default) = persistent kernel for 1/2/4 streams, many-stream kernels otherwise;
  * 1 = always the many-stream kernels */
 int svanon_batch_set_ar_path(svanon_batch* b, int path);
+int svanon_batch_set_encoder_mode(svanon_batch* b, int incremental);   /* as svanon_stream_set_encoder_mode */
 /* per-stage device time of the last non-warm-up chunk, as svanon_stream_last_timing */
 int svanon_batch_set_timing(svanon_batch* b, int enable);
 int svanon_batch_last_timing(svanon_batch* b, float* ms);

@@ -49,6 +49,8 @@ _SIGS = {
     "svanon_stream_setup": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "svanon_stream_process_chunk": (C.c_int, [_p, _p, C.c_int, _p, _p, _p]),
     "svanon_stream_set_vocoder_mode": (C.c_int, [_p, C.c_int]),
+    "svanon_stream_set_encoder_mode": (C.c_int, [_p, C.c_int]),
+    "svanon_batch_set_encoder_mode": (C.c_int, [_p, C.c_int]),
     "svanon_stream_set_timing": (C.c_int, [_p, C.c_int]),
     "svanon_stream_last_timing": (C.c_int, [_p, C.POINTER(C.c_float)]),
     "svanon_stream_history": (C.c_int, [_p, _p, C.POINTER(C.c_int), _p, C.POINTER(C.c_int), C.c_int]),

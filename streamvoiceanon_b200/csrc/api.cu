@@ -404,6 +404,7 @@ int svanon_stream_setup(svanon_stream* sh, int enc_win, int dec_win, int max_seq
     s.codes_win_dev = dmalloc<long long>((size_t)8 * dec_win);
     s.wave_win_dev = dmalloc<float>((size_t)dec_win * SAMPLES_PER_FRAME);
     s.n_src = 0; s.n_pred = 0; s.delay_prefilled = false;
+    s.enc_state.valid = false;
     // incremental vocoder when the window leaves >= 15 frames of history in front of the new chunk
     s.voc_incremental = s.voc_mode != 0 && (dec_win - chunk >= 15) && (std::min(dec_win - chunk, 24) / chunk * chunk >= 15);
     s.voc_fed = 0;
@@ -434,7 +435,8 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
     // 2. E: re-encode the whole window, keep the last `chunk` ids (:505-518)
     s.ev_valid = false;
     if (s.timing) SV_CUDA(cudaEventRecord(s.ev[0], st));
-    e.enc_encode(s.wave_ring, 1, (long long)nw, s.ids_win_dev, st);
+    if (s.enc_state.enabled) e.enc_window_step(s.enc_state, s.wave_ring, 1, s.enc_win, s.chunk, s.ids_win_dev, st);
+    else e.enc_encode(s.wave_ring, 1, (long long)nw, s.ids_win_dev, st);
     if (s.timing) SV_CUDA(cudaEventRecord(s.ev[1], st));
     if (s.n_src + s.chunk > HIST_CAP) {
       const int keep = HIST_CAP / 2;
@@ -513,6 +515,14 @@ int svanon_stream_set_vocoder_mode(svanon_stream* sh, int incremental) {
                           (std::min(s.dec_win - s.chunk, 24) / s.chunk * s.chunk >= 15);
       if (s.voc_incremental && !s.voc.arena) s.eng->voc_state_init(s.voc, s.chunk);
     }
+  });
+}
+
+int svanon_stream_set_encoder_mode(svanon_stream* sh, int incremental) {
+  return guarded([&] {
+    SV_CHECK(sh, "null stream");
+    sh->st.enc_state.enabled = incremental != 0;
+    sh->st.enc_state.valid = false;
   });
 }
 

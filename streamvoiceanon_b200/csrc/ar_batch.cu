@@ -28,38 +28,14 @@ __global__ void __launch_bounds__(256) arb_gather_kernel(const ArBatchSlot* __re
   for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)m * D + c] = src[c];
 }
 
-// RoPE on q (in place) and k, then k/v of every new row into its stream's cache.  grid = rows, block = 384 (one
-// thread per (head, pair)).  RPS rows per stream; FAST: position = codebook index, 8-slot cache.
-template <bool FAST>
-__global__ void __launch_bounds__(384) arb_rope_append_kernel(const ArBatchSlot* __restrict__ slots, float* __restrict__ qkv,
-                                                              const float* __restrict__ table, int layer, int cb, int max_seq) {
-  pdl_trigger();
-  pdl_wait();
-  constexpr int RPS = FAST ? 1 : 2;
-  const int m = blockIdx.x, b = m / RPS, j = m % RPS;
-  const ArBatchSlot& s = slots[b];
-  const int pos = FAST ? cb : s.pos + j;
-  const int pr = threadIdx.x;              // 0..383
-  const int h = pr >> 5, i = pr & 31;
-  float* row = qkv + (long long)m * 3 * D;
-  const float cs = __ldg(table + ((long long)pos * (HEAD_DIM / 2) + i) * 2);
-  const float sn = __ldg(table + ((long long)pos * (HEAD_DIM / 2) + i) * 2 + 1);
-  const float2 qv = *reinterpret_cast<const float2*>(row + 2 * pr);
-  *reinterpret_cast<float2*>(row + 2 * pr) = make_float2(qv.x * cs - qv.y * sn, qv.y * cs + qv.x * sn);
-  const float2 kv = *reinterpret_cast<const float2*>(row + D + 2 * pr);
-  const float2 vv = *reinterpret_cast<const float2*>(row + 2 * D + 2 * pr);
-  const long long dst = FAST ? (((long long)layer * H + h) * AR_CODEBOOKS + pos) * HEAD_DIM + 2 * i
-                             : (((long long)layer * H + h) * max_seq + pos) * HEAD_DIM + 2 * i;
-  *reinterpret_cast<float2*>((FAST ? s.fkc : s.kc) + dst) = make_float2(kv.x * cs - kv.y * sn, kv.y * cs + kv.x * sn);
-  *reinterpret_cast<float2*>((FAST ? s.fvc : s.vc) + dst) = vv;
-}
-
-// Slow-stack attention of the two new tokens of one (stream, head) over that stream's valid cache prefix.
-// grid (H, B), 8 warps walk the keys; token 0 sits at pos (keys <= pos), token 1 at pos+1.
+// Slow-stack attention of one (stream, head), fused with what precedes it in Attention.forward
+// (dual_ar_stream.py:895-936): RoPE on q and k of the two new tokens, KV-cache append, then attention of both tokens
+// over that stream's valid cache prefix.  grid (H, B); every lane owns the interleaved pair (2*lane, 2*lane+1) of
+// the head, 8 warps walk the keys; token 0 sits at pos (keys <= pos), token 1 at pos+1.
 constexpr int ATT_WARPS = 8;
 __global__ void __launch_bounds__(ATT_WARPS * 32) arb_attn_slow_kernel(const ArBatchSlot* __restrict__ slots,
                                                                        const float* __restrict__ qkv, float* __restrict__ y,
-                                                                       int layer, int max_seq) {
+                                                                       const float* __restrict__ rope, int layer, int max_seq) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sm[ATT_WARPS * 2 * PART];
@@ -68,10 +44,26 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) arb_attn_slow_kernel(const ArB
   const ArBatchSlot& s = slots[b];
   const int pos = s.pos;
   const int nkeys = pos + 2;
-  const float* kc = s.kc + ((long long)layer * H + h) * max_seq * HEAD_DIM;
-  const float* vc = s.vc + ((long long)layer * H + h) * max_seq * HEAD_DIM;
-  const float2 q0 = *(reinterpret_cast<const float2*>(qkv + (long long)(2 * b) * 3 * D + h * HEAD_DIM) + lane);
-  const float2 q1 = *(reinterpret_cast<const float2*>(qkv + (long long)(2 * b + 1) * 3 * D + h * HEAD_DIM) + lane);
+  float* kc = s.kc + ((long long)layer * H + h) * max_seq * HEAD_DIM;
+  float* vc = s.vc + ((long long)layer * H + h) * max_seq * HEAD_DIM;
+  float2 q[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float* row = qkv + (long long)(2 * b + j) * 3 * D + h * HEAD_DIM;
+    const float2 cs = __ldg(reinterpret_cast<const float2*>(rope + ((long long)(pos + j) * (HEAD_DIM / 2) + lane) * 2));
+    const float2 qv = *(reinterpret_cast<const float2*>(row) + lane);
+    q[j] = make_float2(qv.x * cs.x - qv.y * cs.y, qv.y * cs.x + qv.x * cs.y);
+    if (warp == 0) {
+      const float2 kv = *(reinterpret_cast<const float2*>(row + D) + lane);
+      const float2 vv = *(reinterpret_cast<const float2*>(row + 2 * D) + lane);
+      *(reinterpret_cast<float2*>(kc + (long long)(pos + j) * HEAD_DIM) + lane) =
+          make_float2(kv.x * cs.x - kv.y * cs.y, kv.y * cs.x + kv.x * cs.y);
+      *(reinterpret_cast<float2*>(vc + (long long)(pos + j) * HEAD_DIM) + lane) = vv;
+    }
+  }
+  if (warp == 0) __threadfence();
+  __syncthreads();                       // the two new keys are in the cache before anybody walks it
+  const float2 q0 = q[0], q1 = q[1];
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
   for (int key = warp; key < nkeys; key += ATT_WARPS) {
@@ -111,25 +103,35 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) arb_attn_slow_kernel(const ArB
   }
 }
 
-// Fast-stack attention: <= 8 keys, one warp per (stream, head).
+// Fast-stack attention, fused the same way: RoPE at position cb, append into the 8-slot cache, attention over the
+// <= 8 keys.  One warp per (stream, head).
 __global__ void __launch_bounds__(128) arb_attn_fast_kernel(const ArBatchSlot* __restrict__ slots, const float* __restrict__ qkv,
-                                                            float* __restrict__ y, int layer, int cb, int n_items) {
+                                                            float* __restrict__ y, const float* __restrict__ rope, int layer,
+                                                            int cb, int n_items) {
   pdl_trigger();
   pdl_wait();
   const int item = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (item >= n_items) return;
   const int b = item / H, h = item % H;
   const ArBatchSlot& s = slots[b];
-  const float2 qv = *(reinterpret_cast<const float2*>(qkv + (long long)b * 3 * D + h * HEAD_DIM) + lane);
-  const float* kc = s.fkc + ((long long)layer * H + h) * AR_CODEBOOKS * HEAD_DIM;
-  const float* vc = s.fvc + ((long long)layer * H + h) * AR_CODEBOOKS * HEAD_DIM;
+  float* kc = s.fkc + ((long long)layer * H + h) * AR_CODEBOOKS * HEAD_DIM;
+  float* vc = s.fvc + ((long long)layer * H + h) * AR_CODEBOOKS * HEAD_DIM;
+  const float* row = qkv + (long long)b * 3 * D + h * HEAD_DIM;
+  const float2 cs = __ldg(reinterpret_cast<const float2*>(rope + ((long long)cb * (HEAD_DIM / 2) + lane) * 2));
+  const float2 qr = *(reinterpret_cast<const float2*>(row) + lane);
+  const float2 kr = *(reinterpret_cast<const float2*>(row + D) + lane);
+  const float2 v_new = *(reinterpret_cast<const float2*>(row + 2 * D) + lane);
+  const float2 qv = make_float2(qr.x * cs.x - qr.y * cs.y, qr.y * cs.x + qr.x * cs.y);
+  const float2 k_new = make_float2(kr.x * cs.x - kr.y * cs.y, kr.y * cs.x + kr.x * cs.y);
+  *(reinterpret_cast<float2*>(kc + cb * HEAD_DIM) + lane) = k_new;
+  *(reinterpret_cast<float2*>(vc + cb * HEAD_DIM) + lane) = v_new;
   float sc[AR_CODEBOOKS];
   float mx = -INFINITY;
 #pragma unroll
   for (int key = 0; key < AR_CODEBOOKS; ++key) {
     float v = -INFINITY;
     if (key <= cb) {
-      const float2 kv = __ldcg(reinterpret_cast<const float2*>(kc + key * HEAD_DIM) + lane);
+      const float2 kv = key == cb ? k_new : __ldcg(reinterpret_cast<const float2*>(kc + key * HEAD_DIM) + lane);
       v = warp_sum(qv.x * kv.x + qv.y * kv.y) * 0.125f;
     }
     sc[key] = v;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(128) arb_attn_fast_kernel(const ArBatchSlot* _
   for (int key = 0; key < AR_CODEBOOKS; ++key) {
     if (key <= cb) {
       const float p = expf(sc[key] - mx);
-      const float2 vv = __ldcg(reinterpret_cast<const float2*>(vc + key * HEAD_DIM) + lane);
+      const float2 vv = key == cb ? v_new : __ldcg(reinterpret_cast<const float2*>(vc + key * HEAD_DIM) + lane);
       l += p; ax += p * vv.x; ay += p * vv.y;
     }
   }
@@ -252,21 +254,24 @@ void Engine::ar_decode_step_gemm(Stream* const* streams, int batch, cudaStream_t
     launch_rmsnorm(xr, arb.nrm, w.attn_norm, M, AR_DIM, AR_NORM_EPS, st);
     gemm(arb.nrm, AR_DIM, w.wqkv, arb.qkv, 3 * AR_DIM, nullptr, M, 3 * AR_DIM, AR_DIM, st);
     if (fast) {
-      launch_pdl(arb_rope_append_kernel<true>, dim3(M), dim3(384), 0, st, sd, arb.qkv, ar.fast_rope, li, cb, max_seq);
-      SV_LAUNCHED();
-      launch_pdl(arb_attn_fast_kernel, dim3((B * AR_HEADS + 3) / 4), dim3(128), 0, st, sd, (const float*)arb.qkv, arb.y, li, cb,
-                 B * AR_HEADS);
-      SV_LAUNCHED();
+      launch_pdl(arb_attn_fast_kernel, dim3((B * AR_HEADS + 3) / 4), dim3(128), 0, st, sd, (const float*)arb.qkv, arb.y,
+                 ar.fast_rope, li, cb, B * AR_HEADS);
     } else {
-      launch_pdl(arb_rope_append_kernel<false>, dim3(M), dim3(384), 0, st, sd, arb.qkv, ar.rope, li, 0, max_seq);
-      SV_LAUNCHED();
-      launch_pdl(arb_attn_slow_kernel, dim3(AR_HEADS, B), dim3(ATT_WARPS * 32), 0, st, sd, (const float*)arb.qkv, arb.y, li, max_seq);
-      SV_LAUNCHED();
+      launch_pdl(arb_attn_slow_kernel, dim3(AR_HEADS, B), dim3(ATT_WARPS * 32), 0, st, sd, (const float*)arb.qkv, arb.y,
+                 ar.rope, li, max_seq);
     }
+    SV_LAUNCHED();
     gemm(arb.y, AR_DIM, w.wo, xr, AR_DIM, xr, M, AR_DIM, AR_DIM, st);
     launch_rmsnorm(xr, arb.nrm, w.ffn_norm, M, AR_DIM, AR_NORM_EPS, st);
-    gemm(arb.nrm, AR_DIM, w.w1, arb.h13, 2 * AR_INTER, nullptr, M, AR_INTER, AR_DIM, st);
-    gemm(arb.nrm, AR_DIM, w.w3, arb.h13 + AR_INTER, 2 * AR_INTER, nullptr, M, AR_INTER, AR_DIM, st);
+    {
+      GemmParams p13[2];                     // w1 and w3 side by side in one launch
+      for (int i = 0; i < 2; ++i) {
+        GemmParams& p = p13[i];
+        p.A = arb.nrm; p.W = i ? w.w3 : w.w1; p.C = arb.h13 + i * AR_INTER; p.M = M; p.N = AR_INTER; p.K = AR_DIM;
+        p.lda = AR_DIM; p.ldc = 2 * AR_INTER;
+      }
+      launch_gemm(p13, 2, st);
+    }
     launch_silu_mul(arb.h13, arb.g, M, AR_INTER, st);
     gemm(arb.g, AR_INTER, w.w2, xr, AR_DIM, xr, M, AR_DIM, AR_INTER, st);
   };

@@ -18,6 +18,7 @@ struct svanon_batch {
   long long* codes_win = nullptr;                         // [n][8][chunk]
   long long* step_ids = nullptr;                          // [chunk][n] content ids of this chunk, step-major
   VocState voc;
+  EncWindowState enc_state;
   struct SlotPtrs {                                       // static per-stream pointers (device table)
     long long* src_hist;
     int* pred_hist;
@@ -174,6 +175,7 @@ int svanon_batch_setup(svanon_batch* b, int enc_win, int dec_win, int max_seq_fr
     b->ptrs_dev = dmalloc<SlotPtrs>(n);
     SV_CUDA(cudaMemcpy(b->ptrs_dev, ptrs.data(), (size_t)n * sizeof(SlotPtrs), cudaMemcpyHostToDevice));
     b->n_src = 0; b->n_pred = 0; b->voc_fed = 0; b->delay_prefilled = false;
+    b->enc_state.valid = false;
     e.voc_state_init(b->voc, chunk, n);
   });
 }
@@ -205,7 +207,8 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     // 2. E: all windows side by side, keep the last `chunk` ids of each (:505-518)
     b->ev_valid = false;
     if (b->timing) SV_CUDA(cudaEventRecord(b->ev[0], st));
-    e.enc_encode(b->wave_ring, n, (long long)nw, b->ids_win, st);
+    if (b->enc_state.enabled) e.enc_window_step(b->enc_state, b->wave_ring, n, b->enc_win, c, b->ids_win, st);
+    else e.enc_encode(b->wave_ring, n, (long long)nw, b->ids_win, st);
     if (b->timing) SV_CUDA(cudaEventRecord(b->ev[1], st));
     if (b->n_src + c > HIST_CAP) {
       const int keep = HIST_CAP / 2;
@@ -294,6 +297,14 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     if (b->timing) { SV_CUDA(cudaEventRecord(b->ev[4], st)); b->ev_valid = true; }
     b->voc_fed += c;
     a.finish();
+  });
+}
+
+int svanon_batch_set_encoder_mode(svanon_batch* b, int incremental) {
+  return guarded([&] {
+    SV_CHECK(b, "null batch");
+    b->enc_state.enabled = incremental != 0;
+    b->enc_state.valid = false;
   });
 }
 

@@ -414,19 +414,17 @@ void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float
 }
 
 // ------------------------------------------------------------------------------------------ stage E
-// FireflyArchitecture.encode (firefly_encoder.py:553-566) for B full-length utterances / windows of the same length,
-// side by side: wave [B][n] -> ids [B][n/2048].  Streams never mix: every causal conv reads its own stream's zero
-// margin, attention is per stream; the GEMMs simply see B times more rows.
-void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_dev, cudaStream_t st) {
-  SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
-  SV_CHECK(B >= 1, "no utterances");
+// FireflyArchitecture.encode (firefly_encoder.py:553-566) in two halves.
+//
+// enc_conv_stack: everything up to the transformer input -- log-mel, ConvNeXtEncoder, the two down-sampling blocks --
+// for NS same-length wave segments side by side (segment i = rows of src[i / per_src] with pitch[i / per_src]): wave
+// -> xt [NS][n/2048][512].  Streams never mix: every causal conv reads its own segment's zero margin; the GEMMs simply
+// see NS times more rows.  Workspace comes from `ws` (caller has sized and reset it).
+void Engine::enc_conv_stack(const float* const* src, const long long* pitch, int nsrc, int per_src, long long n, float* xt,
+                            cudaStream_t st) {
+  const int B = nsrc * per_src;
   const int T = (int)(n / HOP);
   const int T2 = T / 2, S = T2 / 2;
-  SV_CHECK(S >= 1, "utterance shorter than one content frame (2048 samples)");
-  SV_CHECK(S <= 2048, "utterance longer than the tokenizer's RoPE table (2048 content frames)");
-  SV_CHECK((long long)B * T < (1 << 30), "batch too large");
-  ws.ensure((((size_t)T * 14000 + (size_t)n) * B + (4u << 20)) * sizeof(float));
-  ws.reset();
   const int MARG = 6;
   const int BT = B * T;
   const int segT = B > 1 ? T : 0;          // seg_rows of the T-row buffers (0 = plain single stream)
@@ -434,8 +432,9 @@ void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_de
   const long long wseg = N_FFT - HOP + n;
   float* wpad = ws.alloc_f(wseg * B);
   launch_fill(wpad, N_FFT - HOP, 0.f, st, B, wseg);
-  SV_CUDA(cudaMemcpy2DAsync(wpad + (N_FFT - HOP), (size_t)wseg * sizeof(float), wave, (size_t)n * sizeof(float),
-                            (size_t)n * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < nsrc; ++i)
+    SV_CUDA(cudaMemcpy2DAsync(wpad + (long long)i * per_src * wseg + (N_FFT - HOP), (size_t)wseg * sizeof(float), src[i],
+                              (size_t)pitch[i] * sizeof(float), (size_t)n * sizeof(float), per_src, cudaMemcpyDeviceToDevice, st));
   const int SPEC_LD = 2052;
   float* spec = ws.alloc_f((long long)BT * SPEC_LD);
   {
@@ -496,7 +495,6 @@ void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_de
   float* cur = feat;
   long long cur_seg = (long long)T * 512;
   int rows = T;
-  float* xt = ws.alloc_f((long long)B * S * ENC_DIM);       // transformer residual stream, plain [B*S][512]
   for (int i = 0; i < 2; ++i) {
     const int r2 = rows / 2;
     const long long ds = (long long)(MARG + r2) * 512;
@@ -508,13 +506,18 @@ void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_de
     p.a_row_step = 2; p.ldc = 512;
     p.seg_rows = B > 1 ? r2 : 0; p.a_seg = cur_seg; p.c_seg = ds;
     launch_gemm(p, st);
-    // the second block writes its result straight into the plain transformer buffer
+    // the second block writes its result straight into the plain output buffer
     convnext(down_block[i], dn, B * r2, tmp, hid, st, i == 1 ? xt : nullptr, B > 1 ? r2 : 0, ds, (long long)r2 * 512);
     cur = dn;
     cur_seg = ds;
     rows = r2;
   }
-  // 5. WindowLimitedTransformer (windowed_transformer.py:337-354), positions 0..S-1 in every stream
+  (void)S;
+}
+
+// enc_transformer_bsq: WindowLimitedTransformer (windowed_transformer.py:337-354) over S tokens per stream, positions
+// 0..S-1 in every stream, in place on xt [B][S][512]; then the 13-bit BSQ ids (bsq.py:330-369).
+void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st) {
   const int BS = B * S;
   float* nrm = ws.alloc_f((long long)BS * ENC_DIM);
   float* qkv = ws.alloc_f((long long)BS * 3 * ENC_DIM);
@@ -537,9 +540,9 @@ void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_de
     launch_rmsnorm(xt, nrm, L.ffn_norm, BS, ENC_DIM, 1e-5f, st);
     GemmParams p1;
     p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = BS; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM; p1.ldc = 2 * ENC_INTER;
-    launch_gemm(p1, st);
-    p1.W = L.w3; p1.C = h13 + ENC_INTER;
-    launch_gemm(p1, st);
+    GemmParams p13[2] = {p1, p1};            // w1 and w3 side by side in one launch
+    p13[1].W = L.w3; p13[1].C = h13 + ENC_INTER;
+    launch_gemm(p13, 2, st);
     launch_silu_mul(h13, gbuf, BS, ENC_INTER, st);
     GemmParams p2;
     p2.A = gbuf; p2.W = L.w2; p2.C = xt; p2.gamma = L.ls_ffn; p2.residual = xt; p2.M = BS; p2.N = ENC_DIM; p2.K = ENC_INTER;
@@ -547,8 +550,89 @@ void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_de
     launch_gemm(p2, st);
   }
   launch_rmsnorm(xt, nrm, enc_norm_w, BS, ENC_DIM, 1e-5f, st);
-  // 6. BSQ ids (bsq.py:330-369)
   launch_bsq(nrm, bsq_w, bsq_b, ids_dev, BS, st);
+}
+
+static size_t enc_ws_floats(int B, long long n) { return ((size_t)(n / HOP) * 14000 + (size_t)n) * B; }
+
+// B full-length utterances / windows of the same length, side by side: wave [B][n] -> ids [B][n/2048].
+void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_dev, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
+  SV_CHECK(B >= 1, "no utterances");
+  const int S = (int)(n / HOP) / 4;
+  SV_CHECK(S >= 1, "utterance shorter than one content frame (2048 samples)");
+  SV_CHECK(S <= 2048, "utterance longer than the tokenizer's RoPE table (2048 content frames)");
+  SV_CHECK((long long)B * (n / HOP) < (1 << 30), "batch too large");
+  ws.ensure((enc_ws_floats(B, n) + (4u << 20)) * sizeof(float));
+  ws.reset();
+  float* xt = ws.alloc_f((long long)B * S * ENC_DIM);
+  enc_conv_stack(&wave, &n, 1, B, n, xt, st);
+  enc_transformer_bsq(xt, B, S, ids_dev, st);
+}
+
+namespace {
+// xt_new[b][p] = p < rf ? head[b][p] : p < S - c ? prev[b][p + c] : tail[b][Ls - (S - p)]
+__global__ void enc_assemble_kernel(const float* __restrict__ spans, const float* __restrict__ prev, float* __restrict__ out,
+                                    int B, int S, int Ls, int rf, int c) {
+  pdl_trigger();
+  pdl_wait();
+  const int p = blockIdx.x, b = blockIdx.y;
+  const float* src;
+  if (p < rf) src = spans + ((long long)b * Ls + p) * ENC_DIM;
+  else if (p < S - c) src = prev + ((long long)b * S + p + c) * ENC_DIM;
+  else src = spans + ((long long)(B + b) * Ls + (Ls - (S - p))) * ENC_DIM;
+  float* dst = out + ((long long)b * S + p) * ENC_DIM;
+  for (int i = threadIdx.x; i < ENC_DIM / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+}
+}  // namespace
+
+// The streaming loop's window re-encode (infer_arvc.py:495-508) with persistent ring-buffer state, same result.
+// Every conv of the tokenizer is left-pad-only causal and the receptive field of one transformer-input token is 39
+// content frames (stem 6 + 18 x 6 + STFT 3 + down-sampling 39 mel steps), so when the window
+// slides by c frames the transformer inputs of window positions >= 39 are the SAME function of the SAME samples as
+// one chunk earlier at position + c.  Only two spans go through the conv stack again: the window's first ENC_RF + c
+// frames (their tokens see the zero padding at the window start, exactly like in the reference's recompute) and its
+// last ENC_RF + c frames (whose last c tokens are the new ones); the tokens in between come from the per-stream
+// state.  The attention transformer then runs over all S tokens as in the reference (its inputs at every position
+// change with the window start, nothing of it can be kept).  state->xt [B][S][512] double-buffered.
+void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,
+                             cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
+  const long long nw = (long long)S * SAMPLES_PER_FRAME;
+  const int Ls = ENC_RF + c;
+  const bool incremental = state.valid && state.B == B && state.S == S && S >= 2 * Ls + 8;
+  if (state.B != B || state.S != S || !state.xt[0]) {
+    for (auto& p : state.xt) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      SV_CUDA(cudaMalloc(&p, (size_t)B * S * ENC_DIM * sizeof(float)));
+    }
+    state.B = B; state.S = S; state.cur = 0; state.valid = false;
+  }
+  float* xt_state = state.xt[state.cur ^ 1];
+  if (!incremental) {
+    ws.ensure((enc_ws_floats(B, nw) + (size_t)B * S * ENC_DIM + (4u << 20)) * sizeof(float));
+    ws.reset();
+    enc_conv_stack(&wave_ring, &nw, 1, B, nw, xt_state, st);
+  } else {
+    const long long ns = (long long)Ls * SAMPLES_PER_FRAME;
+    ws.ensure((enc_ws_floats(2 * B, ns) + enc_ws_floats(B, nw) / 3 + (size_t)(2 * B * Ls + B * S) * ENC_DIM + (4u << 20)) *
+              sizeof(float));
+    ws.reset();
+    float* spans = ws.alloc_f((long long)2 * B * Ls * ENC_DIM);
+    const float* src[2] = {wave_ring, wave_ring + (nw - ns)};
+    const long long pitch[2] = {nw, nw};
+    enc_conv_stack(src, pitch, 2, B, ns, spans, st);
+    launch_pdl(enc_assemble_kernel, dim3(S, B), dim3(128), 0, st, (const float*)spans, (const float*)state.xt[state.cur],
+               xt_state, B, S, Ls, ENC_RF, c);
+    SV_LAUNCHED();
+  }
+  state.cur ^= 1;
+  state.valid = true;
+  float* xt = ws.alloc_f((long long)B * S * ENC_DIM);
+  SV_CUDA(cudaMemcpyAsync(xt, xt_state, (size_t)B * S * ENC_DIM * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  enc_transformer_bsq(xt, B, S, ids_dev, st);
 }
 
 // ------------------------------------------------------------------------------------------ stage V
@@ -717,9 +801,9 @@ void Engine::ar_forward_tokens(Stream& s, float* x, int M, int pos0, cudaStream_
     launch_rmsnorm(x, nrm, L.ffn_norm, M, AR_DIM, AR_NORM_EPS, st);
     GemmParams p1;
     p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = M; p1.N = AR_INTER; p1.K = AR_DIM; p1.lda = AR_DIM; p1.ldc = 2 * AR_INTER;
-    launch_gemm(p1, st);
-    p1.W = L.w3; p1.C = h13 + AR_INTER;
-    launch_gemm(p1, st);
+    GemmParams p13[2] = {p1, p1};            // w1 and w3 side by side in one launch
+    p13[1].W = L.w3; p13[1].C = h13 + AR_INTER;
+    launch_gemm(p13, 2, st);
     launch_silu_mul(h13, gbuf, M, AR_INTER, st);
     GemmParams p2;
     p2.A = gbuf; p2.W = L.w2; p2.C = x; p2.residual = x; p2.M = M; p2.N = AR_DIM; p2.K = AR_INTER; p2.lda = AR_INTER;

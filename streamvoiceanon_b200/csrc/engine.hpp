@@ -117,6 +117,23 @@ struct ArBatchWork {
   ~ArBatchWork();
 };
 
+// Receptive field, in content frames, of one transformer-input token of the tokenizer's conv stack (39, SURVEY.md
+// section 8a-E) plus one frame of slack.
+constexpr int ENC_RF = 40;
+
+// Ring-buffer state of the streaming window encoder (Engine::enc_window_step): the transformer inputs of the last
+// window, for B streams side by side.
+struct EncWindowState {
+  float* xt[2] = {nullptr, nullptr};   // [B][S][512], double-buffered
+  int cur = 0, B = 0, S = 0;
+  bool valid = false;
+  bool enabled = true;
+  ~EncWindowState() {
+    for (auto p : xt)
+      if (p) cudaFree(p);
+  }
+};
+
 constexpr int HIST_CAP = 4096;     // columns kept of src_content_codes / pred_codes (the reference trims to 2048)
 
 struct Stream {
@@ -155,6 +172,7 @@ struct Stream {
   long long* ids_win_dev = nullptr;       // [enc_win]
   long long* codes_win_dev = nullptr;     // [8][dec_win]
   float* wave_win_dev = nullptr;          // [dec_win*2048]
+  EncWindowState enc_state;               // conv-stack outputs of the last window (Engine::enc_window_step)
   VocState voc;                           // incremental vocoder state (used when dec_win >= 16)
   int voc_mode = 1;                       // 1: incremental when possible, 0: always recompute the window
   bool voc_incremental = false;
@@ -223,6 +241,12 @@ struct Engine {
   // stage drivers (all device pointers, stream-ordered, no host sync)
   int enc_num_ids(long long n_samples) const { return (int)(((n_samples / HOP) / 2) / 2); }
   void enc_encode(const float* wave_dev /*[B][n]*/, int B, long long n_samples, long long* ids_dev /*[B][S]*/, cudaStream_t st);
+  void enc_conv_stack(const float* const* src, const long long* pitch, int nsrc, int per_src, long long n, float* xt,
+                      cudaStream_t st);
+  void enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st);
+  // the window re-encode of the streaming loop with the conv-stack outputs kept between chunks (wave_ring [B][S*2048])
+  void enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,
+                       cudaStream_t st);
   void voc_quantizer_decode(const long long* codes_dev, long long ld, int T, float* z_dev /*[4T][512]*/, cudaStream_t st);
   void voc_head(const float* z_dev /*[L][512]*/, int L, float* wave_dev /*[512 L]*/, cudaStream_t st);
   void voc_decode(const long long* codes_dev, long long ld, int T, float* wave_dev, cudaStream_t st);

@@ -91,6 +91,11 @@ class StreamSession:
         """True (default): incremental vocoder; False: recompute the decode window every chunk like the reference."""
         _lib.check(self._engine.lib.svanon_stream_set_vocoder_mode(self._h, int(incremental)))
 
+    def set_encoder_mode(self, incremental: bool = True):
+        """True (default): keep the conv-stack outputs of the window between chunks (ring-buffer state); False:
+        re-encode the whole window every chunk like the reference.  Same result."""
+        _lib.check(self._engine.lib.svanon_stream_set_encoder_mode(self._h, int(incremental)))
+
     def set_timing(self, enable: bool = True):
         _lib.check(self._engine.lib.svanon_stream_set_timing(self._h, int(enable)))
 
@@ -170,6 +175,9 @@ class BatchSession:
                                                                ptr(noise) if noise is not None else None, ptr(out),
                                                                C.c_void_p(_cuda_stream_ptr())))
         return out
+
+    def set_encoder_mode(self, incremental: bool = True):
+        _lib.check(self._engine.lib.svanon_batch_set_encoder_mode(self._h, int(incremental)))
 
     def set_timing(self, enable: bool = True):
         _lib.check(self._engine.lib.svanon_batch_set_timing(self._h, int(enable)))

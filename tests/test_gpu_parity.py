@@ -315,3 +315,67 @@ def test_stream_loop_vs_reference(models, weights, gold, tape, name, host_io, in
     assert np.array_equal(pred_hist.numpy()[None], g["pred_codes"])
     mse = float(((wave.numpy() - g["wave"]) ** 2).mean())
     assert mse < WAVE_MSE_TOL, mse
+
+
+def test_stream_loop_chunk2_truncated_prompt_vs_oracle(models, weights, tape):
+    """BASELINE config 5 shape: decode_chunk_frames=2, delay=2, a prompt longer than max_prompt_frames (the
+    reference prefills the UNtruncated prompt but pads / re-prompts with the truncated copy, infer_arvc.py:469-489),
+    re-prompt firing.  Content ids and codec ids bit-exact vs the CPU oracle, waveform within the fp32 tolerance."""
+    from oracle import content_encoder as E
+    from oracle.streaming import StreamOracle
+    from streamvoiceanon_b200 import StreamSession
+    _, tok, _ = models
+    n_ref, n_chunks, chunk, max_prompt = 40, 9, 2, 30
+    cfg = dict(encode_window_frames=24, decode_window_frames=24, max_seq_frames=66, buffer_frames=6,
+               decode_chunk_frames=chunk)
+    style, timbre = synth.synth_speaker(5200)
+    ref_wave = synth.synth_audio_44k(5200, 3.0)[: n_ref * 2048][None]
+    gen = torch.Generator().manual_seed(321)
+    ref_audio = torch.randint(0, 1000, (1, 8, n_ref), generator=gen).int()
+    src = synth.synth_audio_44k(1200, 1.5)[: n_chunks * chunk * 2048].view(n_chunks, chunk * 2048)
+    ref_content, _ = tok.encode(ref_wave.cuda(), torch.LongTensor([ref_wave.shape[1]]).cuda())
+    sess = StreamSession()
+    sess.set_noise_fn(tape(7500), 0)
+    sess.set_prompt(ref_content[0].cuda(), ref_audio.cuda(), style.cuda(), timbre.cuda(), max_prompt_frames=max_prompt, delay=2)
+    sess.setup(**cfg)
+    waves = torch.cat([sess.process_chunk(src[i].cuda()).cpu() for i in range(n_chunks)])
+    src_hist, pred_hist = sess.history()
+    sess.close()
+    so = StreamOracle(weights["ar"], weights["tok"], weights["voc_folded"], tape(7500))
+    with torch.no_grad():
+        rc = E.encode(ref_wave, weights["tok"])[0].squeeze(0)
+        so.prefill_prompt(ref_audio, rc, style, timbre, max_prompt, 2)
+        so.setup_stream_caches(**cfg)
+        want = torch.cat([so.process_one_chunk(src[i][None]) for i in range(n_chunks)], dim=-1)[0]
+    assert np.array_equal(src_hist.numpy(), so.src_content_codes[0].numpy())
+    assert np.array_equal(pred_hist.numpy(), so.pred_codes[0].numpy())
+    assert float(((waves - want) ** 2).mean()) < WAVE_MSE_TOL
+
+
+def test_ring_buffer_encoder_equals_window_recompute(models, weights, gold, tape):
+    """E with persistent ring-buffer state (conv-stack outputs kept between chunks, only the window's first and last
+    40 + chunk frames re-encoded) against the reference-style full re-encode of the 128-frame window in the same loop:
+    identical content ids (and therefore codec ids) over 20 chunks; both modes are also held to the reference
+    fixture by test_stream_loop_vs_reference."""
+    from streamvoiceanon_b200 import StreamSession
+    _, tok, _ = models
+    g = gold("stream_default")
+    n_ref = int(g["n_ref"])
+    style, timbre = synth.synth_speaker(int(g["ref_seed"]))
+    gen = torch.Generator().manual_seed(int(g["codes_seed"]))
+    ref_audio = torch.randint(0, 1000, (1, 8, n_ref), generator=gen).int()
+    ref_content = torch.from_numpy(g["ref_content"])
+    src = synth.synth_audio_44k(1300, 2.0)[: 20 * 2048].view(20, 2048)
+    out = []
+    for incremental in (True, False):
+        sess = StreamSession()
+        sess.set_noise_fn(tape(7600), 0)
+        sess.set_prompt(ref_content[0].cuda(), ref_audio.cuda(), style.cuda(), timbre.cuda(), 256, 2)
+        sess.setup(128, 64, 768, 32, 1)
+        sess.set_encoder_mode(incremental)
+        waves = torch.cat([sess.process_chunk(src[i].cuda()).cpu() for i in range(20)])
+        out.append((*sess.history(), waves))
+        sess.close()
+    assert torch.equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1])
+    assert float(((out[0][2] - out[1][2]) ** 2).mean()) < 1e-10
