@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   pdl_trigger();
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -182,79 +182,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================================================== producers
-    // fixed per-thread chunk assignment: chunk i = tid + j*512 -> row = i>>3, c = i&7
-    const float* a_base[A_PER];
-    int a_off[A_PER];
-    bool a_ok[A_PER];
+    // fixed per-thread chunk assignment: chunk i = tid + j*512 -> row = i>>3, c = i&7.  All loop state is advanced
+    // incrementally (no division, 32-bit shared-memory addresses): the loop is issue-bound, every instruction counts.
+    const float* a_ptr[A_PER];           // row base + this thread's chunk; null: row past M
+    unsigned a_soff[A_PER];
 #pragma unroll
     for (int j = 0; j < A_PER; ++j) {
       const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
       const int m = m0 + row;
-      a_ok[j] = m < p.M;
-      a_base[j] = p.A + gemm_a_row(p, a_ok[j] ? m : 0) + c * 4;
-      a_off[j] = swz(row, c);
+      a_ptr[j] = (m < p.M) ? p.A + gemm_a_row(p, m) + c * 4 : nullptr;
+      a_soff[j] = (unsigned)swz(row, c) * 4u;
     }
-    const float* b_base[B_PER];
-    int b_off[B_PER];
-    bool b_ok[B_PER];
+    const float* b_ptr[B_PER];
+    unsigned b_soff[B_PER];
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
       const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
       const int n = n0 + row;
-      b_ok[j] = n < p.N;
-      b_base[j] = p.W + (long long)(b_ok[j] ? n : 0) * p.K + c * 4;
-      b_off[j] = swz(row, c);
+      b_ptr[j] = (n < p.N) ? p.W + (long long)n * p.K + c * 4 : nullptr;
+      b_soff[j] = (unsigned)swz(row, c) * 4u;
     }
     const int c4 = (tid & 7) * 4;                      // K offset of this thread's chunks inside a slab
     const bool silu = p.prologue == PRO_SILU;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long tap_stride = (long long)p.N * p.K;
+    // load cursor: tap ld_t, K offset ld_k of the next slab to request
+    int ld_t = it_begin / kSlabs;
+    int ld_k = (it_begin - ld_t * kSlabs) * TK;
+    long long ld_a = (long long)p.tap_off[ld_t] * p.lda, ld_b = (long long)ld_t * tap_stride;
     float4 ra[D][A_PER], rb[D][B_PER];
-    auto load_b = [&](int li, float4 (&dst)[B_PER]) {
-      const int it = it_begin + li;
-      const int t = it / kSlabs;
-      const int k0 = (it - t * kSlabs) * TK;
-      const bool k_ok = (k0 + c4) < p.K;
-      const long long b_shift = (long long)t * p.N * p.K + k0;
+    auto load_b = [&](float4 (&dst)[B_PER]) {
+      const bool k_ok = (ld_k + c4) < p.K;
 #pragma unroll
-      for (int j = 0; j < B_PER; ++j) dst[j] = (b_ok[j] && k_ok) ? ldg_nc(b_base[j] + b_shift) : zero4;
+      for (int j = 0; j < B_PER; ++j) dst[j] = (b_ptr[j] && k_ok) ? ldg_nc(b_ptr[j] + ld_b + ld_k) : zero4;
     };
-    auto load_a = [&](int li, float4 (&dst)[A_PER]) {
-      const int it = it_begin + li;
-      const int t = it / kSlabs;
-      const int k0 = (it - t * kSlabs) * TK;
-      const bool k_ok = (k0 + c4) < p.K;
-      const long long a_shift = (long long)p.tap_off[t] * p.lda + k0;
+    auto load_a = [&](float4 (&dst)[A_PER]) {
+      const bool k_ok = (ld_k + c4) < p.K;
 #pragma unroll
-      for (int j = 0; j < A_PER; ++j) dst[j] = (a_ok[j] && k_ok) ? ldg_nc(a_base[j] + a_shift) : zero4;
+      for (int j = 0; j < A_PER; ++j) dst[j] = (a_ptr[j] && k_ok) ? ldg_nc(a_ptr[j] + ld_a + ld_k) : zero4;
     };
-    // weights do not depend on the previous kernel: request them before waiting for it
+    auto advance = [&] {
+      ld_k += TK;
+      if (ld_k >= kSlabs * TK) {
+        ld_k = 0;
+        ++ld_t;
+        ld_a = (long long)p.tap_off[ld_t < p.taps ? ld_t : 0] * p.lda;
+        ld_b += tap_stride;
+      }
+    };
+    // Weights do not depend on the previous kernel: request them before waiting for it.  The cursor is replayed for
+    // the activation loads of the same slabs afterwards.
+    {
+      const int t0 = ld_t, k0 = ld_k;
+      const long long a0 = ld_a, b0 = ld_b;
 #pragma unroll
-    for (int d = 0; d < D; ++d)
-      if (d < n_it) load_b(d, rb[d]);
-    pdl_wait();
+      for (int d = 0; d < D; ++d)
+        if (d < n_it) { load_b(rb[d]); advance(); }
+      pdl_wait();
+      ld_t = t0; ld_k = k0; ld_a = a0; ld_b = b0;
 #pragma unroll
-    for (int d = 0; d < D; ++d)
-      if (d < n_it) load_a(d, ra[d]);
+      for (int d = 0; d < D; ++d)
+        if (d < n_it) { load_a(ra[d]); advance(); }
+    }
+    const unsigned smem_base = smem_u32(smem);
+    const unsigned full_base = smem_u32(&full_bar[0]), empty_base = smem_u32(&empty_bar[0]);
+    unsigned st_stage = 0, st_parity = 1;              // parity to wait for on empty[stage]
+    auto sts4 = [](unsigned addr, float4 v) {
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    };
+    auto split_sts = [&](unsigned hi_addr, unsigned lo_delta, float4 v) {
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+      sts4(hi_addr, h);
+      sts4(hi_addr + lo_delta, l);
+    };
     for (int li0 = 0; li0 < n_it; li0 += D) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const int li = li0 + d;
         if (li < n_it) {
-          const int stage = li % STAGES;
-          mbar_wait(&empty_bar[stage], ((li / STAGES) & 1) ^ 1);           // MMAs that read this stage are done
-          float* As = smem + stage * STAGE_FLOATS;
-          float* Bs = As + 2 * A_FLOATS;
+          // MMAs that read this stage are done.  One lane per warp polls / arrives: 512 threads hammering one
+          // mbarrier word serialise in the shared-memory pipe that the tile stores need.
+          if (lane == 0) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "TC_PW_LOOP:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra.uni TC_PW_DONE;\n"
+                "bra.uni TC_PW_LOOP;\n"
+                "TC_PW_DONE:\n"
+                "}\n" ::"r"(empty_base + st_stage * 8u), "r"(st_parity) : "memory");
+          }
+          __syncwarp();
+          const unsigned a_stage = smem_base + st_stage * (unsigned)(STAGE_FLOATS * 4);
+          const unsigned b_stage = a_stage + 2u * A_FLOATS * 4u;
 #pragma unroll
           for (int j = 0; j < A_PER; ++j) {
             float4 v = ra[d][j];
             if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-            split_store(As + a_off[j], As + A_FLOATS + a_off[j], v);
+            split_sts(a_stage + a_soff[j], A_FLOATS * 4u, v);
           }
 #pragma unroll
-          for (int j = 0; j < B_PER; ++j) split_store(Bs + b_off[j], Bs + B_FLOATS + b_off[j], rb[d][j]);
+          for (int j = 0; j < B_PER; ++j) split_sts(b_stage + b_soff[j], B_FLOATS * 4u, rb[d][j]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the MMA
-          mbar_arrive(&full_bar[stage]);
-          if (li + D < n_it) { load_b(li + D, rb[d]); load_a(li + D, ra[d]); }
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_base + st_stage * 8u) : "memory");
+          if (++st_stage == STAGES) { st_stage = 0; st_parity ^= 1u; }
+          if (li + D < n_it) { load_b(rb[d]); load_a(ra[d]); advance(); }
         }
       }
     }
@@ -291,7 +329,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   const int quad = warp & 3, grp = warp >> 2;
   cg::cluster_group cluster = cg::this_cluster();
   if (warp < TC_PRODUCER_WARPS) {
-    if (n_it > 0) mbar_wait(&acc_bar, 0);
+    if (n_it > 0 && lane == 0) mbar_wait(&acc_bar, 0);
+    __syncwarp();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   auto finish = [&](float (&v)[16], int m, int col0) {      // bias/act/gamma/residual/scale + store of 16 columns
