@@ -120,6 +120,10 @@ int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const fl
  * words instead of barriers (experimental: correct, but measured slower -- polling congestion, profiles/README.md);
  * 0 = weights loaded straight from global memory + grid barriers (what batched launches use) */
 int svanon_ar_set_kernel_variant(svanon_engine* e, int variant);
+/* grid barrier between the phases of the persistent decode kernels: 0 (default) = a single arrival counter
+ * (`red.release` + acquire poll), 1 = one epoch word per CTA (release store to the CTA's own word, one warp polls all
+ * words; no atomics) -- correct, measured slower (1.31 vs 1.07 ms per frame, profiles/README.md) */
+int svanon_ar_set_barrier_mode(svanon_engine* e, int mode);
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits /*[8192]*/, float* hidden /*[768]*/,
                          float* fast_logits /*[8][1000]*/);
 

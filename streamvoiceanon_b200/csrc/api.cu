@@ -352,6 +352,16 @@ int svanon_ar_set_kernel_variant(svanon_engine* e, int variant) {
   });
 }
 
+int svanon_ar_set_barrier_mode(svanon_engine* e, int mode) {
+  return guarded([&] {
+    SV_CHECK(e, "null engine");
+    SV_CHECK(mode == 0 || mode == 1, "barrier mode: 0 arrival counter, 1 per-CTA epoch words");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    SV_CUDA(cudaDeviceSynchronize());
+    e->eng.ar_barrier_mode = mode;
+  });
+}
+
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits, float* hidden, float* fast_logits) {
   return guarded([&] {
     SV_CHECK(e && e->eng.finalized[MODEL_AR], "AR weights not finalized");

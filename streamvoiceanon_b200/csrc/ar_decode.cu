@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_kernel(const ArDecodeArgs a) 
   const int total_warps = NW * gridDim.x;
   const int gtid = blockIdx.x * NT + threadIdx.x;
 
-  grid_sync_init(a.barrier);
+  grid_sync_init(a.barrier, a.barrier_mode);
   // ---- phase 0: assemble the 2 input rows per stream: [cached_new_audio_emb, embedding[content_id]]
   for (int i = gtid; i < B * 2 * D; i += NT * gridDim.x) {
     const int b = i / (2 * D), j = (i / D) % 2, c = i % D;

@@ -50,7 +50,8 @@ struct ArDecodeArgs {
   float* g;                     // [2B][2304]
   float* part;                  // [B][12][nsplit][2][66]
   float* logits;                // [B][1024]
-  unsigned* barrier;            // [2], zero-initialised once
+  unsigned* barrier;            // [32 + grid]: counter, saved counter, saved epoch, ..., per-CTA epoch words; zeroed once
+  int barrier_mode;             // 0 arrival counter, 1 per-CTA epoch words (ar_decode_common.cuh)
   void* ll;                     // tagged-word scratch of the barrier-free variant (ar_decode_ll.cu), zero-initialised
   unsigned epoch;               // launch counter (>= 1) that makes this launch's tags unique
   float* dbg_slow_logits;       // [8192] or null

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   }
   __syncthreads();
   if (threadIdx.x == 0) issue(a, sg, 0);
-  grid_sync_init(a.barrier);
+  grid_sync_init(a.barrier, a.barrier_mode);
 
   // ---- phase 0: the 2 input rows [cached_new_audio_emb, embedding[content_id]]
   for (int i = gtid; i < 2 * D; i += NT * gridDim.x) {

@@ -150,8 +150,8 @@ void Engine::finalize_ar() {
   SV_CUDA(cudaMalloc(&ar_g, (size_t)2 * B * AR_INTER * 4));
   SV_CUDA(cudaMalloc(&ar_part, (size_t)B * AR_HEADS * 16 * 2 * (2 + HEAD_DIM) * 4));
   SV_CUDA(cudaMalloc(&ar_logits, (size_t)B * 1024 * 4));
-  SV_CUDA(cudaMalloc(&ar_barrier, 2 * sizeof(unsigned)));
-  SV_CUDA(cudaMemset(ar_barrier, 0, 2 * sizeof(unsigned)));
+  SV_CUDA(cudaMalloc(&ar_barrier, 1024 * sizeof(unsigned)));
+  SV_CUDA(cudaMemset(ar_barrier, 0, 1024 * sizeof(unsigned)));
   SV_CUDA(cudaMalloc(&ar_ll, ar_decode_ll_scratch_words() * 8));
   SV_CUDA(cudaMemset(ar_ll, 0, ar_decode_ll_scratch_words() * 8));
   SV_CUDA(cudaMalloc(&dbg_slow_logits, AR_VOCAB * 4));
@@ -912,6 +912,7 @@ void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) 
   nsplit = std::min(nsplit, 16);
   nsplit = std::min(nsplit, std::max(1, max_keys / 16));
   a.nsplit = nsplit;
+  a.barrier_mode = ar_barrier_mode;
   if (debug_logits) { a.dbg_slow_logits = dbg_slow_logits; a.dbg_hidden = dbg_hidden; a.dbg_fast_logits = dbg_fast_logits; }
   else { a.dbg_slow_logits = nullptr; a.dbg_hidden = nullptr; a.dbg_fast_logits = nullptr; }
   if (batch == 1 && ar_variant == 2 && ar_decode_staged_supported(num_sms)) {

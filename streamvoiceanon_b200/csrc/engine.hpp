@@ -199,6 +199,7 @@ struct Engine {
   const float *w4s = nullptr, *w4e = nullptr;
   float *ar_x = nullptr, *ar_h = nullptr, *ar_q = nullptr, *ar_g = nullptr, *ar_part = nullptr, *ar_logits = nullptr;
   unsigned* ar_barrier = nullptr;
+  int ar_barrier_mode = 0;                     // grid barrier of the persistent decode kernels (ar_decode_common.cuh)
   float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
   bool debug_logits = false;
   int ar_variant = 1;                          // batch-1 decode kernel: 0 direct loads, 1 TMA-staged, 2 staged + flag-in-data (no grid barriers)
