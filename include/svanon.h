@@ -69,6 +69,14 @@ int svanon_voc_quantizer_decode(svanon_engine* e, const int64_t* codes, int T, f
 int svanon_voc_head(svanon_engine* e, const float* z, int L, float* wave_out, void* cuda_stream);
 int svanon_voc_decode(svanon_engine* e, const int64_t* codes, int T, float* wave_out, void* cuda_stream);
 
+/* prompt path: `wav2target_fn` (evaluations/infer_arvc.py:168-171) = FireflyArchitecture.encode of
+ * the vocoder (modules/vqgan/modules/firefly.py:561-574) + DownsampleFiniteScalarQuantize.encode (fsq.py:106-110):
+ * reference wave -> the 8 FSQ codec ids per frame that prefill_prompt consumes.  Needs the checkpoint's `backbone.*`,
+ * `quantizer.downsample.*` and `quantizer.residual_fsq.rvqs.*.project_in.*` tensors and "spec_transform.fb" (as for the
+ * tokenizer).  waves [n_utt][n_samples] full-length rows; codes_out [n_utt][8][n_samples / 2048] int32. */
+int svanon_voc_encode(svanon_engine* e, const float* waves, int n_utt, int64_t n_samples, int32_t* codes_out,
+                      void* cuda_stream);
+
 /* ---- stage A: dual-AR decode ------------------------------------------------------------------------------
  * A stream owns what the reference keeps inside one ARVCWrapper/DualARWrapper instance: the slow/fast KV
  * caches (`setup_caches`, infer_arvc.py:55-59, dual_ar_stream.py:225-243,459-475), cached positions,

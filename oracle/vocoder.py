@@ -89,3 +89,37 @@ def head(z, sd):
 def code2wav(codes, sd):
     """evaluations/infer_arvc.py:173-176.  codes [B,8,T] -> wave [B,1,2048 T]."""
     return head(quantizer_decode(codes, sd), sd)
+
+
+# ------------------------------------------------------------------------------------------ encode path (prompt)
+def fsq_encode(z, sd):
+    """GroupedResidualFSQ.forward -> indices for 8 groups x 1 quantizer (vector-quantize-pytorch==1.14.24, restated from
+    the reference's vendored twin modules/bicodec_speaker_encoder/fsq/finite_scalar_quantization.py:126-156 and
+    residual_fsq.py:160-230): per group project_in Linear 64->4, bound (tanh with the even-level half-step shift,
+    eps 1e-3), round half to even, digit = round + L//2, index = sum digit * basis.  z [B,T,512] -> int32 [B,8,T]."""
+    levels = LEVELS.to(torch.int32)
+    half_l = (levels - 1) * (1 + 1e-3) / 2
+    offset = torch.where(levels % 2 == 0, 0.5, 0.0)
+    shift = (offset / half_l).atanh()
+    half_width = levels // 2
+    out = []
+    for g in range(8):
+        x = F.linear(z[..., g * 64:(g + 1) * 64], sd[f"quantizer.residual_fsq.rvqs.{g}.project_in.weight"],
+                     sd[f"quantizer.residual_fsq.rvqs.{g}.project_in.bias"])
+        bounded = (x + shift).tanh() * half_l - offset
+        zhat = bounded.round() / half_width
+        digits = zhat * half_width + half_width
+        out.append((digits * BASIS.to(torch.int32)).sum(dim=-1).to(torch.int32))
+    return torch.stack(out, dim=1)
+
+
+def wav2codes(wav, sd):
+    """`wav2target_fn` (evaluations/infer_arvc.py:168-171) = FireflyArchitecture.encode (firefly.py:561-574) for
+    full-length rows: log-mel -> ConvNeXt backbone -> quantizer.downsample (2 x [causal conv k2 s2 + ConvNeXt]) -> FSQ
+    indices.  wav [B,L] -> int32 [B,8,L//2048]."""
+    from . import content_encoder as E
+    x = E.convnext_encoder(E.log_mel(wav), sd, "backbone")
+    for i in range(2):
+        x = causal_conv1d(x, sd[f"quantizer.downsample.{i}.0.conv.weight"], sd[f"quantizer.downsample.{i}.0.conv.bias"], stride=2)
+        x = convnext_block(x, sd, f"quantizer.downsample.{i}.1")
+    return fsq_encode(x.transpose(1, 2), sd)

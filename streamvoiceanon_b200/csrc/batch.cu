@@ -87,6 +87,18 @@ int svanon_enc_encode_batch(svanon_engine* e, const float* waves, int n_utt, int
   });
 }
 
+int svanon_voc_encode(svanon_engine* e, const float* waves, int n_utt, int64_t n_samples, int32_t* codes_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && waves && codes_out && n_utt >= 1, "bad arguments");
+    const size_t T = (size_t)(n_samples / SAMPLES_PER_FRAME);
+    Args a(e, stream, ((size_t)n_samples * 4 + T * 8 * 4) * n_utt + 65536);
+    const float* w = a.in(waves, (size_t)n_samples * n_utt);
+    int* codes = a.out(codes_out, T * 8 * n_utt);
+    e->eng.voc_encode(w, n_utt, n_samples, codes, a.st);
+    a.finish();
+  });
+}
+
 int svanon_ar_decode_many(svanon_stream* const* streams, int n, const int64_t* content_ids, const float* noise,
                           int32_t* codes_out, void* stream) {
   return guarded([&] {

@@ -178,6 +178,8 @@ void launch_bsq(const float* z /*[T][512]*/, const float* w /*[13][512]*/, const
 void launch_fsq_lookup(const long long* codes /*[8][T] (stride ld)*/, long long ld, const float* w /*[8][64][4]*/,
                        const float* b /*[8][64]*/, float* z /*[T][512]*/, int T, cudaStream_t st, int seg_rows = 0,
                        long long codes_seg = 0);
+void launch_fsq_encode(const float* z /*[B*T][512]*/, const float* w /*[8][4][64]*/, const float* b /*[8][4]*/,
+                       int* codes /*[B][8][T]*/, int B, int T, cudaStream_t st);
 void launch_conv_post(const float* x /*[L][16] with 12 margin rows*/, const float* w /*[13][16]*/, const float* b,
                       float* out, int L, cudaStream_t st, int seg_rows = 0, long long x_seg = 0);
 void launch_gather_rows(const float* table, const long long* idx, float* out, int rows, int C, long long out_ld,

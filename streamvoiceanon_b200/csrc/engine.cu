@@ -234,11 +234,10 @@ static ConvNextW pack_convnext(Engine& e, int model, const std::string& p, int C
 }
 
 // ------------------------------------------------------------------------------------------ tokenizer weights
-void Engine::finalize_tokenizer() {
-  const int M = MODEL_TOKENIZER;
-  auto g = [&](const std::string& n) { return get(M, n).data; };
-  // windowed DFT basis: rows 0..1024 real, 1025..2049 imaginary; torch.hann_window(2048) is periodic
-  {
+// windowed DFT basis (rows 0..1024 real, 1025..2049 imaginary; torch.hann_window(2048) is periodic) and the slaney mel
+// filterbank, shared by the two LogMelSpectrogram instances (identical parameters in both YAMLs)
+void Engine::build_spectrogram_consts(int M) {
+  if (!dft_w) {
     std::vector<float> dft((size_t)2 * N_FREQ * N_FFT);
     const double two_pi = 6.283185307179586476925286766559;
     std::vector<double> win(N_FFT);
@@ -252,7 +251,7 @@ void Engine::finalize_tokenizer() {
       }
     dft_w = upload(dft);
   }
-  {
+  if (!fb_t) {
     const Tensor& fb = get(M, "spec_transform.fb");
     expect_shape(fb, {N_FREQ, N_MELS}, "spec_transform.fb");
     auto h = to_host(fb);
@@ -261,35 +260,48 @@ void Engine::finalize_tokenizer() {
       for (int m = 0; m < N_MELS; ++m) t[(size_t)m * N_FREQ_PAD + f] = h[(size_t)f * N_MELS + m];
     fb_t = upload(t);
   }
+}
+
+// ConvNeXtEncoder (firefly.py:443-517) + quantizer.downsample of model M (same key names in both checkpoints)
+void Engine::pack_conv_stack(int M, ConvStackW& cs) {
+  auto g = [&](const std::string& n) { return get(M, n).data; };
   const int dims[4] = {128, 256, 384, 512};
   const int depths[4] = {3, 3, 9, 3};
   expect_shape(get(M, "backbone.downsample_layers.0.0.conv.weight"), {128, N_MELS, 7}, "stem");
-  stem_w = upload(pack_conv_rows(to_host(get(M, "backbone.downsample_layers.0.0.conv.weight")), 128, N_MELS, 7));
-  stem_b = g("backbone.downsample_layers.0.0.conv.bias");
-  stem_ln_w = g("backbone.downsample_layers.0.1.weight");
-  stem_ln_b = g("backbone.downsample_layers.0.1.bias");
+  cs.stem_w = upload(pack_conv_rows(to_host(get(M, "backbone.downsample_layers.0.0.conv.weight")), 128, N_MELS, 7));
+  cs.stem_b = g("backbone.downsample_layers.0.0.conv.bias");
+  cs.stem_ln_w = g("backbone.downsample_layers.0.1.weight");
+  cs.stem_ln_b = g("backbone.downsample_layers.0.1.bias");
   for (int i = 1; i < 4; ++i) {
     const std::string p = "backbone.downsample_layers." + std::to_string(i);
-    mid_ln_w[i - 1] = g(p + ".0.weight");
-    mid_ln_b[i - 1] = g(p + ".0.bias");
+    cs.mid_ln_w[i - 1] = g(p + ".0.weight");
+    cs.mid_ln_b[i - 1] = g(p + ".0.bias");
     expect_shape(get(M, p + ".1.weight"), {dims[i], dims[i - 1], 1}, p);
-    mid_w[i - 1] = g(p + ".1.weight");
-    mid_b[i - 1] = g(p + ".1.bias");
+    cs.mid_w[i - 1] = g(p + ".1.weight");
+    cs.mid_b[i - 1] = g(p + ".1.bias");
   }
   for (int s = 0; s < 4; ++s) {
-    enc_blocks[s].clear();
+    cs.blocks[s].clear();
     for (int j = 0; j < depths[s]; ++j)
-      enc_blocks[s].push_back(pack_convnext(*this, M, "backbone.stages." + std::to_string(s) + "." + std::to_string(j), dims[s]));
+      cs.blocks[s].push_back(pack_convnext(*this, M, "backbone.stages." + std::to_string(s) + "." + std::to_string(j), dims[s]));
   }
-  bb_norm_w = g("backbone.norm.weight");
-  bb_norm_b = g("backbone.norm.bias");
+  cs.bb_norm_w = g("backbone.norm.weight");
+  cs.bb_norm_b = g("backbone.norm.bias");
   for (int i = 0; i < 2; ++i) {
     const std::string p = "quantizer.downsample." + std::to_string(i);
     expect_shape(get(M, p + ".0.conv.weight"), {ENC_DIM, ENC_DIM, 2}, p);
-    down_w[i] = upload(pack_conv_rows(to_host(get(M, p + ".0.conv.weight")), ENC_DIM, ENC_DIM, 2));
-    down_b[i] = g(p + ".0.conv.bias");
-    down_block[i] = pack_convnext(*this, M, p + ".1", ENC_DIM);
+    cs.down_w[i] = upload(pack_conv_rows(to_host(get(M, p + ".0.conv.weight")), ENC_DIM, ENC_DIM, 2));
+    cs.down_b[i] = g(p + ".0.conv.bias");
+    cs.down_block[i] = pack_convnext(*this, M, p + ".1", ENC_DIM);
   }
+  cs.ready = true;
+}
+
+void Engine::finalize_tokenizer() {
+  const int M = MODEL_TOKENIZER;
+  auto g = [&](const std::string& n) { return get(M, n).data; };
+  build_spectrogram_consts(M);
+  pack_conv_stack(M, tok_cs);
   for (int i = 0; i < ENC_LAYERS; ++i) {
     const std::string p = "quantizer.pre_module.layers." + std::to_string(i);
     EncLayerW& l = enc_layers[i];
@@ -390,6 +402,22 @@ void Engine::finalize_vocoder() {
   expect_shape(get(M, "head.conv_post.conv.weight"), {1, 16, 13}, "conv_post");
   post_w = upload(pack_conv_rows(to_host(get(M, "head.conv_post.conv.weight")), 1, 16, 13));
   post_b = g("head.conv_post.conv.bias");
+  // optional: the vocoder's own encoder (prompt path: reference wave -> codec ids)
+  if (has(M, "backbone.norm.weight") && has(M, "quantizer.residual_fsq.rvqs.0.project_in.weight")) {
+    build_spectrogram_consts(has(M, "spec_transform.fb") ? M : MODEL_TOKENIZER);
+    pack_conv_stack(M, voc_cs);
+    std::vector<float> iw, ib;
+    for (int gi = 0; gi < 8; ++gi) {
+      const std::string p = "quantizer.residual_fsq.rvqs." + std::to_string(gi) + ".project_in";
+      expect_shape(get(M, p + ".weight"), {4, 64}, p);
+      auto a = to_host(get(M, p + ".weight"));
+      auto b = to_host(get(M, p + ".bias"));
+      iw.insert(iw.end(), a.begin(), a.end());
+      ib.insert(ib.end(), b.begin(), b.end());
+    }
+    fsq_in_w = upload(iw);
+    fsq_in_b = upload(ib);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ ConvNeXt block
@@ -414,14 +442,17 @@ void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float
 }
 
 // ------------------------------------------------------------------------------------------ stage E
+static size_t enc_ws_floats(int B, long long n) { return ((size_t)(n / HOP) * 14000 + (size_t)n) * B; }
+
 // FireflyArchitecture.encode (firefly_encoder.py:553-566) in two halves.
 //
 // enc_conv_stack: everything up to the transformer input -- log-mel, ConvNeXtEncoder, the two down-sampling blocks --
 // for NS same-length wave segments side by side (segment i = rows of src[i / per_src] with pitch[i / per_src]): wave
 // -> xt [NS][n/2048][512].  Streams never mix: every causal conv reads its own segment's zero margin; the GEMMs simply
 // see NS times more rows.  Workspace comes from `ws` (caller has sized and reset it).
-void Engine::enc_conv_stack(const float* const* src, const long long* pitch, int nsrc, int per_src, long long n, float* xt,
-                            cudaStream_t st) {
+void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const long long* pitch, int nsrc, int per_src,
+                            long long n, float* xt, cudaStream_t st) {
+  SV_CHECK(w.ready && dft_w && fb_t, "encoder weights not finalized");
   const int B = nsrc * per_src;
   const int T = (int)(n / HOP);
   const int T2 = T / 2, S = T2 / 2;
@@ -472,25 +503,25 @@ void Engine::enc_conv_stack(const float* const* src, const long long* pitch, int
     float* xn = xb + MARG * C;
     if (s == 0) {
       GemmParams p;   // stem: causal conv k=7 as one GEMM over 7 overlapping rows
-      p.A = mel; p.W = stem_w; p.C = tmp; p.bias = stem_b; p.M = BT; p.N = C; p.K = 7 * N_MELS; p.lda = N_MELS;
+      p.A = mel; p.W = w.stem_w; p.C = tmp; p.bias = w.stem_b; p.M = BT; p.N = C; p.K = 7 * N_MELS; p.lda = N_MELS;
       p.ldc = C; p.tap_off[0] = -6;
       p.seg_rows = segT; p.a_seg = mel_seg; p.c_seg = (long long)T * C;
       launch_gemm(p, st);
-      launch_layernorm(tmp, xn, stem_ln_w, stem_ln_b, BT, C, 1e-6f, st, segT, (long long)T * C, xs);
+      launch_layernorm(tmp, xn, w.stem_ln_w, w.stem_ln_b, BT, C, 1e-6f, st, segT, (long long)T * C, xs);
     } else {
       const int Cp = dims[s - 1];
-      launch_layernorm(x, tmp, mid_ln_w[s - 1], mid_ln_b[s - 1], BT, Cp, 1e-6f, st, segT, x_seg, (long long)T * Cp);
+      launch_layernorm(x, tmp, w.mid_ln_w[s - 1], w.mid_ln_b[s - 1], BT, Cp, 1e-6f, st, segT, x_seg, (long long)T * Cp);
       GemmParams p;
-      p.A = tmp; p.W = mid_w[s - 1]; p.C = xn; p.bias = mid_b[s - 1]; p.M = BT; p.N = C; p.K = Cp; p.lda = Cp; p.ldc = C;
+      p.A = tmp; p.W = w.mid_w[s - 1]; p.C = xn; p.bias = w.mid_b[s - 1]; p.M = BT; p.N = C; p.K = Cp; p.lda = Cp; p.ldc = C;
       p.seg_rows = segT; p.a_seg = (long long)T * Cp; p.c_seg = xs;
       launch_gemm(p, st);
     }
     x = xn;
     x_seg = xs;
-    for (auto& blk : enc_blocks[s]) convnext(blk, x, BT, tmp, hid, st, nullptr, segT, x_seg, 0);
+    for (auto& blk : w.blocks[s]) convnext(blk, x, BT, tmp, hid, st, nullptr, segT, x_seg, 0);
   }
   float* feat = ws.alloc_f((long long)BT * 512);
-  launch_layernorm(x, feat, bb_norm_w, bb_norm_b, BT, 512, 1e-6f, st, segT, x_seg, (long long)T * 512);
+  launch_layernorm(x, feat, w.bb_norm_w, w.bb_norm_b, BT, 512, 1e-6f, st, segT, x_seg, (long long)T * 512);
   // 4. DownsampleBinarySphericalQuantize.downsample (bsq_no_upsample.py:46-60): 2 x [conv k2 s2 + ConvNeXt]
   float* cur = feat;
   long long cur_seg = (long long)T * 512;
@@ -502,12 +533,12 @@ void Engine::enc_conv_stack(const float* const* src, const long long* pitch, int
     launch_fill(db, (long long)MARG * 512, 0.f, st, B, ds);
     float* dn = db + MARG * 512;
     GemmParams p;
-    p.A = cur; p.W = down_w[i]; p.C = dn; p.bias = down_b[i]; p.M = B * r2; p.N = 512; p.K = 1024; p.lda = 512;
+    p.A = cur; p.W = w.down_w[i]; p.C = dn; p.bias = w.down_b[i]; p.M = B * r2; p.N = 512; p.K = 1024; p.lda = 512;
     p.a_row_step = 2; p.ldc = 512;
     p.seg_rows = B > 1 ? r2 : 0; p.a_seg = cur_seg; p.c_seg = ds;
     launch_gemm(p, st);
     // the second block writes its result straight into the plain output buffer
-    convnext(down_block[i], dn, B * r2, tmp, hid, st, i == 1 ? xt : nullptr, B > 1 ? r2 : 0, ds, (long long)r2 * 512);
+    convnext(w.down_block[i], dn, B * r2, tmp, hid, st, i == 1 ? xt : nullptr, B > 1 ? r2 : 0, ds, (long long)r2 * 512);
     cur = dn;
     cur_seg = ds;
     rows = r2;
@@ -553,7 +584,6 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
   launch_bsq(nrm, bsq_w, bsq_b, ids_dev, BS, st);
 }
 
-static size_t enc_ws_floats(int B, long long n) { return ((size_t)(n / HOP) * 14000 + (size_t)n) * B; }
 
 // B full-length utterances / windows of the same length, side by side: wave [B][n] -> ids [B][n/2048].
 void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_dev, cudaStream_t st) {
@@ -566,7 +596,7 @@ void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_de
   ws.ensure((enc_ws_floats(B, n) + (4u << 20)) * sizeof(float));
   ws.reset();
   float* xt = ws.alloc_f((long long)B * S * ENC_DIM);
-  enc_conv_stack(&wave, &n, 1, B, n, xt, st);
+  enc_conv_stack(tok_cs, &wave, &n, 1, B, n, xt, st);
   enc_transformer_bsq(xt, B, S, ids_dev, st);
 }
 
@@ -614,7 +644,7 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
   if (!incremental) {
     ws.ensure((enc_ws_floats(B, nw) + (size_t)B * S * ENC_DIM + (4u << 20)) * sizeof(float));
     ws.reset();
-    enc_conv_stack(&wave_ring, &nw, 1, B, nw, xt_state, st);
+    enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nw, xt_state, st);
   } else {
     const long long ns = (long long)Ls * SAMPLES_PER_FRAME;
     ws.ensure((enc_ws_floats(2 * B, ns) + enc_ws_floats(B, nw) / 3 + (size_t)(2 * B * Ls + B * S) * ENC_DIM + (4u << 20)) *
@@ -623,7 +653,7 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
     float* spans = ws.alloc_f((long long)2 * B * Ls * ENC_DIM);
     const float* src[2] = {wave_ring, wave_ring + (nw - ns)};
     const long long pitch[2] = {nw, nw};
-    enc_conv_stack(src, pitch, 2, B, ns, spans, st);
+    enc_conv_stack(tok_cs, src, pitch, 2, B, ns, spans, st);
     launch_pdl(enc_assemble_kernel, dim3(S, B), dim3(128), 0, st, (const float*)spans, (const float*)state.xt[state.cur],
                xt_state, B, S, Ls, ENC_RF, c);
     SV_LAUNCHED();
@@ -633,6 +663,22 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
   float* xt = ws.alloc_f((long long)B * S * ENC_DIM);
   SV_CUDA(cudaMemcpyAsync(xt, xt_state, (size_t)B * S * ENC_DIM * sizeof(float), cudaMemcpyDeviceToDevice, st));
   enc_transformer_bsq(xt, B, S, ids_dev, st);
+}
+
+// ------------------------------------------------------------------------------------------ prompt path: wave -> codec ids
+// FireflyArchitecture.encode of the vocoder (firefly.py:561-574; `wav2target_fn`, infer_arvc.py:168-171) for B
+// full-length rows: the same conv stack as the tokenizer with the vocoder's weights, then the FSQ indices of the 8
+// groups (DownsampleFiniteScalarQuantize.encode, fsq.py:106-110).
+void Engine::voc_encode(const float* wave, int B, long long n, int* codes_dev, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
+  SV_CHECK(voc_cs.ready, "the vocoder checkpoint was loaded without its encoder (backbone.*, quantizer.downsample.*, project_in)");
+  const int S = (int)(n / HOP) / 4;
+  SV_CHECK(B >= 1 && S >= 1, "utterance shorter than one frame (2048 samples)");
+  ws.ensure((enc_ws_floats(B, n) + (4u << 20)) * sizeof(float));
+  ws.reset();
+  float* z = ws.alloc_f((long long)B * S * ENC_DIM);
+  enc_conv_stack(voc_cs, &wave, &n, 1, B, n, z, st);
+  launch_fsq_encode(z, fsq_in_w, fsq_in_b, codes_dev, B, S, st);
 }
 
 // ------------------------------------------------------------------------------------------ stage V

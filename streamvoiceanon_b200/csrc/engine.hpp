@@ -40,6 +40,18 @@ struct ConvNextW {
   int C;
 };
 
+// The conv stack shared by the two FireflyArchitecture encoders (content tokenizer and the vocoder's own encoder):
+// ConvNeXtEncoder (stem + 4 stages) + the quantizer's 2 x [causal conv k2 s2 + ConvNeXt] down-sampling.
+struct ConvStackW {
+  const float *stem_w = nullptr, *stem_b = nullptr, *stem_ln_w = nullptr, *stem_ln_b = nullptr;
+  const float *mid_ln_w[3] = {}, *mid_ln_b[3] = {}, *mid_w[3] = {}, *mid_b[3] = {};
+  std::vector<ConvNextW> blocks[4];
+  const float *bb_norm_w = nullptr, *bb_norm_b = nullptr;
+  const float *down_w[2] = {}, *down_b[2] = {};
+  ConvNextW down_block[2];
+  bool ready = false;
+};
+
 struct EncLayerW {
   const float *attn_norm, *wqkv, *wo, *ffn_norm, *w1, *w3, *w2, *ls_attn, *ls_ffn;
 };
@@ -207,13 +219,8 @@ struct Engine {
   unsigned ar_epoch = 0;
 
   // ---- tokenizer
-  const float *dft_w = nullptr, *fb_t = nullptr, *stem_w = nullptr, *stem_b = nullptr, *stem_ln_w = nullptr,
-              *stem_ln_b = nullptr;
-  const float *mid_ln_w[3] = {}, *mid_ln_b[3] = {}, *mid_w[3] = {}, *mid_b[3] = {};
-  std::vector<ConvNextW> enc_blocks[4];
-  const float *bb_norm_w = nullptr, *bb_norm_b = nullptr;
-  const float *down_w[2] = {}, *down_b[2] = {};
-  ConvNextW down_block[2];
+  const float *dft_w = nullptr, *fb_t = nullptr;      // windowed DFT basis and mel filterbank (same LogMelSpectrogram in both)
+  ConvStackW tok_cs;                                  // tokenizer conv stack
   EncLayerW enc_layers[ENC_LAYERS];
   const float *enc_norm_w = nullptr, *enc_rope = nullptr, *bsq_w = nullptr, *bsq_b = nullptr;
 
@@ -225,6 +232,8 @@ struct Engine {
   const float *ups_w[5] = {}, *ups_b[5] = {};
   ResConvW res1[5][3][3], res2[5][3][3];
   const float *post_w = nullptr, *post_b = nullptr;
+  ConvStackW voc_cs;                                  // the vocoder's own encoder (prompt path), optional
+  const float *fsq_in_w = nullptr, *fsq_in_b = nullptr;   // [8][4][64], [8][4]
 
   ~Engine();
 
@@ -242,8 +251,12 @@ struct Engine {
   // stage drivers (all device pointers, stream-ordered, no host sync)
   int enc_num_ids(long long n_samples) const { return (int)(((n_samples / HOP) / 2) / 2); }
   void enc_encode(const float* wave_dev /*[B][n]*/, int B, long long n_samples, long long* ids_dev /*[B][S]*/, cudaStream_t st);
-  void enc_conv_stack(const float* const* src, const long long* pitch, int nsrc, int per_src, long long n, float* xt,
-                      cudaStream_t st);
+  void enc_conv_stack(const ConvStackW& w, const float* const* src, const long long* pitch, int nsrc, int per_src,
+                      long long n, float* xt, cudaStream_t st);
+  void pack_conv_stack(int model, ConvStackW& cs);
+  void build_spectrogram_consts(int model);
+  // FireflyArchitecture.encode of the vocoder (firefly.py:561-574): wave [B][n] -> codec ids int32 [B][8][n/2048]
+  void voc_encode(const float* wave_dev, int B, long long n, int* codes_dev, cudaStream_t st);
   void enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st);
   // the window re-encode of the streaming loop with the conv-stack outputs kept between chunks (wave_ring [B][S*2048])
   void enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,

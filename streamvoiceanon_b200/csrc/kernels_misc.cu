@@ -224,6 +224,36 @@ __global__ void fsq_lookup_kernel(const long long* __restrict__ codes, long long
   z[idx] = acc;
 }
 
+// GroupedResidualFSQ.forward -> indices, 8 groups x 1 quantizer, levels (8,5,5,5) (vendored twin:
+// finite_scalar_quantization.py:126-156): per group project_in 64 -> 4 (+bias), bound = tanh(x + shift) * half_l - offset
+// with half_l = (L-1) * (1 + 1e-3) / 2, offset = 0.5 for even L, shift = atanh(offset / half_l); round half to even;
+// digit = round + L/2; index = sum digit * basis.  One warp per (token, group); codes [B][8][T] int32.
+__global__ void fsq_encode_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
+                                  int* __restrict__ codes, int B, int T) {
+  pdl_trigger();
+  pdl_wait();
+  const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (item >= B * T * 8) return;
+  const int g = item & 7, tok = item >> 3;
+  const float* zr = z + (long long)tok * 512 + g * 64;
+  const float z0 = zr[lane], z1 = zr[lane + 32];
+  const int levels[4] = {8, 5, 5, 5};
+  const int basis[4] = {1, 8, 40, 200};
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float* wr = w + (g * 4 + i) * 64;
+    float s = fmaf(z1, wr[lane + 32], z0 * wr[lane]);
+    s = warp_sum(s) + b[g * 4 + i];
+    const float half_l = (float)(levels[i] - 1) * 1.001f / 2.f;
+    const float offset = (levels[i] % 2 == 0) ? 0.5f : 0.f;
+    const float shift = atanhf(offset / half_l);
+    const float bounded = tanhf(s + shift) * half_l - offset;
+    idx += ((int)rintf(bounded) + levels[i] / 2) * basis[i];
+  }
+  if (lane == 0) codes[((long long)(tok / T) * 8 + g) * T + (tok % T)] = idx;
+}
+
 // activation_post (SiLU) + conv_post (16 -> 1, k = 13, causal) + tanh, firefly.py:289-291.
 __global__ void conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                  float* __restrict__ out, int L, int seg_rows, long long x_seg) {
@@ -378,6 +408,12 @@ void launch_fsq_lookup(const long long* codes, long long ld, const float* w, con
   if (T <= 0) return;
   launch_pdl(fsq_lookup_kernel, dim3(blocks_for((long long)T * 512, 256)), dim3(256), 0, st, codes, ld, w, b, z, T, seg_rows,
              codes_seg);
+  SV_LAUNCHED();
+}
+
+void launch_fsq_encode(const float* z, const float* w, const float* b, int* codes, int B, int T, cudaStream_t st) {
+  if (B * T <= 0) return;
+  launch_pdl(fsq_encode_kernel, dim3(blocks_for((long long)B * T * 8 * 32, 128)), dim3(128), 0, st, z, w, b, codes, B, T);
   SV_LAUNCHED();
 }
 

@@ -144,7 +144,7 @@ class _Head:
 
 
 class Vocoder(_Shim):
-    _WANTED = ("head.", "quantizer.upsample.", "quantizer.residual_fsq.rvqs.")
+    _WANTED = ("head.", "quantizer.upsample.", "quantizer.residual_fsq.rvqs.", "backbone.", "quantizer.downsample.")
 
     def __init__(self, backbone=None, head=None, quantizer=None, spec_transform=None, device=None):
         self._engine = Engine.get(device)
@@ -155,16 +155,47 @@ class Vocoder(_Shim):
     def load_state_dict(self, sd, strict: bool = False):
         eng = self._engine
 
-        def wanted(k):
-            return k.startswith(self._WANTED) and "project_in" not in k
-        unexpected = eng.load_state_dict(_lib.MODEL_VOCODER, sd, wanted)
+        unexpected = eng.load_state_dict(_lib.MODEL_VOCODER, sd, lambda k: k.startswith(self._WANTED))
+        # the encode path (reference wave -> codec ids of the prompt) is optional: decode-only checkpoints stay valid
+        self.has_encoder = "backbone.norm.weight" in sd and "quantizer.residual_fsq.rvqs.0.project_in.weight" in sd
+        if self.has_encoder:
+            eng.load_tensor(_lib.MODEL_VOCODER, "spec_transform.fb", slaney_fbanks())
         eng.finalize(_lib.MODEL_VOCODER)         # folds weight norm (remove_parametrizations, infer_arvc.py:94)
-        unexpected = [k for k in unexpected if not (k.startswith(("backbone.", "quantizer.downsample.")) or "project_in" in k)]
         return _IncompatibleKeys([], unexpected)
 
     def remove_parametrizations(self):
         """firefly.py:597-602 -- weight norm is folded when the weights are finalized."""
         return None
+
+    @torch.no_grad()
+    def encode(self, audios, audio_lengths):
+        """FireflyArchitecture.encode, firefly.py:561-574 (`wav2target_fn`, infer_arvc.py:168-171): wav [B,L] f32, lens [B]
+        -> ((codes int32 [B,8,T], quantized), feature_lengths).  `quantized` (the FSQ latents, unused by the callers) is
+        returned as None.  Rows shorter than L are encoded one by one on their valid prefix (causal-prefix property),
+        later ids are 0."""
+        if not getattr(self, "has_encoder", False):
+            raise RuntimeError("the vocoder checkpoint was loaded without its encoder tensors (backbone.*, "
+                               "quantizer.downsample.*, quantizer.residual_fsq.rvqs.*.project_in.*)")
+        eng = self._engine
+        audios = audios.float()
+        B, L = audios.shape
+        dev = audios.device if audios.is_cuda else torch.device("cuda", eng.device)
+        T = L // 2048
+        codes = torch.zeros(B, 8, T, dtype=torch.int32, device=dev)
+        lens = [min(int(x), L) for x in audio_lengths.reshape(-1).tolist()]
+        if T > 0 and all(n >= L for n in lens):
+            rows = audios.contiguous()
+            _lib.check(eng.lib.svanon_voc_encode(eng.handle, ptr(rows), B, L, ptr(codes), C.c_void_p(_cuda_stream_ptr())))
+        else:
+            for b in range(B):
+                tb = lens[b] // 2048
+                if tb == 0:
+                    continue
+                row = audios[b, : lens[b]].contiguous()
+                out = torch.empty(8, tb, dtype=torch.int32, device=dev)
+                _lib.check(eng.lib.svanon_voc_encode(eng.handle, ptr(row), 1, lens[b], ptr(out), C.c_void_p(_cuda_stream_ptr())))
+                codes[b, :, :tb] = out
+        return (codes, None), (audio_lengths // 512) // self.downsample_factor
 
     @torch.no_grad()
     def decode_codes(self, codes):

@@ -177,6 +177,30 @@ def make_vocoder_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]:
     return b.sd
 
 
+def make_vocoder_encoder_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """The vocoder's ENCODE path (`FireflyArchitecture.encode`, modules/vqgan/modules/firefly.py:561-574: reference wave ->
+    codec ids for the prompt, evaluations/infer_arvc.py:168-171): ConvNeXt backbone, quantizer.downsample and the FSQ
+    project_in of each of the 8 groups.  Kept apart from make_vocoder_state_dict so that the decode-path fixtures and
+    their weight digest do not change; merge the two dicts to get the full checkpoint."""
+    b = _Builder(seed + 7)
+    dims, depths = [128, 256, 384, 512], [3, 3, 9, 3]
+    b.linear("backbone.downsample_layers.0.0.conv", dims[0], 160, bias=True, extra=(7,))
+    b.norm("backbone.downsample_layers.0.1", dims[0], bias=True)
+    for i in range(1, 4):
+        b.norm(f"backbone.downsample_layers.{i}.0", dims[i - 1], bias=True)
+        b.linear(f"backbone.downsample_layers.{i}.1", dims[i], dims[i - 1], bias=True, extra=(1,))
+    for s in range(4):
+        for j in range(depths[s]):
+            b.convnext(f"backbone.stages.{s}.{j}", dims[s])
+    b.norm("backbone.norm", 512, bias=True)
+    for i in range(2):
+        b.linear(f"quantizer.downsample.{i}.0.conv", 512, 512, bias=True, extra=(2,))
+        b.convnext(f"quantizer.downsample.{i}.1", 512)
+    for g in range(8):
+        b.linear(f"quantizer.residual_fsq.rvqs.{g}.project_in", 4, 64, gain=3.0, bias=True)
+    return b.sd
+
+
 def fold_weight_norm(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """w = g * v / ||v|| over dims (1,2) -- what `remove_parametrizations()` leaves behind
     (evaluations/infer_arvc.py:94, modules/vqgan/modules/firefly.py:105-111)."""

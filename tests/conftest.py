@@ -41,7 +41,8 @@ def weights():
     ar = synth.make_ar_state_dict(seed)
     tok = synth.make_tokenizer_state_dict(seed)
     voc = synth.make_vocoder_state_dict(seed)
-    return dict(ar=ar, tok=tok, voc=voc, voc_folded=synth.fold_weight_norm(voc))
+    voc_enc = synth.make_vocoder_encoder_state_dict(seed)      # the vocoder's encode path (prompt: wave -> codec ids)
+    return dict(ar=ar, tok=tok, voc=voc, voc_enc=voc_enc, voc_folded=synth.fold_weight_norm(voc))
 
 
 @pytest.fixture(scope="session")
@@ -54,7 +55,7 @@ def models(weights):
     tok = ContentTokenizer()
     tok.load_state_dict(weights["tok"], strict=False)
     voc = Vocoder()
-    voc.load_state_dict(weights["voc"], strict=False)       # weight-norm form, folded by the library
+    voc.load_state_dict({**weights["voc"], **weights["voc_enc"]}, strict=False)   # weight-norm form, folded by the library
     voc.remove_parametrizations()
     return ar, tok, voc
 

@@ -400,3 +400,34 @@ def test_ar_epoch_word_grid_barrier(models, gold, tape, variant):
     finally:
         _lib.check(lib.svanon_ar_set_kernel_variant(ar._engine.handle, 1))
         _lib.check(lib.svanon_ar_set_barrier_mode(ar._engine.handle, 0))
+
+
+# ------------------------------------------------------------------------------------------------ prompt path
+def test_vocoder_encode_vs_reference(models, gold):
+    """reference wave -> codec ids (`wav2target_fn`, infer_arvc.py:168-171) through
+    svanon_voc_encode against the reference's own `FireflyArchitecture.encode`: ids bit-exact."""
+    _, _, voc = models
+    g = gold("vocoder_encode")
+    for n in "ab":
+        frames = int(g[f"frames_{n}"])
+        wav = synth.synth_audio_44k(int(g[f"seed_{n}"]), 3.0)[: frames * 2048][None]
+        (codes, _), lens = voc.encode(wav.cuda(), torch.LongTensor([wav.shape[1]]).cuda())
+        assert codes.dtype == torch.int32 and tuple(codes.shape) == (1, 8, frames) and int(lens[0]) == frames
+        assert np.array_equal(codes.cpu().numpy(), g[f"codes_{n}"]), n
+
+
+def test_vocoder_encode_batched_and_ragged_vs_oracle(models, weights):
+    """Rows side by side in one call, host buffers, and a ragged row (valid prefix only) against the oracle."""
+    from oracle import vocoder as V
+    _, _, voc = models
+    n = 19 * 2048
+    wavs = torch.stack([synth.synth_audio_44k(1500 + i, 1.0)[:n] for i in range(3)])
+    with torch.no_grad():
+        want = V.wav2codes(wavs, weights["voc_enc"])
+    (codes, _), _ = voc.encode(wavs, torch.LongTensor([n] * 3))                     # host tensors
+    assert np.array_equal(codes.cpu().numpy(), want.numpy())
+    (ragged, _), lens = voc.encode(wavs.cuda(), torch.LongTensor([n, 7 * 2048 + 100, n]).cuda())
+    assert lens.tolist() == [19, 7, 19]
+    assert np.array_equal(ragged[1, :, :7].cpu().numpy(), want[1, :, :7].numpy())
+    assert int(ragged[1, :, 7:].abs().sum()) == 0
+    assert np.array_equal(ragged[0].cpu().numpy(), want[0].numpy())

@@ -158,3 +158,18 @@ def test_stream_default_loop(weights, gold, tape):
     assert np.array_equal(so.src_content_codes.numpy(), g["src_content"])
     assert np.array_equal(so.pred_codes.numpy(), g["pred_codes"])
     assert float(((wave[0].numpy() - g["wave"]) ** 2).mean()) < 1e-10
+
+
+def test_vocoder_encode_oracle_vs_reference(gold, weights):
+    """`wav2target_fn` (reference wave -> codec ids of the prompt): the restatement of FireflyArchitecture.encode +
+    the FSQ index arithmetic against the reference's own vocoder object (tests/golden/vocoder_encode.npz, written by
+    oracle/make_golden_vocenc.py): ids bit-exact."""
+    from oracle import vocoder as V
+    from streamvoiceanon_b200 import synth
+    g = gold("vocoder_encode")
+    for n in "ab":
+        wav = synth.synth_audio_44k(int(g[f"seed_{n}"]), 3.0)[: int(g[f"frames_{n}"]) * 2048][None]
+        with torch.no_grad():
+            codes = V.wav2codes(wav, weights["voc_enc"])
+        assert codes.dtype == torch.int32
+        assert np.array_equal(codes.numpy(), g[f"codes_{n}"]), n
