@@ -6,6 +6,7 @@ namespace svanon {
 extern bool g_gemm_use_pipe;
 extern bool g_gemm_use_tc;
 extern bool g_use_pdl;
+extern bool g_use_conv_small;
 }
 namespace svanon {
 thread_local std::string g_api_err;
@@ -327,6 +328,7 @@ int svanon_set_gemm_mode(int mode) {
     SV_CHECK(mode >= 0 && mode <= 2, "gemm mode: 0 = fp32 CUDA-core (register double-buffer only), 1 = fp32 CUDA-core, 2 = tcgen05 3xTF32");
     g_gemm_use_pipe = mode >= 1;
     g_gemm_use_tc = mode == 2;
+    g_use_conv_small = mode >= 1;
   });
 }
 

@@ -103,6 +103,87 @@ attention_kernel(const float* __restrict__ q, long long q_ld, const float* __res
   }
 }
 
+// Short sequences (all keys of a stream fit shared memory: <= 128 positions, the encoder's streaming window): the
+// CTA stages K and V of its head ONCE (66 KB) and its 16 warps then run one query each without any further block
+// barrier -- the tiled kernel above pays two barriers and one global round trip per 32 keys, which made it the single
+// slowest kernel of the window encode (26.7 us for 17 MFLOP).
+constexpr int SQW = 16;      // queries (warps) per CTA
+constexpr int SMAXK = 128;   // keys held in shared memory
+__global__ void __launch_bounds__(SQW * 32)
+attention_short_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
+                       long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
+                       int qpos0, int window) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float att_smem[];
+  float (*Ks)[HEAD_DIM + 1] = reinterpret_cast<float (*)[HEAD_DIM + 1]>(att_smem);
+  float (*Vs)[HEAD_DIM] = reinterpret_cast<float (*)[HEAD_DIM]>(att_smem + SMAXK * (HEAD_DIM + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int bps = (nq + SQW - 1) / SQW;
+  const int seg = blockIdx.x / bps;
+  const int qi0 = (blockIdx.x - seg * bps) * SQW;
+  q += (long long)seg * nq * q_ld;
+  k += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
+  v += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
+  out += (long long)seg * nq * out_ld;
+  const int qi = qi0 + warp;
+  const bool active = qi < nq;
+  const int pos = qpos0 + qi;
+  const int lo = max(0, pos - window + 1);
+  const int k_hi = qpos0 + min(qi0 + SQW, nq) - 1;          // newest key any query of this CTA needs (inclusive)
+  for (int i = threadIdx.x; i < (k_hi + 1) * (HEAD_DIM / 4); i += SQW * 32) {
+    const int key = i / (HEAD_DIM / 4), c = (i % (HEAD_DIM / 4)) * 4;
+    const float4 kv = __ldg(reinterpret_cast<const float4*>(k + (long long)key * kv_row_stride + c));
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(v + (long long)key * kv_row_stride + c));
+    Ks[key][c] = kv.x; Ks[key][c + 1] = kv.y; Ks[key][c + 2] = kv.z; Ks[key][c + 3] = kv.w;
+    *reinterpret_cast<float4*>(&Vs[key][c]) = vv;
+  }
+  float qr[HEAD_DIM];
+  if (active) {
+    const float* qp = q + (long long)qi * q_ld + h * HEAD_DIM;
+#pragma unroll
+    for (int d = 0; d < HEAD_DIM; ++d) qr[d] = __ldg(qp + d) * 0.125f;   // 1/sqrt(64)
+  }
+  __syncthreads();
+  if (!active) return;
+  float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;
+  for (int kt = (lo / KT) * KT; kt <= pos; kt += KT) {
+    const int kp = kt + lane;
+    const bool valid = (kp >= lo) && (kp <= pos);
+    float s = 0.f;
+    if (kp <= k_hi) {
+#pragma unroll
+      for (int d = 0; d < HEAD_DIM; ++d) s = fmaf(qr[d], Ks[kp][d], s);
+    }
+    s = valid ? s : -INFINITY;
+    float tmax = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (tmax == -INFINITY) continue;
+    const float m_new = fmaxf(m, tmax);
+    const float corr = expf(m - m_new);
+    const float p = valid ? expf(s - m_new) : 0.f;
+    float psum = p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+    l = l * corr + psum;
+    acc0 *= corr;
+    acc1 *= corr;
+    const int jn = min(KT, pos - kt + 1);
+    for (int j = 0; j < jn; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      acc0 = fmaf(pj, Vs[kt + j][lane], acc0);
+      acc1 = fmaf(pj, Vs[kt + j][lane + 32], acc1);
+    }
+    m = m_new;
+  }
+  float* op = out + (long long)qi * out_ld + h * HEAD_DIM;
+  const float inv = 1.f / l;
+  op[lane] = acc0 * inv;
+  op[lane + 32] = acc1 * inv;
+}
+
 __global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float* __restrict__ kc, float* __restrict__ vc,
                                  int max_seq, int pos0) {
   pdl_trigger();
@@ -125,6 +206,18 @@ void launch_attention(const float* q, long long q_ld, const float* k, const floa
                       long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
                       cudaStream_t st, int nseg) {
   if (nq <= 0 || nseg <= 0) return;
+  if (qpos0 + nq <= SMAXK && (kv_row_stride % 4) == 0) {        // the whole key range of a stream fits shared memory
+    constexpr size_t SMEM = (size_t)SMAXK * (2 * HEAD_DIM + 1) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      SV_CUDA(cudaFuncSetAttribute(attention_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+      configured = true;
+    }
+    launch_pdl(attention_short_kernel, dim3((nq + SQW - 1) / SQW * nseg, heads), dim3(SQW * 32), SMEM, st, q, q_ld, k, v,
+               kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window);
+    SV_LAUNCHED();
+    return;
+  }
   dim3 grid((nq + QW - 1) / QW * nseg, heads);
   launch_pdl(attention_kernel, dim3(grid), dim3(QW * 32), 0, st, q, q_ld, k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0,
                                              window);

@@ -1,0 +1,126 @@
+// Direct causal conv for the two thinnest HiFi-GAN levels (C = 32 and C = 16 channels, ResBlock1 convs of
+// firefly.py:149-219): out[m][co] = bias[co] + sum_tap sum_ci W[tap][co][ci] * silu(x[m + off_tap][ci]) (+ residual).
+//
+// As GEMMs these problems have N = K-per-tap = 16 or 32: far too thin for the tensor cores and latency-bound in the
+// generic cp.async pipeline (11 taps = 11 dependent pipeline steps, ~24 us per launch for 35 MFLOP).  Here a CTA owns
+// TR consecutive output rows of one problem: it stages the SiLU'd input rows (with their causal halo) and the whole
+// weight tensor (<= 45 KB) in shared memory once, then every thread produces 4 output channels of one row from
+// registers.  Same GemmParams contract as gemm.cu (up to 3 problems per launch, streams side by side).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace svanon {
+
+namespace {
+
+struct ConvBatch {
+  GemmParams p[3];
+};
+
+__device__ __forceinline__ float silu_acc(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
+// C channels in and out, TR output rows per CTA, 4 output channels per thread: blockDim = TR * C / 4.
+template <int C, int TR>
+__global__ void __launch_bounds__(TR * C / 4) conv_small_kernel(const ConvBatch batch) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int Q = C / 4;                       // channel quads
+  const GemmParams& p = batch.p[blockIdx.z];
+  const int ktaps = p.taps > 1 ? p.taps : p.K / C;          // dilation 1: one "tap" of k*C overlapping columns
+  const int halo = -p.tap_off[0];                           // the oldest row any tap reaches
+  float* w_s = smem;                                        // [ktaps][Q (ci quad)][C (co)][4]
+  float* x_s = smem + ktaps * C * C;                        // [halo + TR][C], SiLU applied
+  const int tid = threadIdx.x;
+  pdl_trigger();
+  // weights: global layout dilation 1: W[co][tap*C + ci]; dilated: W[(tap*C + co)*C + ci]
+  for (int i = tid; i < ktaps * C * Q; i += blockDim.x) {
+    const int q = i % Q, co = (i / Q) % C, tap = i / (Q * C);
+    const float* src = p.taps > 1 ? p.W + ((long long)tap * C + co) * C + q * 4 : p.W + (long long)co * p.K + tap * C + q * 4;
+    *reinterpret_cast<float4*>(w_s + ((tap * Q + q) * C + co) * 4) = __ldg(reinterpret_cast<const float4*>(src));
+  }
+  pdl_wait();
+  const int m0 = blockIdx.x * TR;                            // TR divides the rows of a stream: a tile never straddles two
+  const float* a0 = p.A + gemm_a_row(p, m0);
+  for (int i = tid; i < (halo + TR) * Q; i += blockDim.x) {
+    const int q = i % Q, r = i / Q;
+    float4 v = *reinterpret_cast<const float4*>(a0 + (long long)(r - halo) * p.lda + q * 4);
+    v.x = silu_acc(v.x); v.y = silu_acc(v.y); v.z = silu_acc(v.z); v.w = silu_acc(v.w);
+    *reinterpret_cast<float4*>(x_s + r * C + q * 4) = v;
+  }
+  __syncthreads();
+  const int cq = tid % Q, row = tid / Q;                     // this thread: output channels cq*4 .. +3 of row m0 + row
+  float acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = p.bias ? __ldg(p.bias + cq * 4 + j) : 0.f;
+  const int first_off = p.taps > 1 ? 0 : p.tap_off[0];
+  for (int tap = 0; tap < ktaps; ++tap) {
+    const int off = p.taps > 1 ? p.tap_off[tap] : first_off + tap;
+    const float* xr = x_s + (halo + row + off) * C;
+    const float* wt = w_s + tap * Q * C * 4 + cq * 16;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + q * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 wv = *reinterpret_cast<const float4*>(wt + (q * C + j) * 4);
+        acc[j] = fmaf(xv.x, wv.x, acc[j]);
+        acc[j] = fmaf(xv.y, wv.y, acc[j]);
+        acc[j] = fmaf(xv.z, wv.z, acc[j]);
+        acc[j] = fmaf(xv.w, wv.w, acc[j]);
+      }
+    }
+  }
+  const int m = m0 + row;
+  if (m < p.M) {
+    float4 o = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (p.residual) {
+      const float4 r4 = *reinterpret_cast<const float4*>(p.residual + gemm_r_row(p, m) + cq * 4);
+      o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+    }
+    *reinterpret_cast<float4*>(p.C + gemm_c_row(p, m) + cq * 4) = o;
+  }
+}
+
+template <int C, int TR>
+void launch_cfg(const ConvBatch& b, int count, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SV_CUDA(cudaFuncSetAttribute(conv_small_kernel<C, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  launch_pdl(conv_small_kernel<C, TR>, dim3((b.p[0].M + TR - 1) / TR, 1, count), dim3(TR * C / 4), smem, st, b);
+}
+
+}  // namespace
+
+// Returns false when the problem is not one of the thin causal convs this kernel is for.
+bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st) {
+  const GemmParams& p0 = ps[0];
+  const int C = p0.N;
+  if (C != 16 && C != 32) return false;
+  const int TR = C == 16 ? 64 : 32;
+  ConvBatch b;
+  size_t smem = 0;
+  for (int i = 0; i < count; ++i) {
+    const GemmParams& p = ps[i];
+    const int kt = p.taps > 1 ? p.taps : p.K / C;
+    if (p.N != C || p.lda != C || p.a_row_step != 1 || p.prologue != PRO_SILU || p.act != ACT_NONE || p.gamma || p.accumulate ||
+        p.out_scale != 1.f || (p.taps > 1 ? p.K != C : p.K % C != 0) || kt < 1 || kt > MAX_TAPS || p.M != p0.M || p.M % TR != 0 ||
+        (p.seg_rows > 0 && p.seg_rows % TR != 0))
+      return false;
+    const int halo = -p.tap_off[0];
+    if (halo < 0) return false;
+    for (int t = 0; t < (p.taps > 1 ? p.taps : 1); ++t)
+      if (p.tap_off[t] > 0 || p.tap_off[t] < -halo) return false;
+    if (p.taps == 1 && p.tap_off[0] + kt - 1 > 0) return false;
+    smem = std::max(smem, ((size_t)kt * C * C + (size_t)(halo + TR) * C) * sizeof(float));
+    b.p[i] = p;
+  }
+  for (int i = count; i < 3; ++i) b.p[i] = ps[0];
+  if (smem > 96 * 1024) return false;
+  if (C == 16) launch_cfg<16, 64>(b, count, smem, st);
+  else launch_cfg<32, 32>(b, count, smem, st);
+  return true;
+}
+
+}  // namespace svanon

@@ -279,6 +279,8 @@ bool g_gemm_use_pipe = true;
 bool g_gemm_use_tc = true;
 bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pipe.cu
 bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st);     // gemm_tc.cu
+bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st);  // conv_small.cu
+bool g_use_conv_small = true;
 
 void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   SV_CHECK(count >= 1 && count <= 3, "gemm batch count");
@@ -295,6 +297,10 @@ void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   for (int i = count; i < 3; ++i) b.p[i] = ps[0];
   const GemmParams& p = ps[0];
   if (p.M <= 0 || p.N <= 0) return;
+  if (g_use_conv_small && launch_conv_small(ps, count, st)) {     // thin causal convs (HiFi-GAN levels with 16/32 channels)
+    SV_LAUNCHED();
+    return;
+  }
   if (g_gemm_use_tc && launch_gemm_tc(ps, count, st)) {         // tcgen05 3xTF32 (M >= 96, N >= 64)
     SV_LAUNCHED();
     return;

@@ -254,7 +254,9 @@ __global__ void fsq_encode_kernel(const float* __restrict__ z, const float* __re
   if (lane == 0) codes[((long long)(tok / T) * 8 + g) * T + (tok % T)] = idx;
 }
 
-// activation_post (SiLU) + conv_post (16 -> 1, k = 13, causal) + tanh, firefly.py:289-291.
+// activation_post (SiLU) + conv_post (16 -> 1, k = 13, causal) + tanh, firefly.py:289-291.  Four lanes share one
+// output sample (taps part, part+4, part+8, part+12) and combine with two shuffles: 4x more threads in flight for a
+// kernel that only has L = 2048 outputs per frame.
 __global__ void conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                  float* __restrict__ out, int L, int seg_rows, long long x_seg) {
   pdl_trigger();
@@ -262,19 +264,31 @@ __global__ void conv_post_kernel(const float* __restrict__ x, const float* __res
   __shared__ float ws[13 * 16];
   for (int i = threadIdx.x; i < 13 * 16; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= L) return;
-  float acc = b[0];
-  const float4* xr = reinterpret_cast<const float4*>(x + seg_row_off(t, seg_rows, x_seg, 16) - 12 * 16);
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = gid >> 2;
+  const int part = (int)(gid & 3);
+  float acc = 0.f;
+  if (t < L) {
+    const float* xr = x + seg_row_off(t, seg_rows, x_seg, 16) - 12 * 16;
 #pragma unroll
-  for (int j = 0; j < 13 * 4; ++j) {
-    float4 v = __ldg(xr + j);
-    v.x = v.x / (1.f + __expf(-v.x)); v.y = v.y / (1.f + __expf(-v.y));
-    v.z = v.z / (1.f + __expf(-v.z)); v.w = v.w / (1.f + __expf(-v.w));
-    acc = fmaf(v.x, ws[j * 4 + 0], acc); acc = fmaf(v.y, ws[j * 4 + 1], acc);
-    acc = fmaf(v.z, ws[j * 4 + 2], acc); acc = fmaf(v.w, ws[j * 4 + 3], acc);
+    for (int i = 0; i < 4; ++i) {
+      const int tap = part + 4 * i;
+      if (tap < 13) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(xr + tap * 16) + q);
+          v.x = __fdividef(v.x, 1.f + __expf(-v.x)); v.y = __fdividef(v.y, 1.f + __expf(-v.y));
+          v.z = __fdividef(v.z, 1.f + __expf(-v.z)); v.w = __fdividef(v.w, 1.f + __expf(-v.w));
+          const float* wp = ws + tap * 16 + q * 4;
+          acc = fmaf(v.x, wp[0], acc); acc = fmaf(v.y, wp[1], acc);
+          acc = fmaf(v.z, wp[2], acc); acc = fmaf(v.w, wp[3], acc);
+        }
+      }
+    }
   }
-  out[t] = tanhf(acc);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (t < L && part == 0) out[t] = tanhf(acc + b[0]);
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
@@ -420,7 +434,7 @@ void launch_fsq_encode(const float* z, const float* w, const float* b, int* code
 void launch_conv_post(const float* x, const float* w, const float* b, float* out, int L, cudaStream_t st, int seg_rows,
                       long long x_seg) {
   if (L <= 0) return;
-  launch_pdl(conv_post_kernel, dim3(blocks_for(L, 256)), dim3(256), 0, st, x, w, b, out, L, seg_rows, x_seg);
+  launch_pdl(conv_post_kernel, dim3(blocks_for((long long)L * 4, 256)), dim3(256), 0, st, x, w, b, out, L, seg_rows, x_seg);
   SV_LAUNCHED();
 }
 
