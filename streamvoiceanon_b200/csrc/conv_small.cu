@@ -7,6 +7,7 @@
 // weight tensor (<= 45 KB) in shared memory once, then every thread produces 4 output channels of one row from
 // registers.  Same GemmParams contract as gemm.cu (up to 3 problems per launch, streams side by side).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -20,15 +21,16 @@ struct ConvBatch {
 
 __device__ __forceinline__ float silu_acc(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
-// C channels in and out, TR output rows per CTA, 4 output channels per thread: blockDim = TR * C / 4.
+// C channels in and out, TR output rows per CTA.  A thread owns RB = 2 rows x 4 output channels {cq, cq+Q, cq+2Q, cq+3Q}
+// (strided, so that the Q threads of a row read CONSECUTIVE float4 weights: conflict-free); blockDim = TR/2 * C/4.
 template <int C, int TR>
-__global__ void __launch_bounds__(TR * C / 4) conv_small_kernel(const ConvBatch batch) {
+__global__ void __launch_bounds__(TR * C / 8) conv_small_kernel(const ConvBatch batch) {
   extern __shared__ __align__(16) float smem[];
   constexpr int Q = C / 4;                       // channel quads
   const GemmParams& p = batch.p[blockIdx.z];
   const int ktaps = p.taps > 1 ? p.taps : p.K / C;          // dilation 1: one "tap" of k*C overlapping columns
   const int halo = -p.tap_off[0];                           // the oldest row any tap reaches
-  float* w_s = smem;                                        // [ktaps][Q (ci quad)][C (co)][4]
+  float* w_s = smem;                                        // [ktaps][Q (ci quad)][C (co)][4 (ci)]
   float* x_s = smem + ktaps * C * C;                        // [halo + TR][C], SiLU applied
   const int tid = threadIdx.x;
   pdl_trigger();
@@ -48,36 +50,40 @@ __global__ void __launch_bounds__(TR * C / 4) conv_small_kernel(const ConvBatch 
     *reinterpret_cast<float4*>(x_s + r * C + q * 4) = v;
   }
   __syncthreads();
-  const int cq = tid % Q, row = tid / Q;                     // this thread: output channels cq*4 .. +3 of row m0 + row
-  float acc[4];
+  const int cq = tid % Q, rp = tid / Q;                      // rows m0 + 2*rp, +1; output channels cq + Q*j
+  float acc[2][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = p.bias ? __ldg(p.bias + cq * 4 + j) : 0.f;
+  for (int j = 0; j < 4; ++j) acc[0][j] = acc[1][j] = p.bias ? __ldg(p.bias + cq + Q * j) : 0.f;
   const int first_off = p.taps > 1 ? 0 : p.tap_off[0];
   for (int tap = 0; tap < ktaps; ++tap) {
     const int off = p.taps > 1 ? p.tap_off[tap] : first_off + tap;
-    const float* xr = x_s + (halo + row + off) * C;
-    const float* wt = w_s + tap * Q * C * 4 + cq * 16;
+    const float* xr = x_s + (halo + 2 * rp + off) * C;
+    const float* wt = w_s + tap * Q * C * 4 + cq * 4;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-      const float4 xv = *reinterpret_cast<const float4*>(xr + q * 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(xr + q * 4);
+      const float4 x1 = *reinterpret_cast<const float4*>(xr + C + q * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 wv = *reinterpret_cast<const float4*>(wt + (q * C + j) * 4);
-        acc[j] = fmaf(xv.x, wv.x, acc[j]);
-        acc[j] = fmaf(xv.y, wv.y, acc[j]);
-        acc[j] = fmaf(xv.z, wv.z, acc[j]);
-        acc[j] = fmaf(xv.w, wv.w, acc[j]);
+        const float4 wv = *reinterpret_cast<const float4*>(wt + (q * C + Q * j) * 4);
+        acc[0][j] = fmaf(x0.x, wv.x, acc[0][j]); acc[1][j] = fmaf(x1.x, wv.x, acc[1][j]);
+        acc[0][j] = fmaf(x0.y, wv.y, acc[0][j]); acc[1][j] = fmaf(x1.y, wv.y, acc[1][j]);
+        acc[0][j] = fmaf(x0.z, wv.z, acc[0][j]); acc[1][j] = fmaf(x1.z, wv.z, acc[1][j]);
+        acc[0][j] = fmaf(x0.w, wv.w, acc[0][j]); acc[1][j] = fmaf(x1.w, wv.w, acc[1][j]);
       }
     }
   }
-  const int m = m0 + row;
-  if (m < p.M) {
-    float4 o = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    if (p.residual) {
-      const float4 r4 = *reinterpret_cast<const float4*>(p.residual + gemm_r_row(p, m) + cq * 4);
-      o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int m = m0 + 2 * rp + r;
+    if (m >= p.M) continue;
+    const float* res = p.residual ? p.residual + gemm_r_row(p, m) : nullptr;
+    float* dst = p.C + gemm_c_row(p, m);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = cq + Q * j;
+      dst[co] = acc[r][j] + (res ? res[co] : 0.f);
     }
-    *reinterpret_cast<float4*>(p.C + gemm_c_row(p, m) + cq * 4) = o;
   }
 }
 
@@ -88,7 +94,7 @@ void launch_cfg(const ConvBatch& b, int count, size_t smem, cudaStream_t st) {
     SV_CUDA(cudaFuncSetAttribute(conv_small_kernel<C, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
-  launch_pdl(conv_small_kernel<C, TR>, dim3((b.p[0].M + TR - 1) / TR, 1, count), dim3(TR * C / 4), smem, st, b);
+  launch_pdl(conv_small_kernel<C, TR>, dim3((b.p[0].M + TR - 1) / TR, 1, count), dim3(TR * C / 8), smem, st, b);
 }
 
 }  // namespace
@@ -98,7 +104,12 @@ bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st) {
   const GemmParams& p0 = ps[0];
   const int C = p0.N;
   if (C != 16 && C != 32) return false;
-  const int TR = C == 16 ? 64 : 32;
+  const int TR = C == 16 ? 128 : 64;
+  static const long long max_m = [] {
+    const char* e = getenv("SVANON_CONV_SMALL_MAX_M");      // tuning knob: largest M that takes this kernel
+    return e ? atoll(e) : (1LL << 40);
+  }();
+  if (p0.M > max_m) return false;
   ConvBatch b;
   size_t smem = 0;
   for (int i = 0; i < count; ++i) {
@@ -118,8 +129,8 @@ bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st) {
   }
   for (int i = count; i < 3; ++i) b.p[i] = ps[0];
   if (smem > 96 * 1024) return false;
-  if (C == 16) launch_cfg<16, 64>(b, count, smem, st);
-  else launch_cfg<32, 32>(b, count, smem, st);
+  if (C == 16) launch_cfg<16, 128>(b, count, smem, st);
+  else launch_cfg<32, 64>(b, count, smem, st);
   return true;
 }
 
