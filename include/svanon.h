@@ -114,7 +114,7 @@ int svanon_ar_position(const svanon_stream* s); /* next free sequence position *
  * heads) of stream 0 of each launch; read them back with svanon_ar_read_debug (host pointers, may be NULL) */
 int svanon_ar_debug_logits(svanon_engine* e, int enable);
 /* GEMM back end of the encoder / prefill / vocoder projections (process-wide): 1 = fp32 on CUDA cores,
- * 2 (default) = tcgen05 tensor cores with a 3xTF32 split (fp32-grade products, accumulator in TMEM) for M >= 96, N >= 64,
+ * 2 (default) = tcgen05 tensor cores with a 3xTF32 split (fp32-grade products, accumulator in TMEM) for M >= 32, N >= 64,
  * 0 = the register double-buffered CUDA-core kernel only.  `svanon_debug_gemm` runs one C = act(A W^T + bias)
  * (A [M][K], W [N][K], row-major fp32, K % 16 == 0; act 0 none / 1 GELU) through the selected back end (tests). */
 int svanon_set_gemm_mode(int mode);
