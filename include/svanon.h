@@ -171,6 +171,15 @@ int svanon_stream_last_timing(svanon_stream* s, float* ms);
 int svanon_stream_history(svanon_stream* s, int64_t* src_content, int* n_src, int64_t* pred_codes, int* n_pred,
                           int cap);
 
+/* ---- host audio boundary ---------------------------------------------------------------
+ * Sample-rate conversion with torchaudio.functional.resample semantics (polyphase windowed sinc): the 16 kHz / device
+ * rate <-> 44.1 kHz step the reference does on the host (`librosa.load(path, sr=self.sr)`, evaluations/infer_arvc.py:
+ * 274-278; `torchaudio.functional.resample` in real-time-gui.py).  `kernel` [new][2*width + orig] is the filter bank for
+ * the gcd-reduced ratio orig:new (streamvoiceanon_b200.audio builds it with the torchaudio formula); output sample
+ * f*new + ph = sum_k kernel[ph][k] * wave[f*orig + k - width]; n_out <= ceil(new * n_in / orig). */
+int svanon_resample(svanon_engine* e, const float* wave, int64_t n_in, const float* kernel, int orig, int new_rate, int width,
+                    float* out, int64_t n_out, void* cuda_stream);
+
 /* ---- many concurrent streams in lock-step --------------------------------------------------------------------
  * The reference is strictly batch-1 (max_batch_size=1, evaluations/infer_arvc.py:56; `x.view(1, 1, -1)`,
  * modules/dual_ar_stream.py:544): N concurrent utterances are N sequential calls.  These entry points run the same

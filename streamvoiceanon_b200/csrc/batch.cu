@@ -99,6 +99,23 @@ int svanon_voc_encode(svanon_engine* e, const float* waves, int n_utt, int64_t n
   });
 }
 
+int svanon_resample(svanon_engine* e, const float* wave, int64_t n_in, const float* kernel, int orig, int nw, int width,
+                    float* out, int64_t n_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && wave && kernel && out, "null argument");
+    SV_CHECK(orig >= 1 && nw >= 1 && width >= 0 && n_in >= 1, "bad resampling ratio");
+    const int taps = 2 * width + orig;
+    const long long full = (n_in / orig + 1) * (long long)nw;
+    SV_CHECK(n_out >= 0 && n_out <= full, "n_out exceeds what the input yields (ceil(new * n_in / orig))");
+    Args a(e, stream, ((size_t)n_in + (size_t)nw * taps + (size_t)n_out) * 4 + 65536);
+    const float* x = a.in(wave, (size_t)n_in);
+    const float* k = a.in(kernel, (size_t)nw * taps);
+    float* o = a.out(out, (size_t)n_out);
+    launch_resample(x, n_in, k, orig, nw, width, taps, o, n_out, a.st);
+    a.finish();
+  });
+}
+
 int svanon_ar_decode_many(svanon_stream* const* streams, int n, const int64_t* content_ids, const float* noise,
                           int32_t* codes_out, void* stream) {
   return guarded([&] {

@@ -182,6 +182,8 @@ void launch_fsq_encode(const float* z /*[B*T][512]*/, const float* w /*[8][4][64
                        int* codes /*[B][8][T]*/, int B, int T, cudaStream_t st);
 void launch_conv_post(const float* x /*[L][16] with 12 margin rows*/, const float* w /*[13][16]*/, const float* b,
                       float* out, int L, cudaStream_t st, int seg_rows = 0, long long x_seg = 0);
+void launch_resample(const float* x, long long n_in, const float* kern /*[new][taps]*/, int orig, int nw, int width, int taps,
+                     float* out, long long n_out, cudaStream_t st);
 void launch_gather_rows(const float* table, const long long* idx, float* out, int rows, int C, long long out_ld,
                         cudaStream_t st);
 // out[t] = sum_i table[codes[i][t] + i*1000]  (BaseTransformer.embed)

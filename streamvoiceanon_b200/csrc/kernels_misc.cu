@@ -291,6 +291,29 @@ __global__ void conv_post_kernel(const float* __restrict__ x, const float* __res
   if (t < L && part == 0) out[t] = tanhf(acc + b[0]);
 }
 
+// Polyphase sinc resampler with torchaudio.functional.resample semantics (host audio boundary: 16 kHz / device rate <->
+// the model's 44.1 kHz, evaluations/infer_arvc.py:274-278): out[f*new + ph] = sum_k kernel[ph][k] * x[f*orig + k - width]
+// with zeros outside [0, n_in).  One thread per output sample; consecutive threads are consecutive phases of (mostly)
+// one input frame, so the input reads are warp-broadcasts and the kernel-matrix reads hit L1/L2 (new x taps floats).
+__global__ void resample_kernel(const float* __restrict__ x, long long n_in, const float* __restrict__ kern, int orig, int nw,
+                                int width, int taps, float* __restrict__ out, long long n_out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const long long f = i / nw;
+  const int ph = (int)(i - f * nw);
+  const float* kr = kern + (long long)ph * taps;
+  const long long x0 = f * orig - width;
+  float acc = 0.f;
+  for (int k = 0; k < taps; ++k) {
+    const long long xi = x0 + k;
+    const float xv = (xi >= 0 && xi < n_in) ? __ldg(x + xi) : 0.f;
+    acc = fmaf(__ldg(kr + k), xv, acc);
+  }
+  out[i] = acc;
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
                                    float* __restrict__ out, int C, long long out_ld) {
   pdl_trigger();
@@ -435,6 +458,13 @@ void launch_conv_post(const float* x, const float* w, const float* b, float* out
                       long long x_seg) {
   if (L <= 0) return;
   launch_pdl(conv_post_kernel, dim3(blocks_for((long long)L * 4, 256)), dim3(256), 0, st, x, w, b, out, L, seg_rows, x_seg);
+  SV_LAUNCHED();
+}
+
+void launch_resample(const float* x, long long n_in, const float* kern, int orig, int nw, int width, int taps, float* out,
+                     long long n_out, cudaStream_t st) {
+  if (n_out <= 0) return;
+  launch_pdl(resample_kernel, dim3(blocks_for(n_out, 256)), dim3(256), 0, st, x, n_in, kern, orig, nw, width, taps, out, n_out);
   SV_LAUNCHED();
 }
 
