@@ -9,7 +9,9 @@ import re
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libsvanon_b200.so"
+import os
+
+LIB_PATH = Path(os.environ["SVANON_LIB"]) if os.environ.get("SVANON_LIB") else PKG / "libsvanon_b200.so"   # tuning builds
 HEADER = PKG.parent / "include" / "svanon.h"
 
 MODEL_AR, MODEL_TOKENIZER, MODEL_VOCODER = 0, 1, 2

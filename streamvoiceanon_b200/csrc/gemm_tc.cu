@@ -104,7 +104,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 constexpr int TC_PRODUCER_WARPS = 16;              // warps 0-15: global -> registers -> hi/lo split -> swizzled tiles; epilogue
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
 constexpr int TC_THREADS = TC_PRODUCERS + 32;      // warp 16: MMA issuer (one elected lane)
-constexpr int TC_DEPTH = 4;                        // K-slabs a producer thread keeps in flight in registers
+constexpr int TC_DEPTH = 2;                        // K-slabs a producer thread keeps in flight in registers (2, 3 and 4
+                                                   // measure the same: the loop is not bound by load latency)
 
 __device__ __forceinline__ float4 ldg_nc(const float* p) {
   float4 r;
@@ -498,7 +499,17 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
     while (s < max_split && n_ctas * s * 2 <= 160 && min_slabs / (s * 2) >= 2) s *= 2;
     return s;
   };
-  if (ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 3>(b, count, 1, st);
+  static const int max_bn = [] {
+    const char* e = getenv("SVANON_TC_MAX_BN");         // tuning knob: widest CTA tile (64 / 128 / 256)
+    return e ? atoi(e) : 256;
+  }();
+  // The kernel is bound by shared-memory traffic (hi/lo tile stores + the MMAs' operand reads, ncu: L1/TEX 51 %, tensor
+  // pipe 26 %): a wider tile amortises the A tile over more MMA work.  128 x 256 when the grid still fills the GPU and
+  // the padded width does not waste more than 128 x 128 tiles would.
+  auto padded = [&](int bn) { return (long long)((p.N + bn - 1) / bn) * bn; };
+  if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107)
+    launch_tc_cfg<256, 2>(b, count, 1, st);
+  else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 3>(b, count, 1, st);
   else launch_tc_cfg<64, 4>(b, count, pick_split(ctas(64)), st);
   return true;
 }
