@@ -107,8 +107,11 @@ attention_kernel(const float* __restrict__ q, long long q_ld, const float* __res
 // CTA stages K and V of its head ONCE (66 KB) and its 16 warps then run one query each without any further block
 // barrier -- the tiled kernel above pays two barriers and one global round trip per 32 keys, which made it the single
 // slowest kernel of the window encode (26.7 us for 17 MFLOP).
-constexpr int SQW = 16;      // queries (warps) per CTA
+constexpr int SQW = 16;      // warps per CTA
 constexpr int SMAXK = 128;   // keys held in shared memory
+// QPW queries per warp: 1 spreads a single stream over many CTAs (latency); 8 makes one CTA own a whole (stream, head)
+// so that K/V are staged once instead of once per 16 queries (many streams: 4.5x less staging traffic).
+template <int QPW>
 __global__ void __launch_bounds__(SQW * 32)
 attention_short_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
                        long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
@@ -120,18 +123,15 @@ attention_short_kernel(const float* __restrict__ q, long long q_ld, const float*
   float (*Vs)[HEAD_DIM] = reinterpret_cast<float (*)[HEAD_DIM]>(att_smem + SMAXK * (HEAD_DIM + 1));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y;
-  const int bps = (nq + SQW - 1) / SQW;
+  constexpr int QPC = SQW * QPW;                            // queries per CTA
+  const int bps = (nq + QPC - 1) / QPC;
   const int seg = blockIdx.x / bps;
-  const int qi0 = (blockIdx.x - seg * bps) * SQW;
+  const int qi0 = (blockIdx.x - seg * bps) * QPC;
   q += (long long)seg * nq * q_ld;
   k += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
   v += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
   out += (long long)seg * nq * out_ld;
-  const int qi = qi0 + warp;
-  const bool active = qi < nq;
-  const int pos = qpos0 + qi;
-  const int lo = max(0, pos - window + 1);
-  const int k_hi = qpos0 + min(qi0 + SQW, nq) - 1;          // newest key any query of this CTA needs (inclusive)
+  const int k_hi = qpos0 + min(qi0 + QPC, nq) - 1;          // newest key any query of this CTA needs (inclusive)
   for (int i = threadIdx.x; i < (k_hi + 1) * (HEAD_DIM / 4); i += SQW * 32) {
     const int key = i / (HEAD_DIM / 4), c = (i % (HEAD_DIM / 4)) * 4;
     const float4 kv = __ldg(reinterpret_cast<const float4*>(k + (long long)key * kv_row_stride + c));
@@ -139,14 +139,18 @@ attention_short_kernel(const float* __restrict__ q, long long q_ld, const float*
     Ks[key][c] = kv.x; Ks[key][c + 1] = kv.y; Ks[key][c + 2] = kv.z; Ks[key][c + 3] = kv.w;
     *reinterpret_cast<float4*>(&Vs[key][c]) = vv;
   }
+  __syncthreads();
+  for (int jq = 0; jq < QPW; ++jq) {
+  const int qi = qi0 + warp + SQW * jq;                     // interleaved: every warp gets early and late queries
+  if (qi >= nq) break;
+  const int pos = qpos0 + qi;
+  const int lo = max(0, pos - window + 1);
   float qr[HEAD_DIM];
-  if (active) {
+  {
     const float* qp = q + (long long)qi * q_ld + h * HEAD_DIM;
 #pragma unroll
     for (int d = 0; d < HEAD_DIM; ++d) qr[d] = __ldg(qp + d) * 0.125f;   // 1/sqrt(64)
   }
-  __syncthreads();
-  if (!active) return;
   float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;
   for (int kt = (lo / KT) * KT; kt <= pos; kt += KT) {
     const int kp = kt + lane;
@@ -182,6 +186,7 @@ attention_short_kernel(const float* __restrict__ q, long long q_ld, const float*
   const float inv = 1.f / l;
   op[lane] = acc0 * inv;
   op[lane + 32] = acc1 * inv;
+  }
 }
 
 __global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float* __restrict__ kc, float* __restrict__ vc,
@@ -210,11 +215,16 @@ void launch_attention(const float* q, long long q_ld, const float* k, const floa
     constexpr size_t SMEM = (size_t)SMAXK * (2 * HEAD_DIM + 1) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-      SV_CUDA(cudaFuncSetAttribute(attention_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+      SV_CUDA(cudaFuncSetAttribute(attention_short_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+      SV_CUDA(cudaFuncSetAttribute(attention_short_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
       configured = true;
     }
-    launch_pdl(attention_short_kernel, dim3((nq + SQW - 1) / SQW * nseg, heads), dim3(SQW * 32), SMEM, st, q, q_ld, k, v,
-               kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window);
+    if (nseg >= 8)
+      launch_pdl(attention_short_kernel<8>, dim3((nq + SQW * 8 - 1) / (SQW * 8) * nseg, heads), dim3(SQW * 32), SMEM, st, q, q_ld,
+                 k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window);
+    else
+      launch_pdl(attention_short_kernel<1>, dim3((nq + SQW - 1) / SQW * nseg, heads), dim3(SQW * 32), SMEM, st, q, q_ld, k, v,
+                 kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window);
     SV_LAUNCHED();
     return;
   }

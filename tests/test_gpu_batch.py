@@ -27,6 +27,18 @@ def test_encode_batch_equals_single(models):
         assert torch.equal(one[0, 0], both[0, i]), i
 
 
+def test_encode_batch_many_rows(models):
+    """>= 8 rows switch the window attention to one CTA per (stream, head); 33 frames: ragged last query block."""
+    _, tok, _ = models
+    n = 33 * 2048
+    wavs = torch.stack([synth.synth_audio_44k(3200 + i, 1.7)[:n] for i in range(9)]).cuda()
+    lens = torch.LongTensor([n] * 9).cuda()
+    both, _ = tok.encode(wavs, lens)
+    for i in (0, 4, 8):
+        one, _ = tok.encode(wavs[i:i + 1].contiguous(), lens[:1])
+        assert torch.equal(one[0, 0], both[0, i]), i
+
+
 def test_encode_batch_streaming_window_vs_reference(models, gold):
     """Row 1 of a 2-row batched call is the reference's 128-frame streaming-window fixture."""
     _, tok, _ = models

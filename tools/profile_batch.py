@@ -1,0 +1,18 @@
+"""A few lock-step batch steps for `ncu --metrics gpu__time_duration.sum` (launch list of the many-stream path)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.argv = [sys.argv[0]] + (sys.argv[1:] or ["48"])
+import tools.bench_batch as bb  # noqa: E402
+
+if __name__ == "__main__":
+    from streamvoiceanon_b200 import ARVCWrapper, ContentTokenizer, Vocoder, synth
+    ar = ARVCWrapper()
+    ar.setup_caches(max_batch_size=1, max_seq_len=2048, dtype=torch.float16)
+    ar.load_state_dict(synth.make_ar_state_dict(1234), strict=False)
+    ContentTokenizer().load_state_dict(synth.make_tokenizer_state_dict(1234), strict=False)
+    Vocoder().load_state_dict(synth.make_vocoder_state_dict(1234), strict=False)
+    print(bb.run(int(sys.argv[1]), steps=1, warm=3))
