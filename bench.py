@@ -191,6 +191,40 @@ def concurrent_sweep(tok, counts, steps=10, warm=3):
     return out
 
 
+def gemm_roofline(peaks):
+    """Tensor-pipe roofline of the dense-projection GEMM kernel (gemm_tc.cu) on the many-stream encoder MLP shape
+    (M = 16384 rows = 32 streams x 512, N = 2048, K = 512, +bias, GELU), timed live with CUDA events.  Every fp32-grade
+    product costs three TF32 MMAs, so `achieved` counts 3 x 2MNK TF32 flops; `peak` = half the measured dense bf16
+    throughput of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate on B200), else half the nominal 2250."""
+    import ctypes as C
+    from streamvoiceanon_b200 import _lib
+    from streamvoiceanon_b200.engine import Engine, ptr
+    eng, lib = Engine.get(torch.cuda.current_device()), _lib.load()
+    M, N, K = 16384, 2048, 512
+    A = torch.randn(M, K, device="cuda")
+    Ws = [torch.randn(N, K, device="cuda") for _ in range(8)]
+    b = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    for i in range(5):
+        _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(Ws[i % 8]), ptr(b), ptr(out), M, N, K, 1, None))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 40
+    e0.record()
+    for i in range(n):
+        _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(Ws[i % 8]), ptr(b), ptr(out), M, N, K, 1, None))
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / n * 1e3
+    fp32_tflops = 2.0 * M * N * K / us / 1e6
+    bf16 = peaks.get("bf16_tflops") or peaks.get("bf16_tflops_sustained")        # kernel timed alone: the burst figure
+    peak, src = (bf16 / 2, "0.5 x measured dense bf16 burst (MEASURED_PEAKS.json)") if bf16 else (1125.0, "0.5 x nominal 2250 bf16")
+    return {"kernel": "gemm_tc_kernel<256,2> (tcgen05 3xTF32, 128x256 tile)", "bound": "tensor", "shape": [M, N, K],
+            "launch_us": us, "fp32_equivalent_tflops": fp32_tflops, "achieved": 3 * fp32_tflops, "peak": peak,
+            "unit": "TFLOP/s", "frac": 3 * fp32_tflops / peak, "peak_source": src,
+            "traffic": None, "note": "ncu (profiles/r1h_gemm_big_ncu_details.txt, 128x128 tile): tensor pipe active 26 % of peak "
+            "sustained; the limiter is shared-memory traffic of the hi/lo operand split"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -333,6 +367,8 @@ def run_engine(args):
                      "algorithmic_bytes_per_launch": ar_bytes, "launch_ms": ar_ms, "s_valid": s_valid},
         "clocks": clocks,
     }
+    if world == 1:
+        line["roofline_gemm"] = gemm_roofline(peaks)
     counts = [int(x) for x in args.concurrent.split(",") if x.strip()] if world == 1 else []
     if counts:
         sess.close()
