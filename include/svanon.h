@@ -161,7 +161,9 @@ int svanon_stream_set_vocoder_mode(svanon_stream* s, int incremental);
  * 40 + chunk frames go through the conv stack again (the first ones see the window-start zero padding exactly as in
  * the reference's recompute, the last ones contain the new frames), the attention transformer then runs over the
  * whole window as in the reference.  Same function of the same samples as 0 = re-encode the whole window every chunk
- * (evaluations/infer_arvc.py:495-508); used when encode_window_frames >= 2 * (40 + chunk) + 8. */
+ * (evaluations/infer_arvc.py:495-508); used when encode_window_frames >= 2 * (40 + chunk) + 8.  With >= 8 streams side by
+ * side (or mode 2: always) the newest frames do not take a 41-frame span either: they continue from PER-LAYER conv
+ * history (the newest 6 rows of every causal-conv input of the stack), 4 mel rows per frame. */
 int svanon_stream_set_encoder_mode(svanon_stream* s, int incremental);
 /* per-stage device time (CUDA events on the launching stream) of the last non-warm-up chunk:
  * ms[0] = E (window encode), ms[1] = A (decode steps), ms[2] = V (vocoder) */

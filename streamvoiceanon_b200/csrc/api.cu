@@ -533,7 +533,9 @@ int svanon_stream_set_vocoder_mode(svanon_stream* sh, int incremental) {
 int svanon_stream_set_encoder_mode(svanon_stream* sh, int incremental) {
   return guarded([&] {
     SV_CHECK(sh, "null stream");
+    SV_CHECK(incremental >= 0 && incremental <= 2, "encoder mode: 0 full re-encode, 1 ring-buffer state (auto), 2 + conv history");
     sh->st.enc_state.enabled = incremental != 0;
+    sh->st.enc_state.tail_hist_min_streams = incremental == 2 ? 1 : 8;
     sh->st.enc_state.valid = false;
   });
 }

@@ -332,7 +332,9 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
 int svanon_batch_set_encoder_mode(svanon_batch* b, int incremental) {
   return guarded([&] {
     SV_CHECK(b, "null batch");
+    SV_CHECK(incremental >= 0 && incremental <= 2, "encoder mode: 0 full re-encode, 1 ring-buffer state (auto), 2 + conv history");
     b->enc_state.enabled = incremental != 0;
+    b->enc_state.tail_hist_min_streams = incremental == 2 ? 1 : 8;
     b->enc_state.valid = false;
   });
 }

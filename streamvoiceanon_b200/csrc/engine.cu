@@ -442,6 +442,57 @@ void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float
 }
 
 // ------------------------------------------------------------------------------------------ stage E
+namespace {
+// One causal-conv input buffer [6 margin rows | T rows][C] per stream (stride seg), history hist [B][6][C].
+// mode 2: margin <- hist (the left context of this step), then hist <- newest 6 rows of [hist | rows];
+// mode 1: margin stays zero, hist <- newest 6 rows of [zeros | rows].  grid (ceil(C/128), B).
+__global__ void conv_hist_kernel(float* __restrict__ buf, long long seg, float* __restrict__ hist, int T, int C, int mode) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float* b = buf + blockIdx.y * seg;                 // points at the first margin row
+  float* h = hist + (long long)blockIdx.y * 6 * C;
+  float old[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) old[r] = (mode == 2) ? h[r * C + c] : 0.f;
+  if (mode == 2) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) b[(long long)r * C + c] = old[r];
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int src = T + r;                           // row index in [hist(6) | rows(T)]
+    h[r * C + c] = src < 6 ? old[src] : b[(long long)src * C + c];
+  }
+}
+
+void launch_conv_hist(float* buf_margin, long long seg, float* hist, int B, int T, int C, int mode, cudaStream_t st) {
+  launch_pdl(conv_hist_kernel, dim3((C + 127) / 128, B), dim3(128), 0, st, buf_margin, seg, hist, T, C, mode);
+  SV_LAUNCHED();
+}
+}  // namespace
+
+void ConvStackHist::alloc(int n) {
+  if (arena && B == n) return;
+  if (arena) cudaFree(arena);
+  arena = nullptr;
+  const int dims[4] = {128, 256, 384, 512};
+  const int depths[4] = {3, 3, 9, 3};
+  size_t total = (size_t)n * 6 * N_MELS;
+  for (int s = 0; s < 4; ++s) total += (size_t)n * 6 * dims[s] * depths[s];
+  total += (size_t)n * 6 * 512 * 2;
+  SV_CUDA(cudaMalloc(&arena, total * sizeof(float)));
+  SV_CUDA(cudaMemset(arena, 0, total * sizeof(float)));
+  float* p = arena;
+  mel = p; p += (size_t)n * 6 * N_MELS;
+  int j = 0;
+  for (int s = 0; s < 4; ++s)
+    for (int d = 0; d < depths[s]; ++d) { blk[j++] = p; p += (size_t)n * 6 * dims[s]; }
+  for (int d = 0; d < 2; ++d) { blk[j++] = p; p += (size_t)n * 6 * 512; }
+  B = n;
+}
+
 static size_t enc_ws_floats(int B, long long n) { return ((size_t)(n / HOP) * 14000 + (size_t)n) * B; }
 
 // FireflyArchitecture.encode (firefly_encoder.py:553-566) in two halves.
@@ -451,8 +502,10 @@ static size_t enc_ws_floats(int B, long long n) { return ((size_t)(n / HOP) * 14
 // -> xt [NS][n/2048][512].  Streams never mix: every causal conv reads its own segment's zero margin; the GEMMs simply
 // see NS times more rows.  Workspace comes from `ws` (caller has sized and reset it).
 void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const long long* pitch, int nsrc, int per_src,
-                            long long n, float* xt, cudaStream_t st) {
+                            long long n, float* xt, cudaStream_t st, ConvStackHist* hist, int hist_mode) {
   SV_CHECK(w.ready && dft_w && fb_t, "encoder weights not finalized");
+  SV_CHECK(hist_mode == 0 || (hist && hist->B == nsrc * per_src), "conv history does not match the stream count");
+  const bool cont = hist_mode == 2;        // continuation: left context comes from the history, not from zeros
   const int B = nsrc * per_src;
   const int T = (int)(n / HOP);
   const int T2 = T / 2, S = T2 / 2;
@@ -462,10 +515,13 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
   // 1. left-pad win-hop zeros (spectrogram.py:37-45) and take frames as overlapping GEMM rows (lda = hop)
   const long long wseg = N_FFT - HOP + n;
   float* wpad = ws.alloc_f(wseg * B);
-  launch_fill(wpad, N_FFT - HOP, 0.f, st, B, wseg);
-  for (int i = 0; i < nsrc; ++i)
-    SV_CUDA(cudaMemcpy2DAsync(wpad + (long long)i * per_src * wseg + (N_FFT - HOP), (size_t)wseg * sizeof(float), src[i],
-                              (size_t)pitch[i] * sizeof(float), (size_t)n * sizeof(float), per_src, cudaMemcpyDeviceToDevice, st));
+  if (!cont) launch_fill(wpad, N_FFT - HOP, 0.f, st, B, wseg);
+  for (int i = 0; i < nsrc; ++i) {
+    const int lead = cont ? (N_FFT - HOP) : 0;          // continuation: the 1536 samples in front of the new ones are real
+    SV_CUDA(cudaMemcpy2DAsync(wpad + (long long)i * per_src * wseg + (N_FFT - HOP) - lead, (size_t)wseg * sizeof(float),
+                              src[i] - lead, (size_t)pitch[i] * sizeof(float), (size_t)(n + lead) * sizeof(float), per_src,
+                              cudaMemcpyDeviceToDevice, st));
+  }
   const int SPEC_LD = 2052;
   float* spec = ws.alloc_f((long long)BT * SPEC_LD);
   {
@@ -479,7 +535,7 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
   // 2. mel filterbank + log(clamp(., 1e-5))  (spectrogram.py:108-130); 6 zero rows in front for the causal stem
   const long long mel_seg = (long long)(MARG + T) * N_MELS;
   float* mel_buf = ws.alloc_f(mel_seg * B);
-  launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st, B, mel_seg);
+  if (!cont) launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st, B, mel_seg);
   float* mel = mel_buf + MARG * N_MELS;
   {
     GemmParams p;
@@ -488,6 +544,8 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     p.seg_rows = segT; p.a_seg = (long long)T * N_FREQ_PAD; p.c_seg = mel_seg;
     launch_gemm(p, st);
   }
+  if (hist_mode) launch_conv_hist(mel_buf, mel_seg, hist->mel, B, T, N_MELS, hist_mode, st);
+  int blk_idx = 0;
 
   // 3. ConvNeXtEncoder (firefly.py:506-517)
   const int dims[4] = {128, 256, 384, 512};
@@ -499,7 +557,7 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     const int C = dims[s];
     const long long xs = (long long)(MARG + T) * C;
     float* xb = ws.alloc_f(xs * B);
-    launch_fill(xb, (long long)MARG * C, 0.f, st, B, xs);
+    if (!cont) launch_fill(xb, (long long)MARG * C, 0.f, st, B, xs);
     float* xn = xb + MARG * C;
     if (s == 0) {
       GemmParams p;   // stem: causal conv k=7 as one GEMM over 7 overlapping rows
@@ -518,7 +576,11 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     }
     x = xn;
     x_seg = xs;
-    for (auto& blk : w.blocks[s]) convnext(blk, x, BT, tmp, hid, st, nullptr, segT, x_seg, 0);
+    for (auto& blk : w.blocks[s]) {
+      if (hist_mode) launch_conv_hist(xb, xs, hist->blk[blk_idx], B, T, C, hist_mode, st);
+      ++blk_idx;
+      convnext(blk, x, BT, tmp, hid, st, nullptr, segT, x_seg, 0);
+    }
   }
   float* feat = ws.alloc_f((long long)BT * 512);
   launch_layernorm(x, feat, w.bb_norm_w, w.bb_norm_b, BT, 512, 1e-6f, st, segT, x_seg, (long long)T * 512);
@@ -530,13 +592,14 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     const int r2 = rows / 2;
     const long long ds = (long long)(MARG + r2) * 512;
     float* db = ws.alloc_f(ds * B);
-    launch_fill(db, (long long)MARG * 512, 0.f, st, B, ds);
+    if (!cont) launch_fill(db, (long long)MARG * 512, 0.f, st, B, ds);
     float* dn = db + MARG * 512;
     GemmParams p;
     p.A = cur; p.W = w.down_w[i]; p.C = dn; p.bias = w.down_b[i]; p.M = B * r2; p.N = 512; p.K = 1024; p.lda = 512;
     p.a_row_step = 2; p.ldc = 512;
     p.seg_rows = B > 1 ? r2 : 0; p.a_seg = cur_seg; p.c_seg = ds;
     launch_gemm(p, st);
+    if (hist_mode) launch_conv_hist(db, ds, hist->blk[ConvStackHist::N_BLK - 2 + i], B, r2, 512, hist_mode, st);
     // the second block writes its result straight into the plain output buffer
     convnext(w.down_block[i], dn, B * r2, tmp, hid, st, i == 1 ? xt : nullptr, B > 1 ? r2 : 0, ds, (long long)r2 * 512);
     cur = dn;
@@ -631,7 +694,6 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
   SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
   const long long nw = (long long)S * SAMPLES_PER_FRAME;
   const int Ls = ENC_RF + c;
-  const bool incremental = state.valid && state.B == B && state.S == S && S >= 2 * Ls + 8;
   if (state.B != B || state.S != S || !state.xt[0]) {
     for (auto& p : state.xt) {
       if (p) cudaFree(p);
@@ -640,11 +702,36 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
     }
     state.B = B; state.S = S; state.cur = 0; state.valid = false;
   }
+  const bool incremental = state.valid && S >= 2 * Ls + 8;
+  // Many streams: the newest frames continue from per-layer conv history (4 mel rows per frame instead of a 41-frame
+  // span); few streams: the tail span rides in the same launches as the head span, which is faster than ~120 more
+  // (tiny) launches.
+  const bool use_hist = state.tail_hist_min_streams > 0 && B >= state.tail_hist_min_streams && S >= 2 * Ls + 8;
+  if (!state.valid) state.hist_valid = false;
   float* xt_state = state.xt[state.cur ^ 1];
-  if (!incremental) {
+  if (!incremental || (use_hist && !state.hist_valid)) {
     ws.ensure((enc_ws_floats(B, nw) + (size_t)B * S * ENC_DIM + (4u << 20)) * sizeof(float));
     ws.reset();
-    enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nw, xt_state, st);
+    if (use_hist) state.hist.alloc(B);
+    enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nw, xt_state, st, use_hist ? &state.hist : nullptr, use_hist ? 1 : 0);
+    state.hist_valid = use_hist;
+  } else if (use_hist) {
+    const long long nh = (long long)Ls * SAMPLES_PER_FRAME, nt = (long long)c * SAMPLES_PER_FRAME;
+    ws.ensure((enc_ws_floats(B, nh) + enc_ws_floats(B, nt) + enc_ws_floats(B, nw) / 3 + (size_t)(2 * B * Ls + B * S) * ENC_DIM +
+               (4u << 20)) * sizeof(float));
+    ws.reset();
+    float* spans = ws.alloc_f((long long)2 * B * Ls * ENC_DIM);          // [head B x Ls | tail B x Ls (last c rows used)]
+    enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nh, spans, st);        // window start: zero left context
+    float* tail = ws.alloc_f((long long)B * c * ENC_DIM);
+    const float* tsrc = wave_ring + (nw - nt);
+    enc_conv_stack(tok_cs, &tsrc, &nw, 1, B, nt, tail, st, &state.hist, 2);
+    // place the c new tokens where the assemble kernel expects the end of a tail span
+    SV_CUDA(cudaMemcpy2DAsync(spans + ((long long)B * Ls + (Ls - c)) * ENC_DIM, (size_t)Ls * ENC_DIM * sizeof(float), tail,
+                              (size_t)c * ENC_DIM * sizeof(float), (size_t)c * ENC_DIM * sizeof(float), B,
+                              cudaMemcpyDeviceToDevice, st));
+    launch_pdl(enc_assemble_kernel, dim3(S, B), dim3(128), 0, st, (const float*)spans, (const float*)state.xt[state.cur],
+               xt_state, B, S, Ls, ENC_RF, c);
+    SV_LAUNCHED();
   } else {
     const long long ns = (long long)Ls * SAMPLES_PER_FRAME;
     ws.ensure((enc_ws_floats(2 * B, ns) + enc_ws_floats(B, nw) / 3 + (size_t)(2 * B * Ls + B * S) * ENC_DIM + (4u << 20)) *

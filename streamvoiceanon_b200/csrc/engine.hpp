@@ -133,6 +133,20 @@ struct ArBatchWork {
 // section 8a-E) plus one frame of slack.
 constexpr int ENC_RF = 40;
 
+// Causal-conv history of the tokenizer's conv stack for B streams side by side: the newest 6 rows of every buffer a
+// k = 7 causal conv reads (the mel rows in front of the stem, the input of each of the 18 + 2 ConvNeXt blocks).
+struct ConvStackHist {
+  static constexpr int N_BLK = 20;
+  float* arena = nullptr;
+  float* mel = nullptr;                 // [B][6][160]
+  float* blk[N_BLK] = {};               // [B][6][C_j]
+  int B = 0;
+  void alloc(int n_streams);
+  ~ConvStackHist() {
+    if (arena) cudaFree(arena);
+  }
+};
+
 // Ring-buffer state of the streaming window encoder (Engine::enc_window_step): the transformer inputs of the last
 // window, for B streams side by side.
 struct EncWindowState {
@@ -140,6 +154,9 @@ struct EncWindowState {
   int cur = 0, B = 0, S = 0;
   bool valid = false;
   bool enabled = true;
+  ConvStackHist hist;                  // per-layer conv history of the newest frames (many-stream mode)
+  bool hist_valid = false;
+  int tail_hist_min_streams = 8;       // use the conv history for the newest frames from this many streams (0: never)
   ~EncWindowState() {
     for (auto p : xt)
       if (p) cudaFree(p);
@@ -251,8 +268,11 @@ struct Engine {
   // stage drivers (all device pointers, stream-ordered, no host sync)
   int enc_num_ids(long long n_samples) const { return (int)(((n_samples / HOP) / 2) / 2); }
   void enc_encode(const float* wave_dev /*[B][n]*/, int B, long long n_samples, long long* ids_dev /*[B][S]*/, cudaStream_t st);
+  // hist_mode 0: zero left context (a window / utterance start); 1: the same, and the newest 6 rows of every causal
+  // conv input are captured into `hist`; 2: left context = `hist` (continuation of the streams captured there: the wave
+  // pointers must have 1536 real samples in front), `hist` is advanced
   void enc_conv_stack(const ConvStackW& w, const float* const* src, const long long* pitch, int nsrc, int per_src,
-                      long long n, float* xt, cudaStream_t st);
+                      long long n, float* xt, cudaStream_t st, ConvStackHist* hist = nullptr, int hist_mode = 0);
   void pack_conv_stack(int model, ConvStackW& cs);
   void build_spectrogram_consts(int model);
   // FireflyArchitecture.encode of the vocoder (firefly.py:561-574): wave [B][n] -> codec ids int32 [B][8][n/2048]

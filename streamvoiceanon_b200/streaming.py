@@ -91,9 +91,10 @@ class StreamSession:
         """True (default): incremental vocoder; False: recompute the decode window every chunk like the reference."""
         _lib.check(self._engine.lib.svanon_stream_set_vocoder_mode(self._h, int(incremental)))
 
-    def set_encoder_mode(self, incremental: bool = True):
-        """True (default): keep the conv-stack outputs of the window between chunks (ring-buffer state); False:
-        re-encode the whole window every chunk like the reference.  Same result."""
+    def set_encoder_mode(self, incremental=True):
+        """True / 1 (default): keep the conv-stack outputs of the window between chunks (ring-buffer state); False / 0:
+        re-encode the whole window every chunk like the reference; 2: additionally continue the newest frames from
+        per-layer conv history (what batches of >= 8 streams do on their own).  Same result."""
         _lib.check(self._engine.lib.svanon_stream_set_encoder_mode(self._h, int(incremental)))
 
     def set_timing(self, enable: bool = True):
@@ -176,7 +177,7 @@ class BatchSession:
                                                                C.c_void_p(_cuda_stream_ptr())))
         return out
 
-    def set_encoder_mode(self, incremental: bool = True):
+    def set_encoder_mode(self, incremental=True):
         _lib.check(self._engine.lib.svanon_batch_set_encoder_mode(self._h, int(incremental)))
 
     def set_timing(self, enable: bool = True):

@@ -115,8 +115,8 @@ def _session(inp, tape_fn, delay):
     return sess
 
 
-@pytest.mark.parametrize("n,chunk,ar_path", [(3, 1, 0), (2, 2, 1), (2, 1, 0)])
-def test_batch_loop_equals_single_sessions(models, tape, n, chunk, ar_path):
+@pytest.mark.parametrize("n,chunk,ar_path,enc_mode", [(3, 1, 0, 1), (2, 2, 1, 1), (2, 1, 0, 1)])
+def test_batch_loop_equals_single_sessions(models, tape, n, chunk, ar_path, enc_mode):
     """N streams with different prompts (lengths 26, 31, ...), sources and noise tapes, small windows so that the
     streams re-prompt at DIFFERENT chunks (stream 0 after 9 frames, stream 1 after 4, stream 2 at once): ids bit-exact and waveform equal to fp32 rounding vs each stream alone."""
     from streamvoiceanon_b200 import BatchSession
@@ -152,9 +152,11 @@ def test_batch_loop_equals_single_sessions(models, tape, n, chunk, ar_path):
         s.close()
 
 
-def test_batch_loop_vs_reference_fixture(models, gold, tape):
+@pytest.mark.parametrize("enc_mode", [1, 2])
+def test_batch_loop_vs_reference_fixture(models, gold, tape, enc_mode):
     """Stream 0 of a 2-stream batch (many-stream decode kernels forced) reproduces the UNMODIFIED reference's
-    process_one_chunk run with CLI-default windows (tests/golden/stream_default.npz)."""
+    process_one_chunk run with CLI-default windows (tests/golden/stream_default.npz); enc_mode 1 = ring-buffer
+    encoder state with a tail span, 2 = newest frames from per-layer conv history."""
     from streamvoiceanon_b200 import BatchSession, StreamSession
     _, tok, _ = models
     g = gold("stream_default")
@@ -173,6 +175,7 @@ def test_batch_loop_vs_reference_fixture(models, gold, tape):
     batch.setup(int(g["encode_window_frames"]), int(g["decode_window_frames"]), int(g["max_seq_frames"]),
                 int(g["buffer_frames"]), 1)
     batch.set_ar_path(1)
+    batch.set_encoder_mode(enc_mode)
     src = synth.synth_audio_44k(int(g["src_seed"]), 1.5)[: n_chunks * 2048].view(n_chunks, 2048)
     waves = torch.cat([batch.process_chunk(torch.stack([src[i], other[4][i]]).cuda())[0].cpu() for i in range(n_chunks)])
     src_hist, pred_hist = s0.history()
@@ -181,6 +184,36 @@ def test_batch_loop_vs_reference_fixture(models, gold, tape):
     mse = float(((waves.numpy() - g["wave"]) ** 2).mean())
     assert mse < WAVE_MSE_TOL, mse
     batch.close(); s0.close(); s1.close()
+
+
+def test_batch_of_nine_default_windows(models, tape):
+    """9 streams, CLI-default windows: the batch switches on its own to one attention CTA per (stream, head), the
+    many-stream decode kernels and the per-layer conv history for the newest encoder frames.  Streams 0 and 8 against
+    the same streams run alone: ids bit-exact, waveform to fp32 rounding."""
+    from streamvoiceanon_b200 import BatchSession
+    _, tok, _ = models
+    n, n_chunks = 9, 10
+    cfg = dict(encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=1)
+    inputs = [_stream_inputs(tok, 20 + b, 70 + 3 * b, n_chunks, 1) for b in range(n)]
+    singles = {}
+    for b in (0, 8):
+        sess = _session(inputs[b], tape(7700 + b), 2)
+        sess.setup(**cfg)
+        waves = torch.cat([sess.process_chunk(inputs[b][4][i].cuda()).cpu() for i in range(n_chunks)])
+        singles[b] = (*sess.history(), waves)
+        sess.close()
+    sessions = [_session(inp, tape(7700 + b), 2) for b, inp in enumerate(inputs)]
+    batch = BatchSession(sessions)
+    batch.setup(**cfg)
+    waves = torch.cat([batch.process_chunk(torch.stack([inp[4][i] for inp in inputs]).cuda()).cpu() for i in range(n_chunks)], dim=1)
+    for b in (0, 8):
+        src_hist, pred_hist = sessions[b].history()
+        assert torch.equal(src_hist, singles[b][0]), b
+        assert torch.equal(pred_hist, singles[b][1]), b
+        assert float(((waves[b] - singles[b][2]) ** 2).mean()) < 1e-10, b
+    batch.close()
+    for s in sessions:
+        s.close()
 
 
 def test_batch_errors(models, tape):
