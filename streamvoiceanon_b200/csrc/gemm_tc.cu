@@ -35,16 +35,8 @@ struct TcBatch {
   int split;
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ int swz(int row, int c) { return row * TK + ((c ^ (row & 7)) << 2); }
 
@@ -97,10 +89,6 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 constexpr int TC_PRODUCER_WARPS = 16;              // warps 0-15: global -> registers -> hi/lo split -> swizzled tiles; epilogue
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
 constexpr int TC_THREADS = TC_PRODUCERS + 32;      // warp 16: MMA issuer (one elected lane)
@@ -114,16 +102,6 @@ __device__ __forceinline__ float4 ldg_nc(const float* p) {
   return r;
 }
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
-__device__ __forceinline__ void split_store(float* hi_dst, float* lo_dst, float4 v) {
-  float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-  *reinterpret_cast<float4*>(hi_dst) = h;
-  *reinterpret_cast<float4*>(lo_dst) = l;
-}
-
 // Warp-specialised.  16 producer warps stream the K-slabs: every thread keeps TC_DEPTH slabs of its own 16-byte chunks
 // in flight in REGISTERS (plain 128-bit no-allocate loads; the weight chunks of the first slabs are requested before
 // griddepcontrol.wait), splits a slab into hi/lo TF32 terms straight into the 128-byte-swizzled tiles of a free
