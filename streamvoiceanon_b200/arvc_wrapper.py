@@ -120,7 +120,7 @@ class ARVCWrapper:
         `dtype` is accepted for signature compatibility (the parity build keeps K/V in fp32)."""
         if max_batch_size != 1:
             raise ValueError("ARVCWrapper is a single-stream surface (reference: max_batch_size=1, infer_arvc.py:56); "
-                             "use streamvoiceanon_b200.streaming.StreamBatch for concurrent streams")
+                             "use streamvoiceanon_b200.BatchSession for concurrent streams")
         self._max_seq_len = int(max_seq_len)
         self._new_stream()
 

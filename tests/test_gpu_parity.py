@@ -432,3 +432,37 @@ def test_vocoder_encode_batched_and_ragged_vs_oracle(models, weights):
     assert np.array_equal(ragged[1, :, :7].cpu().numpy(), want[1, :, :7].numpy())
     assert int(ragged[1, :, 7:].abs().sum()) == 0
     assert np.array_equal(ragged[0].cpu().numpy(), want[0].numpy())
+
+
+# ------------------------------------------------------------------------------------------------ limits
+def test_limits_kv_cache_full_and_maximum_lengths(models):
+    """Maximum sizes: a full KV cache refuses to decode further (the reference would index out of range,
+    dual_ar_stream.py:141-150), the tokenizer refuses more than the 2048 positions of its RoPE table, and the one-frame
+    minimum works for both encoders and the vocoder."""
+    from streamvoiceanon_b200 import ARVCWrapper
+    _, tok, voc = models
+    ar = ARVCWrapper()
+    ar.setup_caches(max_batch_size=1, max_seq_len=64)
+    ar.set_delay(delay=2)
+    g = torch.Generator().manual_seed(3)
+    T = 10                                                    # 33 + 2*10 = 53 prompt tokens, +3 for the delay prefill
+    style, timbre = synth.synth_speaker(5300)
+    ar.prefill_prompt(torch.randint(0, 8192, (1, T), generator=g).cuda(), torch.randint(0, 1000, (1, 8, T), generator=g).int().cuda(),
+                      style.cuda(), timbre.cuda())
+    ar.prefill_src_condition4delay(torch.randint(0, 8192, (1, 2), generator=g).cuda())
+    for _ in range(4):                                        # positions 56..63
+        ar.decode_one(torch.randint(0, 8192, (1, 1), generator=g).cuda())
+    with pytest.raises(RuntimeError, match="KV cache full"):
+        ar.decode_one(torch.randint(0, 8192, (1, 1), generator=g).cuda())
+    with pytest.raises(RuntimeError, match="does not fit the KV cache"):
+        ar.prefill_prompt(torch.zeros(1, 40, dtype=torch.long).cuda(), torch.zeros(1, 8, 40, dtype=torch.int32).cuda(),
+                          style.cuda(), timbre.cuda())
+    with pytest.raises(RuntimeError, match="RoPE table"):
+        tok.encode(torch.zeros(1, 2049 * 2048).cuda(), torch.LongTensor([2049 * 2048]).cuda())
+    one = synth.synth_audio_44k(1700, 0.2)[:2048][None].cuda()
+    ids, flen = tok.encode(one, torch.LongTensor([2048]).cuda())
+    assert tuple(ids.shape) == (1, 1, 1) and int(flen[0]) == 1
+    (codes, _), _ = voc.encode(one, torch.LongTensor([2048]).cuda())
+    assert tuple(codes.shape) == (1, 8, 1)
+    wave = voc.decode_codes(codes.long())
+    assert tuple(wave.shape) == (1, 1, 2048) and bool(torch.isfinite(wave).all())
