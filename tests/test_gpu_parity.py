@@ -355,7 +355,7 @@ def test_stream_loop_chunk2_truncated_prompt_vs_oracle(models, weights, tape):
 def test_ring_buffer_encoder_equals_window_recompute(models, weights, gold, tape):
     """E with persistent ring-buffer state (conv-stack outputs kept between chunks, only the window's first and last
     40 + chunk frames re-encoded) against the reference-style full re-encode of the 128-frame window in the same loop:
-    identical content ids (and therefore codec ids) over 20 chunks; both modes are also held to the reference
+    identical content ids (and therefore codec ids) over 150 chunks (every state row has been produced incrementally by then); both modes are also held to the reference
     fixture by test_stream_loop_vs_reference."""
     from streamvoiceanon_b200 import StreamSession
     _, tok, _ = models
@@ -365,7 +365,8 @@ def test_ring_buffer_encoder_equals_window_recompute(models, weights, gold, tape
     gen = torch.Generator().manual_seed(int(g["codes_seed"]))
     ref_audio = torch.randint(0, 1000, (1, 8, n_ref), generator=gen).int()
     ref_content = torch.from_numpy(g["ref_content"])
-    src = synth.synth_audio_44k(1300, 2.0)[: 20 * 2048].view(20, 2048)
+    n_chunks = 150                                  # > one full window turnover (128 frames) of the ring-buffer state
+    src = synth.synth_audio_44k(1300, 8.0)[: n_chunks * 2048].view(n_chunks, 2048)
     out = []
     for incremental in (1, 0, 2):                  # ring-buffer state | full re-encode | + per-layer conv history
         sess = StreamSession()
@@ -373,7 +374,7 @@ def test_ring_buffer_encoder_equals_window_recompute(models, weights, gold, tape
         sess.set_prompt(ref_content[0].cuda(), ref_audio.cuda(), style.cuda(), timbre.cuda(), 256, 2)
         sess.setup(128, 64, 768, 32, 1)
         sess.set_encoder_mode(incremental)
-        waves = torch.cat([sess.process_chunk(src[i].cuda()).cpu() for i in range(20)])
+        waves = torch.cat([sess.process_chunk(src[i].cuda()).cpu() for i in range(n_chunks)])
         out.append((*sess.history(), waves))
         sess.close()
     for other in (out[1], out[2]):
