@@ -364,6 +364,34 @@ int svanon_ar_set_barrier_mode(svanon_engine* e, int mode) {
   });
 }
 
+int svanon_ar_profile(svanon_engine* e, int enable, uint64_t* cycles_out) {
+  return guarded([&] {
+    SV_CHECK(e, "null engine");
+    Engine& eng = e->eng;
+    SV_CUDA(cudaSetDevice(eng.device));
+    SV_CUDA(cudaDeviceSynchronize());
+    if (cycles_out && eng.ar_prof)
+      SV_CUDA(cudaMemcpy(cycles_out, eng.ar_prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (enable) {
+      if (!eng.ar_prof) SV_CUDA(cudaMalloc(&eng.ar_prof, 8 * sizeof(unsigned long long)));
+      SV_CUDA(cudaMemset(eng.ar_prof, 0, 8 * sizeof(unsigned long long)));
+    } else if (eng.ar_prof) {
+      cudaFree(eng.ar_prof);
+      eng.ar_prof = nullptr;
+    }
+  });
+}
+
+int svanon_debug_grid_barrier(svanon_engine* e, int mode, int iters, int exchange, float* ms_out) {
+  return guarded([&] {
+    SV_CHECK(e && ms_out && iters > 0 && (mode == 0 || mode == 1), "bad arguments");
+    SV_CHECK(e->eng.finalized[MODEL_AR], "AR weights not finalized");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    SV_CUDA(cudaDeviceSynchronize());
+    *ms_out = grid_barrier_probe(e->eng.ar_barrier, mode, iters, e->eng.ar_g, exchange, e->eng.num_sms, nullptr);
+  });
+}
+
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits, float* hidden, float* fast_logits) {
   return guarded([&] {
     SV_CHECK(e && e->eng.finalized[MODEL_AR], "AR weights not finalized");

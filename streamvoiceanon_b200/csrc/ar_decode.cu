@@ -328,6 +328,43 @@ void launch_b(const ArDecodeArgs& args, int grid, cudaStream_t st) {
 
 }  // namespace
 
+// Measurement aid: `iters` back-to-back grid barriers (optionally with the store -> fence -> barrier -> L2 load round
+// trip a real phase has) in the launch configuration of the decode kernels.
+__global__ void __launch_bounds__(NT, 1) grid_barrier_probe_kernel(unsigned* bar, int mode, int iters, float* scratch, int exchange) {
+  const unsigned nblocks = gridDim.x;
+  grid_sync_init(bar, mode);
+  float acc = 0.f;
+  for (int i = 0; i < iters; ++i) {
+    if (exchange) {
+      // every CTA publishes 6 floats, then reads everybody's (a 768-float activation vector, as between two phases)
+      if (threadIdx.x < 6) scratch[(i & 1) * 1024 + blockIdx.x * 6 + threadIdx.x] = acc + (float)i;
+    }
+    grid_sync(bar, nblocks);
+    if (exchange) {
+      for (int j = threadIdx.x; j < (int)nblocks * 6; j += NT) acc += __ldcg(scratch + (i & 1) * 1024 + j);
+    }
+  }
+  if (exchange && acc == 12345.678f) scratch[2047] = acc;
+  grid_sync_finish(bar);
+}
+
+float grid_barrier_probe(unsigned* bar, int mode, int iters, float* scratch, int exchange, int grid, cudaStream_t st) {
+  void* kargs[] = {(void*)&bar, (void*)&mode, (void*)&iters, (void*)&scratch, (void*)&exchange};
+  cudaEvent_t e0, e1;
+  SV_CUDA(cudaEventCreate(&e0));
+  SV_CUDA(cudaEventCreate(&e1));
+  SV_CUDA(cudaLaunchCooperativeKernel((void*)grid_barrier_probe_kernel, dim3(grid), dim3(NT), kargs, 0, st));
+  SV_CUDA(cudaEventRecord(e0, st));
+  SV_CUDA(cudaLaunchCooperativeKernel((void*)grid_barrier_probe_kernel, dim3(grid), dim3(NT), kargs, 0, st));
+  SV_CUDA(cudaEventRecord(e1, st));
+  SV_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  SV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms;
+}
+
 int ar_decode_max_batch() { return 4; }
 
 void launch_ar_decode(const ArDecodeArgs& args, int batch, int grid, cudaStream_t st) {

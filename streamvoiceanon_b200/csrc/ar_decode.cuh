@@ -57,6 +57,8 @@ struct ArDecodeArgs {
   float* dbg_slow_logits;       // [8192] or null
   float* dbg_hidden;            // [768] or null
   float* dbg_fast_logits;       // [8][1000] or null
+  float keep_fraction;          // share of the fast-stack weight lines requested with L2 evict_last (rest: evict_first)
+  unsigned long long* prof;     // [8] cycle counters per category (ar_decode_staged.cu Prof), or null
   int max_seq;
   int nsplit;
   float temperature;
@@ -64,6 +66,7 @@ struct ArDecodeArgs {
 };
 
 int ar_decode_max_batch();
+float grid_barrier_probe(unsigned* bar, int mode, int iters, float* scratch, int exchange, int grid, cudaStream_t st);
 void launch_ar_decode(const ArDecodeArgs& args, int batch, int grid, cudaStream_t st);
 // batch-1 variant with TMA-staged weights (ar_decode_staged.cu)
 bool ar_decode_staged_supported(int grid);

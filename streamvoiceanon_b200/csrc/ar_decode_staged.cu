@@ -33,6 +33,19 @@ struct Slice {
   bool fast;
 };
 
+__device__ __forceinline__ int* slice_table() {
+  __shared__ int t[10];
+  return t;
+}
+__device__ __forceinline__ void slice_table_init() {
+  if (threadIdx.x < 5) {
+    const int units[5] = {3 * D / 2, D, I, D, AR_CB_SIZE};        // K_QKV (row pairs), K_WO, K_W13, K_W2, K_LOGITS
+    const int U = units[threadIdx.x];
+    slice_table()[2 * threadIdx.x] = (int)((long long)U * blockIdx.x / gridDim.x);
+    slice_table()[2 * threadIdx.x + 1] = (int)((long long)U * (blockIdx.x + 1) / gridDim.x);
+  }
+}
+
 __device__ __forceinline__ Slice slice_of(const ArDecodeArgs& a, int wp) {
   Slice s;
   int kind;
@@ -47,18 +60,18 @@ __device__ __forceinline__ Slice slice_of(const ArDecodeArgs& a, int wp) {
     if (r == WP_PER_CB - 1) { kind = K_LOGITS; lw = &a.fast[0]; }
     else { lw = &a.fast[r >> 2]; kind = r & 3; }
   }
-  int U;
   s.regions = 1;
   s.src[1] = nullptr;
   switch (kind) {
-    case K_QKV: U = 3 * D / 2; s.src[0] = lw->wqkv; s.bytes_per_unit = 2 * D * 4; break;
-    case K_WO: U = D; s.src[0] = lw->wo; s.bytes_per_unit = D * 4; break;
-    case K_W13: U = I; s.src[0] = lw->w1; s.src[1] = lw->w3; s.bytes_per_unit = D * 4; s.regions = 2; break;
-    case K_W2: U = D; s.src[0] = lw->w2; s.bytes_per_unit = I * 4; break;
-    default: U = AR_CB_SIZE; s.src[0] = a.fast_output_w; s.bytes_per_unit = D * 4; break;
+    case K_QKV: s.src[0] = lw->wqkv; s.bytes_per_unit = 2 * D * 4; break;
+    case K_WO: s.src[0] = lw->wo; s.bytes_per_unit = D * 4; break;
+    case K_W13: s.src[0] = lw->w1; s.src[1] = lw->w3; s.bytes_per_unit = D * 4; s.regions = 2; break;
+    case K_W2: s.src[0] = lw->w2; s.bytes_per_unit = I * 4; break;
+    default: s.src[0] = a.fast_output_w; s.bytes_per_unit = D * 4; break;
   }
-  s.u0 = (int)((long long)U * blockIdx.x / gridDim.x);
-  s.u1 = (int)((long long)U * (blockIdx.x + 1) / gridDim.x);
+  // this CTA's unit range of each kind never changes: computed once per launch (slice_table_init), no divisions here
+  s.u0 = slice_table()[2 * kind];
+  s.u1 = slice_table()[2 * kind + 1];
   return s;
 }
 
@@ -95,6 +108,25 @@ struct Stage {
   int wp;                         // next weight phase to be consumed (uniform across the CTA)
 };
 
+// Optional in-kernel timeline (svanon_ar_profile): thread 0 of CTA 0 accumulates SM clock cycles per category between
+// markers; off (null pointer) in production.
+enum ProfCat : int { P_ACT = 0, P_WAIT = 1, P_DOT = 2, P_SYNC = 3, P_ATTN = 4, P_SAMPLE = 5, P_MISC = 6, P_N = 8 };
+struct Prof {
+  unsigned long long* acc;
+  long long last;
+  __device__ __forceinline__ void start(unsigned long long* out) {
+    acc = (blockIdx.x == 0 && threadIdx.x == 0) ? out : nullptr;
+    if (acc) last = clock64();
+  }
+  __device__ __forceinline__ void tick(int cat) {
+    if (acc) {
+      const long long t = clock64();
+      acc[cat] += (unsigned long long)(t - last);
+      last = t;
+    }
+  }
+};
+
 // issue the bulk copies of weight phase `wp` into buffer wp&1 (one thread)
 __device__ __forceinline__ void issue(const ArDecodeArgs& a, Stage& sg, int wp) {
   if (wp >= N_WP) return;
@@ -119,7 +151,7 @@ __device__ __forceinline__ void issue(const ArDecodeArgs& a, Stage& sg, int wp) 
 // start of a weight phase: prefetch the next one, wait for this one; returns the slice and its smem base
 __device__ __forceinline__ const float* begin_phase(const ArDecodeArgs& a, Stage& sg, Slice& s) {
   const int wp = sg.wp;
-  if (threadIdx.x == 0) issue(a, sg, wp + 1);
+  if (threadIdx.x == NT - 32) issue(a, sg, wp + 1);      // lane 0 of the last warp: it has no rows in most phases
   s = slice_of(a, wp);
   if (s.u1 > s.u0) mbar_wait(sg.mbar + (wp & 1), (wp >> 1) & 1);
   sg.wp = wp + 1;
@@ -162,15 +194,17 @@ __device__ __forceinline__ void warp_rows_dot_s(const float* const* w, const flo
 // one transformer layer for stream 0; M = 2 (slow) or 1 (fast) rows
 template <int M, bool FAST>
 __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLayerWeights& w, int layer_idx, int cb,
-                                             float* xs, Stage& sg, unsigned nblocks) {
+                                             float* xs, Stage& sg, unsigned nblocks, Prof& pf) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ArStreamDev& st = a.s[0];
   Slice s;
 
   // ---- phase 1: attention_norm + wqkv (+RoPE); q -> scratch, k/v -> cache
   load_rmsnorm<M>(a.x, w.attn_norm, xs, nullptr);
+  pf.tick(P_ACT);
   {
     const float* wb = begin_phase(a, sg, s);
+    pf.tick(P_WAIT);
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
       const float* rows[2] = {wb + (size_t)(u - s.u0) * 2 * D, wb + (size_t)(u - s.u0) * 2 * D + D};
       float o[2][M];
@@ -201,7 +235,9 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
       }
     }
   }
+  pf.tick(P_DOT);
   grid_sync(a.barrier, nblocks);
+  pf.tick(P_SYNC);
 
   float* ys = xs;                          // [M][D] attention output
   if (!FAST) {
@@ -259,21 +295,33 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
       }
       __syncthreads();
     }
+    pf.tick(P_ATTN);
     grid_sync(a.barrier, nblocks);
+    pf.tick(P_SYNC);
     // ---- phase 3a: every CTA merges the split partials of all (head, token) into ys
+    // (all loads of an item are issued before any is used: lane sp fetches split sp's (m, l), the accumulator
+    // slices are fetched in one fully unrolled, predicated batch -- one L2 round trip instead of one per split)
     for (int it = warp; it < H * 2; it += NW) {
       const int h = it / 2, tkn = it % 2;
       const float* base = a.part + ((long long)h * a.nsplit * 2 + tkn) * PART;
-      float mm = -INFINITY;
-      for (int sp = 0; sp < a.nsplit; ++sp) mm = fmaxf(mm, __ldcg(base + (long long)sp * 2 * PART));
+      float pm = -INFINITY, pl = 0.f;
+      if (lane < a.nsplit) {
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(base + (long long)lane * 2 * PART));
+        pm = ml.x; pl = ml.y;
+      }
+      float2 av[16];
+#pragma unroll
+      for (int sp = 0; sp < 16; ++sp)
+        av[sp] = sp < a.nsplit ? __ldcg(reinterpret_cast<const float2*>(base + (long long)sp * 2 * PART + 2) + lane)
+                               : make_float2(0.f, 0.f);
+      const float mm = warp_max(pm);
+      const float cl = (pm == -INFINITY) ? 0.f : expf(pm - mm);      // this lane's split: rescale factor
       float ll = 0.f, ax = 0.f, ay = 0.f;
-      for (int sp = 0; sp < a.nsplit; ++sp) {
-        const float* pp = base + (long long)sp * 2 * PART;
-        const float pm = __ldcg(pp);
-        const float c = (pm == -INFINITY) ? 0.f : expf(pm - mm);
-        ll += __ldcg(pp + 1) * c;
-        const float2 av = __ldcg(reinterpret_cast<const float2*>(pp + 2) + lane);
-        ax += av.x * c; ay += av.y * c;
+#pragma unroll
+      for (int sp = 0; sp < 16; ++sp) {                               // fixed split order: deterministic sums
+        const float c = __shfl_sync(0xffffffffu, cl, sp);
+        const float l_sp = __shfl_sync(0xffffffffu, pl, sp);
+        if (sp < a.nsplit) { ll += l_sp * c; ax += av[sp].x * c; ay += av[sp].y * c; }
       }
       const float inv = 1.f / ll;
       ys[tkn * D + h * HEAD_DIM + 2 * lane] = ax * inv;
@@ -314,8 +362,10 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
     __syncthreads();
   }
   // ---- phase 3b: wo + residual -> h
+  pf.tick(P_ATTN);
   {
     const float* wb = begin_phase(a, sg, s);
+    pf.tick(P_WAIT);
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
       const float* rows[1] = {wb + (size_t)(u - s.u0) * D};
       float o[1][M];
@@ -326,12 +376,16 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
       }
     }
   }
+  pf.tick(P_DOT);
   grid_sync(a.barrier, nblocks);
+  pf.tick(P_SYNC);
 
   // ---- phase 4: ffn_norm + silu(w1 h) * (w3 h) -> g
   load_rmsnorm<M>(a.h, w.ffn_norm, xs, nullptr);
+  pf.tick(P_ACT);
   {
     const float* wb = begin_phase(a, sg, s);
+    pf.tick(P_WAIT);
     const int n = s.u1 - s.u0;
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
       const float* rows[2] = {wb + (size_t)(u - s.u0) * D, wb + (size_t)n * D + (size_t)(u - s.u0) * D};
@@ -346,13 +400,17 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
       }
     }
   }
+  pf.tick(P_DOT);
   grid_sync(a.barrier, nblocks);
+  pf.tick(P_SYNC);
 
   // ---- phase 5: w2 + residual -> x
   for (int i = threadIdx.x; i < M * I; i += NT) xs[i] = __ldcg(a.g + i);
   __syncthreads();
+  pf.tick(P_ACT);
   {
     const float* wb = begin_phase(a, sg, s);
+    pf.tick(P_WAIT);
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
       const float* rows[1] = {wb + (size_t)(u - s.u0) * I};
       float o[1][M];
@@ -363,7 +421,9 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
       }
     }
   }
+  pf.tick(P_DOT);
   grid_sync(a.barrier, nblocks);
+  pf.tick(P_SYNC);
 }
 
 __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeArgs a) {
@@ -376,7 +436,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   static_assert(sizeof(SampleSmem) <= XS_FLOATS * sizeof(float), "sampler scratch must fit the activation buffer");
   sg.wp = 0;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(sg.pol_stream));
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(sg.pol_keep));
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(sg.pol_keep) : "f"(a.keep_fraction));
   const unsigned nblocks = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = warp * gridDim.x + blockIdx.x;
@@ -384,6 +444,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   const int gtid = blockIdx.x * NT + threadIdx.x;
   const ArStreamDev& st = a.s[0];
 
+  slice_table_init();
   if (threadIdx.x == 0) {
     mbar_init(sg.mbar + 0, 1);
     mbar_init(sg.mbar + 1, 1);
@@ -391,8 +452,10 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) issue(a, sg, 0);
+  if (threadIdx.x == NT - 32) issue(a, sg, 0);
   grid_sync_init(a.barrier, a.barrier_mode);
+  Prof pf;
+  pf.start(a.prof);
 
   // ---- phase 0: the 2 input rows [cached_new_audio_emb, embedding[content_id]]
   for (int i = gtid; i < 2 * D; i += NT * gridDim.x) {
@@ -405,7 +468,8 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   }
   grid_sync(a.barrier, nblocks);
 
-  for (int l = 0; l < AR_LAYERS; ++l) layer_staged<2, false>(a, a.slow[l], l, 0, xs, sg, nblocks);
+  pf.tick(P_MISC);
+  for (int l = 0; l < AR_LAYERS; ++l) layer_staged<2, false>(a, a.slow[l], l, 0, xs, sg, nblocks, pf);
 
   if (a.dbg_slow_logits) {
     load_rmsnorm<1>(a.x + D, a.norm_w, xs, nullptr);
@@ -424,12 +488,15 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   for (int i = gtid; i < D; i += NT * gridDim.x) a.x[i] = __ldcg(a.h + i);
   grid_sync(a.barrier, nblocks);
 
+  pf.tick(P_MISC);
   for (int cb = 0; cb < AR_CODEBOOKS; ++cb) {
-    for (int l = 0; l < AR_FAST_LAYERS; ++l) layer_staged<1, true>(a, a.fast[l], l, cb, xs, sg, nblocks);
+    for (int l = 0; l < AR_FAST_LAYERS; ++l) layer_staged<1, true>(a, a.fast[l], l, cb, xs, sg, nblocks, pf);
     load_rmsnorm<1>(a.x, a.fast_norm_w, xs, nullptr);
+    pf.tick(P_ACT);
     {
       Slice s;
       const float* wb = begin_phase(a, sg, s);
+      pf.tick(P_WAIT);
       for (int u = s.u0 + warp; u < s.u1; u += NW) {
         const float* rows[1] = {wb + (size_t)(u - s.u0) * D};
         float o[1][1];
@@ -437,7 +504,9 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
         if (lane == 0) a.logits[u] = o[0][0];
       }
     }
+    pf.tick(P_DOT);
     grid_sync(a.barrier, nblocks);
+    pf.tick(P_SYNC);
     if (blockIdx.x == 0) {
       if (a.dbg_fast_logits)
         for (int i = threadIdx.x; i < AR_CB_SIZE; i += NT) a.dbg_fast_logits[cb * AR_CB_SIZE + i] = __ldcg(a.logits + i);
@@ -446,7 +515,9 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
       if (threadIdx.x == 0) st.out_codes[cb] = tok;
       for (int i = threadIdx.x; i < D; i += NT) a.x[i] = __ldg(a.fast_emb + (long long)tok * D + i);
     }
+    pf.tick(P_SAMPLE);
     grid_sync(a.barrier, nblocks);
+    pf.tick(P_SYNC);
   }
 
   // ---- cached_new_audio_emb = embed(pred codes)  (dual_ar_stream.py:245-255, 834)
@@ -459,6 +530,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
     }
     st.x_audio[c] = s;
   }
+  pf.tick(P_MISC);
   grid_sync_finish(a.barrier);
 }
 

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace svanon {
 
@@ -1046,6 +1047,14 @@ void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) 
   nsplit = std::min(nsplit, std::max(1, max_keys / 16));
   a.nsplit = nsplit;
   a.barrier_mode = ar_barrier_mode;
+  a.prof = ar_prof;
+  {
+    static const float keep = [] {
+      const char* e = getenv("SVANON_AR_KEEP_FRACTION");   // tuning knob
+      return e ? (float)atof(e) : 0.25f;
+    }();
+    a.keep_fraction = keep;
+  }
   if (debug_logits) { a.dbg_slow_logits = dbg_slow_logits; a.dbg_hidden = dbg_hidden; a.dbg_fast_logits = dbg_fast_logits; }
   else { a.dbg_slow_logits = nullptr; a.dbg_hidden = nullptr; a.dbg_fast_logits = nullptr; }
   if (batch == 1 && ar_variant == 2 && ar_decode_staged_supported(num_sms)) {

@@ -231,6 +231,7 @@ struct Engine {
   int ar_barrier_mode = 0;                     // grid barrier of the persistent decode kernels (ar_decode_common.cuh)
   float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
   bool debug_logits = false;
+  unsigned long long* ar_prof = nullptr;       // in-kernel timeline counters (svanon_ar_profile), null = off
   int ar_variant = 1;                          // batch-1 decode kernel: 0 direct loads, 1 TMA-staged, 2 staged + flag-in-data (no grid barriers)
   void* ar_ll = nullptr;
   unsigned ar_epoch = 0;
