@@ -39,7 +39,7 @@ WORKLOAD = dict(workload="streaming chunk=1 delay=2, single stream per GPU (BASE
 # algorithmic bytes of one AR decode launch (fp32 weights): every slow/fast layer, norms,
 # fast_output and the touched embedding rows once; the discarded 768->8192 head is skipped
 AR_WEIGHT_PARAMS = 129_782_016 - 6_291_456 - 768
-AR_NCU_DRAM_BYTES = 1.372e9        # 1.317 TB/s x 1.041 ms (ncu, S_valid = 256)
+AR_NCU_DRAM_BYTES = 1.164e9        # 1.265 TB/s x 0.920 ms (ncu, S_valid = 256)
 
 
 def parse():
@@ -362,8 +362,8 @@ def run_engine(args):
         "roofline": {"kernel": "ar_decode_kernel<1> (one launch per frame: 12 slow + 8x4 fast layers + 8 samplers)",
                      "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": AR_NCU_DRAM_BYTES, "traffic_source": "dram__bytes (read+write) of one launch, ncu capture "
-                     "profiles/r1h_ar_decode_ncu_details.txt: the 123 MB fp32 fast stack does not stay in L2 and is "
-                     "re-fetched for each of the 8 codebooks", "peak_source": peak_src,
+                     "profiles/r1z_ar_decode_ncu_details.txt: the 123 MB fp32 fast stack does not fit L2 next to the rest and is "
+                     "mostly re-fetched for each of the 8 codebooks (a quarter of its lines is kept with evict_last)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ar_bytes, "launch_ms": ar_ms, "s_valid": s_valid},
         "clocks": clocks,
     }
