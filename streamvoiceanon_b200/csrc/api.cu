@@ -7,6 +7,9 @@ extern bool g_gemm_use_pipe;
 extern bool g_gemm_use_tc;
 extern bool g_use_pdl;
 extern bool g_use_conv_small;
+#ifdef SVANON_TC_PROF
+void tc_prof_dump();
+#endif
 }
 namespace svanon {
 thread_local std::string g_api_err;
@@ -343,6 +346,9 @@ int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const fl
     p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N; p.act = act;
     launch_gemm(p, a.st);
     a.finish();
+#ifdef SVANON_TC_PROF
+    tc_prof_dump();
+#endif
   });
 }
 

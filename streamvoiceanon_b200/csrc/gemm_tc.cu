@@ -89,6 +89,15 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+#ifdef SVANON_TC_PROF
+// tuning build only (-DSVANON_TC_PROF, tools/profile_gemm_timeline.py): clock64 marks of thread 0 (producer) and the MMA
+// thread of CTA (0,0,0), printed by svanon_debug_gemm
+__device__ long long g_tc_prof[16];
+#define TC_MARK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == TC_PRODUCERS)) g_tc_prof[(i) + (tid == 0 ? 0 : 8)] = clock64(); } while (0)
+#else
+#define TC_MARK(i) do {} while (0)
+#endif
+
 constexpr int TC_PRODUCER_WARPS = 16;              // warps 0-15: global -> registers -> hi/lo split -> swizzled tiles; epilogue
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
 constexpr int TC_THREADS = TC_PRODUCERS + 32;      // warp 16: MMA issuer (one elected lane)
@@ -138,6 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   const int it_end = (int)((long long)total * (rank + 1) / split);
   const int n_it = it_end - it_begin;
 
+  TC_MARK(0);
   pdl_trigger();
   if (tid == 0) {
 #pragma unroll
@@ -158,6 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_d = tmem_holder;
+  TC_MARK(1);
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================================================== producers
@@ -218,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
       for (int d = 0; d < D; ++d)
         if (d < n_it) { load_b(rb[d]); advance(); }
       pdl_wait();
+      TC_MARK(2);
       ld_t = t0; ld_k = k0; ld_a = a0; ld_b = b0;
 #pragma unroll
       for (int d = 0; d < D; ++d)
@@ -275,8 +287,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
         }
       }
     }
+    TC_MARK(3);
   } else {
     pdl_wait();
+    TC_MARK(2);
     if (lane == 0) {
       // =========================================================== MMA issuer
       const unsigned idesc = umma_idesc(BN);
@@ -298,6 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
         umma_commit(&empty_bar[stage]);
       }
       umma_commit(&acc_bar);
+      TC_MARK(3);
     }
   }
   __syncwarp();
@@ -311,6 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     if (n_it > 0 && lane == 0) mbar_wait(&acc_bar, 0);
     __syncwarp();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TC_MARK(4);
   }
   auto finish = [&](float (&v)[16], int m, int col0) {      // bias/act/gamma/residual/scale + store of 16 columns
     const int n_base = n0 + col0;
@@ -380,6 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
         for (int j = 0; j < 16; ++j) smem[(c0 + j) * TBM + row] = v[j];
       }
     }
+    TC_MARK(7);
     cluster.sync();
     // rank r owns the 16-column groups r, r + split, ...: 128 rows x 16 columns = 512 (row, 4-column) items per group
     if (warp < TC_PRODUCER_WARPS) {
@@ -413,9 +430,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
       }
     }
   }
+  TC_MARK(5);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (SPLIT) cluster.sync();
   else __syncthreads();
+  TC_MARK(6);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
 }
 
@@ -450,6 +469,22 @@ void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef SVANON_TC_PROF
+void tc_prof_dump() {
+  long long h[16];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
+  const char* names[8] = {"entry", "prologue done (bars, TMEM alloc, bias)", "griddepcontrol.wait done", "main loop done", "accumulator ready",
+                          "epilogue done", "final sync done", "partials parked (split)"};
+  for (int w = 0; w < 2; ++w) {
+    fprintf(stderr, "%s:", w ? "  mma thread" : "  producer t0");
+    for (int i = 1; i < 8; ++i)
+      if (h[i + 8 * w] && h[8 * w]) fprintf(stderr, "  [%s] +%.2f us", names[i], (h[i + 8 * w] - h[8 * w]) / 1965.0);
+    fprintf(stderr, "\n");
+  }
+}
+#endif
 
 // Returns false when the problem is not a good fit (M < 32: latency kernels; N < 64).  Defaults measured on the streaming
 // loop: M >= 32 (3.79 -> 3.72 ms per chunk vs M >= 96), split-K clusters of at most 4 (8 is no faster).
