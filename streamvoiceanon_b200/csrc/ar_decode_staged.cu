@@ -207,19 +207,27 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
     pf.tick(P_WAIT);
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
       const float* rows[2] = {wb + (size_t)(u - s.u0) * 2 * D, wb + (size_t)(u - s.u0) * 2 * D + D};
+      const int r = 2 * u;
+      const int sec = r / D, c = r % D;
+      const int h = c / HEAD_DIM, d = c % HEAD_DIM;
+      // the RoPE entries are requested BEFORE the dot products: their L2 latency hides behind the math
+      float2 rope_cs[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const int pos = FAST ? cb : st.pos + m;
+        rope_cs[m] = (lane == 0 && sec < 2)
+                         ? __ldg(reinterpret_cast<const float2*>((FAST ? a.fast_rope : a.rope) + ((long long)pos * (HEAD_DIM / 2) + d / 2) * 2))
+                         : make_float2(1.f, 0.f);
+      }
       float o[2][M];
       warp_rows_dot_s<2, M>(rows, xs, D, o);
       if (lane == 0) {
-        const int r = 2 * u;
-        const int sec = r / D, c = r % D;
-        const int h = c / HEAD_DIM, d = c % HEAD_DIM;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
           const int pos = FAST ? cb : st.pos + m;
           float v0 = o[0][m], v1 = o[1][m];
           if (sec < 2) {
-            const float* tab = (FAST ? a.fast_rope : a.rope) + ((long long)pos * (HEAD_DIM / 2) + d / 2) * 2;
-            const float cs = __ldg(tab), sn = __ldg(tab + 1);
+            const float cs = rope_cs[m].x, sn = rope_cs[m].y;
             const float r0 = v0 * cs - v1 * sn, r1 = v1 * cs + v0 * sn;
             v0 = r0; v1 = r1;
           }
@@ -334,15 +342,22 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
       const float2 qv = __ldcg(reinterpret_cast<const float2*>(a.q + h * HEAD_DIM) + lane);
       const float* kc = st.fkc + ((long long)layer_idx * H + h) * AR_CODEBOOKS * HEAD_DIM;
       const float* vc = st.fvc + ((long long)layer_idx * H + h) * AR_CODEBOOKS * HEAD_DIM;
+      // q, all keys and all values are requested before anything is used: one L2 round trip instead of three
+      float2 kv[AR_CODEBOOKS], vv[AR_CODEBOOKS];
+#pragma unroll
+      for (int key = 0; key < AR_CODEBOOKS; ++key) {
+        kv[key] = vv[key] = make_float2(0.f, 0.f);
+        if (key <= cb) {
+          kv[key] = __ldcg(reinterpret_cast<const float2*>(kc + key * HEAD_DIM) + lane);
+          vv[key] = __ldcg(reinterpret_cast<const float2*>(vc + key * HEAD_DIM) + lane);
+        }
+      }
       float sc[AR_CODEBOOKS];
       float mx = -INFINITY;
 #pragma unroll
       for (int key = 0; key < AR_CODEBOOKS; ++key) {
         float sv = -INFINITY;
-        if (key <= cb) {
-          const float2 kv = __ldcg(reinterpret_cast<const float2*>(kc + key * HEAD_DIM) + lane);
-          sv = warp_sum(qv.x * kv.x + qv.y * kv.y) * 0.125f;
-        }
+        if (key <= cb) sv = warp_sum(qv.x * kv[key].x + qv.y * kv[key].y) * 0.125f;
         sc[key] = sv;
         mx = fmaxf(mx, sv);
       }
@@ -351,8 +366,7 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
       for (int key = 0; key < AR_CODEBOOKS; ++key) {
         if (key <= cb) {
           const float p = expf(sc[key] - mx);
-          const float2 vv = __ldcg(reinterpret_cast<const float2*>(vc + key * HEAD_DIM) + lane);
-          l += p; ax += p * vv.x; ay += p * vv.y;
+          l += p; ax += p * vv[key].x; ay += p * vv[key].y;
         }
       }
       const float inv = 1.f / l;
@@ -368,11 +382,14 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
     pf.tick(P_WAIT);
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
       const float* rows[1] = {wb + (size_t)(u - s.u0) * D};
+      float res[M];                          // residual requested before the dot products (latency hidden)
+#pragma unroll
+      for (int m = 0; m < M; ++m) res[m] = lane == 0 ? __ldcg(a.x + m * D + u) : 0.f;
       float o[1][M];
       warp_rows_dot_s<1, M>(rows, ys, D, o);
       if (lane == 0) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) a.h[m * D + u] = __ldcg(a.x + m * D + u) + o[0][m];
+        for (int m = 0; m < M; ++m) a.h[m * D + u] = res[m] + o[0][m];
       }
     }
   }
@@ -413,11 +430,14 @@ __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLaye
     pf.tick(P_WAIT);
     for (int u = s.u0 + warp; u < s.u1; u += NW) {
       const float* rows[1] = {wb + (size_t)(u - s.u0) * I};
+      float res[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) res[m] = lane == 0 ? __ldcg(a.h + m * D + u) : 0.f;
       float o[1][M];
       warp_rows_dot_s<1, M>(rows, xs, I, o);
       if (lane == 0) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) a.x[m * D + u] = __ldcg(a.h + m * D + u) + o[0][m];
+        for (int m = 0; m < M; ++m) a.x[m * D + u] = res[m] + o[0][m];
       }
     }
   }
