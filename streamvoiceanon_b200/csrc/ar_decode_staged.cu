@@ -194,13 +194,13 @@ __device__ __forceinline__ void warp_rows_dot_s(const float* const* w, const flo
 // one transformer layer for stream 0; M = 2 (slow) or 1 (fast) rows
 template <int M, bool FAST>
 __device__ __forceinline__ void layer_staged(const ArDecodeArgs& a, const ArLayerWeights& w, int layer_idx, int cb,
-                                             float* xs, Stage& sg, unsigned nblocks, Prof& pf) {
+                                             float* xs, Stage& sg, unsigned nblocks, Prof& pf, const float* x_in) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ArStreamDev& st = a.s[0];
   Slice s;
 
   // ---- phase 1: attention_norm + wqkv (+RoPE); q -> scratch, k/v -> cache
-  load_rmsnorm<M>(a.x, w.attn_norm, xs, nullptr);
+  load_rmsnorm<M>(x_in, w.attn_norm, xs, nullptr);      // x_in == a.x except right after a sampler (see the codebook loop)
   pf.tick(P_ACT);
   {
     const float* wb = begin_phase(a, sg, s);
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   grid_sync(a.barrier, nblocks);
 
   pf.tick(P_MISC);
-  for (int l = 0; l < AR_LAYERS; ++l) layer_staged<2, false>(a, a.slow[l], l, 0, xs, sg, nblocks, pf);
+  for (int l = 0; l < AR_LAYERS; ++l) layer_staged<2, false>(a, a.slow[l], l, 0, xs, sg, nblocks, pf, a.x);
 
   if (a.dbg_slow_logits) {
     load_rmsnorm<1>(a.x + D, a.norm_w, xs, nullptr);
@@ -503,14 +503,18 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
     __syncthreads();
   }
   // fast residual stream starts from the PRE-norm hidden state of the last token (dual_ar_stream.py:354-355)
-  for (int i = gtid; i < D; i += NT * gridDim.x) a.h[i] = __ldcg(a.x + D + i);
-  grid_sync(a.barrier, nblocks);
-  for (int i = gtid; i < D; i += NT * gridDim.x) a.x[i] = __ldcg(a.h + i);
+  // (row 0 of x, the first token's residual, is dead after the slow stack: the hidden row moves there directly)
+  for (int i = gtid; i < D; i += NT * gridDim.x) a.x[i] = __ldcg(a.x + D + i);
   grid_sync(a.barrier, nblocks);
 
   pf.tick(P_MISC);
+  // Every CTA runs every sampler itself: same logits, same noise -> same token everywhere, so no barrier is needed to
+  // publish it.  CTA 0 additionally stores the code and the token's embedding row into x (the residual the next wo
+  // phase reads, ordered by the QKV-phase barrier); the next layer-0 norm reads the embedding row directly.
+  __shared__ int s_toks[AR_CODEBOOKS];
+  const float* x_in = a.x;
   for (int cb = 0; cb < AR_CODEBOOKS; ++cb) {
-    for (int l = 0; l < AR_FAST_LAYERS; ++l) layer_staged<1, true>(a, a.fast[l], l, cb, xs, sg, nblocks, pf);
+    for (int l = 0; l < AR_FAST_LAYERS; ++l) layer_staged<1, true>(a, a.fast[l], l, cb, xs, sg, nblocks, pf, l == 0 ? x_in : a.x);
     load_rmsnorm<1>(a.x, a.fast_norm_w, xs, nullptr);
     pf.tick(P_ACT);
     {
@@ -527,27 +531,25 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
     pf.tick(P_DOT);
     grid_sync(a.barrier, nblocks);
     pf.tick(P_SYNC);
+    if (blockIdx.x == 0 && a.dbg_fast_logits)
+      for (int i = threadIdx.x; i < AR_CB_SIZE; i += NT) a.dbg_fast_logits[cb * AR_CB_SIZE + i] = __ldcg(a.logits + i);
+    const float* noise = st.noise ? st.noise + cb * AR_CB_SIZE : nullptr;
+    const int tok = sample_topp(a.logits, noise, st.seed, st.step, cb + 1, a.temperature, a.top_p, ssm);
+    if (threadIdx.x == 0) s_toks[cb] = tok;
+    x_in = a.fast_emb + (long long)tok * D;
     if (blockIdx.x == 0) {
-      if (a.dbg_fast_logits)
-        for (int i = threadIdx.x; i < AR_CB_SIZE; i += NT) a.dbg_fast_logits[cb * AR_CB_SIZE + i] = __ldcg(a.logits + i);
-      const float* noise = st.noise ? st.noise + cb * AR_CB_SIZE : nullptr;
-      const int tok = sample_topp(a.logits, noise, st.seed, st.step, cb + 1, a.temperature, a.top_p, ssm);
       if (threadIdx.x == 0) st.out_codes[cb] = tok;
-      for (int i = threadIdx.x; i < D; i += NT) a.x[i] = __ldg(a.fast_emb + (long long)tok * D + i);
+      for (int i = threadIdx.x; i < D; i += NT) a.x[i] = __ldg(x_in + i);
     }
     pf.tick(P_SAMPLE);
-    grid_sync(a.barrier, nblocks);
-    pf.tick(P_SYNC);
   }
 
   // ---- cached_new_audio_emb = embed(pred codes)  (dual_ar_stream.py:245-255, 834)
+  __syncthreads();
   for (int c = gtid; c < D; c += NT * gridDim.x) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < AR_CODEBOOKS; ++k) {
-      const int code = __ldcg(st.out_codes + k);
-      s += __ldg(a.codebook_emb + ((long long)code + k * AR_CB_SIZE) * D + c);
-    }
+    for (int k = 0; k < AR_CODEBOOKS; ++k) s += __ldg(a.codebook_emb + ((long long)s_toks[k] + k * AR_CB_SIZE) * D + c);
     st.x_audio[c] = s;
   }
   pf.tick(P_MISC);
