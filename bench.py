@@ -243,7 +243,7 @@ def run_reference(args):
                                        f"(CPU port of process_one_chunk), torch fp32, {cores} threads",
                              "stage_ms_median": stage},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_engine(args):
@@ -385,12 +385,21 @@ def run_engine(args):
                                 "sample": f"{args.cpu_sample} chunks of the same workload after 2 warm-up chunks, "
                                           f"oracle/streaming.py, torch fp32, {cores} threads",
                                 "ms_per_step": mean_ms, "stage_ms_median": cstage}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything libraries print to fd 1 (e.g. "NCCL version ...") was
+    re-routed to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
