@@ -1,5 +1,6 @@
 // Host-side engine: weight store, workspace, per-stream state and the three stage drivers.
 #pragma once
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -156,7 +157,11 @@ struct EncWindowState {
   bool enabled = true;
   ConvStackHist hist;                  // per-layer conv history of the newest frames (many-stream mode)
   bool hist_valid = false;
-  int tail_hist_min_streams = 8;       // use the conv history for the newest frames from this many streams (0: never)
+  int tail_hist_min_streams = default_tail_hist_min();   // conv history for the newest frames from this many streams (0: never)
+  static int default_tail_hist_min() {
+    const char* e = getenv("SVANON_ENC_HIST_MIN_STREAMS");     // tuning knob
+    return e ? atoi(e) : 8;
+  }
   ~EncWindowState() {
     for (auto p : xt)
       if (p) cudaFree(p);
