@@ -190,6 +190,15 @@ int svanon_stream_history(svanon_stream* s, int64_t* src_content, int* n_src, in
 int svanon_resample(svanon_engine* e, const float* wave, int64_t n_in, const float* kernel, int orig, int new_rate, int width,
                     float* out, int64_t n_out, void* cuda_stream);
 
+/* Speaker-embedding anonymisation: `InferenceWrapper.apply_noise_mixing`,
+ * evaluations/infer_arvc.py:228-232, applied to style_vectors [1,192] and timbre_latents [1,32,128] before
+ * prefill_prompt (:419-421): out = alpha * x + (1 - alpha) * (noise * std(x) + mean(x)), mean / unbiased std over all n
+ * elements.  `noise` holds the n standard-normal draws the reference takes from torch's global generator
+ * (`torch.randn_like`); the caller supplies them (the shim draws them the same way), so results are reproducible against
+ * the reference under a shared seed.  x, noise and out may be host or device pointers; out may alias x. */
+int svanon_noise_mix(svanon_engine* e, const float* x, const float* noise, int64_t n, float alpha, float* out,
+                     void* cuda_stream);
+
 /* ---- many concurrent streams in lock-step --------------------------------------------------------------------
  * The reference is strictly batch-1 (max_batch_size=1, evaluations/infer_arvc.py:56; `x.view(1, 1, -1)`,
  * modules/dual_ar_stream.py:544): N concurrent utterances are N sequential calls.  These entry points run the same

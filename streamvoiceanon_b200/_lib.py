@@ -60,6 +60,7 @@ _SIGS = {
     "svanon_stream_last_timing": (C.c_int, [_p, C.POINTER(C.c_float)]),
     "svanon_stream_history": (C.c_int, [_p, _p, C.POINTER(C.c_int), _p, C.POINTER(C.c_int), C.c_int]),
     "svanon_resample": (C.c_int, [_p, _p, C.c_int64, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int64, _p]),
+    "svanon_noise_mix": (C.c_int, [_p, _p, _p, C.c_int64, C.c_float, _p, _p]),
     "svanon_voc_encode": (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, _p]),
     "svanon_enc_encode_batch": (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, _p]),
     "svanon_ar_decode_many": (C.c_int, [C.POINTER(_p), C.c_int, _p, _p, _p, _p]),

@@ -189,6 +189,69 @@ attention_short_kernel(const float* __restrict__ q, long long q_ld, const float*
   }
 }
 
+// The last c queries of each segment only; thread t owns key t of the segment (nq <= 128).
+__global__ void __launch_bounds__(ATT_TAIL_MAX_KEYS)
+attention_tail_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
+                      long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
+                      int c, int window) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float qs[HEAD_DIM];
+  __shared__ float ps[ATT_TAIL_MAX_KEYS];
+  __shared__ float red[2][ATT_TAIL_MAX_KEYS / 32];
+  __shared__ float osum[2][HEAD_DIM];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int h = blockIdx.y;
+  const int seg = blockIdx.x / c, j = blockIdx.x - seg * c;
+  const int pos = nq - c + j;
+  const int lo = max(0, pos - window + 1);
+  const float* kb = k + (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
+  const float* vb = v + (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
+  if (t < HEAD_DIM) qs[t] = __ldg(q + ((long long)seg * nq + pos) * q_ld + h * HEAD_DIM + t) * 0.125f;   // 1/sqrt(64)
+  __syncthreads();
+  const bool valid = t >= lo && t <= pos;
+  float s = -INFINITY;
+  if (valid) {
+    const float4* kr = reinterpret_cast<const float4*>(kb + (long long)t * kv_row_stride);
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < HEAD_DIM / 4; ++d) {
+      const float4 kv = __ldg(kr + d);
+      a = fmaf(qs[4 * d], kv.x, a);
+      a = fmaf(qs[4 * d + 1], kv.y, a);
+      a = fmaf(qs[4 * d + 2], kv.z, a);
+      a = fmaf(qs[4 * d + 3], kv.w, a);
+    }
+    s = a;
+  }
+  float m = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[0][warp] = m;
+  __syncthreads();
+  m = red[0][0];
+#pragma unroll
+  for (int w = 1; w < ATT_TAIL_MAX_KEYS / 32; ++w) m = fmaxf(m, red[0][w]);
+  const float p = valid ? expf(s - m) : 0.f;
+  ps[t] = p;
+  float l = p;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if (lane == 0) red[1][warp] = l;
+  __syncthreads();
+  l = red[1][0];
+#pragma unroll
+  for (int w = 1; w < ATT_TAIL_MAX_KEYS / 32; ++w) l += red[1][w];
+  // P.V: thread = (half of the keys, output dim)
+  const int d = t & (HEAD_DIM - 1), half = t >> 6;
+  const int k0 = max(lo, half * (ATT_TAIL_MAX_KEYS / 2)), k1 = min(pos, half * (ATT_TAIL_MAX_KEYS / 2) + ATT_TAIL_MAX_KEYS / 2 - 1);
+  float acc = 0.f;
+  for (int key = k0; key <= k1; ++key) acc = fmaf(ps[key], __ldg(vb + (long long)key * kv_row_stride + d), acc);
+  osum[half][d] = acc;
+  __syncthreads();
+  if (t < HEAD_DIM) out[((long long)seg * c + j) * out_ld + h * HEAD_DIM + t] = (osum[0][t] + osum[1][t]) / l;
+}
+
 __global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float* __restrict__ kc, float* __restrict__ vc,
                                  int max_seq, int pos0) {
   pdl_trigger();
@@ -231,6 +294,15 @@ void launch_attention(const float* q, long long q_ld, const float* k, const floa
   dim3 grid((nq + QW - 1) / QW * nseg, heads);
   launch_pdl(attention_kernel, dim3(grid), dim3(QW * 32), 0, st, q, q_ld, k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0,
                                              window);
+  SV_LAUNCHED();
+}
+
+void launch_attention_tail(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
+                           long long kv_row_stride, float* out, long long out_ld, int nq, int c, int heads, int window,
+                           cudaStream_t st, int nseg) {
+  SV_CHECK(nq >= 1 && nq <= ATT_TAIL_MAX_KEYS && c >= 1 && c <= nq && (kv_row_stride % 4) == 0, "attention_tail: unsupported shape");
+  launch_pdl(attention_tail_kernel, dim3(nseg * c, heads), dim3(ATT_TAIL_MAX_KEYS), 0, st, q, q_ld, k, v, kv_head_stride,
+             kv_row_stride, out, out_ld, nq, c, window);
   SV_LAUNCHED();
 }
 

@@ -116,6 +116,19 @@ int svanon_resample(svanon_engine* e, const float* wave, int64_t n_in, const flo
   });
 }
 
+int svanon_noise_mix(svanon_engine* e, const float* x, const float* noise, int64_t n, float alpha, float* out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && x && noise && out, "null argument");
+    SV_CHECK(n >= 1 && n <= (1ll << 24), "element count out of range (1 .. 2^24)");
+    Args a(e, stream, (size_t)n * 12 + 65536);
+    const float* xd = a.in(x, (size_t)n);
+    const float* nd = a.in(noise, (size_t)n);
+    float* o = a.out(out, (size_t)n);
+    launch_noise_mix(xd, nd, n, alpha, o, a.st);
+    a.finish();
+  });
+}
+
 int svanon_ar_decode_many(svanon_stream* const* streams, int n, const int64_t* content_ids, const float* noise,
                           int32_t* codes_out, void* stream) {
   return guarded([&] {

@@ -184,6 +184,9 @@ void launch_conv_post(const float* x /*[L][16] with 12 margin rows*/, const floa
                       float* out, int L, cudaStream_t st, int seg_rows = 0, long long x_seg = 0);
 void launch_resample(const float* x, long long n_in, const float* kern /*[new][taps]*/, int orig, int nw, int width, int taps,
                      float* out, long long n_out, cudaStream_t st);
+// out = alpha * x + (1 - alpha) * (noise * std(x) + mean(x)), std unbiased over all n elements (apply_noise_mixing,
+// evaluations/infer_arvc.py:228-232); statistics accumulated in fp64 by one CTA (n is 192 or 4096 in the reference)
+void launch_noise_mix(const float* x, const float* noise, long long n, float alpha, float* out, cudaStream_t st);
 void launch_gather_rows(const float* table, const long long* idx, float* out, int rows, int C, long long out_ld,
                         cudaStream_t st);
 // out[t] = sum_i table[codes[i][t] + i*1000]  (BaseTransformer.embed)
@@ -206,6 +209,13 @@ void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t 
 void launch_attention(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
                       long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
                       cudaStream_t st, int nseg = 1);
+// Only the last `c` queries of every segment (positions nq-c .. nq-1, nq <= 128 keys): one CTA per (query, head), one
+// thread per key.  out is compact: row seg*c + j.  Used by the last layer of the streaming window encode, whose other
+// rows nobody reads (infer_arvc.py:506-518 keeps the last `chunk` ids).
+constexpr int ATT_TAIL_MAX_KEYS = 128;
+void launch_attention_tail(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
+                           long long kv_row_stride, float* out, long long out_ld, int nq, int c, int heads, int window,
+                           cudaStream_t st, int nseg);
 // scatter k,v of a fused qkv buffer into a [H][max_seq][64] cache at positions pos0..pos0+rows-1
 void launch_kv_append(const float* qkv, int rows, int heads, float* kc, float* vc, int max_seq, int pos0,
                       cudaStream_t st);

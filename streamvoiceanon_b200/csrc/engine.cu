@@ -612,8 +612,12 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
 
 // enc_transformer_bsq: WindowLimitedTransformer (windowed_transformer.py:337-354) over S tokens per stream, positions
 // 0..S-1 in every stream, in place on xt [B][S][512]; then the 13-bit BSQ ids (bsq.py:330-369).
-void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st) {
+// keep_last = c > 0: the caller reads the ids of the last c tokens of every stream only (the streaming loop,
+// infer_arvc.py:506-518), so the LAST layer runs its queries, output projection and MLP for those rows alone -- keys and
+// values of that layer still come from all S tokens.  ids_dev keeps its [B][S] layout; only columns S-c.. are written.
+void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st, int keep_last) {
   const int BS = B * S;
+  const bool tail_only = enc_tail_only && keep_last > 0 && keep_last < S && S <= ATT_TAIL_MAX_KEYS;
   float* nrm = ws.alloc_f((long long)BS * ENC_DIM);
   float* qkv = ws.alloc_f((long long)BS * 3 * ENC_DIM);
   float* y = ws.alloc_f((long long)BS * ENC_DIM);
@@ -626,6 +630,36 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
     p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = BS; p.N = 3 * ENC_DIM; p.K = ENC_DIM; p.lda = ENC_DIM; p.ldc = 3 * ENC_DIM;
     launch_gemm(p, st);
     launch_rope_qk(qkv, enc_rope, BS, ENC_HEADS, 0, st, B > 1 ? S : 0);
+    if (tail_only && l == ENC_LAYERS - 1) {
+      const int c = keep_last, R = B * c;
+      float* xtail = ws.alloc_f((long long)R * ENC_DIM);
+      long long* ids_tail = reinterpret_cast<long long*>(ws.alloc_f((long long)R * 2 + 4));
+      launch_attention_tail(qkv, 3 * ENC_DIM, qkv + ENC_DIM, qkv + 2 * ENC_DIM, HEAD_DIM, 3 * ENC_DIM, y, ENC_DIM, S, c,
+                            ENC_HEADS, ENC_WINDOW, st, B);
+      SV_CUDA(cudaMemcpy2DAsync(xtail, (size_t)c * ENC_DIM * sizeof(float), xt + (long long)(S - c) * ENC_DIM,
+                                (size_t)S * ENC_DIM * sizeof(float), (size_t)c * ENC_DIM * sizeof(float), B,
+                                cudaMemcpyDeviceToDevice, st));
+      GemmParams po;
+      po.A = y; po.W = L.wo; po.C = xtail; po.gamma = L.ls_attn; po.residual = xtail; po.M = R; po.N = ENC_DIM; po.K = ENC_DIM;
+      po.lda = ENC_DIM; po.ldc = ENC_DIM; po.ldr = ENC_DIM;
+      launch_gemm(po, st);
+      launch_rmsnorm(xtail, nrm, L.ffn_norm, R, ENC_DIM, 1e-5f, st);
+      GemmParams p1;
+      p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = R; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM; p1.ldc = 2 * ENC_INTER;
+      GemmParams p13[2] = {p1, p1};
+      p13[1].W = L.w3; p13[1].C = h13 + ENC_INTER;
+      launch_gemm(p13, 2, st);
+      launch_silu_mul(h13, gbuf, R, ENC_INTER, st);
+      GemmParams p2;
+      p2.A = gbuf; p2.W = L.w2; p2.C = xtail; p2.gamma = L.ls_ffn; p2.residual = xtail; p2.M = R; p2.N = ENC_DIM; p2.K = ENC_INTER;
+      p2.lda = ENC_INTER; p2.ldc = ENC_DIM; p2.ldr = ENC_DIM;
+      launch_gemm(p2, st);
+      launch_rmsnorm(xtail, nrm, enc_norm_w, R, ENC_DIM, 1e-5f, st);
+      launch_bsq(nrm, bsq_w, bsq_b, ids_tail, R, st);
+      SV_CUDA(cudaMemcpy2DAsync(ids_dev + (S - c), (size_t)S * sizeof(long long), ids_tail, (size_t)c * sizeof(long long),
+                                (size_t)c * sizeof(long long), B, cudaMemcpyDeviceToDevice, st));
+      return;
+    }
     launch_attention(qkv, 3 * ENC_DIM, qkv + ENC_DIM, qkv + 2 * ENC_DIM, HEAD_DIM, 3 * ENC_DIM, y, ENC_DIM, S, 0,
                      ENC_HEADS, ENC_WINDOW, st, B);
     GemmParams po;
@@ -750,7 +784,7 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
   state.valid = true;
   float* xt = ws.alloc_f((long long)B * S * ENC_DIM);
   SV_CUDA(cudaMemcpyAsync(xt, xt_state, (size_t)B * S * ENC_DIM * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  enc_transformer_bsq(xt, B, S, ids_dev, st);
+  enc_transformer_bsq(xt, B, S, ids_dev, st, c);
 }
 
 // ------------------------------------------------------------------------------------------ prompt path: wave -> codec ids

@@ -233,6 +233,8 @@ struct Engine {
   const float *w4s = nullptr, *w4e = nullptr;
   float *ar_x = nullptr, *ar_h = nullptr, *ar_q = nullptr, *ar_g = nullptr, *ar_part = nullptr, *ar_logits = nullptr;
   unsigned* ar_barrier = nullptr;
+  // last encoder layer for the kept tokens only (enc_transformer_bsq); SVANON_ENC_TAIL_ONLY=0 runs it for all rows
+  bool enc_tail_only = [] { const char* e = getenv("SVANON_ENC_TAIL_ONLY"); return !e || atoi(e) != 0; }();
   int ar_barrier_mode = 0;                     // grid barrier of the persistent decode kernels (ar_decode_common.cuh)
   float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
   bool debug_logits = false;
@@ -283,7 +285,7 @@ struct Engine {
   void build_spectrogram_consts(int model);
   // FireflyArchitecture.encode of the vocoder (firefly.py:561-574): wave [B][n] -> codec ids int32 [B][8][n/2048]
   void voc_encode(const float* wave_dev, int B, long long n, int* codes_dev, cudaStream_t st);
-  void enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st);
+  void enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st, int keep_last = 0);
   // the window re-encode of the streaming loop with the conv-stack outputs kept between chunks (wave_ring [B][S*2048])
   void enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,
                        cudaStream_t st);

@@ -468,6 +468,49 @@ void launch_resample(const float* x, long long n_in, const float* kern, int orig
   SV_LAUNCHED();
 }
 
+namespace {
+constexpr int NMIX_THREADS = 512;
+
+__device__ __forceinline__ double nmix_block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                                    // red may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < NMIX_THREADS / 32; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(NMIX_THREADS)
+noise_mix_kernel(const float* x, const float* __restrict__ noise, long long n, float alpha, float* out) {   // out may alias x
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double red[NMIX_THREADS / 32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += NMIX_THREADS) s += (double)x[i];
+  const double mean = nmix_block_sum(s, red) / (double)n;
+  double q = 0.0;
+  for (long long i = threadIdx.x; i < n; i += NMIX_THREADS) {
+    const double d = (double)x[i] - mean;
+    q += d * d;
+  }
+  const double var = nmix_block_sum(q, red) / (double)(n - 1);      // n == 1: 0/0 = NaN, like torch.std
+  const float meanf = (float)mean, stdf = (float)sqrt(var);
+  for (long long i = threadIdx.x; i < n; i += NMIX_THREADS) {
+    const float nz = noise[i] * stdf + meanf;
+    out[i] = alpha * x[i] + (1.f - alpha) * nz;
+  }
+}
+}  // namespace
+
+void launch_noise_mix(const float* x, const float* noise, long long n, float alpha, float* out, cudaStream_t st) {
+  if (n <= 0) return;
+  launch_pdl(noise_mix_kernel, dim3(1), dim3(NMIX_THREADS), 0, st, x, noise, n, alpha, out);
+  SV_LAUNCHED();
+}
+
 void launch_gather_rows(const float* table, const long long* idx, float* out, int rows, int C, long long out_ld,
                         cudaStream_t st) {
   if (rows <= 0) return;

@@ -435,6 +435,32 @@ def test_vocoder_encode_batched_and_ragged_vs_oracle(models, weights):
     assert np.array_equal(ragged[0].cpu().numpy(), want[0].numpy())
 
 
+def test_noise_mixing_vs_reference(models, gold):
+    """svanon_noise_mix against the unmodified reference method
+    (`InferenceWrapper.apply_noise_mixing`, infer_arvc.py:228-232) on the recorded draws, host and device buffers, and
+    against the oracle; fp32, tolerance 1e-6 absolute.  With `noise=None` the shim draws `torch.randn_like` from the
+    global generator where the reference does."""
+    from oracle import prompt as P
+    from streamvoiceanon_b200.prompt import apply_noise_mixing
+    g = gold("noise_mix")
+    for n in g["names"]:
+        x, nz, alpha = torch.from_numpy(g[f"x_{n}"]), torch.from_numpy(g[f"noise_{n}"]), float(g[f"alpha_{n}"])
+        y_host = apply_noise_mixing(x, alpha, nz)                                # host buffers through the C ABI
+        y_dev = apply_noise_mixing(x.cuda(), alpha, nz.cuda())
+        assert not y_host.is_cuda and y_dev.is_cuda and y_host.shape == x.shape
+        assert np.abs(y_host.numpy() - g[f"y_{n}"]).max() < 1e-6, n
+        assert np.array_equal(y_dev.cpu().numpy(), y_host.numpy()), n
+        assert np.abs(y_host.numpy() - P.apply_noise_mixing(g[f"x_{n}"], alpha, g[f"noise_{n}"])).max() < 1e-6, n
+    x = torch.from_numpy(g["x_style"]).cuda()
+    torch.manual_seed(5)
+    a = apply_noise_mixing(x, 0.7)
+    torch.manual_seed(5)
+    b = apply_noise_mixing(x, 0.7, torch.randn_like(x))
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        apply_noise_mixing(x, 0.7, torch.zeros(3))
+
+
 # ------------------------------------------------------------------------------------------------ limits
 def test_limits_kv_cache_full_and_maximum_lengths(models):
     """Maximum sizes: a full KV cache refuses to decode further (the reference would index out of range,

@@ -173,3 +173,18 @@ def test_vocoder_encode_oracle_vs_reference(gold, weights):
             codes = V.wav2codes(wav, weights["voc_enc"])
         assert codes.dtype == torch.int32
         assert np.array_equal(codes.numpy(), g[f"codes_{n}"]), n
+
+
+def test_noise_mixing_oracle_vs_reference(gold):
+    """the anonymisation mix of `InferenceWrapper.apply_noise_mixing` (infer_arvc.py:228-232)
+    restated in oracle/prompt.py against outputs of the unmodified reference method on the same draws
+    (tests/golden/noise_mix.npz, oracle/make_golden_noise_mix.py).  fp32, tolerance 1e-6 absolute (statistics are
+    accumulated in a different order)."""
+    from oracle import prompt as P
+    g = gold("noise_mix")
+    for n in g["names"]:
+        y = P.apply_noise_mixing(g[f"x_{n}"], float(g[f"alpha_{n}"]), g[f"noise_{n}"])
+        assert y.shape == g[f"y_{n}"].shape and y.dtype == np.float32
+        assert np.abs(y - g[f"y_{n}"]).max() < 1e-6, n
+    # alpha = 1 returns the input unchanged, alpha = 0 pure (re-scaled) noise
+    assert np.array_equal(P.apply_noise_mixing(g["x_timbre_a1"], 1.0, g["noise_timbre_a1"]), g["x_timbre_a1"])
