@@ -48,6 +48,15 @@ def test_tcgen05_3xtf32_gemm(M, N, K):
     assert err < 2e-5 * max(1.0, float(ref.abs().max())), err
 
 
+@pytest.mark.parametrize("M,N,K", [(16384, 2048, 512), (16384, 512, 2048), (20992, 128, 512), (20000, 384, 1008),
+                                   (16500, 300, 784)])
+def test_tcgen05_wide_tiles(M, N, K):
+    """Shapes large enough for the 128 x 256 and 128 x 128 CTA tiles (many-stream batches), ragged M / N / K."""
+    out, ref = _run(2, M, N, K)
+    err = float((out.double() - ref).abs().max())
+    assert err < 2e-5 * max(1.0, float(ref.abs().max())), err
+
+
 def test_tcgen05_gelu_epilogue():
     out, ref = _run(2, 512, 1536, 384, act=1)
     assert float((out.double() - ref).abs().max()) < 3e-5
