@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=10, help="chunks of the CPU baseline sample (main arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--concurrent", default="64,128,144,160", help="stream counts of the lock-step batch sweep (N=1 only; '' = skip)")
+    ap.add_argument("--concurrent", default="64,128,160,176", help="stream counts of the lock-step batch sweep (N=1 only; '' = skip)")
     return ap.parse_args()
 
 

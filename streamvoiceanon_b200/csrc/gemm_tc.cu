@@ -33,7 +33,6 @@ constexpr int TBM = 128;
 struct TcBatch {
   GemmParams p[3];
   int split;
-  int dbg_skip;        // EXPERIMENT
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -75,23 +74,6 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long ad
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// same with the A operand in tensor memory (lane = row, one 32-bit column per K element, 8 columns per K-step)
-__device__ __forceinline__ void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc, unsigned idesc,
-                                             unsigned accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 8 consecutive columns of this thread's TMEM lane (warp w owns lanes (w & 3) * 32 .. +31)
-__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
-               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-               : "memory");
-}
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -128,11 +110,6 @@ __device__ __forceinline__ float4 ldg_nc(const float* p) {
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
-__device__ __forceinline__ float4 ldg_nc_l1(const float* p) {       // allocating: the neighbouring 16 bytes follow at once
-  float4 r;
-  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // Warp-specialised.  16 producer warps stream the K-slabs: every thread keeps TC_DEPTH slabs of its own 16-byte chunks
 // in flight in REGISTERS (plain 128-bit no-allocate loads; the weight chunks of the first slabs are requested before
@@ -144,22 +121,13 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f +
 // (TMEM -> registers -> global).  Split-K over a thread-block cluster: every rank parks its partial tile in its own
 // shared memory and then reduces (in fixed rank order) and writes ONE column slice of the tile, so the DSMEM reads are
 // spread over all ranks instead of being serialised in rank 0.
-//
-// TS = true: the A operand never touches shared memory.  The kernel above is bound by shared-memory traffic (per
-// 128 x 256 x 32 slab 96 KB of tile stores + 144 KB of operand reads by the three MMAs = 1920 clk at 128 B/clk against
-// 1536 clk of TF32 math; a 128 x 128 tile is worse, 1280 against 768), so the hi/lo A tiles are written to TENSOR MEMORY
-// instead (tcgen05.st, thread = row, 8 K-columns per thread and slab; 64 columns per stage next to the accumulator) and
-// the MMAs take A from there (tcgen05.mma [d], [a_tmem], b_desc): 64 + 96 KB per slab, below the math time.
-template <int BN, int STAGES, bool SPLIT, bool TS>
+template <int BN, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch batch) {
   constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;
-  constexpr int A_SMEM = TS ? 0 : 2 * A_FLOATS;
-  constexpr int STAGE_FLOATS = A_SMEM + 2 * B_FLOATS;                 // [A_hi | A_lo |] B_hi | B_lo
+  constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;           // A_hi | A_lo | B_hi | B_lo
   constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = BN * 8 / TC_PRODUCERS;   // 16-byte chunks per thread
   constexpr int D = TC_DEPTH;
-  constexpr int TCOLS = TS ? 512 : BN;                                // TMEM: accumulator [0, BN) | A stages of 64 columns
-  static_assert(!TS || (BN + STAGES * 2 * TK <= 512 && !SPLIT && A_PER == 2), "TS layout");
-  static_assert(!SPLIT || TBM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
+  static_assert(TBM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
   static_assert(A_PER >= 1 && B_PER >= 1, "tile too small for the producer count");
   extern __shared__ unsigned char dsmem_raw[];
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~(uintptr_t)1023);
@@ -188,7 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(TCOLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < BN; i += TC_THREADS) {
@@ -210,14 +178,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     unsigned a_soff[A_PER];
 #pragma unroll
     for (int j = 0; j < A_PER; ++j) {
-      // TS: thread = row (the TMEM lane this warp may write), warp >> 2 = which 8 of the slab's 32 K-columns
-      const int i = tid + j * TC_PRODUCERS;
-      const int row = TS ? (warp & 3) * 32 + lane : i >> 3, c = TS ? (warp >> 2) * 2 + j : i & 7;
+      const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
       const int m = m0 + row;
       a_ptr[j] = (m < p.M) ? p.A + gemm_a_row(p, m) + c * 4 : nullptr;
       a_soff[j] = (unsigned)swz(row, c) * 4u;
     }
-    const int a_c4 = TS ? (warp >> 2) * 8 : (tid & 7) * 4;      // K offset of this thread's first A chunk inside a slab
     const float* b_ptr[B_PER];
     unsigned b_soff[B_PER];
 #pragma unroll
@@ -242,15 +207,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
       for (int j = 0; j < B_PER; ++j) dst[j] = (b_ptr[j] && k_ok) ? ldg_nc(b_ptr[j] + ld_b + ld_k) : zero4;
     };
     auto load_a = [&](float4 (&dst)[A_PER]) {
-      if constexpr (TS) {
+      const bool k_ok = (ld_k + c4) < p.K;
 #pragma unroll
-        for (int j = 0; j < A_PER; ++j)
-          dst[j] = (a_ptr[j] && (ld_k + a_c4 + 4 * j) < p.K) ? ldg_nc_l1(a_ptr[j] + ld_a + ld_k) : zero4;
-      } else {
-        const bool k_ok = (ld_k + a_c4) < p.K;
-#pragma unroll
-        for (int j = 0; j < A_PER; ++j) dst[j] = (a_ptr[j] && k_ok) ? ldg_nc(a_ptr[j] + ld_a + ld_k) : zero4;
-      }
+      for (int j = 0; j < A_PER; ++j) dst[j] = (a_ptr[j] && k_ok) ? ldg_nc(a_ptr[j] + ld_a + ld_k) : zero4;
     };
     auto advance = [&] {
       ld_k += TK;
@@ -311,44 +270,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
           }
           __syncwarp();
           const unsigned a_stage = smem_base + st_stage * (unsigned)(STAGE_FLOATS * 4);
-          const unsigned b_stage = a_stage + (unsigned)A_SMEM * 4u;
-          if constexpr (TS) {
-            float hi[8], lo[8];
+          const unsigned b_stage = a_stage + 2u * A_FLOATS * 4u;
 #pragma unroll
-            for (int j = 0; j < A_PER; ++j) {
-              float4 v = ra[d][j];
-              if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-              const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                hi[4 * j + q] = __uint_as_float(__float_as_uint(e[q]) & 0xFFFFE000u);
-                lo[4 * j + q] = e[q] - hi[4 * j + q];
-              }
-            }
-            const unsigned ta = tmem_d + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(BN + st_stage * 2 * TK + (warp >> 2) * 8);
-            tmem_st8(ta, hi);
-            tmem_st8(ta + TK, lo);
-          } else {
-#pragma unroll
-            for (int j = 0; j < A_PER; ++j) {
-              float4 v = ra[d][j];
-              if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-              split_sts(a_stage + a_soff[j], A_FLOATS * 4u, v);
-            }
+          for (int j = 0; j < A_PER; ++j) {
+            float4 v = ra[d][j];
+            if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
+            split_sts(a_stage + a_soff[j], A_FLOATS * 4u, v);
           }
-          if (!(batch.dbg_skip & 1)) {
 #pragma unroll
           for (int j = 0; j < B_PER; ++j) split_sts(b_stage + b_soff[j], B_FLOATS * 4u, rb[d][j]);
-          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the MMA
-          if constexpr (TS) {
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          }
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_base + st_stage * 8u) : "memory");
           if (++st_stage == STAGES) { st_stage = 0; st_parity ^= 1u; }
-          if (li + D < n_it) { if (!(batch.dbg_skip & 1)) load_b(rb[d]); if (!(batch.dbg_skip & 2)) load_a(ra[d]); advance(); }
+          if (li + D < n_it) { load_b(rb[d]); load_a(ra[d]); advance(); }
         }
       }
     }
@@ -364,26 +299,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
         mbar_wait(&full_bar[stage], (li / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* As = smem + stage * STAGE_FLOATS;
-        float* Bs = As + A_SMEM;
+        float* Bs = As + 2 * A_FLOATS;
+        const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
         const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
-        if constexpr (TS) {
-          const unsigned ta_hi = tmem_d + (unsigned)(BN + stage * 2 * TK), ta_lo = ta_hi + TK;
 #pragma unroll
-          for (int kk = 0; kk < TK / 8; ++kk) {
-            const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
-            umma_tf32_ts(tmem_d, ta_hi + kk * 8, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-            umma_tf32_ts(tmem_d, ta_lo + kk * 8, b_hi + adv, idesc, 1u);
-            umma_tf32_ts(tmem_d, ta_hi + kk * 8, b_hi + adv, idesc, 1u);
-          }
-        } else {
-          const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
-#pragma unroll
-          for (int kk = 0; kk < TK / 8; ++kk) {
-            const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
-            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
-            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
-          }
+        for (int kk = 0; kk < TK / 8; ++kk) {
+          const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
+          umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
+          umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+          umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
         }
         umma_commit(&empty_bar[stage]);
       }
@@ -404,68 +328,123 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TC_MARK(4);
   }
+  auto finish = [&](float (&v)[16], int m, int col0) {      // bias/act/gamma/residual/scale + store of 16 columns
+    const int n_base = n0 + col0;
+    const long long c_row = gemm_c_row(p, m);
+    float* dst = p.C + c_row + n_base;
+    const float* res = p.residual ? p.residual + gemm_r_row(p, m) + n_base : nullptr;
+    const bool vec = (n_base + 15 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float y = v[j] + s_bias[col0 + j];
+      if (p.act == ACT_GELU) y = gelu_erf(y);
+      else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
+      v[j] = y * s_gamma[col0 + j];
+    }
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (res) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(res + j));
+          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (n_base + j < p.N) {
+          float y = v[j];
+          if (res) y += __ldg(res + j);
+          y *= p.out_scale;
+          dst[j] = p.accumulate ? dst[j] + y : y;
+        }
+      }
+    }
+  };
   if (!SPLIT) {
     // A thread holds ROWS of the accumulator (TMEM lane = row), so direct stores would write 32 rows x 16 bytes per
     // instruction (32 sectors, half filled; the same for the residual loads): ~9 us per 128 x 256 tile, more than its
     // math at K = 512.  Every warp therefore transposes its 32 x CG block through its own slice of the (now idle)
     // pipeline shared memory and then reads the residual and writes C in whole row segments.
-    if (warp < TC_PRODUCER_WARPS) {
-      constexpr int SP = CG + 4;                      // padded row pitch of the staging block (floats)
-      static_assert(TC_PRODUCER_WARPS * 32 * SP <= STAGES * STAGE_FLOATS, "staging must fit the pipeline shared memory");
-      float* stg = smem + warp * (32 * SP);
-      const int cg0 = grp * CG;
+    if constexpr (BN >= 128) {
+      if (warp < TC_PRODUCER_WARPS) {
+        constexpr int SP = CG + 4;                      // padded row pitch of the staging block (floats)
+        static_assert(TC_PRODUCER_WARPS * 32 * SP <= STAGES * STAGE_FLOATS, "staging must fit the pipeline shared memory");
+        float* stg = smem + warp * (32 * SP);
+        const int cg0 = grp * CG;
 #pragma unroll
-      for (int c0 = 0; c0 < CG; c0 += 16) {
-        float v[16];
-        if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(quad * 32) << 16) + cg0 + c0, v);
-        else {
+        for (int c0 = 0; c0 < CG; c0 += 16) {
+          float v[16];
+          if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(quad * 32) << 16) + cg0 + c0, v);
+          else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float y = v[j] + s_bias[cg0 + c0 + j];
-          if (p.act == ACT_GELU) y = gelu_erf(y);
-          else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
-          v[j] = y * s_gamma[cg0 + c0 + j];
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * SP + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-      __syncwarp();
-      constexpr int LPR = CG / 4;                     // lanes per row (one float4 each)
-      constexpr int RPI = 32 / LPR;                   // rows per instruction
-      const int rr = lane / LPR, c = (lane % LPR) * 4;
-      const int n_base = n0 + cg0 + c;
-#pragma unroll 4
-      for (int r0 = 0; r0 < 32; r0 += RPI) {
-        const int r = r0 + rr;
-        const int m = m0 + quad * 32 + r;
-        if (m >= p.M || n_base >= p.N) continue;
-        float4 o = *reinterpret_cast<const float4*>(stg + r * SP + c);
-        float* dst = p.C + gemm_c_row(p, m) + n_base;
-        const float* res = p.residual ? p.residual + gemm_r_row(p, m) + n_base : nullptr;
-        const bool vec = (n_base + 3 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                         (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
-        if (vec) {
-          if (res) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(res));
-            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
-          o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
-          *reinterpret_cast<float4*>(dst) = o;
-        } else {
-          const float e[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n_base + j < p.N) {
-              float y = e[j];
-              if (res) y += __ldg(res + j);
-              y *= p.out_scale;
-              dst[j] = p.accumulate ? dst[j] + y : y;
+          for (int j = 0; j < 16; ++j) {
+            float y = v[j] + s_bias[cg0 + c0 + j];
+            if (p.act == ACT_GELU) y = gelu_erf(y);
+            else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
+            v[j] = y * s_gamma[cg0 + c0 + j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * SP + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncwarp();
+        constexpr int LPR = CG / 4;                     // lanes per row (one float4 each)
+        constexpr int RPI = 32 / LPR;                   // rows per instruction
+        const int rr = lane / LPR, c = (lane % LPR) * 4;
+        const int n_base = n0 + cg0 + c;
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+          const int r = r0 + rr;
+          const int m = m0 + quad * 32 + r;
+          if (m >= p.M || n_base >= p.N) continue;
+          float4 o = *reinterpret_cast<const float4*>(stg + r * SP + c);
+          float* dst = p.C + gemm_c_row(p, m) + n_base;
+          const float* res = p.residual ? p.residual + gemm_r_row(p, m) + n_base : nullptr;
+          const bool vec = (n_base + 3 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                           (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
+          if (vec) {
+            if (res) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res));
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            }
+            o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            const float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n_base + j < p.N) {
+                float y = e[j];
+                if (res) y += __ldg(res + j);
+                y *= p.out_scale;
+                dst[j] = p.accumulate ? dst[j] + y : y;
+              }
             }
           }
+        }
+      }
+    } else {
+      // 128 x 64 tile: a thread's 16 columns are two whole sectors already
+      if (warp < TC_PRODUCER_WARPS) {
+        const int row = quad * 32 + lane;
+        const int m = m0 + row;
+#pragma unroll
+        for (int c0 = grp * CG; c0 < (grp + 1) * CG; c0 += 16) {
+          float v[16];
+          if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(quad * 32) << 16) + c0, v);
+          else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+          if (m < p.M) finish(v, m, c0);
         }
       }
     }
@@ -524,337 +503,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   if (SPLIT) cluster.sync();
   else __syncthreads();
   TC_MARK(6);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCOLS) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Persistent variant for large problems (many CTA tiles per SM).  The kernel above spends 10-15 us per 128 x 256 tile
-// outside its main loop (prologue, first loads, epilogue, CTA turnover) while the tensor pipe idles -- as much as the
-// MMAs of a K = 512 tile take.  Here one CTA per SM walks over tiles; the accumulator is double-buffered in tensor
-// memory (2 x BN columns) and 4 dedicated epilogue warps drain tile i (TMEM -> registers -> bias / activation /
-// layer-scale -> a small per-warp transpose in shared memory -> residual + row-segment stores) while the 16 producer
-// warps and the MMA thread already run tile i + 1.  Barriers: full/empty per pipeline stage (as above, phases
-// continue across tiles), acc_full[buf] (tcgen05.commit after a tile's last MMA), acc_empty[buf] (the 4 epilogue warps).
-#ifndef SVANON_TCP_EPI_WARPS
-#define SVANON_TCP_EPI_WARPS 4
-#endif
-constexpr int TCP_EPI_WARPS = SVANON_TCP_EPI_WARPS;   // 4 or 8: warp & 3 = TMEM lane quadrant, (index / 4) = column share
-constexpr int TCP_THREADS = TC_THREADS + TCP_EPI_WARPS * 32;
-constexpr int TCP_CHUNK = 16;                      // columns per epilogue step
-constexpr int TCP_SP = TCP_CHUNK + 4;              // padded row pitch of the per-warp staging block (floats)
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(const TcBatch batch, int tiles_m, int tiles_n, int n_tiles) {
-  constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;
-  constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;           // A_hi | A_lo | B_hi | B_lo
-  constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = BN * 8 / TC_PRODUCERS;
-  constexpr int D = TC_DEPTH;
-  constexpr int TCOLS = 2 * BN;
-  static_assert(TCOLS == 256 || TCOLS == 512, "two accumulators must be a power-of-two column count");
-  extern __shared__ unsigned char dsmem_raw[];
-  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~(uintptr_t)1023);
-  float* stg_all = smem + STAGES * STAGE_FLOATS;
-  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
-  __shared__ unsigned tmem_holder;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int per_problem = tiles_m * tiles_n;
-  pdl_trigger();
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
-#pragma unroll
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TCP_EPI_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(TCOLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned tmem_d = tmem_holder;
-
-  if (warp < TC_PRODUCER_WARPS) {
-    // =========================================================== producers (see gemm_tc_kernel)
-    const unsigned smem_base = smem_u32(smem);
-    const unsigned full_base = smem_u32(&full_bar[0]), empty_base = smem_u32(&empty_bar[0]);
-    unsigned st_stage = 0, st_parity = 1;
-    const int c4 = (tid & 7) * 4;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto sts4 = [](unsigned addr, float4 v) {
-      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    };
-    auto split_sts = [&](unsigned hi_addr, unsigned lo_delta, float4 v) {
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-      sts4(hi_addr, h);
-      sts4(hi_addr + lo_delta, l);
-    };
-    bool first = true;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int zb = t / per_problem, rem = t - zb * per_problem;
-      const int mt = rem / tiles_n, nt = rem - mt * tiles_n;
-      const GemmParams& p = batch.p[zb];
-      const int m0 = mt * TBM, n0 = nt * BN;
-      const int kSlabs = (p.K + TK - 1) / TK;
-      const int n_it = kSlabs * p.taps;
-      const float* a_ptr[A_PER];
-      unsigned a_soff[A_PER];
-#pragma unroll
-      for (int j = 0; j < A_PER; ++j) {
-        const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
-        const int m = m0 + row;
-        a_ptr[j] = (m < p.M) ? p.A + gemm_a_row(p, m) + c * 4 : nullptr;
-        a_soff[j] = (unsigned)swz(row, c) * 4u;
-      }
-      const float* b_ptr[B_PER];
-      unsigned b_soff[B_PER];
-#pragma unroll
-      for (int j = 0; j < B_PER; ++j) {
-        const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
-        const int n = n0 + row;
-        b_ptr[j] = (n < p.N) ? p.W + (long long)n * p.K + c * 4 : nullptr;
-        b_soff[j] = (unsigned)swz(row, c) * 4u;
-      }
-      const bool silu = p.prologue == PRO_SILU;
-      const long long tap_stride = (long long)p.N * p.K;
-      int ld_t = 0, ld_k = 0;
-      long long ld_a = (long long)p.tap_off[0] * p.lda, ld_b = 0;
-      float4 ra[D][A_PER], rb[D][B_PER];
-      auto load_b = [&](float4 (&dst)[B_PER]) {
-        const bool k_ok = (ld_k + c4) < p.K;
-#pragma unroll
-        for (int j = 0; j < B_PER; ++j) dst[j] = (b_ptr[j] && k_ok) ? ldg_nc(b_ptr[j] + ld_b + ld_k) : zero4;
-      };
-      auto load_a = [&](float4 (&dst)[A_PER]) {
-        const bool k_ok = (ld_k + c4) < p.K;
-#pragma unroll
-        for (int j = 0; j < A_PER; ++j) dst[j] = (a_ptr[j] && k_ok) ? ldg_nc(a_ptr[j] + ld_a + ld_k) : zero4;
-      };
-      auto advance = [&] {
-        ld_k += TK;
-        if (ld_k >= kSlabs * TK) {
-          ld_k = 0;
-          ++ld_t;
-          ld_a = (long long)p.tap_off[ld_t < p.taps ? ld_t : 0] * p.lda;
-          ld_b += tap_stride;
-        }
-      };
-      if (first) {                                     // weights do not depend on the previous kernel
-        const int t0 = ld_t, k0 = ld_k;
-        const long long a0 = ld_a, b0 = ld_b;
-#pragma unroll
-        for (int d = 0; d < D; ++d)
-          if (d < n_it) { load_b(rb[d]); advance(); }
-        pdl_wait();
-        ld_t = t0; ld_k = k0; ld_a = a0; ld_b = b0;
-#pragma unroll
-        for (int d = 0; d < D; ++d)
-          if (d < n_it) { load_a(ra[d]); advance(); }
-        first = false;
-      } else {
-#pragma unroll
-        for (int d = 0; d < D; ++d)
-          if (d < n_it) { load_b(rb[d]); load_a(ra[d]); advance(); }
-      }
-      for (int li0 = 0; li0 < n_it; li0 += D) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const int li = li0 + d;
-          if (li < n_it) {
-            if (lane == 0) {
-              asm volatile(
-                  "{\n"
-                  ".reg .pred p;\n"
-                  "TCP_PW_LOOP:\n"
-                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                  "@p bra.uni TCP_PW_DONE;\n"
-                  "bra.uni TCP_PW_LOOP;\n"
-                  "TCP_PW_DONE:\n"
-                  "}\n" ::"r"(empty_base + st_stage * 8u), "r"(st_parity) : "memory");
-            }
-            __syncwarp();
-            const unsigned a_stage = smem_base + st_stage * (unsigned)(STAGE_FLOATS * 4);
-            const unsigned b_stage = a_stage + 2u * A_FLOATS * 4u;
-#pragma unroll
-            for (int j = 0; j < A_PER; ++j) {
-              float4 v = ra[d][j];
-              if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-              split_sts(a_stage + a_soff[j], A_FLOATS * 4u, v);
-            }
-#pragma unroll
-            for (int j = 0; j < B_PER; ++j) split_sts(b_stage + b_soff[j], B_FLOATS * 4u, rb[d][j]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_base + st_stage * 8u) : "memory");
-            if (++st_stage == STAGES) { st_stage = 0; st_parity ^= 1u; }
-            if (li + D < n_it) { load_b(rb[d]); load_a(ra[d]); advance(); }
-          }
-        }
-      }
-    }
-  } else if (warp == TC_PRODUCER_WARPS) {
-    if (lane == 0) {
-      // =========================================================== MMA issuer
-      const unsigned idesc = umma_idesc(BN);
-      unsigned stage = 0, parity = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const GemmParams& p = batch.p[t / per_problem];
-        const int n_it = (p.K + TK - 1) / TK * p.taps;
-        const unsigned buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);       // the epilogue drained this accumulator (first use: free)
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned acc = tmem_d + buf * BN;
-        for (int li = 0; li < n_it; ++li) {
-          mbar_wait(&full_bar[stage], parity);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          float* As = smem + stage * STAGE_FLOATS;
-          float* Bs = As + 2 * A_FLOATS;
-          const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
-          const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
-#pragma unroll
-          for (int kk = 0; kk < TK / 8; ++kk) {
-            const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);
-            umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-            umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, 1u);
-            umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; parity ^= 1u; }
-        }
-        umma_commit(&acc_full[buf]);
-      }
-    }
-  } else {
-    // =========================================================== epilogue warps: lane quadrant warp & 3, all BN columns
-    pdl_wait();                                      // residual / C belong to the previous kernel until it is done
-    const int quad = warp & 3;
-    float* stg = stg_all + (warp - TC_PRODUCER_WARPS - 1) * (32 * TCP_SP);
-    constexpr int LPR = TCP_CHUNK / 4, RPI = 32 / LPR;          // 4 lanes per row, 8 rows per instruction
-    const int rr = lane / LPR, c = (lane % LPR) * 4;
-    int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int zb = t / per_problem, rem = t - zb * per_problem;
-      const int mt = rem / tiles_n, nt = rem - mt * tiles_n;
-      const GemmParams& p = batch.p[zb];
-      const int m0 = mt * TBM, n0 = nt * BN;
-      const unsigned buf = it & 1;
-      if (lane == 0) mbar_wait(&acc_full[buf], (it >> 1) & 1);
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned acc = tmem_d + ((unsigned)(quad * 32) << 16) + buf * BN;
-      constexpr int COLS_PER_WARP = BN / (TCP_EPI_WARPS / 4);
-      const int col_begin = ((warp - TC_PRODUCER_WARPS - 1) >> 2) * COLS_PER_WARP;
-#pragma unroll 1
-      for (int c0 = col_begin; c0 < col_begin + COLS_PER_WARP; c0 += TCP_CHUNK) {
-        if (n0 + c0 >= p.N) break;
-        float v[16];
-        tmem_ld16(acc + c0, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          const bool ok = n < p.N;
-          float y = v[j] + ((p.bias && ok) ? __ldg(p.bias + n) : 0.f);
-          if (p.act == ACT_GELU) y = gelu_erf(y);
-          else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
-          v[j] = y * ((p.gamma && ok) ? __ldg(p.gamma + n) : 1.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * TCP_SP + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        const int n_base = n0 + c0 + c;
-#pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += RPI) {
-          const int r = r0 + rr;
-          const int m = m0 + quad * 32 + r;
-          if (m >= p.M || n_base >= p.N) continue;
-          float4 o = *reinterpret_cast<const float4*>(stg + r * TCP_SP + c);
-          float* dst = p.C + gemm_c_row(p, m) + n_base;
-          const float* res = p.residual ? p.residual + gemm_r_row(p, m) + n_base : nullptr;
-          const bool vec = (n_base + 3 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                           (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
-          if (vec) {
-            if (res) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res));
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-            }
-            o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
-            *reinterpret_cast<float4*>(dst) = o;
-          } else {
-            const float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n_base + j < p.N) {
-                float y = e[j];
-                if (res) y += __ldg(res + j);
-                y *= p.out_scale;
-                dst[j] = p.accumulate ? dst[j] + y : y;
-              }
-            }
-          }
-        }
-        __syncwarp();                                // the staging block is rewritten by the next chunk
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
-    }
-  }
-  __syncwarp();
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCOLS) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
 }
 
 template <int BN, int STAGES>
-void launch_tcp_cfg(TcBatch& b, int count, cudaStream_t st) {
-  constexpr size_t SMEM = (size_t)STAGES * (2 * TBM * TK + 2 * BN * TK) * sizeof(float) +
-                          (size_t)TCP_EPI_WARPS * 32 * TCP_SP * sizeof(float) + 1024;
-  const GemmParams& p = b.p[0];
-  const int tiles_m = (p.M + TBM - 1) / TBM, tiles_n = (p.N + BN - 1) / BN;
-  const int n_tiles = tiles_m * tiles_n * count;
-  b.split = 1;
-  b.dbg_skip = 0;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    SV_CUDA(cudaGetDevice(&dev));
-    SV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SV_CUDA(cudaFuncSetAttribute(gemm_tcp_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(std::min(n_tiles, sms));
-  cfg.blockDim = dim3(TCP_THREADS);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcp_kernel<BN, STAGES>, b, tiles_m, tiles_n, n_tiles));
-}
-
-template <int BN, int STAGES, bool TS = false>
 void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
-  constexpr size_t SMEM = (size_t)STAGES * ((TS ? 0 : 2 * TBM * TK) + 2 * BN * TK) * sizeof(float) + 1024;
+  constexpr size_t SMEM = (size_t)STAGES * (2 * TBM * TK + 2 * BN * TK) * sizeof(float) + 1024;
   const GemmParams& p = b.p[0];
   dim3 grid((p.N + BN - 1) / BN, (p.M + TBM - 1) / TBM, count * split);
   b.split = split;
-  static const int dbg = [] { const char* e = getenv("SVANON_TC_DBG_SKIP"); return e ? atoi(e) : 0; }();
-  b.dbg_skip = dbg;
   static bool configured = false;
   if (!configured) {
-    if constexpr (!TS)
-      SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -871,13 +532,8 @@ void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
   attr[1].val.clusterDim.z = split;
   cfg.attrs = attr;
   cfg.numAttrs = split > 1 ? 2 : 1;
-  if constexpr (TS) {
-    SV_CHECK(split == 1, "the tensor-memory-operand variant has no split-K");
-    SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false, true>, b));
-  } else {
-    if (split > 1) SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true, false>, b));
-    else SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false, false>, b));
-  }
+  if (split > 1) SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, b));
+  else SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false>, b));
 }
 
 }  // namespace
@@ -932,31 +588,9 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
   // pipe 26 %): a wider tile amortises the A tile over more MMA work.  128 x 256 when the grid still fills the GPU and
   // the padded width does not waste more than 128 x 128 tiles would.
   auto padded = [&](int bn) { return (long long)((p.N + bn - 1) / bn) * bn; };
-  static const int use_ts = [] {
-    const char* e = getenv("SVANON_TC_TS");             // tuning knob: A operand in tensor memory (0: in shared memory)
-    return e ? atoi(e) : 0;
-  }();
-  static const int persist = [] {
-    const char* e = getenv("SVANON_TC_PERSIST");        // tuning knob: persistent CTAs with overlapped epilogue (0: off)
-    return e ? atoi(e) : 0;
-  }();
-  // persistent when every SM gets at least ~2 tiles (knob value > 1: that many tiles, for tests)
-  const long long persist_min = persist == 1 ? 2 * 148 : persist;
-  if (persist && max_bn >= 256 && ctas(256) >= persist_min && p.N >= 256 && padded(256) * 100 <= padded(128) * 107) {
-    launch_tcp_cfg<256, 2>(b, count, st);
-    return true;
-  }
-  if (persist && max_bn >= 128 && ctas(128) >= persist_min && p.N >= 128) {
-    launch_tcp_cfg<128, 3>(b, count, st);
-    return true;
-  }
-  if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107) {
-    if (use_ts) launch_tc_cfg<256, 3, true>(b, count, 1, st);
-    else launch_tc_cfg<256, 2>(b, count, 1, st);
-  } else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) {
-    if (use_ts) launch_tc_cfg<128, 4, true>(b, count, 1, st);
-    else launch_tc_cfg<128, 3>(b, count, 1, st);
-  }
+  if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107)
+    launch_tc_cfg<256, 2>(b, count, 1, st);
+  else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 3>(b, count, 1, st);
   else launch_tc_cfg<64, 4>(b, count, pick_split(ctas(64)), st);
   return true;
 }
