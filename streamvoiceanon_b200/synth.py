@@ -201,6 +201,62 @@ def make_vocoder_encoder_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]
     return b.sd
 
 
+def make_campplus_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """Style encoder checkpoint (`pretrained_checkpoints/campplus_cn_common.bin`, configs/hydra_arcs/sv/campplus.yaml:
+    CAMPPlus(feat_dim=80, embedding_size=192)); key names and shapes per modules/campplus/DTDNN.py:13-112 and
+    modules/campplus/layers.py:10-266.  BatchNorm running statistics are non-trivial (eval-mode affine maps)."""
+    b = _Builder(seed + 11)
+
+    def bn(key, dim, affine=True):
+        if affine:
+            b.sd[key + ".weight"] = 1.0 + 0.1 * _randn(key + ".weight", b.seed, dim)
+            b.sd[key + ".bias"] = 0.05 * _randn(key + ".bias", b.seed, dim)
+        b.sd[key + ".running_mean"] = 0.1 * _randn(key + ".running_mean", b.seed, dim)
+        b.sd[key + ".running_var"] = 1.0 + 0.2 * _randn(key + ".running_var", b.seed, dim).abs()
+        b.sd[key + ".num_batches_tracked"] = torch.tensor(1000, dtype=torch.long)
+
+    def conv2d(key, out_c, in_c, k):
+        b.sd[key + ".weight"] = _randn(key + ".weight", b.seed, out_c, in_c, k, k) * (1.4 / math.sqrt(in_c * k * k))
+
+    # FCM head (DTDNN.py:13-48): conv1/bn1, two stages of two BasicResBlocks (layers.py:223-266), conv2/bn2
+    conv2d("head.conv1", 32, 1, 3)
+    bn("head.bn1", 32)
+    for layer in (1, 2):
+        for blk in (0, 1):
+            pre = f"head.layer{layer}.{blk}"
+            conv2d(pre + ".conv1", 32, 32, 3)
+            bn(pre + ".bn1", 32)
+            conv2d(pre + ".conv2", 32, 32, 3)
+            bn(pre + ".bn2", 32)
+            if blk == 0:                                   # stride (2, 1): 1x1 conv + BN shortcut
+                conv2d(pre + ".shortcut.0", 32, 32, 1)
+                bn(pre + ".shortcut.1", 32)
+    conv2d("head.conv2", 32, 32, 3)
+    bn("head.bn2", 32)
+    # x-vector trunk (DTDNN.py:63-95)
+    b.linear("xvector.tdnn.linear", 128, 320, gain=1.4, extra=(5,))
+    bn("xvector.tdnn.nonlinear.batchnorm", 128)
+    channels = 128
+    for i, (num_layers, _k, _d) in enumerate(zip((12, 24, 16), (3, 3, 3), (1, 2, 2))):
+        for j in range(num_layers):
+            pre = f"xvector.block{i + 1}.tdnnd{j + 1}"
+            cin = channels + j * 32
+            bn(pre + ".nonlinear1.batchnorm", cin)
+            b.linear(pre + ".linear1", 128, cin, gain=1.4, extra=(1,))
+            bn(pre + ".nonlinear2.batchnorm", 128)
+            b.linear(pre + ".cam_layer.linear_local", 32, 128, gain=1.4, extra=(3,))
+            b.linear(pre + ".cam_layer.linear1", 64, 128, gain=1.4, bias=True, extra=(1,))
+            b.linear(pre + ".cam_layer.linear2", 32, 64, gain=2.0, bias=True, extra=(1,))
+        channels += num_layers * 32
+        bn(f"xvector.transit{i + 1}.nonlinear.batchnorm", channels)
+        b.linear(f"xvector.transit{i + 1}.linear", channels // 2, channels, gain=1.4, extra=(1,))
+        channels //= 2
+    bn("xvector.out_nonlinear.batchnorm", channels)
+    b.linear("dense.linear", 192, 2 * channels, extra=(1,))
+    bn("dense.nonlinear.batchnorm", 192, affine=False)
+    return b.sd
+
+
 def fold_weight_norm(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """w = g * v / ||v|| over dims (1,2) -- what `remove_parametrizations()` leaves behind
     (evaluations/infer_arvc.py:94, modules/vqgan/modules/firefly.py:105-111)."""

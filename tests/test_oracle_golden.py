@@ -188,3 +188,29 @@ def test_noise_mixing_oracle_vs_reference(gold):
         assert np.abs(y - g[f"y_{n}"]).max() < 1e-6, n
     # alpha = 1 returns the input unchanged, alpha = 0 pure (re-scaled) noise
     assert np.array_equal(P.apply_noise_mixing(g["x_timbre_a1"], 1.0, g["noise_timbre_a1"]), g["x_timbre_a1"])
+
+
+def test_style_vector_oracle_vs_reference(gold):
+    """SURVEY section 8f-3, style branch (groundwork: oracle only, the CUDA port of this row is not built): kaldi fbank
+    -> time-mean removal -> CAMPPlus restated in oracle/speaker.py against the reference's own
+    `calculate_style_vec` + torchaudio fbank (tests/golden/style_vec.npz, oracle/make_golden_style.py).  fp32;
+    tolerance 1e-4 on the log-mel features, 1e-5 on the embedding (summation order of the host BLAS)."""
+    from oracle import speaker as S
+    from streamvoiceanon_b200 import synth
+    g = gold("style_vec")
+    sd = synth.make_campplus_state_dict(int(g["weight_seed"]))
+    a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"]))[None]
+    b = synth.synth_audio_16k(int(g["seed_b"]), float(g["sec_b"]))[None]
+    fb = S.kaldi_fbank(a)
+    assert tuple(fb.shape) == g["fbank_a"].shape == (1 + (a.shape[1] - 400) // 160, 80)
+    assert np.abs(fb.numpy() - g["fbank_a"]).max() < 1e-4
+    with torch.no_grad():
+        sa = S.calculate_style_vec(a, torch.LongTensor([a.shape[1]]), sd)
+        batch = torch.zeros(2, a.shape[1])
+        batch[0], batch[1, : b.shape[1]] = a[0], b[0]
+        sb = S.calculate_style_vec(batch, torch.from_numpy(g["batch_lens"]), sd)
+    assert np.abs(sa.numpy() - g["style_a"]).max() < 1e-5
+    assert np.abs(sb.numpy() - g["style_batch"]).max() < 1e-5
+    # ragged row: padding with the row minimum must not leak into the masked statistics of the short row's ... long row
+    assert np.abs(sb.numpy()[0] - sa.numpy()[0]).max() < 1e-5
+    assert S.kaldi_fbank(a[:, :399]).shape[0] == 0               # shorter than one 25 ms frame: no frames
