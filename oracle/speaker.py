@@ -1,12 +1,18 @@
-"""CPU restatement of the style-vector branch of the prompt path.  TEST INFRASTRUCTURE ONLY --
-never imported by the product; groundwork for the CUDA port of this row (no CUDA counterpart yet).
+"""CPU restatement of the two speaker-embedding branches of the prompt path.  TEST
+INFRASTRUCTURE ONLY -- never imported by the product; groundwork for the CUDA port of this row (no CUDA counterpart yet).
 
     wave (16 kHz) -> kaldi fbank (80 bins) -> minus time-mean -> CAMPPlus -> style vector [192]
     (`InferenceWrapper.calculate_style_vec`, evaluations/infer_arvc.py:179-211)
+    wave (16 kHz) -> slaney mel magnitudes (128 bins, 20 ms hop) -> ECAPA-TDNN trunk -> PerceiverResampler (32 latents)
+    -> FSQ (levels 4^6) -> timbre latents [32, 128]
+    (`InferenceWrapper.calculate_timbre_latent`, evaluations/infer_arvc.py:213-223; `SpeakerEncoder.tokenize_wav`,
+    modules/bicodec_speaker_encoder/speaker_encoder.py:136-144)
 
-Pinned: tests/golden/style_vec.npz holds features and embeddings of the UNMODIFIED reference
-(`torchaudio.compliance.kaldi.fbank` + `modules.campplus.DTDNN.CAMPPlus` through the reference's own
-`calculate_style_vec`), written by oracle/make_golden_style.py; tests/test_oracle_golden.py checks this file against them.
+Pinned: tests/golden/style_vec.npz and tests/golden/timbre_latent.npz hold features and embeddings of the UNMODIFIED
+reference (`torchaudio.compliance.kaldi.fbank` + `modules.campplus.DTDNN.CAMPPlus` through the reference's own
+`calculate_style_vec`; `torchaudio.transforms.MelSpectrogram` + `SpeakerEncoder.tokenize_wav` through
+`calculate_timbre_latent`), written by oracle/make_golden_style.py; tests/test_oracle_golden.py checks this file against
+them.
 
 Third-party arithmetic: the filterbank lives in torchaudio (reference pin `torchaudio==2.4.0`, requirements.txt:7; 2.11.0
 in the build container, same algorithm: a port of Kaldi's `compute-fbank-feats`).  `kaldi_fbank` restates it for the one
@@ -139,3 +145,129 @@ def calculate_style_vec(wave16k: torch.Tensor, wave_lens: torch.Tensor, sd: Dict
     lens = torch.tensor([f.shape[0] for f in feats], dtype=torch.int32) // 2
     feats = [F.pad(f, (0, 0, 0, longest - f.shape[0]), value=float(f.min())) for f in feats]
     return campplus_forward(torch.stack(feats, dim=0), lens, sd)
+
+
+# ------------------------------------------------------------------------------------------------ timbre branch
+def _hz_to_mel_slaney(f: float) -> float:
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    if f >= min_log_hz:
+        return min_log_hz / f_sp + math.log(f / min_log_hz) / (math.log(6.4) / 27.0)
+    return f / f_sp
+
+
+def slaney_mel_fbanks(n_freqs: int = 513, f_min: float = 10.0, f_max: float = 8000.0, n_mels: int = 128,
+                      sr: int = 16000) -> torch.Tensor:
+    """`torchaudio.functional.melscale_fbanks(..., norm="slaney", mel_scale="slaney")`: triangles that are linear in Hz
+    between slaney-mel-spaced points, each scaled by 2 / (its band width)  ->  [n_freqs, n_mels]."""
+    all_freqs = torch.linspace(0, sr // 2, n_freqs)
+    m_pts = torch.linspace(_hz_to_mel_slaney(f_min), _hz_to_mel_slaney(f_max), n_mels + 2)
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, math.log(6.4) / 27.0
+    f_pts = f_sp * m_pts
+    log_t = m_pts >= min_log_mel
+    f_pts[log_t] = min_log_hz * torch.exp(logstep * (m_pts[log_t] - min_log_mel))
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    fb = torch.max(torch.zeros(1), torch.min(down, up))
+    return fb * (2.0 / (f_pts[2: n_mels + 2] - f_pts[:n_mels])).unsqueeze(0)
+
+
+def timbre_mel(wave16k: torch.Tensor) -> torch.Tensor:
+    """The `mel_fn` of configs/hydra_arcs/sv/sparktts_speaker_encoder.yaml (torchaudio MelSpectrogram: n_fft 1024, hann
+    window 640 (periodic) centred in the frame, hop 320, reflect-padded centre frames, MAGNITUDE (power 1), slaney mel
+    128 bins from 10 Hz): wave [B, n] -> [B, T, 128], T = n // 320 + 1  (speaker_encoder.py:138)."""
+    spec = torch.stft(wave16k, 1024, hop_length=320, win_length=640, window=torch.hann_window(640), center=True,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True).abs()
+    return torch.matmul(spec.transpose(-1, -2), slaney_mel_fbanks())
+
+
+def _conv_relu_bn(x, sd, pre, padding=0, dilation=1):
+    """Conv1dReluBn (ecapa_tdnn.py:69-90): conv -> ReLU -> BatchNorm, in this order."""
+    return _bn(F.relu(F.conv1d(x, sd[pre + ".conv.weight"], sd[pre + ".conv.bias"], 1, padding, dilation)), sd, pre + ".bn")
+
+
+def _se_res2block(x, sd, pre, dilation):
+    """SE_Res2Block (ecapa_tdnn.py:117-133): 1x1 -> Res2 (8 splits of 64, 7 dilated k3 convs chained, ecapa_tdnn.py:12-63)
+    -> 1x1 -> squeeze-excitation gate (ecapa_tdnn.py:96-111), plus the residual."""
+    h = _conv_relu_bn(x, sd, pre + ".0")
+    spx = torch.split(h, 64, 1)
+    out, sp = [], spx[0]
+    for i in range(7):
+        if i >= 1:
+            sp = sp + spx[i]
+        sp = F.conv1d(sp, sd[f"{pre}.1.convs.{i}.weight"], sd[f"{pre}.1.convs.{i}.bias"], 1, dilation, dilation)
+        sp = _bn(F.relu(sp), sd, f"{pre}.1.bns.{i}")
+        out.append(sp)
+    out.append(spx[7])
+    h = _conv_relu_bn(torch.cat(out, dim=1), sd, pre + ".2")
+    g = F.relu(F.linear(h.mean(dim=2), sd[pre + ".3.linear1.weight"], sd[pre + ".3.linear1.bias"]))
+    g = torch.sigmoid(F.linear(g, sd[pre + ".3.linear2.weight"], sd[pre + ".3.linear2.bias"]))
+    return x + h * g.unsqueeze(2)
+
+
+def ecapa_latent(mel: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """ECAPA_TDNN.forward(..., return_latent=True)[1] (ecapa_tdnn.py:191-209): mel [B, T, 128] -> [B, 1536, T]."""
+    e = "speaker_encoder"
+    out1 = _conv_relu_bn(mel.permute(0, 2, 1), sd, e + ".layer1", padding=2)
+    out2 = _se_res2block(out1, sd, e + ".layer2.se_res2block", 2)
+    out3 = _se_res2block(out2, sd, e + ".layer3.se_res2block", 3)
+    out4 = _se_res2block(out3, sd, e + ".layer4.se_res2block", 4)
+    return F.relu(F.conv1d(torch.cat([out2, out3, out4], dim=1), sd[e + ".conv.weight"], sd[e + ".conv.bias"]))
+
+
+def perceiver_resample(x: torch.Tensor, mask: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """PerceiverResampler.forward (perceiver_encoder.py:339-351): x [B, T, 1536], mask [B, 32 + T] (True = attend) ->
+    [B, 32, 128].  Two layers of cross attention whose keys/values are [latents ; context] (`cross_attn_include_queries`,
+    perceiver_encoder.py:275-289; 8 heads x 64, no bias, masked scores set to -float32 max, :140-155) and a GEGLU MLP
+    (128 -> 2 x 341 -> 128, :207-229), both residual; final RMSNorm = normalize * sqrt(128) * gamma (:177-190)."""
+    p = "perceiver_sampler"
+    B = x.shape[0]
+    ctx = F.linear(x, sd[p + ".proj_context.weight"], sd[p + ".proj_context.bias"])
+    lat = sd[p + ".latents"].unsqueeze(0).expand(B, -1, -1)
+    neg = -torch.finfo(torch.float32).max
+    for layer in range(2):
+        a = f"{p}.layers.{layer}.0"
+        kv_in = torch.cat((lat, ctx), dim=-2)
+        q = F.linear(lat, sd[a + ".to_q.weight"])
+        k, v = F.linear(kv_in, sd[a + ".to_kv.weight"]).chunk(2, dim=-1)
+        q, k, v = (t.reshape(B, t.shape[1], 8, 64).permute(0, 2, 1, 3) for t in (q, k, v))
+        sim = torch.einsum("bhid,bhjd->bhij", q, k) * (64 ** -0.5)
+        sim = sim.masked_fill(~mask[:, None, None, :], neg)
+        out = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+        out = out.permute(0, 2, 1, 3).reshape(B, -1, 512)
+        lat = F.linear(out, sd[a + ".to_out.weight"]) + lat
+        f = f"{p}.layers.{layer}.1"
+        h, gate = F.linear(lat, sd[f + ".0.weight"], sd[f + ".0.bias"]).chunk(2, dim=-1)
+        lat = F.linear(F.gelu(gate) * h, sd[f + ".2.weight"], sd[f + ".2.bias"]) + lat
+    return F.normalize(lat, dim=-1) * (128 ** 0.5) * sd[p + ".norm.gamma"]
+
+
+def fsq4_quantize(z: torch.Tensor):
+    """FSQ with levels [4] * 6 (fsq/finite_scalar_quantization.py:126-162): bound = tanh(z + atanh(0.5 / h)) * h - 0.5 with
+    h = 1.5 * 1.001, round, / 2  ->  codes in {-1, -0.5, 0, 0.5}; index = sum((code * 2 + 2) * 4^i).  z [..., 6]."""
+    half_l = torch.full((6,), 3.0) * (1 + 1e-3) / 2
+    offset = torch.full((6,), 0.5)
+    shift = (offset / half_l).atanh()
+    bounded = (z + shift).tanh() * half_l - offset
+    codes = bounded.round() / 2
+    basis = torch.tensor([1, 4, 16, 64, 256, 1024], dtype=torch.int32)
+    indices = ((codes * 2 + 2) * basis).sum(dim=-1).to(torch.int32)
+    return codes, indices, bounded
+
+
+def calculate_timbre_latent(wave16k: torch.Tensor, wave_lens: torch.Tensor, sd: Dict[str, torch.Tensor]):
+    """infer_arvc.py:213-223 -> `tokenize_wav` (speaker_encoder.py:136-144): returns (timbre latents [B, 32, 128] =
+    `zq.mT`, FSQ indices [B, 32] int32, pre-rounding FSQ coordinates [B, 32, 6]).  The attention mask keeps the 32
+    latent slots and the first wave_len // 320 context frames."""
+    mel = timbre_mel(wave16k)
+    feats = ecapa_latent(mel, sd)
+    T = feats.shape[2]
+    mel_lens = wave_lens // 320
+    mask = torch.arange(T + 32).unsqueeze(0) < (mel_lens + 32).unsqueeze(1)
+    lat = perceiver_resample(feats.transpose(1, 2), mask, sd)
+    z = F.linear(lat, sd["quantizer.project_in.weight"], sd["quantizer.project_in.bias"])
+    codes, indices, bounded = fsq4_quantize(z)
+    zq = F.linear(codes, sd["quantizer.project_out.weight"], sd["quantizer.project_out.bias"])
+    return zq, indices, bounded

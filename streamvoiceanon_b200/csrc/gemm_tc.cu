@@ -584,9 +584,11 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
     const char* e = getenv("SVANON_TC_MAX_BN");         // tuning knob: widest CTA tile (64 / 128 / 256)
     return e ? atoi(e) : 256;
   }();
-  // The kernel is bound by shared-memory traffic (hi/lo tile stores + the MMAs' operand reads, ncu: L1/TEX 51 %, tensor
-  // pipe 26 %): a wider tile amortises the A tile over more MMA work.  128 x 256 when the grid still fills the GPU and
-  // the padded width does not waste more than 128 x 128 tiles would.
+  // The producers' load/store pipe is the busiest unit (hi/lo tile stores + operand loads, ncu: L1/TEX 51 %, tensor pipe
+  // 26 % on the 128 x 128 tile) and every tile pays a fixed prologue/epilogue: a wider tile amortises both over more MMA
+  // work.  128 x 256 when the grid still fills the GPU and the padded width does not waste more than 128 x 128 tiles
+  // would.  (Switching the weight path off gains 11-16 % on large shapes; the A operand in tensor memory and a persistent
+  // kernel with dedicated epilogue warps were measured slower -- profiles/README.md.)
   auto padded = [&](int bn) { return (long long)((p.N + bn - 1) / bn) * bn; };
   if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107)
     launch_tc_cfg<256, 2>(b, count, 1, st);

@@ -257,6 +257,51 @@ def make_campplus_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]:
     return b.sd
 
 
+def make_timbre_encoder_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """Timbre encoder checkpoint (`pretrained_checkpoints/spark_speaker_encoder.pth`,
+    configs/hydra_arcs/sv/sparktts_speaker_encoder.yaml), only the tensors `tokenize_wav` touches
+    (modules/bicodec_speaker_encoder/speaker_encoder.py:136-144): ECAPA-TDNN trunk up to the 1536-channel latent
+    (ecapa_tdnn.py:150-209; its pooling head is not on this path), PerceiverResampler (perceiver_encoder.py:300-351) and
+    the FSQ projections (fsq/residual_fsq.py:70-76)."""
+    b = _Builder(seed + 13)
+
+    def bn(key, dim):
+        b.sd[key + ".weight"] = 1.0 + 0.1 * _randn(key + ".weight", b.seed, dim)
+        b.sd[key + ".bias"] = 0.05 * _randn(key + ".bias", b.seed, dim)
+        b.sd[key + ".running_mean"] = 0.1 * _randn(key + ".running_mean", b.seed, dim)
+        b.sd[key + ".running_var"] = 1.0 + 0.2 * _randn(key + ".running_var", b.seed, dim).abs()
+        b.sd[key + ".num_batches_tracked"] = torch.tensor(1000, dtype=torch.long)
+
+    e = "speaker_encoder"
+    b.linear(e + ".layer1.conv", 512, 128, gain=0.3, bias=True, extra=(5,))     # mel magnitudes are O(1..30)
+    bn(e + ".layer1.bn", 512)
+    for layer in (2, 3, 4):
+        pre = f"{e}.layer{layer}.se_res2block"
+        b.linear(pre + ".0.conv", 512, 512, gain=1.4, bias=True, extra=(1,))
+        bn(pre + ".0.bn", 512)
+        for i in range(7):
+            b.linear(f"{pre}.1.convs.{i}", 64, 64, gain=1.4, bias=True, extra=(3,))
+            bn(f"{pre}.1.bns.{i}", 64)
+        b.linear(pre + ".2.conv", 512, 512, gain=1.4, bias=True, extra=(1,))
+        bn(pre + ".2.bn", 512)
+        b.linear(pre + ".3.linear1", 128, 512, gain=1.4, bias=True)
+        b.linear(pre + ".3.linear2", 512, 128, gain=2.0, bias=True)
+    b.linear(e + ".conv", 1536, 1536, gain=1.4, bias=True, extra=(1,))
+    ps = "perceiver_sampler"
+    b.table(ps + ".latents", 32, 128, 0.5)
+    b.linear(ps + ".proj_context", 128, 1536, bias=True)
+    for layer in range(2):
+        b.linear(f"{ps}.layers.{layer}.0.to_q", 512, 128, gain=1.5)
+        b.linear(f"{ps}.layers.{layer}.0.to_kv", 1024, 128, gain=1.5)
+        b.linear(f"{ps}.layers.{layer}.0.to_out", 128, 512, gain=0.7)
+        b.linear(f"{ps}.layers.{layer}.1.0", 682, 128, bias=True)
+        b.linear(f"{ps}.layers.{layer}.1.2", 128, 341, gain=0.7, bias=True)
+    b.sd[ps + ".norm.gamma"] = 1.0 + 0.1 * _randn(ps + ".norm.gamma", b.seed, 128)
+    b.linear("quantizer.project_in", 6, 128, gain=1.0, bias=True)
+    b.linear("quantizer.project_out", 128, 6, gain=1.0, bias=True)
+    return b.sd
+
+
 def fold_weight_norm(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """w = g * v / ||v|| over dims (1,2) -- what `remove_parametrizations()` leaves behind
     (evaluations/infer_arvc.py:94, modules/vqgan/modules/firefly.py:105-111)."""

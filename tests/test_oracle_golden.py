@@ -214,3 +214,33 @@ def test_style_vector_oracle_vs_reference(gold):
     # ragged row: padding with the row minimum must not leak into the masked statistics of the short row's ... long row
     assert np.abs(sb.numpy()[0] - sa.numpy()[0]).max() < 1e-5
     assert S.kaldi_fbank(a[:, :399]).shape[0] == 0               # shorter than one 25 ms frame: no frames
+
+
+def test_timbre_latent_oracle_vs_reference(gold):
+    """SURVEY section 8f-3, timbre branch (groundwork: oracle only): slaney mel -> ECAPA-TDNN trunk -> PerceiverResampler ->
+    FSQ restated in oracle/speaker.py against the reference's own `calculate_timbre_latent` / `tokenize_wav` +
+    torchaudio MelSpectrogram (tests/golden/timbre_latent.npz, oracle/make_golden_style.py).  FSQ indices exact and
+    latents to 1e-5 wherever the pre-rounding coordinate is further than 1e-3 from a rounding boundary."""
+    from oracle import speaker as S
+    from streamvoiceanon_b200 import synth
+    g = gold("timbre_latent")
+    sd = synth.make_timbre_encoder_state_dict(int(g["weight_seed"]))
+    a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"]))[None]
+    b = synth.synth_audio_16k(int(g["seed_b"]), float(g["sec_b"]))[None]
+    mel = S.timbre_mel(a)
+    assert tuple(mel.shape) == g["mel_a"].shape == (1, a.shape[1] // 320 + 1, 128)
+    assert np.abs(mel.numpy() - g["mel_a"]).max() < 1e-4
+    batch = torch.zeros(2, a.shape[1])
+    batch[0], batch[1, : b.shape[1]] = a[0], b[0]
+    with torch.no_grad():
+        runs = ((S.calculate_timbre_latent(a, torch.LongTensor([a.shape[1]]), sd), "a"),
+                (S.calculate_timbre_latent(batch, torch.from_numpy(g["batch_lens"]), sd), "batch"))
+    for (zq, idx, bounded), name in runs:
+        assert tuple(zq.shape) == g[f"timbre_{name}"].shape and idx.dtype == torch.int32
+        frac = (bounded - bounded.floor() - 0.5).abs()                       # distance to the .5 rounding boundary
+        safe = (frac > 1e-3).all(dim=-1).numpy()                             # [B, 32] tokens that cannot flip
+        assert safe.mean() > 0.9
+        assert np.array_equal(idx.numpy()[safe], g[f"indices_{name}"][:, 0][safe]), name
+        assert np.abs(zq.numpy() - g[f"timbre_{name}"])[safe].max() < 1e-5, name
+    # the mask keeps padded frames of the short row out of the attention: row 0 of the batch equals the single run
+    assert np.array_equal(runs[1][0][1].numpy()[0], runs[0][0][1].numpy()[0])
