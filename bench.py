@@ -14,6 +14,10 @@ dual-AR decode step, vocoder on the last 64 code frames, tail select.  Prints ON
   N > 1  independent replicas, one stream per GPU, no collective ("replicas only"); value is the
          sum over ranks / max-over-ranks time
   --impl reference   the CPU oracle port of the reference loop (oracle/streaming.py) on the host cores
+  roofline           stage-A decode kernel against measured HBM bandwidth; roofline_gemm: the tcgen05 GEMM against the TF32
+                     tensor peak; stage_compute: executed GFLOP / stage time of the compute-bound stages E and V (single stream
+                     and the largest lock-step batch under RTF 1) against the 3xTF32 ceiling
+  concurrent_streams B streams per GPU in lock-step (svanon_batch_process_chunk): the metric's "streams per GPU at RTF < 1"
 """
 from __future__ import annotations
 
@@ -226,6 +230,32 @@ def gemm_roofline(peaks):
             "and CTA turnover cost as much SM time as the MMAs of a K = 512 tile"}
 
 
+# Executed floating-point work per stream and chunk (chunk = 1), DESIGN.md section 4.  Stage E: conv stack incl. the
+# DFT-as-GEMM spectrogram 26.3 GFLOP per 128 frames = 0.2055 per content frame, window transformer 6.98 GFLOP of which the
+# last layer runs for the kept token only (-0.67); a single stream sends two 41-frame spans through the conv stack, >= 8
+# lock-step streams one span + 0.2 GFLOP for the newest frames from conv history.  Stage V: 2.647 GFLOP per frame
+# (incremental vocoder).  The reference computes 29.0 (E) and 169.4 (V) GFLOP for the same chunk.
+E_GFLOP_SINGLE = 82 * 0.2055 + 6.98 - 0.67
+E_GFLOP_MANY = 41 * 0.2055 + 0.2 + 6.98 - 0.67
+V_GFLOP = 2.647
+
+
+def stage_compute(e_ms, v_ms, streams, peaks):
+    """Achieved fp32-equivalent TFLOP/s of the two compute-bound stages against the 3xTF32 ceiling (one third of the
+    TF32 tensor peak = one sixth of the measured dense bf16 peak): the compute roofline SURVEY.md section 8d asks for."""
+    bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")     # stages are long steps: sustained figure
+    ceiling = (bf16 / 6.0) if bf16 else 2250.0 / 6.0
+    e_g = (E_GFLOP_SINGLE if streams < 8 else E_GFLOP_MANY) * streams
+    v_g = V_GFLOP * streams
+    out = {"streams": streams, "ceiling_fp32_equivalent_tflops": ceiling,
+           "ceiling_source": ("measured dense bf16 (MEASURED_PEAKS.json)" if bf16 else "nominal 2250 bf16") + " / 6: TF32 at half the "
+                             "bf16 rate, three MMAs per fp32-grade product"}
+    for name, g, ms in (("E", e_g, e_ms), ("V", v_g, v_ms)):
+        t = g / ms if ms > 0 else 0.0                                         # GFLOP / ms = TFLOP/s
+        out[name] = {"executed_gflop": g, "ms": ms, "achieved_tflops": t, "frac": t / ceiling}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -379,6 +409,14 @@ def run_engine(args):
             "what": "B streams per GPU in lock-step through svanon_batch_process_chunk (one pass over the weights per chunk "
                     "for all streams), same workload per stream as `value`; the reference is batch-1",
             "max_measured_streams_rtf_lt_1": max(ok) if ok else 1, "sweep": sweep}
+    try:
+        line["stage_compute"] = [stage_compute(med[0], med[2], 1, peaks)]
+        best = [r for r in line.get("concurrent_streams", {}).get("sweep", []) if r["rtf"] < 1.0]
+        if best:
+            r = max(best, key=lambda r: r["streams"])
+            line["stage_compute"].append(stage_compute(r["stage_ms"]["E"], r["stage_ms"]["V"], r["streams"], peaks))
+    except Exception as exc:                                                   # never lose the bench line over a derived figure
+        line["stage_compute"] = {"error": repr(exc)}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         mean_ms, med_ms, cstage = cpu_oracle_loop(0, args.cpu_sample, 2, cores)
