@@ -8,10 +8,11 @@ library (include/svanon.h, streamvoiceanon_b200/libsvanon_b200.so):
     Vocoder            <-> modules.vqgan.modules.firefly.FireflyArchitecture           (quantizer.decode, head)
     StreamSession      <-> InferenceWrapper.process_one_chunk as one library call per chunk
     BatchSession       <-> the same loop for N concurrent streams in lock-step (the reference is batch-1)
+    StreamPool         <-> streams that join / leave at any chunk boundary, grouped into lock-step cohorts
 """
 from . import synth  # noqa: F401
 
-__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "BatchSession", "synth"]
+__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "BatchSession", "StreamPool", "synth"]
 
 
 def __getattr__(name):
@@ -24,4 +25,7 @@ def __getattr__(name):
     if name in ("StreamSession", "BatchSession"):
         from . import streaming
         return getattr(streaming, name)
+    if name == "StreamPool":
+        from .server import StreamPool
+        return StreamPool
     raise AttributeError(name)

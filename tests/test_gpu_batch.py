@@ -152,6 +152,49 @@ def test_batch_loop_equals_single_sessions(models, tape, n, chunk, ar_path, enc_
         s.close()
 
 
+def test_stream_pool_equals_single_sessions(models, tape):
+    """StreamPool (streams joining and leaving at chunk boundaries, two cohorts alive at once): every stream produces
+    what it produces alone -- ids bit-exact, waveform to fp32 rounding."""
+    from streamvoiceanon_b200.server import StreamPool
+    _, tok, _ = models
+    n_chunks, delay = 12, 2
+    cfg = dict(encode_window_frames=24, decode_window_frames=24, max_seq_frames=52, buffer_frames=6, decode_chunk_frames=1)
+    inputs = [_stream_inputs(tok, b, 26 + 5 * b, n_chunks, 1) for b in range(3)]
+    singles = []
+    for b, inp in enumerate(inputs):
+        sess = _session(inp, tape(7400 + b), delay)
+        sess.setup(**cfg)
+        waves = torch.cat([sess.process_chunk(inp[4][i].cuda()).cpu() for i in range(n_chunks)])
+        singles.append((*sess.history(), waves))
+        sess.close()
+    sessions = [_session(inp, tape(7400 + b), delay) for b, inp in enumerate(inputs)]
+    pool = StreamPool(**cfg)
+    join = {0: 0, 1: 0, 2: 3}                       # stream 2 arrives three chunks later -> its own cohort
+    got = {b: [] for b in range(3)}
+    for step in range(n_chunks + 3):
+        for b, at in join.items():
+            if at == step:
+                pool.add(b, sessions[b])
+        chunks = {b: inputs[b][4][step - join[b]].cuda() for b in range(3) if b in pool and step - join[b] < n_chunks}
+        for b, w in pool.step(chunks).items():
+            if b in chunks:
+                got[b].append(w.cpu())
+        if step == n_chunks - 1:
+            assert pool.n_cohorts == 2 and pool.cohort_sizes() == [2, 1]
+            pool.remove(0)                          # streams 0 and 1 are done; 1 leaves last and closes the cohort
+            pool.remove(1)
+            assert pool.n_cohorts == 1
+    for b, sess in enumerate(sessions):
+        src_hist, pred_hist = sess.history()
+        assert torch.equal(src_hist[: singles[b][0].numel()], singles[b][0]), b
+        assert torch.equal(pred_hist[:, : singles[b][1].shape[1]], singles[b][1]), b
+        mse = float(((torch.cat(got[b]) - singles[b][2]) ** 2).mean())
+        assert mse < 1e-10, (b, mse)
+    pool.close()
+    for s in sessions:
+        s.close()
+
+
 @pytest.mark.parametrize("enc_mode", [1, 2])
 def test_batch_loop_vs_reference_fixture(models, gold, tape, enc_mode):
     """Stream 0 of a 2-stream batch (many-stream decode kernels forced) reproduces the UNMODIFIED reference's
