@@ -200,7 +200,6 @@ def gemm_roofline(peaks):
     (M = 16384 rows = 32 streams x 512, N = 2048, K = 512, +bias, GELU), timed live with CUDA events.  Every fp32-grade
     product costs three TF32 MMAs, so `achieved` counts 3 x 2MNK TF32 flops; `peak` = half the measured dense bf16
     throughput of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate on B200), else half the nominal 2250."""
-    import ctypes as C
     from streamvoiceanon_b200 import _lib
     from streamvoiceanon_b200.engine import Engine, ptr
     eng, lib = Engine.get(torch.cuda.current_device()), _lib.load()

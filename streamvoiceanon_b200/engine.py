@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Dict, Iterable, Tuple
+from typing import Dict, Tuple
 
 import torch
 

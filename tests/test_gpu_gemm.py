@@ -1,5 +1,4 @@
 """GEMM back ends against torch fp64 on the GPU: fp32 CUDA-core kernels and the tcgen05 3xTF32 kernel."""
-import ctypes as C
 
 import pytest
 import torch

@@ -1,6 +1,5 @@
 """Micro-benchmark of the GEMM back ends on encoder-window shapes: warm (same weights every call, L2-resident) vs
 cold (cycling through 64 different weight matrices > L2) timings, CUDA events."""
-import ctypes as C
 import sys
 from pathlib import Path
 
