@@ -1,6 +1,8 @@
 """Host audio boundary: sample-rate conversion between the capture / file rate and the model's
 44.1 kHz on the GPU, with `torchaudio.functional.resample` semantics (what `synth.synth_audio_44k`, the reference GUI
-and -- up to the filter design -- `librosa.load(path, sr=44100)` do on the host, evaluations/infer_arvc.py:274-278)."""
+and -- up to the filter design -- `librosa.load(path, sr=44100)` do on the host, evaluations/infer_arvc.py:274-278).
+The filter bank is the one `torchaudio.transforms.Resample` holds (built in fp64, rounded once; the GUI's resamplers);
+`torchaudio.functional.resample` on an fp32 waveform builds the same bank in fp32, ~1e-6 away (oracle/prompt.py)."""
 from __future__ import annotations
 
 import ctypes as C

@@ -244,3 +244,29 @@ def test_timbre_latent_oracle_vs_reference(gold):
         assert np.abs(zq.numpy() - g[f"timbre_{name}"])[safe].max() < 1e-5, name
     # the mask keeps padded frames of the short row out of the attention: row 0 of the batch equals the single run
     assert np.array_equal(runs[1][0][1].numpy()[0], runs[0][0][1].numpy()[0])
+
+
+def test_calculate_prompt_oracle_vs_reference(gold):
+    """BASELINE config 5's prompt: the UNMODIFIED `InferenceWrapper.calculate_prompt` (infer_arvc.py:382-441) on three
+    concatenated references with alpha = 0.7 (tests/golden/prompt_config5.npz, oracle/make_golden_prompt.py) against the
+    chained restatement oracle/prompt.py::calculate_prompt (resample -> both speaker encoders -> noise mix in the
+    reference's draw order -> vocoder encoder ids -> content ids).  Ids exact; embeddings to 1e-5."""
+    import torchaudio
+    from oracle import prompt as P
+    from streamvoiceanon_b200 import synth
+    g = gold("prompt_config5")
+    ws = int(g["weight_seed"])
+    refs = [synth.synth_audio_44k(int(s), float(g["ref_seconds"]))[None] for s in g["ref_seeds"]]
+    with torch.no_grad():
+        codes, content, style, timbre, ref = P.calculate_prompt(
+            refs, float(g["alpha"]), g["noise_style"], g["noise_timbre"], synth.make_campplus_state_dict(ws),
+            synth.make_timbre_encoder_state_dict(ws), synth.make_tokenizer_state_dict(ws),
+            synth.make_vocoder_encoder_state_dict(ws))
+    assert ref.shape[-1] == int(g["n_samples"])
+    assert codes.dtype == torch.int32 and np.array_equal(codes.numpy(), g["ref_audio_codes"])
+    assert np.array_equal(content.numpy(), g["ref_content_codes"])
+    assert np.abs(style.numpy() - g["style_vectors"]).max() < 1e-5
+    assert np.abs(timbre.numpy() - g["timbre_latents"]).max() < 1e-5
+    # the 16 kHz step is torchaudio.functional.resample, whose filter bank is built in the waveform's dtype
+    want = torchaudio.functional.resample(ref, 44100, 16000)
+    assert float((P.resample(ref, 44100, 16000) - want).abs().max()) < 1e-6
