@@ -1,4 +1,4 @@
-"""Generates tests/golden/prompt_config5.npz from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+"""Generates tests/golden/prompt_config5.npz and stream_config5.npz from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
 
     python -m oracle.make_golden_prompt          # build container only (needs /root/reference and torchaudio)
 
@@ -29,7 +29,7 @@ def main():
     torch.set_num_threads(8)
     voc_sd = dict(synth.make_vocoder_state_dict(WEIGHT_SEED))
     voc_sd.update(synth.make_vocoder_encoder_state_dict(WEIGHT_SEED))
-    model, tok, voc, _ = ref_harness.build(synth.make_ar_state_dict(WEIGHT_SEED), synth.make_tokenizer_state_dict(WEIGHT_SEED),
+    model, tok, voc, tape = ref_harness.build(synth.make_ar_state_dict(WEIGHT_SEED), synth.make_tokenizer_state_dict(WEIGHT_SEED),
                                            voc_sd, lambda step, slot, V: synth.noise_tape(7000, step)[slot])
     import torchaudio
     from evaluations.infer_arvc import InferenceWrapper
@@ -62,6 +62,28 @@ def main():
                noise_timbre=noise_timbre.numpy(), n_samples=ref.shape[-1])
     np.savez_compressed(GOLD / "prompt_config5.npz", **out)
     print("wrote", GOLD / "prompt_config5.npz", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+    # ---- the same prompt through the UNMODIFIED streaming loop, chunk = 2 (BASELINE config 5): prefill_prompt (which
+    # calls calculate_prompt and truncates to max_prompt_frames, infer_arvc.py:462-489), setup_stream_caches,
+    # process_one_chunk; small windows so that the re-prompt path (:547-564) fires with two-frame chunks
+    ws = ref_harness.make_inference_wrapper(model, tok, voc, None, None, None)       # installs the CPU Event stubs
+    del ws.calculate_prompt                                                          # back to the class's own method
+    ws.style_encoder, ws.timbre_encoder = w.style_encoder, w.timbre_encoder
+    cfg = dict(encode_window_frames=32, decode_window_frames=16, max_seq_frames=72, buffer_frames=8, decode_chunk_frames=2)
+    n_chunks, max_prompt, delay = 12, 48, 2
+    tape.step = -1
+    with torch.no_grad():
+        torch.manual_seed(MIX_SEED)
+        ws.prefill_prompt(refs, max_prompt_frames=max_prompt, delay=delay, alpha=ALPHA)
+        ws.setup_stream_caches(**cfg)
+        src = synth.synth_audio_44k(1003, 1.5)[: n_chunks * 4096].view(n_chunks, 4096)
+        waves = torch.cat([ws.process_one_chunk(src[i][None]).clone() for i in range(n_chunks)], dim=-1)
+    out = dict(weight_seed=WEIGHT_SEED, mix_seed=MIX_SEED, alpha=np.float32(ALPHA), tape_seed=7000, src_seed=1003,
+               n_chunks=n_chunks, max_prompt_frames=max_prompt, delay=delay, **{k: np.array(v) for k, v in cfg.items()},
+               src_content=ws.src_content_codes.numpy(), pred_codes=ws.pred_codes.numpy(), wave=waves[0].numpy())
+    np.savez_compressed(GOLD / "stream_config5.npz", **out)
+    print("wrote", GOLD / "stream_config5.npz", {k: getattr(v, "shape", v) for k, v in out.items()},
+          "wave rms", float(waves.pow(2).mean().sqrt()))
 
 
 if __name__ == "__main__":

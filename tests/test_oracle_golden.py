@@ -270,3 +270,29 @@ def test_calculate_prompt_oracle_vs_reference(gold):
     # the 16 kHz step is torchaudio.functional.resample, whose filter bank is built in the waveform's dtype
     want = torchaudio.functional.resample(ref, 44100, 16000)
     assert float((P.resample(ref, 44100, 16000) - want).abs().max()) < 1e-6
+
+
+def test_stream_config5_loop_from_reference_waves(weights, gold, tape):
+    """BASELINE config 5 end to end on the CPU: three reference WAVES -> oracle calculate_prompt (speaker encoders, noise
+    mix, codec and content ids) -> prompt truncated to 48 frames -> the streaming loop with two-frame chunks and the
+    re-prompt path firing, against the unmodified reference's `prefill_prompt` + `process_one_chunk`
+    (tests/golden/stream_config5.npz, oracle/make_golden_prompt.py): ids exact, waveform MSE < 1e-10."""
+    from oracle import prompt as P
+    g, gp = gold("stream_config5"), gold("prompt_config5")
+    ws = int(g["weight_seed"])
+    refs = [synth.synth_audio_44k(int(s), float(gp["ref_seconds"]))[None] for s in gp["ref_seeds"]]
+    with torch.no_grad():
+        codes, content, style, timbre, _ = P.calculate_prompt(
+            refs, float(g["alpha"]), gp["noise_style"], gp["noise_timbre"], synth.make_campplus_state_dict(ws),
+            synth.make_timbre_encoder_state_dict(ws), weights["tok"], weights["voc_enc"])
+        so = StreamOracle(weights["ar"], weights["tok"], weights["voc_folded"], tape(int(g["tape_seed"])))
+        so.prefill_prompt(codes, content, style, timbre, max_prompt_frames=int(g["max_prompt_frames"]), delay=int(g["delay"]))
+        chunk = int(g["decode_chunk_frames"])
+        so.setup_stream_caches(int(g["encode_window_frames"]), int(g["decode_window_frames"]), int(g["max_seq_frames"]),
+                               int(g["buffer_frames"]), chunk)
+        n = int(g["n_chunks"])
+        src = synth.synth_audio_44k(int(g["src_seed"]), 1.5)[: n * chunk * 2048].view(n, chunk * 2048)
+        wave = torch.cat([so.process_one_chunk(src[i][None]) for i in range(n)], dim=-1)
+    assert np.array_equal(so.src_content_codes.numpy(), g["src_content"])
+    assert np.array_equal(so.pred_codes.numpy(), g["pred_codes"])
+    assert float(((wave[0].numpy() - g["wave"]) ** 2).mean()) < 1e-10
