@@ -1,0 +1,113 @@
+"""Host orchestration of the speaker-encoder port (streamvoiceanon_b200/csrc/speaker.hpp) against
+the reference-generated fixtures, on a machine WITHOUT a GPU.
+
+speaker.hpp is written against a backend interface; tests/hostemu/speaker_host.cpp compiles the same source with g++:
+functors run as loops and the engine's GEMM is a three-loop restatement of the GemmParams contract.  What this pins:
+buffer shapes and zero margins, weight repacking, GEMM descriptors (overlapping rows, row-offset taps, column slices of
+the concat buffers), functor arguments and the derived buffers built by streamvoiceanon_b200/speaker.py.  What it
+cannot pin: the CUDA launch of the functors and the real GEMM kernels -- tests/test_gpu_zz_speaker.py does that on the
+B200.  The host build is test infrastructure: the product never loads it (tests/test_cabi.py)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from streamvoiceanon_b200 import synth
+
+HERE = Path(__file__).resolve().parent / "hostemu"
+SRC = HERE / "speaker_host.cpp"
+HPP = HERE.parent.parent / "streamvoiceanon_b200" / "csrc" / "speaker.hpp"
+SO = HERE / "_build" / "libspeaker_host.so"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    SO.parent.mkdir(exist_ok=True)
+    if not SO.exists() or SO.stat().st_mtime < max(SRC.stat().st_mtime, HPP.stat().st_mtime):
+        subprocess.run(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include", str(SRC),
+                        "-o", str(SO)], check=True)
+    lib = C.CDLL(str(SO))
+    lib.hostemu_last_error.restype = C.c_char_p
+    from streamvoiceanon_b200 import speaker as SP
+
+    def load(model, sd):
+        for k, v in sd.items():
+            if not torch.is_tensor(v) or not v.is_floating_point() or v.dim() == 0:
+                continue
+            t = v.detach().float().contiguous()
+            shape = (C.c_longlong * t.dim())(*t.shape)
+            assert lib.hostemu_load_tensor(model, k.encode(), C.c_void_p(t.data_ptr()), t.dim(), shape) == 0
+        assert lib.hostemu_finalize(model) == 0, lib.hostemu_last_error().decode()
+
+    seed = int(np.load(HERE.parent / "golden" / "style_vec.npz")["weight_seed"])
+    load(0, {**synth.make_campplus_state_dict(seed), **SP.style_derived_buffers()})
+    load(1, {**synth.make_timbre_encoder_state_dict(seed), **SP.timbre_derived_buffers()})
+    return lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def test_style_branch_host_orchestration_vs_reference(emu, gold):
+    """kaldi fbank to 1e-4 and the style vector to 1e-4 against the unmodified reference (`calculate_style_vec`,
+    tests/golden/style_vec.npz); the ragged batch row goes through fbank + CAMPPlus with the reference's padding rule."""
+    g = gold("style_vec")
+    a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"])).contiguous()
+    b = synth.synth_audio_16k(int(g["seed_b"]), float(g["sec_b"])).contiguous()
+    T = 1 + (a.numel() - 400) // 160
+    feat = torch.empty(80, T)
+    assert emu.hostemu_kaldi_fbank(_p(a), C.c_longlong(a.numel()), _p(feat)) == 0, emu.hostemu_last_error().decode()
+    assert np.abs(feat.T.numpy() - g["fbank_a"]).max() < 1e-4
+    out = torch.empty(192)
+    counts = (C.c_longlong * 2)()
+    assert emu.hostemu_style_vector(_p(a), C.c_longlong(a.numel()), _p(out), counts) == 0, emu.hostemu_last_error().decode()
+    assert np.isfinite(out.numpy()).all()
+    assert np.abs(out.numpy() - g["style_a"][0]).max() < 1e-4
+    assert counts[0] == 1 + 52 * 2 + 3                           # TDNN, 52 x (bottleneck, local conv), 3 transits
+    # the short row of the reference's ragged batch: its own fbank minus its mean, padded with its minimum to the long
+    # row's length, lens = frames // 2
+    Tb = 1 + (b.numel() - 400) // 160
+    fb = torch.empty(80, Tb)
+    assert emu.hostemu_kaldi_fbank(_p(b), C.c_longlong(b.numel()), _p(fb)) == 0
+    fb = fb - fb.mean(dim=1, keepdim=True)
+    padded = torch.nn.functional.pad(fb, (0, T - Tb), value=float(fb.min())).contiguous()
+    assert emu.hostemu_campplus(_p(padded), C.c_longlong(T), Tb // 2, _p(out)) == 0, emu.hostemu_last_error().decode()
+    assert np.abs(out.numpy() - g["style_batch"][1]).max() < 1e-4
+
+
+def test_timbre_branch_host_orchestration_vs_reference(emu, gold):
+    """Timbre latents and FSQ indices against the unmodified reference (`calculate_timbre_latent`,
+    tests/golden/timbre_latent.npz): indices exact and latents to 1e-4 wherever the FSQ input is further than 1e-3 from a
+    rounding boundary; single utterance and the zero-padded short row of the reference's batch (mask = wave_len // 320)."""
+    from oracle import speaker as S
+    g = gold("timbre_latent")
+    a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"])).contiguous()
+    b = synth.synth_audio_16k(int(g["seed_b"]), float(g["sec_b"]))
+    row_b = torch.zeros(a.numel())
+    row_b[: b.numel()] = b
+    for wave, wave_len, want, want_idx in ((a, a.numel(), g["timbre_a"][0], g["indices_a"][0, 0]),
+                                           (row_b, b.numel(), g["timbre_batch"][1], g["indices_batch"][1, 0])):
+        out, idx, z = torch.empty(32, 128), torch.empty(32, dtype=torch.int32), torch.empty(32, 6)
+        counts = (C.c_longlong * 2)()
+        rc = emu.hostemu_timbre_latent(_p(wave), C.c_longlong(wave.numel()), C.c_longlong(wave_len), _p(out), _p(idx), _p(z), counts)
+        assert rc == 0, emu.hostemu_last_error().decode()
+        assert np.isfinite(out.numpy()).all()
+        _, _, bounded = S.fsq4_quantize(z)
+        safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+        assert safe.mean() > 0.9
+        assert np.array_equal(idx.numpy()[safe], want_idx[safe])
+        assert np.abs(out.numpy() - want)[safe].max() < 1e-4
+        assert counts[0] == 1 + 3 * 9 + 1 + 1 + 2                # layer1, 3 x (in, 7 res2, out), cat conv, context, 2 x kv
+
+
+def test_speaker_functions_reject_short_waves(emu):
+    out = torch.empty(192)
+    w = torch.zeros(700)
+    assert emu.hostemu_style_vector(_p(w), C.c_longlong(700), _p(out), None) == 1
+    assert b"shorter" in emu.hostemu_last_error()
+    lat = torch.empty(32, 128)
+    assert emu.hostemu_timbre_latent(_p(w), C.c_longlong(700), C.c_longlong(700), _p(lat), None, None, None) == 1
