@@ -199,6 +199,37 @@ int svanon_resample(svanon_engine* e, const float* wave, int64_t n_in, const flo
 int svanon_noise_mix(svanon_engine* e, const float* x, const float* noise, int64_t n, float alpha, float* out,
                      void* cuda_stream);
 
+/* ---- speaker encoders of the prompt path -------------------------------------------------
+ * Two more model ids for svanon_load_tensor / svanon_finalize_weights:
+ *   3 = style encoder: `modules.campplus.DTDNN.CAMPPlus(feat_dim=80, embedding_size=192)` (configs/hydra_arcs/sv/
+ *       campplus.yaml; construction + load_state_dict at evaluations/infer_arvc.py:98-108), reference key names with the
+ *       `xvector.dense.*` -> `dense.*` rename CAMPPlus.load_state_dict applies (DTDNN.py:114-130), plus two derived
+ *       buffers of torchaudio.compliance.kaldi: "fbank.window" [400] (povey) and "fbank.mel_banks" [80][257];
+ *   4 = timbre encoder: `modules.bicodec_speaker_encoder.speaker_encoder.SpeakerEncoder` (configs/hydra_arcs/sv/
+ *       sparktts_speaker_encoder.yaml; infer_arvc.py:110-121), the tensors `tokenize_wav` touches (speaker_encoder.layer*,
+ *       speaker_encoder.conv, perceiver_sampler.*, quantizer.project_in/out), plus the derived buffers of its
+ *       MelSpectrogram: "mel.window" [1024] (hann(640) centred) and "mel.fb" [513][128] (slaney).
+ * All waves are 16 kHz mono fp32; pointers may be host or device memory.
+ *
+ * svanon_kaldi_fbank      replaces `torchaudio.compliance.kaldi.fbank(wave, num_mel_bins=80, dither=0,
+ *                         sample_frequency=16000)` (call site infer_arvc.py:186-191): wave [n] -> feat_out [m][80],
+ *                         m = 1 + (n - 400) / 160.
+ * svanon_campplus_forward replaces `CAMPPlus.forward(x, x_lens)` for one row (modules/campplus/DTDNN.py:132-138; call site
+ *                         infer_arvc.py:210): feat [n_frames][80], valid_len = x_lens of the row (rows that count in the
+ *                         statistics pooling, after the stride-2 TDNN) -> out [192].
+ * svanon_style_vector     replaces `InferenceWrapper.calculate_style_vec` for one row (infer_arvc.py:179-211): fbank, minus
+ *                         its time mean, lens = frames / 2, CAMPPlus -> out [192].
+ * svanon_timbre_latent    replaces `InferenceWrapper.calculate_timbre_latent` / `SpeakerEncoder.tokenize_wav` for one row
+ *                         (infer_arvc.py:213-223, speaker_encoder.py:136-144): wave [n_samples] whose first wave_len
+ *                         samples are valid (a zero-padded batch row; wave_len = n_samples otherwise) -> latents_out
+ *                         [32][128] (the `zq.mT` the caller keeps) and, if not null, the 32 FSQ indices. */
+int svanon_kaldi_fbank(svanon_engine* e, const float* wave16k, int64_t n_samples, float* feat_out, void* cuda_stream);
+int svanon_campplus_forward(svanon_engine* e, const float* feat, int64_t n_frames, int valid_len, float* out,
+                            void* cuda_stream);
+int svanon_style_vector(svanon_engine* e, const float* wave16k, int64_t n_samples, float* out, void* cuda_stream);
+int svanon_timbre_latent(svanon_engine* e, const float* wave16k, int64_t n_samples, int64_t wave_len, float* latents_out,
+                         int32_t* indices_out, void* cuda_stream);
+
 /* ---- many concurrent streams in lock-step --------------------------------------------------------------------
  * The reference is strictly batch-1 (max_batch_size=1, evaluations/infer_arvc.py:56; `x.view(1, 1, -1)`,
  * modules/dual_ar_stream.py:544): N concurrent utterances are N sequential calls.  These entry points run the same

@@ -14,7 +14,7 @@ import os
 LIB_PATH = Path(os.environ["SVANON_LIB"]) if os.environ.get("SVANON_LIB") else PKG / "libsvanon_b200.so"   # tuning builds
 HEADER = PKG.parent / "include" / "svanon.h"
 
-MODEL_AR, MODEL_TOKENIZER, MODEL_VOCODER = 0, 1, 2
+MODEL_AR, MODEL_TOKENIZER, MODEL_VOCODER, MODEL_STYLE, MODEL_TIMBRE = 0, 1, 2, 3, 4
 
 _lib = None
 
@@ -62,6 +62,10 @@ _SIGS = {
     "svanon_resample": (C.c_int, [_p, _p, C.c_int64, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int64, _p]),
     "svanon_noise_mix": (C.c_int, [_p, _p, _p, C.c_int64, C.c_float, _p, _p]),
     "svanon_voc_encode": (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, _p]),
+    "svanon_kaldi_fbank": (C.c_int, [_p, _p, C.c_int64, _p, _p]),
+    "svanon_campplus_forward": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, _p]),
+    "svanon_style_vector": (C.c_int, [_p, _p, C.c_int64, _p, _p]),
+    "svanon_timbre_latent": (C.c_int, [_p, _p, C.c_int64, C.c_int64, _p, _p, _p]),
     "svanon_enc_encode_batch": (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, _p]),
     "svanon_ar_decode_many": (C.c_int, [C.POINTER(_p), C.c_int, _p, _p, _p, _p]),
     "svanon_batch_create": (C.c_int, [_p, C.POINTER(_p), C.c_int, C.POINTER(_p)]),

@@ -105,7 +105,9 @@ void Engine::finalize(int model) {
   if (finalized[model]) return;
   if (model == MODEL_AR) finalize_ar();
   else if (model == MODEL_TOKENIZER) finalize_tokenizer();
-  else finalize_vocoder();
+  else if (model == MODEL_VOCODER) finalize_vocoder();
+  else if (model == MODEL_STYLE) finalize_style();
+  else finalize_timbre();
   finalized[model] = true;
 }
 

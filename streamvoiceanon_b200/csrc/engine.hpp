@@ -12,7 +12,9 @@
 
 namespace svanon {
 
-enum Model : int { MODEL_AR = 0, MODEL_TOKENIZER = 1, MODEL_VOCODER = 2, MODEL_COUNT = 3 };
+// MODEL_STYLE = CAMPPlus (style vector), MODEL_TIMBRE = BiCodec speaker encoder (timbre latents): the prompt path's two
+// speaker encoders (speaker.hpp)
+enum Model : int { MODEL_AR = 0, MODEL_TOKENIZER = 1, MODEL_VOCODER = 2, MODEL_STYLE = 3, MODEL_TIMBRE = 4, MODEL_COUNT = 5 };
 
 struct Tensor {
   float* data = nullptr;
@@ -222,7 +224,7 @@ struct Engine {
   int device = 0;
   int num_sms = 148;
   std::unordered_map<std::string, Tensor> w[MODEL_COUNT];
-  bool finalized[MODEL_COUNT] = {false, false, false};
+  bool finalized[MODEL_COUNT] = {false, false, false, false, false};
   std::vector<float*> owned;                   // packed weights built at finalize
   Workspace ws;
   cudaStream_t own_stream = nullptr;
@@ -272,6 +274,8 @@ struct Engine {
   void finalize_ar();
   void finalize_tokenizer();
   void finalize_vocoder();
+  void finalize_style();       // speaker.cu
+  void finalize_timbre();
 
   // stage drivers (all device pointers, stream-ordered, no host sync)
   int enc_num_ids(long long n_samples) const { return (int)(((n_samples / HOP) / 2) / 2); }
@@ -301,6 +305,14 @@ struct Engine {
   // codes: stream b's [8][c] block starts b * codes_seg after `codes` (row stride ld); wave_out [B][c*2048]
   void voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st,
                 long long codes_seg = 0);
+
+  // speaker encoders of the prompt path (speaker.cu / speaker.hpp); 16 kHz waves, device pointers
+  std::shared_ptr<void> style_net, timbre_net;
+  void kaldi_fbank(const float* wave, long long n, float* feat /*[frames][80]*/, cudaStream_t st);
+  void campplus_forward(const float* feat /*[T][80]*/, long long T, int len, float* out /*[192]*/, cudaStream_t st);
+  void style_vector(const float* wave, long long n, float* out /*[192]*/, cudaStream_t st);
+  void timbre_latent(const float* wave, long long n, long long wave_len, float* out /*[32][128]*/, int* indices /*[32] or null*/,
+                     cudaStream_t st);
 
   // AR
   void ar_forward_tokens(Stream& s, float* x /*[M][768]*/, int M, int pos0, cudaStream_t st);

@@ -29,7 +29,7 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self.lib.svanon_engine_create(device, C.byref(h)))
         self.handle = h
-        self.loaded = {0: False, 1: False, 2: False}
+        self.loaded = {0: False, 1: False, 2: False, 3: False, 4: False}
         import os
         mode = os.environ.get("SVANON_GEMM_MODE")        # 1 = fp32 CUDA cores, 2 = tcgen05 3xTF32 (library default)
         if mode is not None:

@@ -70,10 +70,6 @@ def _style_key(k: str) -> str:
     return k.replace("xvector.dense", "dense") if k.startswith("xvector.dense") else k
 
 
-def _row(t: torch.Tensor, eng: Engine) -> torch.Tensor:
-    return t.detach().to(torch.float32).contiguous()
-
-
 # ---------------------------------------------------------------------------------------------- style
 class CAMPPlus:
     """`modules.campplus.DTDNN.CAMPPlus(feat_dim=80, embedding_size=192)` (configs/hydra_arcs/sv/campplus.yaml)."""
@@ -108,7 +104,7 @@ class CAMPPlus:
         B, T = x.shape[0], x.shape[1]
         rows_after = (T - 1) // 2 + 1
         lens = [rows_after] * B if x_lens is None else [int(v) for v in x_lens.reshape(-1).tolist()]
-        feat = _row(x, self._engine)
+        feat = x.detach().to(torch.float32).contiguous()
         out = torch.empty(B, 192, dtype=torch.float32, device=feat.device)
         for b in range(B):
             _lib.check(self._engine.lib.svanon_campplus_forward(self._engine.handle, ptr(feat[b]), T, lens[b], ptr(out[b]),

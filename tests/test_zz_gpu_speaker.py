@@ -1,0 +1,111 @@
+"""GPU parity of the two speaker encoders of the prompt path through the C ABI
+(svanon_kaldi_fbank / svanon_campplus_forward / svanon_style_vector / svanon_timbre_latent) against the fixtures written
+by the UNMODIFIED reference (`InferenceWrapper.calculate_style_vec` / `calculate_timbre_latent`;
+tests/golden/style_vec.npz, timbre_latent.npz, prompt_config5.npz; oracle/make_golden_style.py, make_golden_prompt.py).
+
+Floating point, so tolerances instead of bit-exactness: log-mel features 1e-4 (absolute; values are O(10)), style vector
+2e-4 (values O(1); 3xTF32 tensor-core products through 52 dense layers), timbre latents 1e-4 and FSQ indices exact
+wherever the FSQ input is further than 1e-3 from a rounding boundary (the reference's own ids flip there between BLAS
+builds).  The same source was held to the same fixtures by a host build first (tests/test_speaker_hostemu.py); this file
+sorts last so that a failure here cannot hide the hot-path tests under `-x`."""
+import numpy as np
+import pytest
+import torch
+
+from streamvoiceanon_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FBANK_TOL = 1e-4
+STYLE_TOL = 2e-4
+TIMBRE_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def encoders(gold):
+    from streamvoiceanon_b200.speaker import CAMPPlus, SpeakerEncoder
+    seed = int(gold("style_vec")["weight_seed"])
+    style = CAMPPlus()
+    style.load_state_dict(synth.make_campplus_state_dict(seed))
+    timbre = SpeakerEncoder()
+    timbre.load_state_dict(synth.make_timbre_encoder_state_dict(seed))
+    return style, timbre
+
+
+def test_kaldi_fbank_vs_reference(encoders, gold):
+    from streamvoiceanon_b200.speaker import kaldi_fbank
+    g = gold("style_vec")
+    a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"]))[None]
+    fb = kaldi_fbank(a.cuda())
+    assert tuple(fb.shape) == g["fbank_a"].shape
+    assert np.abs(fb.cpu().numpy() - g["fbank_a"]).max() < FBANK_TOL
+    host = kaldi_fbank(a)                                           # host buffers through the same entry point
+    assert torch.equal(host, fb.cpu())
+    assert kaldi_fbank(a[:, :399]).shape[0] == 0                    # shorter than one 25 ms frame: no frames
+
+
+def test_style_vector_vs_reference(encoders, gold):
+    """Single utterance (one fused library call) and the reference's ragged two-row batch (per-row fbank, padding with
+    the row minimum, lens = frames // 2, CAMPPlus per row)."""
+    from streamvoiceanon_b200.speaker import calculate_style_vec
+    style, _ = encoders
+    g = gold("style_vec")
+    a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"]))[None]
+    b = synth.synth_audio_16k(int(g["seed_b"]), float(g["sec_b"]))[None]
+    sa = calculate_style_vec(style, a.cuda(), torch.LongTensor([a.shape[1]]))
+    assert tuple(sa.shape) == (1, 192)
+    assert np.abs(sa.cpu().numpy() - g["style_a"]).max() < STYLE_TOL
+    batch = torch.zeros(2, a.shape[1])
+    batch[0], batch[1, : b.shape[1]] = a[0], b[0]
+    sb = calculate_style_vec(style, batch.cuda(), torch.from_numpy(g["batch_lens"]))
+    assert np.abs(sb.cpu().numpy() - g["style_batch"]).max() < STYLE_TOL
+    with pytest.raises(RuntimeError):
+        calculate_style_vec(style, a[:, :700].cuda(), torch.LongTensor([700]))     # 2 frames: too short to pool
+
+
+def test_timbre_latent_vs_reference(encoders, gold):
+    from oracle import speaker as S
+    from streamvoiceanon_b200.speaker import calculate_timbre_latent
+    _, timbre = encoders
+    g = gold("timbre_latent")
+    a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"]))[None]
+    b = synth.synth_audio_16k(int(g["seed_b"]), float(g["sec_b"]))[None]
+    batch = torch.zeros(2, a.shape[1])
+    batch[0], batch[1, : b.shape[1]] = a[0], b[0]
+    sd = synth.make_timbre_encoder_state_dict(int(g["weight_seed"]))
+    for wav, lens, name in ((a, torch.LongTensor([a.shape[1]]), "a"), (batch, torch.from_numpy(g["batch_lens"]), "batch")):
+        zq, idx = timbre.tokenize_wav(wav.cuda(), lens)
+        assert tuple(zq.shape) == (wav.shape[0], 128, 32) and idx.dtype == torch.int32
+        lat = calculate_timbre_latent(timbre, wav.cuda(), lens)
+        assert torch.equal(lat, zq.mT)
+        with torch.no_grad():                                       # which tokens sit away from a rounding boundary
+            _, _, bounded = S.calculate_timbre_latent(wav, lens, sd)
+        safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+        assert safe.mean() > 0.9
+        assert np.array_equal(idx.cpu().numpy()[:, 0][safe], g[f"indices_{name}"][:, 0][safe]), name
+        assert np.abs(lat.cpu().numpy() - g[f"timbre_{name}"])[safe].max() < TIMBRE_TOL, name
+
+
+def test_config5_prompt_embeddings_vs_reference(encoders, gold):
+    """BASELINE config 5's prompt end to end on the GPU: the 4.8 s concatenation of three references -> resample to
+    16 kHz (svanon_resample) -> both speaker encoders -> anonymisation mix with the reference's draws (alpha 0.7)
+    against the outputs of the unmodified `calculate_prompt` (style / timbre to 5e-4 after the mix)."""
+    from oracle import speaker as S
+    from streamvoiceanon_b200.audio import Resampler
+    from streamvoiceanon_b200.prompt import apply_noise_mixing
+    from streamvoiceanon_b200.speaker import calculate_style_vec, calculate_timbre_latent
+    style, timbre = encoders
+    gp = gold("prompt_config5")
+    refs = [synth.synth_audio_44k(int(s), float(gp["ref_seconds"]))[None] for s in gp["ref_seeds"]]
+    ref = torch.cat(refs, dim=-1).cuda()
+    ref16 = Resampler(44100, 16000)(ref)
+    lens = torch.LongTensor([ref16.shape[-1]])
+    alpha = float(gp["alpha"])
+    sv = apply_noise_mixing(calculate_style_vec(style, ref16, lens), alpha, torch.from_numpy(gp["noise_style"]).cuda())
+    tl = apply_noise_mixing(calculate_timbre_latent(timbre, ref16, lens), alpha, torch.from_numpy(gp["noise_timbre"]).cuda())
+    assert np.abs(sv.cpu().numpy() - gp["style_vectors"]).max() < 5e-4
+    with torch.no_grad():                                           # tokens away from an FSQ rounding boundary
+        _, _, bounded = S.calculate_timbre_latent(ref16.cpu(), lens, synth.make_timbre_encoder_state_dict(int(gp["weight_seed"])))
+    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+    assert safe.mean() > 0.9
+    assert np.abs(tl.cpu().numpy() - gp["timbre_latents"])[safe].max() < 5e-4
