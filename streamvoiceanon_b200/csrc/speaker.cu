@@ -71,27 +71,21 @@ static const spk::StyleNet& style_of(Engine& e) {
   return *static_cast<const spk::StyleNet*>(e.style_net.get());
 }
 
-void Engine::kaldi_fbank(const float* wave, long long n, float* feat_tc, cudaStream_t st) {
+void Engine::kaldi_fbank(const float* wave, long long n, float* feat_rows, cudaStream_t st) {
   const spk::StyleNet& net = style_of(*this);
-  const long long T = spk::style_frames(n);
   ws.ensure(spk::style_ws_floats(n) * sizeof(float));
   ws.reset();
   CudaBK bk{*this, MODEL_STYLE, st};
-  float* feat = bk.alloc(spk::FB_MEL * T);
-  spk::kaldi_fbank(bk, net, wave, n, feat);
-  bk.pfor(T * spk::FB_MEL, spk::ToChannelsLast{feat, spk::FB_MEL, T, feat_tc, 0});
+  spk::kaldi_fbank_rows(bk, net, wave, n, feat_rows);
 }
 
-void Engine::campplus_forward(const float* feat_tc, long long T, int len, float* out, cudaStream_t st) {
+void Engine::campplus_forward(const float* feat_rows, long long T, int len, float* out, cudaStream_t st) {
   const spk::StyleNet& net = style_of(*this);
   SV_CHECK(T >= 4 && T < (1 << 20), "CAMPPlus: between 4 and 2^20 feature frames");
   ws.ensure(spk::style_ws_floats(spk::FB_WIN + (T - 1) * spk::FB_SHIFT) * sizeof(float));
   ws.reset();
   CudaBK bk{*this, MODEL_STYLE, st};
-  float* feat = bk.alloc(spk::FB_MEL * T);
-  // [T][80] (the reference's layout) -> [80][T]: the transpose of ToChannelsLast with the roles of rows and channels swapped
-  bk.pfor(T * spk::FB_MEL, spk::ToChannelsLast{feat_tc, (int)T, spk::FB_MEL, feat, 0});
-  spk::campplus_forward(bk, net, feat, T, len, out);
+  spk::campplus_forward_rows(bk, net, feat_rows, T, len, out);
 }
 
 void Engine::style_vector(const float* wave, long long n, float* out, cudaStream_t st) {

@@ -755,6 +755,24 @@ void style_forward(BK& bk, const StyleNet& net, const float* wave, long long n, 
   campplus_forward(bk, net, feat, T, (int)(T / 2), out);
 }
 
+// the two entry points above in the reference's own layout, features [T][80] (time-major rows)
+template <class BK>
+void kaldi_fbank_rows(BK& bk, const StyleNet& net, const float* wave, long long n, float* feat_rows) {
+  const long long T = style_frames(n);
+  SV_CHECK(T >= 1, "kaldi fbank: the wave is shorter than one 25 ms frame (400 samples at 16 kHz)");
+  float* feat = bk.alloc(FB_MEL * T);
+  kaldi_fbank(bk, net, wave, n, feat);
+  bk.pfor(T * FB_MEL, ToChannelsLast{feat, FB_MEL, T, feat_rows, 0});
+}
+template <class BK>
+void campplus_forward_rows(BK& bk, const StyleNet& net, const float* feat_rows, long long T, int len, float* out) {
+  SV_CHECK(T >= 4 && T < (1 << 20), "CAMPPlus: between 4 and 2^20 feature frames");
+  float* feat = bk.alloc(FB_MEL * T);
+  // [T][80] -> [80][T]: ToChannelsLast with the roles of rows and channels swapped
+  bk.pfor(T * FB_MEL, ToChannelsLast{feat_rows, (int)T, FB_MEL, feat, 0});
+  campplus_forward(bk, net, feat, T, len, out);
+}
+
 // ================================================================================================ timbre (BiCodec)
 constexpr int TM_NFFT = 1024, TM_HOP = 320, TM_WIN = 640, TM_BINS = 513, TM_MEL = 128;
 constexpr int TM_LATENTS = 32, TM_DIM = 128;

@@ -30,3 +30,41 @@ def apply_noise_mixing(tensor: torch.Tensor, alpha: float, noise: torch.Tensor |
     _lib.check(eng.lib.svanon_noise_mix(eng.handle, ptr(x), ptr(nz), x.numel(), C.c_float(float(alpha)), ptr(out),
                                         C.c_void_p(_cuda_stream_ptr())))
     return out.to(tensor.dtype)
+
+
+class PromptBuilder:
+    """`InferenceWrapper.calculate_prompt` (evaluations/infer_arvc.py:382-441) over the engine: reference waves at
+    44.1 kHz -> (ref_audio_codes [1,8,T] i32, ref_content_codes [1,T] i64, style_vectors [1,192], timbre_latents
+    [1,32,128], ref_wav [1,n]) -- the five tensors `prefill_prompt` consumes (:462-489).  Every step is a library call:
+    svanon_resample (44.1 -> 16 kHz), svanon_style_vector, svanon_timbre_latent, svanon_noise_mix (style first, then
+    timbre: the order of the reference's two `randn_like` draws, :419-421), svanon_voc_encode, svanon_enc_encode.
+
+    Only the "concat_mel" collation is offered: the reference's "avg" branch falls through to code that reads a
+    variable the branch never sets (:411-417) and cannot run with more than one reference."""
+
+    def __init__(self, speech_tokenizer, firefly, style_encoder, timbre_encoder, sr: int = 44100, resample_freq: int = 16000):
+        from .audio import Resampler
+        self.speech_tokenizer, self.firefly = speech_tokenizer, firefly
+        self.style_encoder, self.timbre_encoder = style_encoder, timbre_encoder
+        self._resample = Resampler(sr, resample_freq)
+
+    @torch.no_grad()
+    def calculate_prompt(self, ref_wav_tensors, alpha: float = 1.0, spk_emb_collate_type: str = "concat_mel",
+                         noise_style: torch.Tensor | None = None, noise_timbre: torch.Tensor | None = None):
+        from .speaker import calculate_style_vec, calculate_timbre_latent
+        refs = list(ref_wav_tensors) if isinstance(ref_wav_tensors, (list, tuple)) else [ref_wav_tensors]
+        if spk_emb_collate_type == "avg" and len(refs) > 1:
+            raise NotImplementedError('spk_emb_collate_type="avg" cannot run in the reference with more than one '
+                                      "reference wave (evaluations/infer_arvc.py:411-417); use \"concat_mel\"")
+        dev = torch.device("cuda", self.style_encoder._engine.device)
+        ref = (torch.cat(refs, dim=-1) if len(refs) > 1 else refs[0]).to(dev, torch.float32)
+        ref16 = self._resample(ref)
+        lens16 = torch.LongTensor([ref16.shape[-1]])
+        style = calculate_style_vec(self.style_encoder, ref16, lens16)
+        timbre = calculate_timbre_latent(self.timbre_encoder, ref16, lens16)
+        style = apply_noise_mixing(style, alpha, noise_style)              # draws (if any) in the reference's order
+        timbre = apply_noise_mixing(timbre, alpha, noise_timbre)
+        lens = torch.LongTensor([ref.shape[-1]])
+        (codes, _), _ = self.firefly.encode(ref, lens)
+        content, _ = self.speech_tokenizer.encode(ref, lens)
+        return codes, content.squeeze(0), style, timbre, ref

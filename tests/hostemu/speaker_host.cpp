@@ -27,7 +27,7 @@ struct HostBK {
   std::vector<std::unique_ptr<std::vector<float>>>& keep_f;
   std::vector<std::unique_ptr<std::vector<double>>>& keep_d;
   std::vector<std::unique_ptr<std::vector<float>>> scratch;
-  long long gemms = 0, pfors = 0;
+  long long gemms = 0, pfors = 0, gemm_flops = 0;
 
   const HostTensor& get(const std::string& name, std::initializer_list<long long> shape) {
     auto it = w.find(name);
@@ -59,6 +59,7 @@ struct HostBK {
   // C[m][n] = bias[n] + sum_t sum_k A[(m * a_row_step + tap_off[t]) * lda + k] * W[t][n][k]   (common.cuh GemmParams)
   void gemm(const GemmParams& p) {
     ++gemms;
+    gemm_flops += 2LL * p.M * p.N * p.K * p.taps;
     SV_CHECK(p.K % 16 == 0 && p.K > 0, "gemm K must be a positive multiple of 16");
     SV_CHECK(p.lda % 4 == 0, "gemm lda must be a multiple of 4");
     SV_CHECK(p.taps >= 1 && p.taps <= MAX_TAPS, "gemm taps");
@@ -128,29 +129,29 @@ int hostemu_finalize(int model) {
   });
 }
 
-// counts[0] = GEMM calls, counts[1] = functor launches of the call
+// counts[0] = GEMM calls, counts[1] = functor launches, counts[2] = GEMM FLOPs of the call
 int hostemu_style_vector(const float* wave, long long n, float* out192, long long* counts) {
   return guarded([&] {
     HostModel& m = g_models[0];
     HostBK bk{m.w, m.keep_f, m.keep_d};
     spk::style_forward(bk, m.style, wave, n, out192);
-    if (counts) { counts[0] = bk.gemms; counts[1] = bk.pfors; }
+    if (counts) { counts[0] = bk.gemms; counts[1] = bk.pfors; counts[2] = bk.gemm_flops; }
   });
 }
 
-int hostemu_kaldi_fbank(const float* wave, long long n, float* feat /*[80][T]*/) {
+int hostemu_kaldi_fbank(const float* wave, long long n, float* feat /*[T][80]*/) {
   return guarded([&] {
     HostModel& m = g_models[0];
     HostBK bk{m.w, m.keep_f, m.keep_d};
-    spk::kaldi_fbank(bk, m.style, wave, n, feat);
+    spk::kaldi_fbank_rows(bk, m.style, wave, n, feat);
   });
 }
 
-int hostemu_campplus(const float* feat /*[80][T]*/, long long T, int len, float* out192) {
+int hostemu_campplus(const float* feat /*[T][80]*/, long long T, int len, float* out192) {
   return guarded([&] {
     HostModel& m = g_models[0];
     HostBK bk{m.w, m.keep_f, m.keep_d};
-    spk::campplus_forward(bk, m.style, feat, T, len, out192);
+    spk::campplus_forward_rows(bk, m.style, feat, T, len, out192);
   });
 }
 
@@ -159,7 +160,7 @@ int hostemu_timbre_latent(const float* wave, long long n, long long wave_len, fl
     HostModel& m = g_models[1];
     HostBK bk{m.w, m.keep_f, m.keep_d};
     spk::timbre_forward(bk, m.timbre, wave, n, wave_len, out, indices, z);
-    if (counts) { counts[0] = bk.gemms; counts[1] = bk.pfors; }
+    if (counts) { counts[0] = bk.gemms; counts[1] = bk.pfors; counts[2] = bk.gemm_flops; }
   });
 }
 

@@ -5,7 +5,7 @@ speaker.hpp is written against a backend interface; tests/hostemu/speaker_host.c
 functors run as loops and the engine's GEMM is a three-loop restatement of the GemmParams contract.  What this pins:
 buffer shapes and zero margins, weight repacking, GEMM descriptors (overlapping rows, row-offset taps, column slices of
 the concat buffers), functor arguments and the derived buffers built by streamvoiceanon_b200/speaker.py.  What it
-cannot pin: the CUDA launch of the functors and the real GEMM kernels -- tests/test_gpu_zz_speaker.py does that on the
+cannot pin: the CUDA launch of the functors and the real GEMM kernels -- tests/test_zz_gpu_speaker.py does that on the
 B200.  The host build is test infrastructure: the product never loads it (tests/test_cabi.py)."""
 import ctypes as C
 import subprocess
@@ -59,11 +59,11 @@ def test_style_branch_host_orchestration_vs_reference(emu, gold):
     a = synth.synth_audio_16k(int(g["seed_a"]), float(g["sec_a"])).contiguous()
     b = synth.synth_audio_16k(int(g["seed_b"]), float(g["sec_b"])).contiguous()
     T = 1 + (a.numel() - 400) // 160
-    feat = torch.empty(80, T)
+    feat = torch.empty(T, 80)
     assert emu.hostemu_kaldi_fbank(_p(a), C.c_longlong(a.numel()), _p(feat)) == 0, emu.hostemu_last_error().decode()
-    assert np.abs(feat.T.numpy() - g["fbank_a"]).max() < 1e-4
+    assert np.abs(feat.numpy() - g["fbank_a"]).max() < 1e-4
     out = torch.empty(192)
-    counts = (C.c_longlong * 2)()
+    counts = (C.c_longlong * 3)()
     assert emu.hostemu_style_vector(_p(a), C.c_longlong(a.numel()), _p(out), counts) == 0, emu.hostemu_last_error().decode()
     assert np.isfinite(out.numpy()).all()
     assert np.abs(out.numpy() - g["style_a"][0]).max() < 1e-4
@@ -71,10 +71,10 @@ def test_style_branch_host_orchestration_vs_reference(emu, gold):
     # the short row of the reference's ragged batch: its own fbank minus its mean, padded with its minimum to the long
     # row's length, lens = frames // 2
     Tb = 1 + (b.numel() - 400) // 160
-    fb = torch.empty(80, Tb)
+    fb = torch.empty(Tb, 80)
     assert emu.hostemu_kaldi_fbank(_p(b), C.c_longlong(b.numel()), _p(fb)) == 0
-    fb = fb - fb.mean(dim=1, keepdim=True)
-    padded = torch.nn.functional.pad(fb, (0, T - Tb), value=float(fb.min())).contiguous()
+    fb = fb - fb.mean(dim=0, keepdim=True)
+    padded = torch.nn.functional.pad(fb, (0, 0, 0, T - Tb), value=float(fb.min())).contiguous()
     assert emu.hostemu_campplus(_p(padded), C.c_longlong(T), Tb // 2, _p(out)) == 0, emu.hostemu_last_error().decode()
     assert np.abs(out.numpy() - g["style_batch"][1]).max() < 1e-4
 
@@ -92,7 +92,7 @@ def test_timbre_branch_host_orchestration_vs_reference(emu, gold):
     for wave, wave_len, want, want_idx in ((a, a.numel(), g["timbre_a"][0], g["indices_a"][0, 0]),
                                            (row_b, b.numel(), g["timbre_batch"][1], g["indices_batch"][1, 0])):
         out, idx, z = torch.empty(32, 128), torch.empty(32, dtype=torch.int32), torch.empty(32, 6)
-        counts = (C.c_longlong * 2)()
+        counts = (C.c_longlong * 3)()
         rc = emu.hostemu_timbre_latent(_p(wave), C.c_longlong(wave.numel()), C.c_longlong(wave_len), _p(out), _p(idx), _p(z), counts)
         assert rc == 0, emu.hostemu_last_error().decode()
         assert np.isfinite(out.numpy()).all()

@@ -109,3 +109,31 @@ def test_config5_prompt_embeddings_vs_reference(encoders, gold):
     safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
     assert safe.mean() > 0.9
     assert np.abs(tl.cpu().numpy() - gp["timbre_latents"])[safe].max() < 5e-4
+
+
+def test_calculate_prompt_vs_reference(encoders, models, gold):
+    """`PromptBuilder.calculate_prompt` -- every step a library call -- against the five outputs of the unmodified
+    `InferenceWrapper.calculate_prompt` for BASELINE config 5's three-reference prompt: codec ids and content ids
+    bit-exact, embeddings to 5e-4 (timbre on the tokens away from an FSQ rounding boundary)."""
+    from oracle import speaker as S
+    from streamvoiceanon_b200.prompt import PromptBuilder
+    style, timbre = encoders
+    _, tok, voc = models
+    gp = gold("prompt_config5")
+    refs = [synth.synth_audio_44k(int(s), float(gp["ref_seconds"]))[None] for s in gp["ref_seeds"]]
+    pb = PromptBuilder(tok, voc, style, timbre)
+    codes, content, sv, tl, ref = pb.calculate_prompt(refs, float(gp["alpha"]), "concat_mel",
+                                                      torch.from_numpy(gp["noise_style"]), torch.from_numpy(gp["noise_timbre"]))
+    assert ref.shape[-1] == int(gp["n_samples"])
+    assert codes.dtype == torch.int32 and np.array_equal(codes.cpu().numpy(), gp["ref_audio_codes"])
+    assert np.array_equal(content.cpu().numpy(), gp["ref_content_codes"])
+    assert np.abs(sv.cpu().numpy() - gp["style_vectors"]).max() < 5e-4
+    from streamvoiceanon_b200.audio import Resampler
+    ref16 = Resampler(44100, 16000)(ref).cpu()
+    with torch.no_grad():
+        _, _, bounded = S.calculate_timbre_latent(ref16, torch.LongTensor([ref16.shape[-1]]),
+                                                  synth.make_timbre_encoder_state_dict(int(gp["weight_seed"])))
+    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+    assert np.abs(tl.cpu().numpy() - gp["timbre_latents"])[safe].max() < 5e-4
+    with pytest.raises(NotImplementedError):
+        pb.calculate_prompt(refs, 1.0, "avg")
