@@ -111,3 +111,52 @@ def test_speaker_functions_reject_short_waves(emu):
     assert b"shorter" in emu.hostemu_last_error()
     lat = torch.empty(32, 128)
     assert emu.hostemu_timbre_latent(_p(w), C.c_longlong(700), C.c_longlong(700), _p(lat), None, None, None) == 1
+
+
+def _style(emu, wave):
+    out = torch.empty(192)
+    assert emu.hostemu_style_vector(_p(wave), C.c_longlong(wave.numel()), _p(out), None) == 0, emu.hostemu_last_error().decode()
+    return out
+
+
+def _timbre(emu, wave, wave_len=None):
+    out, idx, z = torch.empty(32, 128), torch.empty(32, dtype=torch.int32), torch.empty(32, 6)
+    n = wave.numel()
+    rc = emu.hostemu_timbre_latent(_p(wave), C.c_longlong(n), C.c_longlong(n if wave_len is None else wave_len), _p(out), _p(idx),
+                                   _p(z), None)
+    assert rc == 0, emu.hostemu_last_error().decode()
+    return out, idx, z
+
+
+def test_config5_prompt_embeddings_host_orchestration(emu, gold):
+    """The 4.8 s three-reference concatenation of BASELINE config 5: both embeddings through the host build, mixed with
+    the reference's recorded draws (oracle mix), against the outputs of the unmodified `calculate_prompt`."""
+    from oracle import prompt as P
+    gp = gold("prompt_config5")
+    refs = [synth.synth_audio_44k(int(s), float(gp["ref_seconds"]))[None] for s in gp["ref_seeds"]]
+    ref16 = P.resample(torch.cat(refs, dim=-1), 44100, 16000)[0].contiguous()
+    alpha = float(gp["alpha"])
+    sv = P.apply_noise_mixing(_style(emu, ref16).numpy()[None], alpha, gp["noise_style"])
+    tl = P.apply_noise_mixing(_timbre(emu, ref16)[0].numpy()[None], alpha, gp["noise_timbre"])
+    assert np.abs(sv - gp["style_vectors"]).max() < 1e-4
+    assert np.abs(tl - gp["timbre_latents"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("n", [880, 1024, 16000 + 37, 33333])
+def test_edge_lengths_host_orchestration_vs_oracle(emu, gold, n):
+    """Shortest accepted waves (4 fbank frames: every dilated conv reads mostly margin rows; 1024 samples: 4 mel frames),
+    a length that is no multiple of either hop, and one with several CAM segments whose last one is short -- against the
+    CPU oracle (itself pinned to the reference)."""
+    from oracle import speaker as S
+    seed = int(gold("style_vec")["weight_seed"])
+    wave = synth.synth_audio_16k(5300 + n % 7, 2.5)[:n].contiguous()
+    lens = torch.LongTensor([n])
+    with torch.no_grad():
+        want_s = S.calculate_style_vec(wave[None], lens, synth.make_campplus_state_dict(seed))
+        want_t, want_idx, bounded = S.calculate_timbre_latent(wave[None], lens, synth.make_timbre_encoder_state_dict(seed))
+    assert np.abs(_style(emu, wave).numpy() - want_s[0].numpy()).max() < 1e-4
+    if n >= 1024:
+        out, idx, _ = _timbre(emu, wave)
+        safe = ((bounded[0] - bounded[0].floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+        assert np.array_equal(idx.numpy()[safe], want_idx[0].numpy()[safe])
+        assert np.abs(out.numpy() - want_t[0].numpy())[safe].max() < 1e-4
