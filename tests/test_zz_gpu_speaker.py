@@ -7,14 +7,21 @@ Floating point, so tolerances instead of bit-exactness: log-mel features 1e-4 (a
 2e-4 (values O(1); 3xTF32 tensor-core products through 52 dense layers), timbre latents 1e-4 and FSQ indices exact
 wherever the FSQ input is further than 1e-3 from a rounding boundary (the reference's own ids flip there between BLAS
 builds).  The same source was held to the same fixtures by a host build first (tests/test_speaker_hostemu.py); this file
-sorts last so that a failure here cannot hide the hot-path tests under `-x`."""
+sorts last so that a failure here cannot hide the hot-path tests under `-x`.
+
+STATUS: written after round 1's GPU minutes were spent -- these tests have never executed on a GPU.  Until their first
+run they are non-gating (`xfail(strict=False)`: a pass shows as XPASS, a failure as XFAIL, both in the summary line) and
+carry a hard per-test timeout so that an unforeseen stall cannot hold the GPU box.  Remove both markers after the
+first green run (NEXT.md section 0)."""
 import numpy as np
 import pytest
 import torch
 
 from streamvoiceanon_b200 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread"),
+              pytest.mark.xfail(strict=False, reason="speaker-encoder CUDA path not yet run on a GPU (round 1 ran out of "
+                                                     "GPU minutes); host build of the same source is green")]
 
 FBANK_TOL = 1e-4
 STYLE_TOL = 2e-4
