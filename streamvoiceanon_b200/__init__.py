@@ -9,10 +9,13 @@ library (include/svanon.h, streamvoiceanon_b200/libsvanon_b200.so):
     StreamSession      <-> InferenceWrapper.process_one_chunk as one library call per chunk
     BatchSession       <-> the same loop for N concurrent streams in lock-step (the reference is batch-1)
     StreamPool         <-> streams that join / leave at any chunk boundary, grouped into lock-step cohorts
+    InferenceWrapper   <-> evaluations.infer_arvc.InferenceWrapper (prompt from waves, stream_infer, infer)
+    speaker.CAMPPlus / speaker.SpeakerEncoder <-> the two speaker encoders of the prompt path
 """
 from . import synth  # noqa: F401
 
-__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "BatchSession", "StreamPool", "synth"]
+__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "BatchSession", "StreamPool", "InferenceWrapper",
+           "synth"]
 
 
 def __getattr__(name):
@@ -28,4 +31,7 @@ def __getattr__(name):
     if name == "StreamPool":
         from .server import StreamPool
         return StreamPool
+    if name == "InferenceWrapper":
+        from .inference import InferenceWrapper
+        return InferenceWrapper
     raise AttributeError(name)

@@ -144,3 +144,64 @@ def test_calculate_prompt_vs_reference(encoders, models, gold):
     assert np.abs(tl.cpu().numpy() - gp["timbre_latents"])[safe].max() < 5e-4
     with pytest.raises(NotImplementedError):
         pb.calculate_prompt(refs, 1.0, "avg")
+
+
+def _wrapper(encoders, models):
+    from streamvoiceanon_b200.inference import InferenceWrapper
+    style, timbre = encoders
+    ar, tok, voc = models
+    return InferenceWrapper(ar, tok, voc, style, timbre)
+
+
+def test_inference_wrapper_config5_vs_reference(encoders, models, gold, tape):
+    """The reference's own call sequence -- `prefill_prompt(ref waves, max_prompt_frames, delay, alpha)`,
+    `setup_stream_caches`, `process_one_chunk` x 12 -- through the engine's `InferenceWrapper`, from WAVES (speaker
+    encoders on the GPU), against the unmodified reference's run of BASELINE config 5 (tests/golden/stream_config5.npz):
+    content ids and codec ids bit-exact, waveform MSE < 1e-8."""
+    g, gp = gold("stream_config5"), gold("prompt_config5")
+    iw = _wrapper(encoders, models)
+    iw.set_noise_fn(tape(int(g["tape_seed"])))
+    refs = [synth.synth_audio_44k(int(s), float(gp["ref_seconds"]))[None] for s in gp["ref_seeds"]]
+    iw.prefill_prompt(refs, max_prompt_frames=int(g["max_prompt_frames"]), delay=int(g["delay"]), alpha=float(g["alpha"]),
+                      noise_style=torch.from_numpy(gp["noise_style"]), noise_timbre=torch.from_numpy(gp["noise_timbre"]))
+    assert tuple(iw.ref_audio_codes.shape) == (1, 8, int(g["max_prompt_frames"]))
+    chunk, n = int(g["decode_chunk_frames"]), int(g["n_chunks"])
+    iw.setup_stream_caches(int(g["encode_window_frames"]), int(g["decode_window_frames"]), int(g["max_seq_frames"]),
+                           int(g["buffer_frames"]), chunk)
+    src = synth.synth_audio_44k(int(g["src_seed"]), 1.5)[: n * chunk * 2048].view(n, chunk * 2048).cuda()
+    wave = torch.cat([iw.process_one_chunk(src[i][None]).clone() for i in range(n)], dim=-1)
+    assert np.array_equal(iw.src_content_codes.numpy(), g["src_content"])
+    assert np.array_equal(iw.pred_codes.numpy(), g["pred_codes"])
+    assert float(((wave[0].cpu().numpy() - g["wave"]) ** 2).mean()) < 1e-8
+
+
+def test_inference_wrapper_stream_infer_and_infer(encoders, models, tape):
+    """`stream_infer` == its own parts called by hand (left padding to whole chunks included: a full extra chunk when the
+    source is already aligned, infer_arvc.py:648-649), and `infer` == tokenizer.encode + calculate_prompt + generate +
+    code2wav composed by hand.  alpha = 1 keeps the anonymisation mix out of the comparison (0 * noise)."""
+    iw = _wrapper(encoders, models)
+    ref = synth.synth_audio_44k(5400, 1.2)[None]
+    src = synth.synth_audio_44k(1400, 0.6)[: 6 * 2048 + 100]
+    cfg = dict(encode_window_frames=24, decode_window_frames=16, max_prompt_frames=20, max_seq_frames=60, buffer_frames=6,
+               decode_chunk_frames=2, delay=2)
+    iw.set_noise_fn(tape(7100))
+    got = iw.stream_infer(src, ref, **cfg)
+    assert got.shape == (8 * 2048,)                                 # 6 frames + 100 samples -> 4 two-frame chunks
+    iw.set_noise_fn(tape(7100))
+    iw.prefill_prompt([ref], max_prompt_frames=20, delay=2, alpha=1.0)
+    iw.setup_stream_caches(24, 16, 60, 6, 2)
+    padded = torch.nn.functional.pad(src, (4096 - src.numel() % 4096, 0)).view(-1, 4096).cuda()
+    want = torch.cat([iw.process_one_chunk(padded[i][None]) for i in range(padded.shape[0])], dim=-1)[0].cpu().numpy()
+    assert np.array_equal(got, want)
+    # offline
+    iw.set_noise_fn(tape(7200))
+    wav = iw.infer(src, ref, delay=2)
+    codes, content, style, timbre, _ = iw.calculate_prompt([ref.cuda()], 1.0)
+    ar, tok, voc = models
+    sc, _ = tok.encode(src[None].cuda(), torch.LongTensor([src.numel()]))
+    ar.set_delay(delay=2)
+    ar.set_noise_fn(tape(7200), 0)
+    vc = ar.generate(ref_content_codes=content, ref_audio_codes=codes, src_content_codes=sc.squeeze(0), style_vectors=style,
+                     timbre_latents=timbre)
+    want = voc.head(voc.quantizer.decode(vc.long())).squeeze().cpu().numpy()
+    assert wav.shape == (6 * 2048,) and np.array_equal(wav, want)
