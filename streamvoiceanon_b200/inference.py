@@ -40,7 +40,7 @@ class InferenceWrapper:
         self.model, self.speech_tokenizer, self.firefly = model, speech_tokenizer, firefly
         self.style_encoder, self.timbre_encoder = style_encoder, timbre_encoder
         self.sr = sr
-        self.device = torch.device("cuda", model._engine.device)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", model._engine.device)
         self._prompt = PromptBuilder(speech_tokenizer, firefly, style_encoder, timbre_encoder, sr, self.RESAMPLE_FREQ)
         self._session: Optional[StreamSession] = None
         self._noise_fn: Optional[Callable] = None

@@ -43,10 +43,15 @@ class PromptBuilder:
     variable the branch never sets (:411-417) and cannot run with more than one reference."""
 
     def __init__(self, speech_tokenizer, firefly, style_encoder, timbre_encoder, sr: int = 44100, resample_freq: int = 16000):
-        from .audio import Resampler
         self.speech_tokenizer, self.firefly = speech_tokenizer, firefly
         self.style_encoder, self.timbre_encoder = style_encoder, timbre_encoder
-        self._resample = Resampler(sr, resample_freq)
+        self._rates, self._resampler = (sr, resample_freq), None
+
+    def _resample(self, wave):
+        if self._resampler is None:                      # built on first use: needs the engine (a GPU)
+            from .audio import Resampler
+            self._resampler = Resampler(*self._rates)
+        return self._resampler(wave)
 
     @torch.no_grad()
     def calculate_prompt(self, ref_wav_tensors, alpha: float = 1.0, spk_emb_collate_type: str = "concat_mel",
