@@ -25,7 +25,9 @@ WEIGHT_SEED, MIX_SEED, ALPHA = 1234, 77, 0.7
 REF_SEEDS, REF_SECONDS = (5200, 5201, 5202), 1.6
 
 
-def main():
+def build_wrapper():
+    """The reference's `InferenceWrapper` around the reference's own five modules holding the synthetic checkpoints (no
+    method replaced).  Returns (wrapper, noise tape, (model, tokenizer, vocoder))."""
     torch.set_num_threads(8)
     voc_sd = dict(synth.make_vocoder_state_dict(WEIGHT_SEED))
     voc_sd.update(synth.make_vocoder_encoder_state_dict(WEIGHT_SEED))
@@ -49,6 +51,11 @@ def main():
     w.sr = 44100
     w.model, w.speech_tokenizer, w.firefly = model, tok, voc
     w.style_encoder, w.timbre_encoder = style_enc.eval(), timbre_enc.eval()
+    return w, tape, (model, tok, voc)
+
+
+def main():
+    w, tape, (model, tok, voc) = build_wrapper()
     refs = [synth.synth_audio_44k(s, REF_SECONDS)[None] for s in REF_SEEDS]
     with torch.no_grad():
         torch.manual_seed(MIX_SEED)

@@ -194,15 +194,16 @@ class InferenceWrapper:
     # ------------------------------------------------------------------------------------------ offline
     @torch.no_grad()
     def infer(self, src_path: Wave, ref_path: Union[Wave, Sequence[Wave]], out_dir=None, output_path=None, delay=None,
-              ref_crop_lengths=None, alpha=1.0, spk_emb_collate_type="concat_mel", save_result=False,
-              **sampling_kwargs) -> np.ndarray:
+              ref_crop_lengths=None, alpha=1.0, spk_emb_collate_type="concat_mel", save_result=False, *,
+              noise_style=None, noise_timbre=None, **sampling_kwargs) -> np.ndarray:
         if save_result:
             raise NotImplementedError("writing .wav files is left to the caller (torchaudio.save needs torchcodec)")
         src = self._load(src_path)
         refs, crops = self.process_ref_paths(ref_path, ref_crop_lengths)
         ref_tensors = [self._load(r, c) for r, c in zip(refs, crops)]
         # same arithmetic and the same two noise draws as the reference's inlined copy of calculate_prompt (:280-346)
-        codes, content, style, timbre, _ = self.calculate_prompt(ref_tensors, alpha, spk_emb_collate_type)
+        codes, content, style, timbre, _ = self.calculate_prompt(ref_tensors, alpha, spk_emb_collate_type,
+                                                                 noise_style=noise_style, noise_timbre=noise_timbre)
         src_content, _ = self.speech_tokenizer.encode(src, self.create_wave_lens_tensor(src))
         if delay is not None:
             self.model.set_delay(delay=delay)

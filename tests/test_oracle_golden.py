@@ -296,3 +296,59 @@ def test_stream_config5_loop_from_reference_waves(weights, gold, tape):
     assert np.array_equal(so.src_content_codes.numpy(), g["src_content"])
     assert np.array_equal(so.pred_codes.numpy(), g["pred_codes"])
     assert float(((wave[0].numpy() - g["wave"]) ** 2).mean()) < 1e-10
+
+
+def _infer_inputs(g):
+    src = synth.synth_audio_44k(int(g["src_seed"]), float(g["src_seconds"]))[None]
+    refs = [synth.synth_audio_44k(int(s), float(g["ref_seconds"]))[None] for s in g["ref_seeds"]]
+    return src, refs
+
+
+def test_offline_infer_from_files_oracle_vs_reference(weights, gold, tape):
+    """BASELINE config 1 as a user runs it: the UNMODIFIED `InferenceWrapper.infer(src.wav, [ref_a.wav, ref_b.wav],
+    delay=2, alpha=0.7)` (infer_arvc.py:261-380; tests/golden/infer_config1.npz, oracle/make_golden_infer.py) against the
+    chained oracle: calculate_prompt (both speaker encoders, mix with the recorded draws, codec + content ids) ->
+    tokenizer on the source -> offline `generate` -> code2wav.  Waveform MSE < 1e-10 (ids are exact or it would not be)."""
+    from oracle import prompt as P
+    from oracle import vocoder as V
+    g = gold("infer_config1")
+    ws = int(g["weight_seed"])
+    src, refs = _infer_inputs(g)
+    with torch.no_grad():
+        codes, content, style, timbre, _ = P.calculate_prompt(
+            refs, float(g["alpha"]), g["noise_style"], g["noise_timbre"], synth.make_campplus_state_dict(ws),
+            synth.make_timbre_encoder_state_dict(ws), weights["tok"], weights["voc_enc"])
+        src_content = E.encode(src, weights["tok"])[0].squeeze(0)
+        ar = DualAR(weights["ar"], tape(int(g["tape_seed"])))
+        ar.set_delay(2)
+        vc = ar.generate(content, codes, src_content, style, timbre)
+        wave = V.code2wav(vc.long(), weights["voc_folded"]).squeeze()
+    assert wave.shape == g["wave"].shape == (src.shape[1] // 2048 * 2048,)
+    assert float(((wave.numpy() - g["wave"]) ** 2).mean()) < 1e-10
+
+
+def test_stream_infer_from_files_oracle_vs_reference(weights, gold, tape):
+    """BASELINE config 2 as a user runs it: the UNMODIFIED `InferenceWrapper.stream_infer(src.wav, ref.wav, chunk 1,
+    delay 2)` (infer_arvc.py:598-676) -- file loading, prompt from the reference WAVE, left padding to whole chunks, the
+    loop with the re-prompt firing -- against the chained oracle.  Ids exact, waveform MSE < 1e-10."""
+    from oracle import prompt as P
+    g = gold("infer_config1")
+    ws = int(g["weight_seed"])
+    src, refs = _infer_inputs(g)
+    cfg = {k: int(g[f"stream_{k}"]) for k in ("encode_window_frames", "decode_window_frames", "max_prompt_frames",
+                                              "max_seq_frames", "buffer_frames", "decode_chunk_frames", "delay")}
+    with torch.no_grad():
+        z192, z4096 = np.zeros((1, 192), np.float32), np.zeros((1, 32, 128), np.float32)
+        codes, content, style, timbre, _ = P.calculate_prompt(                      # alpha = 1: the draws do not matter
+            refs[:1], 1.0, z192, z4096, synth.make_campplus_state_dict(ws), synth.make_timbre_encoder_state_dict(ws),
+            weights["tok"], weights["voc_enc"])
+        so = StreamOracle(weights["ar"], weights["tok"], weights["voc_folded"], tape(int(g["tape_seed"])))
+        so.prefill_prompt(codes, content, style, timbre, max_prompt_frames=cfg["max_prompt_frames"], delay=cfg["delay"])
+        so.setup_stream_caches(cfg["encode_window_frames"], cfg["decode_window_frames"], cfg["max_seq_frames"],
+                               cfg["buffer_frames"], cfg["decode_chunk_frames"])
+        step = 2048 * cfg["decode_chunk_frames"]
+        padded = torch.nn.functional.pad(src, (step - src.shape[1] % step, 0)).view(-1, step)
+        wave = torch.cat([so.process_one_chunk(padded[i][None]) for i in range(padded.shape[0])], dim=-1)
+    assert np.array_equal(so.src_content_codes.numpy(), g["stream_src_content"])
+    assert np.array_equal(so.pred_codes.numpy(), g["stream_pred_codes"])
+    assert float(((wave[0].numpy() - g["stream_wave"]) ** 2).mean()) < 1e-10

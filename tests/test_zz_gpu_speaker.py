@@ -205,3 +205,26 @@ def test_inference_wrapper_stream_infer_and_infer(encoders, models, tape):
                      timbre_latents=timbre)
     want = voc.head(voc.quantizer.decode(vc.long())).squeeze().cpu().numpy()
     assert wav.shape == (6 * 2048,) and np.array_equal(wav, want)
+
+
+def test_inference_wrapper_infer_and_stream_infer_vs_reference_files_run(encoders, models, gold, tape):
+    """BASELINE configs 1 and 2 as a user runs them, against the UNMODIFIED reference's `infer(src.wav, [a.wav, b.wav],
+    delay=2, alpha=0.7)` and `stream_infer(src.wav, a.wav, chunk 1, delay 2)` (tests/golden/infer_config1.npz,
+    oracle/make_golden_infer.py): everything from the waves on the GPU -- both speaker encoders, codec and content ids,
+    offline generate / the streaming loop with its padding rule and a re-prompt, vocoder.  Ids exact, waveform MSE < 1e-8."""
+    g = gold("infer_config1")
+    iw = _wrapper(encoders, models)
+    src = synth.synth_audio_44k(int(g["src_seed"]), float(g["src_seconds"]))
+    refs = [synth.synth_audio_44k(int(s), float(g["ref_seconds"])) for s in g["ref_seeds"]]
+    iw.set_noise_fn(tape(int(g["tape_seed"])))
+    wave = iw.infer(src, refs, delay=2, alpha=float(g["alpha"]), noise_style=torch.from_numpy(g["noise_style"]),
+                    noise_timbre=torch.from_numpy(g["noise_timbre"]))
+    assert wave.shape == g["wave"].shape
+    assert float(((wave - g["wave"]) ** 2).mean()) < 1e-8
+    cfg = {k: int(g[f"stream_{k}"]) for k in ("encode_window_frames", "decode_window_frames", "max_prompt_frames",
+                                              "max_seq_frames", "buffer_frames", "decode_chunk_frames", "delay")}
+    iw.set_noise_fn(tape(int(g["tape_seed"])))
+    stream_wave = iw.stream_infer(src, refs[0], alpha=1.0, **cfg)
+    assert np.array_equal(iw.src_content_codes.numpy(), g["stream_src_content"])
+    assert np.array_equal(iw.pred_codes.numpy(), g["stream_pred_codes"])
+    assert float(((stream_wave - g["stream_wave"]) ** 2).mean()) < 1e-8
