@@ -38,6 +38,16 @@ def test_errors_are_reported_not_crashed(lib):
     assert b"null" in lib.svanon_last_error()
 
 
+def test_speaker_entry_points_reject_null_arguments(lib):
+    """The prompt-path entry points fail with a message, not a crash, on null handles / buffers."""
+    buf = (C.c_float * 8)()
+    for rc in (lib.svanon_kaldi_fbank(None, buf, 1000, buf, None),
+               lib.svanon_campplus_forward(None, buf, 10, 5, buf, None),
+               lib.svanon_style_vector(None, buf, 1000, buf, None),
+               lib.svanon_timbre_latent(None, buf, 2000, 2000, buf, None, None)):
+        assert rc != 0 and lib.svanon_last_error()
+
+
 def test_no_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
