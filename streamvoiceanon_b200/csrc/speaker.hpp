@@ -382,42 +382,47 @@ struct ColMean {
 };
 
 // PerceiverResampler cross attention (perceiver_encoder.py:100-175): 32 latent queries, keys / values = the first
-// `nkeys` rows of [latents ; context] (rows past the mask never contribute: their scores are -float max).
-// One thread per (query, head); head dim 64.
-struct PerceiverAttn {
+// `nkeys` rows of [latents ; context] (rows past the mask never contribute: their scores are -float max).  Two passes:
+// scores[q][h][j] = (q . k_j) * scale, one thread per score; then one thread per output element does the softmax
+// statistics of its (query, head) row and the weighted sum of its value column.  Head dim 64.
+struct PerceiverScores {
   const float* q;    // [nq][heads*64]
   const float* kv;   // [rows][2*heads*64]: k then v
   int heads, nkeys;
   float scale;
-  float* out;        // [nq][heads*64]
+  float* scores;     // [nq][heads][nkeys]
   SV_HD void operator()(long long i) const {
-    const int h = (int)(i % heads);
-    const long long qi = i / heads;
+    const int j = (int)(i % nkeys);
+    const long long r = i / nkeys;
+    const int h = (int)(r % heads);
+    const long long qi = r / heads;
     const int D = heads * 64;
     const float* qp = q + qi * D + h * 64;
+    const float* kp = kv + (long long)j * 2 * D + h * 64;
+    float s = 0.f;
+    for (int d = 0; d < 64; ++d) s += qp[d] * kp[d];
+    scores[i] = s * scale;
+  }
+};
+struct PerceiverSoftmaxV {
+  const float* scores;   // [nq][heads][nkeys]
+  const float* kv;
+  int heads, nkeys;
+  float* out;            // [nq][heads*64]
+  SV_HD void operator()(long long i) const {
+    const int D = heads * 64;
+    const int c = (int)(i % D);                  // h * 64 + d
+    const long long qi = i / D;
+    const float* sp = scores + (qi * heads + c / 64) * nkeys;
     float m = -3.4028234663852886e38f;
+    for (int j = 0; j < nkeys; ++j) m = sp[j] > m ? sp[j] : m;
+    float l = 0.f, acc = 0.f;
     for (int j = 0; j < nkeys; ++j) {
-      const float* kp = kv + (long long)j * 2 * D + h * 64;
-      float s = 0.f;
-      for (int d = 0; d < 64; ++d) s += qp[d] * kp[d];
-      s *= scale;
-      m = s > m ? s : m;
-    }
-    float acc[64];
-    for (int d = 0; d < 64; ++d) acc[d] = 0.f;
-    float l = 0.f;
-    for (int j = 0; j < nkeys; ++j) {
-      const float* kp = kv + (long long)j * 2 * D + h * 64;
-      float s = 0.f;
-      for (int d = 0; d < 64; ++d) s += qp[d] * kp[d];
-      const float p = expf(s * scale - m);
+      const float p = expf(sp[j] - m);
       l += p;
-      const float* vp = kp + D;
-      for (int d = 0; d < 64; ++d) acc[d] += p * vp[d];
+      acc += p * kv[(long long)j * 2 * D + D + c];
     }
-    const float inv = 1.f / l;
-    float* op = out + qi * D + h * 64;
-    for (int d = 0; d < 64; ++d) op[d] = acc[d] * inv;
+    out[i] = acc / l;
   }
 };
 
@@ -802,7 +807,7 @@ struct TimbreNet {
 inline long long timbre_frames(long long n) { return n / TM_HOP + 1; }
 inline size_t timbre_ws_floats(long long n) {
   const long long T = timbre_frames(n);
-  return (size_t)T * (TM_NFFT + TM_BINS + 128 + 512 * 5 + 1536 * 2 + 64 + 128 + 1024 + 64) + (1u << 20);
+  return (size_t)T * (TM_NFFT + TM_BINS + 128 + 512 * 5 + 1536 * 2 + 64 + 128 + 1024 + 64 + 256) + (1u << 20);
 }
 
 template <class BK>
@@ -954,6 +959,7 @@ void timbre_forward(BK& bk, const TimbreNet& net, const float* wave, long long n
   float* q = bk.alloc(NL * 512);
   float* kv = bk.alloc((T + NL) * 1024);
   float* att = bk.alloc(NL * 512);
+  float* scores = bk.alloc((long long)NL * 8 * (T + NL));
   float* u = bk.alloc(NL * 682);
   float* gg = bk.alloc(NL * 341);
   for (int l = 0; l < 2; ++l) {
@@ -963,7 +969,8 @@ void timbre_forward(BK& bk, const TimbreNet& net, const float* wave, long long n
     GemmParams p;
     p.A = kvin; p.W = L.wkv; p.C = kv; p.M = Ti + NL; p.N = 1024; p.K = TM_DIM; p.lda = TM_DIM; p.ldc = 1024;
     bk.gemm(p);
-    bk.pfor(NL * 8, PerceiverAttn{q, kv, 8, nkeys, 0.125f, att});
+    bk.pfor((long long)NL * 8 * nkeys, PerceiverScores{q, kv, 8, nkeys, 0.125f, scores});
+    bk.pfor(NL * 512, PerceiverSoftmaxV{scores, kv, 8, nkeys, att});
     bk.pfor(NL * TM_DIM, SmallLinear{att, 512, L.wo, nullptr, lat, TM_DIM, lat, TM_DIM, TM_DIM, 512, 0, nullptr, nullptr});
     bk.pfor(NL * 682, SmallLinear{lat, TM_DIM, L.f0w, L.f0b, nullptr, 0, u, 682, 682, TM_DIM, 0, nullptr, nullptr});
     bk.pfor(NL * 341, Geglu{u, 341, gg});
