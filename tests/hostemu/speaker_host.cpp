@@ -5,6 +5,7 @@
 // (tests/golden/style_vec.npz, timbre_latent.npz) by `pytest -m "not gpu"` on a machine without a GPU.
 // It is built by tests/test_speaker_hostemu.py into tests/hostemu/_build/ and loaded by that test alone; the product
 // (streamvoiceanon_b200/_lib.py) only ever loads libsvanon_b200.so and has no CPU path.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -28,6 +29,14 @@ struct HostBK {
   std::vector<std::unique_ptr<std::vector<double>>>& keep_d;
   std::vector<std::unique_ptr<std::vector<float>>> scratch;
   long long gemms = 0, pfors = 0, gemm_flops = 0;
+  bool tf32x3 = std::getenv("HOSTEMU_TF32X3") != nullptr;      // restate the 3xTF32 products of the tensor-core GEMM
+  static float head(float v) {
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    u &= 0xFFFFE000u;
+    std::memcpy(&v, &u, 4);
+    return v;
+  }
 
   const HostTensor& get(const std::string& name, std::initializer_list<long long> shape) {
     auto it = w.find(name);
@@ -73,7 +82,16 @@ struct HostBK {
         for (int t = 0; t < p.taps; ++t) {
           const float* a = p.A + ((long long)m * p.a_row_step + p.tap_off[t]) * p.lda;
           const float* wr = p.W + ((long long)t * p.N + n) * p.K;
-          for (int k = 0; k < p.K; ++k) acc += a[k] * wr[k];
+          if (!tf32x3) {
+            for (int k = 0; k < p.K; ++k) acc += a[k] * wr[k];
+          } else {
+            // the tensor-core kernel's arithmetic (gemm_tc.cu): operands split into a 10-bit-mantissa head and the
+            // remainder, products hi*hi + hi*lo + lo*hi (lo*lo dropped), fp32 accumulation
+            for (int k = 0; k < p.K; ++k) {
+              const float ah = head(a[k]), al = a[k] - ah, bh = head(wr[k]), bl = wr[k] - bh;
+              acc += ah * bh + ah * bl + al * bh;
+            }
+          }
         }
         if (p.bias) acc += p.bias[n];
         p.C[(long long)m * p.ldc + n] = acc;

@@ -160,3 +160,16 @@ def test_edge_lengths_host_orchestration_vs_oracle(emu, gold, n):
         safe = ((bounded[0] - bounded[0].floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
         assert np.array_equal(idx.numpy()[safe], want_idx[0].numpy()[safe])
         assert np.abs(out.numpy() - want_t[0].numpy())[safe].max() < 1e-4
+
+
+def test_tensor_core_product_arithmetic_keeps_the_embeddings(emu, gold, monkeypatch):
+    """The engine runs these GEMMs on the tensor cores as 3xTF32 products (hi*hi + hi*lo + lo*hi, gemm_tc.cu).  With the
+    host GEMM restating that arithmetic the style vector stays within 1e-5 of the reference and the timbre latents stay
+    exact -- the GPU tolerances (2e-4 / 1e-4) are not there to absorb the GEMM arithmetic."""
+    monkeypatch.setenv("HOSTEMU_TF32X3", "1")
+    gs, gt = gold("style_vec"), gold("timbre_latent")
+    a = synth.synth_audio_16k(int(gs["seed_a"]), float(gs["sec_a"])).contiguous()
+    assert np.abs(_style(emu, a).numpy() - gs["style_a"][0]).max() < 1e-5
+    out, idx, _ = _timbre(emu, a)
+    assert np.array_equal(idx.numpy(), gt["indices_a"][0, 0])
+    assert np.abs(out.numpy() - gt["timbre_a"][0]).max() < 1e-5
