@@ -18,6 +18,8 @@ dual-AR decode step, vocoder on the last 64 code frames, tail select.  Prints ON
                      tensor peak; stage_compute: executed GFLOP / stage time of the compute-bound stages E and V (single stream
                      and the largest lock-step batch under RTF 1) against the 3xTF32 ceiling
   concurrent_streams B streams per GPU in lock-step (svanon_batch_process_chunk): the metric's "streams per GPU at RTF < 1"
+  prompt_path        (N = 1) the setup path beside the headline: calculate_prompt on 5 s of reference audio, per step, timed by
+                     tools/bench_prompt.py in a child process with a time limit; {"unavailable": why} if that fails
 """
 from __future__ import annotations
 
@@ -55,7 +57,28 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=10, help="chunks of the CPU baseline sample (main arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--concurrent", default="64,128,160,176", help="stream counts of the lock-step batch sweep (N=1 only; '' = skip)")
+    ap.add_argument("--no-prompt-path", action="store_true", help="skip the setup-path leg (child process, N=1 only)")
     return ap.parse_args()
+
+
+def prompt_path_leg(timeout_s: int = 150):
+    """Setup path beside the headline (never inside it): `PromptBuilder.calculate_prompt` on 5 s of reference audio --
+    resample, both speaker encoders, noise mix, codec ids, content ids -- per step, CUDA-event ms and kernel launches,
+    measured by tools/bench_prompt.py in a CHILD process with a hard time limit, so that nothing this leg does (its
+    speaker-encoder kernels were written after round 1's GPU minutes ran out and first execute here and in
+    tests/test_zz_gpu_speaker.py) can cost the bench line.  Returns the tool's JSON row or {"unavailable": why}."""
+    what = ("setup path, once per stream: streamvoiceanon_b200.prompt.PromptBuilder.calculate_prompt on 5 s of synthetic "
+            "reference audio (tools/bench_prompt.py, child process): per step CUDA-event ms after warm-up and kernel launches")
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_prompt.py"), "5"], capture_output=True, text=True,
+                           timeout=timeout_s)
+        rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not rows:
+            tail = (r.stderr or r.stdout).strip().splitlines()[-1:] or ["no output"]
+            return {"what": what, "unavailable": f"exit {r.returncode}: {tail[0][:300]}"}
+        return dict(json.loads(rows[-1]), what=what)
+    except Exception as exc:                                                   # timeout included
+        return {"what": what, "unavailable": repr(exc)[:300]}
 
 
 def make_inputs(rank: int):
@@ -423,6 +446,8 @@ def run_engine(args):
                                 "sample": f"{args.cpu_sample} chunks of the same workload after 2 warm-up chunks, "
                                           f"oracle/streaming.py, torch fp32, {cores} threads",
                                 "ms_per_step": mean_ms, "stage_ms_median": cstage}
+    if world == 1 and not args.no_prompt_path:
+        line["prompt_path"] = prompt_path_leg()
     emit(line)
     if world > 1:
         dist.destroy_process_group()
