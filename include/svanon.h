@@ -109,6 +109,13 @@ int svanon_ar_decode_batch(svanon_stream* const* streams, int n, const int64_t* 
 int svanon_ar_generate(svanon_stream* s, const int64_t* ref_content, const int32_t* ref_audio, int Tr,
                        const int64_t* src_content, int Ts, const float* style, const float* timbre,
                        const float* noise, int32_t* codes_out, void* cuda_stream);
+
+/* Per-call sampling arguments of `generate(..., temperature=, top_p=)` (modules/arvc_wrapper.py:82-98): the reference
+ * samples the first frame with its defaults (its prefill call passes no kwargs, modules/dual_ar_stream.py:723) and every
+ * later frame with the caller's (:745-752).  Set before svanon_ar_generate; negative values clear (all frames use
+ * svanon_ar_set_sampling's).  `repetition_penalty` has no effect in the reference (previous_tokens is always None). */
+int svanon_ar_set_generate_sampling(svanon_stream* s, float temperature, float top_p);
+
 int svanon_ar_position(const svanon_stream* s); /* next free sequence position */
 /* test hook: capture the logits of the next decode steps (slow 8192-way head, pre-norm hidden state, 8 fast
  * heads) of stream 0 of each launch; read them back with svanon_ar_read_debug (host pointers, may be NULL) */

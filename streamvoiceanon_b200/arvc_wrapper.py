@@ -195,9 +195,15 @@ class ARVCWrapper:
     def generate(self, ref_content_codes, ref_audio_codes, src_content_codes, style_vectors, timbre_latents,
                  **sampling_kwargs):
         """modules/arvc_wrapper.py:82-98 -> [1, 8, Ts] int32."""
-        if sampling_kwargs:
-            raise NotImplementedError("per-call sampling kwargs: use set_sampling(); note the reference applies them "
-                                      "from the second frame on only (dual_ar_stream.py:723)")
+        # per-call sampling arguments: the reference applies them from the SECOND frame on (its prefill call passes none,
+        # dual_ar_stream.py:723); `repetition_penalty` never has an effect there (previous_tokens is always None)
+        unknown = set(sampling_kwargs) - {"temperature", "top_p", "repetition_penalty"}
+        if unknown:
+            raise TypeError(f"generate() got unexpected sampling arguments {sorted(unknown)}")
+        custom = "temperature" in sampling_kwargs or "top_p" in sampling_kwargs
+        if custom:
+            _lib.check(self._engine.lib.svanon_ar_set_generate_sampling(
+                self._need_stream(), float(sampling_kwargs.get("temperature", 0.7)), float(sampling_kwargs.get("top_p", 0.7))))
         rc = ref_content_codes[0].to(torch.int64).contiguous()
         ra = ref_audio_codes[0].to(torch.int32).contiguous()
         sc = src_content_codes[0].to(torch.int64).contiguous()
@@ -209,9 +215,13 @@ class ARVCWrapper:
         noise = None
         if self._noise_fn is not None:
             noise = torch.stack([self._noise_for_step(self._step + i) for i in range(Ts)]).contiguous()
-        _lib.check(self._engine.lib.svanon_ar_generate(self._need_stream(), ptr(rc), ptr(ra), rc.numel(), ptr(sc), Ts,
-                                                       ptr(sv), ptr(tl), ptr(noise) if noise is not None else None,
-                                                       ptr(out), C.c_void_p(_cuda_stream_ptr())))
+        try:
+            _lib.check(self._engine.lib.svanon_ar_generate(self._need_stream(), ptr(rc), ptr(ra), rc.numel(), ptr(sc), Ts,
+                                                           ptr(sv), ptr(tl), ptr(noise) if noise is not None else None,
+                                                           ptr(out), C.c_void_p(_cuda_stream_ptr())))
+        finally:
+            if custom:
+                _lib.check(self._engine.lib.svanon_ar_set_generate_sampling(self._need_stream(), -1.0, -1.0))
         self._step += Ts
         return out[None]
 

@@ -193,6 +193,14 @@ int svanon_ar_set_sampling(svanon_stream* s, float temperature, float top_p, uin
   });
 }
 
+int svanon_ar_set_generate_sampling(svanon_stream* s, float temperature, float top_p) {
+  return guarded([&] {
+    SV_CHECK(s, "null stream");
+    SV_CHECK((temperature < 0.f && top_p < 0.f) || (temperature >= 0.f && top_p >= 0.f), "set both or clear both (negative)");
+    s->st.gen_temperature = temperature; s->st.gen_top_p = top_p;
+  });
+}
+
 int svanon_ar_prefill_prompt(svanon_stream* s, const int64_t* ref_content, const int32_t* ref_audio, int T,
                              const float* style, const float* timbre, void* stream) {
   return guarded([&] {
@@ -297,7 +305,14 @@ int svanon_ar_generate(svanon_stream* sh, const int64_t* ref_content, const int3
     launch_copy_rows(seq + (long long)(2 * n_pairs - 1) * AR_DIM, AR_DIM, s.x_audio, AR_DIM, 1, AR_DIM, st);
     e.ar_forward_tokens(s, x, n_pre, 0, st);
     s.pos_next = n_pre;
+    // per-call sampling arguments apply from the SECOND frame on: the reference's prefill call passes none
+    // (dual_ar_stream.py:723), the loop passes the caller's (:745-752)
+    struct Restore {
+      Stream& s; float t, p;
+      ~Restore() { s.temperature = t; s.top_p = p; }
+    } restore{s, s.temperature, s.top_p};
     for (int i = 0; i < Ts; ++i) {
+      if (i == 1 && s.gen_temperature >= 0.f) { s.temperature = s.gen_temperature; s.top_p = s.gen_top_p; }
       // remaining = [src_cond[d:], wait4end[:d]]  (dual_ar_stream.py:716)
       const int j = d + i;
       if (j < Ts) { s.step_content_id = sc + j; s.step_cond_row = nullptr; }

@@ -177,6 +177,7 @@ struct Stream {
   int max_seq = AR_MAX_SEQ;
   int delay = 0;
   float temperature = 0.7f, top_p = 0.7f;
+  float gen_temperature = -1.f, gen_top_p = -1.f;   // svanon_ar_set_generate_sampling: frames >= 1 of generate (< 0: unset)
   // ---- AR state (device)
   float *kc = nullptr, *vc = nullptr, *fkc = nullptr, *fvc = nullptr;
   float* x_audio = nullptr;        // [768]     cached_new_audio_emb

@@ -124,6 +124,22 @@ def test_ar_offline_generate(weights, gold, tape):
     assert np.array_equal(out.numpy(), g["codes"])
 
 
+def test_ar_offline_generate_with_sampling_kwargs(weights, gold, tape):
+    """`generate(..., temperature=0.9, top_p=0.85)` against the unmodified reference (tests/golden/ar_generate_kwargs.npz,
+    oracle/make_golden_generate_kwargs.py): the first frame is sampled with the DEFAULT arguments
+    (dual_ar_stream.py:723), the later ones with the caller's."""
+    g, s = gold("ar_generate_kwargs"), gold("ar_stream")
+    ar = DualAR(weights["ar"], tape(int(g["tape_seed"])))
+    style, timbre = synth.synth_speaker(int(s["spk_seed"]))
+    with torch.no_grad():
+        ar.set_delay(2)
+        out = ar.generate(torch.from_numpy(s["ref_content"]), torch.from_numpy(s["ref_audio"]),
+                          torch.from_numpy(s["src_content"])[:, : int(g["n_src"])], style, timbre,
+                          temperature=float(g["temperature"]), top_p=float(g["top_p"]))
+    assert np.array_equal(out.numpy(), g["codes"])
+    assert np.array_equal(out.numpy()[:, :, 0], gold("ar_generate")["codes"][:, :, 0])      # frame 0: defaults
+
+
 def _run_stream(weights, g, tape):
     so = StreamOracle(weights["ar"], weights["tok"], weights["voc_folded"], tape(int(g["tape_seed"])))
     n_ref, n_chunks = int(g["n_ref"]), int(g["n_chunks"])
