@@ -6,7 +6,9 @@ BASELINE configs 1 and 2 as a user runs them -- from .wav FILES, through the ref
 the reference's own five modules (seeded synthetic checkpoints):
 
   * `InferenceWrapper.infer(src_path, [ref_a, ref_b], delay=2, alpha=0.7, save_result=False)`
-    (evaluations/infer_arvc.py:261-380): offline conversion, two references, anonymisation mix;
+    (evaluations/infer_arvc.py:261-380): offline conversion, two references, anonymisation mix -- once with the default
+    "concat_mel" collation and once with "avg" (embeddings of each reference averaged, :282-307; unlike
+    `calculate_prompt`, `infer` implements that branch completely);
   * `InferenceWrapper.stream_infer(src_path, ref_a, ..., decode_chunk_frames=1, delay=2, save_result=False)`
     (:598-676): the streaming loop including its file loading and left padding to whole chunks (small windows so that
     the CPU run stays short and the re-prompt path fires).
@@ -59,10 +61,14 @@ def main():
         noise_style = torch.randn(1, 192)                            # the two draws infer just took, in order (:345-346)
         noise_timbre = torch.randn(1, 32, 128)
         tape.step = -1
+        torch.manual_seed(MIX_SEED)                                  # same draws: the shapes are the same
+        wave_avg = w.infer(str(tmp / "src.wav"), ref_paths, delay=2, alpha=ALPHA, spk_emb_collate_type="avg", save_result=False)
+        tape.step = -1
         stream_wave = w.stream_infer(str(tmp / "src.wav"), ref_paths[0], save_result=False, alpha=1.0, **STREAM_CFG)
     out = dict(weight_seed=WEIGHT_SEED, mix_seed=MIX_SEED, alpha=np.float32(ALPHA), tape_seed=7000, src_seed=SRC_SEED,
                src_seconds=SRC_SECONDS, ref_seeds=np.array(REF_SEEDS), ref_seconds=REF_SECONDS, noise_style=noise_style.numpy(),
                noise_timbre=noise_timbre.numpy(), wave=np.asarray(wave, dtype=np.float32),
+               wave_avg=np.asarray(wave_avg, dtype=np.float32),
                stream_wave=np.asarray(stream_wave, dtype=np.float32), stream_src_content=w.src_content_codes.numpy(),
                stream_pred_codes=w.pred_codes.numpy(), **{f"stream_{k}": np.array(v) for k, v in STREAM_CFG.items()})
     np.savez_compressed(GOLD / "infer_config1.npz", **out)

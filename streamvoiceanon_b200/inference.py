@@ -202,8 +202,8 @@ class InferenceWrapper:
         refs, crops = self.process_ref_paths(ref_path, ref_crop_lengths)
         ref_tensors = [self._load(r, c) for r, c in zip(refs, crops)]
         # same arithmetic and the same two noise draws as the reference's inlined copy of calculate_prompt (:280-346)
-        codes, content, style, timbre, _ = self.calculate_prompt(ref_tensors, alpha, spk_emb_collate_type,
-                                                                 noise_style=noise_style, noise_timbre=noise_timbre)
+        codes, content, style, timbre, _ = self._prompt.calculate_prompt(ref_tensors, alpha, spk_emb_collate_type, noise_style,
+                                                                         noise_timbre, allow_avg=True)
         src_content, _ = self.speech_tokenizer.encode(src, self.create_wave_lens_tensor(src))
         if delay is not None:
             self.model.set_delay(delay=delay)

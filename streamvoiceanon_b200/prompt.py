@@ -39,8 +39,10 @@ class PromptBuilder:
     svanon_resample (44.1 -> 16 kHz), svanon_style_vector, svanon_timbre_latent, svanon_noise_mix (style first, then
     timbre: the order of the reference's two `randn_like` draws, :419-421), svanon_voc_encode, svanon_enc_encode.
 
-    Only the "concat_mel" collation is offered: the reference's "avg" branch falls through to code that reads a
-    variable the branch never sets (:411-417) and cannot run with more than one reference."""
+    `calculate_prompt` offers the "concat_mel" collation only, like the reference in effect: its "avg" branch falls through
+    to code that reads a variable the branch never sets (:411-417) and cannot run with more than one reference.  The
+    reference's offline `infer` carries a complete copy of that branch (:282-307: embeddings of each reference on its own,
+    averaged; ids still from the concatenation) -- `allow_avg=True` is that copy."""
 
     def __init__(self, speech_tokenizer, firefly, style_encoder, timbre_encoder, sr: int = 44100, resample_freq: int = 16000):
         self.speech_tokenizer, self.firefly = speech_tokenizer, firefly
@@ -55,18 +57,30 @@ class PromptBuilder:
 
     @torch.no_grad()
     def calculate_prompt(self, ref_wav_tensors, alpha: float = 1.0, spk_emb_collate_type: str = "concat_mel",
-                         noise_style: torch.Tensor | None = None, noise_timbre: torch.Tensor | None = None):
+                         noise_style: torch.Tensor | None = None, noise_timbre: torch.Tensor | None = None,
+                         allow_avg: bool = False):
         from .speaker import calculate_style_vec, calculate_timbre_latent
         refs = list(ref_wav_tensors) if isinstance(ref_wav_tensors, (list, tuple)) else [ref_wav_tensors]
-        if spk_emb_collate_type == "avg" and len(refs) > 1:
+        avg = spk_emb_collate_type == "avg" and len(refs) > 1
+        if avg and not allow_avg:
             raise NotImplementedError('spk_emb_collate_type="avg" cannot run in the reference with more than one '
                                       "reference wave (evaluations/infer_arvc.py:411-417); use \"concat_mel\"")
         dev = torch.device("cuda", self.style_encoder._engine.device)
         ref = (torch.cat(refs, dim=-1) if len(refs) > 1 else refs[0]).to(dev, torch.float32)
-        ref16 = self._resample(ref)
-        lens16 = torch.LongTensor([ref16.shape[-1]])
-        style = calculate_style_vec(self.style_encoder, ref16, lens16)
-        timbre = calculate_timbre_latent(self.timbre_encoder, ref16, lens16)
+        if avg:
+            styles, timbres = [], []
+            for r in refs:
+                r16 = self._resample(r.to(dev, torch.float32))
+                l16 = torch.LongTensor([r16.shape[-1]])
+                styles.append(calculate_style_vec(self.style_encoder, r16, l16))
+                timbres.append(calculate_timbre_latent(self.timbre_encoder, r16, l16))
+            style = torch.mean(torch.stack(styles, dim=0), dim=0)
+            timbre = torch.mean(torch.stack(timbres, dim=0), dim=0)
+        else:
+            ref16 = self._resample(ref)
+            lens16 = torch.LongTensor([ref16.shape[-1]])
+            style = calculate_style_vec(self.style_encoder, ref16, lens16)
+            timbre = calculate_timbre_latent(self.timbre_encoder, ref16, lens16)
         style = apply_noise_mixing(style, alpha, noise_style)              # draws (if any) in the reference's order
         timbre = apply_noise_mixing(timbre, alpha, noise_timbre)
         lens = torch.LongTensor([ref.shape[-1]])

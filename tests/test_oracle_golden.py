@@ -5,6 +5,7 @@ only differences are operator fusion / summation order)."""
 import hashlib
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import content_encoder as E
@@ -320,11 +321,13 @@ def _infer_inputs(g):
     return src, refs
 
 
-def test_offline_infer_from_files_oracle_vs_reference(weights, gold, tape):
+@pytest.mark.parametrize("collate,key", [("concat_mel", "wave"), ("avg", "wave_avg")])
+def test_offline_infer_from_files_oracle_vs_reference(weights, gold, tape, collate, key):
     """BASELINE config 1 as a user runs it: the UNMODIFIED `InferenceWrapper.infer(src.wav, [ref_a.wav, ref_b.wav],
     delay=2, alpha=0.7)` (infer_arvc.py:261-380; tests/golden/infer_config1.npz, oracle/make_golden_infer.py) against the
     chained oracle: calculate_prompt (both speaker encoders, mix with the recorded draws, codec + content ids) ->
-    tokenizer on the source -> offline `generate` -> code2wav.  Waveform MSE < 1e-10 (ids are exact or it would not be)."""
+    tokenizer on the source -> offline `generate` -> code2wav, with both speaker-embedding collations ("avg": each
+    reference's embeddings on their own, averaged, :282-307).  Waveform MSE < 1e-10 (ids are exact or it would not be)."""
     from oracle import prompt as P
     from oracle import vocoder as V
     g = gold("infer_config1")
@@ -333,14 +336,14 @@ def test_offline_infer_from_files_oracle_vs_reference(weights, gold, tape):
     with torch.no_grad():
         codes, content, style, timbre, _ = P.calculate_prompt(
             refs, float(g["alpha"]), g["noise_style"], g["noise_timbre"], synth.make_campplus_state_dict(ws),
-            synth.make_timbre_encoder_state_dict(ws), weights["tok"], weights["voc_enc"])
+            synth.make_timbre_encoder_state_dict(ws), weights["tok"], weights["voc_enc"], collate=collate)
         src_content = E.encode(src, weights["tok"])[0].squeeze(0)
         ar = DualAR(weights["ar"], tape(int(g["tape_seed"])))
         ar.set_delay(2)
         vc = ar.generate(content, codes, src_content, style, timbre)
         wave = V.code2wav(vc.long(), weights["voc_folded"]).squeeze()
-    assert wave.shape == g["wave"].shape == (src.shape[1] // 2048 * 2048,)
-    assert float(((wave.numpy() - g["wave"]) ** 2).mean()) < 1e-10
+    assert wave.shape == g[key].shape == (src.shape[1] // 2048 * 2048,)
+    assert float(((wave.numpy() - g[key]) ** 2).mean()) < 1e-10
 
 
 def test_stream_infer_from_files_oracle_vs_reference(weights, gold, tape):

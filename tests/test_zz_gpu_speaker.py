@@ -221,6 +221,10 @@ def test_inference_wrapper_infer_and_stream_infer_vs_reference_files_run(encoder
                     noise_timbre=torch.from_numpy(g["noise_timbre"]))
     assert wave.shape == g["wave"].shape
     assert float(((wave - g["wave"]) ** 2).mean()) < 1e-8
+    iw.set_noise_fn(tape(int(g["tape_seed"])))                      # "avg": embeddings per reference, averaged (:282-307)
+    wave = iw.infer(src, refs, delay=2, alpha=float(g["alpha"]), spk_emb_collate_type="avg",
+                    noise_style=torch.from_numpy(g["noise_style"]), noise_timbre=torch.from_numpy(g["noise_timbre"]))
+    assert float(((wave - g["wave_avg"]) ** 2).mean()) < 1e-8
     cfg = {k: int(g[f"stream_{k}"]) for k in ("encode_window_frames", "decode_window_frames", "max_prompt_frames",
                                               "max_seq_frames", "buffer_frames", "decode_chunk_frames", "delay")}
     iw.set_noise_fn(tape(int(g["tape_seed"])))
