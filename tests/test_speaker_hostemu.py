@@ -173,3 +173,23 @@ def test_tensor_core_product_arithmetic_keeps_the_embeddings(emu, gold, monkeypa
     out, idx, _ = _timbre(emu, a)
     assert np.array_equal(idx.numpy(), gt["indices_a"][0, 0])
     assert np.abs(out.numpy() - gt["timbre_a"][0]).max() < 1e-5
+
+
+def test_derived_buffers_are_torchaudios():
+    """The four buffers the shim uploads next to the checkpoints are the ones torchaudio builds for the reference:
+    kaldi mel banks + povey window (torchaudio.compliance.kaldi), slaney filterbank + the window torch.stft pads to n_fft."""
+    import torchaudio
+    from torchaudio.compliance import kaldi
+    from streamvoiceanon_b200 import speaker as SP
+    banks, _ = kaldi.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+    mine = SP.kaldi_mel_banks()
+    assert tuple(mine.shape) == (80, 257) and torch.equal(mine[:, :256], banks) and float(mine[:, 256].abs().max()) == 0.0
+    povey = kaldi._feature_window_function("povey", 400, 0.42, torch.device("cpu"), torch.float32)
+    assert torch.equal(SP.povey_window(), povey)
+    fb = torchaudio.functional.melscale_fbanks(513, 10.0, 8000.0, 128, 16000, norm="slaney", mel_scale="slaney")
+    assert torch.equal(SP.timbre_derived_buffers()["mel.fb"], fb)
+    # torch.stft centres a short window in the frame: spectrum of one frame with the padded window == torch.stft's
+    x = torch.randn(1024)
+    want = torch.stft(x, 1024, hop_length=320, win_length=640, window=torch.hann_window(640), center=False, return_complex=True)[:, 0]
+    got = torch.fft.rfft(x * SP.centred_hann())
+    assert float((got - want).abs().max()) < 1e-4
