@@ -61,6 +61,27 @@ def parse():
     return ap.parse_args()
 
 
+def cpu_prompt_path(threads: int):
+    """CPU side of the prompt_path leg: the oracle's `calculate_prompt` (oracle/prompt.py: resample, both speaker encoders,
+    noise mix, codec ids, content ids; torch fp32) on the same 5 s of synthetic reference audio, host threads as given."""
+    import numpy as np
+    from oracle import prompt as P
+    from streamvoiceanon_b200 import synth
+    torch.set_num_threads(threads)
+    ref = synth.synth_audio_44k(5000, 5.0)[None]
+    sds = (synth.make_campplus_state_dict(1234), synth.make_timbre_encoder_state_dict(1234), synth.make_tokenizer_state_dict(1234),
+           synth.make_vocoder_encoder_state_dict(1234))
+    z1, z2 = np.zeros((1, 192), np.float32), np.zeros((1, 32, 128), np.float32)
+    ms = []
+    with torch.no_grad():
+        for _ in range(3):
+            t0 = time.perf_counter()
+            P.calculate_prompt([ref], 0.7, z1, z2, *sds)
+            ms.append((time.perf_counter() - t0) * 1e3)
+    return {"ms": sorted(ms)[1], "cores": threads, "kind": "port",
+            "sample": "oracle/prompt.py calculate_prompt, 5 s of reference audio, median of 3 calls, torch fp32"}
+
+
 def prompt_path_leg(timeout_s: int = 150):
     """Setup path beside the headline (never inside it): `PromptBuilder.calculate_prompt` on 5 s of reference audio --
     resample, both speaker encoders, noise mix, codec ids, content ids -- per step, CUDA-event ms and kernel launches,
@@ -448,6 +469,11 @@ def run_engine(args):
                                 "ms_per_step": mean_ms, "stage_ms_median": cstage}
     if world == 1 and not args.no_prompt_path:
         line["prompt_path"] = prompt_path_leg()
+        if not args.no_cpu_baseline:
+            try:
+                line["prompt_path"]["cpu_baseline"] = cpu_prompt_path(os.cpu_count() or 1)
+            except Exception as exc:
+                line["prompt_path"]["cpu_baseline"] = {"unavailable": repr(exc)[:300]}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
