@@ -130,6 +130,15 @@ int svanon_set_gemm_mode(int mode);
 int svanon_set_pdl(int enable);
 int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N,
                       int K, int act, void* cuda_stream);
+
+/* test hook: the general form of the GEMM contract the conv layers use (common.cuh GemmParams) --
+ *   C[m][c_col0 + n] = bias[n] + sum_t sum_k A[(a_row0 + m * a_row_step + tap_off[t]) * lda + k] * W[t][n][k]
+ * A [a_rows][lda] (rows may overlap: lda < K), W [taps][N][K], C [M][ldc]; device pointers only.  Lets a test hold any
+ * single descriptor (row-offset taps of either sign, strided rows, column slices) to an fp64 product. */
+int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda, int a_row0, int a_row_step, const float* W,
+                           int taps, const int* tap_off, const float* bias, float* C, int ldc, int c_col0, int M, int N,
+                           int K, void* cuda_stream);
+
 /* batch-1 decode kernel variant: 1 (default) = weights staged through shared memory with TMA bulk copies, grid
  * barriers between phases; 2 = staged weights + activations exchanged between CTAs as self-validating {value, tag}
  * words instead of barriers (experimental: correct, but measured slower -- polling congestion, profiles/README.md);

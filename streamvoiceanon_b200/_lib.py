@@ -46,6 +46,8 @@ _SIGS = {
     "svanon_set_gemm_mode": (C.c_int, [C.c_int]),
     "svanon_set_pdl": (C.c_int, [C.c_int]),
     "svanon_debug_gemm": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "svanon_debug_gemm_taps": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, C.POINTER(C.c_int), _p, _p, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "svanon_ar_set_kernel_variant": (C.c_int, [_p, C.c_int]),
     "svanon_ar_set_barrier_mode": (C.c_int, [_p, C.c_int]),
     "svanon_ar_profile": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint64)]),

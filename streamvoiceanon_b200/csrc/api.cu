@@ -367,6 +367,26 @@ int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const fl
   });
 }
 
+int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda, int a_row0, int a_row_step, const float* W,
+                           int taps, const int* tap_off, const float* bias, float* C, int ldc, int c_col0, int M, int N, int K,
+                           void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && A && W && C && tap_off && M > 0 && N > 0 && K > 0 && taps >= 1 && taps <= MAX_TAPS, "bad arguments");
+    SV_CHECK(on_device(A) && on_device(W) && on_device(C) && (!bias || on_device(bias)), "device pointers only");
+    SV_CHECK(a_row_step >= 1 && c_col0 >= 0 && c_col0 + N <= ldc, "bad layout");
+    for (int t = 0; t < taps; ++t) {
+      const long long lo = (long long)a_row0 + tap_off[t], hi = (long long)a_row0 + (long long)(M - 1) * a_row_step + tap_off[t];
+      SV_CHECK(lo >= 0 && hi * lda + K <= (long long)a_rows * lda, "a tap reads outside the A buffer");
+    }
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    GemmParams p;
+    p.A = A + (long long)a_row0 * lda; p.W = W; p.bias = bias; p.C = C + c_col0;
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.a_row_step = a_row_step; p.taps = taps;
+    for (int t = 0; t < taps; ++t) p.tap_off[t] = tap_off[t];
+    launch_gemm(p, (cudaStream_t)stream);
+  });
+}
+
 int svanon_ar_set_kernel_variant(svanon_engine* e, int variant) {
   return guarded([&] {
     SV_CHECK(e, "null engine");

@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 T=r3a
 # 1. the unrun parity tests (non-gating markers: read the XPASS / XFAIL lines)
-timeout 600 python -m pytest tests/test_zz_gpu_speaker.py tests/test_zz_gpu_generate_kwargs.py -q -rxXs \
+timeout 600 python -m pytest tests/test_zz_gpu_gemm_descriptors.py tests/test_zz_gpu_speaker.py tests/test_zz_gpu_generate_kwargs.py -q -rxXs \
   > gpurun_out/${T}_unrun_tests.log 2>&1
 echo "unrun tests rc=$?" >> gpurun_out/${T}_unrun_tests.log
 # 2. setup-path timing per step (resample, style, timbre, mix, codec ids, content ids, whole calculate_prompt)
