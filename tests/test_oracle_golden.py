@@ -371,3 +371,22 @@ def test_stream_infer_from_files_oracle_vs_reference(weights, gold, tape):
     assert np.array_equal(so.src_content_codes.numpy(), g["stream_src_content"])
     assert np.array_equal(so.pred_codes.numpy(), g["stream_pred_codes"])
     assert float(((wave[0].numpy() - g["stream_wave"]) ** 2).mean()) < 1e-10
+
+
+def test_speaker_encoders_full_size_oracle_vs_reference(gold):
+    """Both speaker encoders at BASELINE config 5's full size (15 s = three 5 s references: 1498 fbank frames, 8 CAM
+    segments, 751 mel frames) against the unmodified reference (tests/golden/speaker_full_15s.npz,
+    oracle/make_golden_speaker_full.py)."""
+    from oracle import speaker as S
+    g = gold("speaker_full_15s")
+    ws = int(g["weight_seed"])
+    wave = torch.cat([synth.synth_audio_16k(int(s), float(g["seconds"])) for s in g["seeds"]])[None]
+    lens = torch.LongTensor([wave.shape[1]])
+    with torch.no_grad():
+        style = S.calculate_style_vec(wave, lens, synth.make_campplus_state_dict(ws))
+        zq, idx, bounded = S.calculate_timbre_latent(wave, lens, synth.make_timbre_encoder_state_dict(ws))
+    assert np.abs(style.numpy() - g["style"]).max() < 1e-5
+    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+    assert safe.mean() > 0.9
+    assert np.array_equal(idx.numpy()[safe], g["indices"][:, 0][safe])
+    assert np.abs(zq.numpy() - g["timbre"])[safe].max() < 1e-5

@@ -193,3 +193,18 @@ def test_derived_buffers_are_torchaudios():
     want = torch.stft(x, 1024, hop_length=320, win_length=640, window=torch.hann_window(640), center=False, return_complex=True)[:, 0]
     got = torch.fft.rfft(x * SP.centred_hann())
     assert float((got - want).abs().max()) < 1e-4
+
+
+def test_full_size_15s_host_orchestration_vs_reference(emu, gold):
+    """BASELINE config 5's full prompt size (15 s: 1498 fbank frames, 749 TDNN rows in 8 CAM segments, 751 mel frames)
+    against the unmodified reference (tests/golden/speaker_full_15s.npz)."""
+    from oracle import speaker as S
+    g = gold("speaker_full_15s")
+    wave = torch.cat([synth.synth_audio_16k(int(s), float(g["seconds"])) for s in g["seeds"]]).contiguous()
+    assert np.abs(_style(emu, wave).numpy() - g["style"][0]).max() < 1e-4
+    out, idx, z = _timbre(emu, wave)
+    _, _, bounded = S.fsq4_quantize(z)
+    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+    assert safe.mean() > 0.9
+    assert np.array_equal(idx.numpy()[safe], g["indices"][0, 0][safe])
+    assert np.abs(out.numpy() - g["timbre"][0])[safe].max() < 1e-4

@@ -232,3 +232,24 @@ def test_inference_wrapper_infer_and_stream_infer_vs_reference_files_run(encoder
     assert np.array_equal(iw.src_content_codes.numpy(), g["stream_src_content"])
     assert np.array_equal(iw.pred_codes.numpy(), g["stream_pred_codes"])
     assert float(((stream_wave - g["stream_wave"]) ** 2).mean()) < 1e-8
+
+
+def test_speaker_encoders_full_size_vs_reference(encoders, gold):
+    """BASELINE config 5's full prompt size: 15 s of reference audio (1498 fbank frames, 8 CAM segments, 751 mel frames)
+    against the unmodified reference (tests/golden/speaker_full_15s.npz, oracle/make_golden_speaker_full.py)."""
+    from oracle import speaker as S
+    from streamvoiceanon_b200.speaker import calculate_style_vec, calculate_timbre_latent
+    style, timbre = encoders
+    g = gold("speaker_full_15s")
+    wave = torch.cat([synth.synth_audio_16k(int(s), float(g["seconds"])) for s in g["seeds"]])[None]
+    lens = torch.LongTensor([wave.shape[1]])
+    sv = calculate_style_vec(style, wave.cuda(), lens)
+    assert np.abs(sv.cpu().numpy() - g["style"]).max() < STYLE_TOL
+    zq, idx = timbre.tokenize_wav(wave.cuda(), lens)
+    with torch.no_grad():
+        _, _, bounded = S.calculate_timbre_latent(wave, lens, synth.make_timbre_encoder_state_dict(int(g["weight_seed"])))
+    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+    assert safe.mean() > 0.9
+    assert np.array_equal(idx.cpu().numpy()[:, 0][safe], g["indices"][:, 0][safe])
+    assert np.abs(zq.mT.cpu().numpy() - g["timbre"])[safe].max() < TIMBRE_TOL
+    assert calculate_timbre_latent(timbre, wave.cuda(), lens).shape == (1, 32, 128)
