@@ -27,7 +27,8 @@ container: `oracle/make_golden.py` imports /root/reference (through the import s
 `tests/golden/*.npz` (`make_golden_vocenc.py`, `make_golden_noise_mix.py`, `make_golden_style.py`,
 `make_golden_prompt.py` do the same for the prompt path, up to the unmodified
 `prefill_prompt` + `process_one_chunk` of BASELINE config 5; `make_golden_infer.py` runs the
-unmodified `infer()` and `stream_infer()` from .wav files: configs 1 and 2); `tests/test_oracle_golden.py`
+unmodified `infer()` and `stream_infer()` from .wav files: configs 1 and 2; `make_golden_speaker_full.py` the speaker
+encoders on 15 s; `make_golden_generate_kwargs.py` `generate` with sampling arguments); `tests/test_oracle_golden.py`
 checks the oracle against those fixtures on every CPU run.  The third-party FSQ arithmetic
 (`vector-quantize-pytorch==1.14.24`, reference requirements.txt:26) is not vendored as a
 package; it is pinned through the reference's own vendored twin
