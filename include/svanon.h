@@ -116,6 +116,17 @@ int svanon_ar_generate(svanon_stream* s, const int64_t* ref_content, const int32
  * svanon_ar_set_sampling's).  `repetition_penalty` has no effect in the reference (previous_tokens is always None). */
 int svanon_ar_set_generate_sampling(svanon_stream* s, float temperature, float top_p);
 
+/* BASELINE config 3 (batched offline conversion; the reference runs its utterances one `generate` after the other, batch
+ * size 1: evaluations/infer_arvc.py:56,350-357): `generate` for n utterances with ONE pass over the weights per frame.
+ * Every utterance has its own stream (same delay and max_seq_len), prompt, length and noise tape; utterance k produces
+ * exactly what svanon_ar_generate produces for it alone.  Arrays of n DEVICE pointers: ref_content[k] [Tr[k]],
+ * ref_audio[k] [8][Tr[k]] int32, src_content[k] [Ts[k]], style[k] [192], timbre[k] [32][128], noise NULL or noise[k] NULL or
+ * [Ts[k]][8][1000], codes_out[k] [8][Ts[k]] int32.  Shorter utterances leave the lock-step batch when they are done. */
+int svanon_ar_generate_many(svanon_stream* const* streams, int n, const int64_t* const* ref_content,
+                            const int32_t* const* ref_audio, const int* Tr, const int64_t* const* src_content, const int* Ts,
+                            const float* const* style, const float* const* timbre, const float* const* noise,
+                            int32_t* const* codes_out, void* cuda_stream);
+
 int svanon_ar_position(const svanon_stream* s); /* next free sequence position */
 /* test hook: capture the logits of the next decode steps (slow 8192-way head, pre-norm hidden state, 8 fast
  * heads) of stream 0 of each launch; read them back with svanon_ar_read_debug (host pointers, may be NULL) */

@@ -36,6 +36,8 @@ _SIGS = {
     "svanon_ar_set_delay": (C.c_int, [_p, C.c_int]),
     "svanon_ar_set_sampling": (C.c_int, [_p, C.c_float, C.c_float, C.c_uint64]),
     "svanon_ar_set_generate_sampling": (C.c_int, [_p, C.c_float, C.c_float]),
+    "svanon_ar_generate_many": (C.c_int, [C.POINTER(_p), C.c_int, C.POINTER(_p), C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(_p),
+                                         C.POINTER(C.c_int), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _p]),
     "svanon_ar_prefill_prompt": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, _p]),
     "svanon_ar_prefill_delay": (C.c_int, [_p, _p, C.c_int, _p]),
     "svanon_ar_decode_one": (C.c_int, [_p, _p, _p, _p, C.POINTER(C.c_int32), _p]),

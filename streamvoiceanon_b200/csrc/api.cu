@@ -327,6 +327,101 @@ int svanon_ar_generate(svanon_stream* sh, const int64_t* ref_content, const int3
   });
 }
 
+namespace {
+// Prompt part of offline generate for one utterance: the token sequence of svanon_ar_generate above (33 speaker rows,
+// (cond_t, audio'_t) pairs for t < Tr + d, then the first remaining condition) up to, not including, the first decode
+// step.  Kept separate from svanon_ar_generate until this path has run on a GPU; the two are meant to share it.
+void generate_prefill(Engine& e, Stream& s, const long long* rc, const int* ra, int Tr, const long long* sc, int Ts,
+                      const float* sv, const float* tl, cudaStream_t st) {
+  const int d = s.delay;
+  const int n_pairs = Tr + d;
+  const int n_tok = AR_SPK_TOKENS + 2 * n_pairs + 1;
+  SV_CHECK(n_tok + 2 * (Ts - 1) <= s.max_seq, "utterance does not fit the KV cache (max_seq_len)");
+  e.ws.ensure(((size_t)(n_tok + 8) * 12000 + (1u << 20)) * sizeof(float));
+  e.ws.reset();
+  float* x = e.ws.alloc_f((long long)(n_tok + 2) * AR_DIM);
+  GemmParams p;
+  p.A = tl; p.W = e.ctx_w; p.C = x; p.bias = e.ctx_b; p.M = 32; p.N = AR_DIM; p.K = 128; p.lda = 128; p.ldc = AR_DIM;
+  launch_gemm(p, st);
+  GemmParams q;
+  q.A = sv; q.W = e.style_w; q.C = x + 32 * AR_DIM; q.bias = e.style_b; q.M = 1; q.N = AR_DIM; q.K = 192; q.lda = 192;
+  q.ldc = AR_DIM;
+  launch_gemm(q, st);
+  float* seq = x + AR_SPK_TOKENS * AR_DIM;
+  launch_gather_rows(e.ar.cond_emb, rc, seq, Tr, AR_DIM, 2 * AR_DIM, st);
+  if (d > 0) {
+    launch_gather_rows(e.ar.cond_emb, sc, seq + (long long)2 * Tr * AR_DIM, d, AR_DIM, 2 * AR_DIM, st);
+    launch_copy_rows(e.w4s, AR_DIM, seq + AR_DIM, 2 * AR_DIM, d, AR_DIM, st);
+  }
+  launch_embed_codes(e.ar.codebook_emb, ra, Tr, seq + (long long)(2 * d + 1) * AR_DIM, Tr, 2 * AR_DIM, st);
+  const int n_pre = n_tok - 2;
+  launch_copy_rows(seq + (long long)(2 * n_pairs - 1) * AR_DIM, AR_DIM, s.x_audio, AR_DIM, 1, AR_DIM, st);
+  e.ar_forward_tokens(s, x, n_pre, 0, st);
+  s.pos_next = n_pre;
+}
+}  // namespace
+
+int svanon_ar_generate_many(svanon_stream* const* streams, int n, const int64_t* const* ref_content,
+                            const int32_t* const* ref_audio, const int* Tr, const int64_t* const* src_content, const int* Ts,
+                            const float* const* style, const float* const* timbre, const float* const* noise,
+                            int32_t* const* codes_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(streams && n >= 1 && ref_content && ref_audio && Tr && src_content && Ts && style && timbre && codes_out,
+             "null argument");
+    svanon_engine* h = streams[0] ? streams[0]->owner : nullptr;
+    SV_CHECK(h, "null stream");
+    SV_CUDA(cudaSetDevice(h->eng.device));
+    Engine& e = h->eng;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<Stream*> ss(n);
+    int max_ts = 0;
+    for (int k = 0; k < n; ++k) {
+      SV_CHECK(streams[k] && streams[k]->owner == h, "streams must belong to one engine");
+      for (int j = 0; j < k; ++j) SV_CHECK(streams[j] != streams[k], "a stream may appear only once in a call");
+      SV_CHECK(ref_content[k] && ref_audio[k] && src_content[k] && style[k] && timbre[k] && codes_out[k], "null utterance buffer");
+      SV_CHECK(on_device(ref_content[k]) && on_device(ref_audio[k]) && on_device(src_content[k]) && on_device(style[k]) &&
+                   on_device(timbre[k]) && on_device(codes_out[k]) && (!noise || !noise[k] || on_device(noise[k])),
+               "per-utterance buffers must be device pointers");
+      Stream& s = streams[k]->st;
+      SV_CHECK(s.delay == streams[0]->st.delay && s.max_seq == streams[0]->st.max_seq, "utterances of one call share delay and max_seq_len");
+      SV_CHECK(Tr[k] >= 1 && Ts[k] >= 1 && Ts[k] >= s.delay && Ts[k] <= HIST_CAP, "generate needs Tr >= 1 and delay <= Ts <= 4096");
+      ss[k] = &s;
+      max_ts = std::max(max_ts, Ts[k]);
+    }
+    for (int k = 0; k < n; ++k)
+      generate_prefill(e, *ss[k], (const long long*)ref_content[k], ref_audio[k], Tr[k], (const long long*)src_content[k], Ts[k],
+                       style[k], timbre[k], st);
+    const int d = ss[0]->delay;
+    std::vector<Stream*> active;
+    active.reserve(n);
+    for (int i = 0; i < max_ts; ++i) {
+      active.clear();
+      for (int k = 0; k < n; ++k) {
+        if (i >= Ts[k]) continue;                     // shorter utterances leave the lock-step batch when they are done
+        Stream& s = *ss[k];
+        const long long* sc = (const long long*)src_content[k];
+        const int j = d + i;                          // remaining = [src_cond[d:], wait4end[:d]]  (dual_ar_stream.py:716)
+        if (j < Ts[k]) { s.step_content_id = sc + j; s.step_cond_row = nullptr; }
+        else { s.step_content_id = nullptr; s.step_cond_row = e.w4e + (long long)(j - Ts[k]) * AR_DIM; }
+        s.step_noise = (noise && noise[k]) ? noise[k] + (size_t)i * 8 * AR_CB_SIZE : nullptr;
+        s.step_pred_hist = s.pred_hist;               // the step writes its 8 codes into column i of the history
+        s.step_pred_col = i;
+        active.push_back(&s);
+      }
+      e.ar_decode_step_gemm(active.data(), (int)active.size(), st);
+    }
+    for (int k = 0; k < n; ++k) {
+      Stream& s = *ss[k];
+      SV_CUDA(cudaMemcpy2DAsync(codes_out[k], (size_t)Ts[k] * sizeof(int), s.pred_hist, (size_t)HIST_CAP * sizeof(int),
+                                (size_t)Ts[k] * sizeof(int), 8, cudaMemcpyDeviceToDevice, st));
+      s.step_pred_hist = nullptr;
+      s.step_content_id = nullptr;
+      s.step_cond_row = nullptr;
+      s.step_noise = nullptr;
+    }
+  });
+}
+
 int svanon_ar_position(const svanon_stream* s) { return s ? s->st.pos_next : -1; }
 
 int svanon_ar_debug_logits(svanon_engine* e, int enable) {

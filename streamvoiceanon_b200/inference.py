@@ -212,3 +212,69 @@ class InferenceWrapper:
         vc_codes = self.model.generate(ref_content_codes=content, ref_audio_codes=codes, src_content_codes=src_content.squeeze(0),
                                        style_vectors=style, timbre_latents=timbre, **sampling_kwargs)
         return self.code2wav_fn(vc_codes.long()).squeeze().cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------ offline, many utterances
+    @torch.no_grad()
+    def infer_batch(self, src_paths: Sequence[Wave], ref_paths: Sequence[Union[Wave, Sequence[Wave]]], delay: int = 2,
+                    alpha: float = 1.0, spk_emb_collate_type: str = "concat_mel", noise_fns: Optional[Sequence[Callable]] = None,
+                    noises_style=None, noises_timbre=None):
+        """BASELINE config 3: `infer` for many (source, reference) pairs at once.  The reference is batch-1 and would call
+        `infer` once per pair (evaluations/infer_arvc.py:56,261-380); here the prompts are built per pair, and the
+        autoregressive decode of ALL pairs advances in lock-step with one pass over the weights per frame
+        (svanon_ar_generate_many; pairs of different length leave the batch as they finish).  Pair k yields exactly what
+        `infer(src_paths[k], ref_paths[k], delay=delay, alpha=alpha)` yields.  Returns a list of waveforms (np.ndarray).
+
+        `noise_fns[k]` (tests): sampling-noise tape of pair k; `noises_style[k]` / `noises_timbre[k]`: recorded draws of
+        the anonymisation mix (default: torch's global generator, style then timbre, pair after pair)."""
+        import ctypes as C
+        from . import _lib
+        from .engine import ptr, _cuda_stream_ptr
+        n = len(src_paths)
+        if n == 0 or len(ref_paths) != n:
+            raise ValueError("one reference (or list of references) per source")
+        eng = self.model._engine
+        lib = eng.lib
+        keep, streams = [], []
+        rc_p, ra_p, sc_p, sv_p, tl_p, nz_p, out_p = ([] for _ in range(7))
+        Tr, Ts, outs = [], [], []
+        try:
+            for k in range(n):
+                src = self._load(src_paths[k])
+                refs, crops = self.process_ref_paths(ref_paths[k], None)
+                ref_tensors = [self._load(r, c) for r, c in zip(refs, crops)]
+                codes, content, style, timbre, _ = self._prompt.calculate_prompt(
+                    ref_tensors, alpha, spk_emb_collate_type, None if noises_style is None else noises_style[k],
+                    None if noises_timbre is None else noises_timbre[k], allow_avg=True)
+                src_content, _ = self.speech_tokenizer.encode(src, self.create_wave_lens_tensor(src))
+                rc = content.reshape(-1).to(self.device, torch.int64).contiguous()
+                ra = codes.reshape(8, -1).to(self.device, torch.int32).contiguous()
+                sc = src_content.reshape(-1).to(self.device, torch.int64).contiguous()
+                sv = style.reshape(-1).to(self.device, torch.float32).contiguous()
+                tl = timbre.reshape(32, 128).to(self.device, torch.float32).contiguous()
+                out = torch.empty(8, sc.numel(), dtype=torch.int32, device=self.device)
+                noise = None
+                if noise_fns is not None and noise_fns[k] is not None:
+                    noise = torch.stack([torch.stack([noise_fns[k](i, s, 1000)[:1000] for s in range(1, 9)])
+                                         for i in range(sc.numel())]).float().contiguous().to(self.device)
+                h = C.c_void_p()
+                _lib.check(lib.svanon_stream_create(eng.handle, getattr(self.model, "_max_seq_len", 2048), C.byref(h)))
+                streams.append(h)
+                _lib.check(lib.svanon_ar_set_delay(h, int(delay)))
+                keep += [rc, ra, sc, sv, tl, out, noise]
+                for lst, t in ((rc_p, rc), (ra_p, ra), (sc_p, sc), (sv_p, sv), (tl_p, tl), (out_p, out)):
+                    lst.append(t.data_ptr())
+                nz_p.append(noise.data_ptr() if noise is not None else None)
+                Tr.append(rc.numel())
+                Ts.append(sc.numel())
+                outs.append(out)
+            arr = lambda ps: (C.c_void_p * n)(*ps)                                       # noqa: E731
+            ints = lambda v: (C.c_int * n)(*v)                                           # noqa: E731
+            _lib.check(lib.svanon_ar_generate_many(arr([s.value for s in streams]), n, arr(rc_p), arr(ra_p), ints(Tr), arr(sc_p),
+                                                   ints(Ts), arr(sv_p), arr(tl_p), arr(nz_p), arr(out_p),
+                                                   C.c_void_p(_cuda_stream_ptr())))
+            waves = [self.code2wav_fn(o[None].long()).squeeze().cpu().numpy() for o in outs]
+        finally:
+            for h in streams:
+                lib.svanon_stream_destroy(h)
+        del keep
+        return waves

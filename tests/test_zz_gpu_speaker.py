@@ -253,3 +253,21 @@ def test_speaker_encoders_full_size_vs_reference(encoders, gold):
     assert np.array_equal(idx.cpu().numpy()[:, 0][safe], g["indices"][:, 0][safe])
     assert np.abs(zq.mT.cpu().numpy() - g["timbre"])[safe].max() < TIMBRE_TOL
     assert calculate_timbre_latent(timbre, wave.cuda(), lens).shape == (1, 32, 128)
+
+
+def test_infer_batch_equals_sequential_infer(encoders, models, tape):
+    """BASELINE config 3 (batched offline conversion): `infer_batch` over three (source, reference) pairs of different
+    lengths -- lock-step decode through svanon_ar_generate_many, shorter utterances leaving the batch as they finish --
+    against three sequential `infer` calls, which is what the batch-1 reference does.  Bit-identical waveforms."""
+    iw = _wrapper(encoders, models)
+    srcs = [synth.synth_audio_44k(1500 + k, 0.5 + 0.15 * k)[: (9 + 3 * k) * 2048 + 17 * k] for k in range(3)]
+    refs = [synth.synth_audio_44k(5600 + k, 1.0 + 0.2 * k) for k in range(3)]
+    fns = [tape(7300 + k) for k in range(3)]
+    got = iw.infer_batch(srcs, refs, delay=2, alpha=1.0, noise_fns=fns)
+    assert [w.shape[0] for w in got] == [(9 + 3 * k) * 2048 for k in range(3)]
+    for k in range(3):
+        iw.set_noise_fn(fns[k])
+        want = iw.infer(srcs[k], refs[k], delay=2, alpha=1.0)
+        assert np.array_equal(got[k], want), k
+    with pytest.raises(ValueError):
+        iw.infer_batch(srcs, refs[:2])
