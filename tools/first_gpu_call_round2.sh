@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # First GPU call of the next round (NEXT.md section 0): everything that was written after round 1's GPU minutes ran out,
 # in one gpurun call, results under gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash tools/first_gpu_call_round2.sh'
+#   gpurun --timeout 2400 -- 'bash tools/first_gpu_call_round2.sh'
 set -u
 mkdir -p gpurun_out
 T=r3a
@@ -14,7 +14,7 @@ timeout 300 python tools/bench_prompt.py 5 15 > gpurun_out/${T}_prompt.jsonl 2> 
 # 3. host issue time vs device time of the single-stream loop (graphs or persistent kernels?)
 timeout 200 python tools/bench_launch_overhead.py 200 > gpurun_out/${T}_launch_overhead.json 2> gpurun_out/${T}_launch_overhead.err
 # 3a. the user-facing path from state dicts: InferenceWrapper.from_state_dicts -> stream_infer (config 5 shape) -> infer
-timeout 300 python tools/demo_stream_infer.py 2 0.7 > gpurun_out/${T}_demo.json gpurun_out/${T}_offline_batch.json 2> gpurun_out/${T}_demo.err
+timeout 300 python tools/demo_stream_infer.py 2 0.7 > gpurun_out/${T}_demo.json 2> gpurun_out/${T}_demo.err
 # 3b. BASELINE config 3: 64 offline conversions in lock-step vs sequential infer
 timeout 400 python tools/bench_offline_batch.py 64 4 > gpurun_out/${T}_offline_batch.json 2> gpurun_out/${T}_offline_batch.err
 # 4. the gating suite and the bench line with the new library
