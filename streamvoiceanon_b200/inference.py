@@ -65,6 +65,39 @@ class InferenceWrapper:
         timbre.load_state_dict(timbre_sd, strict=False)
         return cls(model, tok, voc, style, timbre, device=device)
 
+    @classmethod
+    def from_config(cls, config_path, checkpoint_path, compile_encoder=False, compile_decoder=False, compile_ar=False,
+                    fp16=False, root=None):
+        """The reference's constructor (`InferenceWrapper(config_path, checkpoint_path, compile_*=...)`,
+        evaluations/infer_arvc.py:33-126; `load_models` of real-time-gui.py:52-57): reads the top-level YAML, loads the AR
+        checkpoint and the four helper checkpoints it names (`speech_tokenizer` / `firefly` / `style_encoder` /
+        `timbre_encoder` -> `checkpoint_path`; the tokenizer may be wrapped in {'net': ...} with a 'module.' prefix,
+        :73-78) and builds the engine's shims from them.  The `compile_*` / `fp16` switches are accepted and have nothing
+        to do: the decode step already is one kernel, encode / head are library calls, the parity build is fp32.
+        Relative paths resolve against `root` (default: the working directory, like the reference CLI)."""
+        import yaml
+        base = Path(root) if root is not None else Path.cwd()
+
+        def resolve(p):
+            p = Path(p)
+            return p if p.is_absolute() else base / p
+
+        config = yaml.safe_load(open(resolve(config_path)))
+
+        def ckpt(section):
+            return torch.load(resolve(config[section]["checkpoint_path"]), map_location="cpu")
+
+        tok_sd = ckpt("speech_tokenizer")
+        if "net" in tok_sd:
+            tok_sd = tok_sd["net"]
+        tok_sd = {k[7:] if k.startswith("module.") else k: v for k, v in tok_sd.items()}
+        iw = cls.from_state_dicts(torch.load(resolve(checkpoint_path), map_location="cpu"), tok_sd, ckpt("firefly"),
+                                  ckpt("style_encoder"), ckpt("timbre_encoder"))
+        iw.config = config
+        iw.sr = config["preprocess_params"]["sr"]
+        iw._prompt = PromptBuilder(iw.speech_tokenizer, iw.firefly, iw.style_encoder, iw.timbre_encoder, iw.sr, cls.RESAMPLE_FREQ)
+        return iw
+
     # ------------------------------------------------------------------------------------------ helpers
     def set_noise_fn(self, fn: Optional[Callable]):
         """Sampling-noise tape `fn(step, slot, V)` shared with the oracle (tests); None: the library's own generator."""

@@ -88,3 +88,32 @@ def test_process_one_chunk_checks_the_chunk_length():
     assert tuple(iw.process_one_chunk(torch.ones(1, 4096)).shape) == (1, 4096)
     with pytest.raises(ValueError):
         iw.process_one_chunk(torch.ones(1, 2048))
+
+
+def test_from_config_reads_the_reference_layout(tmp_path, monkeypatch):
+    """`from_config` follows the reference constructor (infer_arvc.py:33-126): five checkpoints named by the top-level
+    YAML, tokenizer unwrapped from {'net': ...} / 'module.', relative paths against the root, sr from preprocess_params."""
+    import yaml
+    (tmp_path / "ckpt").mkdir()
+    names = {"speech_tokenizer": "tok.pth", "firefly": "voc.pth", "style_encoder": "style.bin", "timbre_encoder": "timbre.pth"}
+    cfg = {"preprocess_params": {"sr": 44100}, "model_params": {"config_path": "unused.yaml"}}
+    for section, f in names.items():
+        cfg[section] = {"config_path": "unused.yaml", "checkpoint_path": f"ckpt/{f}"}
+        sd = {"w": torch.full((2,), float(len(section)))}
+        torch.save({"net": {"module.w": sd["w"]}} if section == "speech_tokenizer" else sd, tmp_path / "ckpt" / f)
+    torch.save({"embedding.weight": torch.ones(3)}, tmp_path / "ckpt" / "ar.pth")
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump(cfg))
+    seen = {}
+
+    def fake(cls, ar_sd, tok_sd, voc_sd, style_sd, timbre_sd, **kw):
+        seen.update(ar=ar_sd, tok=tok_sd, voc=voc_sd, style=style_sd, timbre=timbre_sd)
+        return InferenceWrapper(None, None, None, None, None, device="cpu")
+
+    monkeypatch.setattr(InferenceWrapper, "from_state_dicts", classmethod(fake))
+    iw = InferenceWrapper.from_config("config.yaml", "ckpt/ar.pth", compile_ar=True, compile_decoder=True, compile_encoder=True,
+                                      root=tmp_path)
+    assert iw.sr == 44100 and iw.config["firefly"]["checkpoint_path"] == "ckpt/voc.pth"
+    assert list(seen["ar"]) == ["embedding.weight"]
+    assert list(seen["tok"]) == ["w"] and float(seen["tok"]["w"][0]) == len("speech_tokenizer")
+    assert float(seen["voc"]["w"][0]) == len("firefly") and float(seen["style"]["w"][0]) == len("style_encoder")
+    assert float(seen["timbre"]["w"][0]) == len("timbre_encoder")
