@@ -105,7 +105,9 @@ class InferenceWrapper:
 
     def _load(self, wave: Wave, crop_seconds: Optional[float] = None) -> torch.Tensor:
         """`librosa.load(path, sr=self.sr)` (infer_arvc.py:274,615,623) for 16-bit / float .wav files, or a tensor /
-        array that already is at self.sr  ->  [1, n] float32 on the device."""
+        array that already is at self.sr  ->  [1, n] float32 on the device.  A file at another rate is converted with the
+        engine's windowed-sinc resampler (torchaudio semantics); librosa's default is soxr_hq, so such files give close
+        but not bit-identical samples -- parity claims are made on audio that already is at the model rate."""
         if isinstance(wave, (str, Path)):
             from scipy.io import wavfile
             rate, data = wavfile.read(str(wave))
