@@ -64,6 +64,8 @@ def test_product_does_not_import_oracle():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.hpp")):
         text = p.read_text()
         assert "import oracle" not in text and "from oracle" not in text, p
+        # ... and the host build of the speaker-encoder source (tests/hostemu) is test infrastructure too
+        assert "libspeaker_host" not in text and "hostemu_" not in text, p
 
 
 def test_custom_ops_registered_with_fake_impls():
