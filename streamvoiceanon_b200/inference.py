@@ -295,6 +295,8 @@ class InferenceWrapper:
                 _lib.check(lib.svanon_stream_create(eng.handle, getattr(self.model, "_max_seq_len", 2048), C.byref(h)))
                 streams.append(h)
                 _lib.check(lib.svanon_ar_set_delay(h, int(delay)))
+                if noise is None:                      # the library's counter-based generator: one seed per utterance
+                    _lib.check(lib.svanon_ar_set_sampling(h, 0.7, 0.7, 1000 + k))
                 keep += [rc, ra, sc, sv, tl, out, noise]
                 for lst, t in ((rc_p, rc), (ra_p, ra), (sc_p, sc), (sv_p, sv), (tl_p, tl), (out_p, out)):
                     lst.append(t.data_ptr())
