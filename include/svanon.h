@@ -151,14 +151,10 @@ int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda
                            int K, void* cuda_stream);
 
 /* batch-1 decode kernel variant: 1 (default) = weights staged through shared memory with TMA bulk copies, grid
- * barriers between phases; 2 = staged weights + activations exchanged between CTAs as self-validating {value, tag}
- * words instead of barriers (experimental: correct, but measured slower -- polling congestion, profiles/README.md);
- * 0 = weights loaded straight from global memory + grid barriers (what batched launches use) */
+ * barriers between phases; 0 = weights loaded straight from global memory + grid barriers (what the 2- and 4-stream
+ * launches use).  (Two more variants -- a barrier-free flag-in-data exchange and a per-CTA epoch-word barrier -- were
+ * measured slower in round 1, profiles/README.md, and were removed from the product; git history keeps them.) */
 int svanon_ar_set_kernel_variant(svanon_engine* e, int variant);
-/* grid barrier between the phases of the persistent decode kernels: 0 (default) = a single arrival counter
- * (`red.release` + acquire poll), 1 = one epoch word per CTA (release store to the CTA's own word, one warp polls all
- * words; no atomics) -- correct, measured slower (1.31 vs 1.07 ms per frame, profiles/README.md) */
-int svanon_ar_set_barrier_mode(svanon_engine* e, int mode);
 /* measurement aid: in-kernel timeline of the batch-1 decode kernel (variant 1).  enable != 0 zeroes and arms 8 cycle
  * counters that thread 0 of CTA 0 accumulates per category between markers: [0] activation load + norm, [1] wait for the
  * staged weights, [2] dot products + result stores, [3] grid barrier, [4] attention, [5] sampler, [6] other; cycles_out
@@ -166,7 +162,7 @@ int svanon_ar_set_barrier_mode(svanon_engine* e, int mode);
 int svanon_ar_profile(svanon_engine* e, int enable, uint64_t* cycles_out);
 /* measurement aid: `iters` back-to-back grid barriers of the persistent decode kernels (one CTA per SM), optionally with
  * the publish -> barrier -> read-everybody round trip of a real phase; *ms_out = device time of the whole launch */
-int svanon_debug_grid_barrier(svanon_engine* e, int mode, int iters, int exchange, float* ms_out);
+int svanon_debug_grid_barrier(svanon_engine* e, int iters, int exchange, float* ms_out);
 int svanon_ar_read_debug(svanon_engine* e, float* slow_logits /*[8192]*/, float* hidden /*[768]*/,
                          float* fast_logits /*[8][1000]*/);
 

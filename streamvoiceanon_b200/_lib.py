@@ -51,9 +51,8 @@ _SIGS = {
     "svanon_debug_gemm_taps": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, C.POINTER(C.c_int), _p, _p, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "svanon_ar_set_kernel_variant": (C.c_int, [_p, C.c_int]),
-    "svanon_ar_set_barrier_mode": (C.c_int, [_p, C.c_int]),
     "svanon_ar_profile": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint64)]),
-    "svanon_debug_grid_barrier": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "svanon_debug_grid_barrier": (C.c_int, [_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "svanon_ar_read_debug": (C.c_int, [_p, _p, _p, _p]),
     "svanon_stream_set_prompt": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, C.c_int, C.c_int, _p]),
     "svanon_stream_setup": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -131,6 +131,10 @@ class ARVCWrapper:
         h = C.c_void_p()
         _lib.check(lib.svanon_stream_create(self._engine.handle, self._max_seq_len, C.byref(h)))
         self._stream = h
+        # the reference samples from torch's global generator (dual_ar_stream.py:1095): a new stream draws the seed of
+        # the library's counter-based generator from it (torch.manual_seed reproduces a run; no two streams are alike)
+        from .streaming import new_sampler_seed
+        _lib.check(lib.svanon_ar_set_sampling(h, 0.7, 0.7, new_sampler_seed()))
         d = self.decoder.delay
         if isinstance(d, int):
             _lib.check(lib.svanon_ar_set_delay(self._stream, d))
@@ -190,7 +194,9 @@ class ARVCWrapper:
                                                          ptr(noise) if noise is not None else None, ptr(out),
                                                          C.byref(pos), C.c_void_p(_cuda_stream_ptr())))
         self._step += 1
-        return out, torch.tensor(pos.value, device=dev)
+        # the position is host-side bookkeeping (no device read); the caller only does `current_pos // 2 >= max_seq_frames`
+        # (infer_arvc.py:547), which a 0-d CPU tensor serves without a device round trip
+        return out, torch.tensor(pos.value)
 
     def generate(self, ref_content_codes, ref_audio_codes, src_content_codes, style_vectors, timbre_latents,
                  **sampling_kwargs):

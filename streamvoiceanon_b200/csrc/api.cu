@@ -258,79 +258,11 @@ int svanon_ar_decode_one(svanon_stream* s, const int64_t* content_id, const floa
   return rc;
 }
 
-int svanon_ar_generate(svanon_stream* sh, const int64_t* ref_content, const int32_t* ref_audio, int Tr,
-                       const int64_t* src_content, int Ts, const float* style, const float* timbre, const float* noise,
-                       int32_t* codes_out, void* stream) {
-  return guarded([&] {
-    SV_CHECK(sh && ref_content && ref_audio && src_content && style && timbre && codes_out, "null argument");
-    Stream& s = sh->st;
-    Engine& e = *s.eng;
-    const int d = s.delay;
-    SV_CHECK(Tr >= 1 && Ts >= 1 && Ts >= d, "generate needs Tr >= 1 and Ts >= delay");
-    Args a(sh->owner, stream, (size_t)(Tr + Ts) * 64 + (size_t)Ts * 8 * AR_CB_SIZE * 4 + 65536);
-    const long long* rc = (const long long*)a.in(ref_content, (size_t)Tr);
-    const int* ra = a.in(ref_audio, (size_t)8 * Tr);
-    const long long* sc = (const long long*)a.in(src_content, (size_t)Ts);
-    const float* sv = a.in(style, 192);
-    const float* tl = a.in(timbre, 32 * 128);
-    const float* nz = a.in(noise, (size_t)Ts * 8 * AR_CB_SIZE);
-    int* out = a.out(codes_out, (size_t)8 * Ts);
-    cudaStream_t st = a.st;
-    // prefill sequence (dual_ar_stream.py:709-722): 33 spk rows, then (cond_t, audio'_t) for t < Tr+d with
-    // cond = [ref_cond, src_cond[:d]] and audio' = [wait4start[:d], embed(ref_audio)], then remaining[0].
-    const int n_pairs = Tr + d;
-    const int n_tok = AR_SPK_TOKENS + 2 * n_pairs + 1;
-    SV_CHECK(n_tok + 2 * (Ts - 1) <= s.max_seq, "utterance does not fit the KV cache (max_seq_len)");
-    e.ws.ensure(((size_t)(n_tok + 8) * 12000 + (1u << 20)) * sizeof(float));
-    e.ws.reset();
-    float* x = e.ws.alloc_f((long long)(n_tok + 2) * AR_DIM);
-    {
-      GemmParams p;
-      p.A = tl; p.W = e.ctx_w; p.C = x; p.bias = e.ctx_b; p.M = 32; p.N = AR_DIM; p.K = 128; p.lda = 128; p.ldc = AR_DIM;
-      launch_gemm(p, st);
-      GemmParams q;
-      q.A = sv; q.W = e.style_w; q.C = x + 32 * AR_DIM; q.bias = e.style_b; q.M = 1; q.N = AR_DIM; q.K = 192; q.lda = 192;
-      q.ldc = AR_DIM;
-      launch_gemm(q, st);
-    }
-    float* seq = x + AR_SPK_TOKENS * AR_DIM;
-    launch_gather_rows(e.ar.cond_emb, rc, seq, Tr, AR_DIM, 2 * AR_DIM, st);
-    if (d > 0) {
-      launch_gather_rows(e.ar.cond_emb, sc, seq + (long long)2 * Tr * AR_DIM, d, AR_DIM, 2 * AR_DIM, st);
-      launch_copy_rows(e.w4s, AR_DIM, seq + AR_DIM, 2 * AR_DIM, d, AR_DIM, st);
-    }
-    launch_embed_codes(e.ar.codebook_emb, ra, Tr, seq + (long long)(2 * d + 1) * AR_DIM, Tr, 2 * AR_DIM, st);
-    // all but the last two tokens through the multi-token path; the last two are a normal decode step
-    const int n_pre = n_tok - 2;
-    launch_copy_rows(seq + (long long)(2 * n_pairs - 1) * AR_DIM, AR_DIM, s.x_audio, AR_DIM, 1, AR_DIM, st);
-    e.ar_forward_tokens(s, x, n_pre, 0, st);
-    s.pos_next = n_pre;
-    // per-call sampling arguments apply from the SECOND frame on: the reference's prefill call passes none
-    // (dual_ar_stream.py:723), the loop passes the caller's (:745-752)
-    struct Restore {
-      Stream& s; float t, p;
-      ~Restore() { s.temperature = t; s.top_p = p; }
-    } restore{s, s.temperature, s.top_p};
-    for (int i = 0; i < Ts; ++i) {
-      if (i == 1 && s.gen_temperature >= 0.f) { s.temperature = s.gen_temperature; s.top_p = s.gen_top_p; }
-      // remaining = [src_cond[d:], wait4end[:d]]  (dual_ar_stream.py:716)
-      const int j = d + i;
-      if (j < Ts) { s.step_content_id = sc + j; s.step_cond_row = nullptr; }
-      else { s.step_content_id = nullptr; s.step_cond_row = e.w4e + (long long)(j - Ts) * AR_DIM; }
-      s.step_noise = nz ? nz + (size_t)i * 8 * AR_CB_SIZE : nullptr;
-      Stream* one = &s;
-      e.ar_decode_step(&one, 1, st);
-      SV_CUDA(cudaMemcpy2DAsync(out + i, (size_t)Ts * sizeof(int), s.codes_dev, sizeof(int), sizeof(int), 8,
-                                cudaMemcpyDeviceToDevice, st));
-    }
-    a.finish();
-  });
-}
-
 namespace {
-// Prompt part of offline generate for one utterance: the token sequence of svanon_ar_generate above (33 speaker rows,
-// (cond_t, audio'_t) pairs for t < Tr + d, then the first remaining condition) up to, not including, the first decode
-// step.  Kept separate from svanon_ar_generate until this path has run on a GPU; the two are meant to share it.
+// Prompt part of offline generate for one utterance (dual_ar_stream.py:709-722), shared by svanon_ar_generate and
+// svanon_ar_generate_many: 33 speaker rows, then (cond_t, audio'_t) for t < Tr + d with cond = [ref_cond, src_cond[:d]]
+// and audio' = [wait4start[:d], embed(ref_audio)], then remaining[0] -- up to, not including, the first decode step
+// (all but the last two tokens go through the multi-token path; the last two are a normal decode step).
 void generate_prefill(Engine& e, Stream& s, const long long* rc, const int* ra, int Tr, const long long* sc, int Ts,
                       const float* sv, const float* tl, cudaStream_t st) {
   const int d = s.delay;
@@ -360,6 +292,47 @@ void generate_prefill(Engine& e, Stream& s, const long long* rc, const int* ra, 
   s.pos_next = n_pre;
 }
 }  // namespace
+
+int svanon_ar_generate(svanon_stream* sh, const int64_t* ref_content, const int32_t* ref_audio, int Tr,
+                       const int64_t* src_content, int Ts, const float* style, const float* timbre, const float* noise,
+                       int32_t* codes_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(sh && ref_content && ref_audio && src_content && style && timbre && codes_out, "null argument");
+    Stream& s = sh->st;
+    Engine& e = *s.eng;
+    const int d = s.delay;
+    SV_CHECK(Tr >= 1 && Ts >= 1 && Ts >= d, "generate needs Tr >= 1 and Ts >= delay");
+    Args a(sh->owner, stream, (size_t)(Tr + Ts) * 64 + (size_t)Ts * 8 * AR_CB_SIZE * 4 + 65536);
+    const long long* rc = (const long long*)a.in(ref_content, (size_t)Tr);
+    const int* ra = a.in(ref_audio, (size_t)8 * Tr);
+    const long long* sc = (const long long*)a.in(src_content, (size_t)Ts);
+    const float* sv = a.in(style, 192);
+    const float* tl = a.in(timbre, 32 * 128);
+    const float* nz = a.in(noise, (size_t)Ts * 8 * AR_CB_SIZE);
+    int* out = a.out(codes_out, (size_t)8 * Ts);
+    cudaStream_t st = a.st;
+    generate_prefill(e, s, rc, ra, Tr, sc, Ts, sv, tl, st);
+    // per-call sampling arguments apply from the SECOND frame on: the reference's prefill call passes none
+    // (dual_ar_stream.py:723), the loop passes the caller's (:745-752)
+    struct Restore {
+      Stream& s; float t, p;
+      ~Restore() { s.temperature = t; s.top_p = p; }
+    } restore{s, s.temperature, s.top_p};
+    for (int i = 0; i < Ts; ++i) {
+      if (i == 1 && s.gen_temperature >= 0.f) { s.temperature = s.gen_temperature; s.top_p = s.gen_top_p; }
+      // remaining = [src_cond[d:], wait4end[:d]]  (dual_ar_stream.py:716)
+      const int j = d + i;
+      if (j < Ts) { s.step_content_id = sc + j; s.step_cond_row = nullptr; }
+      else { s.step_content_id = nullptr; s.step_cond_row = e.w4e + (long long)(j - Ts) * AR_DIM; }
+      s.step_noise = nz ? nz + (size_t)i * 8 * AR_CB_SIZE : nullptr;
+      Stream* one = &s;
+      e.ar_decode_step(&one, 1, st);
+      SV_CUDA(cudaMemcpy2DAsync(out + i, (size_t)Ts * sizeof(int), s.codes_dev, sizeof(int), sizeof(int), 8,
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    a.finish();
+  });
+}
 
 int svanon_ar_generate_many(svanon_stream* const* streams, int n, const int64_t* const* ref_content,
                             const int32_t* const* ref_audio, const int* Tr, const int64_t* const* src_content, const int* Ts,
@@ -394,7 +367,18 @@ int svanon_ar_generate_many(svanon_stream* const* streams, int n, const int64_t*
     const int d = ss[0]->delay;
     std::vector<Stream*> active;
     active.reserve(n);
+    // per-call sampling arguments (svanon_ar_set_generate_sampling) apply from the SECOND frame on, per utterance
+    struct Saved { float t, p; };
+    std::vector<Saved> saved(n);
+    for (int k = 0; k < n; ++k) saved[k] = {ss[k]->temperature, ss[k]->top_p};
+    struct Restore {
+      std::vector<Stream*>& ss; std::vector<Saved>& sv;
+      ~Restore() { for (size_t k = 0; k < ss.size(); ++k) { ss[k]->temperature = sv[k].t; ss[k]->top_p = sv[k].p; } }
+    } restore{ss, saved};
     for (int i = 0; i < max_ts; ++i) {
+      if (i == 1)
+        for (Stream* s : ss)
+          if (s->gen_temperature >= 0.f) { s->temperature = s->gen_temperature; s->top_p = s->gen_top_p; }
       active.clear();
       for (int k = 0; k < n; ++k) {
         if (i >= Ts[k]) continue;                     // shorter utterances leave the lock-step batch when they are done
@@ -485,18 +469,8 @@ int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda
 int svanon_ar_set_kernel_variant(svanon_engine* e, int variant) {
   return guarded([&] {
     SV_CHECK(e, "null engine");
-    SV_CHECK(variant >= 0 && variant <= 2, "variant: 0 direct loads, 1 TMA-staged weights, 2 staged + flag-in-data exchange");
+    SV_CHECK(variant == 0 || variant == 1, "variant: 0 direct loads, 1 TMA-staged weights");
     e->eng.ar_variant = variant;
-  });
-}
-
-int svanon_ar_set_barrier_mode(svanon_engine* e, int mode) {
-  return guarded([&] {
-    SV_CHECK(e, "null engine");
-    SV_CHECK(mode == 0 || mode == 1, "barrier mode: 0 arrival counter, 1 per-CTA epoch words");
-    SV_CUDA(cudaSetDevice(e->eng.device));
-    SV_CUDA(cudaDeviceSynchronize());
-    e->eng.ar_barrier_mode = mode;
   });
 }
 
@@ -518,13 +492,13 @@ int svanon_ar_profile(svanon_engine* e, int enable, uint64_t* cycles_out) {
   });
 }
 
-int svanon_debug_grid_barrier(svanon_engine* e, int mode, int iters, int exchange, float* ms_out) {
+int svanon_debug_grid_barrier(svanon_engine* e, int iters, int exchange, float* ms_out) {
   return guarded([&] {
-    SV_CHECK(e && ms_out && iters > 0 && (mode == 0 || mode == 1), "bad arguments");
+    SV_CHECK(e && ms_out && iters > 0, "bad arguments");
     SV_CHECK(e->eng.finalized[MODEL_AR], "AR weights not finalized");
     SV_CUDA(cudaSetDevice(e->eng.device));
     SV_CUDA(cudaDeviceSynchronize());
-    *ms_out = grid_barrier_probe(e->eng.ar_barrier, mode, iters, e->eng.ar_g, exchange, e->eng.num_sms, nullptr);
+    *ms_out = grid_barrier_probe(e->eng.ar_barrier, iters, e->eng.ar_g, exchange, e->eng.num_sms, nullptr);
   });
 }
 
@@ -533,7 +507,6 @@ int svanon_ar_read_debug(svanon_engine* e, float* slow_logits, float* hidden, fl
     SV_CHECK(e && e->eng.finalized[MODEL_AR], "AR weights not finalized");
     SV_CUDA(cudaSetDevice(e->eng.device));
     SV_CUDA(cudaDeviceSynchronize());
-    SV_CHECK(!ar_decode_ll_aborted(), "AR decode kernel (flag-in-data variant) hit its poll watchdog");
     if (slow_logits) SV_CUDA(cudaMemcpy(slow_logits, e->eng.dbg_slow_logits, AR_VOCAB * 4, cudaMemcpyDeviceToHost));
     if (hidden) SV_CUDA(cudaMemcpy(hidden, e->eng.dbg_hidden, AR_DIM * 4, cudaMemcpyDeviceToHost));
     if (fast_logits) SV_CUDA(cudaMemcpy(fast_logits, e->eng.dbg_fast_logits, 8 * AR_CB_SIZE * 4, cudaMemcpyDeviceToHost));
@@ -597,6 +570,7 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
     SV_CHECK(s.enc_win > 0, "svanon_stream_setup has not been called");
     SV_CHECK(s.ref_frames > 0, "svanon_stream_set_prompt has not been called");
     SV_CHECK(n == s.chunk * SAMPLES_PER_FRAME, "chunk must hold decode_chunk_frames * 2048 samples");
+    NvtxRange nvtx_("svanon_stream_process_chunk");
     Args a(sh->owner, stream, (size_t)n * 8 + (size_t)s.chunk * 8 * AR_CB_SIZE * 4 +
                                   (size_t)(s.ref_frames + s.buffer_frames) * 64 + 65536);
     cudaStream_t st = a.st;
@@ -735,7 +709,6 @@ int svanon_stream_history(svanon_stream* sh, int64_t* src_content, int* n_src, i
     Stream& s = sh->st;
     SV_CUDA(cudaSetDevice(s.eng->device));
     SV_CUDA(cudaDeviceSynchronize());
-    SV_CHECK(!ar_decode_ll_aborted(), "AR decode kernel (flag-in-data variant) hit its poll watchdog");
     const int ns = std::min(s.n_src, cap), np = std::min(s.n_pred, cap);
     *n_src = ns; *n_pred = np;
     if (src_content && ns > 0)

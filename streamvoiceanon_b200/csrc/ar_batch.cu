@@ -152,15 +152,14 @@ __global__ void __launch_bounds__(128) arb_attn_fast_kernel(const ArBatchSlot* _
 
 // top-p / temperature sampler of codebook `cb` for every stream (one CTA each), then the next fast input row
 __global__ void __launch_bounds__(NT) arb_sample_kernel(const ArBatchSlot* __restrict__ slots, const float* __restrict__ logits,
-                                                        const float* __restrict__ fast_emb, float* __restrict__ xf, int cb,
-                                                        float temperature, float top_p) {
+                                                        const float* __restrict__ fast_emb, float* __restrict__ xf, int cb) {
   pdl_trigger();
   pdl_wait();
   __shared__ SampleSmem ssm;
   const int b = blockIdx.x;
   const ArBatchSlot& s = slots[b];
   const float* noise = s.noise ? s.noise + cb * AR_CB_SIZE : nullptr;
-  const int tok = sample_topp(logits + (long long)b * 1024, noise, s.seed, s.step, cb + 1, temperature, top_p, ssm);
+  const int tok = sample_topp(logits + (long long)b * 1024, noise, s.seed, s.step, cb + 1, s.temperature, s.top_p, ssm);
   if (threadIdx.x == 0) s.out_codes[cb] = tok;
   for (int i = threadIdx.x; i < D; i += NT) xf[(long long)b * D + i] = __ldg(fast_emb + (long long)tok * D + i);
 }
@@ -223,6 +222,7 @@ void ArBatchWork::ensure(int B) {
 
 // One decode step for `batch` streams (any count) on the GEMM path.
 void Engine::ar_decode_step_gemm(Stream* const* streams, int batch, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:A decode (many streams)");
   SV_CHECK(finalized[MODEL_AR], "AR weights not finalized");
   SV_CHECK(batch >= 1, "empty decode batch");
   arb.ensure(batch);
@@ -242,13 +242,13 @@ void Engine::ar_decode_step_gemm(Stream* const* streams, int batch, cudaStream_t
     d.kc = s.kc; d.vc = s.vc; d.fkc = s.fkc; d.fvc = s.fvc; d.x_audio = s.x_audio;
     d.content_id = s.step_content_id; d.cond_row = s.step_cond_row; d.noise = s.step_noise; d.out_codes = s.codes_dev;
     d.pos = s.pos_next; d.step = s.step; d.seed = s.seed;
+    d.temperature = s.temperature; d.top_p = s.top_p;
     d.pred_hist = s.step_pred_hist; d.pred_ld = HIST_CAP; d.pred_col = s.step_pred_col;
   }
   SV_CUDA(cudaMemcpyAsync(arb.slots_dev, hs, (size_t)B * sizeof(ArBatchSlot), cudaMemcpyHostToDevice, st));
   SV_CUDA(cudaEventRecord(arb.ev[slot], st));
   arb.ev_pending[slot] = true;
   const ArBatchSlot* sd = arb.slots_dev;
-  const float temperature = streams[0]->temperature, top_p = streams[0]->top_p;
 
   auto layer = [&](const ArLayerWeights& w, float* xr, int M, int li, bool fast, int cb) {
     launch_rmsnorm(xr, arb.nrm, w.attn_norm, M, AR_DIM, AR_NORM_EPS, st);
@@ -285,7 +285,7 @@ void Engine::ar_decode_step_gemm(Stream* const* streams, int batch, cudaStream_t
     for (int l = 0; l < AR_FAST_LAYERS; ++l) layer(ar.fast[l], arb.xf, B, l, true, cb);
     launch_rmsnorm(arb.xf, arb.nrm, ar.fast_norm_w, B, AR_DIM, AR_NORM_EPS, st);
     gemm(arb.nrm, AR_DIM, ar.fast_output_w, arb.logits, 1024, nullptr, B, AR_CB_SIZE, AR_DIM, st);
-    launch_pdl(arb_sample_kernel, dim3(B), dim3(NT), 0, st, sd, (const float*)arb.logits, ar.fast_emb, arb.xf, cb, temperature, top_p);
+    launch_pdl(arb_sample_kernel, dim3(B), dim3(NT), 0, st, sd, (const float*)arb.logits, ar.fast_emb, arb.xf, cb);
     SV_LAUNCHED();
   }
   launch_pdl(arb_finish_kernel, dim3(B), dim3(256), 0, st, sd, ar.codebook_emb);

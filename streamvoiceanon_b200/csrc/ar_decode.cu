@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_kernel(const ArDecodeArgs a) 
   const int total_warps = NW * gridDim.x;
   const int gtid = blockIdx.x * NT + threadIdx.x;
 
-  grid_sync_init(a.barrier, a.barrier_mode);
+  grid_sync_init(a.barrier);
   // ---- phase 0: assemble the 2 input rows per stream: [cached_new_audio_emb, embedding[content_id]]
   for (int i = gtid; i < B * 2 * D; i += NT * gridDim.x) {
     const int b = i / (2 * D), j = (i / D) % 2, c = i % D;
@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_kernel(const ArDecodeArgs a) 
       if (a.dbg_fast_logits && b == 0)
         for (int i = threadIdx.x; i < AR_CB_SIZE; i += NT) a.dbg_fast_logits[cb * AR_CB_SIZE + i] = __ldcg(a.logits + i);
       const float* noise = a.s[b].noise ? a.s[b].noise + cb * AR_CB_SIZE : nullptr;
-      const int tok = sample_topp(a.logits + b * 1024, noise, a.s[b].seed, a.s[b].step, cb + 1, a.temperature,
-                                  a.top_p, ssm);
+      const int tok = sample_topp(a.logits + b * 1024, noise, a.s[b].seed, a.s[b].step, cb + 1, a.s[b].temperature,
+                                  a.s[b].top_p, ssm);
       if (threadIdx.x == 0) a.s[b].out_codes[cb] = tok;
       for (int i = threadIdx.x; i < D; i += NT) a.x[b * D + i] = __ldg(a.fast_emb + (long long)tok * D + i);
     }
@@ -330,9 +330,9 @@ void launch_b(const ArDecodeArgs& args, int grid, cudaStream_t st) {
 
 // Measurement aid: `iters` back-to-back grid barriers (optionally with the store -> fence -> barrier -> L2 load round
 // trip a real phase has) in the launch configuration of the decode kernels.
-__global__ void __launch_bounds__(NT, 1) grid_barrier_probe_kernel(unsigned* bar, int mode, int iters, float* scratch, int exchange) {
+__global__ void __launch_bounds__(NT, 1) grid_barrier_probe_kernel(unsigned* bar, int iters, float* scratch, int exchange) {
   const unsigned nblocks = gridDim.x;
-  grid_sync_init(bar, mode);
+  grid_sync_init(bar);
   float acc = 0.f;
   for (int i = 0; i < iters; ++i) {
     if (exchange) {
@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(NT, 1) grid_barrier_probe_kernel(unsigned* bar
   grid_sync_finish(bar);
 }
 
-float grid_barrier_probe(unsigned* bar, int mode, int iters, float* scratch, int exchange, int grid, cudaStream_t st) {
-  void* kargs[] = {(void*)&bar, (void*)&mode, (void*)&iters, (void*)&scratch, (void*)&exchange};
+float grid_barrier_probe(unsigned* bar, int iters, float* scratch, int exchange, int grid, cudaStream_t st) {
+  void* kargs[] = {(void*)&bar, (void*)&iters, (void*)&scratch, (void*)&exchange};
   cudaEvent_t e0, e1;
   SV_CUDA(cudaEventCreate(&e0));
   SV_CUDA(cudaEventCreate(&e1));

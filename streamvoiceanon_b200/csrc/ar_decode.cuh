@@ -29,6 +29,8 @@ struct ArStreamDev {
   int pos;                      // sequence position of the first of the two new tokens
   unsigned step;
   unsigned long long seed;
+  float temperature;            // this stream's sampling arguments (dual_ar_stream.py:1103-1104 defaults 0.7 / 0.7)
+  float top_p;
 };
 
 struct ArDecodeArgs {
@@ -50,10 +52,7 @@ struct ArDecodeArgs {
   float* g;                     // [2B][2304]
   float* part;                  // [B][12][nsplit][2][66]
   float* logits;                // [B][1024]
-  unsigned* barrier;            // [32 + grid]: counter, saved counter, saved epoch, ..., per-CTA epoch words; zeroed once
-  int barrier_mode;             // 0 arrival counter, 1 per-CTA epoch words (ar_decode_common.cuh)
-  void* ll;                     // tagged-word scratch of the barrier-free variant (ar_decode_ll.cu), zero-initialised
-  unsigned epoch;               // launch counter (>= 1) that makes this launch's tags unique
+  unsigned* barrier;            // [2]: arrival counter, counter value saved across launches; zeroed once
   float* dbg_slow_logits;       // [8192] or null
   float* dbg_hidden;            // [768] or null
   float* dbg_fast_logits;       // [8][1000] or null
@@ -61,19 +60,13 @@ struct ArDecodeArgs {
   unsigned long long* prof;     // [8] cycle counters per category (ar_decode_staged.cu Prof), or null
   int max_seq;
   int nsplit;
-  float temperature;
-  float top_p;
 };
 
 int ar_decode_max_batch();
-float grid_barrier_probe(unsigned* bar, int mode, int iters, float* scratch, int exchange, int grid, cudaStream_t st);
+float grid_barrier_probe(unsigned* bar, int iters, float* scratch, int exchange, int grid, cudaStream_t st);
 void launch_ar_decode(const ArDecodeArgs& args, int batch, int grid, cudaStream_t st);
 // batch-1 variant with TMA-staged weights (ar_decode_staged.cu)
 bool ar_decode_staged_supported(int grid);
 void launch_ar_decode_staged(const ArDecodeArgs& args, int grid, cudaStream_t st);
-// batch-1 variant without grid barriers: flag-in-data exchange of activations (ar_decode_ll.cu)
-size_t ar_decode_ll_scratch_words();
-int ar_decode_ll_aborted();      // 1 if a launch hit the poll watchdog (synchronises)
-void launch_ar_decode_ll(const ArDecodeArgs& args, int grid, cudaStream_t st);
 
 }  // namespace svanon

@@ -30,70 +30,39 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Grid barrier; co-residency is guaranteed by the cooperative launch.  Two implementations, selected per launch:
-//  mode 0  one monotonically increasing arrival counter (bar[0]): arriving is a fire-and-forget `red.release`, waiting
-//          an acquire-poll until the counter reaches base + k * nblocks.  bar[1] carries the counter across launches.
-//          Default.
-//  mode 1  one epoch word PER CTA (bar[32 + cta]): arriving is a plain release store to the CTA's own word, waiting is
-//          one warp reading all words (5 coalesced loads) until every one has reached this barrier's epoch.  No
-//          atomics; bar[2] carries the epoch across launches.  Measured SLOWER on B200 (1.31 vs 1.07 ms per frame:
-//          148 x 5 polling loads per round cost more than 148 same-address reds); kept as an option.
-constexpr int GRID_FLAGS_OFF = 32;
+// Grid barrier; co-residency is guaranteed by the cooperative launch.  One monotonically increasing arrival counter
+// (bar[0]): arriving is a fire-and-forget `red.release`, waiting an acquire-poll until the counter reaches
+// base + k * nblocks.  bar[1] carries the counter across launches.  (A per-CTA epoch-word barrier and a barrier-free
+// flag-in-data exchange were measured slower in round 1 -- profiles/README.md -- and live in git history only.)
 __device__ __forceinline__ unsigned& grid_target() {
   __shared__ unsigned t;
   return t;
 }
-__device__ __forceinline__ unsigned& grid_mode() {
-  __shared__ unsigned m;
-  return m;
-}
-__device__ __forceinline__ void grid_sync_init(unsigned* bar, int mode = 0) {
+__device__ __forceinline__ void grid_sync_init(unsigned* bar) {
   if (threadIdx.x == 0) {
     unsigned base;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(base) : "l"(bar + (mode ? 2 : 1)) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(base) : "l"(bar + 1) : "memory");
     grid_target() = base;
-    grid_mode() = (unsigned)mode;
   }
   __syncthreads();
 }
 __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned nblocks) {
   __syncthreads();
-  if (grid_mode() == 0) {
-    if (threadIdx.x == 0) {
-      const unsigned t = grid_target() + nblocks;
-      grid_target() = t;
-      __threadfence();
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-      unsigned v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      } while ((int)(v - t) < 0);
-    }
-  } else if (threadIdx.x < 32) {
-    const unsigned t = grid_target() + 1;
-    __syncwarp();
-    unsigned* flags = bar + GRID_FLAGS_OFF;
-    if (threadIdx.x == 0) {
-      grid_target() = t;
-      __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(t) : "memory");
-    }
-    bool done;
+  if (threadIdx.x == 0) {
+    const unsigned t = grid_target() + nblocks;
+    grid_target() = t;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned v;
     do {
-      done = true;
-      for (unsigned i = threadIdx.x; i < nblocks; i += 32) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
-        done = done && ((int)(v - t) >= 0);
-      }
-      done = __all_sync(0xffffffffu, done);
-    } while (!done);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while ((int)(v - t) < 0);
   }
   __syncthreads();
 }
-// every CTA has passed the last barrier's arrive before any CTA can get here, so the counter / epoch is final
+// every CTA has passed the last barrier's arrive before any CTA can get here, so the counter is final
 __device__ __forceinline__ void grid_sync_finish(unsigned* bar) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) bar[grid_mode() ? 2 : 1] = grid_target();
+  if (blockIdx.x == 0 && threadIdx.x == 0) bar[1] = grid_target();
 }
 
 // dot products of NR weight rows (length K, row-major, streamed) with M activation vectors held in shared

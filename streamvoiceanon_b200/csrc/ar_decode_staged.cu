@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
   }
   __syncthreads();
   if (threadIdx.x == NT - 32) issue(a, sg, 0);
-  grid_sync_init(a.barrier, a.barrier_mode);
+  grid_sync_init(a.barrier);
   Prof pf;
   pf.start(a.prof);
 
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(NT, 1) ar_decode_staged_kernel(const ArDecodeA
     if (blockIdx.x == 0 && a.dbg_fast_logits)
       for (int i = threadIdx.x; i < AR_CB_SIZE; i += NT) a.dbg_fast_logits[cb * AR_CB_SIZE + i] = __ldcg(a.logits + i);
     const float* noise = st.noise ? st.noise + cb * AR_CB_SIZE : nullptr;
-    const int tok = sample_topp(a.logits, noise, st.seed, st.step, cb + 1, a.temperature, a.top_p, ssm);
+    const int tok = sample_topp(a.logits, noise, st.seed, st.step, cb + 1, st.temperature, st.top_p, ssm);
     if (threadIdx.x == 0) s_toks[cb] = tok;
     x_in = a.fast_emb + (long long)tok * D;
     if (blockIdx.x == 0) {

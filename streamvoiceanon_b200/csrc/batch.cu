@@ -228,6 +228,7 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     SV_CHECK(b && wave_chunks && wave_out, "null argument");
     SV_CHECK(b->enc_win > 0, "svanon_batch_setup has not been called");
     SV_CHECK(n_samples == b->chunk * SAMPLES_PER_FRAME, "every stream's chunk must hold decode_chunk_frames * 2048 samples");
+    NvtxRange nvtx_("svanon_batch_process_chunk");
     Engine& e = b->owner->eng;
     const int n = (int)b->streams.size();
     const int c = b->chunk;

@@ -1,6 +1,7 @@
 // Shared declarations for the svanon_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -27,6 +28,15 @@ struct Error : std::runtime_error {
       throw ::svanon::Error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" + \
                             std::to_string(__LINE__));                                 \
   } while (0)
+
+// NVTX range over a host-side scope: the stages of the per-chunk loop show up by name ("svanon:E window", "svanon:A
+// decode", "svanon:V step", ...) on an Nsight Systems / ncu --nvtx timeline.  Costs a few ns without a profiler attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 extern long long g_kernel_launches;

@@ -45,7 +45,7 @@ Engine::~Engine() {
     for (auto& kv : w[m]) cudaFree(kv.second.data);
   for (float* p : owned) cudaFree(p);
   for (void* p : {(void*)ar_x, (void*)ar_h, (void*)ar_q, (void*)ar_g, (void*)ar_part, (void*)ar_logits,
-                  (void*)ar_barrier, (void*)ar_ll, (void*)dbg_slow_logits, (void*)dbg_hidden, (void*)dbg_fast_logits})
+                  (void*)ar_barrier, (void*)dbg_slow_logits, (void*)dbg_hidden, (void*)dbg_fast_logits})
     if (p) cudaFree(p);
   if (own_stream) cudaStreamDestroy(own_stream);
 }
@@ -155,15 +155,11 @@ void Engine::finalize_ar() {
   SV_CUDA(cudaMalloc(&ar_logits, (size_t)B * 1024 * 4));
   SV_CUDA(cudaMalloc(&ar_barrier, 1024 * sizeof(unsigned)));
   SV_CUDA(cudaMemset(ar_barrier, 0, 1024 * sizeof(unsigned)));
-  SV_CUDA(cudaMalloc(&ar_ll, ar_decode_ll_scratch_words() * 8));
-  SV_CUDA(cudaMemset(ar_ll, 0, ar_decode_ll_scratch_words() * 8));
   SV_CUDA(cudaMalloc(&dbg_slow_logits, AR_VOCAB * 4));
   SV_CUDA(cudaMalloc(&dbg_hidden, AR_DIM * 4));
   SV_CUDA(cudaMalloc(&dbg_fast_logits, AR_CODEBOOKS * AR_CB_SIZE * 4));
   ar.x = ar_x; ar.h = ar_h; ar.q = ar_q; ar.g = ar_g; ar.part = ar_part; ar.logits = ar_logits;
   ar.barrier = ar_barrier;
-  ar.temperature = 0.7f;   // logits_to_probs defaults, dual_ar_stream.py:1103-1104
-  ar.top_p = 0.7f;
 }
 
 // ------------------------------------------------------------------------------------------ shared packers
@@ -687,6 +683,7 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
 
 // B full-length utterances / windows of the same length, side by side: wave [B][n] -> ids [B][n/2048].
 void Engine::enc_encode(const float* wave, int B, long long n, long long* ids_dev, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:E encode");
   SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
   SV_CHECK(B >= 1, "no utterances");
   const int S = (int)(n / HOP) / 4;
@@ -728,6 +725,7 @@ __global__ void enc_assemble_kernel(const float* __restrict__ spans, const float
 // change with the window start, nothing of it can be kept).  state->xt [B][S][512] double-buffered.
 void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,
                              cudaStream_t st) {
+  NvtxRange nvtx_("svanon:E window step");
   SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
   const long long nw = (long long)S * SAMPLES_PER_FRAME;
   const int Ls = ENC_RF + c;
@@ -794,6 +792,7 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
 // full-length rows: the same conv stack as the tokenizer with the vocoder's weights, then the FSQ indices of the 8
 // groups (DownsampleFiniteScalarQuantize.encode, fsq.py:106-110).
 void Engine::voc_encode(const float* wave, int B, long long n, int* codes_dev, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:prompt voc_encode");
   SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
   SV_CHECK(voc_cs.ready, "the vocoder checkpoint was loaded without its encoder (backbone.*, quantizer.downsample.*, project_in)");
   const int S = (int)(n / HOP) / 4;
@@ -933,6 +932,7 @@ void Engine::voc_head(const float* z, int L, float* wave, cudaStream_t st) {
 }
 
 void Engine::voc_decode(const long long* codes, long long ld, int T, float* wave, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:V window decode");
   SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
   SV_CHECK(T >= 1, "empty code sequence");
   ws.ensure(voc_ws_bytes(T));
@@ -947,6 +947,7 @@ void Engine::voc_decode(const long long* codes, long long ld, int T, float* wave
 // BaseTransformer.forward_generate over M new tokens at positions pos0.. (dual_ar_stream.py:312-356) without the
 // heads: fills the KV cache; x is updated in place to the last layer's residual stream.
 void Engine::ar_forward_tokens(Stream& s, float* x, int M, int pos0, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:A prefill tokens");
   SV_CHECK(pos0 + M <= s.max_seq, "sequence position exceeds the KV cache (max_seq_len)");
   float* nrm = ws.alloc_f((long long)M * AR_DIM);
   float* qkv = ws.alloc_f((long long)M * 3 * AR_DIM);
@@ -1024,6 +1025,7 @@ void Engine::ar_prefill_prompt(Stream& s, const long long* ref_content, const in
 
 // ARVCWrapper.prefill_src_condition4delay (arvc_wrapper.py:114-119) -> dual_ar_stream.py:798-815
 void Engine::ar_prefill_delay(Stream& s, const long long* src_content, int n, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:A prefill delay");
   const int d = s.delay;
   SV_CHECK(n == d, "prefill_src_condition4delay expects exactly `delay` content codes");
   SV_CHECK(d > 0, "prefill_src_condition4delay is only defined for delay > 0");
@@ -1043,6 +1045,7 @@ void Engine::ar_prefill_delay(Stream& s, const long long* src_content, int n, cu
 // Re-prompt of the per-chunk loop (infer_arvc.py:547-564): the prompt kept at set_prompt time, extended by the last
 // `buffer_frames` predicted frames and their source content ids, is prefilled again from position 0.
 void Engine::reprompt(Stream& s, Workspace& staging, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:A re-prompt");
   const int buf = std::min(s.buffer_frames, s.n_pred);
   const int Tn = s.ref_frames + buf;
   SV_CHECK(s.n_src - s.delay >= buf, "not enough source history for re-prompting");
@@ -1060,6 +1063,7 @@ void Engine::reprompt(Stream& s, Workspace& staging, cudaStream_t st) {
 
 // DualARWrapper.decode_one (dual_ar_stream.py:817-837) for `batch` independent streams in one launch.
 void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:A decode (persistent kernel)");
   SV_CHECK(finalized[MODEL_AR], "AR weights not finalized");
   SV_CHECK(batch == 1 || batch == 2 || batch == 4, "decode batch must be 1, 2 or 4");
   ArDecodeArgs a = ar;
@@ -1073,16 +1077,14 @@ void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) 
     sd.content_id = s.step_content_id; sd.cond_row = s.step_cond_row; sd.noise = s.step_noise; sd.out_codes = s.codes_dev;
     SV_CHECK(sd.content_id || sd.cond_row, "decode step without a content id");
     sd.pos = s.pos_next; sd.step = s.step; sd.seed = s.seed;
+    sd.temperature = s.temperature; sd.top_p = s.top_p;
     max_keys = std::max(max_keys, s.pos_next + 2);
   }
   a.max_seq = streams[0]->max_seq;
-  a.temperature = streams[0]->temperature;
-  a.top_p = streams[0]->top_p;
   int nsplit = std::max(1, num_sms / (batch * AR_HEADS));
   nsplit = std::min(nsplit, 16);
   nsplit = std::min(nsplit, std::max(1, max_keys / 16));
   a.nsplit = nsplit;
-  a.barrier_mode = ar_barrier_mode;
   a.prof = ar_prof;
   {
     static const float keep = [] {
@@ -1093,12 +1095,7 @@ void Engine::ar_decode_step(Stream* const* streams, int batch, cudaStream_t st) 
   }
   if (debug_logits) { a.dbg_slow_logits = dbg_slow_logits; a.dbg_hidden = dbg_hidden; a.dbg_fast_logits = dbg_fast_logits; }
   else { a.dbg_slow_logits = nullptr; a.dbg_hidden = nullptr; a.dbg_fast_logits = nullptr; }
-  if (batch == 1 && ar_variant == 2 && ar_decode_staged_supported(num_sms)) {
-    a.ll = ar_ll;
-    a.epoch = ++ar_epoch;
-    if ((a.epoch & 0xFFFFFu) == 0) a.epoch = ++ar_epoch;      // tag base must never be 0
-    launch_ar_decode_ll(a, num_sms, st);
-  } else if (batch == 1 && ar_variant == 1 && ar_decode_staged_supported(num_sms)) {
+  if (batch == 1 && ar_variant == 1 && ar_decode_staged_supported(num_sms)) {
     launch_ar_decode_staged(a, num_sms, st);
   } else {
     launch_ar_decode(a, batch, num_sms, st);

@@ -116,6 +116,7 @@ struct ArBatchSlot {
   int pos;
   unsigned step;
   unsigned long long seed;
+  float temperature, top_p;     // this stream's sampling arguments
 };
 
 struct ArBatchWork {
@@ -238,13 +239,10 @@ struct Engine {
   unsigned* ar_barrier = nullptr;
   // last encoder layer for the kept tokens only (enc_transformer_bsq); SVANON_ENC_TAIL_ONLY=0 runs it for all rows
   bool enc_tail_only = [] { const char* e = getenv("SVANON_ENC_TAIL_ONLY"); return !e || atoi(e) != 0; }();
-  int ar_barrier_mode = 0;                     // grid barrier of the persistent decode kernels (ar_decode_common.cuh)
   float *dbg_slow_logits = nullptr, *dbg_hidden = nullptr, *dbg_fast_logits = nullptr;
   bool debug_logits = false;
   unsigned long long* ar_prof = nullptr;       // in-kernel timeline counters (svanon_ar_profile), null = off
-  int ar_variant = 1;                          // batch-1 decode kernel: 0 direct loads, 1 TMA-staged, 2 staged + flag-in-data (no grid barriers)
-  void* ar_ll = nullptr;
-  unsigned ar_epoch = 0;
+  int ar_variant = 1;                          // batch-1 decode kernel: 0 direct loads, 1 TMA-staged weights
 
   // ---- tokenizer
   const float *dft_w = nullptr, *fb_t = nullptr;      // windowed DFT basis and mel filterbank (same LogMelSpectrogram in both)

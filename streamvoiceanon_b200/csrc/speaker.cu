@@ -89,6 +89,7 @@ void Engine::campplus_forward(const float* feat_rows, long long T, int len, floa
 }
 
 void Engine::style_vector(const float* wave, long long n, float* out, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:prompt style_vector");
   const spk::StyleNet& net = style_of(*this);
   ws.ensure(spk::style_ws_floats(n) * sizeof(float));
   ws.reset();
@@ -97,6 +98,7 @@ void Engine::style_vector(const float* wave, long long n, float* out, cudaStream
 }
 
 void Engine::timbre_latent(const float* wave, long long n, long long wave_len, float* out, int* indices, cudaStream_t st) {
+  NvtxRange nvtx_("svanon:prompt timbre_latent");
   SV_CHECK(finalized[MODEL_TIMBRE] && timbre_net, "timbre encoder (BiCodec speaker encoder) weights not loaded");
   const spk::TimbreNet& net = *static_cast<const spk::TimbreNet*>(timbre_net.get());
   SV_CHECK(n >= spk::TM_NFFT, "timbre encoder: the reference wave is shorter than 1024 samples at 16 kHz");

@@ -108,6 +108,7 @@ void Engine::voc_state_reset(VocState& vs, cudaStream_t st) {
 // One step: vs.c new code frames per stream (codes [8][..] with row stride ld) -> vs.c * 2048 new samples per stream.
 void Engine::voc_step(VocState& vs, const long long* codes, long long ld, float* wave_out, cudaStream_t st,
                       long long codes_seg) {
+  NvtxRange nvtx_("svanon:V step");
   SV_CHECK(finalized[MODEL_VOCODER], "vocoder weights not finalized");
   SV_CHECK(vs.arena, "vocoder state not initialised");
   const int c = vs.c, B = vs.B;

@@ -34,9 +34,6 @@ class Engine:
         mode = os.environ.get("SVANON_GEMM_MODE")        # 1 = fp32 CUDA cores, 2 = tcgen05 3xTF32 (library default)
         if mode is not None:
             _lib.check(self.lib.svanon_set_gemm_mode(int(mode)))
-        bar = os.environ.get("SVANON_AR_BARRIER")        # 0 arrival counter (library default), 1 per-CTA epoch words
-        if bar is not None:
-            _lib.check(self.lib.svanon_ar_set_barrier_mode(h, int(bar)))
         pdl = os.environ.get("SVANON_PDL")
         if pdl is not None:
             _lib.check(self.lib.svanon_set_pdl(int(pdl)))

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from .prompt import PromptBuilder
-from .streaming import StreamSession
+from .streaming import StreamSession, new_sampler_seed
 
 Wave = Union[str, Path, torch.Tensor, np.ndarray]
 
@@ -111,8 +111,15 @@ class InferenceWrapper:
         if isinstance(wave, (str, Path)):
             from scipy.io import wavfile
             rate, data = wavfile.read(str(wave))
-            x = torch.from_numpy(np.asarray(data))
-            x = x.float() / 32768.0 if not x.is_floating_point() else x.float()
+            data = np.asarray(data)
+            if data.dtype == np.uint8:                               # 8-bit PCM is unsigned, offset 128
+                x = (torch.from_numpy(data.astype(np.float32)) - 128.0) / 128.0
+            elif np.issubdtype(data.dtype, np.integer):              # int16, or int32 for 24/32-bit PCM: full scale of the dtype
+                x = torch.from_numpy(data.astype(np.float64) / (float(np.iinfo(data.dtype).max) + 1.0)).float()
+            elif np.issubdtype(data.dtype, np.floating):
+                x = torch.from_numpy(data.astype(np.float32))
+            else:
+                raise ValueError(f"unsupported .wav sample type {data.dtype}")
             if x.dim() == 2:
                 x = x.mean(dim=1)                                    # librosa mono=True: channel mean
             x = x[None].to(self.device)
@@ -175,7 +182,7 @@ class InferenceWrapper:
         if self._session is not None:
             self._session.close()
         self._session = StreamSession(self.device, getattr(self.model, "_max_seq_len", 2048))
-        if self._noise_fn is not None:
+        if self._noise_fn is not None:           # else: the new session seeded the library's generator from torch's
             self._session.set_noise_fn(self._noise_fn, 0)
         self._session.set_prompt(content[0], codes, style, timbre, max_prompt_frames=max_prompt_frames, delay=self.delay)
 
@@ -189,8 +196,9 @@ class InferenceWrapper:
 
     # ------------------------------------------------------------------------------------------ the loop
     @torch.no_grad()
-    def process_one_chunk(self, src_wav_chunk: torch.Tensor) -> torch.Tensor:
-        """infer_arvc.py:492-596: [1, chunk * 2048] -> [1, chunk * 2048] (zeros while the delay warm-up fills)."""
+    def process_one_chunk(self, src_wav_chunk: torch.Tensor, pitch_shift: float = 0.0) -> torch.Tensor:
+        """infer_arvc.py:492-596: [1, chunk * 2048] -> [1, chunk * 2048] (zeros while the delay warm-up fills).
+        `pitch_shift` is accepted and unused, as in the reference (:494 -- nothing in its body reads it)."""
         n = self.decode_chunk_frames * self.SAMPLES_PER_FRAME
         if src_wav_chunk.shape[-1] != n:
             raise ValueError(f"chunk of {src_wav_chunk.shape[-1]} samples, expected decode_chunk_frames * 2048 = {n}")
@@ -242,15 +250,16 @@ class InferenceWrapper:
         src_content, _ = self.speech_tokenizer.encode(src, self.create_wave_lens_tensor(src))
         if delay is not None:
             self.model.set_delay(delay=delay)
-        if self._noise_fn is not None:
-            self.model.set_noise_fn(self._noise_fn, 0)
+        self.model.set_noise_fn(self._noise_fn, 0)          # None too: a stale tape must not be replayed
+        if self._noise_fn is None:
+            self.model.set_sampling(seed=new_sampler_seed())
         vc_codes = self.model.generate(ref_content_codes=content, ref_audio_codes=codes, src_content_codes=src_content.squeeze(0),
                                        style_vectors=style, timbre_latents=timbre, **sampling_kwargs)
         return self.code2wav_fn(vc_codes.long()).squeeze().cpu().numpy()
 
     # ------------------------------------------------------------------------------------------ offline, many utterances
     @torch.no_grad()
-    def infer_batch(self, src_paths: Sequence[Wave], ref_paths: Sequence[Union[Wave, Sequence[Wave]]], delay: int = 2,
+    def infer_batch(self, src_paths: Sequence[Wave], ref_paths: Sequence[Union[Wave, Sequence[Wave]]], delay: Optional[int] = None,
                     alpha: float = 1.0, spk_emb_collate_type: str = "concat_mel", noise_fns: Optional[Sequence[Callable]] = None,
                     noises_style=None, noises_timbre=None):
         """BASELINE config 3: `infer` for many (source, reference) pairs at once.  The reference is batch-1 and would call
@@ -267,6 +276,8 @@ class InferenceWrapper:
         n = len(src_paths)
         if n == 0 or len(ref_paths) != n:
             raise ValueError("one reference (or list of references) per source")
+        if delay is None:                               # `infer`'s default: whatever the model is set to
+            delay = self.model.decoder.delay if isinstance(self.model.decoder.delay, int) else 0
         eng = self.model._engine
         lib = eng.lib
         keep, streams = [], []
@@ -295,8 +306,8 @@ class InferenceWrapper:
                 _lib.check(lib.svanon_stream_create(eng.handle, getattr(self.model, "_max_seq_len", 2048), C.byref(h)))
                 streams.append(h)
                 _lib.check(lib.svanon_ar_set_delay(h, int(delay)))
-                if noise is None:                      # the library's counter-based generator: one seed per utterance
-                    _lib.check(lib.svanon_ar_set_sampling(h, 0.7, 0.7, 1000 + k))
+                if noise is None:                      # the library's counter-based generator: a fresh seed per utterance,
+                    _lib.check(lib.svanon_ar_set_sampling(h, 0.7, 0.7, new_sampler_seed()))   # drawn from torch's generator
                 keep += [rc, ra, sc, sv, tl, out, noise]
                 for lst, t in ((rc_p, rc), (ra_p, ra), (sc_p, sc), (sv_p, sv), (tl_p, tl), (out_p, out)):
                     lst.append(t.data_ptr())

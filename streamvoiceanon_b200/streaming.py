@@ -13,6 +13,13 @@ from . import _lib
 from .engine import Engine, ptr, _cuda_stream_ptr
 
 
+def new_sampler_seed() -> int:
+    """A fresh seed for the library's counter-based Exp(1) generator, drawn from torch's GLOBAL generator: the
+    reference samples from that generator (modules/dual_ar_stream.py:1095), fresh per run and per stream, and
+    `torch.manual_seed` makes it reproducible -- the same holds here."""
+    return int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
+
+
 class StreamSession:
     def __init__(self, device=None, max_seq_len: int = 2048):
         self._engine = Engine.get(device)
@@ -26,6 +33,7 @@ class StreamSession:
         self.chunk = 1
         self._noise_fn: Optional[Callable] = None
         self._step = 0
+        self.set_sampling(seed=new_sampler_seed())     # every new stream samples differently unless told otherwise
 
     def set_noise_fn(self, fn, step0: int = 0):
         self._noise_fn, self._step = fn, step0

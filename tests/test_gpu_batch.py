@@ -259,6 +259,47 @@ def test_batch_of_nine_default_windows(models, tape):
         s.close()
 
 
+def test_batch_of_128_default_windows(models, tape):
+    """BASELINE config 4's per-GPU share: 128 streams in lock-step with the CLI-default windows, so that the loop runs on
+    the GEMM tiles the headline stream count uses (M = 128 x 512 encoder rows: the 128 x 256 / 128 x 128 tensor-core tiles,
+    M = 256 decode rows) -- streams 0, 63 and 127 against the same streams run alone (which test_gpu_parity.py pins to
+    the reference): content ids and codec ids bit-exact, waveform to fp32 rounding.  Every stream has its own prompt
+    codes, speaker vectors, source and noise tape; four prompt lengths."""
+    from streamvoiceanon_b200 import BatchSession
+    _, tok, _ = models
+    n, n_chunks, check = 128, 7, (0, 63, 127)
+    cfg = dict(encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=1)
+    base = [_stream_inputs(tok, 40 + k, 66 + 7 * k, n_chunks, 1) for k in range(4)]      # four distinct prompts / sources
+
+    def inputs_of(b):
+        ref_content, _, _, _, src = base[b % 4]
+        gen = torch.Generator().manual_seed(8800 + b)
+        ref_audio = torch.randint(0, 1000, (1, 8, ref_content.numel()), generator=gen).int()
+        style, timbre = synth.synth_speaker(5300 + b)
+        return ref_content, ref_audio, style, timbre, src.roll(b % 5, dims=0) * (0.5 + 0.5 * ((b * 37) % 11) / 10.0)
+    singles = {}
+    for b in check:
+        inp = inputs_of(b)
+        sess = _session(inp, tape(9100 + b), 2)
+        sess.setup(**cfg)
+        waves = torch.cat([sess.process_chunk(inp[4][i].cuda()).cpu() for i in range(n_chunks)])
+        singles[b] = (*sess.history(), waves)
+        sess.close()
+    inputs = [inputs_of(b) for b in range(n)]
+    sessions = [_session(inp, tape(9100 + b), 2) for b, inp in enumerate(inputs)]
+    batch = BatchSession(sessions)
+    batch.setup(**cfg)
+    waves = torch.cat([batch.process_chunk(torch.stack([inp[4][i] for inp in inputs]).cuda()).cpu() for i in range(n_chunks)], dim=1)
+    for b in check:
+        src_hist, pred_hist = sessions[b].history()
+        assert torch.equal(src_hist, singles[b][0]), b
+        assert torch.equal(pred_hist, singles[b][1]), b
+        assert float(((waves[b] - singles[b][2]) ** 2).mean()) < 1e-10, b
+    batch.close()
+    for s in sessions:
+        s.close()
+
+
 def test_batch_errors(models, tape):
     from streamvoiceanon_b200 import BatchSession
     _, tok, _ = models

@@ -1,16 +1,13 @@
 """The GEMM descriptors that only the speaker encoders issue (csrc/speaker.hpp), one at a time through
 svanon_debug_gemm_taps against an fp64 product on the GPU -- the bisection tool for tests/test_zz_gpu_speaker.py:
 row-offset taps of BOTH signs (non-causal dilated convs), a thin N = 32 output written into a column slice of a wide
-concat buffer, stride-2 overlapping rows (the TDNN), an A operand that is itself a column slice (lda > K).
-
-STATUS: added after round 1's GPU minutes were spent -- not yet executed on a GPU; non-gating until its first run."""
+concat buffer, stride-2 overlapping rows (the TDNN), an A operand that is itself a column slice (lda > K)."""
 import ctypes as C
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread"),
-              pytest.mark.xfail(strict=False, reason="not yet run on a GPU (round 1 ran out of GPU minutes)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]
 
 # name, M, N, K, lda, a_row_step, taps (row offsets), ldc, c_col0, a_col0
 CASES = [

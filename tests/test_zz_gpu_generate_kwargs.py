@@ -1,18 +1,14 @@
 """`generate(..., temperature=, top_p=)` on the GPU against the UNMODIFIED reference (tests/golden/ar_generate_kwargs.npz,
 oracle/make_golden_generate_kwargs.py): the first frame is sampled with the default arguments, the later frames with
 the caller's (modules/dual_ar_stream.py:723,745-752).  Codec ids bit-exact.
-
-STATUS: added after round 1's GPU minutes were spent -- not yet executed on a GPU; non-gating until its first run
-(`xfail(strict=False)`: a pass shows as XPASS), like tests/test_zz_gpu_speaker.py."""
+"""
 import numpy as np
 import pytest
 import torch
 
 from streamvoiceanon_b200 import synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread"),
-              pytest.mark.xfail(strict=False, reason="svanon_ar_set_generate_sampling not yet run on a GPU (round 1 ran out "
-                                                     "of GPU minutes); the oracle is pinned to the same fixture on the CPU")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]
 
 
 def test_generate_sampling_kwargs_vs_reference(models, gold, tape):

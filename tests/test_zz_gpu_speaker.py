@@ -5,27 +5,35 @@ tests/golden/style_vec.npz, timbre_latent.npz, prompt_config5.npz; oracle/make_g
 
 Floating point, so tolerances instead of bit-exactness: log-mel features 1e-4 (absolute; values are O(10)), style vector
 2e-4 (values O(1); 3xTF32 tensor-core products through 52 dense layers), timbre latents 1e-4 and FSQ indices exact
-wherever the FSQ input is further than 1e-3 from a rounding boundary (the reference's own ids flip there between BLAS
-builds).  The same source was held to the same fixtures by a host build first (tests/test_speaker_hostemu.py); this file
-sorts last so that a failure here cannot hide the hot-path tests under `-x`.
+wherever the FSQ input is further than FSQ_EDGE = 2e-4 from a rounding boundary (the reference's own ids flip there
+between BLAS builds).  `_fsq_safe` prints how many tokens that masks and fails when it is more than 1 % of them (on the
+committed fixtures the closest token sits 4.7e-4 from a boundary: nothing is masked); outside the mask every index must
+be equal.  The same source was held to the same fixtures by a host build first (tests/test_speaker_hostemu.py).
 
-STATUS: written after round 1's GPU minutes were spent -- these tests have never executed on a GPU.  Until their first
-run they are non-gating (`xfail(strict=False)`: a pass shows as XPASS, a failure as XFAIL, both in the summary line) and
-carry a hard per-test timeout so that an unforeseen stall cannot hold the GPU box.  Remove both markers after the
-first green run (NEXT.md section 0)."""
+Gating: the file ran green on a B200 at the end of round 1 (31 passed); the per-test timeout stays so that a stall
+cannot hold the GPU box."""
 import numpy as np
 import pytest
 import torch
 
 from streamvoiceanon_b200 import synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread"),
-              pytest.mark.xfail(strict=False, reason="speaker-encoder CUDA path not yet run on a GPU (round 1 ran out of "
-                                                     "GPU minutes); host build of the same source is green")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]
 
 FBANK_TOL = 1e-4
 STYLE_TOL = 2e-4
 TIMBRE_TOL = 1e-4
+FSQ_EDGE = 2e-4
+
+
+def _fsq_safe(bounded, what):
+    """Tokens whose six FSQ inputs all sit further than FSQ_EDGE from a rounding boundary ([rows, 32] bool).  Prints the
+    number of masked tokens; more than 1 % of them is a failure (the comparison would be hollow)."""
+    safe = ((bounded - bounded.floor() - 0.5).abs() > FSQ_EDGE).all(dim=-1).numpy()
+    masked = int((~safe).sum())
+    print(f"[fsq mask] {what}: {masked} of {safe.size} tokens within {FSQ_EDGE} of a rounding boundary")
+    assert masked <= 0.01 * safe.size, f"{what}: {masked} of {safe.size} tokens masked (> 1 %)"
+    return safe
 
 
 @pytest.fixture(scope="module")
@@ -87,9 +95,11 @@ def test_timbre_latent_vs_reference(encoders, gold):
         assert torch.equal(lat, zq.mT)
         with torch.no_grad():                                       # which tokens sit away from a rounding boundary
             _, _, bounded = S.calculate_timbre_latent(wav, lens, sd)
-        safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
-        assert safe.mean() > 0.9
-        assert np.array_equal(idx.cpu().numpy()[:, 0][safe], g[f"indices_{name}"][:, 0][safe]), name
+        safe = _fsq_safe(bounded, f"timbre_latent[{name}]")
+        got_idx, want_idx = idx.cpu().numpy()[:, 0], g[f"indices_{name}"][:, 0]
+        print(f"[fsq mask] timbre_latent[{name}]: {int((got_idx != want_idx).sum())} mismatching tokens in all, "
+              f"{int((got_idx != want_idx)[safe].sum())} outside the mask")
+        assert np.array_equal(got_idx[safe], want_idx[safe]), name
         assert np.abs(lat.cpu().numpy() - g[f"timbre_{name}"])[safe].max() < TIMBRE_TOL, name
 
 
@@ -113,8 +123,7 @@ def test_config5_prompt_embeddings_vs_reference(encoders, gold):
     assert np.abs(sv.cpu().numpy() - gp["style_vectors"]).max() < 5e-4
     with torch.no_grad():                                           # tokens away from an FSQ rounding boundary
         _, _, bounded = S.calculate_timbre_latent(ref16.cpu(), lens, synth.make_timbre_encoder_state_dict(int(gp["weight_seed"])))
-    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
-    assert safe.mean() > 0.9
+    safe = _fsq_safe(bounded, "config5 prompt")
     assert np.abs(tl.cpu().numpy() - gp["timbre_latents"])[safe].max() < 5e-4
 
 
@@ -140,7 +149,7 @@ def test_calculate_prompt_vs_reference(encoders, models, gold):
     with torch.no_grad():
         _, _, bounded = S.calculate_timbre_latent(ref16, torch.LongTensor([ref16.shape[-1]]),
                                                   synth.make_timbre_encoder_state_dict(int(gp["weight_seed"])))
-    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
+    safe = _fsq_safe(bounded, "calculate_prompt config5")
     assert np.abs(tl.cpu().numpy() - gp["timbre_latents"])[safe].max() < 5e-4
     with pytest.raises(NotImplementedError):
         pb.calculate_prompt(refs, 1.0, "avg")
@@ -248,9 +257,10 @@ def test_speaker_encoders_full_size_vs_reference(encoders, gold):
     zq, idx = timbre.tokenize_wav(wave.cuda(), lens)
     with torch.no_grad():
         _, _, bounded = S.calculate_timbre_latent(wave, lens, synth.make_timbre_encoder_state_dict(int(g["weight_seed"])))
-    safe = ((bounded - bounded.floor() - 0.5).abs() > 1e-3).all(dim=-1).numpy()
-    assert safe.mean() > 0.9
-    assert np.array_equal(idx.cpu().numpy()[:, 0][safe], g["indices"][:, 0][safe])
+    safe = _fsq_safe(bounded, "15 s prompt")
+    got_idx, want_idx = idx.cpu().numpy()[:, 0], g["indices"][:, 0]
+    print(f"[fsq mask] 15 s prompt: {int((got_idx != want_idx).sum())} mismatching tokens in all")
+    assert np.array_equal(got_idx[safe], want_idx[safe])
     assert np.abs(zq.mT.cpu().numpy() - g["timbre"])[safe].max() < TIMBRE_TOL
     assert calculate_timbre_latent(timbre, wave.cuda(), lens).shape == (1, 32, 128)
 

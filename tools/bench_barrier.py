@@ -12,10 +12,8 @@ ar = ARVCWrapper()
 ar.setup_caches(max_batch_size=1, max_seq_len=2048, dtype=torch.float16)
 ar.load_state_dict(synth.make_ar_state_dict(1234), strict=False)
 lib = _lib.load()
-for mode in (0, 1):
-    for exchange in (0, 1):
-        ms = C.c_float()
-        iters = 2000
-        _lib.check(lib.svanon_debug_grid_barrier(ar._engine.handle, mode, iters, exchange, C.byref(ms)))
-        print(f"barrier mode {mode} ({'arrival counter' if mode == 0 else 'per-CTA epoch words'}), exchange {exchange}: "
-              f"{ms.value / iters * 1e3:.2f} us per barrier")
+for exchange in (0, 1):
+    ms = C.c_float()
+    iters = 2000
+    _lib.check(lib.svanon_debug_grid_barrier(ar._engine.handle, iters, exchange, C.byref(ms)))
+    print(f"grid barrier (arrival counter), exchange {exchange}: {ms.value / iters * 1e3:.2f} us per barrier")
