@@ -150,6 +150,15 @@ int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda
                            int taps, const int* tap_off, const float* bias, float* C, int ldc, int c_col0, int M, int N,
                            int K, void* cuda_stream);
 
+/* measurement aid (bench.py `roofline`): while enabled, EVERY GEMM launch of the library is bracketed by CUDA events on
+ * the stream it is launched on; svanon_gemm_timing_read synchronises and returns, per back end -- [0] tcgen05 3xTF32
+ * (gemm_tc.cu), [1] pipelined CUDA-core (gemm_pipe.cu), [2] register-tiled CUDA-core (gemm.cu), [3] thin-channel direct
+ * conv (conv_small.cu) -- the summed launch durations (ms), the executed 2*M*N*K*taps work (GFLOP, fp32-grade products) and
+ * the launch count since it was enabled.  The events break programmatic-dependent-launch overlap, so timed passes are
+ * slower than production passes; enable != 0 also clears the counters. */
+int svanon_gemm_timing(svanon_engine* e, int enable);
+int svanon_gemm_timing_read(svanon_engine* e, double* ms /*[4]*/, double* gflop /*[4]*/, int64_t* launches /*[4]*/);
+
 /* batch-1 decode kernel variant: 1 (default) = weights staged through shared memory with TMA bulk copies, grid
  * barriers between phases; 0 = weights loaded straight from global memory + grid barriers (what the 2- and 4-stream
  * launches use).  (Two more variants -- a barrier-free flag-in-data exchange and a per-CTA epoch-word barrier -- were

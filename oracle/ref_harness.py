@@ -1,6 +1,7 @@
 """Builds the UNMODIFIED reference models in this container.  TEST INFRASTRUCTURE ONLY.
 
-Only usable where /root/reference exists (the build container; never the GPU box).  Adds
+Usable where /root/reference exists (the build container) or where `oracle/_ref/` -- the same modules byte-compiled by
+oracle/build_ref.py, which travels to the GPU box -- is present.  Adds
 the import shims (oracle/refshim) and the reference root to sys.path, instantiates the
 three hot-path models from the reference's own YAMLs through its own
 `hydra.utils.instantiate` call pattern (evaluations/infer_arvc.py:53-54,68-69,88-89),
@@ -20,12 +21,28 @@ from pathlib import Path
 import torch
 import yaml
 
-REF_ROOT = Path(os.environ.get("SVANON_REFERENCE", "/root/reference"))
 SHIMS = Path(__file__).resolve().parent / "refshim"
+BUILT = Path(__file__).resolve().parent / "_ref"
+
+
+def _root() -> Path:
+    env = os.environ.get("SVANON_REFERENCE")
+    if env:
+        return Path(env)
+    src = Path("/root/reference")
+    return src if (src / "modules" / "arvc_wrapper.py").exists() else BUILT
+
+
+REF_ROOT = _root()
 
 
 def available() -> bool:
-    return (REF_ROOT / "modules" / "arvc_wrapper.py").exists()
+    return (REF_ROOT / "modules" / "arvc_wrapper.py").exists() or (REF_ROOT / "modules" / "arvc_wrapper.pyc").exists()
+
+
+def kind() -> str:
+    """'source' (the reference tree itself) or 'bytecode' (oracle/_ref)."""
+    return "source" if (REF_ROOT / "modules" / "arvc_wrapper.py").exists() else "bytecode"
 
 
 def _paths():

@@ -51,6 +51,8 @@ _SIGS = {
     "svanon_debug_gemm_taps": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, C.POINTER(C.c_int), _p, _p, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "svanon_ar_set_kernel_variant": (C.c_int, [_p, C.c_int]),
+    "svanon_gemm_timing": (C.c_int, [_p, C.c_int]),
+    "svanon_gemm_timing_read": (C.c_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "svanon_ar_profile": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint64)]),
     "svanon_debug_grid_barrier": (C.c_int, [_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "svanon_ar_read_debug": (C.c_int, [_p, _p, _p, _p]),

@@ -466,6 +466,24 @@ int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda
   });
 }
 
+int svanon_gemm_timing(svanon_engine* e, int enable) {
+  return guarded([&] {
+    SV_CHECK(e, "null engine");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    gemm_timing_enable(enable != 0);
+  });
+}
+
+int svanon_gemm_timing_read(svanon_engine* e, double* ms, double* gflop, int64_t* launches) {
+  return guarded([&] {
+    SV_CHECK(e && ms && gflop && launches, "null argument");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    long long n[GEMM_BACKENDS];
+    gemm_timing_read(ms, gflop, n);
+    for (int i = 0; i < GEMM_BACKENDS; ++i) launches[i] = n[i];
+  });
+}
+
 int svanon_ar_set_kernel_variant(svanon_engine* e, int variant) {
   return guarded([&] {
     SV_CHECK(e, "null engine");

@@ -163,6 +163,11 @@ __device__ __forceinline__ long long seg_row_off(long long row, int seg_rows, lo
 }
 #endif
 
+// measurement aid behind svanon_gemm_timing: per back end, summed event-timed launch durations and executed flops
+enum GemmBackend : int { GEMM_BACKEND_TC = 0, GEMM_BACKEND_PIPE = 1, GEMM_BACKEND_FP32 = 2, GEMM_BACKEND_CONV_SMALL = 3, GEMM_BACKENDS = 4 };
+void gemm_timing_enable(bool on);
+void gemm_timing_read(double* ms /*[4]*/, double* gflop /*[4]*/, long long* launches /*[4]*/);
+
 // up to 3 independent problems of identical shape run as blockIdx.z
 void launch_gemm(const GemmParams* p, int count, cudaStream_t st);
 inline void launch_gemm(const GemmParams& p, cudaStream_t st) { launch_gemm(&p, 1, st); }

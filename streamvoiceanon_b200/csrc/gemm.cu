@@ -21,6 +21,8 @@
 
 #include <algorithm>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -282,7 +284,62 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st);     // ge
 bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st);  // conv_small.cu
 bool g_use_conv_small = true;
 
+// ---- measurement aid (svanon_gemm_timing): every GEMM launch bracketed by CUDA events on its own stream, summed per
+// back end.  The events sit between consecutive kernels, so programmatic dependent launch cannot overlap a GEMM's
+// prologue with its predecessor while this is on: bench.py uses it in a separate pass, never for `value`.
+namespace {
+struct GemmTiming {
+  bool on = false;
+  struct Rec { cudaEvent_t e0, e1; int backend; double flop; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    SV_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+} g_gemm_timing;
+double gemm_flop(const GemmParams* ps, int count) {
+  double f = 0;
+  for (int i = 0; i < count; ++i) f += 2.0 * ps[i].M * ps[i].N * ps[i].K * ps[i].taps;
+  return f;
+}
+}  // namespace
+
+void gemm_timing_enable(bool on) {
+  SV_CUDA(cudaDeviceSynchronize());
+  for (auto& r : g_gemm_timing.recs) { g_gemm_timing.pool.push_back(r.e0); g_gemm_timing.pool.push_back(r.e1); }
+  g_gemm_timing.recs.clear();
+  g_gemm_timing.on = on;
+}
+void gemm_timing_read(double* ms, double* gflop, long long* launches) {
+  SV_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < GEMM_BACKENDS; ++i) { ms[i] = 0; gflop[i] = 0; launches[i] = 0; }
+  for (auto& r : g_gemm_timing.recs) {
+    float t = 0.f;
+    SV_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.backend] += t; gflop[r.backend] += r.flop * 1e-9; launches[r.backend] += 1;
+  }
+}
+
+static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t st, int* backend);
+
 void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
+  if (!g_gemm_timing.on) {
+    int backend;
+    launch_gemm_dispatch(ps, count, st, &backend);
+    return;
+  }
+  GemmTiming::Rec r{g_gemm_timing.get(), g_gemm_timing.get(), 0, gemm_flop(ps, count)};
+  SV_CUDA(cudaEventRecord(r.e0, st));
+  launch_gemm_dispatch(ps, count, st, &r.backend);
+  SV_CUDA(cudaEventRecord(r.e1, st));
+  g_gemm_timing.recs.push_back(r);
+}
+
+static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t st, int* backend) {
+  *backend = GEMM_BACKEND_FP32;
   SV_CHECK(count >= 1 && count <= 3, "gemm batch count");
   GemmBatch b;
   int min_iters = 1 << 30;
@@ -298,14 +355,17 @@ void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   const GemmParams& p = ps[0];
   if (p.M <= 0 || p.N <= 0) return;
   if (g_use_conv_small && launch_conv_small(ps, count, st)) {     // thin causal convs (HiFi-GAN levels with 16/32 channels)
+    *backend = GEMM_BACKEND_CONV_SMALL;
     SV_LAUNCHED();
     return;
   }
-  if (g_gemm_use_tc && launch_gemm_tc(ps, count, st)) {         // tcgen05 3xTF32 (M >= 96, N >= 64)
+  if (g_gemm_use_tc && launch_gemm_tc(ps, count, st)) {         // tcgen05 3xTF32 (M >= 32, N >= 64)
+    *backend = GEMM_BACKEND_TC;
     SV_LAUNCHED();
     return;
   }
   if (g_gemm_use_pipe && launch_gemm_pipe(ps, count, st)) {     // small / latency-bound problems
+    *backend = GEMM_BACKEND_PIPE;
     SV_LAUNCHED();
     return;
   }

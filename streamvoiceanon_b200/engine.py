@@ -30,6 +30,7 @@ class Engine:
         _lib.check(self.lib.svanon_engine_create(device, C.byref(h)))
         self.handle = h
         self.loaded = {0: False, 1: False, 2: False, 3: False, 4: False}
+        self._digest = {}
         import os
         mode = os.environ.get("SVANON_GEMM_MODE")        # 1 = fp32 CUDA cores, 2 = tcgen05 3xTF32 (library default)
         if mode is not None:
@@ -49,6 +50,8 @@ class Engine:
         return _ENGINES[device]
 
     def load_tensor(self, model: int, name: str, t: torch.Tensor):
+        if self.loaded[model]:              # same checkpoint loaded again (load_state_dict verified the digest): nothing to do
+            return
         t = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
         shape = (C.c_int64 * t.dim())(*t.shape)
         _lib.check(self.lib.svanon_load_tensor(self.handle, model, name.encode(), ptr(t), t.dim(), shape))
@@ -56,19 +59,38 @@ class Engine:
     def load_state_dict(self, model: int, sd: Dict[str, torch.Tensor], wanted) -> Tuple[list, list]:
         """Uploads the tensors `wanted(key)` accepts; returns (missing-from-wanted-set is checked at
         finalize by the library, unexpected = keys nobody wanted)."""
-        unexpected = []
+        unexpected, take = [], []
         for k, v in sd.items():
             if not torch.is_tensor(v) or not (v.is_floating_point()):
                 continue
             if v.dim() == 0 or v.dim() > 4:
                 continue
             if wanted(k):
-                self.load_tensor(model, k, v)
+                take.append((k, v))
             else:
                 unexpected.append(k)
+        # One engine per GPU holds ONE checkpoint per model (streams keep pointers into it).  Constructing the model
+        # objects a second time with the same checkpoint (a second InferenceWrapper, a GUI reload) is a no-op; a
+        # different checkpoint needs a new process.
+        import hashlib
+        h = hashlib.sha1()
+        for k, v in sorted(take, key=lambda kv: kv[0]):
+            f = v.detach().reshape(-1)
+            h.update(f"{k}|{tuple(v.shape)}|{float(f.double().sum()):.9e}|{float(f[0]):.9e}|{float(f[-1]):.9e};".encode())
+        digest = h.hexdigest()
+        if self.loaded[model]:
+            if digest != self._digest.get(model):
+                raise RuntimeError("this engine already holds different weights for this model: one engine per GPU and "
+                                   "process holds one checkpoint (streams point into it); start a new process to load another")
+            return unexpected
+        self._digest[model] = digest
+        for k, v in take:
+            self.load_tensor(model, k, v)
         return unexpected
 
     def finalize(self, model: int):
+        if self.loaded[model]:
+            return
         _lib.check(self.lib.svanon_finalize_weights(self.handle, model))
         self.loaded[model] = True
 

@@ -390,3 +390,43 @@ def test_speaker_encoders_full_size_oracle_vs_reference(gold):
     assert safe.mean() > 0.9
     assert np.array_equal(idx.numpy()[safe], g["indices"][:, 0][safe])
     assert np.abs(zq.numpy() - g["timbre"])[safe].max() < 1e-5
+
+
+def test_named_inputs_oracle_vs_reference(weights, gold, tape):
+    """BASELINE configs 1-2 on the inputs BASELINE.json names (tests/golden/trump_0.wav -> azuma_0.wav; fixture
+    tests/golden/config12_named.npz from the unmodified reference, oracle/make_golden_named.py): the oracle's prompt from
+    the 153-frame reference wave (codec ids, content ids exact; speaker embeddings 1e-5) and the first 10 chunks of the
+    CLI-default streaming loop (content ids and codec ids exact; waveform MSE < 1e-10).  Bounded so that the CPU suite
+    stays short; the GPU tests run all 168 chunks and the offline call."""
+    from pathlib import Path
+    from scipy.io import wavfile
+    from oracle import prompt as P
+    GOLD = Path(__file__).resolve().parent / "golden"
+    g = gold("config12_named")
+    ws = int(g["weight_seed"])
+
+    def load(name):
+        rate, data = wavfile.read(str(GOLD / name))
+        assert rate == 44100 and data.dtype == np.int16
+        x = torch.from_numpy(data.astype(np.float32) / 32768.0)
+        return (x.mean(dim=1) if x.dim() == 2 else x)[None]
+    src, ref = load("trump_0.wav"), load("azuma_0.wav")
+    assert src.shape[1] == 343483 and ref.shape[1] // 2048 == 153
+    n = 10
+    with torch.no_grad():
+        z192, z4096 = np.zeros((1, 192), np.float32), np.zeros((1, 32, 128), np.float32)
+        codes, content, style, timbre, _ = P.calculate_prompt([ref], 1.0, z192, z4096, synth.make_campplus_state_dict(ws),
+                                                              synth.make_timbre_encoder_state_dict(ws), weights["tok"],
+                                                              weights["voc_enc"])
+        assert np.array_equal(content.numpy(), g["ref_content"])
+        assert np.array_equal(codes.numpy(), g["ref_audio"])
+        assert np.abs(style.numpy() - g["style"]).max() < 1e-5
+        so = StreamOracle(weights["ar"], weights["tok"], weights["voc_folded"], tape(int(g["tape_seed"])))
+        so.prefill_prompt(codes, content, style, timbre, max_prompt_frames=256, delay=2)
+        so.setup_stream_caches(128, 64, 768, 32, 1)
+        padded = torch.nn.functional.pad(src, (2048 - src.shape[1] % 2048, 0)).view(-1, 2048)
+        assert padded.shape[0] == 168
+        wave = torch.cat([so.process_one_chunk(padded[i][None]) for i in range(n)], dim=-1)
+    assert np.array_equal(so.src_content_codes.numpy(), g["stream_src_content"][:, :n])
+    assert np.array_equal(so.pred_codes.numpy(), g["stream_pred_codes"][:, :, : n - 2])
+    assert float(((wave[0].numpy() - g["stream_wave"][: n * 2048]) ** 2).mean()) < 1e-10

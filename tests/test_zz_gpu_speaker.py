@@ -281,3 +281,70 @@ def test_infer_batch_equals_sequential_infer(encoders, models, tape):
         assert np.array_equal(got[k], want), k
     with pytest.raises(ValueError):
         iw.infer_batch(srcs, refs[:2])
+
+
+def test_engine_wrapper_named_inputs_config1_config2(encoders, models, gold, tape):
+    """BASELINE configs 1 and 2 on the inputs BASELINE.json names (tests/golden/trump_0.wav -> azuma_0.wav, 167 source /
+    153 prompt frames) through the ENGINE's InferenceWrapper (one library call per chunk, prompt path on the GPU) with the
+    CLI-default windows: `infer(..., delay=2)` and `stream_infer(..., decode_chunk_frames=1, delay=2)` against the unmodified
+    reference (tests/golden/config12_named.npz, oracle/make_golden_named.py).  Ids exact, waveform MSE < 1e-8."""
+    from pathlib import Path
+    g = gold("config12_named")
+    root = Path(__file__).resolve().parent / "golden"
+    iw = _wrapper(encoders, models)
+    iw.set_noise_fn(tape(int(g["tape_seed"])))
+    wave = iw.infer(root / "trump_0.wav", root / "azuma_0.wav", delay=2)
+    assert wave.shape == g["wave"].shape == (167 * 2048,)
+    assert float(((wave - g["wave"]) ** 2).mean()) < 1e-8
+    iw.set_noise_fn(tape(int(g["tape_seed"])))
+    stream = iw.stream_infer(root / "trump_0.wav", root / "azuma_0.wav", decode_chunk_frames=1, delay=2)
+    assert np.array_equal(iw.ref_content_codes.cpu().numpy(), g["ref_content"])
+    assert np.array_equal(iw.ref_audio_codes.cpu().numpy(), g["ref_audio"])
+    assert np.array_equal(iw.src_content_codes.numpy(), g["stream_src_content"])
+    assert np.array_equal(iw.pred_codes.numpy(), g["stream_pred_codes"])
+    assert stream.shape == g["stream_wave"].shape == (168 * 2048,)
+    assert float(((stream - g["stream_wave"]) ** 2).mean()) < 1e-8
+
+
+def test_realtime_gui_glue(encoders, models, tape):
+    """The GUI's audio path without the GUI (streamvoiceanon_b200/realtime.py, real-time-gui.py:32-49,1204-1287,1316-1359):
+    `custom_infer` == the same prompt / cache / chunk calls made by hand (windows 64/64, prompt 64, buffer 32), it
+    re-prompts when the reference name or the block size changes, and `RealtimeSession.audio_callback` (stereo input at
+    48 kHz, two-frame blocks) returns the converted block resampled to the device rate on both channels."""
+    from streamvoiceanon_b200.audio import Resampler
+    from streamvoiceanon_b200.realtime import GuiState, RealtimeSession, custom_infer
+    iw = _wrapper(encoders, models)
+    ref = synth.synth_audio_44k(5700, 3.3)
+    src = synth.synth_audio_44k(1700, 0.8)[: 7 * 2048].view(7, 2048)
+    iw.set_noise_fn(tape(7500))
+    st = GuiState()
+    got = torch.cat([custom_infer(iw, ref.numpy(), "a.wav", src[i].cuda(), n_frame_delay=2, alpha=1.0, state=st) for i in range(7)])
+    iw.set_noise_fn(tape(7500))
+    iw.prefill_prompt(ref[None].cuda(), max_prompt_frames=64, delay=2, alpha=1.0)
+    iw.setup_stream_caches(encode_window_frames=64, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=1)
+    want = torch.cat([iw.process_one_chunk(src[i][None].cuda())[0].cpu() for i in range(7)])
+    assert torch.equal(got, want) and float(got.abs().max()) > 0
+    assert st.reference_wav_name == "a.wav" and st.decode_chunk_frames == 1
+    first = custom_infer(iw, ref.numpy(), "b.wav", src[0].cuda(), n_frame_delay=2, alpha=1.0, state=st)   # new reference -> re-prompt
+    assert st.reference_wav_name == "b.wav" and float(first.abs().max()) == 0.0                             # delay warm-up again
+    custom_infer(iw, ref.numpy(), "b.wav", torch.zeros(4096).cuda(), n_frame_delay=2, alpha=1.0, state=st)   # new block size
+    assert st.decode_chunk_frames == 2
+    # the callback: 2-frame blocks, stereo, device at 48 kHz
+    iw.set_noise_fn(tape(7600))
+    rt = RealtimeSession(iw, samplerate=48000, channels=2, block_frame=2, n_frame_delay=2, alpha=1.0)
+    rt.start(ref.numpy(), "a.wav")
+    blocks = synth.synth_audio_44k(1701, 0.8)[: 3 * 4096].view(3, 4096)
+    outs = []
+    for i in range(3):
+        indata = torch.stack([blocks[i], blocks[i]], dim=1).numpy()          # [frames, channels]
+        outdata = np.zeros((4096, 2), np.float32)
+        rt.audio_callback(indata, outdata)
+        outs.append(outdata.copy())
+    iw.set_noise_fn(tape(7600))
+    st2 = GuiState()
+    res = Resampler(44100, 48000)
+    for i in range(3):
+        w = custom_infer(iw, ref.numpy(), "a.wav", blocks[i].cuda(), n_frame_delay=2, alpha=1.0, state=st2)
+        want_block = res(w)[:4096].numpy()
+        assert np.array_equal(outs[i][:, 0], want_block) and np.array_equal(outs[i][:, 1], want_block), i
+    assert float(np.abs(outs[2]).max()) > 0 and rt.infer_ms > 0

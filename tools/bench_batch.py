@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 FRAME_S = 2048 / 44100.0
 
 
-def run(B, steps=12, warm=4, enc_win=128, dec_win=64, chunk=1, prompt_s=5.0):
+def run(B, steps=12, warm=4, enc_win=128, dec_win=64, chunk=1, prompt_s=5.0, profile_steps=0):
     from streamvoiceanon_b200 import BatchSession, ContentTokenizer, StreamSession, synth
     tok = ContentTokenizer()
     sessions = []
@@ -58,6 +58,14 @@ def run(B, steps=12, warm=4, enc_win=128, dec_win=64, chunk=1, prompt_s=5.0):
         step()
         st.append(batch.last_timing())
     med = [sorted(x[j] for x in st)[2] for j in range(3)]
+    if profile_steps:                     # ncu --profile-from-start off: only these steps are profiled
+        batch.set_timing(False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(profile_steps):
+            step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     batch.close()
     for s in sessions:
         s.close()

@@ -1,4 +1,9 @@
-"""A few lock-step batch steps for `ncu --metrics gpu__time_duration.sum` (launch list of the many-stream path)."""
+"""One steady-state lock-step batch step inside a cudaProfilerStart/Stop window (many-stream path):
+
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file l.csv \
+        python tools/profile_batch.py 128
+    ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:arb_attn_slow -c 2 -o prof \
+        python tools/profile_batch.py 128"""
 import sys
 from pathlib import Path
 
@@ -15,4 +20,4 @@ if __name__ == "__main__":
     ar.load_state_dict(synth.make_ar_state_dict(1234), strict=False)
     ContentTokenizer().load_state_dict(synth.make_tokenizer_state_dict(1234), strict=False)
     Vocoder().load_state_dict(synth.make_vocoder_state_dict(1234), strict=False)
-    print(bb.run(int(sys.argv[1]), steps=1, warm=3))
+    print(bb.run(int(sys.argv[1]), steps=2, warm=4, profile_steps=1))
