@@ -81,6 +81,8 @@ def parse():
     ap.add_argument("--concurrent", default="128,160,176", help="stream-count ladder of the config-4 leg: the first entry runs on "
                     "every GPU, the rest (N=1 only) are tried in order while p99 stays under the frame period ('' = skip)")
     ap.add_argument("--concurrent-chunks", type=int, default=720, help="chunks per stream of the config-4 leg")
+    ap.add_argument("--stateful", default="256,384,512", help="stream-count ladder of the stateful-encoder leg (N=1 only; '' = skip)")
+    ap.add_argument("--stateful-chunks", type=int, default=150, help="chunks per stream of the stateful-encoder leg")
     ap.add_argument("--no-prompt-path", action="store_true", help="skip the setup-path leg (child process, N=1 only)")
     return ap.parse_args()
 
@@ -289,7 +291,7 @@ def _pct(xs, q):
     return xs[min(len(xs) - 1, int(q * len(xs)))]
 
 
-def concurrent_leg(tok, B, chunks, rank=0, warm=5):
+def concurrent_leg(tok, B, chunks, rank=0, warm=5, enc_mode=None):
     """BASELINE config 4 on this GPU: B streams advanced in lock-step by ONE library call per chunk
     (svanon_batch_process_chunk), CLI-default windows, delay 2, pinned HOST buffers in and out (each call returns after
     its device->host copy), `chunks` chunks per stream.  Reference audio of 2.8-5 s per stream (60..107 prompt frames), so
@@ -313,6 +315,8 @@ def concurrent_leg(tok, B, chunks, rank=0, warm=5):
                      timbre.cuda(), WORKLOAD["max_prompt_frames"], WORKLOAD["delay"])
         sessions.append(s)
     batch = BatchSession(sessions)
+    if enc_mode is not None:
+        batch.set_encoder_mode(enc_mode)
     batch.setup(WORKLOAD["encode_window_frames"], WORKLOAD["decode_window_frames"], WORKLOAD["max_seq_frames"],
                 WORKLOAD["buffer_frames"], 1)
     torch.cuda.synchronize()
@@ -574,6 +578,18 @@ def run_engine(args):
                 if conc[-1]["ms_per_step_p99"] >= frame_ms:
                     break
                 conc.append(concurrent_leg(tok, B, args.concurrent_chunks, rank))
+    # opt-in mode: stateful content encoder (offline-encode semantics, svanon_stream_set_encoder_mode 3), N = 1 only
+    stateful = []
+    if world == 1 and counts:
+        frame_ms = FRAME_S * 1e3
+        for B in [int(x) for x in args.stateful.split(",") if x.strip()]:
+            try:
+                stateful.append(concurrent_leg(tok, B, args.stateful_chunks, rank, enc_mode=3))
+            except Exception as exc:                                            # e.g. out of memory at a large stream count
+                stateful.append({"streams": B, "error": repr(exc)[:300]})
+                break
+            if stateful[-1]["ms_per_step_p99"] >= frame_ms:
+                break
 
     t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -658,6 +674,14 @@ def run_engine(args):
             "ladder": conc,
             "max_streams_per_gpu_p99_lt_frame_period": max([r["streams"] for r in conc if r["ms_per_step_p99"] < frame_ms], default=None),
             "max_streams_per_gpu_mean_rtf_lt_1": max([r["streams"] for r in conc if r["rtf_mean"] < 1.0], default=None)}
+    if stateful:
+        ok = [r["streams"] for r in stateful if "error" not in r and r["ms_per_step_p99"] < FRAME_S * 1e3]
+        line["concurrent_streams_stateful_encoder"] = {
+            "what": "the same lock-step loop with the STATEFUL content encoder (encoder mode 3: ids of the reference's offline "
+                    "encode() of the stream so far, 0.23 GFLOP per frame, instead of the reference's 128-frame window re-encode; "
+                    "opt-in, not the reference's streaming semantics -- include/svanon.h); host buffers; short window "
+                    f"({args.stateful_chunks} chunks: no re-prompt inside)",
+            "max_streams_per_gpu_p99_lt_frame_period": max(ok) if ok else None, "ladder": stateful}
     try:
         line["stage_compute"] = [stage_compute(med[0], med[2], 1, peaks)]
         best = [r for r in conc if r["rtf_mean"] < 1.0]

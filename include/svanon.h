@@ -203,7 +203,11 @@ int svanon_stream_set_vocoder_mode(svanon_stream* s, int incremental);
  * whole window as in the reference.  Same function of the same samples as 0 = re-encode the whole window every chunk
  * (evaluations/infer_arvc.py:495-508); used when encode_window_frames >= 2 * (40 + chunk) + 8.  With >= 8 streams side by
  * side (or mode 2: always) the newest frames do not take a 41-frame span either: they continue from PER-LAYER conv
- * history (the newest 6 rows of every causal-conv input of the stack), 4 mel rows per frame. */
+ * history (the newest 6 rows of every causal-conv input of the stack), 4 mel rows per frame.
+ * Mode 3 (opt-in, call before the first chunk) is a DIFFERENT function: the stateful encoder of svanon_enc_push_chunk --
+ * ids equal to the reference's OFFLINE encode() of the stream so far, not to its 128-frame window re-encode (which restarts
+ * from zero padding every chunk; the two agree on most frames but not bit for bit, SURVEY.md finding 4).  0.23 instead of 15-29
+ * GFLOP per frame: the setting for stream counts per GPU, not for parity with the reference's streaming loop. */
 int svanon_stream_set_encoder_mode(svanon_stream* s, int incremental);
 /* per-stage device time (CUDA events on the launching stream) of the last non-warm-up chunk:
  * ms[0] = E (window encode), ms[1] = A (decode steps), ms[2] = V (vocoder) */
@@ -261,6 +265,33 @@ int svanon_campplus_forward(svanon_engine* e, const float* feat, int64_t n_frame
 int svanon_style_vector(svanon_engine* e, const float* wave16k, int64_t n_samples, float* out, void* cuda_stream);
 int svanon_timbre_latent(svanon_engine* e, const float* wave16k, int64_t n_samples, int64_t wave_len, float* latents_out,
                          int32_t* indices_out, void* cuda_stream);
+
+/* ---- stateful stage entries (`enc_push_chunk`, `voc_push_frames`) -------------------------------
+ * An encoder stream holds, for n_streams streams side by side, what an incremental FireflyArchitecture.encode needs: the
+ * 1536-sample STFT look-back, the newest 6 rows in front of every causal conv of the stack, and a 520-slot K/V ring per
+ * transformer layer.  `svanon_enc_push_chunk` takes the NEW samples only -- wave [n_streams][n_samples_per_stream], 1..8
+ * whole frames of 2048 samples -- and writes the ids of the new frames, ids_out [n_streams][frames].  Parity target: the
+ * ids of the reference's offline `encode()` (modules/vqgan/modules/firefly_encoder.py:553-566) on each stream's whole
+ * prefix (causal-prefix equality; tests/test_gpu_stateful.py), for any stream length (RoPE positions are taken relative to
+ * a base that moves every 8192 frames; the first 8703 frames use the offline encode's absolute positions).
+ * `svanon_enc_stream_reset` starts new utterances (zero left context).
+ *
+ * A vocoder stream is the incremental vocoder of the loop on its own: per-stream causal-conv history of every layer of
+ * `quantizer.upsample` + `HiFiGANGenerator` (firefly.py:280-293).  `svanon_voc_push_frames` takes frames_per_push new
+ * code frames per stream -- codes [n_streams][8][frames_per_push] int64 -- and writes their samples, wave_out
+ * [n_streams][frames_per_push * 2048]; a fresh / reset stream starts from zero history, i.e. pushing an utterance frame by
+ * frame reproduces `svanon_voc_decode` of the whole utterance (every conv is causal). */
+typedef struct svanon_enc_stream svanon_enc_stream;
+typedef struct svanon_voc_stream svanon_voc_stream;
+int svanon_enc_stream_create(svanon_engine* e, int n_streams, svanon_enc_stream** out);
+void svanon_enc_stream_destroy(svanon_enc_stream* s);
+int svanon_enc_stream_reset(svanon_enc_stream* s, void* cuda_stream);
+int64_t svanon_enc_stream_position(const svanon_enc_stream* s);   /* content frames pushed so far */
+int svanon_enc_push_chunk(svanon_enc_stream* s, const float* wave, int n_samples_per_stream, int64_t* ids_out, void* cuda_stream);
+int svanon_voc_stream_create(svanon_engine* e, int n_streams, int frames_per_push, svanon_voc_stream** out);
+void svanon_voc_stream_destroy(svanon_voc_stream* s);
+int svanon_voc_stream_reset(svanon_voc_stream* s, void* cuda_stream);
+int svanon_voc_push_frames(svanon_voc_stream* s, const int64_t* codes, float* wave_out, void* cuda_stream);
 
 /* ---- many concurrent streams in lock-step --------------------------------------------------------------------
  * The reference is strictly batch-1 (max_batch_size=1, evaluations/infer_arvc.py:56; `x.view(1, 1, -1)`,

@@ -3,8 +3,10 @@
     python -m oracle.build_ref            # build container only (needs /root/reference)
 
 The reference is a Python program, so "compiling it from its own source files" means `py_compile`: every module of the
-hot path and of its caller (`modules/**/*.py`, `evaluations/infer_arvc.py`) becomes a sourceless `.pyc` under
-`oracle/_ref/` (same directory layout, so `import modules.dual_ar_stream` / `import evaluations.infer_arvc` resolve), and
+hot path and of its caller (`modules/**/*.py`, `evaluations/infer_arvc.py`) becomes a sourceless byte-code file under
+`oracle/_ref/` (same directory layout; suffix `.pycode` -- plain `.pyc` files are stripped from the snapshot that travels to
+the GPU box -- which `oracle/ref_harness.py` makes importable with a path hook restricted to that directory, so
+`import modules.dual_ar_stream` / `import evaluations.infer_arvc` resolve), and
 the YAML configs the reference's constructor reads (`configs/`, data files) are placed beside them.  No reference source
 enters the repository: `oracle/_ref/` is git-ignored (it travels to the GPU box with the snapshot, like the built
 `libsvanon_b200.so`), and nothing under `streamvoiceanon_b200/` imports it (tests/test_cabi.py checks).
@@ -31,11 +33,12 @@ PY_TREES = ("modules",)
 PY_FILES = ("evaluations/infer_arvc.py",)
 DATA_TREES = ("configs",)
 STAMP = "BUILD_INFO"
+SUFFIX = ".pycode"
 
 
 def is_current() -> bool:
     """True when oracle/_ref holds byte code this interpreter can import."""
-    probe = OUT / "modules" / "arvc_wrapper.pyc"
+    probe = OUT / "modules" / ("arvc_wrapper" + SUFFIX)
     if not probe.exists():
         return False
     with open(probe, "rb") as f:
@@ -54,7 +57,7 @@ def build(force: bool = False) -> Path:
         files += sorted((SRC / tree).rglob("*.py"))
     for src in files:
         rel = src.relative_to(SRC)
-        dst = (OUT / rel).with_suffix(".pyc")
+        dst = (OUT / rel).with_suffix(SUFFIX)
         dst.parent.mkdir(parents=True, exist_ok=True)
         # dfile: the path tracebacks show (the reference's own file name; the source itself is not shipped)
         py_compile.compile(str(src), cfile=str(dst), dfile=str(rel), doraise=True, optimize=0)

@@ -36,8 +36,11 @@ def _root() -> Path:
 REF_ROOT = _root()
 
 
+BYTECODE_SUFFIX = ".pycode"          # oracle/build_ref.py
+
+
 def available() -> bool:
-    return (REF_ROOT / "modules" / "arvc_wrapper.py").exists() or (REF_ROOT / "modules" / "arvc_wrapper.pyc").exists()
+    return (REF_ROOT / "modules" / "arvc_wrapper.py").exists() or (REF_ROOT / "modules" / ("arvc_wrapper" + BYTECODE_SUFFIX)).exists()
 
 
 def kind() -> str:
@@ -45,7 +48,19 @@ def kind() -> str:
     return "source" if (REF_ROOT / "modules" / "arvc_wrapper.py").exists() else "bytecode"
 
 
+def _bytecode_hook(path):
+    """sys.path_hooks entry: directories under the byte-compiled reference are searched for `<module>.pycode` files
+    (sourceless byte code, oracle/build_ref.py); every other path is left to the standard hooks."""
+    from importlib.machinery import FileFinder, SourcelessFileLoader
+    if not os.path.abspath(path).startswith(str(REF_ROOT)):
+        raise ImportError
+    return FileFinder(path, (SourcelessFileLoader, [BYTECODE_SUFFIX]))
+
+
 def _paths():
+    if kind() == "bytecode" and _bytecode_hook not in sys.path_hooks:
+        sys.path_hooks.insert(0, _bytecode_hook)
+        sys.path_importer_cache.clear()
     for p in (str(SHIMS), str(REF_ROOT)):
         if p not in sys.path:
             sys.path.insert(0, p)

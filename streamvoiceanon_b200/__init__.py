@@ -6,6 +6,8 @@ library (include/svanon.h, streamvoiceanon_b200/libsvanon_b200.so):
     ARVCWrapper        <-> modules.arvc_wrapper.ARVCWrapper
     ContentTokenizer   <-> modules.vqgan.modules.firefly_encoder.FireflyArchitecture   (encode)
     Vocoder            <-> modules.vqgan.modules.firefly.FireflyArchitecture           (quantizer.decode, head)
+    EncoderStream      <-> incremental `encode` (new samples in, new ids out; offline-encode semantics)       [stateful entries,
+    VocoderStream      <-> incremental `head(quantizer.decode(.))` (new code frames in, new samples out)       SURVEY 8b]
     StreamSession      <-> InferenceWrapper.process_one_chunk as one library call per chunk
     BatchSession       <-> the same loop for N concurrent streams in lock-step (the reference is batch-1)
     StreamPool         <-> streams that join / leave at any chunk boundary, grouped into lock-step cohorts
@@ -14,7 +16,7 @@ library (include/svanon.h, streamvoiceanon_b200/libsvanon_b200.so):
 """
 from . import synth  # noqa: F401
 
-__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "StreamSession", "BatchSession", "StreamPool", "InferenceWrapper",
+__all__ = ["ARVCWrapper", "ContentTokenizer", "Vocoder", "EncoderStream", "VocoderStream", "StreamSession", "BatchSession", "StreamPool", "InferenceWrapper",
            "synth"]
 
 
@@ -22,7 +24,7 @@ def __getattr__(name):
     if name == "ARVCWrapper":
         from .arvc_wrapper import ARVCWrapper
         return ARVCWrapper
-    if name in ("ContentTokenizer", "Vocoder"):
+    if name in ("ContentTokenizer", "Vocoder", "EncoderStream", "VocoderStream"):
         from . import firefly
         return getattr(firefly, name)
     if name in ("StreamSession", "BatchSession"):

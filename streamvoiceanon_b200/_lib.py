@@ -81,6 +81,15 @@ _SIGS = {
     "svanon_batch_set_ar_path": (C.c_int, [_p, C.c_int]),
     "svanon_batch_set_timing": (C.c_int, [_p, C.c_int]),
     "svanon_batch_last_timing": (C.c_int, [_p, C.POINTER(C.c_float)]),
+    "svanon_enc_stream_create": (C.c_int, [_p, C.c_int, C.POINTER(_p)]),
+    "svanon_enc_stream_destroy": (None, [_p]),
+    "svanon_enc_stream_reset": (C.c_int, [_p, _p]),
+    "svanon_enc_stream_position": (C.c_int64, [_p]),
+    "svanon_enc_push_chunk": (C.c_int, [_p, _p, C.c_int, _p, _p]),
+    "svanon_voc_stream_create": (C.c_int, [_p, C.c_int, C.c_int, C.POINTER(_p)]),
+    "svanon_voc_stream_destroy": (None, [_p]),
+    "svanon_voc_stream_reset": (C.c_int, [_p, _p]),
+    "svanon_voc_push_frames": (C.c_int, [_p, _p, _p, _p]),
 }
 
 

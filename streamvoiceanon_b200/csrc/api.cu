@@ -572,6 +572,7 @@ int svanon_stream_setup(svanon_stream* sh, int enc_win, int dec_win, int max_seq
     s.wave_win_dev = dmalloc<float>((size_t)dec_win * SAMPLES_PER_FRAME);
     s.n_src = 0; s.n_pred = 0; s.delay_prefilled = false;
     s.enc_state.valid = false;
+    if (s.enc_stream.wave) s.eng->enc_stream_reset(s.enc_stream, nullptr);
     // incremental vocoder when the window leaves >= 15 frames of history in front of the new chunk
     s.voc_incremental = s.voc_mode != 0 && (dec_win - chunk >= 15) && (std::min(dec_win - chunk, 24) / chunk * chunk >= 15);
     s.voc_fed = 0;
@@ -603,7 +604,10 @@ int svanon_stream_process_chunk(svanon_stream* sh, const float* wave_chunk, int 
     // 2. E: re-encode the whole window, keep the last `chunk` ids (:505-518)
     s.ev_valid = false;
     if (s.timing) SV_CUDA(cudaEventRecord(s.ev[0], st));
-    if (s.enc_state.enabled) e.enc_window_step(s.enc_state, s.wave_ring, 1, s.enc_win, s.chunk, s.ids_win_dev, st);
+    if (s.enc_stateful) {
+      if (s.enc_stream.B != 1) e.enc_stream_init(s.enc_stream, 1);
+      e.enc_push(s.enc_stream, wc, n, s.chunk, s.ids_win_dev + (s.enc_win - s.chunk), s.enc_win, st);
+    } else if (s.enc_state.enabled) e.enc_window_step(s.enc_state, s.wave_ring, 1, s.enc_win, s.chunk, s.ids_win_dev, st);
     else e.enc_encode(s.wave_ring, 1, (long long)nw, s.ids_win_dev, st);
     if (s.timing) SV_CUDA(cudaEventRecord(s.ev[1], st));
     if (s.n_src + s.chunk > HIST_CAP) {
@@ -689,10 +693,13 @@ int svanon_stream_set_vocoder_mode(svanon_stream* sh, int incremental) {
 int svanon_stream_set_encoder_mode(svanon_stream* sh, int incremental) {
   return guarded([&] {
     SV_CHECK(sh, "null stream");
-    SV_CHECK(incremental >= 0 && incremental <= 2, "encoder mode: 0 full re-encode, 1 ring-buffer state (auto), 2 + conv history");
+    SV_CHECK(incremental >= 0 && incremental <= 3, "encoder mode: 0 full re-encode, 1 ring-buffer state (auto), 2 + conv history, "
+                                                   "3 stateful (offline-encode semantics)");
+    SV_CHECK(incremental != 3 || sh->st.n_src == 0, "switch to the stateful encoder before the first chunk");
     sh->st.enc_state.enabled = incremental != 0;
     sh->st.enc_state.tail_hist_min_streams = incremental == 2 ? 1 : 8;
     sh->st.enc_state.valid = false;
+    sh->st.enc_stateful = incremental == 3;
   });
 }
 

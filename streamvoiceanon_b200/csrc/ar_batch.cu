@@ -13,6 +13,9 @@
 
 namespace svanon {
 
+void launch_arb_attn_slow_tma(const ArBatchSlot* slots, const float* qkv, float* y, const float* rope, int layer, int max_seq,
+                              int B, bool kv_half, cudaStream_t st);      // ar_attn_tma.cu
+
 using namespace ardec;
 
 namespace {
@@ -181,6 +184,13 @@ __global__ void __launch_bounds__(256) arb_finish_kernel(const ArBatchSlot* __re
   if (s.pred_hist && threadIdx.x < AR_CODEBOOKS) s.pred_hist[(long long)threadIdx.x * s.pred_ld + s.pred_col] = code[threadIdx.x];
 }
 
+// 1 (default): the TMA-staged warp-specialised kernel of ar_attn_tma.cu; 0: the warp-per-key kernel above (kept for
+// A/B measurements: SVANON_ATTN_TMA=0)
+bool use_attn_tma() {
+  static const bool on = [] { const char* e = getenv("SVANON_ATTN_TMA"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
 void gemm(const float* A, long long lda, const float* W, float* C, long long ldc, const float* residual, int M, int N, int K,
           cudaStream_t st) {
   GemmParams p;
@@ -256,6 +266,8 @@ void Engine::ar_decode_step_gemm(Stream* const* streams, int batch, cudaStream_t
     if (fast) {
       launch_pdl(arb_attn_fast_kernel, dim3((B * AR_HEADS + 3) / 4), dim3(128), 0, st, sd, (const float*)arb.qkv, arb.y,
                  ar.fast_rope, li, cb, B * AR_HEADS);
+    } else if (use_attn_tma()) {
+      launch_arb_attn_slow_tma(sd, arb.qkv, arb.y, ar.rope, li, max_seq, B, false, st);
     } else {
       launch_pdl(arb_attn_slow_kernel, dim3(AR_HEADS, B), dim3(ATT_WARPS * 32), 0, st, sd, (const float*)arb.qkv, arb.y,
                  ar.rope, li, max_seq);

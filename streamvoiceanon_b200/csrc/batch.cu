@@ -19,6 +19,8 @@ struct svanon_batch {
   long long* step_ids = nullptr;                          // [chunk][n] content ids of this chunk, step-major
   VocState voc;
   EncWindowState enc_state;
+  EncStream enc_stream;                                   // encoder mode 3 (stateful, offline-encode semantics)
+  bool enc_stateful = false;
   struct SlotPtrs {                                       // static per-stream pointers (device table)
     long long* src_hist;
     int* pred_hist;
@@ -218,6 +220,7 @@ int svanon_batch_setup(svanon_batch* b, int enc_win, int dec_win, int max_seq_fr
     SV_CUDA(cudaMemcpy(b->ptrs_dev, ptrs.data(), (size_t)n * sizeof(SlotPtrs), cudaMemcpyHostToDevice));
     b->n_src = 0; b->n_pred = 0; b->voc_fed = 0; b->delay_prefilled = false;
     b->enc_state.valid = false;
+    if (b->enc_stream.wave) e.enc_stream_reset(b->enc_stream, nullptr);
     e.voc_state_init(b->voc, chunk, n);
   });
 }
@@ -250,7 +253,10 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     // 2. E: all windows side by side, keep the last `chunk` ids of each (:505-518)
     b->ev_valid = false;
     if (b->timing) SV_CUDA(cudaEventRecord(b->ev[0], st));
-    if (b->enc_state.enabled) e.enc_window_step(b->enc_state, b->wave_ring, n, b->enc_win, c, b->ids_win, st);
+    if (b->enc_stateful) {
+      if (b->enc_stream.B != n) e.enc_stream_init(b->enc_stream, n);
+      e.enc_push(b->enc_stream, wc, n_samples, c, b->ids_win + (b->enc_win - c), b->enc_win, st);
+    } else if (b->enc_state.enabled) e.enc_window_step(b->enc_state, b->wave_ring, n, b->enc_win, c, b->ids_win, st);
     else e.enc_encode(b->wave_ring, n, (long long)nw, b->ids_win, st);
     if (b->timing) SV_CUDA(cudaEventRecord(b->ev[1], st));
     if (b->n_src + c > HIST_CAP) {
@@ -346,10 +352,13 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
 int svanon_batch_set_encoder_mode(svanon_batch* b, int incremental) {
   return guarded([&] {
     SV_CHECK(b, "null batch");
-    SV_CHECK(incremental >= 0 && incremental <= 2, "encoder mode: 0 full re-encode, 1 ring-buffer state (auto), 2 + conv history");
+    SV_CHECK(incremental >= 0 && incremental <= 3, "encoder mode: 0 full re-encode, 1 ring-buffer state (auto), 2 + conv history, "
+                                                   "3 stateful (offline-encode semantics)");
+    SV_CHECK(incremental != 3 || b->n_src == 0, "switch to the stateful encoder before the first chunk");
     b->enc_state.enabled = incremental != 0;
     b->enc_state.tail_hist_min_streams = incremental == 2 ? 1 : 8;
     b->enc_state.valid = false;
+    b->enc_stateful = incremental == 3;
   });
 }
 

@@ -318,6 +318,10 @@ void Engine::finalize_tokenizer() {
   enc_norm_w = g("quantizer.pre_module.norm.weight");
   expect_shape(get(M, "quantizer.pre_module.freqs_cis"), {2048, HEAD_DIM / 2, 2}, "quantizer.pre_module.freqs_cis");
   enc_rope = g("quantizer.pre_module.freqs_cis");
+  if (has(M, "quantizer.pre_module.freqs_cis_stream")) {
+    expect_shape(get(M, "quantizer.pre_module.freqs_cis_stream"), {ENC_ROPE_STREAM_ROWS, HEAD_DIM / 2, 2}, "freqs_cis_stream");
+    enc_rope_stream = g("quantizer.pre_module.freqs_cis_stream");
+  }
   expect_shape(get(M, "quantizer.residual_bsq.rvqs.0.project_in.weight"), {BSQ_BITS, ENC_DIM}, "bsq project_in");
   bsq_w = g("quantizer.residual_bsq.rvqs.0.project_in.weight");
   bsq_b = g("quantizer.residual_bsq.rvqs.0.project_in.bias");

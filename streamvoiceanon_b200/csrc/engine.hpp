@@ -171,6 +171,23 @@ struct EncWindowState {
   }
 };
 
+// Stateful content encoder (enc_stream.cu): B streams side by side that are fed their NEW samples only.
+constexpr int ENC_RING = 520;                 // K/V ring slots per (layer, stream, head): 512-token window + <= 8 tokens of a push
+constexpr int ENC_POS_PERIOD = 8192;          // RoPE position base moves in steps of this many frames
+constexpr int ENC_ROPE_STREAM_ROWS = ENC_POS_PERIOD + 1024;
+constexpr int ENC_STREAM_WAVE = (N_FFT - HOP) + 8 * SAMPLES_PER_FRAME;   // wave staging per stream: look-back + one push
+struct EncStream {
+  int B = 0;
+  long long pos = 0;                          // content frames pushed so far (all B streams advance together)
+  ConvStackHist hist;                         // per-layer causal-conv history
+  float* wave = nullptr;                      // [B][ENC_STREAM_WAVE]
+  float *kc = nullptr, *vc = nullptr;         // [ENC_LAYERS][B][ENC_HEADS][ENC_RING][64], keys UNROTATED
+  EncStream() = default;
+  EncStream(const EncStream&) = delete;
+  EncStream& operator=(const EncStream&) = delete;
+  ~EncStream();
+};
+
 constexpr int HIST_CAP = 4096;     // columns kept of src_content_codes / pred_codes (the reference trims to 2048)
 
 struct Stream {
@@ -211,6 +228,8 @@ struct Stream {
   long long* codes_win_dev = nullptr;     // [8][dec_win]
   float* wave_win_dev = nullptr;          // [dec_win*2048]
   EncWindowState enc_state;               // conv-stack outputs of the last window (Engine::enc_window_step)
+  EncStream enc_stream;                   // encoder mode 3: stateful encoder (offline-encode semantics), enc_stream.cu
+  bool enc_stateful = false;
   VocState voc;                           // incremental vocoder state (used when dec_win >= 16)
   int voc_mode = 1;                       // 1: incremental when possible, 0: always recompute the window
   bool voc_incremental = false;
@@ -249,6 +268,7 @@ struct Engine {
   ConvStackW tok_cs;                                  // tokenizer conv stack
   EncLayerW enc_layers[ENC_LAYERS];
   const float *enc_norm_w = nullptr, *enc_rope = nullptr, *bsq_w = nullptr, *bsq_b = nullptr;
+  const float* enc_rope_stream = nullptr;             // [ENC_ROPE_STREAM_ROWS][32][2], same formula (optional: stateful encoder)
 
   // ---- vocoder
   const float *fsq_w = nullptr, *fsq_b = nullptr;
@@ -292,6 +312,10 @@ struct Engine {
   // the window re-encode of the streaming loop with the conv-stack outputs kept between chunks (wave_ring [B][S*2048])
   void enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,
                        cudaStream_t st);
+  // stateful encoder (enc_stream.cu): c new frames per stream -> their ids (ids[b * ids_ld + j])
+  void enc_stream_init(EncStream& es, int B);
+  void enc_stream_reset(EncStream& es, cudaStream_t st);
+  void enc_push(EncStream& es, const float* wave_chunk, long long pitch, int c, long long* ids, long long ids_ld, cudaStream_t st);
   void voc_quantizer_decode(const long long* codes_dev, long long ld, int T, float* z_dev /*[4T][512]*/, cudaStream_t st);
   void voc_head(const float* z_dev /*[L][512]*/, int L, float* wave_dev /*[512 L]*/, cudaStream_t st);
   void voc_decode(const long long* codes_dev, long long ld, int T, float* wave_dev, cudaStream_t st);

@@ -52,6 +52,8 @@ class ContentTokenizer(_Shim):
         eng.load_tensor(_lib.MODEL_TOKENIZER, "quantizer.pre_module.freqs_cis",
                         fc.float() if fc is not None else rope_table(2048))
         eng.load_tensor(_lib.MODEL_TOKENIZER, "spec_transform.fb", slaney_fbanks())
+        # the stateful encoder (EncoderStream / encoder mode 3) runs past the reference's 2048-entry table: same formula, longer
+        eng.load_tensor(_lib.MODEL_TOKENIZER, "quantizer.pre_module.freqs_cis_stream", rope_table(8192 + 1024))
         eng.finalize(_lib.MODEL_TOKENIZER)
         unexpected = [k for k in unexpected if not k.startswith(("head.", "quantizer.post_module.", "quantizer.pre_module.",
                                                                  "quantizer.residual_bsq."))]
@@ -208,3 +210,90 @@ class Vocoder(_Shim):
             c = codes[b].to(torch.int64).contiguous()
             _lib.check(eng.lib.svanon_voc_decode(eng.handle, ptr(c), T, ptr(wave[b]), C.c_void_p(_cuda_stream_ptr())))
         return wave
+
+
+class EncoderStream:
+    """Stateful content encoder for `n_streams` streams side by side (SURVEY section 8b `enc_push_chunk`): feed each stream's
+    NEW samples, get the ids of its new content frames.  Ids equal the reference's OFFLINE
+    `FireflyArchitecture.encode()` (firefly_encoder.py:553-566) of the stream so far -- not the streaming loop's 128-frame
+    window re-encode, which restarts from zero padding every chunk (SURVEY finding 4).
+
+        es = EncoderStream(tokenizer, n_streams=4)
+        ids = es.push(wave)            # wave [4, k * 2048] (k = 1..8 frames), host or device -> int64 [4, k]
+        es.reset()                     # new utterances
+    """
+
+    def __init__(self, tokenizer: ContentTokenizer, n_streams: int = 1):
+        self._engine = tokenizer._engine
+        if not self._engine.loaded[_lib.MODEL_TOKENIZER]:
+            raise RuntimeError("load the tokenizer weights first (ContentTokenizer.load_state_dict)")
+        h = C.c_void_p()
+        _lib.check(self._engine.lib.svanon_enc_stream_create(self._engine.handle, int(n_streams), C.byref(h)))
+        self._h, self.n_streams = h, int(n_streams)
+
+    @property
+    def position(self) -> int:
+        return int(self._engine.lib.svanon_enc_stream_position(self._h))
+
+    @torch.no_grad()
+    def push(self, wave: torch.Tensor) -> torch.Tensor:
+        w = wave.reshape(self.n_streams, -1).float().contiguous()
+        if w.shape[1] % 2048 or not 1 <= w.shape[1] // 2048 <= 8:
+            raise ValueError("a push holds 1..8 whole frames of 2048 samples per stream")
+        ids = torch.empty(self.n_streams, w.shape[1] // 2048, dtype=torch.int64, device=w.device)
+        _lib.check(self._engine.lib.svanon_enc_push_chunk(self._h, ptr(w), w.shape[1], ptr(ids), C.c_void_p(_cuda_stream_ptr())))
+        return ids
+
+    def reset(self):
+        _lib.check(self._engine.lib.svanon_enc_stream_reset(self._h, C.c_void_p(_cuda_stream_ptr())))
+
+    def close(self):
+        if self._h is not None:
+            self._engine.lib.svanon_enc_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VocoderStream:
+    """Stateful vocoder for `n_streams` streams side by side (SURVEY section 8b `voc_push_frames`): feed `frames_per_push` new
+    code frames per stream, get their samples.  Pushing an utterance frame by frame reproduces `Vocoder.head(quantizer.decode(
+    codes))` of the whole utterance (every conv of firefly.py:280-293 is causal; per-layer history is kept on the device).
+
+        vs = VocoderStream(vocoder, n_streams=2, frames_per_push=1)
+        wave = vs.push(codes)          # codes [2, 8, 1] int -> float32 [2, 2048]
+    """
+
+    def __init__(self, vocoder: Vocoder, n_streams: int = 1, frames_per_push: int = 1):
+        self._engine = vocoder._engine
+        if not self._engine.loaded[_lib.MODEL_VOCODER]:
+            raise RuntimeError("load the vocoder weights first (Vocoder.load_state_dict)")
+        h = C.c_void_p()
+        _lib.check(self._engine.lib.svanon_voc_stream_create(self._engine.handle, int(n_streams), int(frames_per_push), C.byref(h)))
+        self._h, self.n_streams, self.frames = h, int(n_streams), int(frames_per_push)
+
+    @torch.no_grad()
+    def push(self, codes: torch.Tensor) -> torch.Tensor:
+        c = codes.reshape(self.n_streams, 8, self.frames).to(torch.int64).contiguous()
+        dev = c.device
+        out = torch.empty(self.n_streams, self.frames * 2048, dtype=torch.float32, device=dev)
+        _lib.check(self._engine.lib.svanon_voc_push_frames(self._h, ptr(c), ptr(out), C.c_void_p(_cuda_stream_ptr())))
+        return out
+
+    def reset(self):
+        _lib.check(self._engine.lib.svanon_voc_stream_reset(self._h, C.c_void_p(_cuda_stream_ptr())))
+
+    def close(self):
+        if self._h is not None:
+            self._engine.lib.svanon_voc_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -102,7 +102,9 @@ class StreamSession:
     def set_encoder_mode(self, incremental=True):
         """True / 1 (default): keep the conv-stack outputs of the window between chunks (ring-buffer state); False / 0:
         re-encode the whole window every chunk like the reference; 2: additionally continue the newest frames from
-        per-layer conv history (what batches of >= 8 streams do on their own).  Same result."""
+        per-layer conv history (what batches of >= 8 streams do on their own).  Same result.
+        3 (before the first chunk): the STATEFUL encoder -- a different function: ids of the reference's offline `encode()`
+        of the stream so far instead of its 128-frame window re-encode (include/svanon.h); 0.23 GFLOP per frame."""
         _lib.check(self._engine.lib.svanon_stream_set_encoder_mode(self._h, int(incremental)))
 
     def set_timing(self, enable: bool = True):

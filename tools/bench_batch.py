@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 FRAME_S = 2048 / 44100.0
 
 
-def run(B, steps=12, warm=4, enc_win=128, dec_win=64, chunk=1, prompt_s=5.0, profile_steps=0):
+def run(B, steps=12, warm=4, enc_win=128, dec_win=64, chunk=1, prompt_s=5.0, profile_steps=0, advance=0):
     from streamvoiceanon_b200 import BatchSession, ContentTokenizer, StreamSession, synth
     tok = ContentTokenizer()
     sessions = []
@@ -40,7 +40,7 @@ def run(B, steps=12, warm=4, enc_win=128, dec_win=64, chunk=1, prompt_s=5.0, pro
         i = it % (40 // chunk)
         batch.process_chunk(src[:, i * chunk * 2048:(i + 1) * chunk * 2048], out)
         it += 1
-    for _ in range(warm):
+    for _ in range(warm + advance):       # `advance`: grow the KV caches before measuring (S_valid += 2 per step)
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

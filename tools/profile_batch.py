@@ -3,7 +3,7 @@
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file l.csv \
         python tools/profile_batch.py 128
     ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:arb_attn_slow -c 2 -o prof \
-        python tools/profile_batch.py 128"""
+        python tools/profile_batch.py 128 [prompt seconds, default 5] [steps to advance before the window, default 0]"""
 import sys
 from pathlib import Path
 
@@ -20,4 +20,6 @@ if __name__ == "__main__":
     ar.load_state_dict(synth.make_ar_state_dict(1234), strict=False)
     ContentTokenizer().load_state_dict(synth.make_tokenizer_state_dict(1234), strict=False)
     Vocoder().load_state_dict(synth.make_vocoder_state_dict(1234), strict=False)
-    print(bb.run(int(sys.argv[1]), steps=2, warm=4, profile_steps=1))
+    prompt_s = float(sys.argv[2]) if len(sys.argv) > 2 else 5.0
+    advance = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    print(bb.run(int(sys.argv[1]), steps=2, warm=4, profile_steps=1, prompt_s=prompt_s, advance=advance))
