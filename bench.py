@@ -83,6 +83,8 @@ def parse():
     ap.add_argument("--concurrent-chunks", type=int, default=720, help="chunks per stream of the config-4 leg")
     ap.add_argument("--stateful", default="256,384,512", help="stream-count ladder of the stateful-encoder leg (N=1 only; '' = skip)")
     ap.add_argument("--stateful-chunks", type=int, default=150, help="chunks per stream of the stateful-encoder leg")
+    ap.add_argument("--perf", default="128,192,256", help="stream-count ladder of the perf-mode leg, window encoder (N=1 only; '' = skip)")
+    ap.add_argument("--perf-stateful", default="384,512,768", help="the same with the stateful encoder")
     ap.add_argument("--no-prompt-path", action="store_true", help="skip the setup-path leg (child process, N=1 only)")
     return ap.parse_args()
 
@@ -380,6 +382,43 @@ def concurrent_leg(tok, B, chunks, rank=0, warm=5, enc_mode=None):
             "stage_ms": {"E": st[0], "A": st[1], "V": st[2]}, "setup_s": t_setup}
 
 
+def perf_mode_leg(tok, args, rank):
+    """PERF mode beside the parity-mode line, never instead of it: the many-stream loop with fp16 single-pass tensor-core
+    GEMMs (svanon_set_precision 1 -- the reference's own GPU precision: fp16 autocast, evaluations/infer_arvc.py:493), with
+    the window encoder and with the stateful encoder, plus what the mode costs in fidelity (tools/eval_perf_mode.py in a child
+    process: content-id agreement, teacher-forced codec-id agreement, fast-head logit error, vocoder SNR vs parity mode)."""
+    from streamvoiceanon_b200.engine import Engine
+    eng = Engine.get(torch.cuda.current_device())
+    frame_ms = FRAME_S * 1e3
+    out = {"what": "svanon_set_precision(1): one kind::f16 tcgen05 pass per GEMM (activations rounded to fp16 on the way into the "
+                   "tensor core, fp16 weight copies, fp32 accumulation) instead of the 3xTF32 split; ids are NOT bit-exact in this "
+                   "mode (see `fidelity`); the headline `value` / `e2e` / `concurrent_streams` above are parity mode",
+           "dtype": "f16 operands, f32 accumulate", "window_encoder": [], "stateful_encoder": []}
+    eng.set_precision(1)
+    try:
+        for key, ladder, mode in (("window_encoder", args.perf, None), ("stateful_encoder", args.perf_stateful, 3)):
+            for B in [int(x) for x in ladder.split(",") if x.strip()]:
+                try:
+                    out[key].append(concurrent_leg(tok, B, args.stateful_chunks, rank, enc_mode=mode))
+                except Exception as exc:
+                    out[key].append({"streams": B, "error": repr(exc)[:300]})
+                    break
+                if out[key][-1]["ms_per_step_p99"] >= frame_ms:
+                    break
+            ok = [r["streams"] for r in out[key] if "error" not in r and r["ms_per_step_p99"] < frame_ms]
+            out[f"max_streams_per_gpu_p99_lt_frame_period_{key}"] = max(ok) if ok else None
+    finally:
+        eng.set_precision(0)
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "eval_perf_mode.py"), "32", "40"], capture_output=True, text=True,
+                           timeout=240)
+        rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        out["fidelity"] = json.loads(rows[-1]) if rows else {"unavailable": (r.stderr or r.stdout).strip().splitlines()[-1:][:1]}
+    except Exception as exc:
+        out["fidelity"] = {"unavailable": repr(exc)[:300]}
+    return out
+
+
 def gemm_roofline(peaks):
     """Tensor-pipe roofline of the dense-projection GEMM kernel (gemm_tc.cu) on the many-stream encoder MLP shape
     (M = 16384 rows = 32 streams x 512, N = 2048, K = 512, +bias, GELU), timed live with CUDA events.  Every fp32-grade
@@ -591,6 +630,11 @@ def run_engine(args):
             if stateful[-1]["ms_per_step_p99"] >= frame_ms:
                 break
 
+    # opt-in PERF mode (svanon_set_precision 1: fp16 single-pass tensor-core GEMMs, the reference's own GPU precision), N = 1
+    perf_mode = None
+    if world == 1 and counts and (args.perf or args.perf_stateful):
+        perf_mode = perf_mode_leg(tok, args, rank)
+
     t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -682,6 +726,8 @@ def run_engine(args):
                     "opt-in, not the reference's streaming semantics -- include/svanon.h); host buffers; short window "
                     f"({args.stateful_chunks} chunks: no re-prompt inside)",
             "max_streams_per_gpu_p99_lt_frame_period": max(ok) if ok else None, "ladder": stateful}
+    if perf_mode:
+        line["perf_mode"] = perf_mode
     try:
         line["stage_compute"] = [stage_compute(med[0], med[2], 1, peaks)]
         best = [r for r in conc if r["rtf_mean"] < 1.0]

@@ -136,6 +136,14 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable);
  * 0 = the register double-buffered CUDA-core kernel only.  `svanon_debug_gemm` runs one C = act(A W^T + bias)
  * (A [M][K], W [N][K], row-major fp32, K % 16 == 0; act 0 none / 1 GELU) through the selected back end (tests). */
 int svanon_set_gemm_mode(int mode);
+/* Precision of the tensor-core GEMMs (process-wide): 0 (default) = PARITY mode, fp32-grade products through the 3xTF32
+ * split -- token ids bit-exact against the fp32 reference; 1 = PERF mode at the reference's own GPU precision (fp16 autocast
+ * for linears and convs, evaluations/infer_arvc.py:493): one kind::f16 tcgen05 pass with fp32 accumulation -- activations are
+ * rounded to fp16 on the way into the tensor core (they stay fp32 in HBM), weights come from fp16 copies made once per weight on
+ * first use.  Ids are no longer bit-exact: bench.py reports the id-agreement rate and the teacher-forced logit error of this
+ * mode beside the parity-mode numbers, never instead of them.  GEMMs that run on CUDA cores (M < 32, thin channels) and the
+ * single-stream persistent decode kernel are unaffected. */
+int svanon_set_precision(int mode);
 /* programmatic dependent launch of the GEMM kernels (default on): a GEMM's launch and weight-only prologue overlap
  * the tail of the kernel before it; it blocks in griddepcontrol.wait before touching activations */
 int svanon_set_pdl(int enable);

@@ -429,6 +429,13 @@ int svanon_set_gemm_mode(int mode) {
   });
 }
 
+int svanon_set_precision(int mode) {
+  return guarded([&] {
+    SV_CHECK(mode == 0 || mode == 1, "precision: 0 = fp32-grade (3xTF32 split, parity mode), 1 = fp16 single-pass tensor-core GEMMs (perf mode)");
+    g_gemm_half = mode == 1;
+  });
+}
+
 int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                       int act, void* stream) {
   return guarded([&] {
@@ -438,6 +445,7 @@ int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const fl
     p.A = a.in(A, (size_t)M * K); p.W = a.in(W, (size_t)N * K); p.bias = a.in(bias, (size_t)N);
     p.C = a.out(C, (size_t)M * N);
     p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N; p.act = act;
+    p.w_static = false;                    // caller memory: never cached as an fp16 weight copy
     launch_gemm(p, a.st);
     a.finish();
 #ifdef SVANON_TC_PROF
@@ -462,6 +470,7 @@ int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda
     p.A = A + (long long)a_row0 * lda; p.W = W; p.bias = bias; p.C = C + c_col0;
     p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.a_row_step = a_row_step; p.taps = taps;
     for (int t = 0; t < taps; ++t) p.tap_off[t] = tap_off[t];
+    p.w_static = false;
     launch_gemm(p, (cudaStream_t)stream);
   });
 }

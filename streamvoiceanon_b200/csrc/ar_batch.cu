@@ -297,6 +297,9 @@ void Engine::ar_decode_step_gemm(Stream* const* streams, int batch, cudaStream_t
     for (int l = 0; l < AR_FAST_LAYERS; ++l) layer(ar.fast[l], arb.xf, B, l, true, cb);
     launch_rmsnorm(arb.xf, arb.nrm, ar.fast_norm_w, B, AR_DIM, AR_NORM_EPS, st);
     gemm(arb.nrm, AR_DIM, ar.fast_output_w, arb.logits, 1024, nullptr, B, AR_CB_SIZE, AR_DIM, st);
+    if (debug_logits)        // test / evaluation hook: the fast-head logits of stream 0 (svanon_ar_read_debug)
+      SV_CUDA(cudaMemcpyAsync(dbg_fast_logits + (size_t)cb * AR_CB_SIZE, arb.logits, AR_CB_SIZE * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
     launch_pdl(arb_sample_kernel, dim3(B), dim3(NT), 0, st, sd, (const float*)arb.logits, ar.fast_emb, arb.xf, cb);
     SV_LAUNCHED();
   }

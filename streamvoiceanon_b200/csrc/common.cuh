@@ -129,6 +129,10 @@ struct GemmParams {
   // the base pointer (each stream's buffer keeps its own causal margin rows in front).  seg_rows == 0: one stream.
   int seg_rows = 0;
   long long a_seg = 0, c_seg = 0, r_seg = 0;
+  // perf mode (svanon_set_precision): fp16 copy of W, filled in by the tensor-core launcher from its registry.  w_static =
+  // false keeps a launch out of that registry (W is caller memory that may change: svanon_debug_gemm*).
+  const void* Wh = nullptr;
+  bool w_static = true;
 };
 
 #ifdef __CUDACC__
@@ -162,6 +166,10 @@ __device__ __forceinline__ long long seg_row_off(long long row, int seg_rows, lo
   return row * ld;
 }
 #endif
+
+// perf mode switch of the tensor-core GEMM (gemm_tc.cu): single-pass fp16 MMAs instead of the 3xTF32 split
+extern bool g_gemm_half;
+void gemm_half_release();
 
 // measurement aid behind svanon_gemm_timing: per back end, summed event-timed launch durations and executed flops
 enum GemmBackend : int { GEMM_BACKEND_TC = 0, GEMM_BACKEND_PIPE = 1, GEMM_BACKEND_FP32 = 2, GEMM_BACKEND_CONV_SMALL = 3, GEMM_BACKENDS = 4 };

@@ -15,9 +15,11 @@
 // accumulator = BN TMEM columns, epilogue reads TMEM with tcgen05.ld.  Split-K over a thread-block cluster with a
 // DSMEM reduction distributed over the ranks.
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -64,6 +66,19 @@ __device__ __forceinline__ unsigned long long umma_desc(const void* tile) {
 // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ unsigned umma_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TBM >> 4) << 24);
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (format 0 at [7,10) and [10,13)), K-major, N>>3, M>>4
+__device__ __forceinline__ unsigned umma_idesc_f16(int n) {
+  return (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                         unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
                                           unsigned idesc, unsigned accumulate) {
@@ -121,12 +136,20 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f +
 // (TMEM -> registers -> global).  Split-K over a thread-block cluster: every rank parks its partial tile in its own
 // shared memory and then reduces (in fixed rank order) and writes ONE column slice of the tile, so the DSMEM reads are
 // spread over all ranks instead of being serialised in rank 0.
-template <int BN, int STAGES, bool SPLIT>
+//
+// HALF = true is the PERF MODE of svanon_set_precision (the reference's own GPU precision: fp16 autocast,
+// evaluations/infer_arvc.py:493): one kind::f16 pass instead of the 3xTF32 split.  A K-slab is still one 128-byte swizzle
+// row per tile row -- 64 halves instead of 32 floats -- so the tile geometry, descriptors and the pipeline are the same;
+// activations (fp32 in HBM) are rounded to fp16 by the producers, weights come from an fp16 copy made once per weight
+// (GemmParams::Wh), there is one A tile and one B tile per stage, and a slab costs 4 MMAs instead of 12.
+template <int BN, int STAGES, bool SPLIT, bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch batch) {
-  constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;
-  constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;           // A_hi | A_lo | B_hi | B_lo
+  constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;              // tile sizes in 4-byte words (128 bytes per row)
+  constexpr int STAGE_FLOATS = HALF ? (A_FLOATS + B_FLOATS) : (2 * A_FLOATS + 2 * B_FLOATS);   // A_hi | A_lo | B_hi | B_lo
+  constexpr int TKE = HALF ? 2 * TK : TK;                             // K elements per slab
+  constexpr int AV = HALF ? 2 : 1;                                    // float4 loads per 16-byte A chunk
   constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = BN * 8 / TC_PRODUCERS;   // 16-byte chunks per thread
-  constexpr int D = TC_DEPTH;
+  constexpr int D = (HALF && BN == 256) ? 1 : TC_DEPTH;   // fp16 slabs are twice as deep in K; 2 of them spill at BN = 256
   static_assert(TBM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
   static_assert(A_PER >= 1 && B_PER >= 1, "tile too small for the producer count");
   extern __shared__ unsigned char dsmem_raw[];
@@ -141,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   const GemmParams& p = batch.p[zb];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
-  const int kSlabs = (p.K + TK - 1) / TK;
+  const int kSlabs = (p.K + TKE - 1) / TKE;
   const int total = kSlabs * p.taps;
   const int it_begin = (int)((long long)total * rank / split);
   const int it_end = (int)((long long)total * (rank + 1) / split);
@@ -180,40 +203,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     for (int j = 0; j < A_PER; ++j) {
       const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
       const int m = m0 + row;
-      a_ptr[j] = (m < p.M) ? p.A + gemm_a_row(p, m) + c * 4 : nullptr;
+      a_ptr[j] = (m < p.M) ? p.A + gemm_a_row(p, m) + c * (HALF ? 8 : 4) : nullptr;
       a_soff[j] = (unsigned)swz(row, c) * 4u;
     }
-    const float* b_ptr[B_PER];
+    const float* b_ptr[B_PER];            // HALF: points into the fp16 copy (addressed in 4-byte words: 2 halves each)
     unsigned b_soff[B_PER];
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
       const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
       const int n = n0 + row;
-      b_ptr[j] = (n < p.N) ? p.W + (long long)n * p.K + c * 4 : nullptr;
+      if (HALF) b_ptr[j] = (n < p.N) ? reinterpret_cast<const float*>(p.Wh) + (((long long)n * p.K) >> 1) + c * 4 : nullptr;
+      else b_ptr[j] = (n < p.N) ? p.W + (long long)n * p.K + c * 4 : nullptr;
       b_soff[j] = (unsigned)swz(row, c) * 4u;
     }
-    const int c4 = (tid & 7) * 4;                      // K offset of this thread's chunks inside a slab
+    const int c4 = (tid & 7) * (HALF ? 8 : 4);         // K offset of this thread's chunks inside a slab
     const bool silu = p.prologue == PRO_SILU;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long tap_stride = (long long)p.N * p.K;
-    // load cursor: tap ld_t, K offset ld_k of the next slab to request
+    const long long tap_stride = (long long)p.N * p.K;   // in K elements
+    // load cursor: tap ld_t, K offset ld_k (elements) of the next slab to request
     int ld_t = it_begin / kSlabs;
-    int ld_k = (it_begin - ld_t * kSlabs) * TK;
+    int ld_k = (it_begin - ld_t * kSlabs) * TKE;
     long long ld_a = (long long)p.tap_off[ld_t] * p.lda, ld_b = (long long)ld_t * tap_stride;
-    float4 ra[D][A_PER], rb[D][B_PER];
+    float4 ra[D][A_PER * AV], rb[D][B_PER];
     auto load_b = [&](float4 (&dst)[B_PER]) {
       const bool k_ok = (ld_k + c4) < p.K;
 #pragma unroll
-      for (int j = 0; j < B_PER; ++j) dst[j] = (b_ptr[j] && k_ok) ? ldg_nc(b_ptr[j] + ld_b + ld_k) : zero4;
+      for (int j = 0; j < B_PER; ++j)       // HALF: offsets in 4-byte words of the fp16 copy (2 elements each)
+        dst[j] = (b_ptr[j] && k_ok) ? ldg_nc(b_ptr[j] + (HALF ? ((ld_b + ld_k) >> 1) : (ld_b + ld_k))) : zero4;
     };
-    auto load_a = [&](float4 (&dst)[A_PER]) {
+    auto load_a = [&](float4 (&dst)[A_PER * AV]) {
       const bool k_ok = (ld_k + c4) < p.K;
 #pragma unroll
-      for (int j = 0; j < A_PER; ++j) dst[j] = (a_ptr[j] && k_ok) ? ldg_nc(a_ptr[j] + ld_a + ld_k) : zero4;
+      for (int j = 0; j < A_PER; ++j) {
+#pragma unroll
+        for (int v = 0; v < AV; ++v) dst[j * AV + v] = (a_ptr[j] && k_ok) ? ldg_nc(a_ptr[j] + ld_a + ld_k + 4 * v) : zero4;
+      }
     };
     auto advance = [&] {
-      ld_k += TK;
-      if (ld_k >= kSlabs * TK) {
+      ld_k += TKE;
+      if (ld_k >= kSlabs * TKE) {
         ld_k = 0;
         ++ld_t;
         ld_a = (long long)p.tap_off[ld_t < p.taps ? ld_t : 0] * p.lda;
@@ -271,14 +299,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
           __syncwarp();
           const unsigned a_stage = smem_base + st_stage * (unsigned)(STAGE_FLOATS * 4);
           const unsigned b_stage = a_stage + 2u * A_FLOATS * 4u;
+          if constexpr (HALF) {
+            const unsigned b_stage_h = a_stage + (unsigned)A_FLOATS * 4u;
 #pragma unroll
-          for (int j = 0; j < A_PER; ++j) {
-            float4 v = ra[d][j];
-            if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-            split_sts(a_stage + a_soff[j], A_FLOATS * 4u, v);
+            for (int j = 0; j < A_PER; ++j) {
+              float4 v0 = ra[d][j * AV], v1 = ra[d][j * AV + AV - 1];
+              if (silu) {
+                v0.x = silu_fast(v0.x); v0.y = silu_fast(v0.y); v0.z = silu_fast(v0.z); v0.w = silu_fast(v0.w);
+                v1.x = silu_fast(v1.x); v1.y = silu_fast(v1.y); v1.z = silu_fast(v1.z); v1.w = silu_fast(v1.w);
+              }
+              const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
+              const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+              float4 pk;
+              pk.x = __uint_as_float(*reinterpret_cast<const unsigned*>(&h0));
+              pk.y = __uint_as_float(*reinterpret_cast<const unsigned*>(&h1));
+              pk.z = __uint_as_float(*reinterpret_cast<const unsigned*>(&h2));
+              pk.w = __uint_as_float(*reinterpret_cast<const unsigned*>(&h3));
+              sts4(a_stage + a_soff[j], pk);
+            }
+#pragma unroll
+            for (int j = 0; j < B_PER; ++j) sts4(b_stage_h + b_soff[j], rb[d][j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < A_PER; ++j) {
+              float4 v = ra[d][j];
+              if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
+              split_sts(a_stage + a_soff[j], A_FLOATS * 4u, v);
+            }
+#pragma unroll
+            for (int j = 0; j < B_PER; ++j) split_sts(b_stage + b_soff[j], B_FLOATS * 4u, rb[d][j]);
           }
-#pragma unroll
-          for (int j = 0; j < B_PER; ++j) split_sts(b_stage + b_soff[j], B_FLOATS * 4u, rb[d][j]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the MMA
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_base + st_stage * 8u) : "memory");
@@ -293,21 +343,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     TC_MARK(2);
     if (lane == 0) {
       // =========================================================== MMA issuer
-      const unsigned idesc = umma_idesc(BN);
+      const unsigned idesc = HALF ? umma_idesc_f16(BN) : umma_idesc(BN);
       for (int li = 0; li < n_it; ++li) {
         const int stage = li % STAGES;
         mbar_wait(&full_bar[stage], (li / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* As = smem + stage * STAGE_FLOATS;
-        float* Bs = As + 2 * A_FLOATS;
-        const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
-        const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
+        if constexpr (HALF) {
+          const unsigned long long a_d = umma_desc(As), b_d = umma_desc(As + A_FLOATS);
 #pragma unroll
-        for (int kk = 0; kk < TK / 8; ++kk) {
-          const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
-          umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-          umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
-          umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+          for (int kk = 0; kk < TK / 8; ++kk) {
+            const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 16 halves = 32 bytes per K-step
+            umma_f16(tmem_d, a_d + adv, b_d + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
+          }
+        } else {
+          float* Bs = As + 2 * A_FLOATS;
+          const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
+          const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
+#pragma unroll
+          for (int kk = 0; kk < TK / 8; ++kk) {
+            const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
+            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
         }
         umma_commit(&empty_bar[stage]);
       }
@@ -506,16 +565,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool HALF = false>
 void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
-  constexpr size_t SMEM = (size_t)STAGES * (2 * TBM * TK + 2 * BN * TK) * sizeof(float) + 1024;
+  constexpr size_t SMEM = (size_t)STAGES * (HALF ? 1 : 2) * (TBM * TK + BN * TK) * sizeof(float) + 1024;
   const GemmParams& p = b.p[0];
   dim3 grid((p.N + BN - 1) / BN, (p.M + TBM - 1) / TBM, count * split);
   b.split = split;
   static bool configured = false;
   if (!configured) {
-    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    SV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -532,8 +591,8 @@ void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
   attr[1].val.clusterDim.z = split;
   cfg.attrs = attr;
   cfg.numAttrs = split > 1 ? 2 : 1;
-  if (split > 1) SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, b));
-  else SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false>, b));
+  if (split > 1) SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true, HALF>, b));
+  else SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false, HALF>, b));
 }
 
 }  // namespace
@@ -553,6 +612,75 @@ void tc_prof_dump() {
   }
 }
 #endif
+
+// ---- perf mode: fp16 copies of the (immutable) engine weights, made once per weight pointer on first use
+bool g_gemm_half = false;
+
+namespace {
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<__half2*>(dst + i) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(dst + i + 2) = __floats2half2_rn(v.z, v.w);
+  } else {
+    for (size_t j = i; j < n; ++j) dst[j] = __float2half_rn(src[j]);
+  }
+}
+struct HalfCopy { __half* data; size_t n; };
+std::unordered_map<const float*, HalfCopy>& half_registry() {
+  static std::unordered_map<const float*, HalfCopy> r;
+  return r;
+}
+}  // namespace
+
+// fp16 copy of a weight tensor (keyed on its pointer; engine weights never change after finalize).  The first request
+// allocates and converts on `st`; while a stream capture is running no new copy can be made (null: the caller falls back
+// to the fp32-grade path for this launch).
+const __half* gemm_half_weights(const float* W, size_t n, cudaStream_t st) {
+  auto& reg = half_registry();
+  auto it = reg.find(W);
+  if (it != reg.end() && it->second.n >= n) return it->second.data;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (it != reg.end()) { cudaFree(it->second.data); reg.erase(it); }
+  __half* d = nullptr;
+  SV_CUDA(cudaMalloc(&d, (n + 8) * sizeof(__half)));
+  f32_to_f16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>(W, d, n);
+  SV_CUDA(cudaGetLastError());
+  SV_CUDA(cudaStreamSynchronize(st));       // first use only: the copy is complete before any other stream can see it
+  reg.emplace(W, HalfCopy{d, n});
+  return d;
+}
+
+// caller-owned weights (svanon_debug_gemm*): converted on every call into a grow-only scratch, never cached
+const __half* gemm_half_scratch(const float* W, size_t n, cudaStream_t st) {
+  static __half* buf = nullptr;
+  static size_t cap = 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (n + 8 > cap) {
+    SV_CUDA(cudaDeviceSynchronize());
+    if (buf) cudaFree(buf);
+    buf = nullptr;
+    SV_CUDA(cudaMalloc(&buf, (n + 8) * sizeof(__half)));
+    cap = n + 8;
+  }
+  f32_to_f16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>(W, buf, n);
+  SV_CUDA(cudaGetLastError());
+  return buf;
+}
+
+void gemm_half_release() {
+  for (auto& kv : half_registry()) cudaFree(kv.second.data);
+  half_registry().clear();
+}
 
 // Returns false when the problem is not a good fit (M < 32: latency kernels; N < 64).  Defaults measured on the streaming
 // loop: M >= 32 (3.79 -> 3.72 ms per chunk vs M >= 96), split-K clusters of at most 4 (8 is no faster).
@@ -590,6 +718,22 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
   // would.  (Switching the weight path off gains 11-16 % on large shapes; the A operand in tensor memory and a persistent
   // kernel with dedicated epilogue warps were measured slower -- profiles/README.md.)
   auto padded = [&](int bn) { return (long long)((p.N + bn - 1) / bn) * bn; };
+  // perf mode (svanon_set_precision 1): every problem of the batch needs its fp16 weight copy; K slabs hold 64 elements
+  bool half = g_gemm_half;
+  for (int i = 0; i < count && half; ++i) {
+    const size_t nw = (size_t)ps[i].taps * ps[i].N * ps[i].K;
+    b.p[i].Wh = ps[i].w_static ? gemm_half_weights(ps[i].W, nw, st) : (count == 1 ? gemm_half_scratch(ps[i].W, nw, st) : nullptr);
+    half = b.p[i].Wh != nullptr;
+  }
+  if (half) {
+    min_slabs = 1 << 30;
+    for (int i = 0; i < count; ++i) min_slabs = std::min(min_slabs, (ps[i].K + 2 * TK - 1) / (2 * TK) * ps[i].taps);
+    if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107)
+      launch_tc_cfg<256, 4, true>(b, count, 1, st);
+    else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 4, true>(b, count, 1, st);
+    else launch_tc_cfg<64, 4, true>(b, count, pick_split(ctas(64)), st);
+    return true;
+  }
   if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107)
     launch_tc_cfg<256, 2>(b, count, 1, st);
   else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 3>(b, count, 1, st);

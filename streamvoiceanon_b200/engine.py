@@ -35,9 +35,17 @@ class Engine:
         mode = os.environ.get("SVANON_GEMM_MODE")        # 1 = fp32 CUDA cores, 2 = tcgen05 3xTF32 (library default)
         if mode is not None:
             _lib.check(self.lib.svanon_set_gemm_mode(int(mode)))
+        prec = os.environ.get("SVANON_PRECISION")      # 0 parity (3xTF32, default), 1 perf (fp16 single-pass tensor-core GEMMs)
+        if prec is not None:
+            _lib.check(self.lib.svanon_set_precision(int(prec)))
         pdl = os.environ.get("SVANON_PDL")
         if pdl is not None:
             _lib.check(self.lib.svanon_set_pdl(int(pdl)))
+
+    def set_precision(self, mode: int):
+        """0: parity mode (fp32-grade 3xTF32 GEMMs, ids bit-exact); 1: perf mode (fp16 single-pass tensor-core GEMMs, the
+        reference's own GPU precision).  Process-wide (include/svanon.h)."""
+        _lib.check(self.lib.svanon_set_precision(int(mode)))
 
     @staticmethod
     def get(device=None) -> "Engine":

@@ -59,3 +59,33 @@ def test_tcgen05_wide_tiles(M, N, K):
 def test_tcgen05_gelu_epilogue():
     out, ref = _run(2, 512, 1536, 384, act=1)
     assert float((out.double() - ref).abs().max()) < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 1536, 384), (128, 1536, 512), (545, 2304, 768), (100, 72, 48), (16384, 2048, 512),
+                                   (16384, 512, 2048), (20992, 128, 512), (16500, 300, 784)])
+def test_tcgen05_fp16_perf_mode_gemm(M, N, K):
+    """PERF mode (svanon_set_precision 1): one kind::f16 pass.  The kernel must compute exactly the product of the
+    fp16-ROUNDED operands with fp32 accumulation -- checked against fp64 on the rounded operands (1e-5 relative: only the
+    accumulation order differs) -- which sits ~1e-3 from the fp32 product, the price of the mode (printed)."""
+    from streamvoiceanon_b200 import _lib
+    from streamvoiceanon_b200.engine import Engine, ptr
+    eng, lib = Engine.get(0), _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda")
+    _lib.check(lib.svanon_set_precision(1))
+    try:
+        _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, 0, None))
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.svanon_set_precision(0))
+    rounded = A.half().double() @ W.half().double().T + b.double()
+    exact = A.double() @ W.double().T + b.double()
+    scale = max(1.0, float(exact.abs().max()))
+    err_kernel = float((out.double() - rounded).abs().max())
+    err_mode = float((out.double() - exact).abs().max())
+    print(f"[perf mode] {M}x{N}x{K}: vs fp16-rounded operands {err_kernel:.2e}, vs fp32 product {err_mode:.2e} (scale {scale:.1f})")
+    assert err_kernel < 1e-5 * scale, err_kernel
+    assert err_mode < 2e-2 * scale, err_mode
