@@ -323,9 +323,11 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     }
     if (b->timing) SV_CUDA(cudaEventRecord(b->ev[2], st));
     // 6. re-prompt (:547-564): per stream, on its own schedule (prompt lengths differ)
-    for (Stream* s : ss) {
-      const int current_pos = s->pos_next - 1;
-      if (current_pos / 2 >= b->max_seq_frames) e.reprompt(*s, a.h->staging, st);
+    {
+      std::vector<Stream*> due;
+      for (Stream* s : ss)
+        if ((s->pos_next - 1) / 2 >= b->max_seq_frames) due.push_back(s);
+      if (!due.empty()) e.reprompt_many(due.data(), (int)due.size(), a.h->staging, st);     // one pass over the weights for all
     }
     // 7. V: incremental vocoder on the new frames of every stream; primed with the prompt's newest frames, which
     //    is what the reference puts in front of the first windows (:567-571)

@@ -67,6 +67,14 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.numAttrs = 1;
   SV_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
+// L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): one bulk instruction, no destination.
+// Used for WEIGHTS before griddepcontrol.wait: in the per-chunk chain every GEMM's weights are cold (E + A + V stream
+// ~0.8 GB of fp32 weights through the 126 MB L2 per chunk), and with programmatic dependent launch the kernel starts
+// while its predecessor still runs -- so its weight slice can travel DRAM -> L2 during that time instead of inside the
+// main loop, whose per-slab cost is otherwise one DRAM round trip per prefetch depth.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif

@@ -948,58 +948,71 @@ void Engine::voc_decode(const long long* codes, long long ld, int T, float* wave
 }
 
 // ------------------------------------------------------------------------------------------ stage A (multi-token)
-// BaseTransformer.forward_generate over M new tokens at positions pos0.. (dual_ar_stream.py:312-356) without the
-// heads: fills the KV cache; x is updated in place to the last layer's residual stream.
-void Engine::ar_forward_tokens(Stream& s, float* x, int M, int pos0, cudaStream_t st) {
+// BaseTransformer.forward_generate over new tokens (dual_ar_stream.py:312-356) without the heads, for n streams at once:
+// stream i contributes M[i] rows of x (concatenated in stream order) at positions pos0[i].. of ITS sequence.  The dense
+// projections run over all rows in one GEMM each (one pass over the weights for everybody); RoPE, KV append and the causal
+// attention run per stream on its row slice and its own cache.  x is updated in place to the last layer's residual.
+void Engine::ar_forward_tokens_many(Stream* const* ss, const int* M, const int* pos0, int n, float* x, cudaStream_t st) {
   NvtxRange nvtx_("svanon:A prefill tokens");
-  SV_CHECK(pos0 + M <= s.max_seq, "sequence position exceeds the KV cache (max_seq_len)");
-  float* nrm = ws.alloc_f((long long)M * AR_DIM);
-  float* qkv = ws.alloc_f((long long)M * 3 * AR_DIM);
-  float* y = ws.alloc_f((long long)M * AR_DIM);
-  float* h13 = ws.alloc_f((long long)M * 2 * AR_INTER);
-  float* gbuf = ws.alloc_f((long long)M * AR_INTER);
-  const long long layer_stride = (long long)AR_HEADS * s.max_seq * HEAD_DIM;
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    SV_CHECK(pos0[i] + M[i] <= ss[i]->max_seq, "sequence position exceeds the KV cache (max_seq_len)");
+    total += M[i];
+  }
+  float* nrm = ws.alloc_f((long long)total * AR_DIM);
+  float* qkv = ws.alloc_f((long long)total * 3 * AR_DIM);
+  float* y = ws.alloc_f((long long)total * AR_DIM);
+  float* h13 = ws.alloc_f((long long)total * 2 * AR_INTER);
+  float* gbuf = ws.alloc_f((long long)total * AR_INTER);
   for (int l = 0; l < AR_LAYERS; ++l) {
     const ArLayerWeights& L = ar.slow[l];
-    launch_rmsnorm(x, nrm, L.attn_norm, M, AR_DIM, AR_NORM_EPS, st);
+    launch_rmsnorm(x, nrm, L.attn_norm, total, AR_DIM, AR_NORM_EPS, st);
     GemmParams p;
-    p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = M; p.N = 3 * AR_DIM; p.K = AR_DIM; p.lda = AR_DIM; p.ldc = 3 * AR_DIM;
+    p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = total; p.N = 3 * AR_DIM; p.K = AR_DIM; p.lda = AR_DIM; p.ldc = 3 * AR_DIM;
     launch_gemm(p, st);
-    launch_rope_qk(qkv, ar.rope, M, AR_HEADS, pos0, st);
-    launch_kv_append(qkv, M, AR_HEADS, s.kc + l * layer_stride, s.vc + l * layer_stride, s.max_seq, pos0, st);
-    launch_attention(qkv, 3 * AR_DIM, s.kc + l * layer_stride, s.vc + l * layer_stride, (long long)s.max_seq * HEAD_DIM,
-                     HEAD_DIM, y, AR_DIM, M, pos0, AR_HEADS, 1 << 30, st);
+    int r0 = 0;
+    for (int i = 0; i < n; ++i) {
+      Stream& s = *ss[i];
+      const long long layer_stride = (long long)AR_HEADS * s.max_seq * HEAD_DIM;
+      float* q_i = qkv + (long long)r0 * 3 * AR_DIM;
+      launch_rope_qk(q_i, ar.rope, M[i], AR_HEADS, pos0[i], st);
+      launch_kv_append(q_i, M[i], AR_HEADS, s.kc + l * layer_stride, s.vc + l * layer_stride, s.max_seq, pos0[i], st);
+      launch_attention(q_i, 3 * AR_DIM, s.kc + l * layer_stride, s.vc + l * layer_stride, (long long)s.max_seq * HEAD_DIM,
+                       HEAD_DIM, y + (long long)r0 * AR_DIM, AR_DIM, M[i], pos0[i], AR_HEADS, 1 << 30, st);
+      r0 += M[i];
+    }
     GemmParams po;
-    po.A = y; po.W = L.wo; po.C = x; po.residual = x; po.M = M; po.N = AR_DIM; po.K = AR_DIM; po.lda = AR_DIM;
+    po.A = y; po.W = L.wo; po.C = x; po.residual = x; po.M = total; po.N = AR_DIM; po.K = AR_DIM; po.lda = AR_DIM;
     po.ldc = AR_DIM; po.ldr = AR_DIM;
     launch_gemm(po, st);
-    launch_rmsnorm(x, nrm, L.ffn_norm, M, AR_DIM, AR_NORM_EPS, st);
+    launch_rmsnorm(x, nrm, L.ffn_norm, total, AR_DIM, AR_NORM_EPS, st);
     GemmParams p1;
-    p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = M; p1.N = AR_INTER; p1.K = AR_DIM; p1.lda = AR_DIM; p1.ldc = 2 * AR_INTER;
+    p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = total; p1.N = AR_INTER; p1.K = AR_DIM; p1.lda = AR_DIM; p1.ldc = 2 * AR_INTER;
     GemmParams p13[2] = {p1, p1};            // w1 and w3 side by side in one launch
     p13[1].W = L.w3; p13[1].C = h13 + AR_INTER;
     launch_gemm(p13, 2, st);
-    launch_silu_mul(h13, gbuf, M, AR_INTER, st);
+    launch_silu_mul(h13, gbuf, total, AR_INTER, st);
     GemmParams p2;
-    p2.A = gbuf; p2.W = L.w2; p2.C = x; p2.residual = x; p2.M = M; p2.N = AR_DIM; p2.K = AR_INTER; p2.lda = AR_INTER;
+    p2.A = gbuf; p2.W = L.w2; p2.C = x; p2.residual = x; p2.M = total; p2.N = AR_DIM; p2.K = AR_INTER; p2.lda = AR_INTER;
     p2.ldc = AR_DIM; p2.ldr = AR_DIM;
     launch_gemm(p2, st);
-
   }
 }
 
-// ARVCWrapper.prefill_prompt (arvc_wrapper.py:100-112) -> DualARWrapper.prefill_prompt (dual_ar_stream.py:764-796).
-// ref_content [T] int64 (device), ref_audio [8][T] int32 (device), style [192], timbre [32][128] (device).
-void Engine::ar_prefill_prompt(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
-                               const float* timbre, cudaStream_t st) {
-  SV_CHECK(finalized[MODEL_AR], "AR weights not finalized");
+void Engine::ar_forward_tokens(Stream& s, float* x, int M, int pos0, cudaStream_t st) {
+  Stream* one = &s;
+  ar_forward_tokens_many(&one, &M, &pos0, 1, x, st);
+}
+
+// Token rows of DualARWrapper.prefill_prompt (dual_ar_stream.py:764-796) for one stream, written to x (room for
+// n_tok + 2 rows): 33 speaker rows, then (condition, audio) pairs with the audio rows delayed by `delay` frames.  Also
+// keeps the speaker rows and cached_ref_emb / cached_new_audio_emb on the stream.  Returns n_tok.
+int Engine::ar_prompt_rows(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
+                           const float* timbre, float* x, cudaStream_t st) {
   const int d = s.delay;
   SV_CHECK(T >= 1 && T > d, "prompt must be longer than the delay");
   const int n_tok = AR_SPK_TOKENS + 2 * T - (d == 0 ? 1 : 0);
   SV_CHECK(n_tok <= s.max_seq, "prompt does not fit the KV cache");
-  ws.ensure(((size_t)(n_tok + 8) * 12000 + (1u << 20)) * sizeof(float));
-  ws.reset();
-  float* x = ws.alloc_f((long long)(n_tok + 2) * AR_DIM);
   // speaker rows: context_in(timbre) 32 tokens, style_in(style) 1 token
   {
     GemmParams p;
@@ -1020,7 +1033,29 @@ void Engine::ar_prefill_prompt(Stream& s, const long long* ref_content, const in
   // cached_ref_emb = embed(ref_audio[:, T-d:]) ; for d == 0 cached_new_audio_emb = embed(last frame)
   if (d > 0) launch_embed_codes(ar.codebook_emb, ref_audio + (T - d), T, s.ref_emb_tail, d, AR_DIM, st);
   else launch_embed_codes(ar.codebook_emb, ref_audio + (T - 1), T, s.x_audio, 1, AR_DIM, st);
+  return n_tok;
+}
 
+// Token rows of DualARWrapper.prefill_src_condition4delay (dual_ar_stream.py:798-815): d conditions interleaved with
+// cached_ref_emb, 2d - 1 rows; the last audio row becomes cached_new_audio_emb.
+int Engine::ar_delay_rows(Stream& s, const long long* src_content, float* x, cudaStream_t st) {
+  const int d = s.delay;
+  launch_gather_rows(ar.cond_emb, src_content, x, d, AR_DIM, 2 * AR_DIM, st);
+  launch_copy_rows(s.ref_emb_tail, AR_DIM, x + AR_DIM, 2 * AR_DIM, d, AR_DIM, st);
+  launch_copy_rows(x + (long long)(2 * d - 1) * AR_DIM, AR_DIM, s.x_audio, AR_DIM, 1, AR_DIM, st);
+  return 2 * d - 1;
+}
+
+// ARVCWrapper.prefill_prompt (arvc_wrapper.py:100-112) -> DualARWrapper.prefill_prompt (dual_ar_stream.py:764-796).
+// ref_content [T] int64 (device), ref_audio [8][T] int32 (device), style [192], timbre [32][128] (device).
+void Engine::ar_prefill_prompt(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
+                               const float* timbre, cudaStream_t st) {
+  SV_CHECK(finalized[MODEL_AR], "AR weights not finalized");
+  const int n_max = AR_SPK_TOKENS + 2 * T;
+  ws.ensure(((size_t)(n_max + 8) * 12000 + (1u << 20)) * sizeof(float));
+  ws.reset();
+  float* x = ws.alloc_f((long long)(n_max + 2) * AR_DIM);
+  const int n_tok = ar_prompt_rows(s, ref_content, ref_audio, T, style, timbre, x, st);
   ar_forward_tokens(s, x, n_tok, 0, st);
   s.pos_next = n_tok;
   s.step += 1;
@@ -1036,33 +1071,69 @@ void Engine::ar_prefill_delay(Stream& s, const long long* src_content, int n, cu
   ws.ensure(((size_t)(2 * d + 8) * 12000 + (1u << 20)) * sizeof(float));
   ws.reset();
   float* x = ws.alloc_f((long long)2 * d * AR_DIM);
-  launch_gather_rows(ar.cond_emb, src_content, x, d, AR_DIM, 2 * AR_DIM, st);
-  launch_copy_rows(s.ref_emb_tail, AR_DIM, x + AR_DIM, 2 * AR_DIM, d, AR_DIM, st);
-  launch_copy_rows(x + (long long)(2 * d - 1) * AR_DIM, AR_DIM, s.x_audio, AR_DIM, 1, AR_DIM, st);
-
-  ar_forward_tokens(s, x, 2 * d - 1, s.pos_next, st);
-  s.pos_next += 2 * d - 1;
+  const int rows = ar_delay_rows(s, src_content, x, st);
+  ar_forward_tokens(s, x, rows, s.pos_next, st);
+  s.pos_next += rows;
   s.step += 1;
   s.delay_prefilled = true;
 }
 
-// Re-prompt of the per-chunk loop (infer_arvc.py:547-564): the prompt kept at set_prompt time, extended by the last
-// `buffer_frames` predicted frames and their source content ids, is prefilled again from position 0.
-void Engine::reprompt(Stream& s, Workspace& staging, cudaStream_t st) {
+// Re-prompt of the per-chunk loop (infer_arvc.py:547-564) for the n streams that hit their sequence limit in the same
+// step: the prompt kept at set_prompt time, extended by the last `buffer_frames` predicted frames and their source
+// content ids, is prefilled again from position 0, followed by the delay prefill.  The reference makes two forward calls
+// per stream (prefill_prompt, prefill_src_condition4delay); here the 2d - 1 delay tokens ride at the end of the prompt's
+// rows -- the same causal attention over the same cache positions -- and all streams of the step share ONE pass over the
+// weights (groups of at most REPROMPT_GROUP streams).
+void Engine::reprompt_many(Stream* const* streams, int n_all, Workspace& staging, cudaStream_t st) {
   NvtxRange nvtx_("svanon:A re-prompt");
-  const int buf = std::min(s.buffer_frames, s.n_pred);
-  const int Tn = s.ref_frames + buf;
-  SV_CHECK(s.n_src - s.delay >= buf, "not enough source history for re-prompting");
-  int* ext_audio = (int*)staging.alloc_bytes((size_t)8 * Tn * sizeof(int));
-  long long* ext_content = (long long*)staging.alloc_bytes((size_t)Tn * sizeof(long long));
-  launch_concat_cols(s.ref_audio_dev, s.ref_frames, s.ref_frames, s.pred_hist + (s.n_pred - buf), HIST_CAP, buf,
-                     ext_audio, Tn, 8, false, st);
-  SV_CUDA(cudaMemcpyAsync(ext_content, s.ref_content_dev, (size_t)s.ref_frames * sizeof(long long),
-                          cudaMemcpyDeviceToDevice, st));
-  SV_CUDA(cudaMemcpyAsync(ext_content + s.ref_frames, s.src_hist + (s.n_src - buf - s.delay),
-                          (size_t)buf * sizeof(long long), cudaMemcpyDeviceToDevice, st));
-  ar_prefill_prompt(s, ext_content, ext_audio, Tn, s.style_dev, s.timbre_dev, st);
-  if (s.delay > 0) ar_prefill_delay(s, s.src_hist + (s.n_src - s.delay), s.delay, st);
+  constexpr int REPROMPT_GROUP = 16;
+  for (int g0 = 0; g0 < n_all; g0 += REPROMPT_GROUP) {
+    const int n = std::min(REPROMPT_GROUP, n_all - g0);
+    Stream* const* ss = streams + g0;
+    int M[REPROMPT_GROUP], pos0[REPROMPT_GROUP], Tn[REPROMPT_GROUP];
+    size_t rows_max = 0;
+    for (int i = 0; i < n; ++i) {
+      Stream& s = *ss[i];
+      const int buf = std::min(s.buffer_frames, s.n_pred);
+      SV_CHECK(s.n_src - s.delay >= buf, "not enough source history for re-prompting");
+      Tn[i] = s.ref_frames + buf;
+      rows_max += (size_t)AR_SPK_TOKENS + 2 * Tn[i] + 2 * s.delay + 2;
+    }
+    ws.ensure(((rows_max + 8) * 12000 + (1u << 20)) * sizeof(float));
+    ws.reset();
+    float* x = ws.alloc_f((long long)rows_max * AR_DIM);
+    long long r0 = 0;
+    for (int i = 0; i < n; ++i) {
+      Stream& s = *ss[i];
+      const int buf = Tn[i] - s.ref_frames;
+      int* ext_audio = (int*)staging.alloc_bytes((size_t)8 * Tn[i] * sizeof(int));
+      long long* ext_content = (long long*)staging.alloc_bytes((size_t)Tn[i] * sizeof(long long));
+      launch_concat_cols(s.ref_audio_dev, s.ref_frames, s.ref_frames, s.pred_hist + (s.n_pred - buf), HIST_CAP, buf,
+                         ext_audio, Tn[i], 8, false, st);
+      SV_CUDA(cudaMemcpyAsync(ext_content, s.ref_content_dev, (size_t)s.ref_frames * sizeof(long long),
+                              cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpyAsync(ext_content + s.ref_frames, s.src_hist + (s.n_src - buf - s.delay),
+                              (size_t)buf * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+      float* xi = x + r0 * AR_DIM;
+      int rows = ar_prompt_rows(s, ext_content, ext_audio, Tn[i], s.style_dev, s.timbre_dev, xi, st);
+      if (s.delay > 0) rows += ar_delay_rows(s, s.src_hist + (s.n_src - s.delay), xi + (long long)rows * AR_DIM, st);
+      M[i] = rows;
+      pos0[i] = 0;
+      r0 += rows;
+    }
+    ar_forward_tokens_many(ss, M, pos0, n, x, st);
+    for (int i = 0; i < n; ++i) {
+      Stream& s = *ss[i];
+      s.pos_next = M[i];
+      s.step += s.delay > 0 ? 2 : 1;       // prefill_prompt and prefill_src_condition4delay each count as a sampler step
+      s.delay_prefilled = s.delay > 0;
+    }
+  }
+}
+
+void Engine::reprompt(Stream& s, Workspace& staging, cudaStream_t st) {
+  Stream* one = &s;
+  reprompt_many(&one, 1, staging, st);
 }
 
 // DualARWrapper.decode_one (dual_ar_stream.py:817-837) for `batch` independent streams in one launch.

@@ -339,6 +339,11 @@ struct Engine {
 
   // AR
   void ar_forward_tokens(Stream& s, float* x /*[M][768]*/, int M, int pos0, cudaStream_t st);
+  void ar_forward_tokens_many(Stream* const* ss, const int* M, const int* pos0, int n, float* x, cudaStream_t st);
+  int ar_prompt_rows(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
+                     const float* timbre, float* x, cudaStream_t st);
+  int ar_delay_rows(Stream& s, const long long* src_content, float* x, cudaStream_t st);
+  void reprompt_many(Stream* const* streams, int n, Workspace& staging, cudaStream_t st);
   void ar_prefill_prompt(Stream& s, const long long* ref_content, const int* ref_audio, int T, const float* style,
                          const float* timbre, cudaStream_t st);
   void ar_prefill_delay(Stream& s, const long long* src_content, int n, cudaStream_t st);

@@ -50,7 +50,6 @@ gemm_pipe_kernel(const PipeBatch batch) {
   static_assert(BM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
   extern __shared__ __align__(128) float smem[];
   pdl_trigger();
-  pdl_wait();
 
   const int split = SPLIT ? batch.split : 1;
   const int zb = SPLIT ? blockIdx.z / split : blockIdx.z;
@@ -65,6 +64,21 @@ gemm_pipe_kernel(const PipeBatch batch) {
   const int it_begin = (int)((long long)total * rank / split);
   const int it_end = (int)((long long)total * (rank + 1) / split);
   const int n_it = it_end - it_begin;
+  // weights do not depend on the kernel in front: pull this CTA's slice of weight row n0 + tid into L2 while it finishes
+  if (tid < BN && n0 + tid < p.N && n_it > 0) {
+    int t = it_begin / kSlabs;
+    int s0 = it_begin - t * kSlabs;
+    int left = n_it;
+    while (left > 0) {
+      const int s1 = min(kSlabs, s0 + left);
+      const int k0 = s0 * PK, k1 = min(p.K, s1 * PK);
+      if (k1 > k0) l2_prefetch_bulk(p.W + ((long long)t * p.N + n0 + tid) * p.K + k0, (unsigned)(k1 - k0) * 4u);
+      left -= s1 - s0;
+      s0 = 0;
+      ++t;
+    }
+  }
+  pdl_wait();
 
   float acc[TM][TN];
 #pragma unroll

@@ -35,6 +35,7 @@ constexpr int TBM = 128;
 struct TcBatch {
   GemmParams p[3];
   int split;
+  int wprefetch;     // weight-slice L2 prefetch before griddepcontrol.wait (SVANON_TC_WPREFETCH=0 switches it off)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -172,6 +173,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
 
   TC_MARK(0);
   pdl_trigger();
+  if (batch.wprefetch && tid < BN && n0 + tid < p.N && n_it > 0) {
+    // this CTA's slice of weight row n0 + tid: slabs [it_begin, it_end) = per tap a contiguous K range
+    const unsigned esz = HALF ? 2u : 4u;
+    const char* wbase = HALF ? reinterpret_cast<const char*>(p.Wh) : reinterpret_cast<const char*>(p.W);
+    int t = it_begin / kSlabs;
+    int s0 = it_begin - t * kSlabs;
+    int left = n_it;
+    while (left > 0) {
+      const int s1 = min(kSlabs, s0 + left);
+      const int k0 = s0 * TKE, k1 = min(p.K, s1 * TKE);
+      if (k1 > k0)
+        l2_prefetch_bulk(wbase + (((long long)t * p.N + n0 + tid) * p.K + k0) * esz, (unsigned)(k1 - k0) * esz);
+      left -= s1 - s0;
+      s0 = 0;
+      ++t;
+    }
+  }
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
@@ -686,12 +704,17 @@ void gemm_half_release() {
 // loop: M >= 32 (3.79 -> 3.72 ms per chunk vs M >= 96), split-K clusters of at most 4 (8 is no faster).
 bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
   const GemmParams& p = ps[0];
+  static const int wprefetch = [] {
+    const char* e = getenv("SVANON_TC_WPREFETCH");          // tuning knob: 0 = no weight-slice L2 prefetch
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
   static const int min_m = [] {
     const char* e = getenv("SVANON_TC_MIN_M");          // tuning knob: smallest M that goes to the tensor cores
     return e ? atoi(e) : 32;
   }();
   if (p.M < min_m || p.N < 64) return false;
   TcBatch b;
+  b.wprefetch = wprefetch;
   int min_slabs = 1 << 30;
   for (int i = 0; i < count; ++i) {
     b.p[i] = ps[i];
