@@ -65,7 +65,7 @@ gemm_pipe_kernel(const PipeBatch batch) {
   const int it_end = (int)((long long)total * (rank + 1) / split);
   const int n_it = it_end - it_begin;
   // weights do not depend on the kernel in front: pull this CTA's slice of weight row n0 + tid into L2 while it finishes
-  if (tid < BN && n0 + tid < p.N && n_it > 0) {
+  if (gridDim.x * gridDim.y * gridDim.z <= 160 && tid < BN && n0 + tid < p.N && n_it > 0) {
     int t = it_begin / kSlabs;
     int s0 = it_begin - t * kSlabs;
     int left = n_it;

@@ -714,7 +714,9 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
   }();
   if (p.M < min_m || p.N < 64) return false;
   TcBatch b;
-  b.wprefetch = wprefetch;
+  // Weight-slice L2 prefetch pays where a GEMM is one latency-bound wave of CTAs (single stream: 3.54 -> 3.47 ms per chunk);
+  // on multi-wave grids the extra L2 fill traffic costs more than it hides (128 streams: 34.2 -> 35.5 ms per step).
+  b.wprefetch = (wprefetch && (long long)((p.M + TBM - 1) / TBM) * ((p.N + 63) / 64) * count <= 148) ? 1 : 0;
   int min_slabs = 1 << 30;
   for (int i = 0; i < count; ++i) {
     b.p[i] = ps[i];
