@@ -83,6 +83,8 @@ def parse():
     ap.add_argument("--concurrent-chunks", type=int, default=720, help="chunks per stream of the config-4 leg")
     ap.add_argument("--stateful", default="256,384,512", help="stream-count ladder of the stateful-encoder leg (N=1 only; '' = skip)")
     ap.add_argument("--stateful-chunks", type=int, default=150, help="chunks per stream of the stateful-encoder leg")
+    ap.add_argument("--config5", type=int, default=128, help="streams per GPU of the BASELINE config-5 leg (0 = skip)")
+    ap.add_argument("--config5-steps", type=int, default=240, help="two-frame chunks per stream of the config-5 leg")
     ap.add_argument("--perf", default="128,192,256", help="stream-count ladder of the perf-mode leg, window encoder (N=1 only; '' = skip)")
     ap.add_argument("--perf-stateful", default="384,512,768", help="the same with the stateful encoder")
     ap.add_argument("--no-prompt-path", action="store_true", help="skip the setup-path leg (child process, N=1 only)")
@@ -382,6 +384,77 @@ def concurrent_leg(tok, B, chunks, rank=0, warm=5, enc_mode=None):
             "stage_ms": {"E": st[0], "A": st[1], "V": st[2]}, "setup_s": t_setup}
 
 
+def config5_leg(tok, voc, B, steps, rank=0, warm=4):
+    """BASELINE config 5 on this GPU: anonymisation alpha = 0.7 with THREE mixed references per stream, streaming with
+    two-frame chunks, delay 2.  The prompts come from the real prompt path -- `PromptBuilder.calculate_prompt` on the
+    concatenation of three synthetic references (both speaker encoders, noise mix with torch's generator, codec and content
+    ids; evaluations/infer_arvc.py:382-441), eight distinct prompts of 3 x 4.3..5.0 s shared round-robin by the B streams
+    (prefilled untruncated, kept truncated to 256 frames: :468-489) -- then B streams in lock-step, HOST buffers,
+    `steps` chunks of 2 frames each, every stream re-prompting once inside the window."""
+    from streamvoiceanon_b200 import BatchSession, StreamSession, synth
+    from streamvoiceanon_b200.prompt import PromptBuilder
+    from streamvoiceanon_b200.speaker import CAMPPlus, SpeakerEncoder
+    style_enc, timbre_enc = CAMPPlus(), SpeakerEncoder()
+    style_enc.load_state_dict(synth.make_campplus_state_dict(1234))
+    timbre_enc.load_state_dict(synth.make_timbre_encoder_state_dict(1234))
+    pb = PromptBuilder(tok, voc, style_enc, timbre_enc)
+    torch.manual_seed(77 + rank)
+    t0 = time.perf_counter()
+    prompts = []
+    for k in range(8):
+        sec = 4.3 + 0.1 * k
+        refs = [synth.synth_audio_44k(5200 + 10 * k + j + 100 * rank, sec)[None].cuda() for j in range(3)]
+        prompts.append(pb.calculate_prompt(refs, 0.7, "concat_mel"))
+    torch.cuda.synchronize()
+    t_prompt = (time.perf_counter() - t0) / 8
+    sessions = []
+    for b in range(B):
+        codes, content, style, timbre, _ = prompts[b % 8]
+        s = StreamSession()
+        s.set_sampling(0.7, 0.7, seed=9000 + 1000 * rank + b)
+        s.set_prompt(content[0], codes, style, timbre, WORKLOAD["max_prompt_frames"], 2)
+        sessions.append(s)
+    batch = BatchSession(sessions)
+    batch.setup(WORKLOAD["encode_window_frames"], WORKLOAD["decode_window_frames"], WORKLOAD["max_seq_frames"],
+                WORKLOAD["buffer_frames"], 2)
+    n_src = 20
+    src = torch.stack([synth.synth_audio_44k(1000 + (b % 8), 2.0)[: n_src * 4096] for b in range(B)])
+    pin_in = src.view(B, n_src, 4096).transpose(0, 1).contiguous().pin_memory()
+    pin_out = torch.empty(B, 4096).pin_memory()
+    lib = _lib_mod().load()
+    pos = lambda: [int(lib.svanon_ar_position(s._h)) for s in sessions]                 # noqa: E731
+    it = 0
+    for _ in range(warm):
+        batch.process_chunk(pin_in[it % n_src], pin_out); it += 1
+    last, reprompts, wall = pos(), 0, []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        batch.process_chunk(pin_in[it % n_src], pin_out); it += 1
+        wall.append((time.perf_counter() - t1) * 1e3)
+        now = pos()
+        reprompts += sum(1 for a, b_ in zip(last, now) if b_ < a)
+        last = now
+    t_all = time.perf_counter() - t_all
+    batch.close()
+    for s in sessions:
+        s.close()
+    period = 2 * FRAME_S * 1e3
+    mean = sum(wall) / len(wall)
+    return {"what": "BASELINE config 5: alpha 0.7, three mixed references (concat_mel, prompt path on the GPU), chunk = 2 frames, delay 2",
+            "streams": B, "steps": steps, "chunk_frames": 2, "chunk_period_ms": period, "ms_per_step_mean": mean,
+            "ms_per_step_p50": _pct(wall, 0.5), "ms_per_step_p99": _pct(wall, 0.99), "ms_per_step_max": max(wall),
+            "rtf_mean": mean / period, "rtf_p99": _pct(wall, 0.99) / period, "frames_per_s": 2 * B * steps / t_all,
+            "reprompts_in_window": reprompts, "steps_over_chunk_period": sum(1 for w in wall if w > period),
+            "prompt_frames": [int(p[1].shape[-1]) for p in prompts], "calculate_prompt_ms": t_prompt * 1e3,
+            "h2d_bytes_per_step": B * 4096 * 4, "d2h_bytes_per_step": B * 4096 * 4}
+
+
+def _lib_mod():
+    from streamvoiceanon_b200 import _lib
+    return _lib
+
+
 def perf_mode_leg(tok, args, rank):
     """PERF mode beside the parity-mode line, never instead of it: the many-stream loop with fp16 single-pass tensor-core
     GEMMs (svanon_set_precision 1 -- the reference's own GPU precision: fp16 autocast, evaluations/infer_arvc.py:493), with
@@ -513,7 +586,7 @@ def run_engine(args):
     tok = ContentTokenizer()
     tok.load_state_dict(synth.make_tokenizer_state_dict(1234), strict=False)
     voc = Vocoder()
-    voc.load_state_dict(synth.make_vocoder_state_dict(1234), strict=False)
+    voc.load_state_dict({**synth.make_vocoder_state_dict(1234), **synth.make_vocoder_encoder_state_dict(1234)}, strict=False)
 
     ref_wave, ref_audio, style, timbre, src = make_inputs(rank)
     ref_content, _ = tok.encode(ref_wave.cuda(), torch.LongTensor([ref_wave.shape[1]]).cuda())
@@ -617,6 +690,15 @@ def run_engine(args):
                 if conc[-1]["ms_per_step_p99"] >= frame_ms:
                     break
                 conc.append(concurrent_leg(tok, B, args.concurrent_chunks, rank))
+    # ---------------- BASELINE config 5 on this GPU (every rank): alpha 0.7, three references, two-frame chunks
+    cfg5 = None
+    if counts and args.config5 > 0:
+        barrier()
+        try:
+            cfg5 = config5_leg(tok, voc, args.config5, args.config5_steps, rank)
+        except Exception as exc:
+            cfg5 = {"error": repr(exc)[:400]}
+        barrier()
     # opt-in mode: stateful content encoder (offline-encode semantics, svanon_stream_set_encoder_mode 3), N = 1 only
     stateful = []
     if world == 1 and counts:
@@ -640,8 +722,11 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         per_rank = [None] * world
         dist.all_gather_object(per_rank, conc[0] if conc else None)
+        per_rank5 = [None] * world
+        dist.all_gather_object(per_rank5, cfg5)
     else:
         per_rank = [conc[0] if conc else None]
+        per_rank5 = [cfg5]
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
@@ -718,6 +803,14 @@ def run_engine(args):
             "ladder": conc,
             "max_streams_per_gpu_p99_lt_frame_period": max([r["streams"] for r in conc if r["ms_per_step_p99"] < frame_ms], default=None),
             "max_streams_per_gpu_mean_rtf_lt_1": max([r["streams"] for r in conc if r["rtf_mean"] < 1.0], default=None)}
+    if cfg5:
+        ranks5 = [r for r in per_rank5 if r and "error" not in r]
+        line["config5"] = dict(per_rank5[0]) if per_rank5[0] else {}
+        if ranks5:
+            line["config5"].update({"n_gpus": world, "total_streams": sum(r["streams"] for r in ranks5),
+                                    "frames_per_s_all_gpus": sum(r["frames_per_s"] for r in ranks5),
+                                    "ms_per_step_mean_max_over_ranks": max(r["ms_per_step_mean"] for r in ranks5),
+                                    "ms_per_step_p99_max_over_ranks": max(r["ms_per_step_p99"] for r in ranks5)})
     if stateful:
         ok = [r["streams"] for r in stateful if "error" not in r and r["ms_per_step_p99"] < FRAME_S * 1e3]
         line["concurrent_streams_stateful_encoder"] = {

@@ -332,6 +332,12 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
 /* decode path of the batch: 0 (default) = persistent kernel for 1/2/4 streams, many-stream kernels otherwise;
  * 1 = always the many-stream kernels */
 int svanon_batch_set_ar_path(svanon_batch* b, int path);
+/* Cohort merging (heterogeneous stream phases): two batches with the same settings that are both past
+ * their warm-up chunks become ONE batch -- the members of `a` followed by the members of `b` -- which moves every member's
+ * state (wave ring, encoder window / stateful-encoder state, vocoder histories) into side-by-side buffers; from the next
+ * chunk on all of them share one pass over the weights.  Every stream keeps producing exactly what it produces alone.
+ * `a` and `b` are left without members: destroy them.  wave_chunks / wave_out rows of the merged batch: a's streams, then b's. */
+int svanon_batch_merge(svanon_batch* a, svanon_batch* b, svanon_batch** out, void* cuda_stream);
 int svanon_batch_set_encoder_mode(svanon_batch* b, int incremental);   /* as svanon_stream_set_encoder_mode */
 /* per-stage device time of the last non-warm-up chunk, as svanon_stream_last_timing */
 int svanon_batch_set_timing(svanon_batch* b, int enable);

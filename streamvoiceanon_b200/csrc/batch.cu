@@ -26,7 +26,9 @@ struct svanon_batch {
     int* pred_hist;
     const int* ref_audio;
     int ref_frames;
+    int src_off, pred_off;                                // member's history column = batch counter + offset (merged cohorts)
   };
+  std::vector<int> src_off, pred_off;                     // host copies of the offsets (0 unless the batch came from a merge)
   SlotPtrs* ptrs_dev = nullptr;
   int n_src = 0, n_pred = 0, voc_fed = 0;
   bool delay_prefilled = false;
@@ -54,7 +56,7 @@ __global__ void batch_take_ids_kernel(const SlotPtrs* __restrict__ ptrs, const l
   if (i >= n * chunk) return;
   const int b = i / chunk, j = i % chunk;
   const long long id = ids_win[(long long)b * enc_win + enc_win - chunk + j];
-  ptrs[b].src_hist[col0 + j] = id;
+  ptrs[b].src_hist[col0 + ptrs[b].src_off + j] = id;
   step_ids[(long long)j * n + b] = id;
 }
 
@@ -68,8 +70,49 @@ __global__ void batch_gather_codes_kernel(const SlotPtrs* __restrict__ ptrs, lon
   const int b = i / (8 * chunk), k = (i / chunk) % 8, j = i % chunk;
   const SlotPtrs& p = ptrs[b];
   const int v = from_ref ? p.ref_audio[(long long)k * p.ref_frames + (p.ref_frames - back + j)]
-                         : p.pred_hist[(long long)k * HIST_CAP + col0 + j];
+                         : p.pred_hist[(long long)k * HIST_CAP + col0 + p.pred_off + j];
   codes_win[i] = v;
+}
+
+// (re)builds the device table of per-member pointers and history offsets
+void upload_slot_table(svanon_batch* b, cudaStream_t st) {
+  const int n = (int)b->streams.size();
+  std::vector<SlotPtrs> ptrs(n);
+  for (int i = 0; i < n; ++i) {
+    Stream& s = b->streams[i]->st;
+    ptrs[i] = {s.src_hist, s.pred_hist, s.ref_audio_dev, s.ref_frames, b->src_off[i], b->pred_off[i]};
+  }
+  if (!b->ptrs_dev) b->ptrs_dev = dmalloc<SlotPtrs>(n);
+  SV_CUDA(cudaStreamSynchronize(st));                    // rare (setup, merge, history compaction): a blocking copy is fine
+  SV_CUDA(cudaMemcpy(b->ptrs_dev, ptrs.data(), (size_t)n * sizeof(SlotPtrs), cudaMemcpyHostToDevice));
+}
+
+// Every member keeps the newest HIST_CAP / 2 columns of its source-id (src = true) or codec-id history; afterwards all
+// members sit at column HIST_CAP / 2 again, so the per-member offsets of a merged batch drop to zero.
+void compact_histories(svanon_batch* b, bool src, cudaStream_t st) {
+  Engine& e = b->owner->eng;
+  const int keep = HIST_CAP / 2;
+  const int n = (int)b->streams.size();
+  for (int i = 0; i < n; ++i) {
+    Stream& s = b->streams[i]->st;
+    if (src) {
+      const int have = b->n_src + b->src_off[i];
+      long long* tmp = (long long*)e.ws.base;
+      SV_CUDA(cudaMemcpyAsync(tmp, s.src_hist + (have - keep), keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpyAsync(s.src_hist, tmp, keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+      b->src_off[i] = 0;
+    } else {
+      const int have = b->n_pred + b->pred_off[i];
+      int* tmp = (int*)e.ws.base;
+      SV_CUDA(cudaMemcpy2DAsync(tmp, keep * sizeof(int), s.pred_hist + (have - keep), HIST_CAP * sizeof(int), keep * sizeof(int), 8,
+                                cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpy2DAsync(s.pred_hist, HIST_CAP * sizeof(int), tmp, keep * sizeof(int), keep * sizeof(int), 8,
+                                cudaMemcpyDeviceToDevice, st));
+      b->pred_off[i] = 0;
+    }
+  }
+  if (src) b->n_src = keep; else b->n_pred = keep;
+  upload_slot_table(b, st);
 }
 
 }  // namespace
@@ -214,8 +257,10 @@ int svanon_batch_setup(svanon_batch* b, int enc_win, int dec_win, int max_seq_fr
       s.enc_win = 0;                 // the stream is driven by the batch now, not by svanon_stream_process_chunk
       s.dec_win = dec_win; s.max_seq_frames = max_seq_frames; s.buffer_frames = buffer_frames;
       s.chunk = chunk; s.n_src = 0; s.n_pred = 0; s.delay_prefilled = false;
-      ptrs[i] = {s.src_hist, s.pred_hist, s.ref_audio_dev, s.ref_frames};
+      ptrs[i] = {s.src_hist, s.pred_hist, s.ref_audio_dev, s.ref_frames, 0, 0};
     }
+    b->src_off.assign(n, 0);
+    b->pred_off.assign(n, 0);
     b->ptrs_dev = dmalloc<SlotPtrs>(n);
     SV_CUDA(cudaMemcpy(b->ptrs_dev, ptrs.data(), (size_t)n * sizeof(SlotPtrs), cudaMemcpyHostToDevice));
     b->n_src = 0; b->n_pred = 0; b->voc_fed = 0; b->delay_prefilled = false;
@@ -259,27 +304,20 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     } else if (b->enc_state.enabled) e.enc_window_step(b->enc_state, b->wave_ring, n, b->enc_win, c, b->ids_win, st);
     else e.enc_encode(b->wave_ring, n, (long long)nw, b->ids_win, st);
     if (b->timing) SV_CUDA(cudaEventRecord(b->ev[1], st));
-    if (b->n_src + c > HIST_CAP) {
-      const int keep = HIST_CAP / 2;
-      long long* tmp = (long long*)e.ws.base;
-      for (auto* sh : b->streams) {
-        Stream& s = sh->st;
-        SV_CUDA(cudaMemcpyAsync(tmp, s.src_hist + (b->n_src - keep), keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
-        SV_CUDA(cudaMemcpyAsync(s.src_hist, tmp, keep * sizeof(long long), cudaMemcpyDeviceToDevice, st));
-      }
-      b->n_src = keep;
-    }
+    int max_src_off = 0, max_pred_off = 0;
+    for (int i = 0; i < n; ++i) { max_src_off = std::max(max_src_off, b->src_off[i]); max_pred_off = std::max(max_pred_off, b->pred_off[i]); }
+    if (b->n_src + max_src_off + c > HIST_CAP) compact_histories(b, true, st);
     launch_pdl(batch_take_ids_kernel, dim3((n * c + 127) / 128), dim3(128), 0, st, (const SlotPtrs*)b->ptrs_dev,
                (const long long*)b->ids_win, b->enc_win, c, b->n_src, b->step_ids, n);
     SV_LAUNCHED();
     b->n_src += c;
-    for (auto* sh : b->streams) sh->st.n_src = b->n_src;
+    for (int i = 0; i < n; ++i) b->streams[i]->st.n_src = b->n_src + b->src_off[i];
     // 3./4. warm-up phases (:519-525) -- the streams started together and share the delay
     bool silent = false;
     if (b->n_src < b->delay) {
       silent = true;
     } else if (!b->delay_prefilled && b->delay != 0) {
-      for (auto* sh : b->streams) e.ar_prefill_delay(sh->st, sh->st.src_hist + (b->n_src - b->delay), b->delay, st);
+      for (auto* sh : b->streams) e.ar_prefill_delay(sh->st, sh->st.src_hist + (sh->st.n_src - b->delay), b->delay, st);
       b->delay_prefilled = true;
       silent = true;
     }
@@ -293,16 +331,9 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     for (int i = 0; i < n; ++i) ss[i] = &b->streams[i]->st;
     const bool persistent = b->ar_path == 0 && (n == 1 || n == 2 || n == 4);
     for (int j = 0; j < c; ++j) {
-      if (b->n_pred >= HIST_CAP) {     // keep the newest half (the reference keeps at most 2048 entries, :593-594)
-        const int keep = HIST_CAP / 2;
-        int* tmp = (int*)e.ws.base;
-        for (Stream* s : ss) {
-          SV_CUDA(cudaMemcpy2DAsync(tmp, keep * sizeof(int), s->pred_hist + (b->n_pred - keep), HIST_CAP * sizeof(int),
-                                    keep * sizeof(int), 8, cudaMemcpyDeviceToDevice, st));
-          SV_CUDA(cudaMemcpy2DAsync(s->pred_hist, HIST_CAP * sizeof(int), tmp, keep * sizeof(int), keep * sizeof(int), 8,
-                                    cudaMemcpyDeviceToDevice, st));
-        }
-        b->n_pred = keep;
+      if (b->n_pred + max_pred_off >= HIST_CAP) {     // keep the newest half (the reference keeps at most 2048 entries, :593-594)
+        compact_histories(b, false, st);
+        max_pred_off = 0;
       }
       for (int i = 0; i < n; ++i) {
         Stream& s = *ss[i];
@@ -310,16 +341,16 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
         s.step_cond_row = nullptr;
         s.step_noise = nz ? nz + (size_t)i * per_noise + (size_t)j * 8 * AR_CB_SIZE : nullptr;
         s.step_pred_hist = s.pred_hist;
-        s.step_pred_col = b->n_pred;
+        s.step_pred_col = b->n_pred + b->pred_off[i];
       }
       if (persistent) {
         e.ar_decode_step(ss.data(), n, st);
-        for (Stream* s : ss) launch_append_codes(s->codes_dev, s->pred_hist, HIST_CAP, b->n_pred, st);
+        for (int i = 0; i < n; ++i) launch_append_codes(ss[i]->codes_dev, ss[i]->pred_hist, HIST_CAP, b->n_pred + b->pred_off[i], st);
       } else {
         e.ar_decode_step_gemm(ss.data(), n, st);
       }
       b->n_pred += 1;
-      for (Stream* s : ss) s->n_pred = b->n_pred;
+      for (int i = 0; i < n; ++i) ss[i]->n_pred = b->n_pred + b->pred_off[i];
     }
     if (b->timing) SV_CUDA(cudaEventRecord(b->ev[2], st));
     // 6. re-prompt (:547-564): per stream, on its own schedule (prompt lengths differ)
@@ -348,6 +379,119 @@ int svanon_batch_process_chunk(svanon_batch* b, const float* wave_chunks, int n_
     if (b->timing) { SV_CUDA(cudaEventRecord(b->ev[4], st)); b->ev_valid = true; }
     b->voc_fed += c;
     a.finish();
+  });
+}
+
+// Two cohorts that have both left their warm-up (delay prefilled, vocoder primed) become ONE lock-step batch: the members
+// of `a` followed by the members of `b`, each with the state it had -- wave ring, encoder window state (or stateful-encoder
+// state), vocoder histories -- so every stream keeps producing exactly what it produces alone, and the step after the merge
+// makes one pass over the weights for everybody.  `a` and `b` are left empty (destroy them).  The members' history columns
+// differ (the cohorts started at different chunks): the merged batch counts like `a` and carries a per-member offset.
+int svanon_batch_merge(svanon_batch* a, svanon_batch* b, svanon_batch** out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(a && b && out && a != b, "bad arguments");
+    SV_CHECK(a->owner == b->owner, "batches of different engines");
+    SV_CHECK(a->enc_win > 0 && b->enc_win > 0, "svanon_batch_setup has not been called on both batches");
+    SV_CHECK(a->enc_win == b->enc_win && a->dec_win == b->dec_win && a->max_seq_frames == b->max_seq_frames &&
+                 a->buffer_frames == b->buffer_frames && a->chunk == b->chunk && a->delay == b->delay,
+             "batches with different stream settings cannot merge");
+    SV_CHECK(a->enc_stateful == b->enc_stateful && a->enc_state.enabled == b->enc_state.enabled &&
+                 a->enc_state.tail_hist_min_streams == b->enc_state.tail_hist_min_streams, "batches with different encoder modes");
+    SV_CHECK(a->voc_fed > 0 && b->voc_fed > 0 && (a->delay == 0 || (a->delay_prefilled && b->delay_prefilled)),
+             "both batches must be past their warm-up chunks (delay prefilled, first frame decoded)");
+    Engine& e = a->owner->eng;
+    SV_CUDA(cudaSetDevice(e.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int na = (int)a->streams.size(), nb = (int)b->streams.size(), n = na + nb;
+    auto* c = new svanon_batch();
+    std::unique_ptr<svanon_batch> guard(c);
+    c->owner = a->owner;
+    c->streams = a->streams;
+    c->streams.insert(c->streams.end(), b->streams.begin(), b->streams.end());
+    c->enc_win = a->enc_win; c->dec_win = a->dec_win; c->max_seq_frames = a->max_seq_frames; c->buffer_frames = a->buffer_frames;
+    c->chunk = a->chunk; c->delay = a->delay; c->ar_path = a->ar_path;
+    c->n_src = a->n_src; c->n_pred = a->n_pred; c->voc_fed = std::min(a->voc_fed, b->voc_fed); c->delay_prefilled = true;
+    c->src_off = a->src_off; c->pred_off = a->pred_off;
+    for (int i = 0; i < nb; ++i) {
+      c->src_off.push_back(b->n_src + b->src_off[i] - a->n_src);
+      c->pred_off.push_back(b->n_pred + b->pred_off[i] - a->n_pred);
+    }
+    int lo_src = 0, lo_pred = 0;                      // keep every offset >= 0: count like the member that is furthest behind
+    for (int i = 0; i < n; ++i) { lo_src = std::min(lo_src, c->src_off[i]); lo_pred = std::min(lo_pred, c->pred_off[i]); }
+    c->n_src += lo_src; c->n_pred += lo_pred;
+    for (int i = 0; i < n; ++i) { c->src_off[i] -= lo_src; c->pred_off[i] -= lo_pred; }
+    const size_t nw = (size_t)c->enc_win * SAMPLES_PER_FRAME;
+    c->wave_ring = dmalloc<float>(nw * n);
+    c->wave_ring_tmp = dmalloc<float>(nw * n);
+    c->ids_win = dmalloc<long long>((size_t)c->enc_win * n);
+    c->codes_win = dmalloc<long long>((size_t)8 * c->chunk * n);
+    c->step_ids = dmalloc<long long>((size_t)c->chunk * n);
+    auto cat = [&](float* dst, const float* pa, const float* pb, size_t per) {      // [na][per] ++ [nb][per]
+      SV_CUDA(cudaMemcpyAsync(dst, pa, per * na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpyAsync(dst + per * na, pb, per * nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    };
+    cat(c->wave_ring, a->wave_ring, b->wave_ring, nw);
+    // ---- encoder state
+    c->enc_stateful = a->enc_stateful;
+    c->enc_state.enabled = a->enc_state.enabled;
+    c->enc_state.tail_hist_min_streams = a->enc_state.tail_hist_min_streams;
+    if (c->enc_stateful) {
+      SV_CHECK(a->enc_stream.wave && b->enc_stream.wave && a->enc_stream.pos > 0 && b->enc_stream.pos > 0, "stateful encoder state missing");
+      e.enc_stream_init(c->enc_stream, n);
+      EncStream &ea = a->enc_stream, &eb = b->enc_stream, &ec = c->enc_stream;
+      cat(ec.wave, ea.wave, eb.wave, ENC_STREAM_WAVE);
+      const size_t per_kv = (size_t)ENC_HEADS * ENC_RING * HEAD_DIM;
+      for (int l = 0; l < ENC_LAYERS; ++l) {
+        cat(ec.kc + (size_t)l * n * per_kv, ea.kc + (size_t)l * na * per_kv, eb.kc + (size_t)l * nb * per_kv, per_kv);
+        cat(ec.vc + (size_t)l * n * per_kv, ea.vc + (size_t)l * na * per_kv, eb.vc + (size_t)l * nb * per_kv, per_kv);
+      }
+      // positions: the merged state counts like `a`; b's members carry the difference (ring slot = position % ring size)
+      ec.pos = ea.pos;
+      for (int i = 0; i < na; ++i) ec.off[i] = ea.off[i];
+      for (int i = 0; i < nb; ++i) ec.off[na + i] = eb.pos + eb.off[i] - ea.pos;
+      SV_CUDA(cudaMemcpyAsync(ec.off_dev, ec.off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, st));
+      const int dims[4] = {128, 256, 384, 512}, depths[4] = {3, 3, 9, 3};
+      cat(ec.hist.mel, ea.hist.mel, eb.hist.mel, (size_t)6 * N_MELS);
+      int j = 0;
+      for (int s4 = 0; s4 < 4; ++s4)
+        for (int d = 0; d < depths[s4]; ++d, ++j) cat(ec.hist.blk[j], ea.hist.blk[j], eb.hist.blk[j], (size_t)6 * dims[s4]);
+      for (int d = 0; d < 2; ++d, ++j) cat(ec.hist.blk[j], ea.hist.blk[j], eb.hist.blk[j], (size_t)6 * 512);
+    } else if (a->enc_state.valid && b->enc_state.valid && a->enc_state.S == b->enc_state.S &&
+               a->enc_state.hist_valid == b->enc_state.hist_valid) {
+      EncWindowState &sa = a->enc_state, &sb = b->enc_state, &sc = c->enc_state;
+      const int S = sa.S;
+      for (auto& p : sc.xt) SV_CUDA(cudaMalloc(&p, (size_t)n * S * ENC_DIM * sizeof(float)));
+      sc.B = n; sc.S = S; sc.cur = 0; sc.valid = true;
+      cat(sc.xt[0], sa.xt[sa.cur], sb.xt[sb.cur], (size_t)S * ENC_DIM);
+      sc.hist_valid = sa.hist_valid;
+      if (sc.hist_valid) {
+        sc.hist.alloc(n);
+        const int dims[4] = {128, 256, 384, 512}, depths[4] = {3, 3, 9, 3};
+        cat(sc.hist.mel, sa.hist.mel, sb.hist.mel, (size_t)6 * N_MELS);
+        int j = 0;
+        for (int s4 = 0; s4 < 4; ++s4)
+          for (int d = 0; d < depths[s4]; ++d, ++j) cat(sc.hist.blk[j], sa.hist.blk[j], sb.hist.blk[j], (size_t)6 * dims[s4]);
+        for (int d = 0; d < 2; ++d, ++j) cat(sc.hist.blk[j], sa.hist.blk[j], sb.hist.blk[j], (size_t)6 * 512);
+      }
+    } else {
+      c->enc_state.valid = false;                      // the next step re-encodes the whole window once (same ids)
+    }
+    // ---- vocoder histories
+    e.voc_state_init(c->voc, c->chunk, n);
+    voc_state_concat(c->voc, a->voc, b->voc, st);
+    if (a->timing || b->timing) {
+      for (auto& ev : c->ev) SV_CUDA(cudaEventCreate(&ev));
+      c->timing = true;
+    }
+    upload_slot_table(c, st);                         // synchronises: the copies above are complete
+    for (int i = 0; i < n; ++i) {
+      Stream& s = c->streams[i]->st;
+      s.n_src = c->n_src + c->src_off[i];
+      s.n_pred = c->n_pred + c->pred_off[i];
+    }
+    a->streams.clear(); a->enc_win = 0;
+    b->streams.clear(); b->enc_win = 0;
+    *out = guard.release();
   });
 }
 

@@ -33,11 +33,12 @@ __device__ __forceinline__ float er_warp_sum(float v) {
 
 // ring[l][b][h][slot][64] <- k / v of the push's rows (row r = b * c + j sits at position pos0 + j)
 __global__ void __launch_bounds__(256) enc_ring_append_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
-                                                              float* __restrict__ vc, int c, long long pos0) {
+                                                              float* __restrict__ vc, int c, long long pos0,
+                                                              const long long* __restrict__ off) {
   pdl_trigger();
   pdl_wait();
   const int r = blockIdx.x, b = r / c, j = r % c;
-  const int slot = (int)((pos0 + j) % ENC_RING);
+  const int slot = (int)((pos0 + off[b] + j) % ENC_RING);
   const float* row = qkv + (long long)r * 3 * ENC_DIM;
   for (int i = threadIdx.x; i < ENC_DIM; i += blockDim.x) {
     const int h = i / HEAD_DIM, d = i % HEAD_DIM;
@@ -51,13 +52,14 @@ __global__ void __launch_bounds__(256) enc_ring_append_kernel(const float* __res
 // grid (ENC_HEADS, rows); 4 warps walk the keys (lane = interleaved pair), online softmax per warp, merged in warp order.
 __global__ void __launch_bounds__(ER_WARPS * 32) enc_attn_ring_kernel(const float* __restrict__ qkv, const float* __restrict__ kc,
                                                                       const float* __restrict__ vc, const float* __restrict__ rope,
-                                                                      float* __restrict__ y, int c, long long pos0) {
+                                                                      float* __restrict__ y, int c, long long pos0,
+                                                                      const long long* __restrict__ off) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sm[ER_WARPS][2 + HEAD_DIM];
   const int h = blockIdx.x, r = blockIdx.y, b = r / c, j = r % c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long p = pos0 + j;
+  const long long p = pos0 + off[b] + j;
   const long long lo = p >= ENC_WINDOW ? p - (ENC_WINDOW - 1) : 0;
   const long long base = lo >= ENC_POS_PERIOD ? (lo / ENC_POS_PERIOD) * ENC_POS_PERIOD : 0;
   const float* kh = kc + ((long long)b * ENC_HEADS + h) * ENC_RING * HEAD_DIM;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(ER_WARPS * 32) enc_attn_ring_kernel(const floa
 }  // namespace
 
 EncStream::~EncStream() {
-  for (void* p : {(void*)wave, (void*)kc, (void*)vc})
+  for (void* p : {(void*)wave, (void*)kc, (void*)vc, (void*)off_dev})
     if (p) cudaFree(p);
 }
 
@@ -111,10 +113,13 @@ void Engine::enc_stream_init(EncStream& es, int B) {
   SV_CHECK(finalized[MODEL_TOKENIZER], "tokenizer weights not finalized");
   SV_CHECK(enc_rope_stream, "the tokenizer was loaded without its long RoPE table (quantizer.pre_module.freqs_cis_stream)");
   SV_CHECK(B >= 1, "streams per encoder state");
-  for (void* p : {(void*)es.wave, (void*)es.kc, (void*)es.vc})
+  for (void* p : {(void*)es.wave, (void*)es.kc, (void*)es.vc, (void*)es.off_dev})
     if (p) cudaFree(p);
   es.B = B;
   es.pos = 0;
+  es.off.assign(B, 0);
+  SV_CUDA(cudaMalloc(&es.off_dev, (size_t)B * sizeof(long long)));
+  SV_CUDA(cudaMemset(es.off_dev, 0, (size_t)B * sizeof(long long)));
   const size_t nw = (size_t)B * ENC_STREAM_WAVE;
   const size_t nkv = (size_t)ENC_LAYERS * B * ENC_HEADS * ENC_RING * HEAD_DIM;
   SV_CUDA(cudaMalloc(&es.wave, nw * sizeof(float)));
@@ -129,6 +134,8 @@ void Engine::enc_stream_init(EncStream& es, int B) {
 void Engine::enc_stream_reset(EncStream& es, cudaStream_t st) {
   SV_CHECK(es.wave, "encoder stream not initialised");
   es.pos = 0;                                   // the next push starts an utterance: zero left context everywhere
+  es.off.assign(es.B, 0);
+  SV_CUDA(cudaMemsetAsync(es.off_dev, 0, (size_t)es.B * sizeof(long long), st));
   SV_CUDA(cudaMemsetAsync(es.wave, 0, (size_t)es.B * ENC_STREAM_WAVE * sizeof(float), st));
 }
 
@@ -172,10 +179,11 @@ void Engine::enc_push(EncStream& es, const float* wave_chunk, long long pitch, i
     p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = M; p.N = 3 * ENC_DIM; p.K = ENC_DIM; p.lda = ENC_DIM; p.ldc = 3 * ENC_DIM;
     launch_gemm(p, st);
     launch_pdl(enc_ring_append_kernel, dim3(M), dim3(256), 0, st, (const float*)qkv, es.kc + l * layer_kv, es.vc + l * layer_kv, c,
-               es.pos);
+               es.pos, (const long long*)es.off_dev);
     SV_LAUNCHED();
     launch_pdl(enc_attn_ring_kernel, dim3(ENC_HEADS, M), dim3(ER_WARPS * 32), 0, st, (const float*)qkv,
-               (const float*)(es.kc + l * layer_kv), (const float*)(es.vc + l * layer_kv), enc_rope_stream, y, c, es.pos);
+               (const float*)(es.kc + l * layer_kv), (const float*)(es.vc + l * layer_kv), enc_rope_stream, y, c, es.pos,
+               (const long long*)es.off_dev);
     SV_LAUNCHED();
     GemmParams po;
     po.A = y; po.W = L.wo; po.C = xt; po.gamma = L.ls_attn; po.residual = xt; po.M = M; po.N = ENC_DIM; po.K = ENC_DIM;

@@ -182,11 +182,16 @@ struct EncStream {
   ConvStackHist hist;                         // per-layer causal-conv history
   float* wave = nullptr;                      // [B][ENC_STREAM_WAVE]
   float *kc = nullptr, *vc = nullptr;         // [ENC_LAYERS][B][ENC_HEADS][ENC_RING][64], keys UNROTATED
+  long long* off_dev = nullptr;               // [B] member position = pos + off (non-zero only after a cohort merge)
+  std::vector<long long> off;
   EncStream() = default;
   EncStream(const EncStream&) = delete;
   EncStream& operator=(const EncStream&) = delete;
   ~EncStream();
 };
+
+std::vector<SBuf*> voc_state_bufs(VocState& vs);                                        // voc_stream.cu
+void voc_state_concat(VocState& dst, VocState& a, VocState& b, cudaStream_t st);       // dst <- a's streams, then b's
 
 constexpr int HIST_CAP = 4096;     // columns kept of src_content_codes / pred_codes (the reference trims to 2048)
 

@@ -117,6 +117,7 @@ __device__ long long g_tc_prof[16];
 constexpr int TC_PRODUCER_WARPS = 16;              // warps 0-15: global -> registers -> hi/lo split -> swizzled tiles; epilogue
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
 constexpr int TC_THREADS = TC_PRODUCERS + 32;      // warp 16: MMA issuer (one elected lane)
+constexpr int TC_DEPTH_SMALL = 4;                  // ... on the 128 x 64 tile (see the kernel)
 constexpr int TC_DEPTH = 2;                        // K-slabs a producer thread keeps in flight in registers (2, 3 and 4
                                                    // measure the same: the loop is not bound by load latency)
 
@@ -150,7 +151,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   constexpr int TKE = HALF ? 2 * TK : TK;                             // K elements per slab
   constexpr int AV = HALF ? 2 : 1;                                    // float4 loads per 16-byte A chunk
   constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = BN * 8 / TC_PRODUCERS;   // 16-byte chunks per thread
-  constexpr int D = (HALF && BN == 256) ? 1 : TC_DEPTH;   // fp16 slabs are twice as deep in K; 2 of them spill at BN = 256
+  // K-slabs a producer thread keeps in flight in registers.  Wide tiles are MMA-bound (2, 3 and 4 measure the same); the
+  // 128 x 64 tile of the small, latency-bound problems pays one L2 round trip per D slabs (0.35-0.5 us per slab at D = 2:
+  // profiles/README.md timeline), and has the registers for 4.  fp16 slabs are twice as deep in K; 2 of them spill at BN = 256.
+  constexpr int D = (HALF && BN == 256) ? 1 : (BN == 64 && !HALF && TC_DEPTH_SMALL > TC_DEPTH ? TC_DEPTH_SMALL : TC_DEPTH);
   static_assert(TBM * BN <= STAGES * STAGE_FLOATS, "partial tile must fit the pipeline shared memory");
   static_assert(A_PER >= 1 && B_PER >= 1, "tile too small for the producer count");
   extern __shared__ unsigned char dsmem_raw[];

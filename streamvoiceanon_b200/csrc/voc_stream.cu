@@ -100,6 +100,34 @@ void Engine::voc_state_init(VocState& vs, int c, int B) {
   vs.primed_frames = 0;
 }
 
+// every history buffer of a state, in a fixed order (the same for every state of the same frames-per-step)
+std::vector<SBuf*> voc_state_bufs(VocState& vs) {
+  std::vector<SBuf*> all = {&vs.u1, &vs.u2, &vs.p0, &vs.c0};
+  for (int i = 0; i < 5; ++i) {
+    VocState::Level& L = vs.lv[i];
+    all.push_back(&L.x);
+    for (int j = 0; j < 3; ++j) {
+      for (int d = 0; d < 3; ++d) all.push_back(&L.t[j][d]);
+      for (int d = 0; d < 2; ++d) all.push_back(&L.r[j][d]);
+    }
+    all.push_back(&L.next);
+  }
+  return all;
+}
+
+// dst (B = na + nb streams) <- the histories of a's streams followed by b's
+void voc_state_concat(VocState& dst, VocState& a, VocState& b, cudaStream_t st) {
+  SV_CHECK(a.c == b.c && dst.c == a.c && dst.B == a.B + b.B, "vocoder states do not match");
+  auto bd = voc_state_bufs(dst), ba = voc_state_bufs(a), bb = voc_state_bufs(b);
+  for (size_t i = 0; i < bd.size(); ++i) {
+    SV_CHECK(bd[i]->seg == ba[i]->seg && bd[i]->seg == bb[i]->seg, "vocoder state layouts differ");
+    SV_CUDA(cudaMemcpyAsync(bd[i]->base, ba[i]->base, (size_t)ba[i]->seg * a.B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SV_CUDA(cudaMemcpyAsync(bd[i]->base + bd[i]->seg * a.B, bb[i]->base, (size_t)bb[i]->seg * b.B * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+  }
+  dst.primed_frames = std::min(a.primed_frames, b.primed_frames);
+}
+
 void Engine::voc_state_reset(VocState& vs, cudaStream_t st) {
   if (vs.arena) SV_CUDA(cudaMemsetAsync(vs.arena, 0, vs.arena_floats * sizeof(float), st));
   vs.primed_frames = 0;

@@ -5,8 +5,11 @@ phases").
 the loop (`process_one_chunk`, evaluations/infer_arvc.py:519-525: silent chunks until `delay` ids are there, then the
 delay prefill) are shared by the batch.  A server sees streams arrive and leave at any chunk boundary.  `StreamPool`
 puts the streams that arrive at the same boundary (and use the same `delay`) into one COHORT = one `BatchSession`;
-every `step` advances all cohorts, one library call each.  A stream that leaves stays in its cohort as a silent member
-(the batch-level encoder / vocoder state is laid out per member) until the cohort is empty, then the cohort is closed.
+every `step` advances all cohorts, one library call each.  Once a cohort has left its warm-up chunks it is MERGED into an
+older cohort of the same delay (`BatchSession.merged` / svanon_batch_merge: every member's wave ring, encoder and vocoder
+state moves into side-by-side buffers), so that in steady state the pool is back to one pass over the weights per chunk
+however the streams arrived.  A stream that leaves stays in its cohort as a silent member (the batch-level encoder /
+vocoder state is laid out per member) until the cohort is empty, then the cohort is closed.
 Each stream produces exactly what it produces alone (the `BatchSession` contract, tests/test_gpu_batch.py).
 
 The reference is one stream per process (`max_batch_size=1`, infer_arvc.py:56); its GUI loop
@@ -42,7 +45,7 @@ class StreamPool:
 
     def __init__(self, encode_window_frames: int = 128, decode_window_frames: int = 64, max_seq_frames: int = 768,
                  buffer_frames: int = 32, decode_chunk_frames: int = 1, max_cohort: int = 256,
-                 batch_factory: Optional[Callable] = None):
+                 batch_factory: Optional[Callable] = None, merge_cohorts: bool = True):
         if decode_chunk_frames < 1 or max_cohort < 1:
             raise ValueError("decode_chunk_frames and max_cohort must be >= 1")
         self._cfg = dict(encode_window_frames=encode_window_frames, decode_window_frames=decode_window_frames,
@@ -53,6 +56,8 @@ class StreamPool:
             from .streaming import BatchSession
             batch_factory = BatchSession
         self._batch_factory = batch_factory
+        self._merge = merge_cohorts and hasattr(batch_factory, "merged")
+        self.merges = 0
         self._pending: Dict[Hashable, object] = {}          # key -> session, joined since the last step
         self._cohorts: List[_Cohort] = []
         self._where: Dict[Hashable, tuple] = {}             # key -> (cohort, index)
@@ -119,12 +124,43 @@ class StreamPool:
                     self._where[k] = (cohort, i)
         self._pending.clear()
 
+    def _warm(self, cohort: _Cohort) -> bool:
+        """Past the warm-up chunks of the loop (evaluations/infer_arvc.py:519-525): `delay` ids collected, the delay prefill
+        done and one frame decoded -- from then on every chunk of the cohort is a plain decode step."""
+        need = 1 if cohort.delay == 0 else -(-cohort.delay // self._cfg["decode_chunk_frames"]) + 1
+        return cohort.steps >= need + 1
+
+    def _merge_warm_cohorts(self) -> None:
+        """Folds every warm cohort into the oldest warm cohort of the same delay while the result fits max_cohort."""
+        by_delay: Dict[int, _Cohort] = {}
+        for cohort in list(self._cohorts):
+            if not self._warm(cohort):
+                continue
+            host = by_delay.get(cohort.delay)
+            if host is None or len(host.keys) + len(cohort.keys) > self.max_cohort:
+                if host is None:
+                    by_delay[cohort.delay] = cohort
+                continue
+            merged = self._batch_factory.merged(host.batch, cohort.batch)
+            host.batch = merged
+            base = len(host.keys)
+            host.keys += cohort.keys
+            host.sessions += cohort.sessions
+            host.live += cohort.live
+            for i, k in enumerate(cohort.keys):
+                if k in self._where and self._where[k][0] is cohort:
+                    self._where[k] = (host, base + i)
+            self._cohorts.remove(cohort)
+            self.merges += 1
+
     # ------------------------------------------------------------------------------------------ the loop
     def step(self, chunks: Dict[Hashable, torch.Tensor]) -> Dict[Hashable, torch.Tensor]:
         """One chunk period for every stream of the pool."""
         for key in chunks:
             if key not in self:
                 raise KeyError(f"chunk for unknown stream {key!r}")
+        if self._merge:
+            self._merge_warm_cohorts()
         self._admit()
         out: Dict[Hashable, torch.Tensor] = {}
         for cohort in list(self._cohorts):

@@ -165,6 +165,21 @@ class BatchSession:
             s._n_src = 0
             s._prefilled = False
 
+    @classmethod
+    def merged(cls, a: "BatchSession", b: "BatchSession") -> "BatchSession":
+        """One lock-step batch out of two that are both past their warm-up chunks (same settings): a's streams followed by
+        b's, every stream with the state it had (svanon_batch_merge).  `a` and `b` are closed."""
+        if a._engine is not b._engine:
+            raise ValueError("batches of different engines")
+        h = C.c_void_p()
+        _lib.check(a._engine.lib.svanon_batch_merge(a._h, b._h, C.byref(h), C.c_void_p(_cuda_stream_ptr())))
+        m = cls.__new__(cls)
+        m.sessions = a.sessions + b.sessions
+        m._engine, m._h, m.chunk = a._engine, h, a.chunk
+        a.close()
+        b.close()
+        return m
+
     def set_ar_path(self, path: int):
         """0: persistent kernel for 1/2/4 streams, many-stream kernels otherwise; 1: always the many-stream kernels."""
         _lib.check(self._engine.lib.svanon_batch_set_ar_path(self._h, path))

@@ -168,7 +168,7 @@ def test_stream_pool_equals_single_sessions(models, tape):
         singles.append((*sess.history(), waves))
         sess.close()
     sessions = [_session(inp, tape(7400 + b), delay) for b, inp in enumerate(inputs)]
-    pool = StreamPool(**cfg)
+    pool = StreamPool(merge_cohorts=False, **cfg)
     join = {0: 0, 1: 0, 2: 3}                       # stream 2 arrives three chunks later -> its own cohort
     got = {b: [] for b in range(3)}
     for step in range(n_chunks + 3):
@@ -184,6 +184,57 @@ def test_stream_pool_equals_single_sessions(models, tape):
             pool.remove(0)                          # streams 0 and 1 are done; 1 leaves last and closes the cohort
             pool.remove(1)
             assert pool.n_cohorts == 1
+    for b, sess in enumerate(sessions):
+        src_hist, pred_hist = sess.history()
+        assert torch.equal(src_hist[: singles[b][0].numel()], singles[b][0]), b
+        assert torch.equal(pred_hist[:, : singles[b][1].shape[1]], singles[b][1]), b
+        mse = float(((torch.cat(got[b]) - singles[b][2]) ** 2).mean())
+        assert mse < 1e-10, (b, mse)
+    pool.close()
+    for s in sessions:
+        s.close()
+
+
+@pytest.mark.parametrize("enc_mode", [1, 3])
+def test_stream_pool_merges_cohorts(models, tape, enc_mode):
+    """Cohort merging (svanon_batch_merge): three streams arrive at chunks 0, 0 and 3; once the late cohort has left its
+    warm-up it is folded into the first one -- wave rings, encoder window state (enc_mode 1) or stateful-encoder state with
+    its K/V rings (enc_mode 3), vocoder histories and history columns move over -- and every stream still produces what it
+    produces alone: ids bit-exact, waveform to fp32 rounding.  Small windows, so that re-prompts fire after the merge."""
+    from streamvoiceanon_b200 import BatchSession
+    from streamvoiceanon_b200.server import StreamPool
+    _, tok, _ = models
+    n_chunks, delay = 16, 2
+    cfg = dict(encode_window_frames=24, decode_window_frames=24, max_seq_frames=52, buffer_frames=6, decode_chunk_frames=1)
+    inputs = [_stream_inputs(tok, b, 26 + 5 * b, n_chunks, 1) for b in range(3)]
+    singles = []
+    for b, inp in enumerate(inputs):
+        sess = _session(inp, tape(7450 + b), delay)
+        sess.set_encoder_mode(enc_mode)
+        sess.setup(**cfg)
+        waves = torch.cat([sess.process_chunk(inp[4][i].cuda()).cpu() for i in range(n_chunks)])
+        singles.append((*sess.history(), waves))
+        sess.close()
+    sessions = [_session(inp, tape(7450 + b), delay) for b, inp in enumerate(inputs)]
+
+    class ModeBatch(BatchSession):
+        def setup(self, **kw):
+            self.set_encoder_mode(enc_mode)
+            super().setup(**kw)
+    pool = StreamPool(batch_factory=ModeBatch, **cfg)
+    join = {0: 0, 1: 0, 2: 3}
+    got = {b: [] for b in range(3)}
+    sizes = []
+    for step in range(n_chunks + 3):
+        for b, at in join.items():
+            if at == step:
+                pool.add(b, sessions[b])
+        chunks = {b: inputs[b][4][step - join[b]].cuda() for b in range(3) if b in pool and step - join[b] < n_chunks}
+        for b, w in pool.step(chunks).items():
+            if b in chunks:
+                got[b].append(w.cpu())
+        sizes.append(pool.cohort_sizes())
+    assert [2, 1] in sizes and sizes[-1] == [3] and pool.merges == 1          # two cohorts for a while, then one
     for b, sess in enumerate(sessions):
         src_hist, pred_hist = sess.history()
         assert torch.equal(src_hist[: singles[b][0].numel()], singles[b][0]), b

@@ -99,3 +99,44 @@ def test_membership_errors_and_cohort_size_limit():
     assert all(b.closed for b in FakeBatch.log) and pool.n_cohorts == 0
     with pytest.raises(ValueError):
         StreamPool(max_cohort=0)
+
+
+class FakeMergeBatch(FakeBatch):
+    """A stand-in that can merge: every member keeps its own chunk counter."""
+
+    def __init__(self, sessions):
+        super().__init__(sessions)
+        self.counts = [0] * len(self.sessions)
+
+    def process_chunk(self, waves):
+        assert not self.closed and waves.shape[0] == len(self.sessions)
+        self.counts = [c + 1 for c in self.counts]
+        return torch.stack([s.gain * w + c for s, w, c in zip(self.sessions, waves, self.counts)])
+
+    @classmethod
+    def merged(cls, a, b):
+        m = cls(a.sessions + b.sessions)
+        m.cfg, m.counts = a.cfg, a.counts + b.counts
+        a.close()
+        b.close()
+        return m
+
+
+def test_warm_cohorts_merge_and_keep_their_members_state():
+    FakeBatch.log = []
+    pool = StreamPool(decode_chunk_frames=1, batch_factory=FakeMergeBatch)
+    pool.add("a", FakeSession(1.0))
+    pool.add("b", FakeSession(2.0))
+    pool.step({"a": _chunk(0), "b": _chunk(0)})
+    pool.add("c", FakeSession(3.0))                                                # one chunk later: its own cohort
+    sizes = []
+    for _ in range(6):
+        out = pool.step({k: _chunk(0) for k in ("a", "b", "c")})
+        sizes.append(pool.cohort_sizes())
+    assert sizes[0] == [2, 1] and sizes[-1] == [3] and pool.merges == 1            # merged once c's cohort was warm
+    assert float(out["a"][0]) == 7.0 and float(out["c"][0]) == 6.0                 # every member kept its own count
+    pool.remove("a")
+    out = pool.step({"b": _chunk(1), "c": _chunk(1)})                              # a stays a silent member of the merged cohort
+    assert set(out) == {"b", "c"} and pool.cohort_sizes() == [3]
+    assert float(out["b"][0]) == 2.0 + 8 and float(out["c"][0]) == 3.0 + 7
+    pool.close()
