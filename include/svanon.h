@@ -149,6 +149,11 @@ int svanon_set_precision(int mode);
 int svanon_set_pdl(int enable);
 int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N,
                       int K, int act, void* cuda_stream);
+/* test hook: 1 = svanon_debug_gemm treats W like an engine weight -- the tensor-core kernel then takes its B operand by TMA
+ * bulk copies from a pre-split (hi / lo or fp16), pre-tiled copy of W made for the call and dropped after it; 0 (default) =
+ * W is caller memory and goes through the producers' register path; 2 = like 1 but the copy is kept (micro-benchmarks that
+ * call again with the same, unchanged W) */
+int svanon_debug_gemm_weights_static(int enable);
 
 /* test hook: the general form of the GEMM contract the conv layers use (common.cuh GemmParams) --
  *   C[m][c_col0 + n] = bias[n] + sum_t sum_k A[(a_row0 + m * a_row_step + tap_off[t]) * lda + k] * W[t][n][k]

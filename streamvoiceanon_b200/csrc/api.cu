@@ -14,6 +14,7 @@ void tc_prof_dump();
 namespace svanon {
 thread_local std::string g_api_err;
 }
+static int g_debug_gemm_static = 0;         // svanon_debug_gemm_weights_static: 0 off, 1 static + dropped after the call, 2 static + kept
 
 namespace {
 
@@ -429,6 +430,11 @@ int svanon_set_gemm_mode(int mode) {
   });
 }
 
+int svanon_debug_gemm_weights_static(int enable) {
+  g_debug_gemm_static = enable;
+  return 0;
+}
+
 int svanon_set_precision(int mode) {
   return guarded([&] {
     SV_CHECK(mode == 0 || mode == 1, "precision: 0 = fp32-grade (3xTF32 split, parity mode), 1 = fp16 single-pass tensor-core GEMMs (perf mode)");
@@ -445,9 +451,10 @@ int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const fl
     p.A = a.in(A, (size_t)M * K); p.W = a.in(W, (size_t)N * K); p.bias = a.in(bias, (size_t)N);
     p.C = a.out(C, (size_t)M * N);
     p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N; p.act = act;
-    p.w_static = false;                    // caller memory: never cached as an fp16 weight copy
+    p.w_static = g_debug_gemm_static != 0; // caller memory: normally never cached as a converted weight copy
     launch_gemm(p, a.st);
     a.finish();
+    if (g_debug_gemm_static == 1) gemm_forget_weights(p.W);
 #ifdef SVANON_TC_PROF
     tc_prof_dump();
 #endif

@@ -141,6 +141,10 @@ struct GemmParams {
   // false keeps a launch out of that registry (W is caller memory that may change: svanon_debug_gemm*).
   const void* Wh = nullptr;
   bool w_static = true;
+  // pre-tiled weight copies for the TMA B path of the tensor-core kernel (gemm_tc.cu): Wt[0] = hi term (or the fp16 copy),
+  // Wt[1] = lo term (null in perf mode), rows padded to wt_npad per (tap, K-slab); filled in by the launcher
+  const void* Wt[2] = {nullptr, nullptr};
+  int wt_npad = 0;
 };
 
 #ifdef __CUDACC__
@@ -178,6 +182,7 @@ __device__ __forceinline__ long long seg_row_off(long long row, int seg_rows, lo
 // perf mode switch of the tensor-core GEMM (gemm_tc.cu): single-pass fp16 MMAs instead of the 3xTF32 split
 extern bool g_gemm_half;
 void gemm_half_release();
+void gemm_forget_weights(const float* W);
 
 // measurement aid behind svanon_gemm_timing: per back end, summed event-timed launch durations and executed flops
 enum GemmBackend : int { GEMM_BACKEND_TC = 0, GEMM_BACKEND_PIPE = 1, GEMM_BACKEND_FP32 = 2, GEMM_BACKEND_CONV_SMALL = 3, GEMM_BACKENDS = 4 };

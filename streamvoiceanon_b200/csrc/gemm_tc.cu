@@ -175,9 +175,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   const int it_end = (int)((long long)total * (rank + 1) / split);
   const int n_it = it_end - it_begin;
 
+  // B operand by TMA: the weights exist pre-split (hi / lo, or fp16) and pre-tiled in HBM -- per (tap, K-slab) the rows of
+  // all output channels as 128-byte swizzled tile rows -- so the BN rows of a slab are ONE contiguous block per term and
+  // arrive with one cp.async.bulk each, completing on the stage's `full` barrier; the producer warps only handle A.
+  const bool tma_b = p.Wt[0] != nullptr;
   TC_MARK(0);
   pdl_trigger();
-  if (batch.wprefetch && tid < BN && n0 + tid < p.N && n_it > 0) {
+  if (tma_b && batch.wprefetch && tid < n_it) {
+    // this CTA's weight blocks: one per slab (and term), contiguous
+    const int it = it_begin + tid;
+    const int rows = min(BN, p.wt_npad - n0);
+    const long long off = ((long long)it * p.wt_npad + n0) * 128;
+    l2_prefetch_bulk(reinterpret_cast<const char*>(p.Wt[0]) + off, (unsigned)rows * 128u);
+    if (!HALF) l2_prefetch_bulk(reinterpret_cast<const char*>(p.Wt[1]) + off, (unsigned)rows * 128u);
+  }
+  if (!tma_b && batch.wprefetch && tid < BN && n0 + tid < p.N && n_it > 0) {
     // this CTA's slice of weight row n0 + tid: slabs [it_begin, it_end) = per tap a contiguous K range
     const unsigned esz = HALF ? 2u : 4u;
     const char* wbase = HALF ? reinterpret_cast<const char*>(p.Wh) : reinterpret_cast<const char*>(p.W);
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCER_WARPS + (tma_b ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -248,6 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     long long ld_a = (long long)p.tap_off[ld_t] * p.lda, ld_b = (long long)ld_t * tap_stride;
     float4 ra[D][A_PER * AV], rb[D][B_PER];
     auto load_b = [&](float4 (&dst)[B_PER]) {
+      if (tma_b) return;
       const bool k_ok = (ld_k + c4) < p.K;
 #pragma unroll
       for (int j = 0; j < B_PER; ++j)       // HALF: offsets in 4-byte words of the fp16 copy (2 elements each)
@@ -321,6 +334,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
           __syncwarp();
           const unsigned a_stage = smem_base + st_stage * (unsigned)(STAGE_FLOATS * 4);
           const unsigned b_stage = a_stage + 2u * A_FLOATS * 4u;
+          if (tma_b && tid == 0) {
+            const int rows = min(BN, p.wt_npad - n0);
+            const unsigned bytes = (unsigned)rows * 128u;
+            const long long off = ((long long)(it_begin + li) * p.wt_npad + n0) * 128;
+            const unsigned bar = full_base + st_stage * 8u;
+            const unsigned b0 = HALF ? a_stage + (unsigned)A_FLOATS * 4u : b_stage;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(HALF ? bytes : 2u * bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(b0), "l"(reinterpret_cast<const char*>(p.Wt[0]) + off), "r"(bytes), "r"(bar) : "memory");
+            if (!HALF)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(b0 + (unsigned)B_FLOATS * 4u), "l"(reinterpret_cast<const char*>(p.Wt[1]) + off), "r"(bytes), "r"(bar) : "memory");
+          }
           if constexpr (HALF) {
             const unsigned b_stage_h = a_stage + (unsigned)A_FLOATS * 4u;
 #pragma unroll
@@ -339,8 +365,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
               pk.w = __uint_as_float(*reinterpret_cast<const unsigned*>(&h3));
               sts4(a_stage + a_soff[j], pk);
             }
+            if (!tma_b) {
 #pragma unroll
-            for (int j = 0; j < B_PER; ++j) sts4(b_stage_h + b_soff[j], rb[d][j]);
+              for (int j = 0; j < B_PER; ++j) sts4(b_stage_h + b_soff[j], rb[d][j]);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < A_PER; ++j) {
@@ -348,8 +376,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
               if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
               split_sts(a_stage + a_soff[j], A_FLOATS * 4u, v);
             }
+            if (!tma_b) {
 #pragma unroll
-            for (int j = 0; j < B_PER; ++j) split_sts(b_stage + b_soff[j], B_FLOATS * 4u, rb[d][j]);
+              for (int j = 0; j < B_PER; ++j) split_sts(b_stage + b_soff[j], B_FLOATS * 4u, rb[d][j]);
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the MMA
           __syncwarp();
@@ -699,9 +729,103 @@ const __half* gemm_half_scratch(const float* W, size_t n, cudaStream_t st) {
   return buf;
 }
 
+// ---- pre-tiled weights for the TMA B path.  Layout per term (hi, lo, or the single fp16 term): [tap][K-slab][n_pad rows]
+// [128 bytes], a row = the slab's K elements of output channel n (32 floats / 64 halves) with its eight 16-byte chunks
+// XOR-swizzled by (n & 7) -- exactly the bytes a tile row holds in shared memory -- zero-filled past N and past K.
+namespace {
+template <bool HALF>
+__global__ void tile_weights_kernel(const float* __restrict__ W, unsigned char* __restrict__ t0, unsigned char* __restrict__ t1,
+                                    int taps, int N, int K, int n_pad, int kSlabs) {
+  constexpr int TKE = HALF ? 64 : 32, E = HALF ? 8 : 4;       // K elements per slab / per 16-byte chunk
+  const long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)taps * kSlabs * n_pad * 8;
+  if (chunk >= total) return;
+  const int c = (int)(chunk & 7);
+  const long long row = chunk >> 3;                            // (t * kSlabs + s) * n_pad + n
+  const int n = (int)(row % n_pad);
+  const long long ts = row / n_pad;
+  const int s = (int)(ts % kSlabs), t = (int)(ts / kSlabs);
+  const int k = s * TKE + c * E;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < E; ++i) v[i] = (n < N && k + i < K) ? W[((long long)t * N + n) * K + k + i] : 0.f;
+  const long long dst = row * 128 + ((c ^ (n & 7)) << 4);
+  if (HALF) {
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(t0 + dst) = *reinterpret_cast<const uint4*>(h);
+  } else {
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
+    *reinterpret_cast<float4*>(t0 + dst) = hi;
+    *reinterpret_cast<float4*>(t1 + dst) = lo;
+  }
+}
+struct TiledCopy { unsigned char *t0, *t1; int n_pad; size_t n; };
+std::unordered_map<const float*, TiledCopy>& tiled_registry(bool half) {
+  static std::unordered_map<const float*, TiledCopy> r[2];
+  return r[half ? 1 : 0];
+}
+}  // namespace
+
+// Pre-tiled copy of an (immutable) engine weight, made on first use; false while a stream capture is running or when the
+// feature is off (the launch then takes the register path).
+bool gemm_tiled_weights(const float* W, int taps, int N, int K, bool half, cudaStream_t st, const void** t0, const void** t1,
+                        int* n_pad_out) {
+  auto& reg = tiled_registry(half);
+  const size_t n_el = (size_t)taps * N * K;
+  auto it = reg.find(W);
+  if (it != reg.end() && it->second.n == n_el) {
+    *t0 = it->second.t0; *t1 = it->second.t1; *n_pad_out = it->second.n_pad;
+    return true;
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return false;
+  }
+  if (it != reg.end()) { cudaFree(it->second.t0); if (it->second.t1) cudaFree(it->second.t1); reg.erase(it); }
+  const int tke = half ? 64 : 32;
+  const int kSlabs = (K + tke - 1) / tke;
+  const int n_pad = (N + 63) / 64 * 64;
+  const size_t bytes = (size_t)taps * kSlabs * n_pad * 128;
+  TiledCopy tc{nullptr, nullptr, n_pad, n_el};
+  SV_CUDA(cudaMalloc(&tc.t0, bytes));
+  if (!half) SV_CUDA(cudaMalloc(&tc.t1, bytes));
+  const long long chunks = (long long)taps * kSlabs * n_pad * 8;
+  const unsigned blocks = (unsigned)((chunks + 255) / 256);
+  if (half) tile_weights_kernel<true><<<blocks, 256, 0, st>>>(W, tc.t0, tc.t1, taps, N, K, n_pad, kSlabs);
+  else tile_weights_kernel<false><<<blocks, 256, 0, st>>>(W, tc.t0, tc.t1, taps, N, K, n_pad, kSlabs);
+  SV_CUDA(cudaGetLastError());
+  SV_CUDA(cudaStreamSynchronize(st));       // first use only
+  reg.emplace(W, tc);
+  *t0 = tc.t0; *t1 = tc.t1; *n_pad_out = n_pad;
+  return true;
+}
+
+// drops the cached copies of one weight pointer (test hook: svanon_debug_gemm with static-weight treatment)
+void gemm_forget_weights(const float* W) {
+  cudaDeviceSynchronize();
+  auto ih = half_registry().find(W);
+  if (ih != half_registry().end()) { cudaFree(ih->second.data); half_registry().erase(ih); }
+  for (int h = 0; h < 2; ++h) {
+    auto& reg = tiled_registry(h != 0);
+    auto it = reg.find(W);
+    if (it != reg.end()) { cudaFree(it->second.t0); if (it->second.t1) cudaFree(it->second.t1); reg.erase(it); }
+  }
+}
+
 void gemm_half_release() {
   for (auto& kv : half_registry()) cudaFree(kv.second.data);
   half_registry().clear();
+  for (int h = 0; h < 2; ++h) {
+    for (auto& kv : tiled_registry(h != 0)) { cudaFree(kv.second.t0); if (kv.second.t1) cudaFree(kv.second.t1); }
+    tiled_registry(h != 0).clear();
+  }
 }
 
 // Returns false when the problem is not a good fit (M < 32: latency kernels; N < 64).  Defaults measured on the streaming
@@ -748,11 +872,35 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
   // kernel with dedicated epilogue warps were measured slower -- profiles/README.md.)
   auto padded = [&](int bn) { return (long long)((p.N + bn - 1) / bn) * bn; };
   // perf mode (svanon_set_precision 1): every problem of the batch needs its fp16 weight copy; K slabs hold 64 elements
+  static const bool tma_weights = [] {
+    const char* e = getenv("SVANON_TC_TMA_WEIGHTS");     // 1 (default): B operand by bulk copies from pre-tiled weights; 0: register path
+    return !e || atoi(e) != 0;
+  }();
   bool half = g_gemm_half;
-  for (int i = 0; i < count && half; ++i) {
-    const size_t nw = (size_t)ps[i].taps * ps[i].N * ps[i].K;
-    b.p[i].Wh = ps[i].w_static ? gemm_half_weights(ps[i].W, nw, st) : (count == 1 ? gemm_half_scratch(ps[i].W, nw, st) : nullptr);
-    half = b.p[i].Wh != nullptr;
+  bool all_static = tma_weights;
+  for (int i = 0; i < count; ++i) all_static = all_static && ps[i].w_static;
+  if (half && all_static) {          // fp16, pre-tiled
+    bool ok = true;
+    for (int i = 0; i < count && ok; ++i)
+      ok = gemm_tiled_weights(ps[i].W, ps[i].taps, ps[i].N, ps[i].K, true, st, &b.p[i].Wt[0], &b.p[i].Wt[1], &b.p[i].wt_npad);
+    if (!ok) for (int i = 0; i < count; ++i) b.p[i].Wt[0] = b.p[i].Wt[1] = nullptr;
+    for (int i = count; i < 3; ++i) { b.p[i].Wt[0] = b.p[0].Wt[0]; b.p[i].Wt[1] = b.p[0].Wt[1]; b.p[i].wt_npad = b.p[0].wt_npad; }
+    half = ok;
+    if (!ok) all_static = false;
+  }
+  if (half && !all_static) {
+    for (int i = 0; i < count && half; ++i) {
+      const size_t nw = (size_t)ps[i].taps * ps[i].N * ps[i].K;
+      b.p[i].Wh = ps[i].w_static ? gemm_half_weights(ps[i].W, nw, st) : (count == 1 ? gemm_half_scratch(ps[i].W, nw, st) : nullptr);
+      half = b.p[i].Wh != nullptr;
+    }
+  }
+  if (!half && all_static) {         // parity mode, pre-split + pre-tiled
+    bool ok = true;
+    for (int i = 0; i < count && ok; ++i)
+      ok = gemm_tiled_weights(ps[i].W, ps[i].taps, ps[i].N, ps[i].K, false, st, &b.p[i].Wt[0], &b.p[i].Wt[1], &b.p[i].wt_npad);
+    if (!ok) for (int i = 0; i < count; ++i) b.p[i].Wt[0] = b.p[i].Wt[1] = nullptr;
+    for (int i = count; i < 3; ++i) { b.p[i].Wt[0] = b.p[0].Wt[0]; b.p[i].Wt[1] = b.p[0].Wt[1]; b.p[i].wt_npad = b.p[0].wt_npad; }
   }
   if (half) {
     min_slabs = 1 << 30;

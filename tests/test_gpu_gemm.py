@@ -89,3 +89,34 @@ def test_tcgen05_fp16_perf_mode_gemm(M, N, K):
     print(f"[perf mode] {M}x{N}x{K}: vs fp16-rounded operands {err_kernel:.2e}, vs fp32 product {err_mode:.2e} (scale {scale:.1f})")
     assert err_kernel < 1e-5 * scale, err_kernel
     assert err_mode < 2e-2 * scale, err_mode
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(512, 1536, 384), (128, 1536, 512), (545, 2304, 768), (100, 72, 48), (328, 520, 2048),
+                                   (16384, 2048, 512), (16384, 512, 2048), (20992, 128, 512), (16500, 300, 784)])
+def test_tcgen05_weights_by_tma(M, N, K, precision):
+    """The engine's weight path: W pre-split (hi / lo) or converted (fp16) and pre-tiled in HBM, the B operand of every K-slab
+    arriving by cp.async.bulk on the stage's mbarrier (ragged N / K: zero-filled tile rows).  Same bounds as the register path."""
+    from streamvoiceanon_b200 import _lib
+    from streamvoiceanon_b200.engine import Engine, ptr
+    eng, lib = Engine.get(0), _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda")
+    _lib.check(lib.svanon_set_precision(precision))
+    _lib.check(lib.svanon_debug_gemm_weights_static(1))
+    try:
+        _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, 0, None))
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.svanon_debug_gemm_weights_static(0))
+        _lib.check(lib.svanon_set_precision(0))
+    exact = A.double() @ W.double().T + b.double()
+    scale = max(1.0, float(exact.abs().max()))
+    if precision == 0:
+        assert float((out.double() - exact).abs().max()) < 2e-5 * scale
+    else:
+        rounded = A.half().double() @ W.half().double().T + b.double()
+        assert float((out.double() - rounded).abs().max()) < 1e-5 * scale

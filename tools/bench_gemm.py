@@ -1,5 +1,9 @@
 """Micro-benchmark of the GEMM back ends on encoder-window shapes: warm (same weights every call, L2-resident) vs
-cold (cycling through 64 different weight matrices > L2) timings, CUDA events."""
+cold (cycling through 64 different weight matrices > L2) timings, CUDA events.
+
+    python tools/bench_gemm.py [modes ...] [--static] [--half]
+      --static   weights treated like engine weights: B operand by TMA from pre-tiled copies (kept across calls)
+      --half     perf mode (fp16 single-pass)"""
 import sys
 from pathlib import Path
 
@@ -14,7 +18,10 @@ lib = _lib.load()
 SHAPES = [(512, 1536, 384), (512, 384, 1536), (512, 2048, 512), (512, 512, 2048), (128, 1536, 512), (128, 512, 1536),
           (512, 2050, 2048), (256, 128, 1408), (32, 256, 2816), (16, 2304, 768), (16, 768, 2304), (64, 2304, 768),
           (256, 2304, 768), (4096, 1536, 384), (16384, 2048, 512), (16384, 512, 2048), (8192, 128, 1408)]
-MODES = [int(x) for x in sys.argv[1:]] or [1, 2]
+STATIC, HALF = "--static" in sys.argv, "--half" in sys.argv
+MODES = [int(x) for x in sys.argv[1:] if not x.startswith("--")] or [1, 2]
+_lib.check(lib.svanon_debug_gemm_weights_static(2 if STATIC else 0))
+_lib.check(lib.svanon_set_precision(1 if HALF else 0))
 for mode in MODES:
     _lib.check(lib.svanon_set_gemm_mode(mode))
     for (M, N, K) in SHAPES:
@@ -39,3 +46,5 @@ for mode in MODES:
         print(f"mode {mode} M={M:4d} N={N:4d} K={K:4d}: warm {res['warm']:6.1f} us ({gf / res['warm'] * 1e3:6.1f} TFLOP/s)  "
               f"cold {res['cold']:6.1f} us ({gf / res['cold'] * 1e3:6.1f} TFLOP/s)")
 _lib.check(lib.svanon_set_gemm_mode(2))
+_lib.check(lib.svanon_debug_gemm_weights_static(0))
+_lib.check(lib.svanon_set_precision(0))
