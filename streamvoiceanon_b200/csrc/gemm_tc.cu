@@ -617,343 +617,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
 }
 
-// =====================================================================================================================
-// Persistent wide-tile kernel (many-stream shapes: the grid would be several waves of 128 x BN tiles).
-//
-// One CTA per SM walks its tiles (tile = blockIdx.x + i * gridDim.x, N fastest so that neighbouring CTAs share A rows in
-// L2) with TWO accumulators in tensor memory (2 x BN columns), so that the epilogue of tile i runs while the tensor core
-// works on tile i + 1:
-//   warps 0-7   producers: A only (global -> registers -> hi/lo split or fp16 -> swizzled tile); thread 0 also issues the
-//               slab's B block(s) as cp.async.bulk from the pre-tiled weight copy (gemm_tiled_weights) -- this kernel is
-//               only used with weights that have one.  The load cursor runs across tile boundaries, so the first slabs
-//               of the next tile are in flight while the last slabs of this one are stored.
-//   warps 8-15  epilogue: wait acc_full[i & 1], tcgen05.ld 16 columns at a time, bias / activation / layer-scale, per-warp
-//               transpose through a 2.5 KB staging block, residual + row-segment stores, then arrive on acc_empty[i & 1].
-//   warp 16     one lane issues the MMAs: waits acc_empty[i & 1] before the first slab of tile i, commits every slab to
-//               empty[stage] and the tile to acc_full[i & 1].
-// Per tile this removes the prologue (mbarrier init, TMEM alloc, bias staging), the first-load latency, the accumulator
-// drain and the CTA turnover of the one-tile kernel, and hides the epilogue (5-11 us of a 33 us tile at K = 512).
-constexpr int TCP_PROD_WARPS = 8, TCP_EPI_WARPS = 8;
-constexpr int TCP_PRODUCERS = TCP_PROD_WARPS * 32;
-constexpr int TCP_STG_PITCH = 20;                       // floats per staged row (16 columns + 4 padding)
-
-template <int BN, int STAGES, bool HALF>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const TcBatch batch, int count, int m_tiles, int n_tiles) {
-  constexpr int A_FLOATS = TBM * TK, B_FLOATS = BN * TK;
-  constexpr int STAGE_FLOATS = HALF ? (A_FLOATS + B_FLOATS) : (2 * A_FLOATS + 2 * B_FLOATS);
-  constexpr int TKE = HALF ? 2 * TK : TK;
-  constexpr int AV = HALF ? 2 : 1;
-  constexpr int A_PER = TBM * 8 / TCP_PRODUCERS;                     // 4 chunks of 16 bytes per producer thread and slab
-  constexpr int D = HALF ? 1 : 2;                                    // fp16 slabs are twice as deep in K (two of them spill)
-  extern __shared__ unsigned char dsmem_raw[];
-  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~(uintptr_t)1023);
-  float* stg_base = smem + STAGES * STAGE_FLOATS;                    // TCP_EPI_WARPS x 32 x TCP_STG_PITCH floats
-  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
-  __shared__ unsigned tmem_holder;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_per_problem = m_tiles * n_tiles;
-  const int T = count * tiles_per_problem;
-
-  pdl_trigger();
-  if (tid == 0) {
-#pragma unroll
-    for (int s2 = 0; s2 < STAGES; ++s2) { mbar_init(&full_bar[s2], TCP_PROD_WARPS + 1); mbar_init(&empty_bar[s2], 1); }
-    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], TCP_EPI_WARPS); mbar_init(&acc_empty[1], TCP_EPI_WARPS);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(2 * BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned tmem_d = tmem_holder;
-  pdl_wait();
-
-  if (warp < TCP_PROD_WARPS) {
-    // =========================================================== producers (A) + TMA issue (B)
-    // load cursor: walks (tile, tap, K-slab) of this CTA's tiles, D slabs ahead of the store side
-    int c_tile = blockIdx.x, c_z = 0, c_n0 = 0, c_it = 0, c_total = 0, c_kslabs = 0, c_k = 0, c_tap = 0;
-    const float* a_ptr[A_PER];
-    bool c_valid = false, c_silu = false;
-    long long c_lda = 0;
-    int c_K = 0;
-    const int* c_tapoff = nullptr;
-    auto enter_tile = [&] {
-      c_valid = c_tile < T;
-      if (!c_valid) return;
-      c_z = c_tile / tiles_per_problem;
-      const int r = c_tile - c_z * tiles_per_problem;
-      const int mt = r / n_tiles;
-      const GemmParams& p = batch.p[c_z];
-      c_n0 = (r - mt * n_tiles) * BN;
-      c_kslabs = (p.K + TKE - 1) / TKE;
-      c_total = c_kslabs * p.taps;
-      c_it = 0; c_k = 0; c_tap = 0;
-      c_lda = p.lda; c_K = p.K; c_tapoff = p.tap_off; c_silu = p.prologue == PRO_SILU;
-#pragma unroll
-      for (int j = 0; j < A_PER; ++j) {
-        const int i = tid + j * TCP_PRODUCERS, row = i >> 3, c = i & 7;
-        const int m = mt * TBM + row;
-        a_ptr[j] = (m < p.M) ? p.A + gemm_a_row(p, m) + c * (HALF ? 8 : 4) : nullptr;
-      }
-    };
-    enter_tile();
-    const int c4 = (tid & 7) * (HALF ? 8 : 4);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 ra[D][A_PER * AV];
-    int m_z[D], m_it[D], m_n0[D];          // what the in-flight slab is (for the TMA issue and the SiLU prologue)
-    bool m_silu[D], have[D];
-    auto fetch = [&](int d) {
-      have[d] = c_valid;
-      if (!c_valid) return;
-      const long long a_off = (long long)c_tapoff[c_tap] * c_lda + c_k;
-      const bool k_ok = (c_k + c4) < c_K;
-#pragma unroll
-      for (int j = 0; j < A_PER; ++j) {
-#pragma unroll
-        for (int v = 0; v < AV; ++v) ra[d][j * AV + v] = (a_ptr[j] && k_ok) ? ldg_nc(a_ptr[j] + a_off + 4 * v) : zero4;
-      }
-      m_z[d] = c_z; m_it[d] = c_it; m_n0[d] = c_n0; m_silu[d] = c_silu;
-      ++c_it;
-      c_k += TKE;
-      if (c_k >= c_kslabs * TKE) { c_k = 0; ++c_tap; }
-      if (c_it == c_total) { c_tile += gridDim.x; enter_tile(); }
-    };
-    unsigned a_soff[A_PER];
-#pragma unroll
-    for (int j = 0; j < A_PER; ++j) {
-      const int i = tid + j * TCP_PRODUCERS;
-      a_soff[j] = (unsigned)swz(i >> 3, i & 7) * 4u;
-    }
-#pragma unroll
-    for (int d = 0; d < D; ++d) fetch(d);
-    const unsigned smem_base = smem_u32(smem);
-    const unsigned full_base = smem_u32(&full_bar[0]), empty_base = smem_u32(&empty_bar[0]);
-    unsigned st_stage = 0, st_parity = 1;
-    auto sts4 = [](unsigned addr, float4 v) {
-      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    };
-    bool more = true;
-    while (more) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        if (!have[d]) { more = false; break; }
-        if (lane == 0) {
-          asm volatile(
-              "{\n"
-              ".reg .pred p;\n"
-              "TCP_PW_LOOP:\n"
-              "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-              "@p bra.uni TCP_PW_DONE;\n"
-              "bra.uni TCP_PW_LOOP;\n"
-              "TCP_PW_DONE:\n"
-              "}\n" ::"r"(empty_base + st_stage * 8u), "r"(st_parity) : "memory");
-        }
-        __syncwarp();
-        const unsigned a_stage = smem_base + st_stage * (unsigned)(STAGE_FLOATS * 4);
-        if (tid == 0) {
-          const GemmParams& p = batch.p[m_z[d]];
-          const int rows = min(BN, p.wt_npad - m_n0[d]);
-          const unsigned bytes = (unsigned)rows * 128u;
-          const long long off = ((long long)m_it[d] * p.wt_npad + m_n0[d]) * 128;
-          const unsigned bar = full_base + st_stage * 8u;
-          const unsigned b0 = HALF ? a_stage + (unsigned)A_FLOATS * 4u : a_stage + 2u * A_FLOATS * 4u;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(HALF ? bytes : 2u * bytes) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(b0), "l"(reinterpret_cast<const char*>(p.Wt[0]) + off), "r"(bytes), "r"(bar) : "memory");
-          if (!HALF)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(b0 + (unsigned)B_FLOATS * 4u), "l"(reinterpret_cast<const char*>(p.Wt[1]) + off), "r"(bytes), "r"(bar) : "memory");
-        }
-        const bool silu = m_silu[d];
-        if constexpr (HALF) {
-#pragma unroll
-          for (int j = 0; j < A_PER; ++j) {
-            float4 v0 = ra[d][j * AV], v1 = ra[d][j * AV + AV - 1];
-            if (silu) {
-              v0.x = silu_fast(v0.x); v0.y = silu_fast(v0.y); v0.z = silu_fast(v0.z); v0.w = silu_fast(v0.w);
-              v1.x = silu_fast(v1.x); v1.y = silu_fast(v1.y); v1.z = silu_fast(v1.z); v1.w = silu_fast(v1.w);
-            }
-            const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
-            const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
-            float4 pk;
-            pk.x = __uint_as_float(*reinterpret_cast<const unsigned*>(&h0));
-            pk.y = __uint_as_float(*reinterpret_cast<const unsigned*>(&h1));
-            pk.z = __uint_as_float(*reinterpret_cast<const unsigned*>(&h2));
-            pk.w = __uint_as_float(*reinterpret_cast<const unsigned*>(&h3));
-            sts4(a_stage + a_soff[j], pk);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < A_PER; ++j) {
-            float4 v = ra[d][j];
-            if (silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-            sts4(a_stage + a_soff[j], h);
-            sts4(a_stage + a_soff[j] + (unsigned)A_FLOATS * 4u, l);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_base + st_stage * 8u) : "memory");
-        if (++st_stage == STAGES) { st_stage = 0; st_parity ^= 1u; }
-        fetch(d);
-      }
-    }
-  } else if (warp == TC_PRODUCER_WARPS) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      const unsigned idesc = HALF ? umma_idesc_f16(BN) : umma_idesc(BN);
-      unsigned g = 0;
-      int i = 0;
-      for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++i) {
-        const GemmParams& p = batch.p[tile / tiles_per_problem];
-        const int nslab = (p.K + TKE - 1) / TKE * p.taps;
-        mbar_wait(&acc_empty[i & 1], ((i >> 1) & 1) ^ 1);            // epilogue of tile i - 2 has drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned acc = tmem_d + (unsigned)((i & 1) * BN);
-        for (int li = 0; li < nslab; ++li, ++g) {
-          const unsigned stage = g % STAGES;
-          mbar_wait(&full_bar[stage], (g / STAGES) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          float* As = smem + stage * STAGE_FLOATS;
-          if constexpr (HALF) {
-            const unsigned long long a_d = umma_desc(As), b_d = umma_desc(As + A_FLOATS);
-#pragma unroll
-            for (int kk = 0; kk < TK / 8; ++kk) {
-              const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);
-              umma_f16(acc, a_d + adv, b_d + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-            }
-          } else {
-            float* Bs = As + 2 * A_FLOATS;
-            const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
-            const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
-#pragma unroll
-            for (int kk = 0; kk < TK / 8; ++kk) {
-              const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);
-              umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-              umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, 1u);
-              umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1u);
-            }
-          }
-          umma_commit(&empty_bar[stage]);
-        }
-        umma_commit(&acc_full[i & 1]);
-      }
-    }
-  } else {
-    // =========================================================== epilogue warps
-    const int ew = warp - TCP_PROD_WARPS;
-    const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
-    constexpr int CGW = BN / 2;                         // columns per epilogue warp
-    const int cg0 = (ew >> 2) * CGW;
-    float* stg = stg_base + ew * (32 * TCP_STG_PITCH);
-    int i = 0;
-    for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++i) {
-      const int z = tile / tiles_per_problem;
-      const int r = tile - z * tiles_per_problem;
-      const int mt = r / n_tiles;
-      const GemmParams& p = batch.p[z];
-      const int m0 = mt * TBM, n0 = (r - mt * n_tiles) * BN;
-      if (lane == 0) mbar_wait(&acc_full[i & 1], (i >> 1) & 1);
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned acc = tmem_d + (unsigned)((i & 1) * BN) + ((unsigned)(quad * 32) << 16);
-      for (int c0 = 0; c0 < CGW; c0 += 16) {
-        float v[16];
-        tmem_ld16(acc + cg0 + c0, v);
-        const int ncol = n0 + cg0 + c0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = ncol + j;
-          float y = v[j] + ((p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f);
-          if (p.act == ACT_GELU) y = gelu_erf(y);
-          else if (p.act == ACT_LOGCLAMP) y = logf(fmaxf(y, 1e-5f));
-          v[j] = y * ((p.gamma && n < p.N) ? __ldg(p.gamma + n) : 1.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * TCP_STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        // 4 lanes per row (one float4 each), 8 rows per instruction
-        const int rr = lane >> 2, c = (lane & 3) * 4;
-        const int n_base = ncol + c;
-#pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += 8) {
-          const int row = r0 + rr;
-          const int m = m0 + quad * 32 + row;
-          if (m >= p.M || n_base >= p.N) continue;
-          float4 o = *reinterpret_cast<const float4*>(stg + row * TCP_STG_PITCH + c);
-          float* dst = p.C + gemm_c_row(p, m) + n_base;
-          const float* res = p.residual ? p.residual + gemm_r_row(p, m) + n_base : nullptr;
-          const bool vec = (n_base + 3 < p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                           (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) && !p.accumulate;
-          if (vec) {
-            if (res) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res));
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-            }
-            o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
-            *reinterpret_cast<float4*>(dst) = o;
-          } else {
-            const float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n_base + j < p.N) {
-                float y = e[j];
-                if (res) y += __ldg(res + j);
-                y *= p.out_scale;
-                dst[j] = p.accumulate ? dst[j] + y : y;
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[i & 1])) : "memory");
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(2 * BN) : "memory");
-}
-
-template <int BN, int STAGES, bool HALF>
-void launch_tcp_cfg(TcBatch& b, int count, int num_sms, cudaStream_t st) {
-  constexpr size_t SMEM = (size_t)STAGES * (HALF ? 1 : 2) * (TBM * TK + BN * TK) * sizeof(float) +
-                          (size_t)TCP_EPI_WARPS * 32 * TCP_STG_PITCH * sizeof(float) + 1024;
-  static_assert(SMEM <= 232448, "persistent GEMM configuration exceeds the shared memory of an SM");
-  const GemmParams& p = b.p[0];
-  const int m_tiles = (p.M + TBM - 1) / TBM, n_tiles = (p.N + BN - 1) / BN;
-  const int T = count * m_tiles * n_tiles;
-  b.split = 1;
-  static bool configured = false;
-  if (!configured) {
-    SV_CUDA(cudaFuncSetAttribute(gemm_tcp_kernel<BN, STAGES, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(std::min(T, num_sms));
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcp_kernel<BN, STAGES, HALF>, b, count, m_tiles, n_tiles));
-}
-
 template <int BN, int STAGES, bool HALF = false>
 void launch_tc_cfg(TcBatch& b, int count, int split, cudaStream_t st) {
   constexpr size_t SMEM = (size_t)STAGES * (HALF ? 1 : 2) * (TBM * TK + BN * TK) * sizeof(float) + 1024;
@@ -1239,38 +902,23 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
     if (!ok) for (int i = 0; i < count; ++i) b.p[i].Wt[0] = b.p[i].Wt[1] = nullptr;
     for (int i = count; i < 3; ++i) { b.p[i].Wt[0] = b.p[0].Wt[0]; b.p[i].Wt[1] = b.p[0].Wt[1]; b.p[i].wt_npad = b.p[0].wt_npad; }
   }
-  // Wide tiles of problems whose weights have a pre-tiled copy run in the persistent kernel (two TMEM accumulators: the
-  // epilogue of a tile overlaps the MMAs of the next) once the grid is more than one wave of tiles.
-  static const bool persist = [] {
-    const char* e = getenv("SVANON_TC_PERSIST");          // tuning knob: 0 = one-tile-per-CTA kernels only
-    return !e || atoi(e) != 0;
-  }();
-  static const int num_sms = [] {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  const bool tiled = b.p[0].Wt[0] != nullptr;
+  // (A persistent variant of the wide tiles -- 8 producer + 8 epilogue warps, two TMEM accumulators, the epilogue of tile i over
+  // the MMAs of tile i + 1 -- was built and measured in round 2: correct, but SLOWER, 227 vs 211 us on 16384 x 2048 x 512 and 201
+  // vs 164 us on 16384 x 512 x 2048: with half the producer warps the main loop fell from 1.28 to 1.57 us per slab, more than the
+  // hidden epilogue gave back.  profiles/r2f_*; the kernel lives in git history, commit "persistent wide-tile kernel".)
   if (half) {
     min_slabs = 1 << 30;
     for (int i = 0; i < count; ++i) min_slabs = std::min(min_slabs, (ps[i].K + 2 * TK - 1) / (2 * TK) * ps[i].taps);
-    if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107) {
-      if (persist && tiled && ctas(256) > num_sms) launch_tcp_cfg<256, 4, true>(b, count, num_sms, st);
-      else launch_tc_cfg<256, 4, true>(b, count, 1, st);
-    } else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) {
-      if (persist && tiled && ctas(128) > num_sms) launch_tcp_cfg<128, 6, true>(b, count, num_sms, st);
-      else launch_tc_cfg<128, 4, true>(b, count, 1, st);
-    } else launch_tc_cfg<64, 4, true>(b, count, pick_split(ctas(64)), st);
+    if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107)
+      launch_tc_cfg<256, 4, true>(b, count, 1, st);
+    else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 4, true>(b, count, 1, st);
+    else launch_tc_cfg<64, 4, true>(b, count, pick_split(ctas(64)), st);
     return true;
   }
-  if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107) {
-    if (persist && tiled && ctas(256) > num_sms) launch_tcp_cfg<256, 2, false>(b, count, num_sms, st);
-    else launch_tc_cfg<256, 2>(b, count, 1, st);
-  } else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) {
-    if (persist && tiled && ctas(128) > num_sms) launch_tcp_cfg<128, 3, false>(b, count, num_sms, st);
-    else launch_tc_cfg<128, 3>(b, count, 1, st);
-  } else launch_tc_cfg<64, 4>(b, count, pick_split(ctas(64)), st);
+  if (max_bn >= 256 && ctas(256) >= 120 && p.N >= 256 && padded(256) * 100 <= padded(128) * 107)
+    launch_tc_cfg<256, 2>(b, count, 1, st);
+  else if (max_bn >= 128 && ctas(128) >= 120 && p.N >= 128) launch_tc_cfg<128, 3>(b, count, 1, st);
+  else launch_tc_cfg<64, 4>(b, count, pick_split(ctas(64)), st);
   return true;
 }
 
