@@ -106,8 +106,8 @@ bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st) {
   if (C != 16 && C != 32) return false;
   const int TR = C == 16 ? 128 : 64;
   static const long long max_m = [] {
-    const char* e = getenv("SVANON_CONV_SMALL_MAX_M");      // tuning knob: largest M that takes this kernel
-    return e ? atoll(e) : (1LL << 40);
+    const char* e = getenv("SVANON_CONV_SMALL_MAX_M");      // tuning knob: largest M that takes this kernel (above it the
+    return e ? atoll(e) : (1LL << 40);                       // tensor-core kernel's thin 128 x N tile takes over: measured slower)
   }();
   if (p0.M > max_m) return false;
   ConvBatch b;

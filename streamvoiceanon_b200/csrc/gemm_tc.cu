@@ -150,7 +150,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   constexpr int STAGE_FLOATS = HALF ? (A_FLOATS + B_FLOATS) : (2 * A_FLOATS + 2 * B_FLOATS);   // A_hi | A_lo | B_hi | B_lo
   constexpr int TKE = HALF ? 2 * TK : TK;                             // K elements per slab
   constexpr int AV = HALF ? 2 : 1;                                    // float4 loads per 16-byte A chunk
-  constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = BN * 8 / TC_PRODUCERS;   // 16-byte chunks per thread
+  // 16-byte chunks per thread.  Thin tiles (BN = 16 / 32: the low-channel HiFi-GAN levels at many streams) have fewer B chunks
+  // than producer threads: they are only launched with the B operand arriving by TMA, the register path stays compiled
+  // for one (guarded) chunk.
+  constexpr int A_PER = TBM * 8 / TC_PRODUCERS, B_PER = (BN * 8 >= TC_PRODUCERS) ? BN * 8 / TC_PRODUCERS : 1;
+  constexpr int TM_COLS = BN < 32 ? 32 : BN;                          // tensor-memory allocation granule
   // K-slabs a producer thread keeps in flight in registers.  Wide tiles are MMA-bound (2, 3 and 4 measure the same); the
   // 128 x 64 tile of the small, latency-bound problems pays one L2 round trip per D slabs (0.35-0.5 us per slab at D = 2:
   // profiles/README.md timeline), and has the registers for 4.  fp16 slabs are twice as deep in K; 2 of them spill at BN = 256.
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < BN; i += TC_THREADS) {
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
       const int i = tid + j * TC_PRODUCERS, row = i >> 3, c = i & 7;
-      const int n = n0 + row;
+      const int n = (i < BN * 8) ? n0 + row : p.N;                    // thin tiles: chunks past the tile are nobody's
       if (HALF) b_ptr[j] = (n < p.N) ? reinterpret_cast<const float*>(p.Wh) + (((long long)n * p.K) >> 1) + c * 4 : nullptr;
       else b_ptr[j] = (n < p.N) ? p.W + (long long)n * p.K + c * 4 : nullptr;
       b_soff[j] = (unsigned)swz(row, c) * 4u;
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
 
   // ---------------------------------------------------------------- TMEM -> registers -> (split-K reduce) -> global
   // warp w reads TMEM lanes (w & 3) * 32 .. +31 (the hardware's lane quadrant of a warp) and the column group w >> 2
-  constexpr int CG = BN / 4;                        // columns per column group
+  constexpr int CG = BN >= 64 ? BN / 4 : 16;        // columns per column group (thin tiles: BN / 16 groups of 16, the other warps idle)
   const int quad = warp & 3, grp = warp >> 2;
   cg::cluster_group cluster = cg::this_cluster();
   if (warp < TC_PRODUCER_WARPS) {
@@ -547,21 +551,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
       if (warp < TC_PRODUCER_WARPS) {
         const int row = quad * 32 + lane;
         const int m = m0 + row;
+        if (grp * CG < BN) {
 #pragma unroll
-        for (int c0 = grp * CG; c0 < (grp + 1) * CG; c0 += 16) {
-          float v[16];
-          if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(quad * 32) << 16) + c0, v);
-          else {
+          for (int c0 = grp * CG; c0 < (grp + 1) * CG; c0 += 16) {
+            float v[16];
+            if (n_it > 0) tmem_ld16(tmem_d + ((unsigned)(quad * 32) << 16) + c0, v);
+            else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+              for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (m < p.M) finish(v, m, c0);
           }
-          if (m < p.M) finish(v, m, c0);
         }
       }
     }
   } else {
     // every rank parks its partial tile column-major ([BN][128] floats) in its own shared memory
-    if (warp < TC_PRODUCER_WARPS) {
+    if (warp < TC_PRODUCER_WARPS && grp * CG < BN) {
       const int row = quad * 32 + lane;
 #pragma unroll
       for (int c0 = grp * CG; c0 < (grp + 1) * CG; c0 += 16) {
@@ -614,7 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   if (SPLIT) cluster.sync();
   else __syncthreads();
   TC_MARK(6);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TM_COLS) : "memory");
 }
 
 template <int BN, int STAGES, bool HALF = false>
@@ -840,7 +846,12 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
     const char* e = getenv("SVANON_TC_MIN_M");          // tuning knob: smallest M that goes to the tensor cores
     return e ? atoi(e) : 32;
   }();
-  if (p.M < min_m || p.N < 64) return false;
+  // thin outputs (N = 16 / 32: the two lowest HiFi-GAN levels): a 128 x N tile with the B operand by TMA exists and is
+  // correct (tests/test_gpu_gemm.py), but measured SLOWER than the shared-memory direct conv kernel (conv_small.cu) at 128
+  // streams -- V 7.41 vs 6.61 ms per step, profiles/r2h_batch128_*.json -- so conv_small keeps precedence in launch_gemm (gemm.cu); this
+  // tile only takes the thin shapes conv_small declines (SVANON_CONV_SMALL_MAX_M=8191 routes the vocoder levels here for A/B)
+  const bool thin = (p.N == 16 || p.N == 32) && p.M >= 8192;
+  if (p.M < min_m || (p.N < 64 && !thin)) return false;
   TcBatch b;
   // Weight-slice L2 prefetch pays where a GEMM is one latency-bound wave of CTAs (single stream: 3.54 -> 3.47 ms per chunk);
   // on multi-wave grids the extra L2 fill traffic costs more than it hides (128 streams: 34.2 -> 35.5 ms per step).
@@ -906,6 +917,12 @@ bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st) {
   // the MMAs of tile i + 1 -- was built and measured in round 2: correct, but SLOWER, 227 vs 211 us on 16384 x 2048 x 512 and 201
   // vs 164 us on 16384 x 512 x 2048: with half the producer warps the main loop fell from 1.28 to 1.57 us per slab, more than the
   // hidden epilogue gave back.  profiles/r2f_*; the kernel lives in git history, commit "persistent wide-tile kernel".)
+  if (thin) {
+    if (b.p[0].Wt[0] == nullptr) return false;          // thin tiles need the pre-tiled weights (TMA B path)
+    if (half) { if (p.N == 32) launch_tc_cfg<32, 4, true>(b, count, 1, st); else launch_tc_cfg<16, 4, true>(b, count, 1, st); }
+    else { if (p.N == 32) launch_tc_cfg<32, 4>(b, count, 1, st); else launch_tc_cfg<16, 4>(b, count, 1, st); }
+    return true;
+  }
   if (half) {
     min_slabs = 1 << 30;
     for (int i = 0; i < count; ++i) min_slabs = std::min(min_slabs, (ps[i].K + 2 * TK - 1) / (2 * TK) * ps[i].taps);

@@ -93,7 +93,8 @@ def test_tcgen05_fp16_perf_mode_gemm(M, N, K):
 
 @pytest.mark.parametrize("precision", [0, 1])
 @pytest.mark.parametrize("M,N,K", [(512, 1536, 384), (128, 1536, 512), (545, 2304, 768), (100, 72, 48), (328, 520, 2048),
-                                   (16384, 2048, 512), (16384, 512, 2048), (20992, 128, 512), (16500, 300, 784)])
+                                   (16384, 2048, 512), (16384, 512, 2048), (20992, 128, 512), (16500, 300, 784),
+                                   (16384, 32, 224), (16384, 16, 112), (9216, 32, 96), (8192, 16, 48)])   # thin 128 x N tiles
 def test_tcgen05_weights_by_tma(M, N, K, precision):
     """The engine's weight path: W pre-split (hi / lo) or converted (fp16) and pre-tiled in HBM, the B operand of every K-slab
     arriving by cp.async.bulk on the stage's mbarrier (ragged N / K: zero-filled tile rows).  Same bounds as the register path."""
