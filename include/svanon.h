@@ -136,6 +136,20 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable);
  * 0 = the register double-buffered CUDA-core kernel only.  `svanon_debug_gemm` runs one C = act(A W^T + bias)
  * (A [M][K], W [N][K], row-major fp32, K % 16 == 0; act 0 none / 1 GELU) through the selected back end (tests). */
 int svanon_set_gemm_mode(int mode);
+/* Single-stream stages as persistent chain kernels (process-wide; the default comes from SVANON_CHAIN in the environment): 1 =
+ * the window encoder's assemble + transformer + BSQ (and whatever else has been moved there) run as ONE cooperative launch
+ * that walks a device-side op list with grid barriers (csrc/chain.cu); 0 = one kernel launch per op.  Same arithmetic either
+ * way (3xTF32 tensor-core products, fp32 elsewhere); the tests hold both paths to the same fixtures. */
+int svanon_set_chain_mode(int mode);
+/* test hooks of the chain kernel (device pointers).  svanon_debug_chain_gemm: C = act(A W^T + bias) (A [M][K], W [N][K], M <= 384,
+ * K % 32 == 0, N % 16 == 0; act 0 none / 1 GELU) as `repeat` x [GEMM phase, element-wise phase] of one chain launch.
+ * svanon_debug_enc_transformer: WindowLimitedTransformer + BSQ (windowed_transformer.py:337-354, bsq.py:330-369) of one window
+ * xt [S][512], S <= 128, through the chain (use_chain 1) or the per-op path (0); keep > 0: only the last `keep` rows are produced
+ * (the streaming loop, infer_arvc.py:506-518); hidden_out = their final-norm rows [rows][512], ids_out [S]. */
+int svanon_debug_chain_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                            int act, int repeat, void* cuda_stream);
+int svanon_debug_enc_transformer(svanon_engine* e, const float* xt, int S, int keep, int use_chain, float* hidden_out,
+                                 int64_t* ids_out, void* cuda_stream);
 /* Precision of the tensor-core GEMMs (process-wide): 0 (default) = PARITY mode, fp32-grade products through the 3xTF32
  * split -- token ids bit-exact against the fp32 reference; 1 = PERF mode at the reference's own GPU precision (fp16 autocast
  * for linears and convs, evaluations/infer_arvc.py:493): one kind::f16 tcgen05 pass with fp32 accumulation -- activations are

@@ -47,6 +47,9 @@ _SIGS = {
     "svanon_ar_debug_logits": (C.c_int, [_p, C.c_int]),
     "svanon_set_gemm_mode": (C.c_int, [C.c_int]),
     "svanon_set_pdl": (C.c_int, [C.c_int]),
+    "svanon_set_chain_mode": (C.c_int, [C.c_int]),
+    "svanon_debug_chain_gemm": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "svanon_debug_enc_transformer": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
     "svanon_set_precision": (C.c_int, [C.c_int]),
     "svanon_debug_gemm_weights_static": (C.c_int, [C.c_int]),
     "svanon_debug_gemm": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),

@@ -7,6 +7,7 @@ extern bool g_gemm_use_pipe;
 extern bool g_gemm_use_tc;
 extern bool g_use_pdl;
 extern bool g_use_conv_small;
+extern bool g_use_chain;
 #ifdef SVANON_TC_PROF
 void tc_prof_dump();
 #endif
@@ -419,6 +420,31 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable) {
 int svanon_set_pdl(int enable) {
   g_use_pdl = enable != 0;
   return 0;
+}
+
+int svanon_set_chain_mode(int mode) {
+  g_use_chain = mode != 0;
+  return 0;
+}
+
+int svanon_debug_chain_gemm(svanon_engine* e, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                            int act, int repeat, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && A && W && C && M > 0 && N > 0 && K > 0, "bad arguments");
+    SV_CHECK(on_device(A) && on_device(W) && on_device(C) && (!bias || on_device(bias)), "device pointers only");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    e->eng.debug_chain_gemm(A, W, bias, C, M, N, K, act, repeat, (cudaStream_t)stream);
+  });
+}
+
+int svanon_debug_enc_transformer(svanon_engine* e, const float* xt, int S, int keep, int use_chain, float* hidden_out,
+                                 int64_t* ids_out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && xt && ids_out, "bad arguments");
+    SV_CHECK(on_device(xt) && on_device(ids_out) && (!hidden_out || on_device(hidden_out)), "device pointers only");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    e->eng.debug_enc_transformer(xt, S, keep, use_chain != 0, hidden_out, reinterpret_cast<long long*>(ids_out), (cudaStream_t)stream);
+  });
 }
 
 int svanon_set_gemm_mode(int mode) {

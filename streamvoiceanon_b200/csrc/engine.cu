@@ -617,7 +617,7 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
 // keep_last = c > 0: the caller reads the ids of the last c tokens of every stream only (the streaming loop,
 // infer_arvc.py:506-518), so the LAST layer runs its queries, output projection and MLP for those rows alone -- keys and
 // values of that layer still come from all S tokens.  ids_dev keeps its [B][S] layout; only columns S-c.. are written.
-void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st, int keep_last) {
+void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st, int keep_last, float* hidden_out) {
   const int BS = B * S;
   const bool tail_only = enc_tail_only && keep_last > 0 && keep_last < S && S <= ATT_TAIL_MAX_KEYS;
   float* nrm = ws.alloc_f((long long)BS * ENC_DIM);
@@ -657,6 +657,7 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
       p2.lda = ENC_INTER; p2.ldc = ENC_DIM; p2.ldr = ENC_DIM;
       launch_gemm(p2, st);
       launch_rmsnorm(xtail, nrm, enc_norm_w, R, ENC_DIM, 1e-5f, st);
+      if (hidden_out) SV_CUDA(cudaMemcpyAsync(hidden_out, nrm, (size_t)R * ENC_DIM * sizeof(float), cudaMemcpyDeviceToDevice, st));
       launch_bsq(nrm, bsq_w, bsq_b, ids_tail, R, st);
       SV_CUDA(cudaMemcpy2DAsync(ids_dev + (S - c), (size_t)S * sizeof(long long), ids_tail, (size_t)c * sizeof(long long),
                                 (size_t)c * sizeof(long long), B, cudaMemcpyDeviceToDevice, st));
@@ -681,6 +682,7 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
     launch_gemm(p2, st);
   }
   launch_rmsnorm(xt, nrm, enc_norm_w, BS, ENC_DIM, 1e-5f, st);
+  if (hidden_out) SV_CUDA(cudaMemcpyAsync(hidden_out, nrm, (size_t)BS * ENC_DIM * sizeof(float), cudaMemcpyDeviceToDevice, st));
   launch_bsq(nrm, bsq_w, bsq_b, ids_dev, BS, st);
 }
 
@@ -780,6 +782,11 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
     const float* src[2] = {wave_ring, wave_ring + (nw - ns)};
     const long long pitch[2] = {nw, nw};
     enc_conv_stack(tok_cs, src, pitch, 2, B, ns, spans, st);
+    if (B == 1 && enc_window_chain(spans, state.xt[state.cur], xt_state, S, c, Ls, ids_dev, st)) {
+      state.cur ^= 1;                    // the chain assembled the window, ran the transformer and wrote the ids
+      state.valid = true;
+      return;
+    }
     launch_pdl(enc_assemble_kernel, dim3(S, B), dim3(128), 0, st, (const float*)spans, (const float*)state.xt[state.cur],
                xt_state, B, S, Ls, ENC_RF, c);
     SV_LAUNCHED();

@@ -313,10 +313,20 @@ struct Engine {
   void build_spectrogram_consts(int model);
   // FireflyArchitecture.encode of the vocoder (firefly.py:561-574): wave [B][n] -> codec ids int32 [B][8][n/2048]
   void voc_encode(const float* wave_dev, int B, long long n, int* codes_dev, cudaStream_t st);
-  void enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st, int keep_last = 0);
+  // hidden_out (test hook): the final-norm output of the rows whose ids are produced ([B * S] or [B * keep_last] rows x 512)
+  void enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cudaStream_t st, int keep_last = 0,
+                           float* hidden_out = nullptr);
   // the window re-encode of the streaming loop with the conv-stack outputs kept between chunks (wave_ring [B][S*2048])
   void enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,
                        cudaStream_t st);
+  // one stream: window assemble + transformer + BSQ as one persistent chain launch (enc_chain.cu); false = not applicable
+  bool enc_window_chain(const float* spans, const float* prev, float* next, int S, int c, int Ls, long long* ids,
+                        cudaStream_t st);
+  std::shared_ptr<struct EncChains> enc_chains;
+  // test hooks (svanon_debug_enc_transformer, svanon_debug_chain_gemm): device pointers
+  void debug_enc_transformer(const float* xt, int S, int keep, bool use_chain, float* hidden_out, long long* ids_out, cudaStream_t st);
+  void debug_chain_gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act, int repeat,
+                        cudaStream_t st);
   // stateful encoder (enc_stream.cu): c new frames per stream -> their ids (ids[b * ids_ld + j])
   void enc_stream_init(EncStream& es, int B);
   void enc_stream_reset(EncStream& es, cudaStream_t st);

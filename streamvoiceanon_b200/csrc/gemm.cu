@@ -323,6 +323,20 @@ void gemm_timing_read(double* ms, double* gflop, long long* launches) {
   }
 }
 
+// a kernel that runs several GEMMs inside one launch (chain.cu) brackets itself: counted as one tensor-core launch
+bool gemm_timing_on() { return g_gemm_timing.on; }
+void gemm_timing_external(cudaStream_t st, bool begin, double flop) {
+  static cudaEvent_t e0 = nullptr;
+  if (begin) {
+    e0 = g_gemm_timing.get();
+    SV_CUDA(cudaEventRecord(e0, st));
+    return;
+  }
+  GemmTiming::Rec r{e0, g_gemm_timing.get(), GEMM_BACKEND_TC, flop};
+  SV_CUDA(cudaEventRecord(r.e1, st));
+  g_gemm_timing.recs.push_back(r);
+}
+
 static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t st, int* backend);
 
 void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
