@@ -24,6 +24,11 @@ namespace svanon {
 enum ChainKind : int { CH_GEMM = 1, CH_NORM = 2, CH_DWLN = 3, CH_ACT = 4, CH_QKV_ROPE = 5, CH_ATTN = 6, CH_BSQ = 7 };
 enum ChainNorm : int { CHN_RMS = 0, CHN_LN = 1 };
 enum ChainAct : int { CHA_NONE = 0, CHA_GELU = 1, CHA_SILU_MUL = 2 };
+// what a GEMM phase does with its accumulators.  EPI_PARTIAL: K-slice partials to Pout (summed by the consuming row phase);
+// the others need ksplit == 1 and write finished values: EPI_DIRECT y = act(res + gamma * (acc + bias)) (terms of `in`),
+// EPI_ROPE the same plus RoPE on the q | k columns of a qkv row (table, q_first, heads), EPI_SILU_MUL y[:, j] =
+// silu(acc[:, h1 col j]) * acc[:, h3 col j] for weights whose rows interleave 16 rows of w1 with the same 16 rows of w3.
+enum ChainEpi : int { EPI_PARTIAL = 0, EPI_DIRECT = 1, EPI_ROPE = 2, EPI_SILU_MUL = 3 };
 
 constexpr int CHAIN_DYN = 8;             // per-launch pointers: a pointer field holding 1..CHAIN_DYN means dyn[value - 1]
 inline const float* chain_dyn(int slot) { return reinterpret_cast<const float*>((uintptr_t)(slot + 1)); }
@@ -38,7 +43,7 @@ struct ChainPend {
   int ks = 0, ldp = 0, ldr = 0, pad_ = 0;
 };
 
-struct ChainOp {
+struct alignas(16) ChainOp {
   int kind = 0;
   int M = 0, N = 0, K = 0;               // rows, columns (row ops: N = C), reduction length (GEMM)
   ChainPend in;                          // row ops: the input value
@@ -51,6 +56,10 @@ struct ChainOp {
   long long pout_ks_stride = 0;
   int wt_npad = 0, BN = 0, n_tiles = 0, ksplit = 0, slabs = 0, gemm_seq = -1, ldp_out = 0;
   int no_grid_sync = 0;                  // the next op does not read this op's result (independent GEMM): CTA barrier only
+  int epi = 0;                           // ChainEpi
+  int slab_lo = 0;                       // first K-slab of W (and of the A rows) this op covers; `slabs` counts from there
+  int acc_keep = 0;                      // no epilogue: the next GEMM op (same tiling) continues these accumulators ...
+  int acc_cont = 0;                      // ... and sets this: first MMA accumulates (a K range too long for one weight block)
   // ---- row ops
   float* xout = nullptr;                 // optional: the materialised input value (may be a dyn slot)
   float* xout2 = nullptr;                // optional second copy (may be a dyn slot)
@@ -75,6 +84,16 @@ struct ChainOp {
   long long* ids = nullptr;              // may be a dyn slot
 };
 
+// this CTA's weight block of one GEMM phase (made by Chain::upload): n_sl K-slabs, per slab one `bytes` block of each term
+struct ChainWJob {
+  const unsigned char* w0;
+  const unsigned char* w1;
+  unsigned bytes;
+  int n_sl;
+  long long slab_stride;
+};
+static_assert(sizeof(ChainWJob) == 32, "ChainWJob is read as two 16-byte words");
+
 struct ChainDyn {
   const void* p[CHAIN_DYN];
 };
@@ -84,11 +103,12 @@ struct Chain {
   std::vector<ChainOp> ops;              // host copy
   ChainOp* ops_dev = nullptr;
   int* gemm_ops_dev = nullptr;           // op index of the q-th GEMM
-  int n_gemm = 0;
+  ChainWJob* wjobs_dev = nullptr;        // [n_gemm][grid]
+  int n_gemm = 0, grid = 0;
   double gemm_flop = 0;                  // 2 M N K summed over the GEMM ops
   bool uploaded = false;
   ~Chain();
-  void upload();
+  void upload(int grid);
 };
 
 constexpr int CHAIN_B_BYTES = 64 * 1024;          // weight block of one GEMM job (all its K-slabs, hi + lo)
@@ -99,6 +119,9 @@ bool chain_gemm_config(int M, int N, int K, int grid, int* BN, int* ksplit);
 // Fills the GEMM fields of `op` (tiling, pre-tiled weights made on first use, partial buffer); P must hold ksplit * M * N floats.
 void chain_set_gemm(ChainOp& op, const float* A, long long a_row_stride, const float* W, int M, int N, int K, float* P, int grid,
                     cudaStream_t st);
+// the same with the tiling given: BN columns per job, `ksplit` K slices over the slabs [slab_lo, slab_lo + slabs) of W [N][K]
+void chain_set_gemm_tiled(ChainOp& op, const float* A, long long a_row_stride, const float* W, int M, int N, int K, int BN,
+                          int ksplit, int slab_lo, int slabs, int grid, cudaStream_t st);
 size_t chain_partial_floats(int M, int N, int K, int grid);
 extern bool g_use_chain;                          // svanon_set_chain_mode / SVANON_CHAIN
 bool chain_supported(int grid);

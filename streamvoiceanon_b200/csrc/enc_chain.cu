@@ -3,6 +3,7 @@
 // launches of the per-op path -- as a list of tcgen05 GEMM phases and row-wise phases separated by grid barriers.
 // Same arithmetic as enc_transformer_bsq (engine.cu): 3xTF32 products, fp32 everything else; K-slice partials are summed in
 // fixed order by the consuming row phase.
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <tuple>
@@ -56,6 +57,7 @@ static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int 
   }
   ec->P = ec->alloc(pf);
   auto& ops = ec->chain.ops;
+  static const bool fused = [] { const char* v = getenv("SVANON_CHAIN_FUSE"); return !v || atoi(v) != 0; }();   // A/B knob
   auto pend = [&](const ChainOp& gemm) {
     ChainPend p;
     p.P = gemm.Pout; p.ks = gemm.ksplit; p.ks_stride = gemm.pout_ks_stride; p.ldp = gemm.ldp_out;
@@ -76,10 +78,16 @@ static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int 
     const EncLayerW& L = e.enc_layers[l];
     const bool tail = tail_only && l == ENC_LAYERS - 1;
     const int rows = tail ? c : S, off = tail ? S - c : 0;
-    ChainOp gq;
-    chain_set_gemm(gq, ec->nrm, D, L.wqkv, S, 3 * D, D, ec->P, grid, st);
-    ops.push_back(gq);
-    {
+    if (fused) {
+      // qkv with the whole K range per job (16 columns x 512: one 64 KB weight block): RoPE in the GEMM's epilogue
+      ChainOp gq;
+      chain_set_gemm_tiled(gq, ec->nrm, D, L.wqkv, S, 3 * D, D, 16, 1, 0, D / 32, grid, st);
+      gq.epi = EPI_ROPE; gq.heads = ENC_HEADS; gq.table = e.enc_rope; gq.q_first = 0; gq.y = ec->qkv; gq.ldy = 3 * D;
+      ops.push_back(gq);
+    } else {
+      ChainOp gq;
+      chain_set_gemm(gq, ec->nrm, D, L.wqkv, S, 3 * D, D, ec->P, grid, st);
+      ops.push_back(gq);
       ChainOp o;
       o.kind = CH_QKV_ROPE; o.M = S; o.N = 3 * D; o.in = pend(gq); o.heads = ENC_HEADS; o.table = e.enc_rope; o.q_first = 0;
       o.y = ec->qkv; o.ldy = 3 * D;
@@ -104,6 +112,24 @@ static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int 
     }
     // w1 and w3: two independent GEMM phases with no grid barrier in between (their weights together exceed one CTA's weight
     // buffer), partials side by side in P[ks][rows][2 I]
+    if (fused) {
+      // w1 | w3 as ONE weight matrix whose rows interleave 16 rows of w1 with the same 16 rows of w3: a 32-column tile holds
+      // h1 and h3 of 16 hidden units, so silu(h1) * h3 happens in the epilogue.  The K range is two weight blocks long: two
+      // GEMM ops on the same accumulators, no barrier in between.
+      float* w13 = ec->alloc((size_t)2 * I * D);
+      SV_CUDA(cudaMemcpy2DAsync(w13, (size_t)32 * D * sizeof(float), L.w1, (size_t)16 * D * sizeof(float),
+                                (size_t)16 * D * sizeof(float), I / 16, cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpy2DAsync(w13 + (size_t)16 * D, (size_t)32 * D * sizeof(float), L.w3, (size_t)16 * D * sizeof(float),
+                                (size_t)16 * D * sizeof(float), I / 16, cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaStreamSynchronize(st));
+      ChainOp ga, gb;
+      chain_set_gemm_tiled(ga, ec->nrm, D, w13, rows, 2 * I, D, 32, 1, 0, D / 64, grid, st);
+      chain_set_gemm_tiled(gb, ec->nrm, D, w13, rows, 2 * I, D, 32, 1, D / 64, D / 64, grid, st);
+      ga.acc_keep = 1; ga.no_grid_sync = 1;
+      gb.acc_cont = 1; gb.epi = EPI_SILU_MUL; gb.y = ec->g; gb.ldy = I;
+      ops.push_back(ga);
+      ops.push_back(gb);
+    } else {
     ChainOp g1, g3;
     chain_set_gemm(g1, ec->nrm, D, L.w1, rows, I, D, ec->P, grid, st);
     chain_set_gemm(g3, ec->nrm, D, L.w3, rows, I, D, ec->P + I, grid, st);
@@ -116,6 +142,7 @@ static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int 
       ChainOp o;
       o.kind = CH_ACT; o.act = CHA_SILU_MUL; o.M = rows; o.N = I; o.in = pend(g1); o.y = ec->g; o.ldy = I;
       ops.push_back(o);
+    }
     }
     ChainOp g2;
     chain_set_gemm(g2, ec->g, I, L.w2, rows, D, I, ec->P, grid, st);
@@ -132,7 +159,7 @@ static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int 
       ops.push_back(o);
     }
   }
-  ec->chain.upload();
+  ec->chain.upload(grid);
   return ec;
 }
 
@@ -227,7 +254,7 @@ void Engine::debug_chain_gemm(const float* A, const float* W, const float* bias,
     o.y = C; o.ldy = N;
     ch.ops.push_back(o);
   }
-  ch.upload();
+  ch.upload(num_sms);
   ChainDyn dyn{};
   launch_chain(ch, dyn, enc_chains->barrier, num_sms, st);
   SV_CUDA(cudaStreamSynchronize(st));

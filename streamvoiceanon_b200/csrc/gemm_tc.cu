@@ -90,6 +90,17 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long ad
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -171,7 +182,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   const int zb = SPLIT ? blockIdx.z / split : blockIdx.z;
   const int rank = SPLIT ? blockIdx.z % split : 0;
   const GemmParams& p = batch.p[zb];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // broadcast from lane 0: the compiler then knows the warp index -- and every role branch on it -- is warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
   const int kSlabs = (p.K + TKE - 1) / TKE;
   const int total = kSlabs * p.taps;
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
           __syncwarp();
           const unsigned a_stage = smem_base + st_stage * (unsigned)(STAGE_FLOATS * 4);
           const unsigned b_stage = a_stage + 2u * A_FLOATS * 4u;
-          if (tma_b && tid == 0) {
+          if (tma_b && warp == 0 && elect_one()) {         // (uniform branch + elected lane: no per-copy R2UR loop; measured neutral)
             const int rows = min(BN, p.wt_npad - n0);
             const unsigned bytes = (unsigned)rows * 128u;
             const long long off = ((long long)(it_begin + li) * p.wt_npad + n0) * 128;
@@ -397,36 +410,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcBatch ba
   } else {
     pdl_wait();
     TC_MARK(2);
-    if (lane == 0) {
+    {
       // =========================================================== MMA issuer
+      // The whole warp walks the loop and ONE ELECTED lane issues: with everything the descriptors are built from
+      // warp-uniform (the accumulator address is broadcast from lane 0), they live in uniform registers and the slab's MMAs
+      // issue back to back.  Issued from inside an `if (lane == 0)` branch the compiler wrapped EVERY tcgen05.mma in an
+      // ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY loop: ~45 ns per instruction, 0.55 us per 12-MMA slab (chain-kernel trace,
+      // profiles/r2m_*), which is what bounded the small tiles.
+      const unsigned tmem_u = (unsigned)__shfl_sync(0xffffffffu, (int)tmem_d, 0);
       const unsigned idesc = HALF ? umma_idesc_f16(BN) : umma_idesc(BN);
       for (int li = 0; li < n_it; ++li) {
         const int stage = li % STAGES;
         mbar_wait(&full_bar[stage], (li / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* As = smem + stage * STAGE_FLOATS;
-        if constexpr (HALF) {
-          const unsigned long long a_d = umma_desc(As), b_d = umma_desc(As + A_FLOATS);
+        if (elect_one()) {
+          if constexpr (HALF) {
+            const unsigned long long a_d = umma_desc(As), b_d = umma_desc(As + A_FLOATS);
 #pragma unroll
-          for (int kk = 0; kk < TK / 8; ++kk) {
-            const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 16 halves = 32 bytes per K-step
-            umma_f16(tmem_d, a_d + adv, b_d + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-          }
-        } else {
-          float* Bs = As + 2 * A_FLOATS;
-          const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
-          const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
+            for (int kk = 0; kk < TK / 8; ++kk) {
+              const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 16 halves = 32 bytes per K-step
+              umma_f16(tmem_u, a_d + adv, b_d + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
+            }
+          } else {
+            float* Bs = As + 2 * A_FLOATS;
+            const unsigned long long a_hi = umma_desc(As), a_lo = umma_desc(As + A_FLOATS);
+            const unsigned long long b_hi = umma_desc(Bs), b_lo = umma_desc(Bs + B_FLOATS);
 #pragma unroll
-          for (int kk = 0; kk < TK / 8; ++kk) {
-            const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
-            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
-            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
-            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+            for (int kk = 0; kk < TK / 8; ++kk) {
+              const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
+              umma_tf32(tmem_u, a_hi + adv, b_lo + adv, idesc, (li > 0 || kk > 0) ? 1u : 0u);
+              umma_tf32(tmem_u, a_lo + adv, b_hi + adv, idesc, 1u);
+              umma_tf32(tmem_u, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
       }
-      umma_commit(&acc_bar);
+      if (elect_one()) umma_commit(&acc_bar);
+      __syncwarp();
       TC_MARK(3);
     }
   }

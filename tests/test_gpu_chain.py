@@ -52,8 +52,9 @@ def test_chain_gemm_phase_vs_fp64(M, N, K, repeat):
 @pytest.mark.parametrize("S,keep", [(128, 1), (128, 2), (128, 0), (96, 4), (40, 1), (128, 8)])
 def test_chain_encoder_transformer_equals_per_op_path(models, S, keep):
     """WindowLimitedTransformer + BSQ of one window (windowed_transformer.py:337-354, bsq.py:330-369) as one chain launch
-    against the per-op kernels (which the reference fixtures pin): final-norm rows within 5e-5 (values are O(1); a wrong
-    attention or MLP output moves them by >= 1e-2 through the layer scales), ids identical."""
+    against the per-op kernels (which the reference fixtures pin): final-norm rows within 1e-4 after 8 layers (values are
+    O(1); the two paths sum the K slices in different orders and the chain applies RoPE / SiLU-mul in the GEMM epilogue; a
+    wrong attention or MLP output moves the rows by >= 1e-2 through the layer scales), ids identical."""
     _lib, lib, eng, ptr = _lib_eng()
     g = torch.Generator(device="cuda").manual_seed(S * 31 + keep)
     xt = torch.randn(S, 512, device="cuda", generator=g)
@@ -67,7 +68,7 @@ def test_chain_encoder_transformer_equals_per_op_path(models, S, keep):
         res.append((hid.cpu(), ids.cpu()))
     assert torch.isfinite(res[1][0]).all()
     err = float((res[0][0] - res[1][0]).abs().max())
-    assert err < 5e-5, err
+    assert err < 1e-4, err
     assert torch.equal(res[0][1], res[1][1])
     assert (res[1][1][S - rows:] >= 0).all()
 
@@ -98,7 +99,7 @@ def test_chain_stream_loop_equals_per_op_path(models, gold, tape):
             out.append((*sess.history(), waves))
             sess.close()
     finally:
-        _lib.check(lib.svanon_set_chain_mode(int(os.environ.get("SVANON_CHAIN", "0"))))
+        _lib.check(lib.svanon_set_chain_mode(int(os.environ.get("SVANON_CHAIN", "1"))))
     assert torch.equal(out[0][0], out[1][0])
     assert torch.equal(out[0][1], out[1][1])
     assert float(((out[0][2] - out[1][2]) ** 2).mean()) < 1e-10
