@@ -136,10 +136,12 @@ int svanon_ar_debug_logits(svanon_engine* e, int enable);
  * 0 = the register double-buffered CUDA-core kernel only.  `svanon_debug_gemm` runs one C = act(A W^T + bias)
  * (A [M][K], W [N][K], row-major fp32, K % 16 == 0; act 0 none / 1 GELU) through the selected back end (tests). */
 int svanon_set_gemm_mode(int mode);
-/* Single-stream stages as persistent chain kernels (process-wide; the default comes from SVANON_CHAIN in the environment): 1 =
- * the window encoder's assemble + transformer + BSQ (and whatever else has been moved there) run as ONE cooperative launch
- * that walks a device-side op list with grid barriers (csrc/chain.cu); 0 = one kernel launch per op.  Same arithmetic either
- * way (3xTF32 tensor-core products, fp32 elsewhere); the tests hold both paths to the same fixtures. */
+/* Single-stream stages as persistent chain kernels (process-wide; the default, 1, can be changed with SVANON_CHAIN in the
+ * environment).  Bit 0: the window encoder's assemble + transformer + BSQ run as ONE cooperative launch that walks a
+ * device-side op list with grid barriers (csrc/chain.cu) instead of 75 kernel launches (measured 3.41 -> 3.30 ms per chunk).
+ * Bit 1: the conv stack behind the mel filterbank joins the same launch (116 more phases; correct, measured SLOWER than the
+ * per-op kernels -- profiles/r2q_* -- so it is off).  0 = one kernel launch per op.  Same arithmetic either way (3xTF32
+ * tensor-core products, fp32 elsewhere); the tests hold all three to the same fixtures. */
 int svanon_set_chain_mode(int mode);
 /* test hooks of the chain kernel (device pointers).  svanon_debug_chain_gemm: C = act(A W^T + bias) (A [M][K], W [N][K], M <= 384,
  * K % 32 == 0, N % 16 == 0; act 0 none / 1 GELU) as `repeat` x [GEMM phase, element-wise phase] of one chain launch.

@@ -7,7 +7,7 @@ extern bool g_gemm_use_pipe;
 extern bool g_gemm_use_tc;
 extern bool g_use_pdl;
 extern bool g_use_conv_small;
-extern bool g_use_chain;
+extern bool g_use_chain, g_chain_conv;
 #ifdef SVANON_TC_PROF
 void tc_prof_dump();
 #endif
@@ -423,7 +423,8 @@ int svanon_set_pdl(int enable) {
 }
 
 int svanon_set_chain_mode(int mode) {
-  g_use_chain = mode != 0;
+  g_use_chain = (mode & 1) != 0;
+  g_chain_conv = (mode & 2) != 0;
   return 0;
 }
 

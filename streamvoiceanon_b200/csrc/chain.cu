@@ -128,18 +128,12 @@ __device__ __forceinline__ T* dynp(T* p, const ChainDyn& d) {
   return (v >= 1 && v <= (uintptr_t)CHAIN_DYN) ? reinterpret_cast<T*>(const_cast<void*>(d.p[v - 1])) : p;
 }
 
-// the K-slab range [s0, s1) of K slice ks
-__device__ __forceinline__ void job_slabs(int slabs, int ksplit, int ks, int& s0, int& s1) {
-  s0 = slabs * ks / ksplit;                      // slabs <= 2^12, ksplit <= 32: int arithmetic is exact
-  s1 = slabs * (ks + 1) / ksplit;
-}
-
 // value of 4 consecutive columns of row `row` of a pending sum
 __device__ __forceinline__ float4 pend4(const ChainPend& in, const float* res, long long row, int col) {
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (in.P) {
     const float* p = in.P + row * in.ldp + col;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < in.ks; ++k) {
       const float4 v = ldcg4(p + (long long)k * in.ks_stride);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -168,15 +162,13 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 }
 
 // issue the bulk copies of this CTA's weight block (descriptor `w`) into the B buffer at `bbuf` (one thread)
-__device__ __forceinline__ ChainWJob load_wjob(const ChainWJob* p) {
-  const int4 a = __ldg(reinterpret_cast<const int4*>(p)), b = __ldg(reinterpret_cast<const int4*>(p) + 1);
-  ChainWJob w;
-  w.w0 = reinterpret_cast<const unsigned char*>(((unsigned long long)(unsigned)a.y << 32) | (unsigned)a.x);
-  w.w1 = reinterpret_cast<const unsigned char*>(((unsigned long long)(unsigned)a.w << 32) | (unsigned)a.z);
-  w.bytes = (unsigned)b.x;
-  w.n_sl = b.y;
-  w.slab_stride = (long long)(((unsigned long long)(unsigned)b.w << 32) | (unsigned)b.z);
-  return w;
+__device__ __forceinline__ bool row_map(const ChainOp& op, int r, long long& ro) {
+  ro = r;
+  if (op.period <= 0) return true;
+  const int seg = r / op.period, t = r - seg * op.period - op.margin;
+  if (t < 0) return false;
+  if (op.y_period > 0) ro = (long long)seg * op.y_period + op.y_margin + t;
+  return true;
 }
 __device__ __forceinline__ void prefetch_weights(const ChainWJob& w, unsigned bbuf, unsigned bar) {
   if (w.n_sl <= 0) return;
@@ -195,7 +187,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
   extern __shared__ unsigned char ch_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ch_smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ unsigned long long full_bar[CH_STAGES], empty_bar[CH_STAGES], acc_bar, bfull_bar[2], bfree_bar[2];
-  __shared__ __align__(16) ChainWJob s_wj[2];      // weight-block descriptors of the GEMMs in flight (cp.async targets)
+  __shared__ __align__(16) ChainWJob s_wj[4];      // job descriptors of the GEMMs in flight: GEMM q in slot q & 3 (cp.async targets)
   __shared__ unsigned tmem_holder;
   // the op descriptors are double-buffered: warp 16 fetches op i + 1 while phase i runs (the list is static)
   constexpr int OP_INTS = (int)(sizeof(ChainOp) / 4);
@@ -251,9 +243,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
     // into L2 once, so that the per-phase descriptor fetches below are L2 hits
     l2_prefetch_bulk(a.ops, (unsigned)a.n_ops * (unsigned)sizeof(ChainOp));
     if (a.n_gemm > 0) l2_prefetch_bulk(my_wjobs, (unsigned)a.n_gemm * (unsigned)sizeof(ChainWJob));
-    for (int q = 0; q < 2 && q < a.n_gemm; ++q)
-      prefetch_weights(load_wjob(my_wjobs + q), bbase + (unsigned)q * CHAIN_B_BYTES, smem_u32(&bfull_bar[q]));
   }
+  if (warp == CH_WW && lane < 8 && (lane >> 2) < a.n_gemm)          // descriptors of the first two GEMMs
+    reinterpret_cast<int4*>(s_wj)[lane] = __ldg(reinterpret_cast<const int4*>(my_wjobs) + lane);
+  __syncwarp();
+  if (ctl) {
+    for (int q = 0; q < 2 && q < a.n_gemm; ++q)
+      prefetch_weights(s_wj[q], bbase + (unsigned)q * CHAIN_B_BYTES, smem_u32(&bfull_bar[q]));
+  }
+  __syncthreads();
 
   for (int oi = 0; oi < a.n_ops; ++oi) {
     const ChainOp& op = *reinterpret_cast<const ChainOp*>(s_op_raw[oi & 1]);
@@ -272,22 +270,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
 
     if (op.kind == CH_GEMM) {
       // ================================================================================ GEMM phase
-      const int job = blockIdx.x;
-      const bool has_job = job < op.n_tiles * op.ksplit;
+      const ChainWJob& wj = s_wj[op.gemm_seq & 3];
+      const int n_sl = wj.n_sl;
+      const bool has_job = n_sl > 0;
       const int buf = op.gemm_seq & 1;
       const bool more = op.gemm_seq + 2 < a.n_gemm;
-      if (ctl && more) {                 // descriptor of the weight block this buffer receives next
-        const unsigned dst = smem_u32(&s_wj[buf]);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(my_wjobs + op.gemm_seq + 2);
+      if (warp == CH_WW && lane < 4 && more) {     // descriptor of the next-but-one GEMM (its weight block goes into this buffer)
+        const unsigned dst = smem_u32(&s_wj[(op.gemm_seq + 2) & 3]) + (unsigned)lane * 16u;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(my_wjobs + op.gemm_seq + 2) + lane * 16;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 16) : "memory");
       }
       if (has_job) {
-        const int nt = job % op.n_tiles, ks = job / op.n_tiles;
-        const int BN = op.BN, n0 = nt * BN;
-        int s0, s1;
-        job_slabs(op.slabs, op.ksplit, ks, s0, s1);
-        const int n_sl = s1 - s0;
+        const int ks = wj.ks;
+        const int BN = op.BN, n0 = wj.n0;
         const int m_tiles = (op.M + 127) >> 7;
         const int n_it = n_sl * m_tiles;
         if (warp < CH_WW) {
@@ -300,7 +295,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
             const int row = row0 + 32 * j;
             soff[j] = (unsigned)(row * 128 + ((c ^ (row & 7)) << 4));
           }
-          const float* abase = op.A + (long long)(op.slab_lo + s0) * 32 + c * 4;
+          const float* abase = op.A + wj.a_off + c * 4;
           int ld_sl = 0, ld_mt = 0;
           float4 ra[CH_DEPTH][4];
           auto load = [&](float4 (&dst)[4]) {
@@ -399,8 +394,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
           if (op.epi == EPI_SILU_MUL) {
             // the tile holds 16 columns of h1 next to the same 16 columns of h3 (interleaved weight rows): y = silu(h1) * h3
             const int pairs = BN >> 5;
-            for (int item = grp; item < m_tiles * pairs; item += CH_WW / 4) {
-              const int mt = item / pairs, pr = item - mt * pairs;
+            for (int mt = 0; mt < m_tiles; ++mt)
+            for (int pr = grp; pr < pairs; pr += CH_WW / 4) {
               float v1[16], v3[16];
               const unsigned tad = tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(mt * BN + pr * 32);
               tmem_ld16(tad, v1);
@@ -424,8 +419,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
             const int cgs = BN >> 4;                         // 16-column groups per M tile
             float* pout = op.Pout + (long long)ks * op.pout_ks_stride;
             const float* eres = dynp(op.in.res, a.dyn);
-            for (int item = grp; item < m_tiles * cgs; item += CH_WW / 4) {
-              const int mt = item / cgs, cg = item - mt * cgs;
+            for (int mt = 0; mt < m_tiles; ++mt)
+            for (int cg = grp; cg < cgs; cg += CH_WW / 4) {
               float v[16];
               tmem_ld16(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(mt * BN + cg * 16), v);
               const int m = mt * 128 + quad * 32 + lane;
@@ -484,10 +479,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
           mbar_wait(smem_u32(&bfree_bar[buf]), buf ? f_par1 : f_par0);
           if (buf) f_par1 ^= 1u; else f_par0 ^= 1u;
         }
-        if (more) {
-          asm volatile("cp.async.wait_all;" ::: "memory");
-          prefetch_weights(s_wj[buf], bbase + (unsigned)buf * CHAIN_B_BYTES, smem_u32(&bfull_bar[buf]));
-        }
+      }
+      if (warp == CH_WW && more) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) prefetch_weights(s_wj[(op.gemm_seq + 2) & 3], bbase + (unsigned)buf * CHAIN_B_BYTES, smem_u32(&bfull_bar[buf]));
       }
       if (gmark && ctl) gmark[7] = gtime_ns();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -507,6 +503,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
         float* xout2 = dynp(op.xout2, a.dyn);
         const float* prev = dynp(op.prev, a.dyn);
         for (int r = blockIdx.x; r < op.M; r += (int)nblocks) {
+          long long ro;
+          if (!row_map(op, r, ro)) continue;               // (CTA-uniform)
           long long srow = r;
           bool from_prev = false;
           if (op.asm_S > 0) {
@@ -569,7 +567,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
               o.x = (v.x - mean) * inv * w.x; o.y = (v.y - mean) * inv * w.y;
               o.z = (v.z - mean) * inv * w.z; o.w = (v.w - mean) * inv * w.w;
               if (op.b) { const float4 bb = ldg4(op.b + col); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-              if (op.y) *reinterpret_cast<float4*>(op.y + (long long)r * op.ldy + col) = o;
+              if (op.y) *reinterpret_cast<float4*>(op.y + ro * op.ldy + col) = o;
             }
             if (op.kind == CH_BSQ) {
               // LFQ ids (bsq.py:330-369): bit_i = (proj_i > 0), id = sum bit_i << (12 - i)
@@ -600,6 +598,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
         // ============================================================================== depthwise causal conv k = 7 + LayerNorm
         const int C = op.N, nv = C >> 7;
         for (int r = blockIdx.x + (int)nblocks * warp; r < op.M; r += (int)nblocks * CH_WW) {
+          long long ro;
+          if (!row_map(op, r, ro)) continue;
           const int seg0 = op.seg_rows > 0 ? (r / op.seg_rows) * op.seg_rows : 0;
           float4 acc[4];
 #pragma unroll
@@ -641,16 +641,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
               float4 o;
               o.x = (acc[i].x - mean) * inv * w.x + bb.x; o.y = (acc[i].y - mean) * inv * w.y + bb.y;
               o.z = (acc[i].z - mean) * inv * w.z + bb.z; o.w = (acc[i].w - mean) * inv * w.w + bb.w;
-              *reinterpret_cast<float4*>(op.y + (long long)r * op.ldy + col) = o;
+              *reinterpret_cast<float4*>(op.y + ro * op.ldy + col) = o;
             }
         }
       } else if (op.kind == CH_ACT) {
         // ============================================================================== element-wise: y = act(value)
         const int n4 = op.N >> 2;
-        const long long total = (long long)op.M * n4;
-        for (long long idx = (long long)blockIdx.x * CH_WORKERS + tid; idx < total; idx += (long long)nblocks * CH_WORKERS) {
-          const long long r = idx / n4;
-          const int col = (int)(idx - r * n4) * 4;
+        const int total = op.M * n4;                       // < 2^31: M <= 384 rows
+        float* yb = dynp(op.y, a.dyn);
+        for (int idx = blockIdx.x * CH_WORKERS + tid; idx < total; idx += (int)nblocks * CH_WORKERS) {
+          const int r = idx / n4;
+          const int col = (idx - r * n4) * 4;
+          long long ro;
+          if (!row_map(op, r, ro)) continue;
           float4 o;
           if (op.act == CHA_SILU_MUL) {
             const float4 h1 = pend4(in, res, r, col), h3 = pend4(in, res, r, op.N + col);
@@ -660,7 +663,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
             o = pend4(in, res, r, col);
             if (op.act == CHA_GELU) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
           }
-          *reinterpret_cast<float4*>(op.y + r * op.ldy + col) = o;
+          *reinterpret_cast<float4*>(yb + ro * op.ldy + col) = o;
         }
       } else if (op.kind == CH_QKV_ROPE) {
         // ============================================================================== qkv = value; RoPE on q and k
@@ -835,7 +838,7 @@ void Chain::upload(int grid_) {
                              ops[gi[q - 1]].ksplit == g.ksplit && ops[gi[q - 1]].M == g.M), "chain: accumulator continuation");
     for (int cta = 0; cta < grid; ++cta) {
       ChainWJob& w = wj[(size_t)cta * n_gemm + q];
-      w = ChainWJob{nullptr, nullptr, 0u, 0, 0};
+      w = ChainWJob{nullptr, nullptr, 0u, 0, 0, 0, 0, 0, {0, 0, 0, 0}};
       if (cta >= g.n_tiles * g.ksplit) continue;
       const int nt = cta % g.n_tiles, ks = cta / g.n_tiles;
       const int s0 = g.slabs * ks / g.ksplit, s1 = g.slabs * (ks + 1) / g.ksplit;
@@ -846,6 +849,9 @@ void Chain::upload(int grid_) {
       w.bytes = (unsigned)g.BN * 128u;
       w.n_sl = s1 - s0;
       w.slab_stride = (long long)g.wt_npad * 128;
+      w.a_off = (long long)(g.slab_lo + s0) * 32;
+      w.n0 = nt * g.BN;
+      w.ks = ks;
     }
   }
   if (wjobs_dev) cudaFree(wjobs_dev);
@@ -923,10 +929,12 @@ void chain_set_gemm(ChainOp& op, const float* A, long long a_row_stride, const f
   op.Pout = P; op.ldp_out = N; op.pout_ks_stride = (long long)M * N;
 }
 
-bool g_use_chain = [] {
-  const char* e = getenv("SVANON_CHAIN");                // 0: every op as its own kernel launch (svanon_set_chain_mode)
-  return !e || atoi(e) != 0;
-}();
+static int chain_env_mode() {
+  const char* e = getenv("SVANON_CHAIN");                // svanon_set_chain_mode's argument; default 1
+  return e ? atoi(e) : 1;
+}
+bool g_use_chain = (chain_env_mode() & 1) != 0;          // bit 0: the encoder's transformer half as a chain launch
+bool g_chain_conv = (chain_env_mode() & 2) != 0;         // bit 1: the conv stack inside the chain as well (measured slower: off)
 
 bool chain_supported(int grid) { return g_use_chain && grid >= 100 && !g_gemm_half; }
 

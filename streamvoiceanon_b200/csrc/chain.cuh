@@ -72,6 +72,10 @@ struct alignas(16) ChainOp {
   const float* dw_w = nullptr;           // [7][C]
   const float* dw_b = nullptr;
   int seg_rows = 0;                      // rows per independent segment (0: one segment)
+  // row phases over buffers of several segments with zero MARGIN rows in front of each (the causal convs' left context):
+  // period > 0: row r belongs to segment r / period at t = r % period - margin; rows with t < 0 are margin rows and are left
+  // alone; y_period > 0: the result goes to row seg * y_period + y_margin + t of y (another segment layout)
+  int period = 0, margin = 0, y_period = 0, y_margin = 0;
   // CH_NORM with asm_S > 0: the window assemble of the streaming encoder (Engine::enc_window_step): row p of the value is
   // row p of `in` (p < asm_rf), prev[p + asm_c] (p < S - c), or row 2 * Ls - (S - p) of `in` (the tail span)
   int asm_S = 0, asm_Ls = 0, asm_rf = 0, asm_c = 0, pad1_ = 0;
@@ -85,14 +89,19 @@ struct alignas(16) ChainOp {
 };
 
 // this CTA's weight block of one GEMM phase (made by Chain::upload): n_sl K-slabs, per slab one `bytes` block of each term
+// ... and the job's geometry, so that no CTA divides anything at the start of a GEMM phase
 struct ChainWJob {
   const unsigned char* w0;
   const unsigned char* w1;
   unsigned bytes;
-  int n_sl;
+  int n_sl;                              // 0: this CTA has no job in the GEMM
   long long slab_stride;
+  long long a_off;                       // floats from op.A to the job's first K-slab
+  int n0;                                // first output column
+  int ks;                                // K-slice index (partial buffer)
+  int pad_[4];
 };
-static_assert(sizeof(ChainWJob) == 32, "ChainWJob is read as two 16-byte words");
+static_assert(sizeof(ChainWJob) == 64, "ChainWJob is read as four 16-byte words");
 
 struct ChainDyn {
   const void* p[CHAIN_DYN];
@@ -123,7 +132,7 @@ void chain_set_gemm(ChainOp& op, const float* A, long long a_row_stride, const f
 void chain_set_gemm_tiled(ChainOp& op, const float* A, long long a_row_stride, const float* W, int M, int N, int K, int BN,
                           int ksplit, int slab_lo, int slabs, int grid, cudaStream_t st);
 size_t chain_partial_floats(int M, int N, int K, int grid);
-extern bool g_use_chain;                          // svanon_set_chain_mode / SVANON_CHAIN
+extern bool g_use_chain, g_chain_conv;            // svanon_set_chain_mode / SVANON_CHAIN
 bool chain_supported(int grid);
 void launch_chain(Chain& c, const ChainDyn& dyn, unsigned* barrier, int grid, cudaStream_t st);
 

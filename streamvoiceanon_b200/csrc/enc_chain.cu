@@ -16,6 +16,11 @@ namespace svanon {
 struct EncChain {
   Chain chain;
   float *x = nullptr, *nrm = nullptr, *qkv = nullptr, *y = nullptr, *g = nullptr, *P = nullptr;
+  // conv-stack half (with_conv): log-mel rows of the two spans [6 pad rows | 2 x (6 margin + T) rows][160] -- written by the
+  // per-op front (DFT, magnitude, mel filterbank) -- and the spans the transformer half assembles the window from
+  float *mel = nullptr, *spans = nullptr;
+  bool with_conv = false;
+  int T = 0;
   std::vector<float*> bufs;
   ~EncChain() {
     for (auto p : bufs) cudaFree(p);
@@ -23,13 +28,14 @@ struct EncChain {
   float* alloc(size_t n) {
     float* p = nullptr;
     SV_CUDA(cudaMalloc(&p, n * sizeof(float)));
+    SV_CUDA(cudaMemset(p, 0, n * sizeof(float)));          // margin rows are never written: they stay zero
     bufs.push_back(p);
     return p;
   }
 };
 
 struct EncChains {
-  std::map<std::tuple<int, int, int, int>, std::unique_ptr<EncChain>> by_cfg;   // (S, c, Ls, tail_only)
+  std::map<std::tuple<int, int, int, int>, std::unique_ptr<EncChain>> by_cfg;   // (S, c, Ls, tail_only + 2 * with_conv)
   unsigned* barrier = nullptr;
   ~EncChains() {
     if (barrier) cudaFree(barrier);
@@ -38,10 +44,126 @@ struct EncChains {
 
 enum { DYN_SPANS = 0, DYN_PREV = 1, DYN_NEXT = 2, DYN_IDS = 3 };
 
-static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int S, int c, int Ls, bool tail_only, cudaStream_t st) {
+// The conv-stack half of the window encoder for the two spans (head: the window's first Ls frames, tail: its last Ls frames):
+// ConvNeXtEncoder (firefly.py:506-517: stem, 4 stages of ConvNeXt blocks, LayerNorms) and the quantizer's two down-sampling
+// blocks (bsq_no_upsample.py:46-60) -- Engine::enc_conv_stack from the stem on -- as chain phases.
+//
+// Layout: every activation buffer holds BOTH spans with their 6 zero margin rows (the causal left context) as ONE matrix of
+// 2 x (6 + rows) rows; GEMM phases run over all those rows (margin rows compute values nobody reads), row phases skip the
+// margin rows when they write into a margin-carrying buffer (ChainOp::period / margin), so the margins stay zero.  The
+// stride-2 convs read two consecutive rows per output row: their inputs are written with a period of twice the output's
+// (12 margin rows), which makes "input row = 2 x output row" hold across the segment boundary.
+static void build_conv_ops(Engine& e, EncChain& ec, const ConvStackW& w, int T, int grid, cudaStream_t st) {
+  auto& ops = ec.chain.ops;
+  const int MARG = 6;
+  const int P0 = MARG + T, M0 = 2 * P0;                       // stage rows
+  const int dims[4] = {128, 256, 384, 512};
+  auto pend = [&](const ChainOp& gemm, const float* bias) {
+    ChainPend p;
+    p.P = gemm.Pout; p.ks = gemm.ksplit; p.ks_stride = gemm.pout_ks_stride; p.ldp = gemm.ldp_out; p.bias = bias;
+    return p;
+  };
+  // partial-sum buffer: the largest ksplit * M * N of the GEMM phases below
+  size_t pf = chain_partial_floats(M0, 128, 7 * N_MELS, grid);
+  for (int s = 0; s < 4; ++s) {
+    pf = std::max(pf, chain_partial_floats(M0, 4 * dims[s], dims[s], grid));
+    pf = std::max(pf, chain_partial_floats(M0, dims[s], 4 * dims[s], grid));
+    if (s > 0) pf = std::max(pf, chain_partial_floats(M0, dims[s], dims[s - 1], grid));
+  }
+  pf = std::max(pf, chain_partial_floats(M0, 512, 1024, grid));
+  float* P = ec.alloc(pf);
+  float* tmp = ec.alloc((size_t)M0 * 512);
+  float* hid = ec.alloc((size_t)M0 * 2048);
+  auto gemm = [&](const float* A, long long a_stride, const float* W, int M, int N, int K) {
+    ChainOp g;
+    chain_set_gemm(g, A, a_stride, W, M, N, K, P, grid, st);
+    ops.push_back(g);
+    return g;
+  };
+  // ConvNeXtBlock.forward (firefly.py:421-440) on x (period / margin layout), result into y (its own layout; null = in place)
+  auto convnext = [&](const ConvNextW& cw, float* x, int M, int period, float* y, int y_period, int y_margin) {
+    const int C = cw.C;
+    ChainOp d;
+    d.kind = CH_DWLN; d.M = M; d.N = C; d.in.res = x; d.in.ldr = C; d.dw_w = cw.dw_w; d.dw_b = cw.dw_b; d.w = cw.ln_w; d.b = cw.ln_b;
+    d.eps = 1e-6f; d.seg_rows = period; d.period = period; d.margin = MARG; d.y = tmp; d.ldy = C;
+    ops.push_back(d);
+    const ChainOp g1 = gemm(tmp, C, cw.pw1_w, M, 4 * C, C);
+    ChainOp a1;
+    a1.kind = CH_ACT; a1.act = CHA_GELU; a1.M = M; a1.N = 4 * C; a1.in = pend(g1, cw.pw1_b); a1.y = hid; a1.ldy = 4 * C;
+    ops.push_back(a1);
+    const ChainOp g2 = gemm(hid, 4 * C, cw.pw2_w, M, C, 4 * C);
+    ChainOp a2;                                               // x + gamma * (pw2 + bias)
+    a2.kind = CH_ACT; a2.act = CHA_NONE; a2.M = M; a2.N = C; a2.in = pend(g2, cw.pw2_b); a2.in.gamma = cw.gamma; a2.in.res = x; a2.in.ldr = C;
+    a2.period = period; a2.margin = MARG; a2.y = y ? y : x; a2.ldy = C;
+    if (y) { a2.y_period = y_period; a2.y_margin = y_margin; }
+    ops.push_back(a2);
+  };
+  // stem: causal conv k = 7 over the mel rows as one GEMM over 7 overlapping rows, then LayerNorm
+  float* x = ec.alloc((size_t)M0 * dims[0]);
+  {
+    const ChainOp g = gemm(ec.mel, N_MELS, w.stem_w, M0, dims[0], 7 * N_MELS);
+    ChainOp n;
+    n.kind = CH_NORM; n.norm = CHN_LN; n.M = M0; n.N = dims[0]; n.eps = 1e-6f; n.w = w.stem_ln_w; n.b = w.stem_ln_b;
+    n.in = pend(g, w.stem_b); n.period = P0; n.margin = MARG; n.y = x; n.ldy = dims[0];
+    ops.push_back(n);
+  }
+  for (int s = 0; s < 4; ++s) {
+    const int C = dims[s];
+    if (s > 0) {
+      const int Cp = dims[s - 1];
+      ChainOp n;                                              // LayerNorm + 1 x 1 conv into the next stage's buffer
+      n.kind = CH_NORM; n.norm = CHN_LN; n.M = M0; n.N = Cp; n.eps = 1e-6f; n.w = w.mid_ln_w[s - 1]; n.b = w.mid_ln_b[s - 1];
+      n.in.res = x; n.in.ldr = Cp; n.y = tmp; n.ldy = Cp;
+      ops.push_back(n);
+      const ChainOp g = gemm(tmp, Cp, w.mid_w[s - 1], M0, C, Cp);
+      float* xn = ec.alloc((size_t)M0 * C);
+      ChainOp a;
+      a.kind = CH_ACT; a.act = CHA_NONE; a.M = M0; a.N = C; a.in = pend(g, w.mid_b[s - 1]); a.period = P0; a.margin = MARG; a.y = xn; a.ldy = C;
+      ops.push_back(a);
+      x = xn;
+    }
+    for (const auto& blk : w.blocks[s]) convnext(blk, x, M0, P0, nullptr, 0, 0);
+  }
+  // final LayerNorm into the first stride-2 conv's input layout, then 2 x [conv k2 s2 + ConvNeXt]
+  int rows = T;
+  float* cur = ec.alloc((size_t)2 * (2 * MARG + rows) * 512);
+  {
+    ChainOp n;
+    n.kind = CH_NORM; n.norm = CHN_LN; n.M = M0; n.N = 512; n.eps = 1e-6f; n.w = w.bb_norm_w; n.b = w.bb_norm_b;
+    n.in.res = x; n.in.ldr = 512; n.period = P0; n.margin = MARG; n.y_period = 2 * MARG + rows; n.y_margin = 2 * MARG;
+    n.y = cur; n.ldy = 512;
+    ops.push_back(n);
+  }
+  for (int i = 0; i < 2; ++i) {
+    const int r2 = rows / 2, Pd = MARG + r2, Md = 2 * Pd;
+    const ChainOp g = gemm(cur, 1024, w.down_w[i], Md, 512, 1024);
+    float* dn = ec.alloc((size_t)Md * 512);
+    ChainOp a;
+    a.kind = CH_ACT; a.act = CHA_NONE; a.M = Md; a.N = 512; a.in = pend(g, w.down_b[i]); a.period = Pd; a.margin = MARG; a.y = dn; a.ldy = 512;
+    ops.push_back(a);
+    if (i == 0) {
+      float* nxt = ec.alloc((size_t)2 * (2 * MARG + r2) * 512);
+      convnext(w.down_block[i], dn, Md, Pd, nxt, 2 * MARG + r2, 2 * MARG);
+      cur = nxt;
+    } else {
+      convnext(w.down_block[i], dn, Md, Pd, ec.spans, r2, 0);   // plain [2][Ls][512]
+    }
+    rows = r2;
+  }
+}
+
+static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int S, int c, int Ls, bool tail_only, bool with_conv,
+                                                 cudaStream_t st) {
   auto ec = std::make_unique<EncChain>();
   const int grid = e.num_sms;
   const int D = ENC_DIM, I = ENC_INTER;
+  ec->with_conv = with_conv;
+  if (with_conv) {
+    ec->T = 4 * Ls;
+    ec->mel = ec->alloc((size_t)(6 + 2 * (6 + ec->T)) * N_MELS);
+    ec->spans = ec->alloc((size_t)2 * Ls * D);
+    build_conv_ops(e, *ec, e.tok_cs, ec->T, grid, st);
+  }
   ec->x = ec->alloc((size_t)S * D);
   ec->nrm = ec->alloc((size_t)S * D);
   ec->qkv = ec->alloc((size_t)S * 3 * D);
@@ -66,7 +188,7 @@ static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int 
   {
     ChainOp o;                            // window assemble + attention norm of layer 0
     o.kind = CH_NORM; o.M = S; o.N = D; o.norm = CHN_RMS; o.eps = 1e-5f; o.w = e.enc_layers[0].attn_norm;
-    o.in.res = chain_dyn(DYN_SPANS); o.in.ldr = D;
+    o.in.res = with_conv ? ec->spans : chain_dyn(DYN_SPANS); o.in.ldr = D;
     o.prev = chain_dyn(DYN_PREV);
     o.asm_S = S; o.asm_Ls = Ls; o.asm_rf = ENC_RF; o.asm_c = c;
     o.xout = const_cast<float*>(chain_dyn(DYN_NEXT)); o.ldx = D;
@@ -167,8 +289,11 @@ static std::unique_ptr<EncChain> build_enc_chain(Engine& e, EncChains& set, int 
 // first and last Ls frames), prev / next = the window state of the previous / this chunk, ids [S] (the last c, or all S, are
 // written).  False: not applicable (the caller runs the per-op path).
 bool Engine::enc_window_chain(const float* spans, const float* prev, float* next, int S, int c, int Ls, long long* ids,
-                              cudaStream_t st) {
+                              cudaStream_t st, const float* const* span_src, const long long* span_pitch) {
   if (!chain_supported(num_sms) || S > 128 || c < 1 || c > S) return false;
+  // with the wave spans given, the conv stack runs inside the chain as well (two spans of 4 Ls mel rows: <= 384 rows in all)
+  const bool with_conv = g_chain_conv && span_src && 2 * (6 + 4 * Ls) <= 128 * CHAIN_MAX_MTILES;
+  if (!with_conv && !spans) return false;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
     cudaGetLastError();
@@ -180,9 +305,15 @@ bool Engine::enc_window_chain(const float* spans, const float* prev, float* next
     SV_CUDA(cudaMemset(enc_chains->barrier, 0, 64 * sizeof(unsigned)));
   }
   const bool tail_only = enc_tail_only && c < S;
-  auto key = std::make_tuple(S, c, Ls, tail_only ? 1 : 0);
+  auto key = std::make_tuple(S, c, Ls, (tail_only ? 1 : 0) + (with_conv ? 2 : 0));
   auto& slot = enc_chains->by_cfg[key];
-  if (!slot) slot = build_enc_chain(*this, *enc_chains, S, c, Ls, tail_only, st);
+  if (!slot) slot = build_enc_chain(*this, *enc_chains, S, c, Ls, tail_only, with_conv, st);
+  if (with_conv) {
+    // per-op front: left-padded frames -> DFT GEMM -> magnitude -> mel filterbank + log, straight into the chain's mel rows
+    const int T = slot->T;
+    enc_conv_stack(tok_cs, span_src, span_pitch, 2, 1, (long long)T * HOP, nullptr, st, nullptr, 0,
+                   slot->mel + (size_t)(6 + 6) * N_MELS, (long long)(6 + T) * N_MELS);
+  }
   ChainDyn dyn{};
   dyn.p[DYN_SPANS] = spans;
   dyn.p[DYN_PREV] = prev;
@@ -222,7 +353,7 @@ void Engine::debug_enc_transformer(const float* xt, int S, int keep, bool use_ch
                           cudaMemcpyDeviceToDevice, st));
   const bool was = g_use_chain;
   g_use_chain = true;
-  const bool ok = enc_window_chain(spans, prev, next, S, c, Ls, ids_out, st);
+  const bool ok = enc_window_chain(spans, prev, next, S, c, Ls, ids_out, st, nullptr, nullptr);
   g_use_chain = was;
   SV_CHECK(ok, "chain not applicable here");
   if (hidden_out) {

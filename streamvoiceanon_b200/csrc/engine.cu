@@ -504,8 +504,11 @@ static size_t enc_ws_floats(int B, long long n) { return ((size_t)(n / HOP) * 14
 // for NS same-length wave segments side by side (segment i = rows of src[i / per_src] with pitch[i / per_src]): wave
 // -> xt [NS][n/2048][512].  Streams never mix: every causal conv reads its own segment's zero margin; the GEMMs simply
 // see NS times more rows.  Workspace comes from `ws` (caller has sized and reset it).
+// mel_dst: front only -- the log-mel rows of segment i go to mel_dst + i * mel_dst_seg and nothing else runs (the chain kernel
+// continues from there, enc_chain.cu).
 void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const long long* pitch, int nsrc, int per_src,
-                            long long n, float* xt, cudaStream_t st, ConvStackHist* hist, int hist_mode) {
+                            long long n, float* xt, cudaStream_t st, ConvStackHist* hist, int hist_mode, float* mel_dst,
+                            long long mel_dst_seg) {
   SV_CHECK(w.ready && dft_w && fb_t, "encoder weights not finalized");
   SV_CHECK(hist_mode == 0 || (hist && hist->B == nsrc * per_src), "conv history does not match the stream count");
   const bool cont = hist_mode == 2;        // continuation: left context comes from the history, not from zeros
@@ -536,9 +539,9 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
   float* mag = ws.alloc_f((long long)BT * N_FREQ_PAD);
   launch_magnitude(spec, mag, BT, SPEC_LD, st);
   // 2. mel filterbank + log(clamp(., 1e-5))  (spectrogram.py:108-130); 6 zero rows in front for the causal stem
-  const long long mel_seg = (long long)(MARG + T) * N_MELS;
-  float* mel_buf = ws.alloc_f(mel_seg * B);
-  if (!cont) launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st, B, mel_seg);
+  const long long mel_seg = mel_dst ? mel_dst_seg : (long long)(MARG + T) * N_MELS;
+  float* mel_buf = mel_dst ? mel_dst - MARG * N_MELS : ws.alloc_f(mel_seg * B);
+  if (!cont && !mel_dst) launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st, B, mel_seg);
   float* mel = mel_buf + MARG * N_MELS;
   {
     GemmParams p;
@@ -547,6 +550,7 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     p.seg_rows = segT; p.a_seg = (long long)T * N_FREQ_PAD; p.c_seg = mel_seg;
     launch_gemm(p, st);
   }
+  if (mel_dst) return;
   if (hist_mode) launch_conv_hist(mel_buf, mel_seg, hist->mel, B, T, N_MELS, hist_mode, st);
   int blk_idx = 0;
 
@@ -781,6 +785,12 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
     float* spans = ws.alloc_f((long long)2 * B * Ls * ENC_DIM);
     const float* src[2] = {wave_ring, wave_ring + (nw - ns)};
     const long long pitch[2] = {nw, nw};
+    // one stream: the chain kernel runs everything behind the mel filterbank (conv stack, assemble, transformer, BSQ)
+    if (B == 1 && enc_window_chain(nullptr, state.xt[state.cur], xt_state, S, c, Ls, ids_dev, st, src, pitch)) {
+      state.cur ^= 1;
+      state.valid = true;
+      return;
+    }
     enc_conv_stack(tok_cs, src, pitch, 2, B, ns, spans, st);
     if (B == 1 && enc_window_chain(spans, state.xt[state.cur], xt_state, S, c, Ls, ids_dev, st)) {
       state.cur ^= 1;                    // the chain assembled the window, ran the transformer and wrote the ids

@@ -308,7 +308,8 @@ struct Engine {
   // conv input are captured into `hist`; 2: left context = `hist` (continuation of the streams captured there: the wave
   // pointers must have 1536 real samples in front), `hist` is advanced
   void enc_conv_stack(const ConvStackW& w, const float* const* src, const long long* pitch, int nsrc, int per_src,
-                      long long n, float* xt, cudaStream_t st, ConvStackHist* hist = nullptr, int hist_mode = 0);
+                      long long n, float* xt, cudaStream_t st, ConvStackHist* hist = nullptr, int hist_mode = 0,
+                      float* mel_dst = nullptr, long long mel_dst_seg = 0);
   void pack_conv_stack(int model, ConvStackW& cs);
   void build_spectrogram_consts(int model);
   // FireflyArchitecture.encode of the vocoder (firefly.py:561-574): wave [B][n] -> codec ids int32 [B][8][n/2048]
@@ -320,8 +321,10 @@ struct Engine {
   void enc_window_step(EncWindowState& state, const float* wave_ring, int B, int S, int c, long long* ids_dev,
                        cudaStream_t st);
   // one stream: window assemble + transformer + BSQ as one persistent chain launch (enc_chain.cu); false = not applicable
+  // span_src / span_pitch given (the two wave spans, as for enc_conv_stack): the conv stack from the stem on runs inside the
+  // chain too and `spans` is not read
   bool enc_window_chain(const float* spans, const float* prev, float* next, int S, int c, int Ls, long long* ids,
-                        cudaStream_t st);
+                        cudaStream_t st, const float* const* span_src = nullptr, const long long* span_pitch = nullptr);
   std::shared_ptr<struct EncChains> enc_chains;
   // test hooks (svanon_debug_enc_transformer, svanon_debug_chain_gemm): device pointers
   void debug_enc_transformer(const float* xt, int S, int keep, bool use_chain, float* hidden_out, long long* ids_out, cudaStream_t st);

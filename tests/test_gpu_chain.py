@@ -74,9 +74,9 @@ def test_chain_encoder_transformer_equals_per_op_path(models, S, keep):
 
 
 def test_chain_stream_loop_equals_per_op_path(models, gold, tape):
-    """The streaming loop with the encoder's transformer half as a chain launch (default) against the same loop with one
-    kernel launch per op: content ids, codec ids identical, waveform within 1e-10, over 40 chunks (window state carried by
-    the chain's assemble phase)."""
+    """The streaming loop with the encoder's transformer half as a chain launch (default), and with the conv stack inside
+    the chain as well (mode 3), against the same loop with one kernel launch per op: content ids, codec ids identical,
+    waveform within 1e-10, over 40 chunks (window state carried by the chain's assemble phase)."""
     from streamvoiceanon_b200 import StreamSession
     _lib, lib, eng, ptr = _lib_eng()
     g = gold("stream_default")
@@ -89,7 +89,7 @@ def test_chain_stream_loop_equals_per_op_path(models, gold, tape):
     src = synth.synth_audio_44k(1301, 3.0)[: n_chunks * 2048].view(n_chunks, 2048)
     out = []
     try:
-        for chain in (1, 0):
+        for chain in (1, 3, 0):                           # transformer half; + conv stack; one launch per op
             _lib.check(lib.svanon_set_chain_mode(chain))
             sess = StreamSession()
             sess.set_noise_fn(tape(7601), 0)
@@ -100,6 +100,7 @@ def test_chain_stream_loop_equals_per_op_path(models, gold, tape):
             sess.close()
     finally:
         _lib.check(lib.svanon_set_chain_mode(int(os.environ.get("SVANON_CHAIN", "1"))))
-    assert torch.equal(out[0][0], out[1][0])
-    assert torch.equal(out[0][1], out[1][1])
-    assert float(((out[0][2] - out[1][2]) ** 2).mean()) < 1e-10
+    for k in (0, 1):
+        assert torch.equal(out[k][0], out[2][0]), k
+        assert torch.equal(out[k][1], out[2][1]), k
+        assert float(((out[k][2] - out[2][2]) ** 2).mean()) < 1e-10, k
