@@ -391,6 +391,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (gmark && tid == 0) gmark[5] = gtime_ns();
           const int quad = warp & 3, grp = warp >> 2;
+          // A thread holds ROWS of the accumulator (TMEM lane = row): stored straight from registers, one instruction would
+          // touch 32 different 128-byte lines (32 LSU wavefronts for 512 bytes -- 1 us of the phase for a 128 x 64 tile).  Every
+          // warp therefore passes its 32-row block through its own slice of the (now idle) A ring and writes whole row segments.
+          float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 36);
           if (op.epi == EPI_SILU_MUL) {
             // the tile holds 16 columns of h1 next to the same 16 columns of h3 (interleaved weight rows): y = silu(h1) * h3
             const int pairs = BN >> 5;
@@ -400,73 +404,93 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const ChainArgs a)
               const unsigned tad = tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(mt * BN + pr * 32);
               tmem_ld16(tad, v1);
               tmem_ld16(tad + 16u, v3);
-              const int m = mt * 128 + quad * 32 + lane;
-              const int n = (n0 >> 1) + pr * 16;
-              if (m < op.M) {
-                float4* dst = reinterpret_cast<float4*>(op.y + (long long)m * op.ldy + n);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float4 o;
-                  o.x = (v1[4 * j] / (1.f + expf(-v1[4 * j]))) * v3[4 * j];
-                  o.y = (v1[4 * j + 1] / (1.f + expf(-v1[4 * j + 1]))) * v3[4 * j + 1];
-                  o.z = (v1[4 * j + 2] / (1.f + expf(-v1[4 * j + 2]))) * v3[4 * j + 2];
-                  o.w = (v1[4 * j + 3] / (1.f + expf(-v1[4 * j + 3]))) * v3[4 * j + 3];
-                  dst[j] = o;
-                }
+              for (int j = 0; j < 4; ++j) {
+                float4 o;
+                o.x = (v1[4 * j] / (1.f + expf(-v1[4 * j]))) * v3[4 * j];
+                o.y = (v1[4 * j + 1] / (1.f + expf(-v1[4 * j + 1]))) * v3[4 * j + 1];
+                o.z = (v1[4 * j + 2] / (1.f + expf(-v1[4 * j + 2]))) * v3[4 * j + 2];
+                o.w = (v1[4 * j + 3] / (1.f + expf(-v1[4 * j + 3]))) * v3[4 * j + 3];
+                *reinterpret_cast<float4*>(stg + lane * 20 + 4 * j) = o;
               }
+              __syncwarp();
+              const int rr = lane >> 2, c = (lane & 3) * 4;
+              const int n = (n0 >> 1) + pr * 16 + c;
+#pragma unroll
+              for (int r0 = 0; r0 < 32; r0 += 8) {
+                const int r = r0 + rr, m = mt * 128 + quad * 32 + r;
+                if (m < op.M) *reinterpret_cast<float4*>(op.y + (long long)m * op.ldy + n) = *reinterpret_cast<const float4*>(stg + r * 20 + c);
+              }
+              __syncwarp();
             }
           } else {
             const int cgs = BN >> 4;                         // 16-column groups per M tile
-            float* pout = op.Pout + (long long)ks * op.pout_ks_stride;
+            const int W = cgs >= 4 ? 2 : 1;                  // groups per warp and pass (BN = 64: two halves of 32 columns)
+            const int per_pass = W * (CH_WW / 4);            // groups the warps of one lane quadrant cover per pass
+            const int SP = W * 16 + 4;
+            const int lpr_sh = W == 2 ? 3 : 2;               // lanes per row segment: 8 or 4
+            float* dbase = op.epi == EPI_PARTIAL ? op.Pout + (long long)ks * op.pout_ks_stride : op.y;
+            const long long dld = op.epi == EPI_PARTIAL ? op.ldp_out : op.ldy;
             const float* eres = dynp(op.in.res, a.dyn);
             for (int mt = 0; mt < m_tiles; ++mt)
-            for (int cg = grp; cg < cgs; cg += CH_WW / 4) {
-              float v[16];
-              tmem_ld16(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(mt * BN + cg * 16), v);
+            for (int cb = grp * W; cb < cgs; cb += per_pass) {
               const int m = mt * 128 + quad * 32 + lane;
-              const int n = n0 + cg * 16;
-              if (m < op.M && n < op.N) {
-                if (op.epi == EPI_PARTIAL) {
-                  float4* dst = reinterpret_cast<float4*>(pout + (long long)m * op.ldp_out + n);
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                  // direct result: y = act(res + gamma * (acc + bias)), or RoPE on the q / k columns of a qkv row
-                  if (op.in.bias) {
+              for (int g = 0; g < 2; ++g) {
+                if (g < W && cb + g < cgs) {
+                  const int cg = cb + g;
+                  float v[16];
+                  tmem_ld16(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(mt * BN + cg * 16), v);
+                  const int n = n0 + cg * 16;
+                  if (op.epi != EPI_PARTIAL && m < op.M && n < op.N) {
+                    // direct result: y = act(res + gamma * (acc + bias)), or RoPE on the q / k columns of a qkv row
+                    if (op.in.bias) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += __ldg(op.in.bias + n + j);
-                  }
-                  if (op.in.gamma) {
+                      for (int j = 0; j < 16; ++j) v[j] += __ldg(op.in.bias + n + j);
+                    }
+                    if (op.in.gamma) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] *= __ldg(op.in.gamma + n + j);
-                  }
-                  if (eres) {
-                    const float4* rp = reinterpret_cast<const float4*>(eres + (long long)m * op.in.ldr + n);
+                      for (int j = 0; j < 16; ++j) v[j] *= __ldg(op.in.gamma + n + j);
+                    }
+                    if (eres) {
+                      const float4* rp = reinterpret_cast<const float4*>(eres + (long long)m * op.in.ldr + n);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float4 r = __ldcg(rp + j);
-                      v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                      for (int j = 0; j < 4; ++j) {
+                        const float4 r = __ldcg(rp + j);
+                        v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                      }
+                    }
+                    if (op.epi == EPI_ROPE && n < 2 * op.heads * HEAD_DIM) {
+                      const float4* cs = reinterpret_cast<const float4*>(op.table + ((long long)(op.q_first + m) * (HEAD_DIM / 2) + ((n & (HEAD_DIM - 1)) >> 1)) * 2);
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        const float4 t = __ldg(cs + j);        // (cos, sin) of pairs 2 j and 2 j + 1
+                        const float x0 = v[4 * j], x1 = v[4 * j + 1], x2 = v[4 * j + 2], x3 = v[4 * j + 3];
+                        v[4 * j] = x0 * t.x - x1 * t.y; v[4 * j + 1] = x1 * t.x + x0 * t.y;
+                        v[4 * j + 2] = x2 * t.z - x3 * t.w; v[4 * j + 3] = x3 * t.z + x2 * t.w;
+                      }
+                    }
+                    if (op.act == CHA_GELU) {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
                     }
                   }
-                  if (op.epi == EPI_ROPE && n < 2 * op.heads * HEAD_DIM) {
-                    const float4* cs = reinterpret_cast<const float4*>(op.table + ((long long)(op.q_first + m) * (HEAD_DIM / 2) + ((n & (HEAD_DIM - 1)) >> 1)) * 2);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float4 t = __ldg(cs + j);        // (cos, sin) of pairs 2 j and 2 j + 1
-                      const float x0 = v[4 * j], x1 = v[4 * j + 1], x2 = v[4 * j + 2], x3 = v[4 * j + 3];
-                      v[4 * j] = x0 * t.x - x1 * t.y; v[4 * j + 1] = x1 * t.x + x0 * t.y;
-                      v[4 * j + 2] = x2 * t.z - x3 * t.w; v[4 * j + 3] = x3 * t.z + x2 * t.w;
-                    }
-                  }
-                  if (op.act == CHA_GELU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-                  }
-                  float4* dst = reinterpret_cast<float4*>(op.y + (long long)m * op.ldy + n);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                  for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * SP + g * 16 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
               }
+              __syncwarp();
+              const int rr = lane >> lpr_sh, c = (lane & ((1 << lpr_sh) - 1)) * 4;
+              const int n = n0 + cb * 16 + c;
+              const int rpi = 32 >> lpr_sh;
+              if (c < (min(W, cgs - cb) << 4) && n < op.N) {
+                for (int r0 = 0; r0 < 32; r0 += rpi) {
+                  const int r = r0 + rr, mm = mt * 128 + quad * 32 + r;
+                  if (mm < op.M) *reinterpret_cast<float4*>(dbase + (long long)mm * dld + n) = *reinterpret_cast<const float4*>(stg + r * SP + c);
+                }
+              }
+              __syncwarp();
             }
           }
         }
