@@ -160,6 +160,13 @@ int svanon_debug_enc_transformer(svanon_engine* e, const float* xt, int S, int k
  * mode beside the parity-mode numbers, never instead of them.  GEMMs that run on CUDA cores (M < 32, thin channels) and the
  * single-stream persistent decode kernel are unaffected. */
 int svanon_set_precision(int mode);
+/* Wide GEMMs (M >= 4096 rows: the many-stream batches) on CTA pairs -- tcgen05.mma.cta_group::2, operands by tensor-map TMA,
+ * persistent tile loop with two TMEM accumulators (csrc/gemm_pair.cu).  Same arithmetic and results as the single-CTA kernel,
+ * bit for bit.  -1 = environment (SVANON_GEMM_PAIR, default on), 0 = off, 1 = on, 2 = on with explicitly masked hi terms (A/B
+ * check of the "kind::tf32 truncates" assumption the kernel rests on). */
+int svanon_set_gemm_pair(int mode);
+/* number of GEMM launches the pair kernel has taken in this process (tests: the path under test really ran) */
+long long svanon_gemm_pair_launches(void);
 /* programmatic dependent launch of the GEMM kernels (default on): a GEMM's launch and weight-only prologue overlap
  * the tail of the kernel before it; it blocks in griddepcontrol.wait before touching activations */
 int svanon_set_pdl(int enable);

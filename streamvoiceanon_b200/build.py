@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libsvanon_b200.so"
-SOURCES = ["gemm.cu", "gemm_pipe.cu", "gemm_tc.cu", "conv_small.cu", "kernels_misc.cu", "attn.cu", "ar_decode.cu", "ar_decode_staged.cu", "ar_batch.cu", "ar_attn_tma.cu", "engine.cu", "voc_stream.cu", "api.cu", "batch.cu", "enc_stream.cu", "speaker.cu", "chain.cu", "enc_chain.cu"]
+SOURCES = ["gemm.cu", "gemm_pipe.cu", "gemm_tc.cu", "gemm_pair.cu", "conv_small.cu", "kernels_misc.cu", "attn.cu", "ar_decode.cu", "ar_decode_staged.cu", "ar_batch.cu", "ar_attn_tma.cu", "engine.cu", "voc_stream.cu", "api.cu", "batch.cu", "enc_stream.cu", "speaker.cu", "chain.cu", "enc_chain.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177"]

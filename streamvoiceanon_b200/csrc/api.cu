@@ -453,6 +453,7 @@ int svanon_set_gemm_mode(int mode) {
     SV_CHECK(mode >= 0 && mode <= 2, "gemm mode: 0 = fp32 CUDA-core (register double-buffer only), 1 = fp32 CUDA-core, 2 = tcgen05 3xTF32");
     g_gemm_use_pipe = mode >= 1;
     g_gemm_use_tc = mode == 2;
+    g_gemm_pair_allowed = mode == 2;
     g_use_conv_small = mode >= 1;
   });
 }
@@ -461,6 +462,15 @@ int svanon_debug_gemm_weights_static(int enable) {
   g_debug_gemm_static = enable;
   return 0;
 }
+
+int svanon_set_gemm_pair(int mode) {
+  return guarded([&] {
+    SV_CHECK(mode >= -1 && mode <= 2, "gemm pair mode: -1 environment, 0 off, 1 on, 2 on with masked hi copies");
+    g_gemm_pair_mode = mode;
+  });
+}
+
+long long svanon_gemm_pair_launches(void) { return g_gemm_pair_launches; }
 
 int svanon_set_precision(int mode) {
   return guarded([&] {

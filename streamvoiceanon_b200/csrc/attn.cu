@@ -115,7 +115,7 @@ template <int QPW>
 __global__ void __launch_bounds__(SQW * 32)
 attention_short_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
                        long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
-                       int qpos0, int window) {
+                       int qpos0, int window, float* __restrict__ out_lo) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float att_smem[];
@@ -131,6 +131,7 @@ attention_short_kernel(const float* __restrict__ q, long long q_ld, const float*
   k += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
   v += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
   out += (long long)seg * nq * out_ld;
+  if (out_lo) out_lo += (long long)seg * nq * out_ld;      // lo term of the result, same layout (common.cuh: tf32_lo)
   const int k_hi = qpos0 + min(qi0 + QPC, nq) - 1;          // newest key any query of this CTA needs (inclusive)
   for (int i = threadIdx.x; i < (k_hi + 1) * (HEAD_DIM / 4); i += SQW * 32) {
     const int key = i / (HEAD_DIM / 4), c = (i % (HEAD_DIM / 4)) * 4;
@@ -186,6 +187,11 @@ attention_short_kernel(const float* __restrict__ q, long long q_ld, const float*
   const float inv = 1.f / l;
   op[lane] = acc0 * inv;
   op[lane + 32] = acc1 * inv;
+  if (out_lo) {
+    float* lp = out_lo + (long long)qi * out_ld + h * HEAD_DIM;
+    lp[lane] = tf32_lo(acc0 * inv);
+    lp[lane + 32] = tf32_lo(acc1 * inv);
+  }
   }
 }
 
@@ -272,7 +278,7 @@ __global__ void kv_append_kernel(const float* __restrict__ qkv, int heads, float
 
 void launch_attention(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
                       long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
-                      cudaStream_t st, int nseg) {
+                      cudaStream_t st, int nseg, float* out_lo) {
   if (nq <= 0 || nseg <= 0) return;
   if (qpos0 + nq <= SMAXK && (kv_row_stride % 4) == 0) {        // the whole key range of a stream fits shared memory
     constexpr size_t SMEM = (size_t)SMAXK * (2 * HEAD_DIM + 1) * sizeof(float);
@@ -284,13 +290,14 @@ void launch_attention(const float* q, long long q_ld, const float* k, const floa
     }
     if (nseg >= 8)
       launch_pdl(attention_short_kernel<8>, dim3((nq + SQW * 8 - 1) / (SQW * 8) * nseg, heads), dim3(SQW * 32), SMEM, st, q, q_ld,
-                 k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window);
+                 k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window, out_lo);
     else
       launch_pdl(attention_short_kernel<1>, dim3((nq + SQW - 1) / SQW * nseg, heads), dim3(SQW * 32), SMEM, st, q, q_ld, k, v,
-                 kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window);
+                 kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window, out_lo);
     SV_LAUNCHED();
     return;
   }
+  SV_CHECK(out_lo == nullptr, "attention: the lo output exists on the short-sequence kernel only");
   dim3 grid((nq + QW - 1) / QW * nseg, heads);
   launch_pdl(attention_kernel, dim3(grid), dim3(QW * 32), 0, st, q, q_ld, k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0,
                                              window);

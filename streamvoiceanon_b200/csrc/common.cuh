@@ -145,6 +145,11 @@ struct GemmParams {
   // Wt[1] = lo term (null in perf mode), rows padded to wt_npad per (tap, K-slab); filled in by the launcher
   const void* Wt[2] = {nullptr, nullptr};
   int wt_npad = 0;
+  // pair kernel (gemm_pair.cu): lo terms x - trunc_tf32(x) as arrays of their own.  Alo: the lo term of A, compact [M][K], written
+  // by whoever produced A (null: one split pass in front of the GEMM); Clo: if set, the kernel also writes the lo term of its
+  // result, compact [M][N], for the GEMM that consumes C next.  Kernels other than the pair kernel ignore both.
+  const float* Alo = nullptr;
+  float* Clo = nullptr;
 };
 
 #ifdef __CUDACC__
@@ -169,6 +174,9 @@ __device__ __forceinline__ long long gemm_r_row(const GemmParams& p, int m) {
   }
   return (long long)m * p.ldr;
 }
+// lo term of the 3xTF32 split: x - trunc_tf32(x) (exact in fp32).  Row-wise kernels that feed a wide GEMM write it beside their
+// result (`*_lo` arguments, same compact layout) so that the pair kernel (gemm_pair.cu) takes both terms by TMA.
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // row `row` of a buffer made of segments of seg_rows rows that start seg_stride floats apart (0 rows: plain)
 __device__ __forceinline__ long long seg_row_off(long long row, int seg_rows, long long seg_stride, long long ld) {
   if (seg_rows > 0) {
@@ -183,6 +191,13 @@ __device__ __forceinline__ long long seg_row_off(long long row, int seg_rows, lo
 extern bool g_gemm_half;
 void gemm_half_release();
 void gemm_forget_weights(const float* W);
+// pair kernel switch (gemm_pair.cu): -1 environment (SVANON_GEMM_PAIR, default on), 0 off, 1 on, 2 on with masked hi copies
+extern int g_gemm_pair_mode;
+extern long long g_gemm_pair_launches;
+extern bool g_gemm_pair_allowed;
+bool gemm_pair_eligible(const GemmParams* ps, int count);
+void gemm_pair_release();
+void gemm_pair_forget_weights(const float* W);
 
 // measurement aid behind svanon_gemm_timing: per back end, summed event-timed launch durations and executed flops
 enum GemmBackend : int { GEMM_BACKEND_TC = 0, GEMM_BACKEND_PIPE = 1, GEMM_BACKEND_FP32 = 2, GEMM_BACKEND_CONV_SMALL = 3, GEMM_BACKENDS = 4 };
@@ -201,12 +216,13 @@ void launch_layernorm(const float* x, float* y, const float* w, const float* b, 
 // depthwise causal conv k=7 (rows before 0 are read from the buffer margin) + LayerNorm over C, channels-last
 void launch_dwconv7_ln(const float* x, float* y, const float* dw_w /*[7][C]*/, const float* dw_b, const float* ln_w,
                        const float* ln_b, int rows, int C, float eps, cudaStream_t st, int seg_rows = 0,
-                       long long x_seg = 0);
+                       long long x_seg = 0, float* y_lo = nullptr);
 void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st,
-                    long long x_ld = 0);
+                    long long x_ld = 0, float* y_lo = nullptr);
 // interleaved-pair RoPE on q and k inside a fused [rows, 3*H*64] qkv buffer; table [pos][32][2] (bf16-rounded fp32)
 void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos0, cudaStream_t st, int seg_rows = 0);
-void launch_silu_mul(const float* h13 /*[rows][2*I]*/, float* out /*[rows][I]*/, int rows, int I, cudaStream_t st);
+void launch_silu_mul(const float* h13 /*[rows][2*I]*/, float* out /*[rows][I]*/, int rows, int I, cudaStream_t st,
+                     float* out_lo = nullptr);
 void launch_magnitude(const float* spec /*[T][ld_in] re|im*/, float* mag /*[T][N_FREQ_PAD]*/, int T, int ld_in,
                       cudaStream_t st);
 void launch_bsq(const float* z /*[T][512]*/, const float* w /*[13][512]*/, const float* b, long long* ids, int T,
@@ -244,7 +260,7 @@ void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t 
 // max(0, pos-window+1) .. pos.
 void launch_attention(const float* q, long long q_ld, const float* k, const float* v, long long kv_head_stride,
                       long long kv_row_stride, float* out, long long out_ld, int nq, int qpos0, int heads, int window,
-                      cudaStream_t st, int nseg = 1);
+                      cudaStream_t st, int nseg = 1, float* out_lo = nullptr);
 // Only the last `c` queries of every segment (positions nq-c .. nq-1, nq <= 128 keys): one CTA per (query, head), one
 // thread per key.  out is compact: row seg*c + j.  Used by the last layer of the streaming window encode, whose other
 // rows nobody reads (infer_arvc.py:506-518 keeps the last `chunk` ids).

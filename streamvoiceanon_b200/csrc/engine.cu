@@ -47,7 +47,25 @@ Engine::~Engine() {
   for (void* p : {(void*)ar_x, (void*)ar_h, (void*)ar_q, (void*)ar_g, (void*)ar_part, (void*)ar_logits,
                   (void*)ar_barrier, (void*)dbg_slow_logits, (void*)dbg_hidden, (void*)dbg_fast_logits})
     if (p) cudaFree(p);
+  for (auto& l : lo_scr) if (l.p) cudaFree(l.p);
   if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+float* Engine::lo_scratch(int slot, size_t n, cudaStream_t st) {
+  LoScratch& s = lo_scr[slot];
+  if (n <= s.cap) return s.p;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  SV_CUDA(cudaDeviceSynchronize());
+  if (s.p) cudaFree(s.p);
+  s.p = nullptr;
+  s.cap = 0;
+  SV_CUDA(cudaMalloc(&s.p, (n + n / 8) * sizeof(float)));
+  s.cap = n + n / 8;
+  return s.p;
 }
 
 const Tensor& Engine::get(int model, const std::string& name) const {
@@ -430,17 +448,21 @@ void Engine::finalize_vocoder() {
 void Engine::convnext(const ConvNextW& cw, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out,
                       int seg_rows, long long x_seg, long long out_seg) {
   const int C = cw.C;
-  launch_dwconv7_ln(x, tmp, cw.dw_w, cw.dw_b, cw.ln_w, cw.ln_b, rows, C, 1e-6f, st, seg_rows, x_seg);
   GemmParams p1;
   p1.A = tmp; p1.W = cw.pw1_w; p1.C = hid; p1.bias = cw.pw1_b; p1.M = rows; p1.N = 4 * C; p1.K = C;
   p1.lda = C; p1.ldc = 4 * C; p1.act = ACT_GELU;
-  launch_gemm(p1, st);
   GemmParams p2;
   p2.A = hid; p2.W = cw.pw2_w; p2.C = out ? out : x; p2.bias = cw.pw2_b; p2.gamma = cw.gamma; p2.residual = x;
   p2.M = rows; p2.N = C; p2.K = 4 * C; p2.lda = 4 * C; p2.ldc = C; p2.ldr = C;
   if (seg_rows > 0) {
     p2.seg_rows = seg_rows; p2.a_seg = (long long)seg_rows * 4 * C; p2.c_seg = out ? out_seg : x_seg; p2.r_seg = x_seg;
   }
+  // wide batches (pair GEMM kernel): the producers write the lo terms of the GEMM inputs beside their results
+  if (gemm_pair_eligible(&p1, 1)) p1.Alo = lo_scratch(0, (size_t)rows * C, st);
+  if (p1.Alo && gemm_pair_eligible(&p2, 1)) p1.Clo = lo_scratch(1, (size_t)rows * 4 * C, st);
+  p2.Alo = p1.Clo;
+  launch_dwconv7_ln(x, tmp, cw.dw_w, cw.dw_b, cw.ln_w, cw.ln_b, rows, C, 1e-6f, st, seg_rows, x_seg, const_cast<float*>(p1.Alo));
+  launch_gemm(p1, st);
   launch_gemm(p2, st);
 }
 
@@ -629,11 +651,25 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
   float* y = ws.alloc_f((long long)BS * ENC_DIM);
   float* h13 = ws.alloc_f((long long)BS * 2 * ENC_INTER);
   float* gbuf = ws.alloc_f((long long)BS * ENC_INTER);
+  // wide batches (pair GEMM kernel, gemm_pair.cu): norm / attention / SiLU-mul write the lo terms of their results as well
+  float *nrm_lo = nullptr, *y_lo = nullptr, *g_lo = nullptr;
+  {
+    GemmParams probe;
+    probe.A = nrm; probe.W = enc_layers[0].wqkv; probe.C = qkv; probe.M = BS; probe.N = 3 * ENC_DIM; probe.K = ENC_DIM;
+    probe.lda = ENC_DIM; probe.ldc = 3 * ENC_DIM;
+    if (gemm_pair_eligible(&probe, 1)) {
+      nrm_lo = lo_scratch(0, (size_t)BS * ENC_DIM, st);
+      g_lo = lo_scratch(1, (size_t)BS * ENC_INTER, st);
+      y_lo = lo_scratch(2, (size_t)BS * ENC_DIM, st);
+      if (!nrm_lo || !g_lo || !y_lo) nrm_lo = y_lo = g_lo = nullptr;
+    }
+  }
   for (int l = 0; l < ENC_LAYERS; ++l) {
     const EncLayerW& L = enc_layers[l];
-    launch_rmsnorm(xt, nrm, L.attn_norm, BS, ENC_DIM, 1e-5f, st);
+    launch_rmsnorm(xt, nrm, L.attn_norm, BS, ENC_DIM, 1e-5f, st, 0, nrm_lo);
     GemmParams p;
     p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = BS; p.N = 3 * ENC_DIM; p.K = ENC_DIM; p.lda = ENC_DIM; p.ldc = 3 * ENC_DIM;
+    p.Alo = nrm_lo;
     launch_gemm(p, st);
     launch_rope_qk(qkv, enc_rope, BS, ENC_HEADS, 0, st, B > 1 ? S : 0);
     if (tail_only && l == ENC_LAYERS - 1) {
@@ -667,22 +703,27 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
                                 (size_t)c * sizeof(long long), B, cudaMemcpyDeviceToDevice, st));
       return;
     }
+    // (the lo output exists on the short-sequence attention kernel only: windows of <= 128 tokens, the streaming loop)
+    float* y_lo_l = (S <= 128) ? y_lo : nullptr;
     launch_attention(qkv, 3 * ENC_DIM, qkv + ENC_DIM, qkv + 2 * ENC_DIM, HEAD_DIM, 3 * ENC_DIM, y, ENC_DIM, S, 0,
-                     ENC_HEADS, ENC_WINDOW, st, B);
+                     ENC_HEADS, ENC_WINDOW, st, B, y_lo_l);
     GemmParams po;
     po.A = y; po.W = L.wo; po.C = xt; po.gamma = L.ls_attn; po.residual = xt; po.M = BS; po.N = ENC_DIM; po.K = ENC_DIM;
     po.lda = ENC_DIM; po.ldc = ENC_DIM; po.ldr = ENC_DIM;
+    po.Alo = y_lo_l;
     launch_gemm(po, st);
-    launch_rmsnorm(xt, nrm, L.ffn_norm, BS, ENC_DIM, 1e-5f, st);
+    launch_rmsnorm(xt, nrm, L.ffn_norm, BS, ENC_DIM, 1e-5f, st, 0, nrm_lo);
     GemmParams p1;
     p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = BS; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM; p1.ldc = 2 * ENC_INTER;
+    p1.Alo = nrm_lo;
     GemmParams p13[2] = {p1, p1};            // w1 and w3 side by side in one launch
     p13[1].W = L.w3; p13[1].C = h13 + ENC_INTER;
     launch_gemm(p13, 2, st);
-    launch_silu_mul(h13, gbuf, BS, ENC_INTER, st);
+    launch_silu_mul(h13, gbuf, BS, ENC_INTER, st, g_lo);
     GemmParams p2;
     p2.A = gbuf; p2.W = L.w2; p2.C = xt; p2.gamma = L.ls_ffn; p2.residual = xt; p2.M = BS; p2.N = ENC_DIM; p2.K = ENC_INTER;
     p2.lda = ENC_INTER; p2.ldc = ENC_DIM; p2.ldr = ENC_DIM;
+    p2.Alo = g_lo;
     launch_gemm(p2, st);
   }
   launch_rmsnorm(xt, nrm, enc_norm_w, BS, ENC_DIM, 1e-5f, st);

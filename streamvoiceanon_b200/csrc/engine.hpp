@@ -254,6 +254,11 @@ struct Engine {
   std::vector<float*> owned;                   // packed weights built at finalize
   Workspace ws;
   cudaStream_t own_stream = nullptr;
+  // lo terms (x - trunc_tf32(x)) of the activations that feed the pair GEMM kernel (gemm_pair.cu), written by their producers:
+  // grow-only buffers, one per role (0: norm / dwconv output, 1: hidden of the MLP, 2: attention output).  null while a stream
+  // capture is running and the buffer would have to grow -- the GEMM then splits A itself or stays on the single-CTA kernel.
+  struct LoScratch { float* p = nullptr; size_t cap = 0; } lo_scr[3];
+  float* lo_scratch(int slot, size_t n_floats, cudaStream_t st);
 
   // ---- AR
   ArDecodeArgs ar{};

@@ -282,6 +282,7 @@ bool g_gemm_use_tc = true;
 bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pipe.cu
 bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st);     // gemm_tc.cu
 bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st);  // conv_small.cu
+bool launch_gemm_pair(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pair.cu
 bool g_use_conv_small = true;
 
 // ---- measurement aid (svanon_gemm_timing): every GEMM launch bracketed by CUDA events on its own stream, summed per
@@ -370,6 +371,11 @@ static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t s
   if (p.M <= 0 || p.N <= 0) return;
   if (g_use_conv_small && launch_conv_small(ps, count, st)) {     // thin causal convs (HiFi-GAN levels with 16/32 channels)
     *backend = GEMM_BACKEND_CONV_SMALL;
+    SV_LAUNCHED();
+    return;
+  }
+  if (g_gemm_use_tc && launch_gemm_pair(ps, count, st)) {       // tcgen05 3xTF32 on CTA pairs, operands by tensor-map TMA (M >= 4096)
+    *backend = GEMM_BACKEND_TC;
     SV_LAUNCHED();
     return;
   }

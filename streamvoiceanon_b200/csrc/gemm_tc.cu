@@ -839,6 +839,7 @@ bool gemm_tiled_weights(const float* W, int taps, int N, int K, bool half, cudaS
 // drops the cached copies of one weight pointer (test hook: svanon_debug_gemm with static-weight treatment)
 void gemm_forget_weights(const float* W) {
   cudaDeviceSynchronize();
+  gemm_pair_forget_weights(W);
   auto ih = half_registry().find(W);
   if (ih != half_registry().end()) { cudaFree(ih->second.data); half_registry().erase(ih); }
   for (int h = 0; h < 2; ++h) {
@@ -849,6 +850,7 @@ void gemm_forget_weights(const float* W) {
 }
 
 void gemm_half_release() {
+  gemm_pair_release();
   for (auto& kv : half_registry()) cudaFree(kv.second.data);
   half_registry().clear();
   for (int h = 0; h < 2; ++h) {

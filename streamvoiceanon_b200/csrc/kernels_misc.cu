@@ -66,7 +66,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict_
 template <int MAXPT>
 __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ dw_w,
                                   const float* __restrict__ dw_b, const float* __restrict__ ln_w,
-                                  const float* __restrict__ ln_b, int C, float eps, int seg_rows, long long x_seg) {
+                                  const float* __restrict__ ln_b, int C, float eps, int seg_rows, long long x_seg,
+                                  float* __restrict__ y_lo) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
@@ -99,13 +100,17 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, float* __restrict
 #pragma unroll
   for (int i = 0; i < MAXPT; ++i) {
     const int c = threadIdx.x + i * blockDim.x;
-    if (c < C) y[row * C + c] = (v[i] - mean) * inv * ln_w[c] + ln_b[c];
+    if (c < C) {
+      const float o = (v[i] - mean) * inv * ln_w[c] + ln_b[c];
+      y[row * C + c] = o;
+      if (y_lo) y_lo[row * C + c] = tf32_lo(o);
+    }
   }
 }
 
 template <int MAXPT>
 __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w, int C,
-                               float eps, long long x_ld) {
+                               float eps, long long x_ld, float* __restrict__ y_lo) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
@@ -123,7 +128,11 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, float* __restrict__ 
 #pragma unroll
   for (int i = 0; i < MAXPT; ++i) {
     const int c = threadIdx.x + i * blockDim.x;
-    if (c < C) y[row * C + c] = v[i] * inv * w[c];
+    if (c < C) {
+      const float o = v[i] * inv * w[c];
+      y[row * C + c] = o;
+      if (y_lo) y_lo[row * C + c] = tf32_lo(o);
+    }
   }
 }
 
@@ -151,7 +160,8 @@ __global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict_
   p[1] = x1 * c + x0 * s;
 }
 
-__global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__ out, long long rows, int I) {
+__global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__ out, long long rows, int I,
+                                float* __restrict__ out_lo) {
   pdl_trigger();
   pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +169,9 @@ __global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__
   const long long r = idx / I;
   const int c = idx % I;
   const float a = h[r * 2 * I + c], b = h[r * 2 * I + I + c];
-  out[idx] = (a / (1.f + expf(-a))) * b;
+  const float o = (a / (1.f + expf(-a))) * b;
+  out[idx] = o;
+  if (out_lo) out_lo[idx] = tf32_lo(o);
 }
 
 // LinearSpectrogram magnitude, spectrogram.py:62: sqrt(re^2 + im^2 + 1e-6); pad columns are zero.
@@ -400,18 +412,19 @@ void launch_layernorm(const float* x, float* y, const float* w, const float* b, 
 }
 
 void launch_dwconv7_ln(const float* x, float* y, const float* dw_w, const float* dw_b, const float* ln_w,
-                       const float* ln_b, int rows, int C, float eps, cudaStream_t st, int seg_rows, long long x_seg) {
+                       const float* ln_b, int rows, int C, float eps, cudaStream_t st, int seg_rows, long long x_seg,
+                       float* y_lo) {
   if (rows <= 0) return;
   SV_CHECK(C <= 512, "dwconv C");
-  launch_pdl(dwconv7_ln_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, dw_w, dw_b, ln_w, ln_b, C, eps, seg_rows, x_seg);
+  launch_pdl(dwconv7_ln_kernel<4>, dim3(rows), dim3(128), 0, st, x, y, dw_w, dw_b, ln_w, ln_b, C, eps, seg_rows, x_seg, y_lo);
   SV_LAUNCHED();
 }
 
 void launch_rmsnorm(const float* x, float* y, const float* w, int rows, int C, float eps, cudaStream_t st,
-                    long long x_ld) {
+                    long long x_ld, float* y_lo) {
   if (rows <= 0) return;
   SV_CHECK(C <= 1024, "rmsnorm C");
-  launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, x, y, w, C, eps, x_ld > 0 ? x_ld : (long long)C);
+  launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, x, y, w, C, eps, x_ld > 0 ? x_ld : (long long)C, y_lo);
   SV_LAUNCHED();
 }
 
@@ -422,9 +435,9 @@ void launch_rope_qk(float* qkv, const float* table, int rows, int heads, int pos
   SV_LAUNCHED();
 }
 
-void launch_silu_mul(const float* h13, float* out, int rows, int I, cudaStream_t st) {
+void launch_silu_mul(const float* h13, float* out, int rows, int I, cudaStream_t st, float* out_lo) {
   if (rows <= 0) return;
-  launch_pdl(silu_mul_kernel, dim3(blocks_for((long long)rows * I, 256)), dim3(256), 0, st, h13, out, rows, I);
+  launch_pdl(silu_mul_kernel, dim3(blocks_for((long long)rows * I, 256)), dim3(256), 0, st, h13, out, (long long)rows, I, out_lo);
   SV_LAUNCHED();
 }
 

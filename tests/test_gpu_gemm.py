@@ -108,10 +108,12 @@ def test_tcgen05_weights_by_tma(M, N, K, precision):
     out = torch.empty(M, N, device="cuda")
     _lib.check(lib.svanon_set_precision(precision))
     _lib.check(lib.svanon_debug_gemm_weights_static(1))
+    _lib.check(lib.svanon_set_gemm_pair(0))          # this test holds the single-CTA kernel; the pair kernel has its own below
     try:
         _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, 0, None))
         torch.cuda.synchronize()
     finally:
+        _lib.check(lib.svanon_set_gemm_pair(-1))
         _lib.check(lib.svanon_debug_gemm_weights_static(0))
         _lib.check(lib.svanon_set_precision(0))
     exact = A.double() @ W.double().T + b.double()
@@ -121,3 +123,40 @@ def test_tcgen05_weights_by_tma(M, N, K, precision):
     else:
         rounded = A.half().double() @ W.half().double().T + b.double()
         assert float((out.double() - rounded).abs().max()) < 1e-5 * scale
+
+
+@pytest.mark.parametrize("M,N,K,act", [(16384, 2048, 512, 1), (16384, 512, 2048, 0), (20992, 384, 1536, 0), (20992, 128, 512, 0),
+                                       (12500, 256, 96, 0), (16384, 1536, 512, 0)])
+def test_pair_gemm_bitwise(M, N, K, act):
+    """The CTA-pair kernel (csrc/gemm_pair.cu: tcgen05.mma.cta_group::2, both operands by tensor-map TMA, RAW fp32 arrays as the
+    hi terms) computes the same bits as the single-CTA kernel (explicitly masked hi terms, operands through registers), with
+    its own lo-split pass (mode 1) and with explicitly masked hi copies (mode 2); ragged M; the launch counter proves the
+    kernel under test ran."""
+    from streamvoiceanon_b200 import _lib
+    from streamvoiceanon_b200.engine import Engine, ptr
+    eng, lib = Engine.get(0), _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    outs = {}
+    _lib.check(lib.svanon_debug_gemm_weights_static(1))
+    try:
+        for mode in (0, 1, 2):
+            out = torch.full((M, N), float("nan"), device="cuda")
+            _lib.check(lib.svanon_set_gemm_pair(mode))
+            n0 = lib.svanon_gemm_pair_launches()
+            _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, act, None))
+            torch.cuda.synchronize()
+            assert lib.svanon_gemm_pair_launches() - n0 == (1 if mode else 0)
+            outs[mode] = out
+    finally:
+        _lib.check(lib.svanon_set_gemm_pair(-1))
+        _lib.check(lib.svanon_debug_gemm_weights_static(0))
+    exact = A.double() @ W.double().T + b.double()
+    if act == 1:
+        exact = torch.nn.functional.gelu(exact)
+    scale = max(1.0, float(exact.abs().max()))
+    assert float((outs[1].double() - exact).abs().max()) < 2e-5 * scale
+    assert torch.equal(outs[1], outs[0]), int((outs[1] != outs[0]).sum())
+    assert torch.equal(outs[2], outs[0]), int((outs[2] != outs[0]).sum())
