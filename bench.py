@@ -19,7 +19,7 @@ dual-AR decode step, vocoder on the last 64 code frames, tail select.  Prints ON
                      encode and stage V's wide levels): executed flops of the step's ACTUAL GEMM shapes / their event-timed
                      launch durations (svanon_gemm_timing) against the TF32 tensor peak
   roofline_ar        the stage-A decode kernel against measured HBM bandwidth
-  roofline_gemm_many_streams   the same GEMM kernel on the many-stream encoder MLP shape (128 x 256 tile)
+  roofline_gemm_many_streams   the wide-GEMM kernel of the many-stream batches (gemm_pair.cu) on the encoder MLP shape
   stage_compute      executed GFLOP / stage time of the compute-bound stages E and V against the 3xTF32 ceiling
   concurrent_streams BASELINE config 4 on every GPU: B = 128 streams in lock-step (svanon_batch_process_chunk) for >= 700
                      chunks with HOST buffers, so that every stream's re-prompt falls inside the window: mean / p50 / p99 /
@@ -493,38 +493,59 @@ def perf_mode_leg(tok, args, rank):
 
 
 def gemm_roofline(peaks):
-    """Tensor-pipe roofline of the dense-projection GEMM kernel (gemm_tc.cu) on the many-stream encoder MLP shape
-    (M = 16384 rows = 32 streams x 512, N = 2048, K = 512, +bias, GELU), timed live with CUDA events.  Every fp32-grade
-    product costs three TF32 MMAs, so `achieved` counts 3 x 2MNK TF32 flops; `peak` = half the measured dense bf16
-    throughput of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate on B200), else half the nominal 2250."""
+    """Tensor-pipe roofline of the wide-GEMM kernel of the many-stream batches (gemm_pair.cu: CTA pairs, operands by tensor-map
+    TMA) on the encoder MLP shape (M = 16384 rows = 128 streams x 128 window tokens, N = 2048, K = 512, +bias, GELU), timed
+    live with CUDA events the way the engine runs it: engine-owned (static) weights, the lo term of A already written by
+    the producer of A.  `with_split_pass_us` is the same launch when the kernel has to split A itself; `single_cta_us` is
+    the round-1/2 kernel (gemm_tc.cu, 128 x 256 tile) on the same problem.  Every fp32-grade product costs three TF32 MMAs, so
+    `achieved` counts 3 x 2MNK TF32 flops; `peak` = half the measured dense bf16 throughput of MEASURED_PEAKS.json (TF32 runs at
+    half the bf16 rate on B200), else half the nominal 2250."""
     from streamvoiceanon_b200 import _lib
     from streamvoiceanon_b200.engine import Engine, ptr
     eng, lib = Engine.get(torch.cuda.current_device()), _lib.load()
     M, N, K = 16384, 2048, 512
     A = torch.randn(M, K, device="cuda")
+    A_lo = A - (A.view(torch.int32) & -8192).view(torch.float32)          # x - trunc_tf32(x), exact in fp32
     Ws = [torch.randn(N, K, device="cuda") for _ in range(8)]
     b = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda")
-    for i in range(5):
-        _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(Ws[i % 8]), ptr(b), ptr(out), M, N, K, 1, None))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 40
-    e0.record()
-    for i in range(n):
-        _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(Ws[i % 8]), ptr(b), ptr(out), M, N, K, 1, None))
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / n * 1e3
+
+    def timed(pair_mode, a_lo):
+        _lib.check(lib.svanon_set_gemm_pair(pair_mode))
+        _lib.check(lib.svanon_debug_gemm_alo(ptr(a_lo) if a_lo is not None else None))
+        for i in range(8):
+            _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(Ws[i % 8]), ptr(b), ptr(out), M, N, K, 1, None))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 40
+        n0 = lib.svanon_gemm_pair_launches()
+        e0.record()
+        for i in range(n):
+            _lib.check(lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(Ws[i % 8]), ptr(b), ptr(out), M, N, K, 1, None))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3, lib.svanon_gemm_pair_launches() - n0
+
+    _lib.check(lib.svanon_debug_gemm_weights_static(2))       # like engine weights: converted copies cached per weight pointer
+    try:
+        us, took = timed(1, A_lo)
+        us_split, _ = timed(1, None)
+        us_single, _ = timed(0, None)
+    finally:
+        _lib.check(lib.svanon_set_gemm_pair(-1))
+        _lib.check(lib.svanon_debug_gemm_alo(None))
+        _lib.check(lib.svanon_debug_gemm_weights_static(0))
     fp32_tflops = 2.0 * M * N * K / us / 1e6
     bf16 = peaks.get("bf16_tflops") or peaks.get("bf16_tflops_sustained")        # kernel timed alone: the burst figure
     peak, src = (bf16 / 2, "0.5 x measured dense bf16 burst (MEASURED_PEAKS.json)") if bf16 else (1125.0, "0.5 x nominal 2250 bf16")
-    return {"kernel": "gemm_tc_kernel<256,2> (tcgen05 3xTF32, 128x256 tile)", "bound": "tensor", "shape": [M, N, K],
-            "where": "encoder ConvNeXt MLP of 32 lock-step streams (M = 32 x 512); does not occur in the single-stream step",
-            "launch_us": us, "fp32_equivalent_tflops": fp32_tflops, "achieved": 3 * fp32_tflops, "peak": peak,
+    return {"kernel": "gemm_pair_kernel<256> (tcgen05.mma.cta_group::2 3xTF32, 256x256 tile per CTA pair, A and B by tensor-map "
+                      "TMA, persistent with two TMEM accumulators)", "bound": "tensor", "shape": [M, N, K],
+            "where": "encoder transformer MLP of 128 lock-step streams (M = 128 x 128 window tokens); does not occur in the "
+                     "single-stream step", "pair_kernel_launches_timed": int(took),
+            "launch_us": us, "with_split_pass_us": us_split, "single_cta_us": us_single,
+            "fp32_equivalent_tflops": fp32_tflops, "achieved": 3 * fp32_tflops, "peak": peak,
             "unit": "TFLOP/s", "frac": 3 * fp32_tflops / peak, "peak_source": src,
-            "traffic": None, "note": "profiles/README.md (last section): the main loop runs within 15 % of the practical TF32 MMA rate "
-            "(1.12 us per 128x256x32 slab); the rest is per-tile overhead -- prologue, first loads, accumulator drain, epilogue "
-            "and CTA turnover cost as much SM time as the MMAs of a K = 512 tile"}
+            "traffic": None, "note": "profiles/r2x_gemm_pair_ncu_summary.txt: tensor pipe active 79 % of elapsed cycles (the single-CTA "
+            "kernel: 34 %); what is left is the first tile's fill, the last tile's epilogue and 512 tiles on 74 pairs (6.9 rounds)"}
 
 
 # Executed floating-point work per stream and chunk (chunk = 1), DESIGN.md section 4.  Stage E: conv stack incl. the

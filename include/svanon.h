@@ -165,6 +165,17 @@ int svanon_set_precision(int mode);
  * bit for bit.  -1 = environment (SVANON_GEMM_PAIR, default on), 0 = off, 1 = on, 2 = on with explicitly masked hi terms (A/B
  * check of the "kind::tf32 truncates" assumption the kernel rests on). */
 int svanon_set_gemm_pair(int mode);
+/* test / measurement hook: the lo term of A (A - trunc_tf32(A), device memory, [M][K] compact) for the following
+ * svanon_debug_gemm calls, as the engine's row-wise kernels write it beside their results; null (default): the pair kernel
+ * runs its own split pass in front of the GEMM */
+int svanon_debug_gemm_alo(const float* a_lo);
+/* test hook for the fused GEMM forms of the encoder transformer (device pointers only, synchronous): W2 != NULL: C [M][N] =
+ * silu(A W^T) * (A W2^T) (SwiGLU gate, windowed_transformer.py FeedForward); rope_table != NULL: C [M][N] = A W^T with the
+ * interleaved-pair RoPE of apply_rotary_emb (windowed_transformer.py:368-380) on its first rope_cols columns, position of row m
+ * = m % rope_seg_rows (rope_seg_rows > 0) or m.  The pair kernel does both in its epilogue, the other back ends through the
+ * row-wise kernels: the results are the same bits. */
+int svanon_debug_gemm_fused(svanon_engine* e, const float* A, const float* W, const float* W2, const float* rope_table,
+                            int rope_cols, int rope_seg_rows, float* C, int M, int N, int K, void* cuda_stream);
 /* number of GEMM launches the pair kernel has taken in this process (tests: the path under test really ran) */
 long long svanon_gemm_pair_launches(void);
 /* programmatic dependent launch of the GEMM kernels (default on): a GEMM's launch and weight-only prologue overlap

@@ -53,6 +53,8 @@ _SIGS = {
     "svanon_set_precision": (C.c_int, [C.c_int]),
     "svanon_set_gemm_pair": (C.c_int, [C.c_int]),
     "svanon_gemm_pair_launches": (C.c_longlong, []),
+    "svanon_debug_gemm_alo": (C.c_int, [_p]),
+    "svanon_debug_gemm_fused": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p]),
     "svanon_debug_gemm_weights_static": (C.c_int, [C.c_int]),
     "svanon_debug_gemm": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "svanon_debug_gemm_taps": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, C.POINTER(C.c_int), _p, _p, C.c_int,

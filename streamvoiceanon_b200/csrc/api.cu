@@ -15,6 +15,7 @@ void tc_prof_dump();
 namespace svanon {
 thread_local std::string g_api_err;
 }
+static const float* g_debug_gemm_alo = nullptr;   // svanon_debug_gemm_alo: lo term of A for the next svanon_debug_gemm calls
 static int g_debug_gemm_static = 0;         // svanon_debug_gemm_weights_static: 0 off, 1 static + dropped after the call, 2 static + kept
 
 namespace {
@@ -463,6 +464,11 @@ int svanon_debug_gemm_weights_static(int enable) {
   return 0;
 }
 
+int svanon_debug_gemm_alo(const float* a_lo) {
+  g_debug_gemm_alo = a_lo;
+  return 0;
+}
+
 int svanon_set_gemm_pair(int mode) {
   return guarded([&] {
     SV_CHECK(mode >= -1 && mode <= 2, "gemm pair mode: -1 environment, 0 off, 1 on, 2 on with masked hi copies");
@@ -489,12 +495,40 @@ int svanon_debug_gemm(svanon_engine* e, const float* A, const float* W, const fl
     p.C = a.out(C, (size_t)M * N);
     p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N; p.act = act;
     p.w_static = g_debug_gemm_static != 0; // caller memory: normally never cached as a converted weight copy
+    if (g_debug_gemm_alo) { SV_CHECK(on_device(g_debug_gemm_alo) && on_device(A), "svanon_debug_gemm_alo: device pointers only"); p.Alo = g_debug_gemm_alo; }
     launch_gemm(p, a.st);
     a.finish();
     if (g_debug_gemm_static == 1) gemm_forget_weights(p.W);
 #ifdef SVANON_TC_PROF
     tc_prof_dump();
 #endif
+  });
+}
+
+int svanon_debug_gemm_fused(svanon_engine* e, const float* A, const float* W, const float* W2, const float* rope_table,
+                            int rope_cols, int rope_seg_rows, float* C, int M, int N, int K, void* stream) {
+  return guarded([&] {
+    SV_CHECK(e && A && W && C && M > 0 && N > 0 && K > 0 && K % 16 == 0, "bad arguments");
+    SV_CHECK(on_device(A) && on_device(W) && on_device(C) && (!W2 || on_device(W2)) && (!rope_table || on_device(rope_table)),
+             "device pointers only");
+    SV_CHECK((W2 != nullptr) != (rope_table != nullptr), "exactly one fused form: W2 (SwiGLU gate) or rope_table (RoPE on q | k)");
+    SV_CUDA(cudaSetDevice(e->eng.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmParams p;
+    p.A = A; p.W = W; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N;
+    p.w_static = g_debug_gemm_static != 0;
+    p.Alo = g_debug_gemm_alo;
+    float* tmp = nullptr;
+    if (W2) {
+      SV_CUDA(cudaMalloc(&tmp, (size_t)M * 2 * N * sizeof(float)));
+      p.W2 = W2; p.dual_tmp = tmp;
+    } else {
+      p.rope_table = rope_table; p.rope_cols = rope_cols; p.rope_seg_rows = rope_seg_rows;
+    }
+    launch_gemm(p, st);
+    SV_CUDA(cudaStreamSynchronize(st));
+    if (tmp) cudaFree(tmp);
+    if (g_debug_gemm_static == 1) { gemm_forget_weights(p.W); if (W2) gemm_forget_weights(W2); }
   });
 }
 

@@ -150,6 +150,16 @@ struct GemmParams {
   // result, compact [M][N], for the GEMM that consumes C next.  Kernels other than the pair kernel ignore both.
   const float* Alo = nullptr;
   float* Clo = nullptr;
+  // Fused forms (launch_gemm computes them with any back end; the pair kernel does them in its epilogue, the others through the
+  // row-wise kernels afterwards):
+  //   W2 != null: SwiGLU gate, C[m, n] = silu(sum_k A W[n]) * (sum_k A W2[n]) -- W2 has W's shape, no bias / gamma / residual;
+  //     dual_tmp [M][2N] is scratch for back ends that need the two products in memory.
+  //   rope_table != null: interleaved-pair RoPE on the first rope_cols columns of C (q | k of a fused qkv row), position of row
+  //     m = rope_pos0 + (rope_seg_rows > 0 ? m % rope_seg_rows : m); table as launch_rope_qk takes it.
+  const float* W2 = nullptr;
+  float* dual_tmp = nullptr;
+  const float* rope_table = nullptr;
+  int rope_cols = 0, rope_seg_rows = 0, rope_pos0 = 0;
 };
 
 #ifdef __CUDACC__

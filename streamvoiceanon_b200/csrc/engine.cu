@@ -670,8 +670,9 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
     GemmParams p;
     p.A = nrm; p.W = L.wqkv; p.C = qkv; p.M = BS; p.N = 3 * ENC_DIM; p.K = ENC_DIM; p.lda = ENC_DIM; p.ldc = 3 * ENC_DIM;
     p.Alo = nrm_lo;
+    // RoPE on q | k rides in the GEMM (pair kernel: in its epilogue; other back ends: launch_rope_qk afterwards)
+    p.rope_table = enc_rope; p.rope_cols = 2 * ENC_DIM; p.rope_seg_rows = B > 1 ? S : 0; p.rope_pos0 = 0;
     launch_gemm(p, st);
-    launch_rope_qk(qkv, enc_rope, BS, ENC_HEADS, 0, st, B > 1 ? S : 0);
     if (tail_only && l == ENC_LAYERS - 1) {
       const int c = keep_last, R = B * c;
       float* xtail = ws.alloc_f((long long)R * ENC_DIM);
@@ -713,13 +714,11 @@ void Engine::enc_transformer_bsq(float* xt, int B, int S, long long* ids_dev, cu
     po.Alo = y_lo_l;
     launch_gemm(po, st);
     launch_rmsnorm(xt, nrm, L.ffn_norm, BS, ENC_DIM, 1e-5f, st, 0, nrm_lo);
-    GemmParams p1;
-    p1.A = nrm; p1.W = L.w1; p1.C = h13; p1.M = BS; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM; p1.ldc = 2 * ENC_INTER;
-    p1.Alo = nrm_lo;
-    GemmParams p13[2] = {p1, p1};            // w1 and w3 side by side in one launch
-    p13[1].W = L.w3; p13[1].C = h13 + ENC_INTER;
-    launch_gemm(p13, 2, st);
-    launch_silu_mul(h13, gbuf, BS, ENC_INTER, st, g_lo);
+    GemmParams p1;                           // SwiGLU gate: silu(x w1^T) * (x w3^T), both products in one launch
+    p1.A = nrm; p1.W = L.w1; p1.W2 = L.w3; p1.C = gbuf; p1.M = BS; p1.N = ENC_INTER; p1.K = ENC_DIM; p1.lda = ENC_DIM;
+    p1.ldc = ENC_INTER; p1.dual_tmp = h13;
+    p1.Alo = nrm_lo; p1.Clo = g_lo;
+    launch_gemm(p1, st);
     GemmParams p2;
     p2.A = gbuf; p2.W = L.w2; p2.C = xt; p2.gamma = L.ls_ffn; p2.residual = xt; p2.M = BS; p2.N = ENC_DIM; p2.K = ENC_INTER;
     p2.lda = ENC_INTER; p2.ldc = ENC_DIM; p2.ldr = ENC_DIM;

@@ -340,15 +340,44 @@ void gemm_timing_external(cudaStream_t st, bool begin, double flop) {
 
 static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t st, int* backend);
 
+// Back ends other than the pair kernel compute the fused forms of GemmParams (SwiGLU gate, RoPE) through the row-wise kernels.
+static void launch_gemm_fused(const GemmParams* ps, int count, cudaStream_t st, int* backend) {
+  const GemmParams& p = ps[0];
+  if (!p.W2 && !p.rope_table) { launch_gemm_dispatch(ps, count, st, backend); return; }
+  SV_CHECK(count == 1, "fused GEMM forms take one problem per launch");
+  if (g_gemm_use_tc && launch_gemm_pair(ps, 1, st)) {
+    *backend = GEMM_BACKEND_TC;
+    SV_LAUNCHED();
+    return;
+  }
+  if (p.W2) {
+    SV_CHECK(p.dual_tmp && !p.bias && !p.gamma && !p.residual && !p.accumulate && p.seg_rows == 0 && p.ldc == p.N,
+             "SwiGLU GEMM: plain output, no epilogue terms, scratch for the two products");
+    GemmParams q[2] = {p, p};
+    for (auto& g : q) { g.W2 = nullptr; g.dual_tmp = nullptr; g.Clo = nullptr; g.ldc = 2 * p.N; }
+    q[0].C = p.dual_tmp;
+    q[1].C = p.dual_tmp + p.N;
+    q[1].W = p.W2;
+    launch_gemm_dispatch(q, 2, st, backend);
+    launch_silu_mul(p.dual_tmp, p.C, p.M, p.N, st, p.Clo);
+    return;
+  }
+  GemmParams q = p;
+  q.rope_table = nullptr;
+  launch_gemm_dispatch(&q, 1, st, backend);
+  SV_CHECK(p.seg_rows == 0 && p.ldc == 3LL * (p.rope_cols / 2), "RoPE GEMM: plain fused qkv output");
+  launch_rope_qk(p.C, p.rope_table, p.M, p.rope_cols / (2 * HEAD_DIM), p.rope_pos0, st, p.rope_seg_rows);
+}
+
 void launch_gemm(const GemmParams* ps, int count, cudaStream_t st) {
   if (!g_gemm_timing.on) {
     int backend;
-    launch_gemm_dispatch(ps, count, st, &backend);
+    launch_gemm_fused(ps, count, st, &backend);
     return;
   }
-  GemmTiming::Rec r{g_gemm_timing.get(), g_gemm_timing.get(), 0, gemm_flop(ps, count)};
+  GemmTiming::Rec r{g_gemm_timing.get(), g_gemm_timing.get(), 0, gemm_flop(ps, count) * (ps[0].W2 ? 2.0 : 1.0)};
   SV_CUDA(cudaEventRecord(r.e0, st));
-  launch_gemm_dispatch(ps, count, st, &r.backend);
+  launch_gemm_fused(ps, count, st, &r.backend);
   SV_CUDA(cudaEventRecord(r.e1, st));
   g_gemm_timing.recs.push_back(r);
 }

@@ -46,12 +46,14 @@ constexpr int P_THREADS = 18 * 32;
 
 struct alignas(64) PairProblem {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap b2_hi, b2_lo;             // SwiGLU form: the second weight matrix (boxes of 64 rows, like b_hi / b_lo in that form)
   GemmParams p;
   float* C_lo;                          // optional: lo term of the result, [M][N] compact
 };
 struct PairArgs {
   PairProblem prob[2];
   int count, tiles_m, tiles_n, k_slabs;
+  int dual;                             // SwiGLU form (GemmParams::W2): see the kernel
 };
 
 __device__ __forceinline__ float gelu_erf_p(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -173,7 +175,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
       const int z = tile / tiles_per_problem, r = tile - z * tiles_per_problem;
       const int mt = r / args.tiles_n, nt = r - mt * args.tiles_n;
       const PairProblem& pr = args.prob[z];
-      const int row0 = mt * 256 + (int)rank * PBM, n0 = nt * BN + (int)rank * BH;
+      // SwiGLU form: a pair tile is 128 OUTPUT columns; this CTA's B half = 64 rows of W | the same 64 rows of W2
+      const int row0 = mt * 256 + (int)rank * PBM, n0 = args.dual ? nt * (BN / 2) + (int)rank * (BH / 2) : nt * BN + (int)rank * BH;
       for (int s = 0; s < k_slabs; ++s) {
         pmbar_wait(smem_u32p(&empty_bar[stage]), parity);
         if (pelect_one()) {
@@ -186,6 +189,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
           tma_load_2d_pair(dst + A_BYTES, &pr.a_lo, s * PK, row0, bar);
           tma_load_2d_pair(dst + 2u * A_BYTES, &pr.b_hi, s * PK, n0, bar);
           tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES, &pr.b_lo, s * PK, n0, bar);
+          if (args.dual) {
+            tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES / 2u, &pr.b2_hi, s * PK, n0, bar);
+            tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES + B_BYTES / 2u, &pr.b2_lo, s * PK, n0, bar);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; parity ^= 1u; }
@@ -250,6 +257,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
       const long long r_row = (row_ok && p.residual) ? gemm_r_row(p, m) : 0;
       const int act = p.act;
       const float out_scale = p.out_scale;
+      if (args.dual) {
+        // accumulator columns: [0,64) = A W^T for output columns 0..63 of the tile, [64,128) = A W2^T for the same columns,
+        // [128,192) / [192,256) the same for output columns 64..127 (the peer CTA's B half).  Warp group g owns output
+        // columns [32 g, 32 g + 32).
+        const unsigned col1 = (unsigned)((grp >> 1) * (BN / 2) + (grp & 1) * 32);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          float v1[16], v3[16];
+          ptmem_ld16(tmem_base + acc * BN + ((unsigned)(quad * 32) << 16) + col1 + (unsigned)c0, v1);
+          ptmem_ld16(tmem_base + acc * BN + ((unsigned)(quad * 32) << 16) + col1 + (unsigned)(BN / 4 + c0), v3);
+          if (c0 == 16) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0)
+              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32p(&acc_empty[acc]), 0)) : "memory");
+          }
+          if (!row_ok) continue;
+          const int n_base = nt * (BN / 2) + grp * 32 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = v1[j + e], b = v3[j + e];
+              o[e] = (a / (1.f + expf(-a))) * b;                       // silu_mul_kernel's expression
+            }
+            *reinterpret_cast<float4*>(p.C + c_row + n_base + j) = make_float4(o[0], o[1], o[2], o[3]);
+            if (pr.C_lo)
+              *reinterpret_cast<float4*>(pr.C_lo + (long long)m * p.N + n_base + j) =
+                  make_float4(tf32_lo(o[0]), tf32_lo(o[1]), tf32_lo(o[2]), tf32_lo(o[3]));
+          }
+        }
+        continue;
+      }
+      const float* rope = p.rope_table;
+      const long long rope_row = rope ? (long long)(p.rope_pos0 + (p.rope_seg_rows > 0 ? m % p.rope_seg_rows : m)) * HEAD_DIM : 0;
 #pragma unroll 1
       for (int c0 = grp * CG; c0 < (grp + 1) * CG; c0 += 16) {
         float v[16];
@@ -281,15 +324,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
           }
           o.x *= out_scale; o.y *= out_scale; o.z *= out_scale; o.w *= out_scale;
-          *reinterpret_cast<float4*>(p.C + c_row + n_base + j) = o;
-          if (pr.C_lo) {
-            float4 l;
-            l.x = o.x - __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u);
-            l.y = o.y - __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
-            l.z = o.z - __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u);
-            l.w = o.w - __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(pr.C_lo + (long long)m * p.N + n_base + j) = l;
+          if (rope && n_base < p.rope_cols) {
+            // rope_qk_kernel's arithmetic on the pairs (2i, 2i + 1) of a head; table entry [pos][i] = (cos, sin)
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(rope + rope_row + ((n_base + j) & (HEAD_DIM - 1))));
+            const float x0 = o.x, x1 = o.y, x2 = o.z, x3 = o.w;
+            o.x = x0 * cs.x - x1 * cs.y;
+            o.y = x1 * cs.x + x0 * cs.y;
+            o.z = x2 * cs.z - x3 * cs.w;
+            o.w = x3 * cs.z + x2 * cs.w;
           }
+          *reinterpret_cast<float4*>(p.C + c_row + n_base + j) = o;
+          if (pr.C_lo)
+            *reinterpret_cast<float4*>(pr.C_lo + (long long)m * p.N + n_base + j) =
+                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
         }
       }
     }
@@ -502,6 +549,10 @@ bool gemm_pair_eligible(const GemmParams* ps, int count) {
   for (int i = 0; i < count; ++i) {
     const GemmParams& p = ps[i];
     if (p.M != p0.M || p.N != p0.N || p.K != p0.K) return false;
+    if (p.W2 && (count != 1 || p.bias || p.gamma || p.residual || p.act != ACT_NONE || p.out_scale != 1.f || p.seg_rows != 0 ||
+                 p.ldc != p.N || p.rope_table || (reinterpret_cast<uintptr_t>(p.W2) & 15)))
+      return false;
+    if (p.rope_table && (count != 1 || p.rope_cols % 16 != 0 || (reinterpret_cast<uintptr_t>(p.rope_table) & 15))) return false;
     if (p.taps != 1 || p.a_row_step != 1 || p.tap_off[0] != 0 || p.prologue != PRO_NONE || p.accumulate || !p.w_static) return false;
     if (p.seg_rows > 0 && p.a_seg != (long long)p.seg_rows * p.lda) return false;      // A rows must be one plain array
     if (p.lda % 4 != 0 || p.ldc % 4 != 0 || (p.residual && p.ldr % 4 != 0)) return false;
@@ -510,8 +561,9 @@ bool gemm_pair_eligible(const GemmParams* ps, int count) {
     if (!al16(p.A) || !al16(p.W) || !al16(p.C) || !al16(p.bias) || !al16(p.gamma) || !al16(p.residual) || !al16(p.Alo) || !al16(p.Clo))
       return false;
   }
-  const int BN = (p0.N % 256 == 0) ? 256 : 128;
-  return (long long)((p0.M + 255) / 256) * (p0.N / BN) * count >= min_tiles;
+  const int BN = (p0.W2 || p0.N % 256 == 0) ? 256 : 128;
+  const int tile_n = p0.W2 ? 128 : BN;                       // output columns per pair tile
+  return (long long)((p0.M + 255) / 256) * (p0.N / tile_n) * count >= min_tiles;
 }
 
 // Returns false when the launch is not one this kernel takes (the caller continues with gemm_tc.cu).
@@ -519,11 +571,13 @@ bool launch_gemm_pair(const GemmParams* ps, int count, cudaStream_t st) {
   if (!gemm_pair_eligible(ps, count)) return false;
   const int mode = pair_mode();
   const GemmParams& p0 = ps[0];
-  const int BN = (p0.N % 256 == 0) ? 256 : 128;
+  const bool dual = p0.W2 != nullptr;
+  const int BN = (dual || p0.N % 256 == 0) ? 256 : 128;
   PairArgs a;
   a.count = count;
+  a.dual = dual ? 1 : 0;
   a.tiles_m = (p0.M + 255) / 256;
-  a.tiles_n = p0.N / BN;
+  a.tiles_n = p0.N / (dual ? 128 : BN);
   a.k_slabs = p0.K / PK;
   const bool mask_hi = mode == 2;
   for (int i = 0; i < count; ++i) {
@@ -553,8 +607,17 @@ bool launch_gemm_pair(const GemmParams* ps, int count, cudaStream_t st) {
       pr.a_hi = tensor_map_2d(a_hi, p.M, p.K, a_hi_ld, PBM);
       pr.a_lo = tensor_map_2d(a_lo, p.M, p.K, p.K, PBM);
     }
-    pr.b_hi = tensor_map_2d(mask_hi ? w->hi : p.W, p.N, p.K, p.K, BN / 2);
-    pr.b_lo = tensor_map_2d(w->lo, p.N, p.K, p.K, BN / 2);
+    const int b_box = dual ? BN / 4 : BN / 2;
+    pr.b_hi = tensor_map_2d(mask_hi ? w->hi : p.W, p.N, p.K, p.K, b_box);
+    pr.b_lo = tensor_map_2d(w->lo, p.N, p.K, p.K, b_box);
+    pr.b2_hi = pr.b_hi;
+    pr.b2_lo = pr.b_lo;
+    if (dual) {
+      const LoCopy* w2 = weight_lo(p.W2, p.N, p.K, mask_hi, st);
+      if (!w2) return false;
+      pr.b2_hi = tensor_map_2d(mask_hi ? w2->hi : p.W2, p.N, p.K, p.K, b_box);
+      pr.b2_lo = tensor_map_2d(w2->lo, p.N, p.K, p.K, b_box);
+    }
   }
   if (count == 1) a.prob[1] = a.prob[0];
   if (BN == 256) launch_pair_cfg<256>(a, st);

@@ -160,3 +160,59 @@ def test_pair_gemm_bitwise(M, N, K, act):
     assert float((outs[1].double() - exact).abs().max()) < 2e-5 * scale
     assert torch.equal(outs[1], outs[0]), int((outs[1] != outs[0]).sum())
     assert torch.equal(outs[2], outs[0]), int((outs[2] != outs[0]).sum())
+
+
+def _fused(lib, eng, ptr, A, W, W2, table, rope_cols, seg, M, N, K):
+    from streamvoiceanon_b200 import _lib
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.svanon_debug_gemm_fused(eng.handle, ptr(A), ptr(W), ptr(W2) if W2 is not None else None,
+                                           ptr(table) if table is not None else None, rope_cols, seg, ptr(out), M, N, K, None))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("form", ["swiglu", "rope"])
+def test_pair_gemm_fused_epilogues(form):
+    """The fused forms of the many-stream encoder transformer: SwiGLU gate (w1 | w3 as the two halves of the pair's B tile, gate
+    in the epilogue) and RoPE on q | k in the qkv epilogue -- the same bits as the GEMM followed by the row-wise kernels, and
+    close to fp64."""
+    from streamvoiceanon_b200 import _lib
+    from streamvoiceanon_b200.engine import Engine, ptr
+    eng, lib = Engine.get(0), _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(23)
+    M, K = 16384, 512
+    A = torch.randn(M, K, device="cuda", generator=g)
+    if form == "swiglu":
+        N = 1536
+        W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+        W2 = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+        args = (W, W2, None, 0, 0)
+        h1, h3 = A.double() @ W.double().T, A.double() @ W2.double().T
+        exact = torch.nn.functional.silu(h1) * h3
+    else:
+        N, S = 1536, 128
+        W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+        ang = torch.rand(S, 32, device="cuda", generator=g) * 6.28
+        table = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()          # [pos][32][2]
+        args = (W, None, table, 1024, S)
+        y = (A.double() @ W.double().T).view(M, N)
+        pos = torch.arange(M, device="cuda") % S
+        c, s_ = table[pos, :, 0].double(), table[pos, :, 1].double()               # [M][32]
+        qk = y[:, :1024].reshape(M, 16, 32, 2)
+        x0, x1 = qk[..., 0], qk[..., 1]
+        rot = torch.stack([x0 * c[:, None] - x1 * s_[:, None], x1 * c[:, None] + x0 * s_[:, None]], dim=-1).reshape(M, 1024)
+        exact = torch.cat([rot, y[:, 1024:]], dim=1)
+    outs = {}
+    _lib.check(lib.svanon_debug_gemm_weights_static(1))
+    try:
+        for mode in (0, 1):
+            _lib.check(lib.svanon_set_gemm_pair(mode))
+            n0 = lib.svanon_gemm_pair_launches()
+            outs[mode] = _fused(lib, eng, ptr, A, *args, M, N, K)
+            assert lib.svanon_gemm_pair_launches() - n0 == mode
+    finally:
+        _lib.check(lib.svanon_set_gemm_pair(-1))
+        _lib.check(lib.svanon_debug_gemm_weights_static(0))
+    scale = max(1.0, float(exact.abs().max()))
+    assert float((outs[1].double() - exact).abs().max()) < 3e-5 * scale
+    assert torch.equal(outs[1], outs[0]), int((outs[1] != outs[0]).sum())

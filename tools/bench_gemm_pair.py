@@ -77,6 +77,18 @@ if "check" in WHAT:
             ok_all &= describe(f"pair mode {mode}", out, ref)
             print(f"    pair mode {mode} vs fp64: {float((out.double() - r64).abs().max()):.3e}")
     print("CHECK", "OK" if ok_all else "FAILED")
+if "few" in WHAT:          # for ncu: two launches of each kernel on three shapes
+    for (M, N, K) in [(16384, 2048, 512), (16384, 512, 2048), (20992, 384, 1536)]:
+        A = torch.randn(M, K, device="cuda")
+        W = torch.randn(N, K, device="cuda")
+        KEEP.append(W)
+        b = torch.randn(N, device="cuda")
+        out = torch.empty(M, N, device="cuda")
+        for mode in (0, 1):
+            _lib.check(lib.svanon_set_gemm_pair(mode))
+            for i in range(3):
+                lib.svanon_debug_gemm(eng.handle, ptr(A), ptr(W), ptr(b), ptr(out), M, N, K, 1, None)
+        torch.cuda.synchronize()
 if "time" in WHAT:
     for (M, N, K) in [(16384, 2048, 512), (16384, 512, 2048), (16384, 1536, 512), (16384, 512, 512), (16384, 512, 1536),
                       (20992, 1536, 384), (20992, 384, 1536), (20992, 512, 128), (20992, 128, 512), (20992, 1024, 256),
