@@ -187,6 +187,12 @@ __device__ __forceinline__ long long gemm_r_row(const GemmParams& p, int m) {
 // lo term of the 3xTF32 split: x - trunc_tf32(x) (exact in fp32).  Row-wise kernels that feed a wide GEMM write it beside their
 // result (`*_lo` arguments, same compact layout) so that the pair kernel (gemm_pair.cu) takes both terms by TMA.
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// interleaved-pair rotation of apply_rotary_emb with the rounding points spelled out (one product rounded, the other fused),
+// so that every kernel that applies it -- rope_qk_kernel, the pair GEMM's epilogue -- produces the same bits
+__device__ __forceinline__ void rope_pair(float x0, float x1, float c, float s, float& y0, float& y1) {
+  y0 = __fmaf_rn(x0, c, -__fmul_rn(x1, s));
+  y1 = __fmaf_rn(x0, s, __fmul_rn(x1, c));
+}
 // row `row` of a buffer made of segments of seg_rows rows that start seg_stride floats apart (0 rows: plain)
 __device__ __forceinline__ long long seg_row_off(long long row, int seg_rows, long long seg_stride, long long ld) {
   if (seg_rows > 0) {

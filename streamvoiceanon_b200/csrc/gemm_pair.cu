@@ -328,10 +328,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
             // rope_qk_kernel's arithmetic on the pairs (2i, 2i + 1) of a head; table entry [pos][i] = (cos, sin)
             const float4 cs = __ldg(reinterpret_cast<const float4*>(rope + rope_row + ((n_base + j) & (HEAD_DIM - 1))));
             const float x0 = o.x, x1 = o.y, x2 = o.z, x3 = o.w;
-            o.x = x0 * cs.x - x1 * cs.y;
-            o.y = x1 * cs.x + x0 * cs.y;
-            o.z = x2 * cs.z - x3 * cs.w;
-            o.w = x3 * cs.z + x2 * cs.w;
+            rope_pair(x0, x1, cs.x, cs.y, o.x, o.y);
+            rope_pair(x2, x3, cs.z, cs.w, o.z, o.w);
           }
           *reinterpret_cast<float4*>(p.C + c_row + n_base + j) = o;
           if (pr.C_lo)

@@ -156,8 +156,7 @@ __global__ void rope_qk_kernel(float* __restrict__ qkv, const float* __restrict_
   const float c = table[((long long)pos * (HEAD_DIM / 2) + i) * 2 + 0];
   const float s = table[((long long)pos * (HEAD_DIM / 2) + i) * 2 + 1];
   const float x0 = p[0], x1 = p[1];
-  p[0] = x0 * c - x1 * s;
-  p[1] = x1 * c + x0 * s;
+  rope_pair(x0, x1, c, s, p[0], p[1]);
 }
 
 __global__ void silu_mul_kernel(const float* __restrict__ h, float* __restrict__ out, long long rows, int I,
