@@ -471,7 +471,8 @@ namespace {
 // One causal-conv input buffer [6 margin rows | T rows][C] per stream (stride seg), history hist [B][6][C].
 // mode 2: margin <- hist (the left context of this step), then hist <- newest 6 rows of [hist | rows];
 // mode 1: margin stays zero, hist <- newest 6 rows of [zeros | rows].  grid (ceil(C/128), B).
-__global__ void conv_hist_kernel(float* __restrict__ buf, long long seg, float* __restrict__ hist, int T, int C, int mode) {
+__global__ void conv_hist_kernel(float* __restrict__ buf, long long seg, float* __restrict__ hist, int T, int C, int mode,
+                                 float* __restrict__ ring, int ring_cap, long long abs_row0) {
   pdl_trigger();
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -490,13 +491,73 @@ __global__ void conv_hist_kernel(float* __restrict__ buf, long long seg, float* 
     const int src = T + r;                           // row index in [hist(6) | rows(T)]
     h[r * C + c] = src < 6 ? old[src] : b[(long long)src * C + c];
   }
+  if (ring) {                                        // ConvStackRings: the T rows at absolute rows abs_row0 ..
+    float* rg = ring + (long long)blockIdx.y * ring_cap * C;
+    for (int t = 0; t < T; ++t) rg[((abs_row0 + t) & (ring_cap - 1)) * C + c] = b[(long long)(6 + t) * C + c];
+  }
 }
 
-void launch_conv_hist(float* buf_margin, long long seg, float* hist, int B, int T, int C, int mode, cudaStream_t st) {
-  launch_pdl(conv_hist_kernel, dim3((C + 127) / 128, B), dim3(128), 0, st, buf_margin, seg, hist, T, C, mode);
+void launch_conv_hist(float* buf_margin, long long seg, float* hist, int B, int T, int C, int mode, cudaStream_t st,
+                      float* ring = nullptr, int ring_cap = 0, long long abs_row0 = 0) {
+  launch_pdl(conv_hist_kernel, dim3((C + 127) / 128, B), dim3(128), 0, st, buf_margin, seg, hist, T, C, mode, ring, ring_cap, abs_row0);
+  SV_LAUNCHED();
+}
+
+// rows [0, T) of B side-by-side buffers (stride seg) -> ring rows abs_row0 .. (no margin in front of src)
+__global__ void ring_append_kernel(const float* __restrict__ src, long long seg, int T, int C, float* __restrict__ ring, int ring_cap,
+                                   long long abs_row0) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* b = src + blockIdx.y * seg;
+  float* rg = ring + (long long)blockIdx.y * ring_cap * C;
+  for (int t = blockIdx.z; t < T; t += gridDim.z) rg[((abs_row0 + t) & (ring_cap - 1)) * C + c] = b[(long long)t * C + c];
+}
+void launch_ring_append(const float* src, long long seg, int B, int T, int C, float* ring, int ring_cap, long long abs_row0, cudaStream_t st) {
+  launch_pdl(ring_append_kernel, dim3((C + 127) / 128, B, T > 32 ? 32 : 1), dim3(128), 0, st, src, seg, T, C, ring, ring_cap, abs_row0);
+  SV_LAUNCHED();
+}
+// ring rows abs_row0 .. abs_row0 + n - 1 -> rows [0, n) at dst (B buffers, stride seg)
+__global__ void ring_fetch_kernel(const float* __restrict__ ring, int ring_cap, long long abs_row0, int n, float* __restrict__ dst,
+                                  long long seg, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* rg = ring + (long long)blockIdx.y * ring_cap * C;
+  float* d = dst + blockIdx.y * seg;
+  for (int t = 0; t < n; ++t) d[(long long)t * C + c] = rg[((abs_row0 + t) & (ring_cap - 1)) * C + c];
+}
+void launch_ring_fetch(const float* ring, int ring_cap, long long abs_row0, int n, float* dst, long long seg, int B, int C, cudaStream_t st) {
+  launch_pdl(ring_fetch_kernel, dim3((C + 127) / 128, B), dim3(128), 0, st, ring, ring_cap, abs_row0, n, dst, seg, C);
   SV_LAUNCHED();
 }
 }  // namespace
+
+void ConvStackRings::alloc(int n, int window_frames) {
+  int cap = 64;
+  while (cap < window_frames + 8) cap *= 2;
+  if (arena && B == n && frames_cap == cap) { frames = 0; filled_from = 0; return; }
+  release();
+  const int dims[4] = {128, 256, 384, 512};
+  const int depths[4] = {3, 3, 9, 3};
+  size_t per = (size_t)4 * cap * N_MELS;
+  for (int s = 0; s < 4; ++s) per += (size_t)4 * cap * dims[s] * depths[s];
+  per += (size_t)2 * cap * 512 + (size_t)cap * 512;           // blocks of the two down-sampled levels
+  per += (size_t)4 * cap * 512 + (size_t)2 * cap * 512;       // inputs of the two stride-2 convs
+  SV_CUDA(cudaMalloc(&arena, per * n * sizeof(float)));
+  float* p = arena;
+  mel = p; p += (size_t)n * 4 * cap * N_MELS;
+  int j = 0;
+  for (int s = 0; s < 4; ++s)
+    for (int d = 0; d < depths[s]; ++d) { blk[j++] = p; p += (size_t)n * 4 * cap * dims[s]; }
+  blk[j++] = p; p += (size_t)n * 2 * cap * 512;
+  blk[j++] = p; p += (size_t)n * cap * 512;
+  ds_in[0] = p; p += (size_t)n * 4 * cap * 512;
+  ds_in[1] = p; p += (size_t)n * 2 * cap * 512;
+  B = n; frames_cap = cap; frames = 0; filled_from = 0;
+}
 
 void ConvStackHist::alloc(int n) {
   if (arena && B == n) return;
@@ -573,7 +634,13 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     launch_gemm(p, st);
   }
   if (mel_dst) return;
-  if (hist_mode) launch_conv_hist(mel_buf, mel_seg, hist->mel, B, T, N_MELS, hist_mode, st);
+  // ConvStackRings (optional): this pass runs with true left context (or is the first full-window pass) -- its layer inputs are
+  // the steady-state rows the window-start pass of later chunks reads back
+  ConvStackRings* rg = (hist_mode && hist->rings && hist->rings->B == B) ? hist->rings : nullptr;
+  const long long abs_row0 = rg ? 4 * rg->frames : 0;
+  const int rcap = rg ? rg->frames_cap : 0;
+  if (rg) SV_CHECK(T % 4 == 0 && T <= 4 * rcap, "conv-stack rings: whole frames, at most the ring depth");
+  if (hist_mode) launch_conv_hist(mel_buf, mel_seg, hist->mel, B, T, N_MELS, hist_mode, st, rg ? rg->mel : nullptr, 4 * rcap, abs_row0);
   int blk_idx = 0;
 
   // 3. ConvNeXtEncoder (firefly.py:506-517)
@@ -606,7 +673,7 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     x = xn;
     x_seg = xs;
     for (auto& blk : w.blocks[s]) {
-      if (hist_mode) launch_conv_hist(xb, xs, hist->blk[blk_idx], B, T, C, hist_mode, st);
+      if (hist_mode) launch_conv_hist(xb, xs, hist->blk[blk_idx], B, T, C, hist_mode, st, rg ? rg->blk[blk_idx] : nullptr, 4 * rcap, abs_row0);
       ++blk_idx;
       convnext(blk, x, BT, tmp, hid, st, nullptr, segT, x_seg, 0);
     }
@@ -623,12 +690,14 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     float* db = ws.alloc_f(ds * B);
     if (!cont) launch_fill(db, (long long)MARG * 512, 0.f, st, B, ds);
     float* dn = db + MARG * 512;
+    if (rg) launch_ring_append(cur, cur_seg, B, rows, 512, rg->ds_in[i], (i == 0 ? 4 : 2) * rcap, abs_row0 >> i, st);
     GemmParams p;
     p.A = cur; p.W = w.down_w[i]; p.C = dn; p.bias = w.down_b[i]; p.M = B * r2; p.N = 512; p.K = 1024; p.lda = 512;
     p.a_row_step = 2; p.ldc = 512;
     p.seg_rows = B > 1 ? r2 : 0; p.a_seg = cur_seg; p.c_seg = ds;
     launch_gemm(p, st);
-    if (hist_mode) launch_conv_hist(db, ds, hist->blk[ConvStackHist::N_BLK - 2 + i], B, r2, 512, hist_mode, st);
+    if (hist_mode) launch_conv_hist(db, ds, hist->blk[ConvStackHist::N_BLK - 2 + i], B, r2, 512, hist_mode, st,
+                                    rg ? rg->blk[ConvStackHist::N_BLK - 2 + i] : nullptr, (i == 0 ? 2 : 1) * rcap, abs_row0 >> (i + 1));
     // the second block writes its result straight into the plain output buffer
     convnext(w.down_block[i], dn, B * r2, tmp, hid, st, i == 1 ? xt : nullptr, B > 1 ? r2 : 0, ds, (long long)r2 * 512);
     cur = dn;
@@ -636,6 +705,106 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
     rows = r2;
   }
   (void)S;
+}
+
+// The window-start span with only the rows the zero padding can reach.  The reference re-encodes the whole window with zero
+// left context (infer_arvc.py:495-508); a row of a causal layer that lies further from the window start than the padding's
+// reach is the same function of the same samples as in the pass that ran with true left context, so it is READ BACK from
+// ConvStackRings instead of recomputed.  Reach, in rows from the window start: log-mel 3 (STFT left pad), stem 9, ConvNeXt
+// block j (1..18) 9 + 6 j, first stride-2 conv ceil(117 / 2) = 59, its block 65, second stride-2 conv 33, its block 39 =
+// ENC_RF - 1 transformer inputs.  Block j therefore runs on 9 + 6 j rows per stream instead of the span's 164: its input is
+// the fresh output of block j - 1 (9 + 6 (j - 1) rows) followed by 6 ring rows.  45 % of the span's GEMM work remains.
+void Engine::enc_conv_stack_head(const ConvStackW& w, const float* wave, long long pitch, int B, const ConvStackRings& rg,
+                                 long long abs_frame0, float* xt_out, long long out_seg, cudaStream_t st) {
+  SV_CHECK(w.ready && rg.arena && rg.B == B && B > 1, "conv-stack rings not ready");
+  const int MARG = 6;
+  const int cap = rg.frames_cap;
+  const long long r1 = 4 * abs_frame0, r2a = 2 * abs_frame0, r4 = abs_frame0;      // absolute row of the window start per rate
+  // 1. log-mel: rows 0..2 fresh (zero left pad), rows 3..8 from the ring
+  const int MEL_ROWS = 9;
+  const long long mel_seg = (long long)(MARG + MEL_ROWS) * N_MELS;
+  float* mel_buf = ws.alloc_f(mel_seg * B);
+  launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st, B, mel_seg);
+  float* mel = mel_buf + MARG * N_MELS;
+  {
+    const long long n3 = 3 * HOP;
+    enc_conv_stack(w, &wave, &pitch, 1, B, n3, nullptr, st, nullptr, 0, mel, mel_seg);
+  }
+  launch_ring_fetch(rg.mel, 4 * cap, r1 + 3, 6, mel + 3 * N_MELS, mel_seg, B, N_MELS, st);
+  const int dims[4] = {128, 256, 384, 512};
+  const int ROWS_MAX = 9 + 6 * 18;               // 117
+  float* tmp = ws.alloc_f((long long)B * (ROWS_MAX + 1) * 512);
+  float* hid = ws.alloc_f((long long)B * (ROWS_MAX + 1) * 2048);
+  float* x = nullptr;
+  long long x_seg = 0;
+  int rows = MEL_ROWS;                           // fresh rows of the current layer input
+  int j = 0;                                     // blocks done
+  for (int s = 0; s < 4; ++s) {
+    const int C = dims[s];
+    const int rows_end = 9 + 6 * (j + (int)w.blocks[s].size());        // rows after the stage's last block
+    const long long xs = (long long)(MARG + rows_end) * C;
+    float* xb = ws.alloc_f(xs * B);
+    launch_fill(xb, (long long)MARG * C, 0.f, st, B, xs);
+    float* xn = xb + MARG * C;
+    if (s == 0) {
+      GemmParams p;   // stem on 9 rows
+      p.A = mel; p.W = w.stem_w; p.C = tmp; p.bias = w.stem_b; p.M = B * rows; p.N = C; p.K = 7 * N_MELS; p.lda = N_MELS;
+      p.ldc = C; p.tap_off[0] = -6;
+      p.seg_rows = rows; p.a_seg = mel_seg; p.c_seg = (long long)rows * C;
+      launch_gemm(p, st);
+      launch_layernorm(tmp, xn, w.stem_ln_w, w.stem_ln_b, B * rows, C, 1e-6f, st, rows, (long long)rows * C, xs);
+    } else {
+      const int Cp = dims[s - 1];
+      launch_layernorm(x, tmp, w.mid_ln_w[s - 1], w.mid_ln_b[s - 1], B * rows, Cp, 1e-6f, st, rows, x_seg, (long long)rows * Cp);
+      GemmParams p;
+      p.A = tmp; p.W = w.mid_w[s - 1]; p.C = xn; p.bias = w.mid_b[s - 1]; p.M = B * rows; p.N = C; p.K = Cp; p.lda = Cp; p.ldc = C;
+      p.seg_rows = rows; p.a_seg = (long long)rows * Cp; p.c_seg = xs;
+      launch_gemm(p, st);
+    }
+    x = xn;
+    x_seg = xs;
+    for (auto& blk : w.blocks[s]) {
+      // input of block j + 1: fresh rows [0, rows) + 6 steady-state rows
+      launch_ring_fetch(rg.blk[j], 4 * cap, r1 + rows, 6, x + (long long)rows * C, xs, B, C, st);
+      rows += 6;
+      convnext(blk, x, B * rows, tmp, hid, st, nullptr, rows, x_seg, 0);
+      ++j;
+    }
+  }
+  // rows == 117 fresh rows of the backbone output; the stride-2 conv pairs rows (2 i, 2 i + 1): row 117 from the ring
+  const int R0 = rows + 1;                       // 118
+  float* feat = ws.alloc_f((long long)B * R0 * 512);
+  launch_layernorm(x, feat, w.bb_norm_w, w.bb_norm_b, B * rows, 512, 1e-6f, st, rows, x_seg, (long long)R0 * 512);
+  launch_ring_fetch(rg.ds_in[0], 4 * cap, r1 + rows, 1, feat + (long long)rows * 512, (long long)R0 * 512, B, 512, st);
+  float* cur = feat;
+  long long cur_seg = (long long)R0 * 512;
+  int in_rows = R0;
+  for (int i = 0; i < 2; ++i) {
+    const int o = in_rows / 2;                   // 59, then 33
+    const int o_end = o + 6;                     // rows after the level's block: 65, 39
+    const bool last = i == 1;
+    // the block's output feeds the next stride-2 conv, which needs one more (ring) row behind it
+    const long long ds = (long long)(MARG + o_end + 1) * 512;
+    float* db = ws.alloc_f(ds * B);
+    launch_fill(db, (long long)MARG * 512, 0.f, st, B, ds);
+    float* dn = db + MARG * 512;
+    GemmParams p;
+    p.A = cur; p.W = w.down_w[i]; p.C = dn; p.bias = w.down_b[i]; p.M = B * o; p.N = 512; p.K = 1024; p.lda = 512;
+    p.a_row_step = 2; p.ldc = 512;
+    p.seg_rows = o; p.a_seg = cur_seg; p.c_seg = ds;
+    launch_gemm(p, st);
+    launch_ring_fetch(rg.blk[ConvStackHist::N_BLK - 2 + i], (i == 0 ? 2 : 1) * cap, (i == 0 ? r2a : r4) + o, 6, dn + (long long)o * 512, ds,
+                      B, 512, st);
+    convnext(w.down_block[i], dn, B * o_end, tmp, hid, st, last ? xt_out : nullptr, o_end, ds, out_seg);
+    if (!last) {
+      launch_ring_fetch(rg.ds_in[1], 2 * cap, r2a + o_end, 1, dn + (long long)o_end * 512, ds, B, 512, st);
+      cur = dn;
+      cur_seg = ds;
+      in_rows = o_end + 1;                       // 66
+    } else {
+      SV_CHECK(o_end == ENC_RF - 1, "window-start reach");
+    }
+  }
 }
 
 // enc_transformer_bsq: WindowLimitedTransformer (windowed_transformer.py:337-354) over S tokens per stream, positions
@@ -794,28 +963,43 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
   const bool use_hist = state.tail_hist_min_streams > 0 && B >= state.tail_hist_min_streams && S >= 2 * Ls + 8;
   if (!state.valid) state.hist_valid = false;
   float* xt_state = state.xt[state.cur ^ 1];
+  // Steady-state layer inputs of the last window (ConvStackRings): with them the window-start pass recomputes only the rows
+  // the zero padding reaches.  (Re)allocated empty when the stream count changes (cohort merge); usable once they cover the
+  // window again.
+  const bool want_rings = use_hist && state.use_rings;
+  state.hist.rings = want_rings ? &state.rings : nullptr;
+  if (!want_rings && state.rings.arena) state.rings.release();
   if (!incremental || (use_hist && !state.hist_valid)) {
     ws.ensure((enc_ws_floats(B, nw) + (size_t)B * S * ENC_DIM + (4u << 20)) * sizeof(float));
     ws.reset();
     if (use_hist) state.hist.alloc(B);
+    if (want_rings) state.rings.alloc(B, S);                  // empty; the pass below appends the window's 4 S rows per layer
     enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nw, xt_state, st, use_hist ? &state.hist : nullptr, use_hist ? 1 : 0);
+    if (want_rings) state.rings.frames += S;
     state.hist_valid = use_hist;
   } else if (use_hist) {
     const long long nh = (long long)Ls * SAMPLES_PER_FRAME, nt = (long long)c * SAMPLES_PER_FRAME;
     ws.ensure((enc_ws_floats(B, nh) + enc_ws_floats(B, nt) + enc_ws_floats(B, nw) / 3 + (size_t)(2 * B * Ls + B * S) * ENC_DIM +
                (4u << 20)) * sizeof(float));
     ws.reset();
+    if (want_rings && (state.rings.B != B || state.rings.frames_cap < S + 8)) state.rings.alloc(B, S);
+    // absolute frame number of the window start after this chunk; the rings serve it when they hold every frame from there on
+    // (>= 1: the rows of frame 0 of a first full-window pass saw that pass's own zero padding)
+    const long long start = want_rings ? state.rings.frames + c - S : -1;
+    const bool tri = want_rings && start >= 1;
     float* spans = ws.alloc_f((long long)2 * B * Ls * ENC_DIM);          // [head B x Ls | tail B x Ls (last c rows used)]
-    enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nh, spans, st);        // window start: zero left context
+    if (tri) enc_conv_stack_head(tok_cs, wave_ring, nw, B, state.rings, start, spans, (long long)Ls * ENC_DIM, st);
+    else enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nh, spans, st);  // window start: zero left context, whole span
     float* tail = ws.alloc_f((long long)B * c * ENC_DIM);
     const float* tsrc = wave_ring + (nw - nt);
     enc_conv_stack(tok_cs, &tsrc, &nw, 1, B, nt, tail, st, &state.hist, 2);
+    if (want_rings) state.rings.frames += c;
     // place the c new tokens where the assemble kernel expects the end of a tail span
     SV_CUDA(cudaMemcpy2DAsync(spans + ((long long)B * Ls + (Ls - c)) * ENC_DIM, (size_t)Ls * ENC_DIM * sizeof(float), tail,
                               (size_t)c * ENC_DIM * sizeof(float), (size_t)c * ENC_DIM * sizeof(float), B,
                               cudaMemcpyDeviceToDevice, st));
     launch_pdl(enc_assemble_kernel, dim3(S, B), dim3(128), 0, st, (const float*)spans, (const float*)state.xt[state.cur],
-               xt_state, B, S, Ls, ENC_RF, c);
+               xt_state, B, S, Ls, tri ? ENC_RF - 1 : ENC_RF, c);
     SV_LAUNCHED();
   } else {
     const long long ns = (long long)Ls * SAMPLES_PER_FRAME;

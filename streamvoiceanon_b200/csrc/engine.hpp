@@ -139,12 +139,32 @@ constexpr int ENC_RF = 40;
 
 // Causal-conv history of the tokenizer's conv stack for B streams side by side: the newest 6 rows of every buffer a
 // k = 7 causal conv reads (the mel rows in front of the stem, the input of each of the 18 + 2 ConvNeXt blocks).
+// Steady-state INPUT rows of every causal layer of the conv stack for the last `frames_cap` content frames of B streams (rings
+// indexed by absolute row number modulo the capacity; mel-rate layers hold 4 rows per frame, the two down-sampled levels 2 and
+// 1).  Filled by the passes that run with true left context (the per-layer-history pass of the newest frames, and the
+// first full-window pass); read by the window-start pass of Engine::enc_window_step, which then recomputes only the rows
+// the zero padding at the window start can reach (Engine::enc_conv_stack_head).
+struct ConvStackRings {
+  float* arena = nullptr;
+  float* mel = nullptr;                 // stem input          [B][4 F][160]
+  float* blk[20] = {};                  // ConvNeXt block inputs [B][4 F][C_j] (18 blocks), [B][2 F][512], [B][F][512]
+  float* ds_in[2] = {};                 // inputs of the two stride-2 convs [B][4 F][512], [B][2 F][512]
+  int B = 0, frames_cap = 0;            // F (power of two)
+  long long frames = 0;                 // content frames appended so far = absolute frame number of the next append
+  long long filled_from = 0;            // rings hold steady-state rows for absolute frames >= filled_from (contaminated rows of
+                                        // the first pass excluded by construction, see enc_conv_stack_head)
+  void alloc(int n_streams, int window_frames);
+  void release() { if (arena) cudaFree(arena); arena = nullptr; B = 0; frames_cap = 0; frames = 0; }
+  ~ConvStackRings() { release(); }
+};
+
 struct ConvStackHist {
   static constexpr int N_BLK = 20;
   float* arena = nullptr;
   float* mel = nullptr;                 // [B][6][160]
   float* blk[N_BLK] = {};               // [B][6][C_j]
   int B = 0;
+  ConvStackRings* rings = nullptr;      // optional: every pass that updates the history also appends its rows here
   void alloc(int n_streams);
   ~ConvStackHist() {
     if (arena) cudaFree(arena);
@@ -160,6 +180,12 @@ struct EncWindowState {
   bool enabled = true;
   ConvStackHist hist;                  // per-layer conv history of the newest frames (many-stream mode)
   bool hist_valid = false;
+  ConvStackRings rings;                // steady-state layer inputs of the last window (triangular window-start pass)
+  bool use_rings = default_use_rings();
+  static bool default_use_rings() {
+    const char* e = getenv("SVANON_ENC_HEAD_TRI");            // 0: the window-start span always goes through the whole conv stack
+    return !e || atoi(e) != 0;
+  }
   int tail_hist_min_streams = default_tail_hist_min();   // conv history for the newest frames from this many streams (0: never)
   static int default_tail_hist_min() {
     const char* e = getenv("SVANON_ENC_HIST_MIN_STREAMS");     // tuning knob
@@ -343,6 +369,11 @@ struct Engine {
   void voc_head(const float* z_dev /*[L][512]*/, int L, float* wave_dev /*[512 L]*/, cudaStream_t st);
   void voc_decode(const long long* codes_dev, long long ld, int T, float* wave_dev, cudaStream_t st);
   // out == nullptr: in place on x
+  // window-start span of B streams with only the rows the zero padding can reach recomputed (ConvStackRings): wave = the
+  // windows' first samples (stream b at wave + b * pitch), abs_frame0 = absolute frame number of the window start; writes the
+  // ENC_RF - 1 transformer inputs per stream that differ from the steady state to xt_out [B][ENC_RF - 1][512]
+  void enc_conv_stack_head(const ConvStackW& w, const float* wave, long long pitch, int B, const ConvStackRings& rings,
+                           long long abs_frame0, float* xt_out, long long out_seg, cudaStream_t st);
   void convnext(const ConvNextW& w, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out = nullptr,
                 int seg_rows = 0, long long x_seg = 0, long long out_seg = 0);
   // stateful (incremental) vocoder, voc_stream.cu

@@ -310,6 +310,45 @@ def test_batch_of_nine_default_windows(models, tape):
         s.close()
 
 
+def test_batch_long_run_window_start_rings(models, tape):
+    """300 chunks of 8 lock-step streams with the CLI-default windows: long enough for the rings of steady-state layer inputs
+    (ConvStackRings, 256 frames deep for a 128-frame window) to wrap, so the window-start pass that recomputes only the rows the
+    zero padding reaches (Engine::enc_conv_stack_head) reads rows written hundreds of chunks earlier.  Streams 0 and 7 against
+    the same streams run alone (whole-span recompute, reference semantics): content ids and codec ids bit-exact."""
+    from streamvoiceanon_b200 import BatchSession
+    _, tok, _ = models
+    n, n_chunks = 8, 300
+    cfg = dict(encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=1)
+
+    def inputs_of(b):
+        ref_content, ref_audio, style, timbre, _ = _stream_inputs(tok, 60 + b, 64 + 5 * b, 4, 1)
+        src = synth.synth_audio_44k(1500 + b, 14.5)[: n_chunks * 2048].view(n_chunks, 2048)
+        return ref_content, ref_audio, style, timbre, src
+    inputs = [inputs_of(b) for b in range(n)]
+    singles = {}
+    for b in (0, 7):
+        sess = _session(inputs[b], tape(9900 + b), 2)
+        sess.setup(**cfg)
+        for i in range(n_chunks):
+            sess.process_chunk(inputs[b][4][i].cuda())
+        singles[b] = sess.history()
+        sess.close()
+    sessions = [_session(inp, tape(9900 + b), 2) for b, inp in enumerate(inputs)]
+    batch = BatchSession(sessions)
+    batch.setup(**cfg)
+    for i in range(n_chunks):
+        batch.process_chunk(torch.stack([inp[4][i] for inp in inputs]).cuda())
+    for b in (0, 7):
+        src_hist, pred_hist = sessions[b].history()
+        assert src_hist.shape == singles[b][0].shape
+        bad = (src_hist != singles[b][0]).nonzero()
+        assert bad.numel() == 0, (b, "content ids differ first at", bad[:4].tolist())
+        assert torch.equal(pred_hist, singles[b][1]), b
+    batch.close()
+    for s in sessions:
+        s.close()
+
+
 def test_batch_of_128_default_windows(models, tape):
     """BASELINE config 4's per-GPU share: 128 streams in lock-step with the CLI-default windows, so that the loop runs on
     the GEMM tiles the headline stream count uses (M = 128 x 512 encoder rows: the 128 x 256 / 128 x 128 tensor-core tiles,
