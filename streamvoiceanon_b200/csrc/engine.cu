@@ -716,7 +716,7 @@ void Engine::enc_conv_stack(const ConvStackW& w, const float* const* src, const 
 // the fresh output of block j - 1 (9 + 6 (j - 1) rows) followed by 6 ring rows.  45 % of the span's GEMM work remains.
 void Engine::enc_conv_stack_head(const ConvStackW& w, const float* wave, long long pitch, int B, const ConvStackRings& rg,
                                  long long abs_frame0, float* xt_out, long long out_seg, cudaStream_t st) {
-  SV_CHECK(w.ready && rg.arena && rg.B == B && B > 1, "conv-stack rings not ready");
+  SV_CHECK(w.ready && rg.arena && rg.B == B && B >= 1, "conv-stack rings not ready");
   const int MARG = 6;
   const int cap = rg.frames_cap;
   const long long r1 = 4 * abs_frame0, r2a = 2 * abs_frame0, r4 = abs_frame0;      // absolute row of the window start per rate
