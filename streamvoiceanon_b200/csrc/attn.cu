@@ -3,6 +3,8 @@
 // and by the AR prompt prefill (dual_ar_stream.py:895-936 with the causal_mask rows of :333).
 // Keys/values are staged through shared memory in tiles of 32 keys shared by the 8 queries of a CTA;
 // softmax is the usual running max / running sum formulation in fp32.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace svanon {
@@ -195,6 +197,117 @@ attention_short_kernel(const float* __restrict__ q, long long q_ld, const float*
   }
 }
 
+// Many streams, short sequences (<= 128 positions): TWO THREADS PER QUERY, each owning 32 of the head's 64 dimensions (every
+// other 16-byte chunk, so that the pair's two addresses of a 128-bit shared-memory load are adjacent: one wavefront, no conflict).
+// attention_short_kernel gives every key a lane and pays one shared-memory load per FMA in the q . k phase plus shuffle
+// reductions per 32 keys (288 us per layer at 128 streams: 7.4 TFLOP/s).  Here the CTA of a (stream, head) stages K and V once
+// and a lane pair keeps its query (2 x 32 registers) and output accumulator (2 x 32): a key or value row is read with broadcast
+// 128-bit loads (two addresses per warp instruction) for 32 FMAs of each of the warp's 16 queries -- FMA-bound instead of
+// shared-memory-bound -- the two half dot products meet in one shuffle, and max / sum / rescale are thread-local (flash-style
+// over tiles of 16 keys).  Causal: warp w of 8 owns queries 16 w .. 16 w + 15 and walks exactly w + 1 key tiles; odd CTAs map
+// their warps in reverse so that the long warps of co-resident CTAs do not share a scheduler.  (A first version with one thread
+// per query needed 185 registers: 8 warps per SM, FMA pipe 20 % busy, 235 us -- profiles/r2zf_*.)
+constexpr int RQ_KT = 16;
+constexpr int RQ_THREADS = 2 * SMAXK;
+__global__ void __launch_bounds__(RQ_THREADS, 2)
+attention_rowq_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
+                      long long kv_head_stride, long long kv_row_stride, float* __restrict__ out, long long out_ld, int nq,
+                      int qpos0, int window, float* __restrict__ out_lo) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float att_smem[];
+  float (*Ks)[HEAD_DIM] = reinterpret_cast<float (*)[HEAD_DIM]>(att_smem);
+  float (*Vs)[HEAD_DIM] = reinterpret_cast<float (*)[HEAD_DIM]>(att_smem + SMAXK * HEAD_DIM);
+  constexpr int HD = HEAD_DIM / 2;
+  const int h = blockIdx.y, seg = blockIdx.x;
+  q += (long long)seg * nq * q_ld + h * HEAD_DIM;
+  k += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
+  v += (long long)seg * nq * kv_row_stride + (long long)h * kv_head_stride;
+  out += (long long)seg * nq * out_ld + h * HEAD_DIM;
+  if (out_lo) out_lo += (long long)seg * nq * out_ld + h * HEAD_DIM;
+  const int n_keys = qpos0 + nq;                              // keys 0 .. n_keys - 1 (<= SMAXK)
+  for (int i = threadIdx.x; i < n_keys * (HEAD_DIM / 4); i += RQ_THREADS) {
+    const int key = i / (HEAD_DIM / 4), c = (i % (HEAD_DIM / 4)) * 4;
+    *reinterpret_cast<float4*>(&Ks[key][c]) = __ldg(reinterpret_cast<const float4*>(k + (long long)key * kv_row_stride + c));
+    *reinterpret_cast<float4*>(&Vs[key][c]) = __ldg(reinterpret_cast<const float4*>(v + (long long)key * kv_row_stride + c));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wq = ((blockIdx.x + blockIdx.y) & 1) ? (RQ_THREADS / 32 - 1 - warp) : warp;
+  const int qi = wq * 16 + (lane >> 1);
+  const int d0 = (lane & 1) * 4;                              // this thread's dimensions: 8 i + d0 .. + 3, i = 0..7
+  const bool q_ok = qi < nq;
+  const int pos = qpos0 + (q_ok ? qi : 0);
+  const int lo = max(0, pos - window + 1);
+  float qr[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; d += 4) {
+    const float4 t = q_ok ? __ldg(reinterpret_cast<const float4*>(q + (long long)qi * q_ld + d0 + 2 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    qr[d] = t.x * 0.125f; qr[d + 1] = t.y * 0.125f; qr[d + 2] = t.z * 0.125f; qr[d + 3] = t.w * 0.125f;      // 1/sqrt(64)
+    acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  // the warp walks the key tiles any of its queries needs (warp-uniform bounds; every lane takes part in the shuffles)
+  const int w_hi = min(n_keys - 1, qpos0 + min(wq * 16 + 15, nq - 1));
+  const int w_lo = max(0, qpos0 + wq * 16 - window + 1);
+  for (int kt = (w_lo / RQ_KT) * RQ_KT; kt <= w_hi; kt += RQ_KT) {
+    float sc[RQ_KT];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < RQ_KT; ++j) {
+      const int kp = kt + j;
+      float s0 = 0.f, s1 = 0.f;
+      if (kp < n_keys) {                                      // warp-uniform
+#pragma unroll
+        for (int d = 0; d < HD; d += 8) {
+          const float4 a = *reinterpret_cast<const float4*>(&Ks[kp][d0 + 2 * d]);
+          const float4 b = *reinterpret_cast<const float4*>(&Ks[kp][d0 + 2 * d + 8]);
+          s0 = fmaf(qr[d], a.x, s0); s0 = fmaf(qr[d + 1], a.y, s0); s0 = fmaf(qr[d + 2], a.z, s0); s0 = fmaf(qr[d + 3], a.w, s0);
+          s1 = fmaf(qr[d + 4], b.x, s1); s1 = fmaf(qr[d + 5], b.y, s1); s1 = fmaf(qr[d + 6], b.z, s1); s1 = fmaf(qr[d + 7], b.w, s1);
+        }
+      }
+      float sp = s0 + s1;
+      // both lanes of the pair end up with the same bits: (low half) + (high half)
+      const float other = __shfl_xor_sync(0xffffffffu, sp, 1);
+      sp = (lane & 1) ? other + sp : sp + other;
+      const bool valid = q_ok && kp >= lo && kp <= pos;
+      sc[j] = valid ? sp : -INFINITY;
+      tmax = fmaxf(tmax, sc[j]);
+    }
+    if (tmax == -INFINITY) continue;                          // pair-uniform; no shuffles below
+    const float m_new = fmaxf(m, tmax);
+    const float corr = expf(m - m_new);
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] *= corr;
+#pragma unroll
+    for (int j = 0; j < RQ_KT; ++j) {
+      const int kp = kt + j;
+      const float pj = expf(sc[j] - m_new);                   // 0 for masked keys
+      l += pj;
+      if (kp < n_keys) {
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+          const float4 vv = *reinterpret_cast<const float4*>(&Vs[kp][d0 + 2 * d]);
+          acc[d] = fmaf(pj, vv.x, acc[d]); acc[d + 1] = fmaf(pj, vv.y, acc[d + 1]);
+          acc[d + 2] = fmaf(pj, vv.z, acc[d + 2]); acc[d + 3] = fmaf(pj, vv.w, acc[d + 3]);
+        }
+      }
+    }
+    m = m_new;
+  }
+  if (!q_ok) return;
+  const float inv = 1.f / l;
+  float* op = out + (long long)qi * out_ld + d0;
+  float* lp = out_lo ? out_lo + (long long)qi * out_ld + d0 : nullptr;
+#pragma unroll
+  for (int d = 0; d < HD; d += 4) {
+    const float4 o = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+    *reinterpret_cast<float4*>(op + 2 * d) = o;
+    if (lp) *reinterpret_cast<float4*>(lp + 2 * d) = make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
+  }
+}
+
 // The last c queries of each segment only; thread t owns key t of the segment (nq <= 128).
 __global__ void __launch_bounds__(ATT_TAIL_MAX_KEYS)
 attention_tail_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ k, const float* __restrict__ v,
@@ -288,7 +401,23 @@ void launch_attention(const float* q, long long q_ld, const float* k, const floa
       SV_CUDA(cudaFuncSetAttribute(attention_short_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
       configured = true;
     }
-    if (nseg >= 8)
+    static const bool rowq = [] {
+      const char* e = getenv("SVANON_ATTN_ROWQ");          // 0: many streams keep the lane-per-key kernel (A/B)
+      return !e || atoi(e) != 0;
+    }();
+    const bool al16 = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0 &&
+                      q_ld % 4 == 0 && out_ld % 4 == 0 && kv_head_stride % 4 == 0;
+    if (nseg >= 8 && rowq && al16) {
+      constexpr size_t SMEM_RQ = (size_t)SMAXK * 2 * HEAD_DIM * sizeof(float);
+      static bool configured_rq = false;
+      if (!configured_rq) {
+        SV_CUDA(cudaFuncSetAttribute(attention_rowq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_RQ));
+        configured_rq = true;
+      }
+      launch_pdl(attention_rowq_kernel, dim3(nseg, heads), dim3(RQ_THREADS), SMEM_RQ, st, q, q_ld, k, v, kv_head_stride, kv_row_stride, out,
+                 out_ld, nq, qpos0, window, out_lo);
+    } else if (nseg >= 8)
       launch_pdl(attention_short_kernel<8>, dim3((nq + SQW * 8 - 1) / (SQW * 8) * nseg, heads), dim3(SQW * 32), SMEM, st, q, q_ld,
                  k, v, kv_head_stride, kv_row_stride, out, out_ld, nq, qpos0, window, out_lo);
     else
