@@ -1,6 +1,8 @@
 // Direct causal conv for the two thinnest HiFi-GAN levels (C = 32 and C = 16 channels, ResBlock1 convs of
 // firefly.py:149-219): out[m][co] = bias[co] + sum_tap sum_ci W[tap][co][ci] * silu(x[m + off_tap][ci]) (+ residual).
 //
+// (Input rows are staged with a pitch of C + 4 floats: the 4 / 8 rows a warp reads in one instruction then fall in different
+// banks -- with pitch C every input load was a 4-way / 8-way conflict; V 6.5 -> 5.8 ms at 128 streams, profiles/r2zi_*.)
 // As GEMMs these problems have N = K-per-tap = 16 or 32: far too thin for the tensor cores and latency-bound in the
 // generic cp.async pipeline (11 taps = 11 dependent pipeline steps, ~24 us per launch for 35 MFLOP).  Here a CTA owns
 // TR consecutive output rows of one problem: it stages the SiLU'd input rows (with their causal halo) and the whole
@@ -31,7 +33,9 @@ __global__ void __launch_bounds__(TR * C / 8) conv_small_kernel(const ConvBatch 
   const int ktaps = p.taps > 1 ? p.taps : p.K / C;          // dilation 1: one "tap" of k*C overlapping columns
   const int halo = -p.tap_off[0];                           // the oldest row any tap reaches
   float* w_s = smem;                                        // [ktaps][Q (ci quad)][C (co)][4 (ci)]
-  float* x_s = smem + ktaps * C * C;                        // [halo + TR][C], SiLU applied
+  constexpr int XP = C + 4;                                 // row pitch of x_s: the 4 (C = 32) / 8 (C = 16) rows a warp reads at once
+                                                            // must not share banks (pitch C: 4-way / 8-way conflicts on every load)
+  float* x_s = smem + ktaps * C * C;                        // [halo + TR][XP], SiLU applied
   const int tid = threadIdx.x;
   pdl_trigger();
   // weights: global layout dilation 1: W[co][tap*C + ci]; dilated: W[(tap*C + co)*C + ci]
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(TR * C / 8) conv_small_kernel(const ConvBatch 
     const int q = i % Q, r = i / Q;
     float4 v = *reinterpret_cast<const float4*>(a0 + (long long)(r - halo) * p.lda + q * 4);
     v.x = silu_acc(v.x); v.y = silu_acc(v.y); v.z = silu_acc(v.z); v.w = silu_acc(v.w);
-    *reinterpret_cast<float4*>(x_s + r * C + q * 4) = v;
+    *reinterpret_cast<float4*>(x_s + r * XP + q * 4) = v;
   }
   __syncthreads();
   const int cq = tid % Q, rp = tid / Q;                      // rows m0 + 2*rp, +1; output channels cq + Q*j
@@ -57,12 +61,12 @@ __global__ void __launch_bounds__(TR * C / 8) conv_small_kernel(const ConvBatch 
   const int first_off = p.taps > 1 ? 0 : p.tap_off[0];
   for (int tap = 0; tap < ktaps; ++tap) {
     const int off = p.taps > 1 ? p.tap_off[tap] : first_off + tap;
-    const float* xr = x_s + (halo + 2 * rp + off) * C;
+    const float* xr = x_s + (halo + 2 * rp + off) * XP;
     const float* wt = w_s + tap * Q * C * 4 + cq * 4;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       const float4 x0 = *reinterpret_cast<const float4*>(xr + q * 4);
-      const float4 x1 = *reinterpret_cast<const float4*>(xr + C + q * 4);
+      const float4 x1 = *reinterpret_cast<const float4*>(xr + XP + q * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 wv = *reinterpret_cast<const float4*>(wt + (q * C + Q * j) * 4);
@@ -104,7 +108,11 @@ bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st) {
   const GemmParams& p0 = ps[0];
   const int C = p0.N;
   if (C != 16 && C != 32) return false;
-  const int TR = C == 16 ? 128 : 64;
+  static const bool big_tiles = [] {
+    const char* e = getenv("SVANON_CONV_SMALL_BIG");        // 0: 64 / 128 rows per CTA also at many streams (A/B).  Default: twice the
+    return !e || atoi(e) != 0;                              // rows from M = 8192 on -- the weight tensor is staged half as often
+  }();
+  const int TR = (C == 16 ? 128 : 64) * ((big_tiles && p0.M >= 8192) ? 2 : 1);
   static const long long max_m = [] {
     const char* e = getenv("SVANON_CONV_SMALL_MAX_M");      // tuning knob: largest M that takes this kernel (above it the
     return e ? atoll(e) : (1LL << 40);                       // tensor-core kernel's thin 128 x N tile takes over: measured slower)
@@ -124,13 +132,13 @@ bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st) {
     for (int t = 0; t < (p.taps > 1 ? p.taps : 1); ++t)
       if (p.tap_off[t] > 0 || p.tap_off[t] < -halo) return false;
     if (p.taps == 1 && p.tap_off[0] + kt - 1 > 0) return false;
-    smem = std::max(smem, ((size_t)kt * C * C + (size_t)(halo + TR) * C) * sizeof(float));
+    smem = std::max(smem, ((size_t)kt * C * C + (size_t)(halo + TR) * (C + 4)) * sizeof(float));
     b.p[i] = p;
   }
   for (int i = count; i < 3; ++i) b.p[i] = ps[0];
   if (smem > 96 * 1024) return false;
-  if (C == 16) launch_cfg<16, 128>(b, count, smem, st);
-  else launch_cfg<32, 64>(b, count, smem, st);
+  if (C == 16) { if (TR == 256) launch_cfg<16, 256>(b, count, smem, st); else launch_cfg<16, 128>(b, count, smem, st); }
+  else { if (TR == 128) launch_cfg<32, 128>(b, count, smem, st); else launch_cfg<32, 64>(b, count, smem, st); }
   return true;
 }
 
