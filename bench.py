@@ -78,7 +78,7 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=10, help="chunks of the CPU baseline sample (main arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--concurrent", default="128,160,192,208,224", help="stream-count ladder of the config-4 leg: the first entry runs on "
+    ap.add_argument("--concurrent", default="128,192,224,240", help="stream-count ladder of the config-4 leg: the first entry runs on "
                     "every GPU, the rest (N=1 only) are tried in order while p99 stays under the frame period ('' = skip)")
     ap.add_argument("--concurrent-chunks", type=int, default=720, help="chunks per stream of the config-4 leg")
     ap.add_argument("--stateful", default="256,384,512", help="stream-count ladder of the stateful-encoder leg (N=1 only; '' = skip)")
@@ -553,8 +553,13 @@ def gemm_roofline(peaks):
 # last layer runs for the kept token only (-0.67); a single stream sends two 41-frame spans through the conv stack, >= 8
 # lock-step streams one span + 0.2 GFLOP for the newest frames from conv history.  Stage V: 2.647 GFLOP per frame
 # (incremental vocoder).  The reference computes 29.0 (E) and 169.4 (V) GFLOP for the same chunk.
+# From 8 lock-step streams the window-start span recomputes only the rows the zero padding reaches ("rings of
+# steady-state layer inputs"): 3 log-mel rows of DFT (0.026), stem on 9 rows, ConvNeXt block j on 9 + 6 j rows (3.13 over the 18
+# blocks), stage transitions 0.05, the two down-sampled levels 0.53 = 3.74 GFLOP instead of the span's 41 * 0.2055 = 8.43
+# (SVANON_ENC_HEAD_TRI=0 restores the whole span, and this accounting).
 E_GFLOP_SINGLE = 82 * 0.2055 + 6.98 - 0.67
-E_GFLOP_MANY = 41 * 0.2055 + 0.2 + 6.98 - 0.67
+E_HEAD_SPAN_GFLOP = 41 * 0.2055 if os.environ.get("SVANON_ENC_HEAD_TRI", "1") == "0" else 3.74
+E_GFLOP_MANY = E_HEAD_SPAN_GFLOP + 0.2 + 6.98 - 0.67
 V_GFLOP = 2.647
 
 
