@@ -533,6 +533,54 @@ void launch_ring_fetch(const float* ring, int ring_cap, long long abs_row0, int 
   launch_pdl(ring_fetch_kernel, dim3((C + 127) / 128, B), dim3(128), 0, st, ring, ring_cap, abs_row0, n, dst, seg, C);
   SV_LAUNCHED();
 }
+// One causal layer's input of the MERGED pass (Engine::enc_conv_stack_merged), in place, per stream:
+//   before: [head_old valid rows | ... | n_new rows of the newest frames at new_src]
+//   after:  [head_old | 6 ring rows (steady-state rows behind the head) | 6 history rows (the newest frames' left context) | n_new]
+// and, like conv_hist_kernel in mode 2, history <- newest 6 rows of [history | new rows], ring <- new rows.  A thread owns one
+// channel of one stream and reads the new rows before it writes anything, so the overlapping ranges are safe.
+constexpr int RELAYOUT_MAX_NEW = 16;
+__global__ void relayout_kernel(float* __restrict__ x, long long seg, int C, int head_old, int new_src, int n_new,
+                                float* __restrict__ ring, int ring_cap, long long abs_head, long long abs_new, float* __restrict__ hist) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float* b = x + blockIdx.y * seg;
+  float* rg = ring + (long long)blockIdx.y * ring_cap * C;
+  float* h = hist + (long long)blockIdx.y * 6 * C;
+  float nw[RELAYOUT_MAX_NEW], old[6];
+#pragma unroll
+  for (int i = 0; i < RELAYOUT_MAX_NEW; ++i) nw[i] = i < n_new ? b[(long long)(new_src + i) * C + c] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) old[i] = h[i * C + c];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b[(long long)(head_old + i) * C + c] = rg[((abs_head + i) & (ring_cap - 1)) * C + c];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b[(long long)(head_old + 6 + i) * C + c] = old[i];
+#pragma unroll
+  for (int i = 0; i < RELAYOUT_MAX_NEW; ++i)
+    if (i < n_new) {
+      b[(long long)(head_old + 12 + i) * C + c] = nw[i];
+      rg[((abs_new + i) & (ring_cap - 1)) * C + c] = nw[i];
+    }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int src = n_new + r;                        // row index in [history(6) | new(n_new)]
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) if (src == i) v = old[i];
+#pragma unroll
+    for (int i = 0; i < RELAYOUT_MAX_NEW; ++i) if (src == 6 + i) v = nw[i];
+    h[r * C + c] = v;
+  }
+}
+void launch_relayout(float* x, long long seg, int B, int C, int head_old, int new_src, int n_new, float* ring, int ring_cap,
+                     long long abs_head, long long abs_new, float* hist, cudaStream_t st) {
+  SV_CHECK(n_new >= 1 && n_new <= RELAYOUT_MAX_NEW, "merged conv pass: at most 4 content frames per chunk");
+  launch_pdl(relayout_kernel, dim3((C + 127) / 128, B), dim3(128), 0, st, x, seg, C, head_old, new_src, n_new, ring, ring_cap, abs_head,
+             abs_new, hist);
+  SV_LAUNCHED();
+}
 }  // namespace
 
 void ConvStackRings::alloc(int n, int window_frames) {
@@ -807,6 +855,140 @@ void Engine::enc_conv_stack_head(const ConvStackW& w, const float* wave, long lo
   }
 }
 
+// The window-start pass (enc_conv_stack_head) and the per-layer-history pass of the c newest frames (enc_conv_stack, hist_mode 2) in
+// the SAME launches.  Separately the second is ~80 latency-bound launches on 4 c rows per stream; here every layer's input is
+// [6 zero rows | head rows | 6 ring rows | 6 history rows | 4 c new rows] per stream: the causal convs of the new rows see their true
+// left context (the history rows), the rows computed at the history positions are junk nobody reads, and one small kernel per
+// layer (relayout_kernel) moves the new rows behind the grown head, fetches ring and history rows and appends the new rows to
+// both.  The stride-2 convs read row pairs, so their inputs are re-packed as [head rows | new rows] with even counts.
+// xt_head [B][ENC_RF - 1][512] with stream pitch head_seg, xt_tail [B][c][512] plain.
+void Engine::enc_conv_stack_merged(const ConvStackW& w, const float* wave_ring, long long pitch, long long nw, int B, int c,
+                                   ConvStackHist& hist, ConvStackRings& rg, long long abs_frame0, float* xt_head, long long head_seg,
+                                   float* xt_tail, cudaStream_t st) {
+  SV_CHECK(w.ready && rg.arena && rg.B == B && hist.B == B && c >= 1 && 4 * c <= RELAYOUT_MAX_NEW, "merged conv pass: state not ready");
+  const int MARG = 6;
+  const int cap = rg.frames_cap;
+  const long long r1 = 4 * abs_frame0, r2a = 2 * abs_frame0, r4 = abs_frame0;      // absolute row of the window start per rate
+  const long long a1 = 4 * rg.frames, a2 = 2 * rg.frames, a4 = rg.frames;          // absolute row of the first new row per rate
+  const int n1 = 4 * c, n2 = 2 * c, n4 = c;
+  // 1. log-mel: [6 zero | 3 fresh head rows | 6 ring | 6 history | n1 new]
+  const int MEL_ROWS = 9 + 6 + n1;
+  const long long mel_seg = (long long)(MARG + MEL_ROWS) * N_MELS;
+  float* mel_buf = ws.alloc_f(mel_seg * B);
+  launch_fill(mel_buf, (long long)MARG * N_MELS, 0.f, st, B, mel_seg);
+  float* mel = mel_buf + MARG * N_MELS;
+  {
+    const long long n3 = 3 * HOP;
+    enc_conv_stack(w, &wave_ring, &pitch, 1, B, n3, nullptr, st, nullptr, 0, mel, mel_seg);
+    // newest frames with their true left context (the 1536 samples in front), straight to their final rows
+    const long long nt = (long long)c * SAMPLES_PER_FRAME;
+    const float* tsrc = wave_ring + (nw - nt);
+    ConvStackRings* keep = hist.rings;
+    hist.rings = nullptr;                                    // the front only: history and rings are updated by relayout below
+    enc_conv_stack(w, &tsrc, &pitch, 1, B, nt, nullptr, st, &hist, 2, mel + 15 * N_MELS, mel_seg);
+    hist.rings = keep;
+  }
+  launch_relayout(mel, mel_seg, B, N_MELS, 3, 15, n1, rg.mel, 4 * cap, r1 + 3, a1, hist.mel, st);
+  const int dims[4] = {128, 256, 384, 512};
+  const int TAILR = 6 + n1;                      // history + new rows behind the head rows
+  const int ROWS_MAX = 117 + TAILR;
+  float* tmp = ws.alloc_f((long long)B * (ROWS_MAX + 1) * 512);
+  float* hid = ws.alloc_f((long long)B * (ROWS_MAX + 1) * 2048);
+  float* x = nullptr;
+  long long x_seg = 0;
+  int rows = 9;                                  // head rows of the current layer input
+  int j = 0;                                     // blocks done
+  for (int s = 0; s < 4; ++s) {
+    const int C = dims[s];
+    const int rows_end = 9 + 6 * (j + (int)w.blocks[s].size());
+    const long long xs = (long long)(MARG + rows_end + TAILR) * C;
+    float* xb = ws.alloc_f(xs * B);
+    launch_fill(xb, (long long)MARG * C, 0.f, st, B, xs);
+    float* xn = xb + MARG * C;
+    const int seg_rows = rows + TAILR;           // every row of the layout goes through the point-wise layers
+    if (s == 0) {
+      GemmParams p;
+      p.A = mel; p.W = w.stem_w; p.C = tmp; p.bias = w.stem_b; p.M = B * seg_rows; p.N = C; p.K = 7 * N_MELS; p.lda = N_MELS;
+      p.ldc = C; p.tap_off[0] = -6;
+      p.seg_rows = seg_rows; p.a_seg = mel_seg; p.c_seg = (long long)seg_rows * C;
+      launch_gemm(p, st);
+      launch_layernorm(tmp, xn, w.stem_ln_w, w.stem_ln_b, B * seg_rows, C, 1e-6f, st, seg_rows, (long long)seg_rows * C, xs);
+    } else {
+      const int Cp = dims[s - 1];
+      launch_layernorm(x, tmp, w.mid_ln_w[s - 1], w.mid_ln_b[s - 1], B * seg_rows, Cp, 1e-6f, st, seg_rows, x_seg, (long long)seg_rows * Cp);
+      GemmParams p;
+      p.A = tmp; p.W = w.mid_w[s - 1]; p.C = xn; p.bias = w.mid_b[s - 1]; p.M = B * seg_rows; p.N = C; p.K = Cp; p.lda = Cp; p.ldc = C;
+      p.seg_rows = seg_rows; p.a_seg = (long long)seg_rows * Cp; p.c_seg = xs;
+      launch_gemm(p, st);
+    }
+    x = xn;
+    x_seg = xs;
+    for (auto& blk : w.blocks[s]) {
+      // [rows | 6 junk | n1 new at rows + 6] -> [rows + 6 | 6 history | n1 new]
+      launch_relayout(x, xs, B, C, rows, rows + 6, n1, rg.blk[j], 4 * cap, r1 + rows, a1, hist.blk[j], st);
+      rows += 6;
+      convnext(blk, x, B * (rows + TAILR), tmp, hid, st, nullptr, rows + TAILR, x_seg, 0);
+      ++j;
+    }
+  }
+  // backbone output: head rows [0, 117), new rows at 117 + 6.  Input of the first stride-2 conv: [117 head | ring row | n1 new]
+  const int R0 = rows + 1;                       // 118
+  const long long f_seg = (long long)(R0 + n1) * 512;
+  float* feat = ws.alloc_f(f_seg * B);
+  launch_layernorm(x, feat, w.bb_norm_w, w.bb_norm_b, B * rows, 512, 1e-6f, st, rows, x_seg, f_seg);
+  launch_layernorm(x + (long long)(rows + 6) * 512, feat + (long long)R0 * 512, w.bb_norm_w, w.bb_norm_b, B * n1, 512, 1e-6f, st, n1, x_seg,
+                   f_seg);
+  launch_ring_fetch(rg.ds_in[0], 4 * cap, r1 + rows, 1, feat + (long long)rows * 512, f_seg, B, 512, st);
+  launch_ring_append(feat + (long long)R0 * 512, f_seg, B, n1, 512, rg.ds_in[0], 4 * cap, a1, st);
+  const float* cur = feat;
+  long long cur_seg = f_seg;
+  int in_head = R0;                              // head rows of the stride-2 conv's input (even)
+  int n_in = n1;
+  for (int i = 0; i < 2; ++i) {
+    const int o = in_head / 2, n_out = n_in / 2; // head rows 59 / 33, new rows 2 c / c
+    const int o_end = o + 6;                     // 65, 39
+    const bool last = i == 1;
+    const long long ds = (long long)(MARG + o_end + 6 + n_out) * 512;
+    float* db = ws.alloc_f(ds * B);
+    launch_fill(db, (long long)MARG * 512, 0.f, st, B, ds);
+    float* dn = db + MARG * 512;
+    GemmParams p;
+    p.A = cur; p.W = w.down_w[i]; p.C = dn; p.bias = w.down_b[i]; p.M = B * (o + n_out); p.N = 512; p.K = 1024; p.lda = 512;
+    p.a_row_step = 2; p.ldc = 512;
+    p.seg_rows = o + n_out; p.a_seg = cur_seg; p.c_seg = ds;
+    launch_gemm(p, st);
+    // [o head | n_out new at o] -> [o + 6 | 6 history | n_out new]
+    const int bi = ConvStackHist::N_BLK - 2 + i;
+    launch_relayout(dn, ds, B, 512, o, o, n_out, rg.blk[bi], (i == 0 ? 2 : 1) * cap, (i == 0 ? r2a : r4) + o, i == 0 ? a2 : a4, hist.blk[bi], st);
+    const int seg_rows = o_end + 6 + n_out;
+    if (!last) {
+      convnext(w.down_block[i], dn, B * seg_rows, tmp, hid, st, nullptr, seg_rows, ds, 0);
+      // input of the second stride-2 conv: [65 head | ring row | n_out new]
+      const long long g_seg = (long long)(o_end + 1 + n_out) * 512;
+      float* g = ws.alloc_f(g_seg * B);
+      SV_CUDA(cudaMemcpy2DAsync(g, (size_t)g_seg * sizeof(float), dn, (size_t)ds * sizeof(float), (size_t)o_end * 512 * sizeof(float), B,
+                                cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpy2DAsync(g + (long long)(o_end + 1) * 512, (size_t)g_seg * sizeof(float), dn + (long long)(o_end + 6) * 512,
+                                (size_t)ds * sizeof(float), (size_t)n_out * 512 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+      launch_ring_fetch(rg.ds_in[1], 2 * cap, r2a + o_end, 1, g + (long long)o_end * 512, g_seg, B, 512, st);
+      launch_ring_append(g + (long long)(o_end + 1) * 512, g_seg, B, n_out, 512, rg.ds_in[1], 2 * cap, a2, st);
+      cur = g;
+      cur_seg = g_seg;
+      in_head = o_end + 1;                       // 66
+      n_in = n_out;
+    } else {
+      SV_CHECK(o_end == ENC_RF - 1 && n_out == c, "window-start reach");
+      const long long o_seg = (long long)seg_rows * 512;
+      float* outb = ws.alloc_f(o_seg * B);
+      convnext(w.down_block[i], dn, B * seg_rows, tmp, hid, st, outb, seg_rows, ds, o_seg);
+      SV_CUDA(cudaMemcpy2DAsync(xt_head, (size_t)head_seg * sizeof(float), outb, (size_t)o_seg * sizeof(float),
+                                (size_t)o_end * 512 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+      SV_CUDA(cudaMemcpy2DAsync(xt_tail, (size_t)c * 512 * sizeof(float), outb + (long long)(o_end + 6) * 512, (size_t)o_seg * sizeof(float),
+                                (size_t)c * 512 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+}
+
 // enc_transformer_bsq: WindowLimitedTransformer (windowed_transformer.py:337-354) over S tokens per stream, positions
 // 0..S-1 in every stream, in place on xt [B][S][512]; then the 13-bit BSQ ids (bsq.py:330-369).
 // keep_last = c > 0: the caller reads the ids of the last c tokens of every stream only (the streaming loop,
@@ -988,11 +1170,19 @@ void Engine::enc_window_step(EncWindowState& state, const float* wave_ring, int 
     const long long start = want_rings ? state.rings.frames + c - S : -1;
     const bool tri = want_rings && start >= 1;
     float* spans = ws.alloc_f((long long)2 * B * Ls * ENC_DIM);          // [head B x Ls | tail B x Ls (last c rows used)]
-    if (tri) enc_conv_stack_head(tok_cs, wave_ring, nw, B, state.rings, start, spans, (long long)Ls * ENC_DIM, st);
-    else enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nh, spans, st);  // window start: zero left context, whole span
     float* tail = ws.alloc_f((long long)B * c * ENC_DIM);
-    const float* tsrc = wave_ring + (nw - nt);
-    enc_conv_stack(tok_cs, &tsrc, &nw, 1, B, nt, tail, st, &state.hist, 2);
+    static const bool merged = [] {
+      const char* e = getenv("SVANON_ENC_MERGED");           // 0: window-start pass and newest-frames pass as separate launches
+      return !e || atoi(e) != 0;
+    }();
+    if (tri && merged && 4 * c <= 16) {
+      enc_conv_stack_merged(tok_cs, wave_ring, nw, nw, B, c, state.hist, state.rings, start, spans, (long long)Ls * ENC_DIM, tail, st);
+    } else {
+      if (tri) enc_conv_stack_head(tok_cs, wave_ring, nw, B, state.rings, start, spans, (long long)Ls * ENC_DIM, st);
+      else enc_conv_stack(tok_cs, &wave_ring, &nw, 1, B, nh, spans, st);  // window start: zero left context, whole span
+      const float* tsrc = wave_ring + (nw - nt);
+      enc_conv_stack(tok_cs, &tsrc, &nw, 1, B, nt, tail, st, &state.hist, 2);
+    }
     if (want_rings) state.rings.frames += c;
     // place the c new tokens where the assemble kernel expects the end of a tail span
     SV_CUDA(cudaMemcpy2DAsync(spans + ((long long)B * Ls + (Ls - c)) * ENC_DIM, (size_t)Ls * ENC_DIM * sizeof(float), tail,

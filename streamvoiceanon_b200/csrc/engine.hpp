@@ -374,6 +374,10 @@ struct Engine {
   // ENC_RF - 1 transformer inputs per stream that differ from the steady state to xt_out [B][ENC_RF - 1][512]
   void enc_conv_stack_head(const ConvStackW& w, const float* wave, long long pitch, int B, const ConvStackRings& rings,
                            long long abs_frame0, float* xt_out, long long out_seg, cudaStream_t st);
+  // the window-start pass and the per-layer-history pass of the c newest frames in the same launches (engine.cu)
+  void enc_conv_stack_merged(const ConvStackW& w, const float* wave_ring, long long pitch, long long nw, int B, int c, ConvStackHist& hist,
+                             ConvStackRings& rings, long long abs_frame0, float* xt_head, long long head_seg, float* xt_tail,
+                             cudaStream_t st);
   void convnext(const ConvNextW& w, float* x, int rows, float* tmp, float* hid, cudaStream_t st, float* out = nullptr,
                 int seg_rows = 0, long long x_seg = 0, long long out_seg = 0);
   // stateful (incremental) vocoder, voc_stream.cu

@@ -310,19 +310,21 @@ def test_batch_of_nine_default_windows(models, tape):
         s.close()
 
 
-def test_batch_long_run_window_start_rings(models, tape):
-    """300 chunks of 8 lock-step streams with the CLI-default windows: long enough for the rings of steady-state layer inputs
+@pytest.mark.parametrize("chunk,n_chunks", [(1, 300), (2, 150)])
+def test_batch_long_run_window_start_rings(models, tape, chunk, n_chunks):
+    """300 frames (as one- or two-frame chunks) of 8 lock-step streams with the CLI-default windows: long enough for the rings of steady-state layer inputs
     (ConvStackRings, 256 frames deep for a 128-frame window) to wrap, so the window-start pass that recomputes only the rows the
-    zero padding reaches (Engine::enc_conv_stack_head) reads rows written hundreds of chunks earlier.  Streams 0 and 7 against
+    zero padding reaches (Engine::enc_conv_stack_head; merged with the pass of the newest frames: enc_conv_stack_merged) reads
+    rows written hundreds of chunks earlier.  Streams 0 and 7 against
     the same streams run alone (whole-span recompute, reference semantics): content ids and codec ids bit-exact."""
     from streamvoiceanon_b200 import BatchSession
     _, tok, _ = models
-    n, n_chunks = 8, 300
-    cfg = dict(encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=1)
+    n = 8
+    cfg = dict(encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=chunk)
 
     def inputs_of(b):
         ref_content, ref_audio, style, timbre, _ = _stream_inputs(tok, 60 + b, 64 + 5 * b, 4, 1)
-        src = synth.synth_audio_44k(1500 + b, 14.5)[: n_chunks * 2048].view(n_chunks, 2048)
+        src = synth.synth_audio_44k(1500 + b, 14.5)[: n_chunks * chunk * 2048].view(n_chunks, chunk * 2048)
         return ref_content, ref_audio, style, timbre, src
     inputs = [inputs_of(b) for b in range(n)]
     singles = {}
