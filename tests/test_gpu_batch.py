@@ -246,6 +246,52 @@ def test_stream_pool_merges_cohorts(models, tape, enc_mode):
         s.close()
 
 
+def test_stream_pool_merge_then_long_run(models, tape):
+    """Two cohorts of 8 streams (CLI-default windows), the second arriving 5 chunks late and folded into the first after its
+    warm-up: the merged batch starts with EMPTY rings of steady-state layer inputs (ConvStackRings), runs the whole-span
+    window-start pass until the rings cover the 128-frame window again (chunk ~136), and the ring-based pass after that.
+    200 chunks; one stream of each cohort against the same stream run alone: ids bit-exact."""
+    from streamvoiceanon_b200 import BatchSession
+    from streamvoiceanon_b200.server import StreamPool
+    _, tok, _ = models
+    n_chunks, late, delay = 200, 5, 2
+    cfg = dict(encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=1)
+
+    def inputs_of(b):
+        ref_content, ref_audio, style, timbre, _ = _stream_inputs(tok, 80 + b, 60 + 3 * b, 4, 1)
+        src = synth.synth_audio_44k(1700 + b, 10.0)[: n_chunks * 2048].view(n_chunks, 2048)
+        return ref_content, ref_audio, style, timbre, src
+    inputs = [inputs_of(b) for b in range(16)]
+    check = (3, 12)
+    singles = {}
+    for b in check:
+        sess = _session(inputs[b], tape(6600 + b), delay)
+        sess.setup(**cfg)
+        for i in range(n_chunks):
+            sess.process_chunk(inputs[b][4][i].cuda())
+        singles[b] = sess.history()
+        sess.close()
+    sessions = [_session(inp, tape(6600 + b), delay) for b, inp in enumerate(inputs)]
+    pool = StreamPool(batch_factory=BatchSession, **cfg)
+    join = {b: (0 if b < 8 else late) for b in range(16)}
+    sizes = []
+    for step in range(n_chunks + late):
+        for b, at in join.items():
+            if at == step:
+                pool.add(b, sessions[b])
+        chunks = {b: inputs[b][4][step - join[b]].cuda() for b in range(16) if b in pool and step - join[b] < n_chunks}
+        pool.step(chunks)
+        sizes.append(pool.cohort_sizes())
+    assert [8, 8] in sizes and [16] in sizes and pool.merges == 1
+    for b in check:
+        src_hist, pred_hist = sessions[b].history()
+        assert torch.equal(src_hist[: singles[b][0].numel()], singles[b][0]), b
+        assert torch.equal(pred_hist[:, : singles[b][1].shape[1]], singles[b][1]), b
+    pool.close()
+    for s in sessions:
+        s.close()
+
+
 @pytest.mark.parametrize("enc_mode", [1, 2])
 def test_batch_loop_vs_reference_fixture(models, gold, tape, enc_mode):
     """Stream 0 of a 2-stream batch (many-stream decode kernels forced) reproduces the UNMODIFIED reference's

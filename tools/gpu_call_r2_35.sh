@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round 2, call 35: evidence at the final state of the round: GPU suite, bench line (config-4 ladder 128 / 192 / 224 / 240), reference
+# arm, launch lists (single-stream chunk, 128-stream step), ncu --set full of the dominant kernels, memcheck of the many-stream tests.
+set -u
+O=gpurun_out/r2zo
+mkdir -p $O
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.txt 2>&1; tail -4 $O/pytest_gpu.txt
+( time timeout 1200 python bench.py ) > $O/bench.json 2> $O/bench.err; tail -c 300 $O/bench.err
+( time timeout 600 python bench.py --impl reference ) > $O/bench_reference.json 2> $O/bench_reference.err
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/single_launches.csv python tools/profile_single.py 2 > $O/ncu_single.log 2>&1
+timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/batch128_launches.csv python tools/profile_batch.py 128 > $O/ncu_batch.log 2>&1
+timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -c 8 -o $O/gemm_tc_single python tools/profile_single.py 1 > $O/ncu_gemm.log 2>&1
+timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:chain_kernel -c 1 -o $O/chain_single python tools/profile_single.py 1 > $O/ncu_chain.log 2>&1
+timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:ar_decode_staged -c 1 -o $O/ar_decode_single python tools/profile_single.py 1 > $O/ncu_ar.log 2>&1
+timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_pair_kernel -c 6 -o $O/gemm_pair_batch128 python tools/profile_batch.py 128 > $O/ncu_pair.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_batch.py -x -q -k "nine or many_rows or merges" > $O/sanitizer_memcheck_batch.txt 2>&1; echo "memcheck rc=$?"; tail -4 $O/sanitizer_memcheck_batch.txt
+python - <<'P'
+import json
+try:
+    d=json.loads(open('gpurun_out/r2zo/bench.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','stage_ms_median','gpu_launches') if k in d})
+    print('e2e', d.get('e2e'))
+    print('roofline', {k:v for k,v in d.get('roofline',{}).items() if k in ('achieved','frac','share_of_step')})
+    r=d.get('roofline_gemm_many_streams',{}); print('gemm', {k:r.get(k) for k in ('launch_us','with_split_pass_us','single_cta_us','frac')})
+    c=d.get('concurrent_streams',{}); print('config4', {k:c.get(k) for k in ('streams_per_gpu','frames_per_s_all_gpus','ms_per_step_mean_max_over_ranks','ms_per_step_p99_max_over_ranks','max_streams_per_gpu_p99_lt_frame_period')})
+    for l in c.get('ladder',[]): print('  ladder', {k:l.get(k) for k in ('streams','ms_per_step_mean','ms_per_step_p99','stage_ms')})
+    c5=d.get('config5',{}); print('config5', {k:c5.get(k) for k in ('ms_per_step_mean','ms_per_step_p99','rtf_p99')})
+    for s in d.get('stage_compute',[]): print('stage_compute', s['streams'], {k:(round(s[k]['achieved_tflops'],1), round(s[k]['frac'],3)) for k in ('E','V')})
+    r=json.loads(open('gpurun_out/r2zo/bench_reference.json').read().strip().splitlines()[-1]); print('reference', r['value'], r['ms_per_step'])
+except Exception as e:
+    print('parse failed', e)
+P
+ls -la $O | head -30
