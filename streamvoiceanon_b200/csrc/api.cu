@@ -548,8 +548,12 @@ int svanon_debug_gemm_taps(svanon_engine* e, const float* A, int a_rows, int lda
     p.A = A + (long long)a_row0 * lda; p.W = W; p.bias = bias; p.C = C + c_col0;
     p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.a_row_step = a_row_step; p.taps = taps;
     for (int t = 0; t < taps; ++t) p.tap_off[t] = tap_off[t];
-    p.w_static = false;
+    p.w_static = g_debug_gemm_static != 0;     // svanon_debug_gemm_weights_static: W treated like an engine weight
     launch_gemm(p, (cudaStream_t)stream);
+    if (g_debug_gemm_static == 1) {
+      SV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+      gemm_forget_weights(p.W);
+    }
   });
 }
 

@@ -283,6 +283,7 @@ bool launch_gemm_pipe(const GemmParams* ps, int count, cudaStream_t st);   // ge
 bool launch_gemm_tc(const GemmParams* ps, int count, cudaStream_t st);     // gemm_tc.cu
 bool launch_conv_small(const GemmParams* ps, int count, cudaStream_t st);  // conv_small.cu
 bool launch_gemm_pair(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pair.cu
+bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st);   // gemm_pair.cu: convs with taps
 bool g_use_conv_small = true;
 
 // ---- measurement aid (svanon_gemm_timing): every GEMM launch bracketed by CUDA events on its own stream, summed per
@@ -404,6 +405,11 @@ static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t s
     return;
   }
   if (g_gemm_use_tc && launch_gemm_pair(ps, count, st)) {       // tcgen05 3xTF32 on CTA pairs, operands by tensor-map TMA (M >= 4096)
+    *backend = GEMM_BACKEND_TC;
+    SV_LAUNCHED();
+    return;
+  }
+  if (g_gemm_use_tc && launch_gemm_pair_taps(ps, count, st)) {  // the same kernel for causal convs with taps / SiLU input (M >= 4096)
     *backend = GEMM_BACKEND_TC;
     SV_LAUNCHED();
     return;

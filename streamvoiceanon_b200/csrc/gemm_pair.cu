@@ -49,9 +49,14 @@ struct alignas(64) PairProblem {
   CUtensorMap b2_hi, b2_lo;             // SwiGLU form: the second weight matrix (boxes of 64 rows, like b_hi / b_lo in that form)
   GemmParams p;
   float* C_lo;                          // optional: lo term of the result, [M][N] compact
+  // conv form (TAPS instantiation): A maps are 3-D (channel, row in segment incl. `reach` rows of left context, segment); K-slab s
+  // belongs to tap s / spt, whose A rows start toff[tap] (>= 0, relative to the first context row) and whose weights start
+  // b_col_tap * tap columns / b_row_tap * tap rows into the 2-D weight map
+  int k_slabs, spt, a_seg_rows, a_box_rows, b_col_tap, b_row_tap;
+  int toff[MAX_TAPS];
 };
 struct PairArgs {
-  PairProblem prob[2];
+  PairProblem prob[3];
   int count, tiles_m, tiles_n, k_slabs;
   int dual;                             // SwiGLU form (GemmParams::W2): see the kernel
 };
@@ -117,6 +122,11 @@ __device__ __forceinline__ void tma_load_2d_pair(unsigned dst, const CUtensorMap
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void ptmem_ld16(unsigned taddr, float (&v)[16]) {
   unsigned r[16];
   asm volatile(
@@ -129,7 +139,7 @@ __device__ __forceinline__ void ptmem_ld16(unsigned taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int BN>
+template <int BN, bool TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_constant__ PairArgs args) {
   constexpr int BH = BN / 2;                                  // B rows (output columns) this CTA stages
   constexpr unsigned A_BYTES = PBM * 128u, B_BYTES = BH * 128u;
@@ -177,7 +187,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
       const PairProblem& pr = args.prob[z];
       // SwiGLU form: a pair tile is 128 OUTPUT columns; this CTA's B half = 64 rows of W | the same 64 rows of W2
       const int row0 = mt * 256 + (int)rank * PBM, n0 = args.dual ? nt * (BN / 2) + (int)rank * (BH / 2) : nt * BN + (int)rank * BH;
-      for (int s = 0; s < k_slabs; ++s) {
+      const int n_slabs = TAPS ? pr.k_slabs : k_slabs;
+      // conv form: this CTA's 128 rows are 128 / a_box_rows runs of rows inside one segment each
+      const int seg0 = TAPS ? row0 / pr.a_seg_rows : 0, r_in0 = TAPS ? row0 - seg0 * pr.a_seg_rows : 0;
+      for (int s = 0; s < n_slabs; ++s) {
         pmbar_wait(smem_u32p(&empty_bar[stage]), parity);
         if (pelect_one()) {
           const unsigned dst = smem_base + stage * STAGE_BYTES;
@@ -185,13 +198,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
           const unsigned bar = mapa_u32(bar_local, 0);
           if (rank == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local), "r"(2u * STAGE_BYTES) : "memory");
-          tma_load_2d_pair(dst, &pr.a_hi, s * PK, row0, bar);
-          tma_load_2d_pair(dst + A_BYTES, &pr.a_lo, s * PK, row0, bar);
-          tma_load_2d_pair(dst + 2u * A_BYTES, &pr.b_hi, s * PK, n0, bar);
-          tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES, &pr.b_lo, s * PK, n0, bar);
-          if (args.dual) {
-            tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES / 2u, &pr.b2_hi, s * PK, n0, bar);
-            tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES + B_BYTES / 2u, &pr.b2_lo, s * PK, n0, bar);
+          if constexpr (TAPS) {
+            const int tap = s / pr.spt, kc = (s - tap * pr.spt) * PK;
+            const int roff = pr.toff[tap];
+            int seg = seg0, r_in = r_in0;
+            for (int sub = 0; sub < PBM; sub += pr.a_box_rows) {
+              tma_load_3d_pair(dst + (unsigned)sub * 128u, &pr.a_hi, kc, r_in + roff, seg, bar);
+              tma_load_3d_pair(dst + A_BYTES + (unsigned)sub * 128u, &pr.a_lo, kc, r_in + roff, seg, bar);
+              r_in += pr.a_box_rows;
+              if (r_in >= pr.a_seg_rows) { r_in = 0; ++seg; }
+            }
+            tma_load_2d_pair(dst + 2u * A_BYTES, &pr.b_hi, kc + tap * pr.b_col_tap, n0 + tap * pr.b_row_tap, bar);
+            tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES, &pr.b_lo, kc + tap * pr.b_col_tap, n0 + tap * pr.b_row_tap, bar);
+          } else {
+            tma_load_2d_pair(dst, &pr.a_hi, s * PK, row0, bar);
+            tma_load_2d_pair(dst + A_BYTES, &pr.a_lo, s * PK, row0, bar);
+            tma_load_2d_pair(dst + 2u * A_BYTES, &pr.b_hi, s * PK, n0, bar);
+            tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES, &pr.b_lo, s * PK, n0, bar);
+            if (args.dual) {
+              tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES / 2u, &pr.b2_hi, s * PK, n0, bar);
+              tma_load_2d_pair(dst + 2u * A_BYTES + B_BYTES + B_BYTES / 2u, &pr.b2_lo, s * PK, n0, bar);
+            }
           }
         }
         __syncwarp();
@@ -215,7 +242,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
         pmbar_wait(smem_u32p(&acc_empty[acc]), (((unsigned)it >> 1) & 1u) ^ 1u);     // both CTAs drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned d_tmem = tmem_u + acc * BN;
-        for (int s = 0; s < k_slabs; ++s) {
+        const int n_slabs = TAPS ? args.prob[tile / tiles_per_problem].k_slabs : k_slabs;
+        for (int s = 0; s < n_slabs; ++s) {
           pmbar_wait(smem_u32p(&full_bar[stage]), parity);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (pelect_one()) {
@@ -463,13 +491,54 @@ std::unordered_map<cudaStream_t, ScratchSet>& scratch_registry() {      // per s
   return r;
 }
 
-template <int BN>
+// [nseg][rows][C] fp32 compact -> boxes of 32 floats x box_rows rows of one segment, 128-byte swizzle, zero fill out of bounds
+CUtensorMap tensor_map_3d(const float* base, int C, int rows, int nseg, int box_rows) {
+  CUtensorMap m;
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)nseg};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)rows * C * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)PK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed");
+  return m;
+}
+
+// conv form: the GEMM's A rows with their left context, SiLU applied if the GEMM asks for it (the prologue gemm_tc.cu applies in its
+// producers, once per TAP there), as hi (the value itself) and lo (its TF32 remainder) arrays [nseg][reach + rows][C] compact
+__global__ void conv_operand_kernel(const float* __restrict__ A, long long lda, long long a_seg, int reach, int rows, int C, int silu,
+                                    float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_trigger();
+  pdl_wait();
+  const int c4 = C >> 2;
+  const long long per_seg = (long long)(reach + rows) * c4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_seg) return;
+  const int r = (int)(i / c4), c = (int)(i - (long long)r * c4) * 4;
+  const long long b = blockIdx.y;
+  float4 v = *reinterpret_cast<const float4*>(A + b * a_seg + (long long)(r - reach) * lda + c);
+  if (silu) {
+    v.x = __fdividef(v.x, 1.f + __expf(-v.x)); v.y = __fdividef(v.y, 1.f + __expf(-v.y));
+    v.z = __fdividef(v.z, 1.f + __expf(-v.z)); v.w = __fdividef(v.w, 1.f + __expf(-v.w));
+  }
+  const long long o = (b * (reach + rows) + r) * C + c;
+  *reinterpret_cast<float4*>(hi + o) = v;
+  *reinterpret_cast<float4*>(lo + o) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+}
+struct ConvScratch { Scratch hi[3], lo[3]; };
+std::unordered_map<cudaStream_t, ConvScratch>& conv_scratch_registry() {
+  static std::unordered_map<cudaStream_t, ConvScratch> r;
+  return r;
+}
+
+template <int BN, bool TAPS = false>
 void launch_pair_cfg(const PairArgs& a, cudaStream_t st) {
   constexpr int STAGES = BN == 256 ? 3 : 4;
   constexpr size_t SMEM = (size_t)STAGES * (2 * PBM * 128 + 2 * (BN / 2) * 128) + 1024;
   static bool configured = false;
   if (!configured) {
-    SV_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    SV_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<BN, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
   static const int n_sm = [] {
@@ -490,7 +559,7 @@ void launch_pair_cfg(const PairArgs& a, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN>, a));
+  SV_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN, TAPS>, a));
 }
 
 }  // namespace
@@ -509,6 +578,12 @@ void gemm_pair_release() {
       if (kv.second.hi[i].p) cudaFree(kv.second.hi[i].p);
     }
   scratch_registry().clear();
+  for (auto& kv : conv_scratch_registry())
+    for (int i = 0; i < 3; ++i) {
+      if (kv.second.hi[i].p) cudaFree(kv.second.hi[i].p);
+      if (kv.second.lo[i].p) cudaFree(kv.second.lo[i].p);
+    }
+  conv_scratch_registry().clear();
 }
 void gemm_pair_forget_weights(const float* W) {
   auto& reg = lo_registry();
@@ -617,9 +692,120 @@ bool launch_gemm_pair(const GemmParams* ps, int count, cudaStream_t st) {
       pr.b2_lo = tensor_map_2d(w2->lo, p.N, p.K, p.K, b_box);
     }
   }
-  if (count == 1) a.prob[1] = a.prob[0];
+  for (int i = count; i < 3; ++i) a.prob[i] = a.prob[0];
   if (BN == 256) launch_pair_cfg<256>(a, st);
   else launch_pair_cfg<128>(a, st);
+  ++g_gemm_pair_launches;
+  return true;
+}
+
+// ---- conv form: causal convs with left context as GEMMs over taps (the ResBlock convs of the wide HiFi-GAN levels at many streams:
+// C = N = 128 / 256 channels, 3 / 7 / 11 taps, up to three problems per launch, SiLU on the input; the transposed up-sampling convs).
+// One pass turns each distinct input into SiLU'd hi / lo arrays (gemm_tc.cu applies the SiLU in its producers, once per tap), the
+// kernel then takes tap t's rows through a 3-D tensor map at row offset tap_off[t]; same term and K order as gemm_tc.cu: same bits.
+bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
+  static const bool on = [] {
+    const char* e = getenv("SVANON_GEMM_PAIR_TAPS");     // 0: convs with taps stay on the single-CTA kernel
+    return !e || atoi(e) != 0;
+  }();
+  static const int min_m = [] {
+    const char* e = getenv("SVANON_GEMM_PAIR_MIN_M");
+    return e ? atoi(e) : 4096;
+  }();
+  static const int min_tiles = [] {
+    const char* e = getenv("SVANON_GEMM_PAIR_MIN_TILES");
+    return e ? atoi(e) : 48;
+  }();
+  if (!on || pair_mode() == 0 || g_gemm_half || !g_gemm_pair_allowed || count < 1 || count > 3) return false;
+  const GemmParams& p0 = ps[0];
+  if (p0.M < min_m || (p0.N % 128 != 0 && p0.N != 64)) return false;
+  const int C = (int)p0.lda;                                   // channels per tap = A row length
+  if (C % PK != 0 || C < PK) return false;
+  const int seg_rows = p0.seg_rows;
+  if (seg_rows > 0 && !(seg_rows % PBM == 0 || (PBM % seg_rows == 0 && seg_rows % 8 == 0))) return false;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  int ktaps[3], reach[3];
+  bool any_taps = false;
+  for (int i = 0; i < count; ++i) {
+    const GemmParams& p = ps[i];
+    if (p.M != p0.M || p.N != p0.N || p.lda != C || p.seg_rows != seg_rows) return false;
+    if (p.a_row_step != 1 || p.accumulate || !p.w_static || p.W2 || p.rope_table || p.Alo || p.Clo) return false;
+    if (p.prologue != PRO_NONE && p.prologue != PRO_SILU) return false;
+    if (p.taps > 1 ? p.K != C : (p.K % C != 0)) return false;
+    ktaps[i] = p.taps > 1 ? p.taps : p.K / C;
+    if (ktaps[i] < 1 || ktaps[i] > MAX_TAPS) return false;
+    int lo_off = 0;
+    for (int t = 0; t < ktaps[i]; ++t) {
+      const int off = p.taps > 1 ? p.tap_off[t] : p.tap_off[0] + t;
+      if (off > 0) return false;
+      lo_off = std::min(lo_off, off);
+    }
+    reach[i] = -lo_off;
+    if (ktaps[i] > 1 || p.prologue == PRO_SILU || reach[i] > 0) any_taps = true;
+    if (p.ldc % 4 != 0 || (p.residual && p.ldr % 4 != 0) || (seg_rows > 0 && (p.a_seg % 4 != 0 || p.c_seg % 4 != 0 || (p.residual && p.r_seg % 4 != 0))))
+      return false;
+    if (!al16(p.A) || !al16(p.W) || !al16(p.C) || !al16(p.bias) || !al16(p.gamma) || !al16(p.residual)) return false;
+  }
+  if (!any_taps) return false;                                 // plain GEMMs take the plain path
+  const int BN = (p0.N % 256 == 0) ? 256 : (p0.N % 128 == 0 ? 128 : 64);
+  PairArgs a;
+  a.count = count;
+  a.dual = 0;
+  a.tiles_m = (p0.M + 255) / 256;
+  a.tiles_n = p0.N / BN;
+  a.k_slabs = 0;
+  if ((long long)a.tiles_m * a.tiles_n * count < min_tiles) return false;
+  if (capturing(st)) return false;
+  const int nseg = seg_rows > 0 ? p0.M / seg_rows : 1;
+  const int rows = seg_rows > 0 ? seg_rows : p0.M;             // rows per segment
+  if (seg_rows > 0 && p0.M % seg_rows != 0) return false;
+  ConvScratch& cs = conv_scratch_registry()[st];
+  for (int i = 0; i < count; ++i) {
+    const GemmParams& p = ps[i];
+    PairProblem& pr = a.prob[i];
+    pr.p = p;
+    pr.C_lo = nullptr;
+    // weights: dilated convs [k][N][C] (tap = N rows further), dilation 1 [N][k C] (tap = C columns further)
+    const int w_rows = p.taps > 1 ? ktaps[i] * p.N : p.N, w_cols = p.taps > 1 ? C : ktaps[i] * C;
+    const LoCopy* w = weight_lo(p.W, w_rows, w_cols, false, st);
+    if (!w) return false;
+    pr.b_hi = tensor_map_2d(p.W, w_rows, w_cols, w_cols, BN / 2);
+    pr.b_lo = tensor_map_2d(w->lo, w_rows, w_cols, w_cols, BN / 2);
+    pr.b2_hi = pr.b_hi;
+    pr.b2_lo = pr.b_lo;
+    pr.b_row_tap = p.taps > 1 ? p.N : 0;
+    pr.b_col_tap = p.taps > 1 ? 0 : C;
+    pr.spt = C / PK;
+    pr.k_slabs = ktaps[i] * pr.spt;
+    pr.a_seg_rows = seg_rows > 0 ? seg_rows : (p0.M + 255) / 256 * 256;
+    pr.a_box_rows = std::min(PBM, rows >= PBM ? PBM : rows);
+    for (int t = 0; t < MAX_TAPS; ++t) pr.toff[t] = 0;
+    for (int t = 0; t < ktaps[i]; ++t) pr.toff[t] = (p.taps > 1 ? p.tap_off[t] : p.tap_off[0] + t) + reach[i];
+    // operand arrays: shared with an earlier problem of the launch that reads the same rows the same way
+    int same = -1;
+    for (int j = 0; j < i; ++j)
+      if (ps[j].A == p.A && ps[j].a_seg == p.a_seg && reach[j] == reach[i] && ps[j].prologue == p.prologue) { same = j; break; }
+    if (same >= 0) {
+      pr.a_hi = a.prob[same].a_hi;
+      pr.a_lo = a.prob[same].a_lo;
+      continue;
+    }
+    const size_t n = (size_t)nseg * (reach[i] + rows) * C;
+    float* hi = scratch_floats(cs.hi[i], n, st);
+    float* lo = scratch_floats(cs.lo[i], n, st);
+    if (!hi || !lo) return false;
+    const long long per_seg = (long long)(reach[i] + rows) * (C / 4);
+    launch_pdl(conv_operand_kernel, dim3((unsigned)((per_seg + 255) / 256), nseg), dim3(256), 0, st, p.A, p.lda,
+               seg_rows > 0 ? p.a_seg : 0LL, reach[i], rows, C, p.prologue == PRO_SILU ? 1 : 0, hi, lo);
+    SV_LAUNCHED();
+    pr.a_hi = tensor_map_3d(hi, C, reach[i] + rows, nseg, pr.a_box_rows);
+    pr.a_lo = tensor_map_3d(lo, C, reach[i] + rows, nseg, pr.a_box_rows);
+  }
+  for (int i = count; i < 3; ++i) a.prob[i] = a.prob[0];
+  for (int i = 0; i < 3; ++i) a.prob[i].p.prologue = PRO_NONE;  // applied by conv_operand_kernel
+  if (BN == 256) launch_pair_cfg<256, true>(a, st);
+  else if (BN == 128) launch_pair_cfg<128, true>(a, st);
+  else launch_pair_cfg<64, true>(a, st);                       // 64-channel level: L2-bound (40 KB of operands per 0.28 us slab)
   ++g_gemm_pair_launches;
   return true;
 }

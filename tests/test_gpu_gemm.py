@@ -216,3 +216,47 @@ def test_pair_gemm_fused_epilogues(form):
     scale = max(1.0, float(exact.abs().max()))
     assert float((outs[1].double() - exact).abs().max()) < 3e-5 * scale
     assert torch.equal(outs[1], outs[0]), int((outs[1] != outs[0]).sum())
+
+
+@pytest.mark.parametrize("M,N,C,offs,k1", [(12544, 128, 128, (-10, -5, 0), 0), (12500, 256, 256, (-30, -25, -20, -15, -10, -5, 0), 0),
+                                           (12544, 256, 256, (-2,), 3), (12544, 128, 64, (-6,), 7), (16384, 64, 64, (-20, -10, 0), 0)])
+def test_pair_gemm_taps_bitwise(M, N, C, offs, k1):
+    """The conv form of the pair kernel (causal convs as GEMMs over taps: 3-D tensor maps over the input rows with their left
+    context, tap t at row offset tap_off[t]; k1 > 0: the dilation-1 form, one "tap" of k1 overlapping rows) against the single-CTA
+    kernel: the same bits, and fp64-close."""
+    import ctypes as C_
+    from streamvoiceanon_b200 import _lib
+    from streamvoiceanon_b200.engine import Engine, ptr
+    eng, lib = Engine.get(0), _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(31)
+    taps = len(offs)
+    K = k1 * C if k1 else C
+    margin = -min(offs)
+    rows = margin + M + (k1 if k1 else 0) + 1
+    A = torch.randn(rows, C, device="cuda", generator=g)
+    W = torch.randn(taps, N, K, device="cuda", generator=g) / (taps * K) ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    arr = (C_.c_int * taps)(*offs)
+    outs = {}
+    _lib.check(lib.svanon_debug_gemm_weights_static(1))
+    try:
+        for mode in (0, 1):
+            out = torch.full((M, N), float("nan"), device="cuda")
+            _lib.check(lib.svanon_set_gemm_pair(mode))
+            n0 = lib.svanon_gemm_pair_launches()
+            _lib.check(lib.svanon_debug_gemm_taps(eng.handle, ptr(A), rows - 1, C, margin, 1, ptr(W), taps, arr, ptr(b), ptr(out), N, 0,
+                                                  M, N, K, None))
+            torch.cuda.synchronize()
+            assert lib.svanon_gemm_pair_launches() - n0 == mode
+            outs[mode] = out
+    finally:
+        _lib.check(lib.svanon_set_gemm_pair(-1))
+        _lib.check(lib.svanon_debug_gemm_weights_static(0))
+    flat = A.reshape(-1).double()
+    ref = b.double().repeat(M, 1)
+    for t, off in enumerate(offs):
+        starts = (margin + torch.arange(M, device="cuda") + off) * C
+        idx = starts[:, None] + torch.arange(K, device="cuda")[None]
+        ref += flat[idx] @ W[t].double().T
+    assert float((outs[1].double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    assert torch.equal(outs[1], outs[0]), int((outs[1] != outs[0]).sum())
