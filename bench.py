@@ -78,7 +78,7 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=10, help="chunks of the CPU baseline sample (main arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--concurrent", default="128,192,224,240", help="stream-count ladder of the config-4 leg: the first entry runs on "
+    ap.add_argument("--concurrent", default="128,192,240,256", help="stream-count ladder of the config-4 leg: the first entry runs on "
                     "every GPU, the rest (N=1 only) are tried in order while p99 stays under the frame period ('' = skip)")
     ap.add_argument("--concurrent-chunks", type=int, default=720, help="chunks per stream of the config-4 leg")
     ap.add_argument("--stateful", default="256,384,512", help="stream-count ladder of the stateful-encoder leg (N=1 only; '' = skip)")
