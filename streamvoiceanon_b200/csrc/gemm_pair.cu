@@ -21,8 +21,11 @@
 //   * persistent: a pair walks tiles t = pair, pair + 74, ...; accumulator (t & 1) of 2 x BN TMEM columns, so the 16 epilogue
 //     warps of both CTAs drain tile i (tcgen05.ld -> bias / GELU / layer-scale / residual -> global, optionally the lo term
 //     of the result for the next GEMM) while the tensor cores run tile i + 1.
-// Restrictions (everything else stays on gemm_tc.cu): taps == 1, unit row step, contiguous A rows, N % 128 == 0, K % 32 == 0,
-// no SiLU prologue, no accumulate, engine-owned weights, parity mode.
+//   * conv form (TAPS instantiation, launch_gemm_pair_taps at the end of this file): causal convs as GEMMs over taps -- the A maps
+//     are 3-D (channel, row in segment incl. left context, segment) over SiLU'd hi / lo operand arrays made by one pass per
+//     distinct input, tap t's rows are taken at row offset tap_off[t], its weights at a row / column offset of the weight map.
+// Restrictions (everything else stays on gemm_tc.cu): unit row step, N % 128 == 0 (conv form: also 64), K (per tap) % 32 == 0,
+// no accumulate, engine-owned weights, parity mode, M >= 4096; the plain form also wants contiguous A rows and no prologue.
 #include <cooperative_groups.h>
 #include <cuda.h>
 
