@@ -81,12 +81,12 @@ def parse():
     ap.add_argument("--concurrent", default="128,192,240,256", help="stream-count ladder of the config-4 leg: the first entry runs on "
                     "every GPU, the rest (N=1 only) are tried in order while p99 stays under the frame period ('' = skip)")
     ap.add_argument("--concurrent-chunks", type=int, default=720, help="chunks per stream of the config-4 leg")
-    ap.add_argument("--stateful", default="256,384,512", help="stream-count ladder of the stateful-encoder leg (N=1 only; '' = skip)")
+    ap.add_argument("--stateful", default="384,512,640,768", help="stream-count ladder of the stateful-encoder leg (N=1 only; '' = skip)")
     ap.add_argument("--stateful-chunks", type=int, default=150, help="chunks per stream of the stateful-encoder leg")
     ap.add_argument("--config5", type=int, default=128, help="streams per GPU of the BASELINE config-5 leg (0 = skip)")
     ap.add_argument("--config5-steps", type=int, default=240, help="two-frame chunks per stream of the config-5 leg")
-    ap.add_argument("--perf", default="128,192,256", help="stream-count ladder of the perf-mode leg, window encoder (N=1 only; '' = skip)")
-    ap.add_argument("--perf-stateful", default="384,512,768", help="the same with the stateful encoder")
+    ap.add_argument("--perf", default="128,256,320", help="stream-count ladder of the perf-mode leg, window encoder (N=1 only; '' = skip)")
+    ap.add_argument("--perf-stateful", default="512,640,768", help="the same with the stateful encoder")
     ap.add_argument("--no-prompt-path", action="store_true", help="skip the setup-path leg (child process, N=1 only)")
     return ap.parse_args()
 
