@@ -23,6 +23,8 @@
 
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -399,6 +401,16 @@ static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t s
   for (int i = count; i < 3; ++i) b.p[i] = ps[0];
   const GemmParams& p = ps[0];
   if (p.M <= 0 || p.N <= 0) return;
+  // the 32-channel HiFi-GAN level at many streams: the pair kernel's conv form (tensor cores, L2-bound) before the CUDA-core kernel
+  static const bool conv32_pair = [] {
+    const char* e = getenv("SVANON_CONV32_PAIR");          // 0: the 32-channel level stays on conv_small at every stream count
+    return !e || atoi(e) != 0;
+  }();
+  if (conv32_pair && g_gemm_use_tc && p.N == 32 && p.M >= 32768 && launch_gemm_pair_taps(ps, count, st)) {
+    *backend = GEMM_BACKEND_TC;
+    SV_LAUNCHED();
+    return;
+  }
   if (g_use_conv_small && launch_conv_small(ps, count, st)) {     // thin causal convs (HiFi-GAN levels with 16/32 channels)
     *backend = GEMM_BACKEND_CONV_SMALL;
     SV_LAUNCHED();

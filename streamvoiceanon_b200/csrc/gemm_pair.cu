@@ -147,8 +147,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
   constexpr int BH = BN / 2;                                  // B rows (output columns) this CTA stages
   constexpr unsigned A_BYTES = PBM * 128u, B_BYTES = BH * 128u;
   constexpr unsigned STAGE_BYTES = 2u * A_BYTES + 2u * B_BYTES;      // A_hi | A_lo | B_hi | B_lo: 64 KB (BN 256) / 48 KB (BN 128)
-  constexpr int STAGES = BN == 256 ? 3 : 4;
-  constexpr int CG = BN / 4;                                  // accumulator columns per epilogue warp
+  constexpr int STAGES = BN == 256 ? 3 : (BN == 32 ? 6 : 4);
+  constexpr int CG = BN >= 64 ? BN / 4 : 16;                  // accumulator columns per epilogue warp (BN = 32: two warp groups idle)
   extern __shared__ unsigned char dsmem_raw[];
   __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
   __shared__ unsigned tmem_holder;
@@ -288,6 +288,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
       const long long r_row = (row_ok && p.residual) ? gemm_r_row(p, m) : 0;
       const int act = p.act;
       const float out_scale = p.out_scale;
+      if (grp * CG >= BN) {
+        // BN = 32: this warp group has no columns; it hands the accumulator back at once
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32p(&acc_empty[acc]), 0)) : "memory");
+        continue;
+      }
       if (args.dual) {
         // accumulator columns: [0,64) = A W^T for output columns 0..63 of the tile, [64,128) = A W2^T for the same columns,
         // [128,192) / [192,256) the same for output columns 64..127 (the peer CTA's B half).  Warp group g owns output
@@ -537,7 +545,7 @@ std::unordered_map<cudaStream_t, ConvScratch>& conv_scratch_registry() {
 
 template <int BN, bool TAPS = false>
 void launch_pair_cfg(const PairArgs& a, cudaStream_t st) {
-  constexpr int STAGES = BN == 256 ? 3 : 4;
+  constexpr int STAGES = BN == 256 ? 3 : (BN == 32 ? 6 : 4);
   constexpr size_t SMEM = (size_t)STAGES * (2 * PBM * 128 + 2 * (BN / 2) * 128) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -721,7 +729,7 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
   }();
   if (!on || pair_mode() == 0 || g_gemm_half || !g_gemm_pair_allowed || count < 1 || count > 3) return false;
   const GemmParams& p0 = ps[0];
-  if (p0.M < min_m || (p0.N % 128 != 0 && p0.N != 64)) return false;
+  if (p0.M < min_m || (p0.N % 128 != 0 && p0.N != 64 && p0.N != 32)) return false;
   const int C = (int)p0.lda;                                   // channels per tap = A row length
   if (C % PK != 0 || C < PK) return false;
   const int seg_rows = p0.seg_rows;
@@ -750,7 +758,7 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
     if (!al16(p.A) || !al16(p.W) || !al16(p.C) || !al16(p.bias) || !al16(p.gamma) || !al16(p.residual)) return false;
   }
   if (!any_taps) return false;                                 // plain GEMMs take the plain path
-  const int BN = (p0.N % 256 == 0) ? 256 : (p0.N % 128 == 0 ? 128 : 64);
+  const int BN = (p0.N % 256 == 0) ? 256 : (p0.N % 128 == 0 ? 128 : p0.N);
   PairArgs a;
   a.count = count;
   a.dual = 0;
@@ -808,7 +816,8 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) a.prob[i].p.prologue = PRO_NONE;  // applied by conv_operand_kernel
   if (BN == 256) launch_pair_cfg<256, true>(a, st);
   else if (BN == 128) launch_pair_cfg<128, true>(a, st);
-  else launch_pair_cfg<64, true>(a, st);                       // 64-channel level: L2-bound (40 KB of operands per 0.28 us slab)
+  else if (BN == 64) launch_pair_cfg<64, true>(a, st);         // 64-channel level: L2-bound (40 KB of operands per 0.28 us slab)
+  else launch_pair_cfg<32, true>(a, st);                       // 32-channel level: L2-bound too, still ~3x the CUDA-core conv kernel
   ++g_gemm_pair_launches;
   return true;
 }
