@@ -518,24 +518,28 @@ CUtensorMap tensor_map_3d(const float* base, int C, int rows, int nseg, int box_
 
 // conv form: the GEMM's A rows with their left context, SiLU applied if the GEMM asks for it (the prologue gemm_tc.cu applies in its
 // producers, once per TAP there), as hi (the value itself) and lo (its TF32 remainder) arrays [nseg][reach + rows][C] compact
-__global__ void conv_operand_kernel(const float* __restrict__ A, long long lda, long long a_seg, int reach, int rows, int C, int silu,
-                                    float* __restrict__ hi, float* __restrict__ lo) {
+struct ConvOperandJob { const float* A; float* hi; float* lo; long long lda, a_seg; int reach, silu; };
+struct ConvOperandArgs { ConvOperandJob job[3]; int rows, C; };
+// (one launch for the up to three distinct inputs of a conv launch: blockIdx.z = input)
+__global__ void conv_operand_kernel(const ConvOperandArgs args) {
   pdl_trigger();
   pdl_wait();
+  const ConvOperandJob& j = args.job[blockIdx.z];
+  const int C = args.C, rows = args.rows, reach = j.reach;
   const int c4 = C >> 2;
   const long long per_seg = (long long)(reach + rows) * c4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_seg) return;
   const int r = (int)(i / c4), c = (int)(i - (long long)r * c4) * 4;
   const long long b = blockIdx.y;
-  float4 v = *reinterpret_cast<const float4*>(A + b * a_seg + (long long)(r - reach) * lda + c);
-  if (silu) {
+  float4 v = *reinterpret_cast<const float4*>(j.A + b * j.a_seg + (long long)(r - reach) * j.lda + c);
+  if (j.silu) {
     v.x = __fdividef(v.x, 1.f + __expf(-v.x)); v.y = __fdividef(v.y, 1.f + __expf(-v.y));
     v.z = __fdividef(v.z, 1.f + __expf(-v.z)); v.w = __fdividef(v.w, 1.f + __expf(-v.w));
   }
   const long long o = (b * (reach + rows) + r) * C + c;
-  *reinterpret_cast<float4*>(hi + o) = v;
-  *reinterpret_cast<float4*>(lo + o) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+  *reinterpret_cast<float4*>(j.hi + o) = v;
+  *reinterpret_cast<float4*>(j.lo + o) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
 }
 struct ConvScratch { Scratch hi[3], lo[3]; };
 std::unordered_map<cudaStream_t, ConvScratch>& conv_scratch_registry() {
@@ -771,6 +775,9 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
   const int rows = seg_rows > 0 ? seg_rows : p0.M;             // rows per segment
   if (seg_rows > 0 && p0.M % seg_rows != 0) return false;
   ConvScratch& cs = conv_scratch_registry()[st];
+  ConvOperandArgs oa;
+  oa.rows = rows; oa.C = C;
+  int n_jobs = 0, max_reach = 0;
   for (int i = 0; i < count; ++i) {
     const GemmParams& p = ps[i];
     PairProblem& pr = a.prob[i];
@@ -805,12 +812,16 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
     float* hi = scratch_floats(cs.hi[i], n, st);
     float* lo = scratch_floats(cs.lo[i], n, st);
     if (!hi || !lo) return false;
-    const long long per_seg = (long long)(reach[i] + rows) * (C / 4);
-    launch_pdl(conv_operand_kernel, dim3((unsigned)((per_seg + 255) / 256), nseg), dim3(256), 0, st, p.A, p.lda,
-               seg_rows > 0 ? p.a_seg : 0LL, reach[i], rows, C, p.prologue == PRO_SILU ? 1 : 0, hi, lo);
-    SV_LAUNCHED();
+    oa.job[n_jobs++] = ConvOperandJob{p.A, hi, lo, p.lda, seg_rows > 0 ? p.a_seg : 0LL, reach[i], p.prologue == PRO_SILU ? 1 : 0};
+    max_reach = std::max(max_reach, reach[i]);
     pr.a_hi = tensor_map_3d(hi, C, reach[i] + rows, nseg, pr.a_box_rows);
     pr.a_lo = tensor_map_3d(lo, C, reach[i] + rows, nseg, pr.a_box_rows);
+  }
+  if (n_jobs > 0) {
+    for (int i = n_jobs; i < 3; ++i) oa.job[i] = oa.job[0];
+    const long long per_seg = (long long)(max_reach + rows) * (C / 4);
+    launch_pdl(conv_operand_kernel, dim3((unsigned)((per_seg + 255) / 256), nseg, n_jobs), dim3(256), 0, st, oa);
+    SV_LAUNCHED();
   }
   for (int i = count; i < 3; ++i) a.prob[i] = a.prob[0];
   for (int i = 0; i < 3; ++i) a.prob[i].p.prologue = PRO_NONE;  // applied by conv_operand_kernel
