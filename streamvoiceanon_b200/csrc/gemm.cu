@@ -406,7 +406,13 @@ static void launch_gemm_dispatch(const GemmParams* ps, int count, cudaStream_t s
     const char* e = getenv("SVANON_CONV32_PAIR");          // 0: the 32-channel level stays on conv_small at every stream count
     return !e || atoi(e) != 0;
   }();
-  if (conv32_pair && g_gemm_use_tc && p.N == 32 && p.M >= 32768 && launch_gemm_pair_taps(ps, count, st)) {
+  static const bool conv16_pair = [] {
+    const char* e = getenv("SVANON_CONV16_PAIR");          // 1: the 16-channel level on the pair kernel too (BN = 16, 64-byte swizzle
+    return e && atoi(e) != 0;                              // rows).  Correct, measured SLOWER than conv_small (V 4.16 vs 3.99 ms at 128
+                                                           // streams, profiles/r2zza_*: 16 KB of A per 128 x 16 x 16 slab): off by default
+  }();
+  if (g_gemm_use_tc && ((conv32_pair && p.N == 32 && p.M >= 32768) || (conv16_pair && p.N == 16 && p.M >= 65536)) &&
+      launch_gemm_pair_taps(ps, count, st)) {
     *backend = GEMM_BACKEND_TC;
     SV_LAUNCHED();
     return;

@@ -98,8 +98,12 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
   return r;
 }
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (same as gemm_tc.cu)
+// ROWB = 128: SWIZZLE_128B tiles (rows of 32 floats, 8-row groups 1024 bytes apart); ROWB = 64: SWIZZLE_64B tiles (rows of 16 floats,
+// 8-row groups 512 bytes apart: the 16-channel convs, whose taps are 16 floats wide)
+template <unsigned ROWB = 128>
 __device__ __forceinline__ unsigned long long pumma_desc(unsigned addr) {
-  return (((unsigned long long)addr & 0x3FFFFull) >> 4) | (1ull << 16) | ((1024ull >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  constexpr unsigned long long layout = ROWB == 128 ? 2ull : 4ull, sbo = 8ull * ROWB;
+  return (((unsigned long long)addr & 0x3FFFFull) >> 4) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 // instruction descriptor: D=f32, A=B=tf32, K-major, N>>3 at [17,23), M>>4 at [24,29) with M = 256 (the pair)
 __device__ __forceinline__ unsigned pumma_idesc(int n) {
@@ -145,9 +149,11 @@ __device__ __forceinline__ void ptmem_ld16(unsigned taddr, float (&v)[16]) {
 template <int BN, bool TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_constant__ PairArgs args) {
   constexpr int BH = BN / 2;                                  // B rows (output columns) this CTA stages
-  constexpr unsigned A_BYTES = PBM * 128u, B_BYTES = BH * 128u;
+  constexpr int KB = BN == 16 ? 16 : PK;                      // floats per K-slab (BN = 16: the 16-channel convs, 64-byte swizzle rows)
+  constexpr unsigned ROWB = KB * 4u;
+  constexpr unsigned A_BYTES = PBM * ROWB, B_BYTES = BH * ROWB;
   constexpr unsigned STAGE_BYTES = 2u * A_BYTES + 2u * B_BYTES;      // A_hi | A_lo | B_hi | B_lo: 64 KB (BN 256) / 48 KB (BN 128)
-  constexpr int STAGES = BN == 256 ? 3 : (BN == 32 ? 6 : 4);
+  constexpr int STAGES = BN == 256 ? 3 : (BN == 32 ? 6 : (BN == 16 ? 8 : 4));
   constexpr int CG = BN >= 64 ? BN / 4 : 16;                  // accumulator columns per epilogue warp (BN = 32: two warp groups idle)
   extern __shared__ unsigned char dsmem_raw[];
   __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
@@ -202,12 +208,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
           if (rank == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local), "r"(2u * STAGE_BYTES) : "memory");
           if constexpr (TAPS) {
-            const int tap = s / pr.spt, kc = (s - tap * pr.spt) * PK;
+            const int tap = s / pr.spt, kc = (s - tap * pr.spt) * KB;
             const int roff = pr.toff[tap];
             int seg = seg0, r_in = r_in0;
             for (int sub = 0; sub < PBM; sub += pr.a_box_rows) {
-              tma_load_3d_pair(dst + (unsigned)sub * 128u, &pr.a_hi, kc, r_in + roff, seg, bar);
-              tma_load_3d_pair(dst + A_BYTES + (unsigned)sub * 128u, &pr.a_lo, kc, r_in + roff, seg, bar);
+              tma_load_3d_pair(dst + (unsigned)sub * ROWB, &pr.a_hi, kc, r_in + roff, seg, bar);
+              tma_load_3d_pair(dst + A_BYTES + (unsigned)sub * ROWB, &pr.a_lo, kc, r_in + roff, seg, bar);
               r_in += pr.a_box_rows;
               if (r_in >= pr.a_seg_rows) { r_in = 0; ++seg; }
             }
@@ -251,10 +257,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) gemm_p
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (pelect_one()) {
             const unsigned a0 = smem_base + stage * STAGE_BYTES;
-            const unsigned long long a_hi = pumma_desc(a0), a_lo = pumma_desc(a0 + A_BYTES);
-            const unsigned long long b_hi = pumma_desc(a0 + 2u * A_BYTES), b_lo = pumma_desc(a0 + 2u * A_BYTES + B_BYTES);
+            const unsigned long long a_hi = pumma_desc<ROWB>(a0), a_lo = pumma_desc<ROWB>(a0 + A_BYTES);
+            const unsigned long long b_hi = pumma_desc<ROWB>(a0 + 2u * A_BYTES), b_lo = pumma_desc<ROWB>(a0 + 2u * A_BYTES + B_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < PK / 8; ++kk) {
+            for (int kk = 0; kk < KB / 8; ++kk) {
               const unsigned long long adv = (unsigned long long)(kk * 32 >> 4);   // 8 tf32 = 32 bytes per K-step
               pumma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, (s > 0 || kk > 0) ? 1u : 0u);
               pumma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
@@ -419,7 +425,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 struct MapKey {
-  const void* ptr; long long rows, ld; int K, box_rows;
+  const void* ptr; long long rows, ld; int K, box_rows;      // box_rows carries the slab width too (+ 1 << 20 for 16-float slabs)
   bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && ld == o.ld && K == o.K && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
@@ -432,19 +438,20 @@ struct MapKeyHash {
   }
 };
 // [rows][K] fp32, row pitch ld floats -> boxes of 32 floats x box_rows rows, 128-byte swizzle, zero fill out of bounds
-const CUtensorMap& tensor_map_2d(const float* base, long long rows, int K, long long ld, int box_rows) {
+const CUtensorMap& tensor_map_2d(const float* base, long long rows, int K, long long ld, int box_rows, int kb = PK) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{base, rows, ld, K, box_rows};
+  const MapKey key{base, rows, ld, K, box_rows + (kb == PK ? 0 : (1 << 20))};
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   if (cache.size() > 4096) cache.clear();
   CUtensorMap m;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)PK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, kb == PK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
   return cache.emplace(key, m).first->second;
@@ -503,14 +510,15 @@ std::unordered_map<cudaStream_t, ScratchSet>& scratch_registry() {      // per s
 }
 
 // [nseg][rows][C] fp32 compact -> boxes of 32 floats x box_rows rows of one segment, 128-byte swizzle, zero fill out of bounds
-CUtensorMap tensor_map_3d(const float* base, int C, int rows, int nseg, int box_rows) {
+CUtensorMap tensor_map_3d(const float* base, int C, int rows, int nseg, int box_rows, int kb = PK) {
   CUtensorMap m;
   const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)nseg};
   const cuuint64_t strides[2] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)rows * C * sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)PK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, kb == PK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed");
   return m;
@@ -549,8 +557,9 @@ std::unordered_map<cudaStream_t, ConvScratch>& conv_scratch_registry() {
 
 template <int BN, bool TAPS = false>
 void launch_pair_cfg(const PairArgs& a, cudaStream_t st) {
-  constexpr int STAGES = BN == 256 ? 3 : (BN == 32 ? 6 : 4);
-  constexpr size_t SMEM = (size_t)STAGES * (2 * PBM * 128 + 2 * (BN / 2) * 128) + 1024;
+  constexpr int STAGES = BN == 256 ? 3 : (BN == 32 ? 6 : (BN == 16 ? 8 : 4));
+  constexpr size_t ROWB = BN == 16 ? 64 : 128;
+  constexpr size_t SMEM = (size_t)STAGES * (2 * PBM * ROWB + 2 * (BN / 2) * ROWB) + 1024;
   static bool configured = false;
   if (!configured) {
     SV_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<BN, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -733,9 +742,10 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
   }();
   if (!on || pair_mode() == 0 || g_gemm_half || !g_gemm_pair_allowed || count < 1 || count > 3) return false;
   const GemmParams& p0 = ps[0];
-  if (p0.M < min_m || (p0.N % 128 != 0 && p0.N != 64 && p0.N != 32)) return false;
+  if (p0.M < min_m || (p0.N % 128 != 0 && p0.N != 64 && p0.N != 32 && p0.N != 16)) return false;
   const int C = (int)p0.lda;                                   // channels per tap = A row length
-  if (C % PK != 0 || C < PK) return false;
+  const int kb = (p0.N == 16) ? 16 : PK;                       // 16 channels: K-slabs of 16 floats (64-byte swizzle rows)
+  if (C % kb != 0 || C < kb || (p0.N == 16 && C != 16)) return false;
   const int seg_rows = p0.seg_rows;
   if (seg_rows > 0 && !(seg_rows % PBM == 0 || (PBM % seg_rows == 0 && seg_rows % 8 == 0))) return false;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -787,13 +797,13 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
     const int w_rows = p.taps > 1 ? ktaps[i] * p.N : p.N, w_cols = p.taps > 1 ? C : ktaps[i] * C;
     const LoCopy* w = weight_lo(p.W, w_rows, w_cols, false, st);
     if (!w) return false;
-    pr.b_hi = tensor_map_2d(p.W, w_rows, w_cols, w_cols, BN / 2);
-    pr.b_lo = tensor_map_2d(w->lo, w_rows, w_cols, w_cols, BN / 2);
+    pr.b_hi = tensor_map_2d(p.W, w_rows, w_cols, w_cols, BN / 2, kb);
+    pr.b_lo = tensor_map_2d(w->lo, w_rows, w_cols, w_cols, BN / 2, kb);
     pr.b2_hi = pr.b_hi;
     pr.b2_lo = pr.b_lo;
     pr.b_row_tap = p.taps > 1 ? p.N : 0;
     pr.b_col_tap = p.taps > 1 ? 0 : C;
-    pr.spt = C / PK;
+    pr.spt = C / kb;
     pr.k_slabs = ktaps[i] * pr.spt;
     pr.a_seg_rows = seg_rows > 0 ? seg_rows : (p0.M + 255) / 256 * 256;
     pr.a_box_rows = std::min(PBM, rows >= PBM ? PBM : rows);
@@ -814,8 +824,8 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
     if (!hi || !lo) return false;
     oa.job[n_jobs++] = ConvOperandJob{p.A, hi, lo, p.lda, seg_rows > 0 ? p.a_seg : 0LL, reach[i], p.prologue == PRO_SILU ? 1 : 0};
     max_reach = std::max(max_reach, reach[i]);
-    pr.a_hi = tensor_map_3d(hi, C, reach[i] + rows, nseg, pr.a_box_rows);
-    pr.a_lo = tensor_map_3d(lo, C, reach[i] + rows, nseg, pr.a_box_rows);
+    pr.a_hi = tensor_map_3d(hi, C, reach[i] + rows, nseg, pr.a_box_rows, kb);
+    pr.a_lo = tensor_map_3d(lo, C, reach[i] + rows, nseg, pr.a_box_rows, kb);
   }
   if (n_jobs > 0) {
     for (int i = n_jobs; i < 3; ++i) oa.job[i] = oa.job[0];
@@ -828,7 +838,8 @@ bool launch_gemm_pair_taps(const GemmParams* ps, int count, cudaStream_t st) {
   if (BN == 256) launch_pair_cfg<256, true>(a, st);
   else if (BN == 128) launch_pair_cfg<128, true>(a, st);
   else if (BN == 64) launch_pair_cfg<64, true>(a, st);         // 64-channel level: L2-bound (40 KB of operands per 0.28 us slab)
-  else launch_pair_cfg<32, true>(a, st);                       // 32-channel level: L2-bound too, still ~3x the CUDA-core conv kernel
+  else if (BN == 32) launch_pair_cfg<32, true>(a, st);         // 32-channel level: L2-bound too, still ~3x the CUDA-core conv kernel
+  else launch_pair_cfg<16, true>(a, st);                       // 16-channel level: 64-byte swizzle rows, K-slabs of one tap
   ++g_gemm_pair_launches;
   return true;
 }

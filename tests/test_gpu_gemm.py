@@ -220,7 +220,7 @@ def test_pair_gemm_fused_epilogues(form):
 
 @pytest.mark.parametrize("M,N,C,offs,k1", [(12544, 128, 128, (-10, -5, 0), 0), (12500, 256, 256, (-30, -25, -20, -15, -10, -5, 0), 0),
                                            (12544, 256, 256, (-2,), 3), (12544, 128, 64, (-6,), 7), (16384, 64, 64, (-20, -10, 0), 0), (16384, 32, 32, (-10, -5, 0), 0),
-                                           (16384, 32, 32, (-6,), 7)])
+                                           (16384, 32, 32, (-6,), 7), (16384, 16, 16, (-10, -5, 0), 0), (16384, 16, 16, (-10,), 11)])
 def test_pair_gemm_taps_bitwise(M, N, C, offs, k1):
     """The conv form of the pair kernel (causal convs as GEMMs over taps: 3-D tensor maps over the input rows with their left
     context, tap t at row offset tap_off[t]; k1 > 0: the dilation-1 form, one "tap" of k1 overlapping rows) against the single-CTA
