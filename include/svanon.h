@@ -377,6 +377,12 @@ int svanon_batch_set_ar_path(svanon_batch* b, int path);
  * chunk on all of them share one pass over the weights.  Every stream keeps producing exactly what it produces alone.
  * `a` and `b` are left without members: destroy them.  wave_chunks / wave_out rows of the merged batch: a's streams, then b's. */
 int svanon_batch_merge(svanon_batch* a, svanon_batch* b, svanon_batch** out, void* cuda_stream);
+/* The members keep[0 .. n_keep) of `a` (indices into a's member order, strictly increasing) as a new lock-step batch, each with
+ * the state it had (the moves of svanon_batch_merge, gathered per member): what a server calls once streams of a cohort have
+ * left, so that the following chunks compute for the remaining streams only.  `a` must be past its warm-up chunks and is left
+ * without members: destroy it.  The streams left out are plain streams again (the caller owns them).  No reference
+ * counterpart (the reference is one stream per process, evaluations/infer_arvc.py:56). */
+int svanon_batch_select(svanon_batch* a, const int* keep, int n_keep, svanon_batch** out, void* cuda_stream);
 int svanon_batch_set_encoder_mode(svanon_batch* b, int incremental);   /* as svanon_stream_set_encoder_mode */
 /* per-stage device time of the last non-warm-up chunk, as svanon_stream_last_timing */
 int svanon_batch_set_timing(svanon_batch* b, int enable);

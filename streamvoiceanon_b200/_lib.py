@@ -89,6 +89,7 @@ _SIGS = {
     "svanon_batch_process_chunk": (C.c_int, [_p, _p, C.c_int, _p, _p, _p]),
     "svanon_batch_set_ar_path": (C.c_int, [_p, C.c_int]),
     "svanon_batch_merge": (C.c_int, [_p, _p, C.POINTER(_p), _p]),
+    "svanon_batch_select": (C.c_int, [_p, C.POINTER(C.c_int), C.c_int, C.POINTER(_p), _p]),
     "svanon_batch_set_timing": (C.c_int, [_p, C.c_int]),
     "svanon_batch_last_timing": (C.c_int, [_p, C.POINTER(C.c_float)]),
     "svanon_enc_stream_create": (C.c_int, [_p, C.c_int, C.POINTER(_p)]),

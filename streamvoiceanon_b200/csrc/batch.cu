@@ -9,6 +9,8 @@
 // stream produces exactly what it would produce alone (tests/test_gpu_batch.py).
 #include "api_common.hpp"
 
+#include <climits>
+
 struct svanon_batch {
   svanon_engine* owner = nullptr;
   std::vector<svanon_stream*> streams;
@@ -491,6 +493,112 @@ int svanon_batch_merge(svanon_batch* a, svanon_batch* b, svanon_batch** out, voi
     }
     a->streams.clear(); a->enc_win = 0;
     b->streams.clear(); b->enc_win = 0;
+    *out = guard.release();
+  });
+}
+
+// The members keep[0 .. n_keep) of `a` (indices into a's member order, strictly increasing) as a batch of their own, each with
+// the state it had: what a server does when streams of a cohort have left, so that the steps afterwards compute for the
+// remaining streams only.  Same state moves as svanon_batch_merge, gathered per member instead of concatenated; the rings of
+// steady-state layer inputs (ConvStackRings) start empty in the new batch, as after a merge.  `a` is left without members
+// (destroy it); the streams that were left out are plain streams again.
+int svanon_batch_select(svanon_batch* a, const int* keep, int n_keep, svanon_batch** out, void* stream) {
+  return guarded([&] {
+    SV_CHECK(a && keep && out && n_keep >= 1, "bad arguments");
+    SV_CHECK(a->enc_win > 0, "svanon_batch_setup has not been called");
+    const int na = (int)a->streams.size(), n = n_keep;
+    SV_CHECK(n <= na, "more members to keep than the batch has");
+    for (int i = 0; i < n; ++i)
+      SV_CHECK(keep[i] >= 0 && keep[i] < na && (i == 0 || keep[i] > keep[i - 1]), "keep: strictly increasing member indices");
+    SV_CHECK(a->voc_fed > 0 && (a->delay == 0 || a->delay_prefilled),
+             "the batch must be past its warm-up chunks (delay prefilled, first frame decoded)");
+    Engine& e = a->owner->eng;
+    SV_CUDA(cudaSetDevice(e.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    auto* c = new svanon_batch();
+    std::unique_ptr<svanon_batch> guard(c);
+    c->owner = a->owner;
+    for (int i = 0; i < n; ++i) c->streams.push_back(a->streams[keep[i]]);
+    c->enc_win = a->enc_win; c->dec_win = a->dec_win; c->max_seq_frames = a->max_seq_frames; c->buffer_frames = a->buffer_frames;
+    c->chunk = a->chunk; c->delay = a->delay; c->ar_path = a->ar_path;
+    c->n_src = a->n_src; c->n_pred = a->n_pred; c->voc_fed = a->voc_fed; c->delay_prefilled = true;
+    int lo_src = INT_MAX, lo_pred = INT_MAX;          // count like the kept member that is furthest behind
+    for (int i = 0; i < n; ++i) { lo_src = std::min(lo_src, a->src_off[keep[i]]); lo_pred = std::min(lo_pred, a->pred_off[keep[i]]); }
+    c->n_src += lo_src; c->n_pred += lo_pred;
+    for (int i = 0; i < n; ++i) {
+      c->src_off.push_back(a->src_off[keep[i]] - lo_src);
+      c->pred_off.push_back(a->pred_off[keep[i]] - lo_pred);
+    }
+    const size_t nw = (size_t)c->enc_win * SAMPLES_PER_FRAME;
+    c->wave_ring = dmalloc<float>(nw * n);
+    c->wave_ring_tmp = dmalloc<float>(nw * n);
+    c->ids_win = dmalloc<long long>((size_t)c->enc_win * n);
+    c->codes_win = dmalloc<long long>((size_t)8 * c->chunk * n);
+    c->step_ids = dmalloc<long long>((size_t)c->chunk * n);
+    auto take = [&](float* dst, const float* src, size_t per) {      // dst [n][per] <- rows keep[] of src; runs travel in one copy
+      for (int i = 0; i < n;) {
+        int j = i + 1;
+        while (j < n && keep[j] == keep[j - 1] + 1) ++j;
+        SV_CUDA(cudaMemcpyAsync(dst + per * i, src + per * keep[i], per * (size_t)(j - i) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        i = j;
+      }
+    };
+    take(c->wave_ring, a->wave_ring, nw);
+    // ---- encoder state
+    c->enc_stateful = a->enc_stateful;
+    c->enc_state.enabled = a->enc_state.enabled;
+    c->enc_state.tail_hist_min_streams = a->enc_state.tail_hist_min_streams;
+    const int dims[4] = {128, 256, 384, 512}, depths[4] = {3, 3, 9, 3};
+    auto take_hist = [&](ConvStackHist& hc, ConvStackHist& ha) {
+      take(hc.mel, ha.mel, (size_t)6 * N_MELS);
+      int j = 0;
+      for (int s4 = 0; s4 < 4; ++s4)
+        for (int d = 0; d < depths[s4]; ++d, ++j) take(hc.blk[j], ha.blk[j], (size_t)6 * dims[s4]);
+      for (int d = 0; d < 2; ++d, ++j) take(hc.blk[j], ha.blk[j], (size_t)6 * 512);
+    };
+    if (c->enc_stateful) {
+      SV_CHECK(a->enc_stream.wave && a->enc_stream.pos > 0 && a->enc_stream.B == na, "stateful encoder state missing");
+      e.enc_stream_init(c->enc_stream, n);
+      EncStream &ea = a->enc_stream, &ec = c->enc_stream;
+      take(ec.wave, ea.wave, ENC_STREAM_WAVE);
+      const size_t per_kv = (size_t)ENC_HEADS * ENC_RING * HEAD_DIM;
+      for (int l = 0; l < ENC_LAYERS; ++l) {
+        take(ec.kc + (size_t)l * n * per_kv, ea.kc + (size_t)l * na * per_kv, per_kv);
+        take(ec.vc + (size_t)l * n * per_kv, ea.vc + (size_t)l * na * per_kv, per_kv);
+      }
+      ec.pos = ea.pos;
+      for (int i = 0; i < n; ++i) ec.off[i] = ea.off[keep[i]];
+      SV_CUDA(cudaMemcpyAsync(ec.off_dev, ec.off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, st));
+      take_hist(ec.hist, ea.hist);
+    } else if (a->enc_state.valid && a->enc_state.B == na) {
+      EncWindowState &sa = a->enc_state, &sc = c->enc_state;
+      const int S = sa.S;
+      for (auto& p : sc.xt) SV_CUDA(cudaMalloc(&p, (size_t)n * S * ENC_DIM * sizeof(float)));
+      sc.B = n; sc.S = S; sc.cur = 0; sc.valid = true;
+      take(sc.xt[0], sa.xt[sa.cur], (size_t)S * ENC_DIM);
+      // fewer members than the conv-history mode wants: the next step runs the tail span instead, the history is not needed
+      sc.hist_valid = sa.hist_valid && sa.hist.B == na && sc.tail_hist_min_streams > 0 && n >= sc.tail_hist_min_streams;
+      if (sc.hist_valid) {
+        sc.hist.alloc(n);
+        take_hist(sc.hist, sa.hist);
+      }
+    } else {
+      c->enc_state.valid = false;                      // the next step re-encodes the whole window once (same ids)
+    }
+    // ---- vocoder histories
+    e.voc_state_init(c->voc, c->chunk, n);
+    voc_state_select(c->voc, a->voc, keep, n, st);
+    if (a->timing) {
+      for (auto& ev : c->ev) SV_CUDA(cudaEventCreate(&ev));
+      c->timing = true;
+    }
+    upload_slot_table(c, st);                         // synchronises: the copies above are complete
+    for (int i = 0; i < n; ++i) {
+      Stream& s = c->streams[i]->st;
+      s.n_src = c->n_src + c->src_off[i];
+      s.n_pred = c->n_pred + c->pred_off[i];
+    }
+    a->streams.clear(); a->enc_win = 0;
     *out = guard.release();
   });
 }

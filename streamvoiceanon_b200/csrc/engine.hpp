@@ -218,6 +218,7 @@ struct EncStream {
 
 std::vector<SBuf*> voc_state_bufs(VocState& vs);                                        // voc_stream.cu
 void voc_state_concat(VocState& dst, VocState& a, VocState& b, cudaStream_t st);       // dst <- a's streams, then b's
+void voc_state_select(VocState& dst, VocState& a, const int* keep, int n, cudaStream_t st);   // dst <- a's streams keep[]
 
 constexpr int HIST_CAP = 4096;     // columns kept of src_content_codes / pred_codes (the reference trims to 2048)
 

@@ -128,6 +128,24 @@ void voc_state_concat(VocState& dst, VocState& a, VocState& b, cudaStream_t st) 
   dst.primed_frames = std::min(a.primed_frames, b.primed_frames);
 }
 
+// dst (B = n streams) <- the histories of a's streams keep[0 .. n) (strictly increasing); runs of neighbours travel in one copy
+void voc_state_select(VocState& dst, VocState& a, const int* keep, int n, cudaStream_t st) {
+  SV_CHECK(dst.c == a.c && dst.B == n && n <= a.B, "vocoder states do not match");
+  auto bd = voc_state_bufs(dst), ba = voc_state_bufs(a);
+  for (size_t i = 0; i < bd.size(); ++i) {
+    SV_CHECK(bd[i]->seg == ba[i]->seg, "vocoder state layouts differ");
+    const size_t seg = (size_t)ba[i]->seg;
+    for (int k = 0; k < n;) {
+      int j = k + 1;
+      while (j < n && keep[j] == keep[j - 1] + 1) ++j;
+      SV_CUDA(cudaMemcpyAsync(bd[i]->base + seg * k, ba[i]->base + seg * keep[k], seg * (size_t)(j - k) * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+      k = j;
+    }
+  }
+  dst.primed_frames = a.primed_frames;
+}
+
 void Engine::voc_state_reset(VocState& vs, cudaStream_t st) {
   if (vs.arena) SV_CUDA(cudaMemsetAsync(vs.arena, 0, vs.arena_floats * sizeof(float), st));
   vs.primed_frames = 0;

@@ -9,7 +9,9 @@ every `step` advances all cohorts, one library call each.  Once a cohort has lef
 older cohort of the same delay (`BatchSession.merged` / svanon_batch_merge: every member's wave ring, encoder and vocoder
 state moves into side-by-side buffers), so that in steady state the pool is back to one pass over the weights per chunk
 however the streams arrived.  A stream that leaves stays in its cohort as a silent member (the batch-level encoder /
-vocoder state is laid out per member) until the cohort is empty, then the cohort is closed.
+vocoder state is laid out per member) until the cohort is empty, then the cohort is closed -- or until the silent members
+are `compact_fraction` of a warm cohort: then the live members continue as a batch of their own
+(`BatchSession.selected` / svanon_batch_select), so a long-running server computes for the streams it has.
 Each stream produces exactly what it produces alone (the `BatchSession` contract, tests/test_gpu_batch.py).
 
 The reference is one stream per process (`max_batch_size=1`, infer_arvc.py:56); its GUI loop
@@ -45,7 +47,7 @@ class StreamPool:
 
     def __init__(self, encode_window_frames: int = 128, decode_window_frames: int = 64, max_seq_frames: int = 768,
                  buffer_frames: int = 32, decode_chunk_frames: int = 1, max_cohort: int = 256,
-                 batch_factory: Optional[Callable] = None, merge_cohorts: bool = True):
+                 batch_factory: Optional[Callable] = None, merge_cohorts: bool = True, compact_fraction: float = 0.25):
         if decode_chunk_frames < 1 or max_cohort < 1:
             raise ValueError("decode_chunk_frames and max_cohort must be >= 1")
         self._cfg = dict(encode_window_frames=encode_window_frames, decode_window_frames=decode_window_frames,
@@ -58,6 +60,8 @@ class StreamPool:
         self._batch_factory = batch_factory
         self._merge = merge_cohorts and hasattr(batch_factory, "merged")
         self.merges = 0
+        self._compact_fraction = float(compact_fraction) if hasattr(batch_factory, "selected") else 0.0
+        self.compactions = 0
         self._pending: Dict[Hashable, object] = {}          # key -> session, joined since the last step
         self._cohorts: List[_Cohort] = []
         self._where: Dict[Hashable, tuple] = {}             # key -> (cohort, index)
@@ -75,8 +79,8 @@ class StreamPool:
         self.underruns[key] = 0
 
     def remove(self, key: Hashable) -> None:
-        """The stream stops producing output; its session is NOT closed (the caller owns it) but must stay alive until its
-        cohort is gone (`cohort_of(key) is None` after a later `step`, or `close()`)."""
+        """The stream stops producing output; its session is NOT closed (the caller owns it) but must stay alive while a
+        cohort still advances it as a silent member (`in_use(session)`; False at the latest after `close()`)."""
         if key in self._pending:
             del self._pending[key]
             del self.underruns[key]
@@ -88,6 +92,10 @@ class StreamPool:
         del self.underruns[key]
         if not any(cohort.live):
             self._retire(cohort)
+
+    def in_use(self, session) -> bool:
+        """True while a cohort's batch still holds `session` (as a live or a silent member)."""
+        return any(session is s for c in self._cohorts for s in c.sessions) or any(session is s for s in self._pending.values())
 
     def __contains__(self, key):
         return key in self._pending or key in self._where
@@ -153,12 +161,30 @@ class StreamPool:
             self._cohorts.remove(cohort)
             self.merges += 1
 
+    def _compact_cohorts(self) -> None:
+        """A warm cohort whose silent members have reached `compact_fraction` of its size continues with its live members only."""
+        if self._compact_fraction <= 0:
+            return
+        for cohort in self._cohorts:
+            dead = cohort.live.count(False)
+            if dead == 0 or dead == len(cohort.live) or dead < self._compact_fraction * len(cohort.live) or not self._warm(cohort):
+                continue
+            keep = [i for i, live in enumerate(cohort.live) if live]
+            cohort.batch = self._batch_factory.selected(cohort.batch, keep)
+            cohort.keys = [cohort.keys[i] for i in keep]
+            cohort.sessions = [cohort.sessions[i] for i in keep]
+            cohort.live = [True] * len(keep)
+            for i, k in enumerate(cohort.keys):
+                self._where[k] = (cohort, i)
+            self.compactions += 1
+
     # ------------------------------------------------------------------------------------------ the loop
     def step(self, chunks: Dict[Hashable, torch.Tensor]) -> Dict[Hashable, torch.Tensor]:
         """One chunk period for every stream of the pool."""
         for key in chunks:
             if key not in self:
                 raise KeyError(f"chunk for unknown stream {key!r}")
+        self._compact_cohorts()
         if self._merge:
             self._merge_warm_cohorts()
         self._admit()

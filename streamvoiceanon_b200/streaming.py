@@ -180,6 +180,21 @@ class BatchSession:
         b.close()
         return m
 
+    @classmethod
+    def selected(cls, a: "BatchSession", keep) -> "BatchSession":
+        """The members `keep` (indices into a.sessions, strictly increasing) of a batch that is past its warm-up chunks as a
+        batch of their own, every stream with the state it had (svanon_batch_select): the batch a server continues with
+        after streams have left.  `a` is closed; the sessions left out stay open (the caller owns them)."""
+        keep = [int(k) for k in keep]
+        arr = (C.c_int * len(keep))(*keep)
+        h = C.c_void_p()
+        _lib.check(a._engine.lib.svanon_batch_select(a._h, arr, len(keep), C.byref(h), C.c_void_p(_cuda_stream_ptr())))
+        m = cls.__new__(cls)
+        m.sessions = [a.sessions[k] for k in keep]
+        m._engine, m._h, m.chunk = a._engine, h, a.chunk
+        a.close()
+        return m
+
     def set_ar_path(self, path: int):
         """0: persistent kernel for 1/2/4 streams, many-stream kernels otherwise; 1: always the many-stream kernels."""
         _lib.check(self._engine.lib.svanon_batch_set_ar_path(self._h, path))

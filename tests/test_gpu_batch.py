@@ -292,6 +292,112 @@ def test_stream_pool_merge_then_long_run(models, tape):
         s.close()
 
 
+@pytest.mark.parametrize("enc_mode", [1, 3])
+def test_stream_pool_drops_streams_that_left(models, tape, enc_mode):
+    """Compaction (svanon_batch_select): streams 0-2 arrive at chunk 0, stream 3 three chunks later (merged into the first
+    cohort once warm, so its history offsets are non-zero); stream 1 leaves after 8 chunks and stream 0 after 10.  Each time the
+    silent members reach a quarter of the cohort it continues with the live members only -- members [0, 2, 3], then [2, 3], at
+    the end [3] alone: wave
+    rings, encoder state (enc_mode 3: stateful K/V rings and positions), vocoder histories and history columns gathered per
+    member.  Every stream equals the stream alone for as long as it ran: ids bit-exact, waveform to fp32 rounding."""
+    from streamvoiceanon_b200 import BatchSession
+    from streamvoiceanon_b200.server import StreamPool
+    _, tok, _ = models
+    n_chunks, delay = 16, 2
+    cfg = dict(encode_window_frames=24, decode_window_frames=24, max_seq_frames=52, buffer_frames=6, decode_chunk_frames=1)
+    inputs = [_stream_inputs(tok, b, 26 + 5 * b, n_chunks, 1) for b in range(4)]
+    join = {0: 0, 1: 0, 2: 0, 3: 3}
+    runs = {0: 10, 1: 8, 2: n_chunks, 3: n_chunks}
+    singles = []
+    for b, inp in enumerate(inputs):
+        sess = _session(inp, tape(7480 + b), delay)
+        sess.set_encoder_mode(enc_mode)
+        sess.setup(**cfg)
+        waves = torch.cat([sess.process_chunk(inp[4][i].cuda()).cpu() for i in range(runs[b])])
+        singles.append((*sess.history(), waves))
+        sess.close()
+    sessions = [_session(inp, tape(7480 + b), delay) for b, inp in enumerate(inputs)]
+
+    class ModeBatch(BatchSession):
+        def setup(self, **kw):
+            self.set_encoder_mode(enc_mode)
+            super().setup(**kw)
+    pool = StreamPool(batch_factory=ModeBatch, compact_fraction=0.25, **cfg)
+    got = {b: [] for b in range(4)}
+    sizes = []
+    for step in range(n_chunks + 3):
+        for b, at in join.items():
+            if at == step:
+                pool.add(b, sessions[b])
+        for b in range(4):
+            if b in pool and step - join[b] == runs[b]:
+                pool.remove(b)
+        chunks = {b: inputs[b][4][step - join[b]].cuda() for b in range(4) if b in pool}
+        for b, w in pool.step(chunks).items():
+            got[b].append(w.cpu())
+        sizes.append(pool.cohort_sizes())
+    # merged at chunk 7; compacted when stream 1, stream 0 and (after its 16 chunks) stream 2 had left: stream 3 ends alone
+    assert pool.merges == 1 and pool.compactions == 3 and all(z in sizes for z in ([3, 1], [4], [3], [2])) and sizes[-1] == [1], sizes
+    assert not any(pool.in_use(sessions[b]) for b in (0, 1, 2)) and pool.in_use(sessions[3])
+    for b, sess in enumerate(sessions):
+        src_hist, pred_hist = sess.history()
+        assert torch.equal(src_hist[: singles[b][0].numel()], singles[b][0]), b
+        assert torch.equal(pred_hist[:, : singles[b][1].shape[1]], singles[b][1]), b
+        assert len(got[b]) == runs[b]
+        mse = float(((torch.cat(got[b]) - singles[b][2]) ** 2).mean())
+        assert mse < 1e-10, (b, mse)
+    pool.close()
+    for s in sessions:
+        s.close()
+
+
+@pytest.mark.parametrize("n,leave,n_chunks", [(10, 3, 40), (12, 4, 160)])
+def test_stream_pool_compaction_default_windows(models, tape, n, leave, n_chunks):
+    """Compaction with the CLI-default windows, where the cohort carries encoder window state: n streams from chunk 0, `leave`
+    of them (every third member) gone after 12 chunks.  10 -> 7 members: the per-layer conv history mode (>= 8 streams) hands
+    over to the tail-span mode on the gathered transformer inputs; 12 -> 8: the conv history itself is gathered and the rings
+    of steady-state layer inputs start again empty and serve the window-start pass once they cover the window (chunk ~140 of
+    160).  Two remaining streams against the same streams alone: ids bit-exact."""
+    from streamvoiceanon_b200 import BatchSession
+    from streamvoiceanon_b200.server import StreamPool
+    _, tok, _ = models
+    gone_at, delay = 12, 2
+    cfg = dict(encode_window_frames=128, decode_window_frames=64, max_seq_frames=768, buffer_frames=32, decode_chunk_frames=1)
+
+    def inputs_of(b):
+        ref_content, ref_audio, style, timbre, _ = _stream_inputs(tok, 60 + b, 64 + b, 4, 1)
+        src = synth.synth_audio_44k(1900 + b, 8.0)[: n_chunks * 2048].view(n_chunks, 2048)
+        return ref_content, ref_audio, style, timbre, src
+    inputs = [inputs_of(b) for b in range(n)]
+    leaving = [3 * i for i in range(leave)]                      # members 0, 3, 6(, 9): the rest is gathered in runs of two
+    check = (1, n - 1)
+    singles = {}
+    for b in check:
+        sess = _session(inputs[b], tape(6700 + b), delay)
+        sess.setup(**cfg)
+        for i in range(n_chunks):
+            sess.process_chunk(inputs[b][4][i].cuda())
+        singles[b] = sess.history()
+        sess.close()
+    sessions = [_session(inp, tape(6700 + b), delay) for b, inp in enumerate(inputs)]
+    pool = StreamPool(batch_factory=BatchSession, compact_fraction=0.25, **cfg)
+    for b in range(n):
+        pool.add(b, sessions[b])
+    for step in range(n_chunks):
+        if step == gone_at:
+            for b in leaving:
+                pool.remove(b)
+        pool.step({b: inputs[b][4][step].cuda() for b in range(n) if b in pool})
+    assert pool.compactions == 1 and pool.cohort_sizes() == [n - leave]
+    for b in check:
+        src_hist, pred_hist = sessions[b].history()
+        assert torch.equal(src_hist[: singles[b][0].numel()], singles[b][0]), b
+        assert torch.equal(pred_hist[:, : singles[b][1].shape[1]], singles[b][1]), b
+    pool.close()
+    for s in sessions:
+        s.close()
+
+
 @pytest.mark.parametrize("enc_mode", [1, 2])
 def test_batch_loop_vs_reference_fixture(models, gold, tape, enc_mode):
     """Stream 0 of a 2-stream batch (many-stream decode kernels forced) reproduces the UNMODIFIED reference's

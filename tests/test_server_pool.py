@@ -140,3 +140,53 @@ def test_warm_cohorts_merge_and_keep_their_members_state():
     assert set(out) == {"b", "c"} and pool.cohort_sizes() == [3]
     assert float(out["b"][0]) == 2.0 + 8 and float(out["c"][0]) == 3.0 + 7
     pool.close()
+
+
+class FakeSelectBatch(FakeMergeBatch):
+    """... and can continue with a subset of its members."""
+
+    @classmethod
+    def selected(cls, a, keep):
+        assert list(keep) == sorted(set(keep)) and all(0 <= k < len(a.sessions) for k in keep)
+        m = cls([a.sessions[k] for k in keep])
+        m.cfg, m.counts = a.cfg, [a.counts[k] for k in keep]
+        a.close()
+        return m
+
+
+def test_silent_members_are_dropped_from_warm_cohorts():
+    """Compaction: once the streams that have left are `compact_fraction` of a warm cohort, the cohort continues with its
+    live members only (BatchSession.selected); every remaining stream keeps its state and its key -> row mapping."""
+    FakeBatch.log = []
+    pool = StreamPool(decode_chunk_frames=1, batch_factory=FakeSelectBatch, compact_fraction=0.5)
+    sessions = {k: FakeSession(g) for k, g in zip("abcd", (1.0, 2.0, 3.0, 4.0))}
+    for k, s in sessions.items():
+        pool.add(k, s)
+    pool.step({k: _chunk(0) for k in "abcd"})
+    pool.remove("b")                                                               # cohort not warm yet: b stays a silent member
+    pool.step({k: _chunk(0) for k in "acd"})
+    assert pool.cohort_sizes() == [4] and pool.compactions == 0
+    for _ in range(3):
+        pool.step({k: _chunk(0) for k in "acd"})
+    assert pool.cohort_sizes() == [4] and pool.compactions == 0                    # warm, but 1 of 4 is below the fraction
+    assert pool.in_use(sessions["b"])
+    pool.remove("d")
+    out = pool.step({"a": _chunk(1), "c": _chunk(1)})                              # 2 of 4 silent: compacted before this step
+    assert pool.cohort_sizes() == [2] and pool.compactions == 1 and len(FakeBatch.log) == 2 and FakeBatch.log[0].closed
+    assert float(out["a"][0]) == 1.0 + 6 and float(out["c"][0]) == 3.0 + 6         # counts carried over
+    assert not pool.in_use(sessions["b"]) and not pool.in_use(sessions["d"]) and pool.in_use(sessions["c"])
+    pool.remove("a")
+    out = pool.step({"c": _chunk(2)})                                              # 1 of 2: compacted again, c is row 0 now
+    assert pool.cohort_sizes() == [1] and pool.compactions == 2 and float(out["c"][0]) == 6.0 + 7
+    pool.remove("c")
+    assert pool.n_cohorts == 0 and all(b.closed for b in FakeBatch.log)
+    # a factory without `selected` (or compact_fraction = 0) keeps the silent members, as before
+    pool = StreamPool(decode_chunk_frames=1, batch_factory=FakeSelectBatch, compact_fraction=0.0)
+    for k in "ab":
+        pool.add(k, FakeSession(1.0))
+    for _ in range(5):
+        pool.step({})
+    pool.remove("a")
+    pool.step({"b": _chunk(0)})
+    assert pool.cohort_sizes() == [2] and pool.compactions == 0
+    pool.close()
