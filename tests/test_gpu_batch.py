@@ -351,6 +351,33 @@ def test_stream_pool_drops_streams_that_left(models, tape, enc_mode):
         s.close()
 
 
+def test_batch_select_argument_errors(models, tape):
+    """svanon_batch_select refuses a batch that is still in its warm-up chunks and member lists that are not strictly
+    increasing indices; the batch stays usable after a refused call."""
+    from streamvoiceanon_b200 import BatchSession
+    _, tok, _ = models
+    cfg = dict(encode_window_frames=24, decode_window_frames=24, max_seq_frames=52, buffer_frames=6, decode_chunk_frames=1)
+    inputs = [_stream_inputs(tok, b, 26 + 5 * b, 6, 1) for b in range(2)]
+    sessions = [_session(inp, tape(7490 + b), 2) for b, inp in enumerate(inputs)]
+    batch = BatchSession(sessions)
+    batch.setup(**cfg)
+    waves = lambda i: torch.stack([inp[4][i] for inp in inputs]).cuda()
+    batch.process_chunk(waves(0))
+    with pytest.raises(RuntimeError, match="warm-up"):
+        BatchSession.selected(batch, [0])
+    for i in range(1, 5):
+        batch.process_chunk(waves(i))
+    for bad in ([1, 0], [0, 0], [2], [-1], []):
+        with pytest.raises(RuntimeError):
+            BatchSession.selected(batch, bad)
+    one = BatchSession.selected(batch, [1])
+    assert len(one.sessions) == 1 and one.sessions[0] is sessions[1] and batch._h is None
+    assert one.process_chunk(inputs[1][4][5][None].cuda()).shape == (1, 2048)
+    one.close()
+    for s in sessions:
+        s.close()
+
+
 @pytest.mark.parametrize("n,leave,n_chunks", [(10, 3, 40), (12, 4, 160)])
 def test_stream_pool_compaction_default_windows(models, tape, n, leave, n_chunks):
     """Compaction with the CLI-default windows, where the cohort carries encoder window state: n streams from chunk 0, `leave`
