@@ -380,8 +380,9 @@ int svanon_batch_merge(svanon_batch* a, svanon_batch* b, svanon_batch** out, voi
 /* The members keep[0 .. n_keep) of `a` (indices into a's member order, strictly increasing) as a new lock-step batch, each with
  * the state it had (the moves of svanon_batch_merge, gathered per member): what a server calls once streams of a cohort have
  * left, so that the following chunks compute for the remaining streams only.  `a` must be past its warm-up chunks and is left
- * without members: destroy it.  The streams left out are plain streams again (the caller owns them).  No reference
- * counterpart (the reference is one stream per process, evaluations/infer_arvc.py:56). */
+ * without members: destroy it.  The streams left out are no longer advanced by any batch; the caller owns them (destroy
+ * them, or give them a new prompt and set them up again before further use).  No reference counterpart (the reference is
+ * one stream per process, evaluations/infer_arvc.py:56). */
 int svanon_batch_select(svanon_batch* a, const int* keep, int n_keep, svanon_batch** out, void* cuda_stream);
 int svanon_batch_set_encoder_mode(svanon_batch* b, int incremental);   /* as svanon_stream_set_encoder_mode */
 /* per-stage device time of the last non-warm-up chunk, as svanon_stream_last_timing */

@@ -501,7 +501,8 @@ int svanon_batch_merge(svanon_batch* a, svanon_batch* b, svanon_batch** out, voi
 // the state it had: what a server does when streams of a cohort have left, so that the steps afterwards compute for the
 // remaining streams only.  Same state moves as svanon_batch_merge, gathered per member instead of concatenated; the rings of
 // steady-state layer inputs (ConvStackRings) start empty in the new batch, as after a merge.  `a` is left without members
-// (destroy it); the streams that were left out are plain streams again.
+// (destroy it); the streams that were left out belong to no batch any more (their batch-level state -- wave ring, encoder and
+// vocoder state -- is gone with `a`).
 int svanon_batch_select(svanon_batch* a, const int* keep, int n_keep, svanon_batch** out, void* stream) {
   return guarded([&] {
     SV_CHECK(a && keep && out && n_keep >= 1, "bad arguments");
